@@ -1,0 +1,56 @@
+// Shared host-side helpers: error propagation (every C-ABI call returns int, 0 = ok) and launch checks.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <stdexcept>
+#include <string>
+
+namespace rlrep {
+
+constexpr int kNumSMs = 148;  // B200: 2 dies x 74 SMs
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+void set_last_error(const std::string& msg);
+const char* get_last_error();
+
+#define RLREP_CUDA(expr)                                                                              \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess) {                                                                          \
+      throw ::rlrep::Error(std::string(#expr) + " failed: " + cudaGetErrorString(_e) + " (" __FILE__ \
+                           ":" + std::to_string(__LINE__) + ")");                                     \
+    }                                                                                                 \
+  } while (0)
+
+#define RLREP_CHECK(cond, msg)                                                                           \
+  do {                                                                                                   \
+    if (!(cond)) {                                                                                       \
+      throw ::rlrep::Error(std::string("check failed: " #cond " -- ") + (msg) + " (" __FILE__ ":" +    \
+                           std::to_string(__LINE__) + ")");                                              \
+    }                                                                                                    \
+  } while (0)
+
+#define RLREP_LAUNCH_CHECK() RLREP_CUDA(cudaGetLastError())
+
+// Wrap a C-ABI body: exceptions become error code + message.
+#define RLREP_API_BEGIN try {
+#define RLREP_API_END                              \
+  return 0;                                        \
+  }                                                \
+  catch (const std::exception& ex) {               \
+    ::rlrep::set_last_error(ex.what());            \
+    return 1;                                      \
+  }                                                \
+  catch (...) {                                    \
+    ::rlrep::set_last_error("unknown exception");  \
+    return 2;                                      \
+  }
+
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace rlrep

@@ -1,0 +1,57 @@
+// GEMM entry points of the library.
+//
+//   C[M,N] = epilogue( sum_k A(m,k) * B(n,k) )
+//
+// Operand addressing ("major" = which index is contiguous in memory):
+//   K-major  A:  A(m,k) = A[m*lda + k]      (activations X[B,in], weights W[out,in] as used by y = x W^T)
+//   MN-major A:  A(m,k) = A[k*lda + m]      (transposed views: dY^T in wgrad, W in dgrad)
+// and the same for B with (n,k).  All three linear-layer passes map onto this one contraction:
+//   forward  Y  = X  W^T : A = X  (K-major),  B = W  (K-major)
+//   dgrad    dX = dY W   : A = dY (K-major),  B = W  (MN-major, k = out index)
+//   wgrad    dW = dY^T X : A = dY (MN-major), B = X  (MN-major, k = batch index)
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "epilogue.cuh"
+
+namespace rlrep {
+
+struct GemmArgs {
+  int M = 0, N = 0, K = 0;
+  const float* A = nullptr;
+  int lda = 0;
+  bool a_mn = false;
+  // Optional second K-segment of A (CUDA-core path, K-major A only): columns [K1, K) come from A2.
+  // Lets first layers read cat(s, a) / cat(s', a') straight from two buffers without a concat pass.
+  const float* A2 = nullptr;
+  int lda2 = 0;
+  int K1 = 0;
+  const float* B = nullptr;
+  int ldb = 0;
+  bool b_mn = false;
+  float* C = nullptr;
+  int ldc = 0;
+  Epilogue epi;
+};
+
+// ---- tcgen05 path (TF32 inputs, FP32 accumulate in TMEM, TMA-fed) ----
+struct TcGemmPlan {
+  CUtensorMap tmA, tmB;
+  GemmArgs args;
+  int bn = 0;
+  int split_k = 1;
+  int kb_per_split = 0;
+  float* ws = nullptr;  // split-K partials [split_k, M, N]
+};
+
+// True when the operands satisfy TMA's constraints (16-byte aligned base, ld % 4 == 0, no A2 segment).
+bool tc_eligible(const GemmArgs& a);
+// bn / split_k = 0 picks them automatically (fill ~148 SMs). ws may be null (forces split_k = 1).
+TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* ws, size_t ws_floats);
+void launch_tc(const TcGemmPlan& p, cudaStream_t stream);
+
+// ---- CUDA-core path (exact FP32 FFMA; small-K / small-N layers and the strict-fp32 mode) ----
+void launch_simt(const GemmArgs& a, cudaStream_t stream);
+
+}  // namespace rlrep
