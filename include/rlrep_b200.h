@@ -87,6 +87,91 @@ RLREP_EXPORT int rlrep_gemm_bench(void* stream, int path, int M, int N, int K, c
                                   const rlrep_epilogue* epi, int bn, int split_k, float* ws_dev, size_t ws_floats,
                                   int iters, float* ms_out, int* bn_out, int* split_out);
 
+/* ------------------------------------------------------------------------------------------------
+ * Replay ring -- replaces utils/buffer.py:13-48 (ReplayBuffer.__init__ / add / sample).
+ * Device-resident fp32 ring of packed records [s | a | r | d | pad | s' | pad]; see rlrep_ring_layout.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rlrep_ring rlrep_ring;
+
+RLREP_EXPORT int rlrep_ring_create(int state_dim, int action_dim, long long capacity, rlrep_ring** out);
+RLREP_EXPORT int rlrep_ring_destroy(rlrep_ring* ring);
+/* Record layout in floats: total width and the offsets of action / reward / done / next_state (state is at 0). */
+RLREP_EXPORT int rlrep_ring_layout(const rlrep_ring* ring, int* record_floats, int* off_action, int* off_reward,
+                                   int* off_done, int* off_next_state);
+RLREP_EXPORT int rlrep_ring_state(const rlrep_ring* ring, long long* size, long long* ptr, long long* capacity);
+/* buffer.py:28-36 `add`, batched: n packed records [n, record_floats] are written at ptr, ptr+1, ... (mod capacity). */
+RLREP_EXPORT int rlrep_ring_add_packed(rlrep_ring* ring, const float* rows_host, int n, void* stream);
+/* Bulk fill from the reference's five column arrays (float64 if is_f64 else float32), n rows from slot 0. */
+RLREP_EXPORT int rlrep_ring_load(rlrep_ring* ring, const void* state_host, const void* action_host,
+                                 const void* next_state_host, const void* reward_host, const void* done_host,
+                                 long long n, int is_f64, void* stream);
+/* buffer.py:39-48 `sample` minus the index draw: out_dev[b, :] = record idx_host[b]; out_dev is [B, record_floats]. */
+RLREP_EXPORT int rlrep_ring_gather(rlrep_ring* ring, const int64_t* idx_host, int B, float* out_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Agent handles -- replace `Agent(**kwargs)`, `agent.train(buffer, batch_size)`, `agent.select_action(state)`
+ * (sac_agent.py:19-31,89-96,169-188; ctrlsac_agent.py:127-143,327-362; main.py:71-104,130,144).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rlrep_agent rlrep_agent;
+
+enum { RLREP_ALG_SAC = 0, RLREP_ALG_CTRLSAC = 1, RLREP_ALG_VLSAC = 2, RLREP_ALG_SPEDERSAC = 3, RLREP_ALG_DIFFSRSAC = 4 };
+enum { RLREP_PRECISION_TF32 = 0, RLREP_PRECISION_FP32 = 1 };
+
+typedef struct rlrep_agent_config {
+  int alg;
+  int state_dim, action_dim, batch_size;
+  int hidden_dim, feature_dim, actor_hidden_dim;
+  int feature_steps;           /* extra_feature_steps + 1; 0 for sac */
+  double lr_critic, lr_feature, lr_actor, lr_alpha;
+  float discount, tau, feature_tau;
+  double alpha;                /* initial temperature; log_alpha is kept in float64 like the reference */
+  int target_update_period, auto_entropy_tuning, use_feature_target;
+  int precision;               /* RLREP_PRECISION_*: tensor-core TF32 (default) or CUDA-core exact fp32 GEMMs */
+  int use_cuda_graph;          /* replay train() as one CUDA graph after the first two calls */
+  int phi_hidden_dim, phi_hidden_depth, mu_hidden_dim, mu_hidden_depth;     /* spedersac / diffsrsac */
+  int nabla_mu_hidden_dim, nabla_mu_hidden_depth, num_noise, num_noises;
+  float sigma_scale_factor;
+} rlrep_agent_config;
+
+RLREP_EXPORT int rlrep_agent_create(const rlrep_agent_config* cfg, void* stream, rlrep_agent** out);
+RLREP_EXPORT int rlrep_agent_destroy(rlrep_agent* agent);
+
+/* Parameters and Polyak targets under the reference's state_dict names ("phi.l1.weight", "critic_target.l2.bias",
+ * ...), as device pointers (so PyTorch can view them, e.g. for NCCL) and through host copies. */
+RLREP_EXPORT int rlrep_agent_num_tensors(rlrep_agent* agent, int* n);
+RLREP_EXPORT int rlrep_agent_tensor_info(rlrep_agent* agent, int i, const char** name, float** ptr_dev, int* rows,
+                                         int* cols);
+RLREP_EXPORT int rlrep_agent_tensor_read(rlrep_agent* agent, int i, float* out_host);
+RLREP_EXPORT int rlrep_agent_tensor_write(rlrep_agent* agent, int i, const float* in_host);
+/* target <- parameter copies for every Polyak target (use after writing parameters). */
+RLREP_EXPORT int rlrep_agent_sync_targets(rlrep_agent* agent);
+RLREP_EXPORT int rlrep_agent_get_log_alpha(rlrep_agent* agent, double* log_alpha);
+RLREP_EXPORT int rlrep_agent_set_log_alpha(rlrep_agent* agent, double log_alpha);
+RLREP_EXPORT int rlrep_agent_get_steps(rlrep_agent* agent, int* steps);
+
+/* One `agent.train(buffer, batch_size)`.  The caller draws the randomness exactly like the reference does
+ * (np.random.randint for replay indices, torch.randn on the CPU generator for every epsilon) and
+ * passes it in; rlrep_agent_train_counts tells how many of each one call consumes.  metrics_host receives the
+ * entries named by rlrep_agent_metric_name. */
+RLREP_EXPORT int rlrep_agent_train_counts(rlrep_agent* agent, int* n_idx, int* n_eps, int* n_metrics);
+RLREP_EXPORT const char* rlrep_agent_metric_name(rlrep_agent* agent, int i);
+RLREP_EXPORT int rlrep_agent_train(rlrep_agent* agent, rlrep_ring* ring, const int64_t* idx_host, int n_idx,
+                                   const float* eps_host, int n_eps, float* metrics_host, int n_metrics);
+/* select_action: eps_host == NULL -> tanh(mu) (explore=False), else tanh(mu + std * eps) with eps[action_dim]. */
+RLREP_EXPORT int rlrep_agent_act(rlrep_agent* agent, const float* state_host, const float* eps_host,
+                                 float* action_host);
+/* Benchmark aids.  train_resident: n_steps updates back to back with all inputs already in HBM (indices / noise of
+ * every step uploaded before the timed region), timed with CUDA events on the agent's stream; idx_host is
+ * [n_steps * n_idx], eps_host [n_steps * n_eps].  profile_train: one eager train() with an event behind every kernel
+ * launch; names[i] / ms[i] describe launch i (n_entries may exceed max_entries; only max_entries are written). */
+RLREP_EXPORT int rlrep_agent_train_resident(rlrep_agent* agent, rlrep_ring* ring, const int64_t* idx_host,
+                                            const float* eps_host, int n_steps, float* total_ms);
+RLREP_EXPORT int rlrep_agent_profile_train(rlrep_agent* agent, rlrep_ring* ring, const int64_t* idx_host,
+                                           const float* eps_host, int max_entries, const char** names, float* ms,
+                                           int* n_entries);
+/* Kernels launched by the most recent train() (a graph replay counts the kernels it contains). */
+RLREP_EXPORT int rlrep_agent_last_launches(rlrep_agent* agent, int* launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -16,6 +16,25 @@ class RlrepError(RuntimeError):
     pass
 
 
+class AgentConfig(C.Structure):
+    """Mirror of `rlrep_agent_config` (include/rlrep_b200.h)."""
+    _fields_ = [
+        ("alg", C.c_int), ("state_dim", C.c_int), ("action_dim", C.c_int), ("batch_size", C.c_int),
+        ("hidden_dim", C.c_int), ("feature_dim", C.c_int), ("actor_hidden_dim", C.c_int), ("feature_steps", C.c_int),
+        ("lr_critic", C.c_double), ("lr_feature", C.c_double), ("lr_actor", C.c_double), ("lr_alpha", C.c_double),
+        ("discount", C.c_float), ("tau", C.c_float), ("feature_tau", C.c_float), ("alpha", C.c_double),
+        ("target_update_period", C.c_int), ("auto_entropy_tuning", C.c_int), ("use_feature_target", C.c_int),
+        ("precision", C.c_int), ("use_cuda_graph", C.c_int),
+        ("phi_hidden_dim", C.c_int), ("phi_hidden_depth", C.c_int), ("mu_hidden_dim", C.c_int),
+        ("mu_hidden_depth", C.c_int), ("nabla_mu_hidden_dim", C.c_int), ("nabla_mu_hidden_depth", C.c_int),
+        ("num_noise", C.c_int), ("num_noises", C.c_int), ("sigma_scale_factor", C.c_float),
+    ]
+
+
+ALG = {"sac": 0, "ctrlsac": 1, "vlsac": 2, "spedersac": 3, "diffsrsac": 4}
+PRECISION = {"tf32": 0, "fp32": 1}
+
+
 class Epilogue(C.Structure):
     """Mirror of `rlrep_epilogue` (include/rlrep_b200.h)."""
     _fields_ = [
@@ -54,7 +73,32 @@ def _declare(lib: C.CDLL) -> None:
         "rlrep_gemm": [vp, i, i, i, i, vp, i, i, vp, i, i, vp, i, i, vp, i, C.POINTER(Epilogue), i, i, vp, sz],
         "rlrep_gemm_bench": [vp, i, i, i, i, vp, i, i, vp, i, i, vp, i, C.POINTER(Epilogue), i, i, vp, sz, i,
                              C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)],
+        "rlrep_ring_create": [i, i, C.c_longlong, C.POINTER(vp)],
+        "rlrep_ring_destroy": [vp],
+        "rlrep_ring_layout": [vp] + [C.POINTER(i)] * 5,
+        "rlrep_ring_state": [vp] + [C.POINTER(C.c_longlong)] * 3,
+        "rlrep_ring_add_packed": [vp, vp, i, vp],
+        "rlrep_ring_load": [vp, vp, vp, vp, vp, vp, C.c_longlong, i, vp],
+        "rlrep_ring_gather": [vp, vp, i, vp, vp],
+        "rlrep_agent_create": [C.POINTER(AgentConfig), vp, C.POINTER(vp)],
+        "rlrep_agent_destroy": [vp],
+        "rlrep_agent_num_tensors": [vp, C.POINTER(i)],
+        "rlrep_agent_tensor_info": [vp, i, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(i), C.POINTER(i)],
+        "rlrep_agent_tensor_read": [vp, i, vp],
+        "rlrep_agent_tensor_write": [vp, i, vp],
+        "rlrep_agent_sync_targets": [vp],
+        "rlrep_agent_get_log_alpha": [vp, C.POINTER(C.c_double)],
+        "rlrep_agent_set_log_alpha": [vp, C.c_double],
+        "rlrep_agent_get_steps": [vp, C.POINTER(i)],
+        "rlrep_agent_train_counts": [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i)],
+        "rlrep_agent_train": [vp, vp, vp, i, vp, i, vp, i],
+        "rlrep_agent_act": [vp, vp, vp, vp],
+        "rlrep_agent_last_launches": [vp, C.POINTER(i)],
+        "rlrep_agent_train_resident": [vp, vp, vp, vp, i, C.POINTER(C.c_float)],
+        "rlrep_agent_profile_train": [vp, vp, vp, vp, i, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(i)],
     }
+    lib.rlrep_agent_metric_name.argtypes = [vp, i]
+    lib.rlrep_agent_metric_name.restype = C.c_char_p
     for name, argtypes in sigs.items():
         fn = getattr(lib, name)
         fn.argtypes = argtypes

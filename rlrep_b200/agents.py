@@ -1,0 +1,309 @@
+"""Host-side mirror of the reference's agent classes over the C-ABI handles of librlrep_b200.so.
+
+Same constructors, `train(buffer, batch_size) -> dict` and `select_action(state, explore=False)` as the reference
+(agent/sac/sac_agent.py:16-188, agent/ctrlsac/ctrlsac_agent.py:123-362), so the reference's `main.py` drives them
+unchanged.  Everything numerical happens in the CUDA library; this file only
+  * draws the randomness the way the reference does (np.random.randint for replay indices, torch.randn on the CPU
+    generator for every epsilon, in the order of SURVEY.md A.5) and hands it to `rlrep_agent_train`,
+  * maps the metrics array back to the reference's info-dict keys,
+  * moves weights in and out under the reference's state_dict names.
+There is no fallback: without the built library or without a CUDA device the constructors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def _orthogonal(out_f, in_f):
+    w = torch.empty(out_f, in_f)
+    torch.nn.init.orthogonal_(w)  # utils/util.py:61-66 (weight_init)
+    return w
+
+
+def _default_linear(out_f, in_f):
+    """nn.Linear's default init (kaiming_uniform(a=sqrt(5)) == U(+-1/sqrt(fan_in)) for weight and bias)."""
+    bound = 1.0 / math.sqrt(in_f)
+    return (torch.rand(out_f, in_f) * 2 - 1) * bound, (torch.rand(out_f) * 2 - 1) * bound
+
+
+class _Handle:
+    """Owns one `rlrep_agent*` and exposes tensors / scalars."""
+
+    def __init__(self, cfg: _lib.AgentConfig):
+        if not torch.cuda.is_available():
+            raise _lib.RlrepError("rlrep_b200 agents need a CUDA device (there is no CPU fallback)")
+        self.lib = _lib.load()
+        self.stream = torch.cuda.current_stream().cuda_stream
+        h = C.c_void_p()
+        _lib.check(self.lib.rlrep_agent_create(C.byref(cfg), self.stream, C.byref(h)))
+        self.h = h
+        n = C.c_int()
+        _lib.check(self.lib.rlrep_agent_num_tensors(self.h, C.byref(n)))
+        self.index = {}
+        for i in range(n.value):
+            name, ptr, rows, cols = C.c_char_p(), C.c_void_p(), C.c_int(), C.c_int()
+            _lib.check(self.lib.rlrep_agent_tensor_info(self.h, i, C.byref(name), C.byref(ptr), C.byref(rows), C.byref(cols)))
+            self.index[name.value.decode()] = (i, ptr.value, rows.value, cols.value)
+        ni, ne, nm = C.c_int(), C.c_int(), C.c_int()
+        _lib.check(self.lib.rlrep_agent_train_counts(self.h, C.byref(ni), C.byref(ne), C.byref(nm)))
+        self.n_idx, self.n_eps, self.n_metrics = ni.value, ne.value, nm.value
+        self.metric_names = [self.lib.rlrep_agent_metric_name(self.h, i).decode() for i in range(self.n_metrics)]
+        self._metrics = np.zeros(self.n_metrics, dtype=np.float32)
+
+    def close(self):
+        h, self.h = self.h, None
+        if h is not None:
+            self.lib.rlrep_agent_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def read(self, name) -> torch.Tensor:
+        i, _, rows, cols = self.index[name]
+        out = np.empty(rows * cols, dtype=np.float32)
+        _lib.check(self.lib.rlrep_agent_tensor_read(self.h, i, out.ctypes.data))
+        t = torch.from_numpy(out)
+        return t.reshape(rows, cols) if not name.endswith(".bias") else t.reshape(rows)
+
+    def write(self, name, value):
+        i, _, rows, cols = self.index[name]
+        arr = np.ascontiguousarray(torch.as_tensor(value).detach().cpu().float().numpy().reshape(-1))
+        if arr.size != rows * cols:
+            raise ValueError(f"{name}: expected {rows * cols} values, got {arr.size}")
+        _lib.check(self.lib.rlrep_agent_tensor_write(self.h, i, arr.ctypes.data))
+
+    def train(self, ring_handle, idx: np.ndarray, eps: np.ndarray) -> np.ndarray:
+        _lib.check(self.lib.rlrep_agent_train(self.h, ring_handle, idx.ctypes.data, idx.size, eps.ctypes.data, eps.size,
+                                              self._metrics.ctypes.data, self._metrics.size))
+        return self._metrics
+
+    @property
+    def log_alpha(self) -> float:
+        v = C.c_double()
+        _lib.check(self.lib.rlrep_agent_get_log_alpha(self.h, C.byref(v)))
+        return v.value
+
+    @log_alpha.setter
+    def log_alpha(self, v):
+        _lib.check(self.lib.rlrep_agent_set_log_alpha(self.h, float(v)))
+
+    @property
+    def last_launches(self) -> int:
+        v = C.c_int()
+        _lib.check(self.lib.rlrep_agent_last_launches(self.h, C.byref(v)))
+        return v.value
+
+
+class SACAgent:
+    """Drop-in for agent.sac.sac_agent.SACAgent (sac_agent.py:16-188)."""
+
+    alg = "sac"
+
+    def __init__(self, state_dim, action_dim, action_space, lr=3e-4, discount=0.99, target_update_period=2, tau=0.005,
+                 alpha=0.1, auto_entropy_tuning=True, hidden_dim=1024, *, precision="tf32", use_cuda_graph=True,
+                 **extra):
+        self.steps = 0
+        self.state_dim, self.action_dim = int(state_dim), int(action_dim)
+        self.action_range = [float(action_space.low.min()), float(action_space.high.max())]  # sac_agent.py:36-39
+        # main.py passes --discount/--tau through argparse without type=, i.e. possibly as strings
+        self.discount, self.tau = float(discount), float(tau)
+        self.target_update_period = int(target_update_period)
+        self.learnable_temperature = bool(auto_entropy_tuning)
+        self.target_entropy = -action_dim
+        self._lr, self._alpha0, self._hidden = float(lr), float(alpha), int(hidden_dim)
+        self._precision, self._use_graph = precision, bool(use_cuda_graph)
+        self._extra = extra
+        self._h: _Handle | None = None
+        self._batch = None
+        self._pending_state = self._initial_state()  # host copy until the handle exists
+
+    # ---- configuration of the C handle (overridden per algorithm) -------------------------------------------
+    def _config(self, batch_size) -> _lib.AgentConfig:
+        c = _lib.AgentConfig()
+        c.alg = _lib.ALG[self.alg]
+        c.state_dim, c.action_dim, c.batch_size = self.state_dim, self.action_dim, int(batch_size)
+        c.hidden_dim, c.feature_dim, c.actor_hidden_dim = self._hidden, 0, self._hidden
+        c.feature_steps = 0
+        c.lr_critic = c.lr_actor = c.lr_alpha = self._lr
+        c.lr_feature = 0.0
+        c.discount, c.tau, c.feature_tau = self.discount, self.tau, 0.0
+        c.alpha = self._alpha0
+        c.target_update_period = self.target_update_period
+        c.auto_entropy_tuning = int(self.learnable_temperature)
+        c.use_feature_target = 0
+        c.precision = _lib.PRECISION[self._precision]
+        c.use_cuda_graph = int(self._use_graph)
+        return c
+
+    def _layers(self):
+        """[(name, out, in, init)] in the reference's construction order."""
+        S, A, H = self.state_dim, self.action_dim, self._hidden
+        q = [(f"critic.{h}.{i}", o, n, "orth") for h in ("Q1", "Q2") for i, o, n in ((0, H, S + A), (2, H, H), (4, 1, H))]
+        return q + self._actor_layers(H)
+
+    def _actor_layers(self, H):
+        S, A = self.state_dim, self.action_dim
+        return [("actor.trunk.0", H, S, "orth"), ("actor.trunk.2", H, H, "orth"), ("actor.trunk.4", 2 * A, H, "orth")]
+
+    def _initial_state(self):
+        sd = {}
+        for name, out, inp, kind in self._layers():
+            if kind == "orth":  # modules that call self.apply(util.weight_init): orthogonal weight, zero bias
+                sd[name + ".weight"], sd[name + ".bias"] = _orthogonal(out, inp), torch.zeros(out)
+            else:
+                sd[name + ".weight"], sd[name + ".bias"] = _default_linear(out, inp)
+        return sd
+
+    # ---- handle management --------------------------------------------------------------------------------------
+    def _ensure(self, batch_size=None):
+        if self._h is not None and (batch_size is None or batch_size == self._batch):
+            return self._h
+        if self._h is not None:
+            if self.steps > 0:
+                raise _lib.RlrepError(f"batch_size is fixed per agent handle (was {self._batch}, got {batch_size})")
+            self._pending_state = self.state_dict()
+            self._pending_state.pop("log_alpha", None)
+            self._h.close()
+        self._batch = int(batch_size or 256)
+        self._h = _Handle(self._config(self._batch))
+        self.load_state_dict(self._pending_state, strict=False)
+        self._pending_state = None
+        return self._h
+
+    def state_dict(self):
+        """All parameters and Polyak targets under the reference's state_dict names, plus float64 `log_alpha`."""
+        if self._h is None:
+            return dict(self._pending_state)
+        sd = {name: self._h.read(name) for name in self._h.index}
+        sd["log_alpha"] = torch.tensor(self._h.log_alpha, dtype=torch.float64)
+        return sd
+
+    def load_state_dict(self, sd, strict=True, sync_targets=None):
+        """Write weights.  Targets not present in `sd` are re-synchronised from their source networks."""
+        if self._h is None:
+            self._pending_state.update({k: torch.as_tensor(v).detach().clone() for k, v in sd.items()})
+            return
+        names = set(self._h.index)
+        for k, v in sd.items():
+            if k == "log_alpha":
+                self._h.log_alpha = float(v)
+            elif k in names:
+                self._h.write(k, v)
+            elif strict:
+                raise KeyError(k)
+        has_targets = any("_target." in k for k in sd)
+        if sync_targets or (sync_targets is None and not has_targets):
+            _lib.check(self._h.lib.rlrep_agent_sync_targets(self._h.h))
+
+    @property
+    def alpha(self):
+        return math.exp(self._h.log_alpha) if self._h is not None else self._alpha0
+
+    @property
+    def gpu_launches_last_train(self):
+        return self._h.last_launches if self._h is not None else 0
+
+    # ---- reference surface ----------------------------------------------------------------------------------------
+    def select_action(self, state, explore=False):  # sac_agent.py:89-96
+        h = self._ensure()
+        s = np.ascontiguousarray(np.asarray(state, dtype=np.float32).reshape(-1))
+        out = np.empty(self.action_dim, dtype=np.float32)
+        eps = None
+        if explore:
+            eps = np.ascontiguousarray(torch.randn(1, self.action_dim).numpy().reshape(-1))
+        _lib.check(h.lib.rlrep_agent_act(h.h, s.ctypes.data, eps.ctypes.data if eps is not None else None,
+                                         out.ctypes.data))
+        return np.clip(out, self.action_range[0], self.action_range[1])
+
+    def _draw(self, buffer, batch_size):
+        """Indices and noise for one train(), in the reference's RNG order (sac)."""
+        idx = np.random.randint(0, buffer.size, size=batch_size)
+        eps = [torch.randn(batch_size, self.action_dim) for _ in range(2)]  # critic step a', then actor step a
+        return idx, torch.stack(eps).numpy().reshape(-1)
+
+    def _info(self, m):
+        d = dict(zip(self._h.metric_names, (float(x) for x in m)))
+        # sac_agent.py:131-135: q_loss = mse1 + mse2; 'q2' reports mean(Q1)
+        return {"q_loss": float(np.float32(d["q1_loss"]) + np.float32(d["q2_loss"])), "q1": d["q1"], "q2": d["q1"],
+                "actor_loss": d["actor_loss"], "alpha_loss": d["alpha_loss"], "alpha": d["alpha"]}
+
+    def train(self, buffer, batch_size):
+        """One update (sac_agent.py:169-188).  `buffer` must be an rlrep_b200.ReplayBuffer."""
+        h = self._ensure(batch_size)
+        buffer.flush()
+        self.steps += 1
+        idx, eps = self._draw(buffer, batch_size)
+        idx = np.ascontiguousarray(idx, dtype=np.int64)
+        eps = np.ascontiguousarray(eps, dtype=np.float32)
+        m = h.train(buffer._h, idx, eps)
+        info = self._info(m)
+        if not self.learnable_temperature:
+            info.pop("alpha_loss", None)
+            info.pop("alpha", None)
+        return info
+
+
+class CTRLSACAgent(SACAgent):
+    """Drop-in for agent.ctrlsac.ctrlsac_agent.CTRLSACAgent (ctrlsac_agent.py:123-362)."""
+
+    alg = "ctrlsac"
+
+    def __init__(self, state_dim, action_dim, action_space, lr=1e-4, discount=0.99, target_update_period=2, tau=0.005,
+                 alpha=0.1, auto_entropy_tuning=True, hidden_dim=1024, feature_tau=0.005, feature_dim=2048,
+                 use_feature_target=True, extra_feature_steps=1, **kw):
+        self.feature_dim, self.feature_tau = int(feature_dim), float(feature_tau)
+        self.use_feature_target, self.extra_feature_steps = bool(use_feature_target), int(extra_feature_steps)
+        super().__init__(state_dim, action_dim, action_space, lr=lr, discount=discount,
+                         target_update_period=target_update_period, tau=tau, alpha=alpha,
+                         auto_entropy_tuning=auto_entropy_tuning, hidden_dim=hidden_dim, **kw)
+
+    def _config(self, batch_size):
+        c = super()._config(batch_size)
+        c.feature_dim, c.actor_hidden_dim = self.feature_dim, 256  # actor hidden fixed at 256, ctrlsac_agent.py:188-194
+        c.feature_steps = self.extra_feature_steps + 1
+        c.lr_feature = c.lr_critic = self._lr
+        c.lr_actor = c.lr_alpha = self._lr / 3  # :195-197
+        c.feature_tau = self.feature_tau
+        c.use_feature_target = int(self.use_feature_target)
+        return c
+
+    def _layers(self):
+        S, A, H, D = self.state_dim, self.action_dim, self._hidden, self.feature_dim
+        return [("phi.l1", H, S + A, "default"), ("phi.l2", H, H, "default"), ("phi.l3", D, H, "default"),
+                ("mu.l1", H, S, "default"), ("mu.l2", H, H, "default"), ("mu.l3", D, H, "default"),
+                ("theta.l", 1, D, "default")] + self._actor_layers(256) + \
+               [("critic.l1", H, D, "default"), ("critic.l2", 1, H, "default"), ("critic.l4", H, D, "default"),
+                ("critic.l5", 1, H, "default")]
+
+    def state_dict(self):
+        sd = super().state_dict()
+        # frozen_phi / frozen_phi_target are aliases of phi after any train() (ctrlsac_agent.py:344-346)
+        for k in [k for k in sd if k.startswith("phi.")]:
+            sd["frozen_phi." + k[4:]] = sd[k]
+            sd["frozen_phi_target." + k[4:]] = sd[k]
+        return sd
+
+    def load_state_dict(self, sd, strict=True, sync_targets=None):
+        sd = {k: v for k, v in sd.items() if not k.startswith("frozen_phi")}
+        super().load_state_dict(sd, strict=strict, sync_targets=sync_targets)
+
+    def _draw(self, buffer, batch_size):  # K x randint[B] -> randn[B,A] -> randn[B,A]
+        K = self.extra_feature_steps + 1
+        idx = np.concatenate([np.random.randint(0, buffer.size, size=batch_size) for _ in range(K)])
+        eps = [torch.randn(batch_size, self.action_dim) for _ in range(2)]
+        return idx, torch.stack(eps).numpy().reshape(-1)
+
+    def _info(self, m):
+        return dict(zip(self._h.metric_names, (float(x) for x in m)))
+
+
+AGENTS = {"sac": SACAgent, "ctrlsac": CTRLSACAgent}

@@ -1,0 +1,220 @@
+// SacBase: what every SAC-family agent shares (reference: agent/sac/sac_agent.py) -- the tanh-Gaussian actor with
+// its forward/backward, the control block with the float64 temperature, staging of the host-drawn indices and
+// noise, metrics read-back, and the eager -> capture -> replay protocol of train().
+#pragma once
+#include "agent.cuh"
+
+namespace rlrep {
+
+class SacBase : public Agent {
+ public:
+  SacBase(const AgentConfig& c, cudaStream_t s) {
+    cfg = c;
+    stream = s;
+    S_ = c.state_dim;
+    A_ = c.action_dim;
+    B_ = c.batch;
+    AH_ = c.actor_hidden_dim;
+    RLREP_CHECK(S_ > 0 && A_ > 0 && B_ > 0, "bad agent dimensions");
+  }
+  ~SacBase() override {
+    if (metrics_host_) cudaFreeHost(metrics_host_);
+    if (idx_host_) cudaFreeHost(idx_host_);
+    if (eps_host_) cudaFreeHost(eps_host_);
+    if (act_host_) cudaFreeHost(act_host_);
+  }
+
+  void train(Ring& ring, const long long* idx_host, int n_idx, const float* eps_host, int n_eps, float* metrics_host,
+             int n_metrics) override {
+    RLREP_CHECK(ring.S == S_ && ring.A == A_, "ring shape does not match the agent");
+    RLREP_CHECK(n_idx == idx_per_train() && n_eps == eps_per_train(), "wrong number of indices / noise values");
+    RLREP_CHECK(n_metrics >= (int)metric_names().size(), "metrics buffer too small");
+    for (int i = 0; i < n_idx; ++i)
+      RLREP_CHECK(idx_host[i] >= 0 && idx_host[i] < ring.size, "replay index out of range");
+    if (ring_bound_ != &ring) {  // graphs bake the ring pointer in
+      graph_.reset();
+      ring_bound_ = &ring;
+    }
+    RLREP_CUDA(cudaStreamSynchronize(stream));  // pinned staging is reused across calls
+    std::memcpy(idx_host_, idx_host, (size_t)n_idx * sizeof(long long));
+    std::memcpy(eps_host_, eps_host, (size_t)n_eps * sizeof(float));
+    RLREP_CUDA(cudaMemcpyAsync(idx_dev_, idx_host_, (size_t)n_idx * sizeof(long long), cudaMemcpyHostToDevice, stream));
+    RLREP_CUDA(cudaMemcpyAsync(eps_dev_, eps_host_, (size_t)n_eps * sizeof(float), cudaMemcpyHostToDevice, stream));
+    const long long before = launch_count();
+    const bool was_captured = graph_.captured();
+    graph_.run(stream, cfg.use_graph != 0, [&] { update(ring); });
+    if (!was_captured) launches_per_train_ = (int)(launch_count() - before);
+    last_launches = launches_per_train_;
+    RLREP_CUDA(cudaMemcpyAsync(metrics_host_, metrics_dev_, kNumMetrics * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    RLREP_CUDA(cudaStreamSynchronize(stream));
+    std::memcpy(metrics_host, metrics_host_, metric_names().size() * sizeof(float));
+  }
+
+  float train_resident(Ring& ring, const long long* idx_host, const float* eps_host, int n_steps) override {
+    const int ni = idx_per_train(), ne = eps_per_train();
+    RLREP_CHECK(ring.S == S_ && ring.A == A_ && n_steps > 0, "bad arguments");
+    if (ring_bound_ != &ring) {
+      graph_.reset();
+      ring_bound_ = &ring;
+    }
+    long long* idx_all = nullptr;
+    float* eps_all = nullptr;
+    RLREP_CUDA(cudaMalloc(&idx_all, (size_t)n_steps * ni * sizeof(long long)));
+    RLREP_CUDA(cudaMalloc(&eps_all, (size_t)n_steps * ne * sizeof(float)));
+    RLREP_CUDA(cudaMemcpy(idx_all, idx_host, (size_t)n_steps * ni * sizeof(long long), cudaMemcpyHostToDevice));
+    RLREP_CUDA(cudaMemcpy(eps_all, eps_host, (size_t)n_steps * ne * sizeof(float), cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    RLREP_CUDA(cudaEventCreate(&e0));
+    RLREP_CUDA(cudaEventCreate(&e1));
+    RLREP_CUDA(cudaStreamSynchronize(stream));
+    RLREP_CUDA(cudaEventRecord(e0, stream));
+    for (int i = 0; i < n_steps; ++i) {
+      RLREP_CUDA(cudaMemcpyAsync(idx_dev_, idx_all + (size_t)i * ni, (size_t)ni * sizeof(long long),
+                                 cudaMemcpyDeviceToDevice, stream));
+      RLREP_CUDA(cudaMemcpyAsync(eps_dev_, eps_all + (size_t)i * ne, (size_t)ne * sizeof(float),
+                                 cudaMemcpyDeviceToDevice, stream));
+      graph_.run(stream, cfg.use_graph != 0, [&] { update(ring); });
+    }
+    RLREP_CUDA(cudaEventRecord(e1, stream));
+    RLREP_CUDA(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    RLREP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(idx_all);
+    cudaFree(eps_all);
+    return ms;
+  }
+
+  std::vector<ProfileEntry> profile_train(Ring& ring, const long long* idx_host, const float* eps_host) override {
+    const int ni = idx_per_train(), ne = eps_per_train();
+    RLREP_CUDA(cudaStreamSynchronize(stream));
+    std::memcpy(idx_host_, idx_host, (size_t)ni * sizeof(long long));
+    std::memcpy(eps_host_, eps_host, (size_t)ne * sizeof(float));
+    RLREP_CUDA(cudaMemcpyAsync(idx_dev_, idx_host_, (size_t)ni * sizeof(long long), cudaMemcpyHostToDevice, stream));
+    RLREP_CUDA(cudaMemcpyAsync(eps_dev_, eps_host_, (size_t)ne * sizeof(float), cudaMemcpyHostToDevice, stream));
+    profile_begin(stream);
+    update(ring);
+    return profile_end(stream);
+  }
+
+  // select_action (sac_agent.py:89-96): eps == nullptr -> tanh(mu), else tanh(mu + std * eps).  Clamping to the
+  // action range is done by the caller (the range belongs to the environment, not to this handle).
+  void act(const float* state_host, const float* eps_host, float* action_host) override {
+    RLREP_CUDA(cudaStreamSynchronize(stream));
+    std::memcpy(act_host_, state_host, S_ * sizeof(float));
+    for (int j = 0; j < A_; ++j) act_host_[S_ + j] = eps_host ? eps_host[j] : 0.f;
+    RLREP_CUDA(cudaMemcpyAsync(act_dev_, act_host_, (S_ + A_) * sizeof(float), cudaMemcpyHostToDevice, stream));
+    const Linear l0 = a0_.view(actor_g_), l1 = a1_.view(actor_g_), l2 = a2_.view(actor_g_);
+    linear_fwd(gemm_, stream, 1, Mat{act_dev_, S_}, l0, ACT_ELU, act_h1_, AH_);
+    linear_fwd(gemm_, stream, 1, Mat{act_h1_, AH_}, l1, ACT_ELU, act_h2_, AH_);
+    linear_fwd(gemm_, stream, 1, Mat{act_h2_, AH_}, l2, ACT_NONE, act_head_, 2 * A_);
+    launch_actor_sample(act_head_, 1, A_, act_dev_ + S_, act_out_, A_, act_logp_, stream);
+    RLREP_CUDA(cudaMemcpyAsync(act_host_, act_out_, A_ * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    RLREP_CUDA(cudaStreamSynchronize(stream));
+    std::memcpy(action_host, act_host_, A_ * sizeof(float));
+  }
+
+ protected:
+  // One full train() worth of launches on `stream`, reading idx_dev_ / eps_dev_ and writing metrics_dev_.
+  virtual void update(Ring& ring) = 0;
+
+  void plan_common(int n_idx, int n_eps, int ring_R) {
+    R_ = ring_R;
+    actor_g_.name = "actor";
+    a0_ = add_linear(actor_g_, "actor.trunk.0", AH_, S_);  // agent/sac/actor.py:66-74
+    a1_ = add_linear(actor_g_, "actor.trunk.2", AH_, AH_);
+    a2_ = add_linear(actor_g_, "actor.trunk.4", 2 * A_, AH_);
+    actor_g_.want(arena_);
+    arena_.want(&ctl, 1);
+    arena_.want(&metrics_dev_, kNumMetrics);
+    arena_.want(&idx_dev_, n_idx);
+    arena_.want(&eps_dev_, n_eps);
+    arena_.want(&batch_, (size_t)B_ * R_);
+    arena_.want(&ah1_, (size_t)B_ * AH_);
+    arena_.want(&ah2_, (size_t)B_ * AH_);
+    arena_.want(&head_, (size_t)B_ * 2 * A_);
+    arena_.want(&action_, (size_t)B_ * A_);
+    arena_.want(&logp_, B_);
+    arena_.want(&dhead_, (size_t)B_ * 2 * A_);
+    arena_.want(&dah2_, (size_t)B_ * AH_);
+    arena_.want(&dah1_, (size_t)B_ * AH_);
+    arena_.want(&d_action_, (size_t)B_ * A_);
+    arena_.want(&dlogp_, 4);
+    arena_.want(&act_dev_, S_ + A_);
+    arena_.want(&act_h1_, AH_);
+    arena_.want(&act_h2_, AH_);
+    arena_.want(&act_head_, 2 * A_);
+    arena_.want(&act_out_, A_);
+    arena_.want(&act_logp_, 4);
+    RLREP_CUDA(cudaMallocHost(&metrics_host_, kNumMetrics * sizeof(float)));
+    RLREP_CUDA(cudaMallocHost(&idx_host_, (size_t)(n_idx > 0 ? n_idx : 1) * sizeof(long long)));
+    RLREP_CUDA(cudaMallocHost(&eps_host_, (size_t)(n_eps > 0 ? n_eps : 1) * sizeof(float)));
+    RLREP_CUDA(cudaMallocHost(&act_host_, (size_t)(S_ + A_) * sizeof(float)));
+  }
+
+  void finish_setup(size_t gemm_ws_floats) {
+    arena_.commit();
+    gemm_.init(static_cast<Precision>(cfg.precision), gemm_ws_floats);
+    Control h;
+    std::memset(&h, 0, sizeof(h));
+    h.log_alpha = std::log(cfg.alpha0);  // torch.tensor(np.log(alpha)), float64
+    h.alpha = (float)cfg.alpha0;
+    RLREP_CUDA(cudaMemcpyAsync(ctl, &h, sizeof(h), cudaMemcpyHostToDevice, stream));
+    RLREP_CUDA(cudaStreamSynchronize(stream));
+  }
+
+  // actor(obs) -> head_, then rsample with eps -> action_out [B, A], logp_out [B]
+  void actor_forward(Mat obs, const float* eps, float* action_out, float* logp_out) {
+    const Linear l0 = a0_.view(actor_g_), l1 = a1_.view(actor_g_), l2 = a2_.view(actor_g_);
+    linear_fwd(gemm_, stream, B_, obs, l0, ACT_ELU, ah1_, AH_);
+    linear_fwd(gemm_, stream, B_, Mat{ah1_, AH_}, l1, ACT_ELU, ah2_, AH_);
+    linear_fwd(gemm_, stream, B_, Mat{ah2_, AH_}, l2, ACT_NONE, head_, 2 * A_);
+    launch_actor_sample(head_, B_, A_, eps, action_out, A_, logp_out, stream);
+  }
+  // Needs d_action_ [B, A] and *dlogp_; the activations of the matching actor_forward(obs, eps, ...) must still be
+  // in ah1_/ah2_/head_.  Leaves the actor gradients in actor_g_.g.
+  void actor_backward(Mat obs, const float* eps) {
+    const Linear l0 = a0_.view(actor_g_), l1 = a1_.view(actor_g_), l2 = a2_.view(actor_g_);
+    launch_actor_sample_bwd(head_, B_, A_, eps, d_action_, A_, dlogp_, dhead_, stream);
+    linear_wgrad(gemm_, stream, B_, Mat{dhead_, 2 * A_}, Mat{ah2_, AH_}, l2);
+    linear_dgrad(gemm_, stream, B_, Mat{dhead_, 2 * A_}, l2, DACT_ELU_OUT, Mat{ah2_, AH_}, dah2_, AH_);
+    linear_wgrad(gemm_, stream, B_, Mat{dah2_, AH_}, Mat{ah1_, AH_}, l1);
+    linear_dgrad(gemm_, stream, B_, Mat{dah2_, AH_}, l1, DACT_ELU_OUT, Mat{ah1_, AH_}, dah1_, AH_);
+    linear_wgrad(gemm_, stream, B_, Mat{dah1_, AH_}, obs, l0);
+  }
+  void actor_adam() {
+    launch_adam_polyak(actor_g_.p, actor_g_.g, actor_g_.m, actor_g_.v, actor_g_.n, &ctl->actor, nullptr, 0, 0.f,
+                       nullptr, stream);
+  }
+  TickParams base_tick() const {
+    TickParams t;
+    t.k_feat = cfg.k_feat;
+    t.period = cfg.target_update_period;
+    t.lr_feat = cfg.lr_feat;
+    t.lr_critic = cfg.lr;
+    t.lr_actor = cfg.lr_actor;
+    t.lr_alpha = cfg.lr_alpha;
+    t.critic_steps = 1;
+    return t;
+  }
+
+  int S_ = 0, A_ = 0, B_ = 0, AH_ = 0, R_ = 0;
+  DeviceArena arena_;
+  GemmRunner gemm_;
+  GraphReplay graph_;
+  Ring* ring_bound_ = nullptr;
+  int launches_per_train_ = 0;
+  ParamGroup actor_g_;
+  LinearSlot a0_, a1_, a2_;
+  float *metrics_dev_ = nullptr, *metrics_host_ = nullptr;
+  long long *idx_dev_ = nullptr, *idx_host_ = nullptr;
+  float *eps_dev_ = nullptr, *eps_host_ = nullptr;
+  float* batch_ = nullptr;
+  float *ah1_ = nullptr, *ah2_ = nullptr, *head_ = nullptr, *action_ = nullptr, *logp_ = nullptr;
+  float *dhead_ = nullptr, *dah2_ = nullptr, *dah1_ = nullptr, *d_action_ = nullptr, *dlogp_ = nullptr;
+  float *act_dev_ = nullptr, *act_h1_ = nullptr, *act_h2_ = nullptr, *act_head_ = nullptr, *act_out_ = nullptr,
+        *act_logp_ = nullptr, *act_host_ = nullptr;
+};
+
+}  // namespace rlrep

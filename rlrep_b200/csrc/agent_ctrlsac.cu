@@ -1,0 +1,262 @@
+// CTRL-SAC update step (reference: agent/ctrlsac/ctrlsac_agent.py:213-362) as one stream of sm_100a kernels.
+//
+// Per train(): K x [gather -> phi/mu forward -> contrastive logits (tcgen05) -> row LSE/CE -> backward ->
+// fused Adam(+Polyak of phi_target)] -> critic step -> actor/alpha step -> critic Polyak (fused into the critic
+// Adam launch, gated by the control block).  All of it is captured into a CUDA graph after the first call.
+//
+// Reference quirks kept: frozen_phi == frozen_phi_target == phi after the feature loop (they are
+// aliases here, not copies); phi_target is Polyak-updated but never read; critic/actor reuse the last feature
+// batch; the actor backward skips the dW of the frozen phi / critic (never consumed by the reference either).
+#include "agent_base.cuh"
+
+namespace rlrep {
+
+namespace {
+
+class CtrlSacAgent final : public SacBase {
+ public:
+  CtrlSacAgent(const AgentConfig& c, cudaStream_t s) : SacBase(c, s) {
+    H_ = c.hidden_dim;
+    D_ = c.feature_dim;
+    K_ = c.k_feat;
+    RLREP_CHECK(K_ >= 1 && K_ <= kMaxFeatureSteps, "extra_feature_steps out of range");
+    const RecordLayout probe_layout = RecordLayout::of(S_, A_);
+    off_r_ = probe_layout.off_r;
+    off_d_ = probe_layout.off_d;
+    off_s2_ = probe_layout.off_s2;
+    plan_common(K_ * B_, 2 * B_ * A_, probe_layout.R);
+
+    // feature group: phi first so that its Polyak target is a prefix (ctrlsac_agent.py:163-178)
+    feat_g_.name = "feature";
+    p1_ = add_linear(feat_g_, "phi.l1", H_, S_ + A_);
+    p2_ = add_linear(feat_g_, "phi.l2", H_, H_);
+    p3_ = add_linear(feat_g_, "phi.l3", D_, H_);
+    feat_g_.n_target = feat_g_.n;
+    feat_g_.target_prefix_from = "phi.";
+    feat_g_.target_prefix_to = "phi_target.";
+    m1_ = add_linear(feat_g_, "mu.l1", H_, S_);
+    m2_ = add_linear(feat_g_, "mu.l2", H_, H_);
+    m3_ = add_linear(feat_g_, "mu.l3", D_, H_);
+    th_ = add_linear(feat_g_, "theta.l", 1, D_);
+    feat_g_.want(arena_);
+
+    // critic group: l1 | l4 stacked so both heads' hidden layers are ONE [2H, D] GEMM (ctrlsac_agent.py:18-52)
+    crit_g_.name = "critic";
+    c14_.out = 2 * H_;
+    c14_.in = D_;
+    c14_.w_off = crit_g_.add("critic.l1.weight", H_, D_);
+    crit_g_.add("critic.l4.weight", H_, D_);
+    c14_.b_off = crit_g_.add("critic.l1.bias", H_, 1);
+    crit_g_.add("critic.l4.bias", H_, 1);
+    c2_ = add_linear(crit_g_, "critic.l2", 1, H_);
+    c5_ = add_linear(crit_g_, "critic.l5", 1, H_);
+    RLREP_CHECK(((size_t)H_ * D_) % 4 == 0 && H_ % 4 == 0, "hidden_dim must be a multiple of 4");
+    crit_g_.n_target = crit_g_.n;
+    crit_g_.target_prefix_from = "critic.";
+    crit_g_.target_prefix_to = "critic_target.";
+    crit_g_.want(arena_);
+
+    const size_t BH = (size_t)B_ * H_, BD = (size_t)B_ * D_;
+    arena_.want(&h1_, BH);
+    arena_.want(&h2_, BH);
+    arena_.want(&g1_, BH);
+    arena_.want(&g2_, BH);
+    arena_.want(&zphi_, BD);
+    arena_.want(&zmu_, BD);
+    arena_.want(&dzphi_, BD);
+    arena_.want(&dzmu_, BD);
+    arena_.want(&dh2_, BH);
+    arena_.want(&dh1_, BH);
+    arena_.want(&logits_, (size_t)B_ * B_);
+    arena_.want(&loss_rows_, B_);
+    arena_.want(&rpred_, B_);
+    arena_.want(&drp_, B_);
+    arena_.want(&hid_, 2 * BH);
+    arena_.want(&hid_t_, 2 * BH);
+    arena_.want(&dhid_, 2 * BH);
+    arena_.want(&q1_, B_);
+    arena_.want(&q2_, B_);
+    arena_.want(&nq1_, B_);
+    arena_.want(&nq2_, B_);
+    arena_.want(&dq1_, B_);
+    arena_.want(&dq2_, B_);
+    arena_.want(&a2_act_, (size_t)B_ * A_);
+    arena_.want(&logp2_, B_);
+    finish_setup((size_t)8 << 20);
+
+    names_ = {"total_loss", "model_loss", "r_loss", "q1_loss", "q2_loss", "q1", "q2", "actor_loss", "alpha_loss",
+              "alpha"};
+  }
+
+  int idx_per_train() const override { return K_ * B_; }
+  int eps_per_train() const override { return 2 * B_ * A_; }
+  const std::vector<std::string>& metric_names() const override { return names_; }
+  std::vector<ParamGroup*> groups() override { return {&feat_g_, &actor_g_, &crit_g_}; }
+
+  void sync_targets_from_params() override {
+    RLREP_CUDA(cudaMemcpyAsync(feat_g_.target, feat_g_.p, feat_g_.n_target * 4, cudaMemcpyDeviceToDevice, stream));
+    RLREP_CUDA(cudaMemcpyAsync(crit_g_.target, crit_g_.p, crit_g_.n_target * 4, cudaMemcpyDeviceToDevice, stream));
+    RLREP_CUDA(cudaStreamSynchronize(stream));
+  }
+
+ protected:
+  void update(Ring& ring) override {
+    launch_tick(ctl, base_tick(), stream);
+    for (int k = 0; k < K_; ++k) {
+      launch_gather(ring.data, R_ / 4, idx_dev_ + (size_t)k * B_, B_, batch_, stream);
+      feature_step(k);
+    }
+    critic_step();
+    actor_step();
+  }
+
+ private:
+  Mat sa() const { return Mat{batch_, R_}; }             // cat(s, a): the first S+A floats of each record
+  Mat s2() const { return Mat{batch_ + off_s2_, R_}; }   // next_state
+  const float* reward() const { return batch_ + off_r_; }
+  const float* done() const { return batch_ + off_d_; }
+
+  // phi(x) with x = cat of one or two segments; leaves h1_/h2_ (needed by backward) and writes z [B, D].
+  void phi_forward(Mat x, Mat x2, int k1, float* z) {
+    const Linear l1 = p1_.view(feat_g_), l2 = p2_.view(feat_g_), l3 = p3_.view(feat_g_);
+    linear_fwd(gemm_, stream, B_, x, l1, ACT_ELU, h1_, H_, x2, k1);
+    linear_fwd(gemm_, stream, B_, Mat{h1_, H_}, l2, ACT_ELU, h2_, H_);
+    linear_fwd(gemm_, stream, B_, Mat{h2_, H_}, l3, ACT_NONE, z, D_);
+  }
+
+  void feature_step(int k) {  // ctrlsac_agent.py:213-251
+    const Linear l1 = p1_.view(feat_g_), l2 = p2_.view(feat_g_), l3 = p3_.view(feat_g_);
+    const Linear n1 = m1_.view(feat_g_), n2 = m2_.view(feat_g_), n3 = m3_.view(feat_g_);
+    const Linear th = th_.view(feat_g_);
+    const float inv_b = 1.f / (float)B_;
+    // ---- forward
+    phi_forward(sa(), Mat(), 0, zphi_);
+    linear_fwd(gemm_, stream, B_, s2(), n1, ACT_ELU, g1_, H_);
+    linear_fwd(gemm_, stream, B_, Mat{g1_, H_}, n2, ACT_ELU, g2_, H_);
+    linear_fwd(gemm_, stream, B_, Mat{g2_, H_}, n3, ACT_TANH, zmu_, D_);
+    {  // logits[i, j] = <phi_i, mu_j>  (the reference's [B,1,D]*[1,B,D] broadcast, :229, as a tensor-core GEMM)
+      GemmArgs a;
+      a.M = B_; a.N = B_; a.K = D_;
+      a.A = zphi_; a.lda = D_;
+      a.B = zmu_; a.ldb = D_;
+      a.C = logits_; a.ldc = B_;
+      gemm_.run(a, stream);
+    }
+    launch_ce_rows(logits_, B_, B_, B_, 0, inv_b, loss_rows_, stream);  // logits_ now holds dL/dlogits
+    launch_rowdot(zphi_, D_, B_, D_, th.W, th.b, rpred_, stream);
+    launch_feature_loss_finalize(loss_rows_, B_, rpred_, reward(), R_, inv_b, drp_, metrics_dev_ + 0, stream);
+    // ---- backward into the embeddings
+    {  // d z_phi = G mu + drp (x) theta.w
+      GemmArgs a;
+      a.M = B_; a.N = D_; a.K = B_;
+      a.A = logits_; a.lda = B_;
+      a.B = zmu_; a.ldb = D_; a.b_mn = true;
+      a.C = dzphi_; a.ldc = D_;
+      a.epi.r1_u = drp_; a.epi.r1_v = th.W;
+      gemm_.run(a, stream);
+    }
+    {  // d (pre-tanh mu) = (G^T phi) * (1 - mu^2)
+      GemmArgs a;
+      a.M = B_; a.N = D_; a.K = B_;
+      a.A = logits_; a.lda = B_; a.a_mn = true;
+      a.B = zphi_; a.ldb = D_; a.b_mn = true;
+      a.C = dzmu_; a.ldc = D_;
+      a.epi.dact = DACT_TANH_OUT; a.epi.aux = zmu_; a.epi.ld_aux = D_;
+      gemm_.run(a, stream);
+    }
+    launch_colreduce(zphi_, D_, B_, D_, drp_, th.dW, 0, stream);  // d theta.w
+    launch_colreduce(drp_, 1, B_, 1, nullptr, th.db, 0, stream);  // d theta.b
+    // ---- phi backward
+    linear_wgrad(gemm_, stream, B_, Mat{dzphi_, D_}, Mat{h2_, H_}, l3);
+    linear_dgrad(gemm_, stream, B_, Mat{dzphi_, D_}, l3, DACT_ELU_OUT, Mat{h2_, H_}, dh2_, H_);
+    linear_wgrad(gemm_, stream, B_, Mat{dh2_, H_}, Mat{h1_, H_}, l2);
+    linear_dgrad(gemm_, stream, B_, Mat{dh2_, H_}, l2, DACT_ELU_OUT, Mat{h1_, H_}, dh1_, H_);
+    linear_wgrad(gemm_, stream, B_, Mat{dh1_, H_}, sa(), l1);
+    // ---- mu backward
+    linear_wgrad(gemm_, stream, B_, Mat{dzmu_, D_}, Mat{g2_, H_}, n3);
+    linear_dgrad(gemm_, stream, B_, Mat{dzmu_, D_}, n3, DACT_ELU_OUT, Mat{g2_, H_}, dh2_, H_);
+    linear_wgrad(gemm_, stream, B_, Mat{dh2_, H_}, Mat{g1_, H_}, n2);
+    linear_dgrad(gemm_, stream, B_, Mat{dh2_, H_}, n2, DACT_ELU_OUT, Mat{g1_, H_}, dh1_, H_);
+    linear_wgrad(gemm_, stream, B_, Mat{dh1_, H_}, s2(), n1);
+    // ---- one fused Adam over phi | mu | theta, plus Polyak of phi_target (:242-244, :253-255)
+    launch_adam_polyak(feat_g_.p, feat_g_.g, feat_g_.m, feat_g_.v, feat_g_.n, &ctl->feat[k],
+                       cfg.use_feature_target ? feat_g_.target : nullptr, feat_g_.n_target, cfg.feature_tau, nullptr,
+                       stream);
+  }
+
+  // twin heads on features z: hid = elu(z [l1|l4]^T + b), q1 = hid[:, :H] . l2, q2 = hid[:, H:] . l5
+  void critic_forward(const float* z, bool target, float* hid, float* q1, float* q2) {
+    const Linear l14 = c14_.view(crit_g_, target), l2 = c2_.view(crit_g_, target), l5 = c5_.view(crit_g_, target);
+    linear_fwd(gemm_, stream, B_, Mat{z, D_}, l14, ACT_ELU, hid, 2 * H_);
+    launch_rowdot(hid, 2 * H_, B_, H_, l2.W, l2.b, q1, stream);
+    launch_rowdot(hid + H_, 2 * H_, B_, H_, l5.W, l5.b, q2, stream);
+  }
+  // d hid from (dq1, dq2) through the N = 1 heads and the ELU
+  void critic_heads_backward_to_hidden() {
+    const Linear l2 = c2_.view(crit_g_), l5 = c5_.view(crit_g_);
+    launch_outer_dact(dq1_, l2.W, B_, H_, hid_, 2 * H_, DACT_ELU_OUT, dhid_, 2 * H_, stream);
+    launch_outer_dact(dq2_, l5.W, B_, H_, hid_ + H_, 2 * H_, DACT_ELU_OUT, dhid_ + H_, 2 * H_, stream);
+  }
+
+  void critic_step() {  // ctrlsac_agent.py:257-293
+    const float* eps = eps_dev_;
+    actor_forward(s2(), eps, a2_act_, logp2_);                     // a' ~ pi(s'), log pi(a'|s')
+    phi_forward(s2(), Mat{a2_act_, A_}, S_, zmu_);                 // frozen_phi_target(s', a')  (zmu_ is free now)
+    critic_forward(zmu_, /*target=*/true, hid_t_, nq1_, nq2_);
+    phi_forward(sa(), Mat(), 0, zphi_);                            // frozen_phi_target(s, a)
+    critic_forward(zphi_, /*target=*/false, hid_, q1_, q2_);
+    launch_td_critic_loss(reward(), done(), R_, nq1_, nq2_, logp2_, q1_, q2_, B_, cfg.discount, ctl, dq1_, dq2_,
+                          metrics_dev_ + 3, stream);
+    // ---- backward (critic parameters only; the features are under no_grad)
+    const Linear l14 = c14_.view(crit_g_), l2 = c2_.view(crit_g_), l5 = c5_.view(crit_g_);
+    critic_heads_backward_to_hidden();
+    launch_colreduce(hid_, 2 * H_, B_, H_, dq1_, l2.dW, 0, stream);
+    launch_colreduce(dq1_, 1, B_, 1, nullptr, l2.db, 0, stream);
+    launch_colreduce(hid_ + H_, 2 * H_, B_, H_, dq2_, l5.dW, 0, stream);
+    launch_colreduce(dq2_, 1, B_, 1, nullptr, l5.db, 0, stream);
+    linear_wgrad(gemm_, stream, B_, Mat{dhid_, 2 * H_}, Mat{zphi_, D_}, l14);
+    // Adam on the critic; its Polyak (sac_agent.py:99-102, every `period` steps) only reads the updated critic and
+    // nothing between here and the end of train() writes it, so it rides in the same launch.
+    launch_adam_polyak(crit_g_.p, crit_g_.g, crit_g_.m, crit_g_.v, crit_g_.n, &ctl->critic, crit_g_.target,
+                       crit_g_.n_target, cfg.tau, &ctl->polyak_critic, stream);
+  }
+
+  void actor_step() {  // ctrlsac_agent.py:295-325
+    const float* eps = eps_dev_ + (size_t)B_ * A_;
+    const Mat s{batch_, R_};
+    actor_forward(s, eps, action_, logp_);
+    phi_forward(s, Mat{action_, A_}, S_, zphi_);  // frozen_phi(s, a_pi)
+    critic_forward(zphi_, false, hid_, q1_, q2_);
+    launch_actor_alpha_loss(q1_, q2_, logp_, B_, (float)(-A_), cfg.learn_alpha, ctl, dq1_, dq2_, dlogp_,
+                            metrics_dev_ + 7, stream);
+    // ---- dgrad only, back to the action input of phi
+    const Linear l14 = c14_.view(crit_g_);
+    const Linear l1 = p1_.view(feat_g_), l2 = p2_.view(feat_g_), l3 = p3_.view(feat_g_);
+    critic_heads_backward_to_hidden();
+    linear_dgrad(gemm_, stream, B_, Mat{dhid_, 2 * H_}, l14, DACT_NONE, Mat(), dzphi_, D_);
+    linear_dgrad(gemm_, stream, B_, Mat{dzphi_, D_}, l3, DACT_ELU_OUT, Mat{h2_, H_}, dh2_, H_);
+    linear_dgrad(gemm_, stream, B_, Mat{dh2_, H_}, l2, DACT_ELU_OUT, Mat{h1_, H_}, dh1_, H_);
+    linear_dgrad(gemm_, stream, B_, Mat{dh1_, H_}, l1, DACT_NONE, Mat(), d_action_, A_, /*col0=*/S_, /*n_cols=*/A_);
+    actor_backward(s, eps);
+    actor_adam();
+  }
+
+  int H_ = 0, D_ = 0, K_ = 0, off_r_ = 0, off_d_ = 0, off_s2_ = 0;
+  ParamGroup feat_g_, crit_g_;
+  LinearSlot p1_, p2_, p3_, m1_, m2_, m3_, th_, c14_, c2_, c5_;
+  float *h1_ = nullptr, *h2_ = nullptr, *g1_ = nullptr, *g2_ = nullptr, *zphi_ = nullptr, *zmu_ = nullptr;
+  float *dzphi_ = nullptr, *dzmu_ = nullptr, *dh2_ = nullptr, *dh1_ = nullptr, *logits_ = nullptr;
+  float *loss_rows_ = nullptr, *rpred_ = nullptr, *drp_ = nullptr, *hid_ = nullptr, *hid_t_ = nullptr,
+        *dhid_ = nullptr;
+  float *q1_ = nullptr, *q2_ = nullptr, *nq1_ = nullptr, *nq2_ = nullptr, *dq1_ = nullptr, *dq2_ = nullptr;
+  float *a2_act_ = nullptr, *logp2_ = nullptr;
+  std::vector<std::string> names_;
+};
+
+}  // namespace
+
+std::unique_ptr<Agent> make_ctrlsac_agent(const AgentConfig& cfg, cudaStream_t s) {
+  return std::unique_ptr<Agent>(new CtrlSacAgent(cfg, s));
+}
+
+}  // namespace rlrep

@@ -1,6 +1,11 @@
 // extern "C" surface of librlrep_b200.so (declared in include/rlrep_b200.h).
+#include <algorithm>
+#include <cmath>
+#include <memory>
 #include <string>
+#include <vector>
 
+#include "agent.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
 #include "rlrep_b200.h"
@@ -31,6 +36,37 @@ Epilogue to_epilogue(const rlrep_epilogue* e) {
 }  // namespace rlrep
 
 using namespace rlrep;
+
+struct rlrep_ring {
+  std::unique_ptr<Ring> impl;
+};
+
+struct TensorRef {
+  std::string name;
+  float* ptr;
+  int rows, cols;
+};
+
+struct rlrep_agent {
+  std::unique_ptr<Agent> impl;
+  std::vector<TensorRef> tensors;
+  cudaStream_t owned_stream = nullptr;  // created when the caller passed the (uncapturable) legacy default stream
+};
+
+static void index_tensors(rlrep_agent* a) {
+  a->tensors.clear();
+  for (ParamGroup* g : a->impl->groups()) {
+    for (const ParamTensor& t : g->tensors) a->tensors.push_back({t.name, g->p + t.offset, t.rows, t.cols});
+    if (g->target) {
+      for (const ParamTensor& t : g->tensors) {
+        if (t.offset >= g->n_target) continue;
+        if (t.name.compare(0, g->target_prefix_from.size(), g->target_prefix_from) != 0) continue;
+        a->tensors.push_back({g->target_prefix_to + t.name.substr(g->target_prefix_from.size()), g->target + t.offset,
+                              t.rows, t.cols});
+      }
+    }
+  }
+}
 
 extern "C" {
 
@@ -74,26 +110,253 @@ int rlrep_gemm_bench(void* stream, int path, int M, int N, int K, const float* A
   cudaEvent_t e0, e1;
   RLREP_CUDA(cudaEventCreate(&e0));
   RLREP_CUDA(cudaEventCreate(&e1));
+  TcGemmPlan p;
   if (path == 0) {
-    TcGemmPlan p = make_tc_plan(g, bn, split_k, ws, ws_floats);
+    p = make_tc_plan(g, bn, split_k, ws, ws_floats);
     if (bn_out) *bn_out = p.bn;
     if (split_out) *split_out = p.split_k;
-    for (int i = 0; i < 3; ++i) launch_tc(p, st);
-    RLREP_CUDA(cudaEventRecord(e0, st));
-    for (int i = 0; i < iters; ++i) launch_tc(p, st);
-    RLREP_CUDA(cudaEventRecord(e1, st));
-  } else {
-    for (int i = 0; i < 3; ++i) launch_simt(g, st);
-    RLREP_CUDA(cudaEventRecord(e0, st));
-    for (int i = 0; i < iters; ++i) launch_simt(g, st);
-    RLREP_CUDA(cudaEventRecord(e1, st));
   }
+  auto launch_once = [&](cudaStream_t s) {
+    if (path == 0) launch_tc(p, s);
+    else launch_simt(g, s);
+  };
+  for (int i = 0; i < 3; ++i) launch_once(st);
+  // Replay through a CUDA graph so the number is device time, not the host's launch rate.
+  cudaStream_t cs;
+  RLREP_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  cudaGraph_t graph;
+  cudaGraphExec_t exec;
+  RLREP_CUDA(cudaStreamSynchronize(st));
+  RLREP_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+  for (int i = 0; i < iters; ++i) launch_once(cs);
+  RLREP_CUDA(cudaStreamEndCapture(cs, &graph));
+  RLREP_CUDA(cudaGraphInstantiate(&exec, graph, 0));
+  RLREP_CUDA(cudaGraphLaunch(exec, cs));
+  RLREP_CUDA(cudaEventRecord(e0, cs));
+  RLREP_CUDA(cudaGraphLaunch(exec, cs));
+  RLREP_CUDA(cudaEventRecord(e1, cs));
+  RLREP_CUDA(cudaStreamSynchronize(cs));
+  cudaGraphExecDestroy(exec);
+  cudaGraphDestroy(graph);
+  cudaStreamDestroy(cs);
   RLREP_CUDA(cudaEventSynchronize(e1));
   float ms = 0.f;
   RLREP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
   *ms_out = ms / iters;
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+  RLREP_API_END
+}
+
+// ------------------------------------------------------------------------------------------------ ring
+int rlrep_ring_create(int state_dim, int action_dim, long long capacity, rlrep_ring** out) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(out != nullptr, "null out pointer");
+  std::unique_ptr<rlrep_ring> r(new rlrep_ring);
+  r->impl.reset(new Ring(state_dim, action_dim, capacity));
+  *out = r.release();
+  RLREP_API_END
+}
+int rlrep_ring_destroy(rlrep_ring* ring) {
+  RLREP_API_BEGIN
+  delete ring;
+  RLREP_API_END
+}
+int rlrep_ring_layout(const rlrep_ring* ring, int* record_floats, int* off_action, int* off_reward, int* off_done,
+                      int* off_next_state) {
+  RLREP_API_BEGIN
+  const Ring& r = *ring->impl;
+  *record_floats = r.R; *off_action = r.off_a; *off_reward = r.off_r; *off_done = r.off_d; *off_next_state = r.off_s2;
+  RLREP_API_END
+}
+int rlrep_ring_state(const rlrep_ring* ring, long long* size, long long* ptr, long long* capacity) {
+  RLREP_API_BEGIN
+  *size = ring->impl->size; *ptr = ring->impl->ptr; *capacity = ring->impl->capacity;
+  RLREP_API_END
+}
+int rlrep_ring_add_packed(rlrep_ring* ring, const float* rows_host, int n, void* stream) {
+  RLREP_API_BEGIN
+  ring->impl->add_packed(rows_host, n, static_cast<cudaStream_t>(stream));
+  RLREP_API_END
+}
+int rlrep_ring_load(rlrep_ring* ring, const void* state, const void* action, const void* next_state,
+                    const void* reward, const void* done, long long n, int is_f64, void* stream) {
+  RLREP_API_BEGIN
+  ring->impl->load_columns(state, action, next_state, reward, done, n, is_f64, static_cast<cudaStream_t>(stream));
+  RLREP_API_END
+}
+int rlrep_ring_gather(rlrep_ring* ring, const int64_t* idx_host, int B, float* out_dev, void* stream) {
+  RLREP_API_BEGIN
+  ring->impl->gather_from_host_idx(reinterpret_cast<const long long*>(idx_host), B, out_dev,
+                                   static_cast<cudaStream_t>(stream));
+  RLREP_API_END
+}
+
+// ------------------------------------------------------------------------------------------------ agents
+int rlrep_agent_create(const rlrep_agent_config* c, void* stream, rlrep_agent** out) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(c != nullptr && out != nullptr, "null argument");
+  AgentConfig a;
+  a.alg = c->alg;
+  a.state_dim = c->state_dim; a.action_dim = c->action_dim; a.batch = c->batch_size;
+  a.hidden_dim = c->hidden_dim; a.feature_dim = c->feature_dim; a.actor_hidden_dim = c->actor_hidden_dim;
+  a.k_feat = c->feature_steps;
+  a.lr = c->lr_critic; a.lr_feat = c->lr_feature; a.lr_actor = c->lr_actor; a.lr_alpha = c->lr_alpha;
+  a.discount = c->discount; a.tau = c->tau; a.feature_tau = c->feature_tau;
+  a.alpha0 = c->alpha;
+  a.target_update_period = c->target_update_period;
+  a.learn_alpha = c->auto_entropy_tuning;
+  a.use_feature_target = c->use_feature_target;
+  a.precision = c->precision;
+  a.use_graph = c->use_cuda_graph;
+  a.phi_hidden_dim = c->phi_hidden_dim; a.phi_hidden_depth = c->phi_hidden_depth;
+  a.mu_hidden_dim = c->mu_hidden_dim; a.mu_hidden_depth = c->mu_hidden_depth;
+  a.nabla_hidden_dim = c->nabla_mu_hidden_dim; a.nabla_hidden_depth = c->nabla_mu_hidden_depth;
+  a.num_noise = c->num_noise; a.num_noises = c->num_noises;
+  a.sigma_scale = c->sigma_scale_factor;
+  RLREP_CHECK(a.target_update_period > 0, "target_update_period must be positive");
+  std::unique_ptr<rlrep_agent> h(new rlrep_agent);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (st == nullptr) {
+    // The legacy default stream cannot be captured into a CUDA graph: give the handle a private stream.  Every
+    // entry point that hands results back to the host synchronises it, so callers never observe the difference.
+    RLREP_CUDA(cudaStreamCreateWithFlags(&h->owned_stream, cudaStreamNonBlocking));
+    st = h->owned_stream;
+  }
+  switch (a.alg) {
+    case RLREP_ALG_SAC: h->impl = make_sac_agent(a, st); break;
+    case RLREP_ALG_CTRLSAC: h->impl = make_ctrlsac_agent(a, st); break;
+    default: throw Error("algorithm not implemented in this build");
+  }
+  index_tensors(h.get());
+  *out = h.release();
+  RLREP_API_END
+}
+int rlrep_agent_destroy(rlrep_agent* agent) {
+  RLREP_API_BEGIN
+  if (agent && agent->impl) cudaStreamSynchronize(agent->impl->stream);
+  if (agent) {
+    agent->impl.reset();
+    if (agent->owned_stream) cudaStreamDestroy(agent->owned_stream);
+  }
+  delete agent;
+  RLREP_API_END
+}
+int rlrep_agent_num_tensors(rlrep_agent* agent, int* n) {
+  RLREP_API_BEGIN
+  *n = (int)agent->tensors.size();
+  RLREP_API_END
+}
+int rlrep_agent_tensor_info(rlrep_agent* agent, int i, const char** name, float** ptr_dev, int* rows, int* cols) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(i >= 0 && i < (int)agent->tensors.size(), "tensor index out of range");
+  const TensorRef& t = agent->tensors[i];
+  if (name) *name = t.name.c_str();
+  if (ptr_dev) *ptr_dev = t.ptr;
+  if (rows) *rows = t.rows;
+  if (cols) *cols = t.cols;
+  RLREP_API_END
+}
+int rlrep_agent_tensor_read(rlrep_agent* agent, int i, float* out_host) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(i >= 0 && i < (int)agent->tensors.size(), "tensor index out of range");
+  const TensorRef& t = agent->tensors[i];
+  cudaStream_t st = agent->impl->stream;
+  RLREP_CUDA(cudaMemcpyAsync(out_host, t.ptr, (size_t)t.rows * t.cols * 4, cudaMemcpyDeviceToHost, st));
+  RLREP_CUDA(cudaStreamSynchronize(st));
+  RLREP_API_END
+}
+int rlrep_agent_tensor_write(rlrep_agent* agent, int i, const float* in_host) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(i >= 0 && i < (int)agent->tensors.size(), "tensor index out of range");
+  const TensorRef& t = agent->tensors[i];
+  cudaStream_t st = agent->impl->stream;
+  RLREP_CUDA(cudaMemcpyAsync(t.ptr, in_host, (size_t)t.rows * t.cols * 4, cudaMemcpyHostToDevice, st));
+  RLREP_CUDA(cudaStreamSynchronize(st));
+  RLREP_API_END
+}
+int rlrep_agent_get_log_alpha(rlrep_agent* agent, double* log_alpha) {
+  RLREP_API_BEGIN
+  Control h;
+  RLREP_CUDA(cudaMemcpyAsync(&h, agent->impl->ctl, sizeof(h), cudaMemcpyDeviceToHost, agent->impl->stream));
+  RLREP_CUDA(cudaStreamSynchronize(agent->impl->stream));
+  *log_alpha = h.log_alpha;
+  RLREP_API_END
+}
+int rlrep_agent_set_log_alpha(rlrep_agent* agent, double log_alpha) {
+  RLREP_API_BEGIN
+  Control h;
+  cudaStream_t st = agent->impl->stream;
+  RLREP_CUDA(cudaMemcpyAsync(&h, agent->impl->ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
+  RLREP_CUDA(cudaStreamSynchronize(st));
+  h.log_alpha = log_alpha;
+  h.alpha = (float)std::exp(log_alpha);
+  RLREP_CUDA(cudaMemcpyAsync(agent->impl->ctl, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+  RLREP_CUDA(cudaStreamSynchronize(st));
+  RLREP_API_END
+}
+int rlrep_agent_get_steps(rlrep_agent* agent, int* steps) {
+  RLREP_API_BEGIN
+  Control h;
+  RLREP_CUDA(cudaMemcpyAsync(&h, agent->impl->ctl, sizeof(h), cudaMemcpyDeviceToHost, agent->impl->stream));
+  RLREP_CUDA(cudaStreamSynchronize(agent->impl->stream));
+  *steps = h.steps;
+  RLREP_API_END
+}
+int rlrep_agent_train_counts(rlrep_agent* agent, int* n_idx, int* n_eps, int* n_metrics) {
+  RLREP_API_BEGIN
+  *n_idx = agent->impl->idx_per_train();
+  *n_eps = agent->impl->eps_per_train();
+  *n_metrics = (int)agent->impl->metric_names().size();
+  RLREP_API_END
+}
+const char* rlrep_agent_metric_name(rlrep_agent* agent, int i) {
+  const auto& names = agent->impl->metric_names();
+  if (i < 0 || i >= (int)names.size()) return nullptr;
+  return names[i].c_str();
+}
+int rlrep_agent_train(rlrep_agent* agent, rlrep_ring* ring, const int64_t* idx_host, int n_idx, const float* eps_host,
+                      int n_eps, float* metrics_host, int n_metrics) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(agent && ring && idx_host && eps_host && metrics_host, "null argument");
+  agent->impl->train(*ring->impl, reinterpret_cast<const long long*>(idx_host), n_idx, eps_host, n_eps, metrics_host,
+                     n_metrics);
+  RLREP_API_END
+}
+int rlrep_agent_act(rlrep_agent* agent, const float* state_host, const float* eps_host, float* action_host) {
+  RLREP_API_BEGIN
+  agent->impl->act(state_host, eps_host, action_host);
+  RLREP_API_END
+}
+int rlrep_agent_last_launches(rlrep_agent* agent, int* launches) {
+  RLREP_API_BEGIN
+  *launches = agent->impl->last_launches;
+  RLREP_API_END
+}
+int rlrep_agent_train_resident(rlrep_agent* agent, rlrep_ring* ring, const int64_t* idx_host, const float* eps_host,
+                               int n_steps, float* total_ms) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(agent && ring && idx_host && eps_host && total_ms, "null argument");
+  *total_ms = agent->impl->train_resident(*ring->impl, reinterpret_cast<const long long*>(idx_host), eps_host, n_steps);
+  RLREP_API_END
+}
+int rlrep_agent_profile_train(rlrep_agent* agent, rlrep_ring* ring, const int64_t* idx_host, const float* eps_host,
+                              int max_entries, const char** names, float* ms, int* n_entries) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(agent && ring && idx_host && eps_host && names && ms && n_entries, "null argument");
+  std::vector<ProfileEntry> prof =
+      agent->impl->profile_train(*ring->impl, reinterpret_cast<const long long*>(idx_host), eps_host);
+  const int n = (int)std::min<size_t>(prof.size(), (size_t)max_entries);
+  for (int i = 0; i < n; ++i) {
+    names[i] = prof[i].name;  // string literals with static storage
+    ms[i] = prof[i].ms;
+  }
+  *n_entries = (int)prof.size();
+  RLREP_API_END
+}
+int rlrep_agent_sync_targets(rlrep_agent* agent) {
+  RLREP_API_BEGIN
+  agent->impl->sync_targets_from_params();
   RLREP_API_END
 }
 

@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <stdexcept>
 #include <string>
+#include <vector>
 
 namespace rlrep {
 
@@ -35,7 +36,23 @@ const char* get_last_error();
     }                                                                                                    \
   } while (0)
 
-#define RLREP_LAUNCH_CHECK() RLREP_CUDA(cudaGetLastError())
+// Every kernel launch goes through this: checks the launch, counts it (bench.py reports gpu_launches) and, when a
+// profile is being recorded, drops a CUDA event behind it so per-kernel device time can be read back.
+void note_launch(const char* name, cudaStream_t stream);
+long long launch_count();
+#define RLREP_LAUNCHED(name, stream)          \
+  do {                                        \
+    RLREP_CUDA(cudaGetLastError());           \
+    ::rlrep::note_launch(name, stream);       \
+  } while (0)
+
+// Per-kernel timing of an eager (non-graph) launch sequence: begin, run the launches, end -> (name, ms) per launch.
+void profile_begin(cudaStream_t stream);
+struct ProfileEntry {
+  const char* name;
+  float ms;
+};
+std::vector<ProfileEntry> profile_end(cudaStream_t stream);
 
 // Wrap a C-ABI body: exceptions become error code + message.
 #define RLREP_API_BEGIN try {

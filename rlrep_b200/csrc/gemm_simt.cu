@@ -111,7 +111,7 @@ void launch_simt(const GemmArgs& a, cudaStream_t stream) {
   p.ldc = a.ldc;
   dim3 grid(ceil_div(a.N, TBN), ceil_div(a.M, TBM));
   gemm_simt_kernel<<<grid, 256, 0, stream>>>(p, a.epi);
-  RLREP_LAUNCH_CHECK();
+  RLREP_LAUNCHED("gemm_simt", stream);
 }
 
 }  // namespace rlrep

@@ -252,7 +252,7 @@ void launch_variant(const TcGemmPlan& p, cudaStream_t stream) {
   dim3 grid(ceil_div(a.N, BN), ceil_div(a.M, BM), p.split_k);
   kern<<<grid, kThreads, smem_bytes(BN), stream>>>(p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, a.K, p.kb_per_split, p.ws,
                                                    a.epi);
-  RLREP_LAUNCH_CHECK();
+  RLREP_LAUNCHED("gemm_tf32", stream);
 }
 
 template <int BN>
@@ -315,7 +315,7 @@ void launch_tc(const TcGemmPlan& p, cudaStream_t stream) {
     int blocks = (int)((total + 255) / 256);
     if (blocks > kNumSMs * 8) blocks = kNumSMs * 8;
     splitk_reduce_kernel<<<blocks, 256, 0, stream>>>(p.ws, p.split_k, a.M, a.N, a.C, a.ldc, a.epi);
-    RLREP_LAUNCH_CHECK();
+    RLREP_LAUNCHED("splitk_reduce", stream);
   }
 }
 

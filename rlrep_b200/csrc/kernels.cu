@@ -1,0 +1,485 @@
+// Non-GEMM kernels of the update step.  See kernels.cuh for the contract of each launcher.
+#include <cmath>
+
+#include "common.cuh"
+#include "epilogue.cuh"
+#include "kernels.cuh"
+
+namespace rlrep {
+
+namespace {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// Block-wide sum, result valid in every thread.  Fixed reduction tree => deterministic.
+template <int kThreads>
+__device__ __forceinline__ float block_sum(float v, float* scratch /* >= 33 floats */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < kThreads / 32 ? scratch[lane] : 0.f;
+    t = warp_sum(t);
+    if (lane == 0) scratch[32] = t;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+template <int kThreads>
+__device__ __forceinline__ float block_max(float v, float* scratch) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_max(v);
+  __syncthreads();
+  if (lane == 0) scratch[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    float t = lane < kThreads / 32 ? scratch[lane] : -INFINITY;
+    t = warp_max(t);
+    if (lane == 0) scratch[32] = t;
+  }
+  __syncthreads();
+  return scratch[32];
+}
+
+// ------------------------------------------------------------------------------------------- tick
+__device__ __forceinline__ AdamHyper adam_hyper(double lr, long long t) {
+  // torch.optim.Adam (single-tensor path): step_size = lr / (1 - beta1^t); denom uses sqrt(1 - beta2^t).
+  const double bc1 = 1.0 - pow(0.9, (double)t);
+  const double bc2 = 1.0 - pow(0.999, (double)t);
+  AdamHyper h;
+  h.step_size = (float)(lr / bc1);
+  h.bc2_sqrt = (float)sqrt(bc2);
+  return h;
+}
+
+__global__ void tick_kernel(Control* c, const TickParams p) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  c->steps += 1;
+  c->polyak_critic = (c->steps % p.period == 0) ? 1 : 0;
+  for (int k = 0; k < p.k_feat; ++k) {
+    c->t_feat += 1;
+    c->feat[k] = adam_hyper(p.lr_feat, c->t_feat);
+  }
+  if (p.critic_steps) {
+    c->t_critic += 1;
+    c->critic = adam_hyper(p.lr_critic, c->t_critic);
+  }
+  c->t_actor += 1;
+  c->actor = adam_hyper(p.lr_actor, c->t_actor);
+  c->t_alpha += 1;
+  c->alpha_step_size = p.lr_alpha / (1.0 - pow(0.9, (double)c->t_alpha));
+  c->alpha_bc2_sqrt = sqrt(1.0 - pow(0.999, (double)c->t_alpha));
+  c->alpha = (float)exp(c->log_alpha);
+}
+
+// ------------------------------------------------------------------------------------------- ring
+__global__ void gather_kernel(const float4* __restrict__ ring, int rec4, const long long* __restrict__ idx, int B,
+                              float4* __restrict__ out) {
+  const int total = B * rec4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / rec4, c = i - b * rec4;
+    out[i] = __ldg(ring + (size_t)idx[b] * rec4 + c);
+  }
+}
+__global__ void ring_write_kernel(float4* __restrict__ ring, int rec4, long long capacity, long long start,
+                                  const float4* __restrict__ rows, int n) {
+  const int total = n * rec4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / rec4, c = i - b * rec4;
+    ring[(size_t)((start + b) % capacity) * rec4 + c] = rows[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------- contrastive CE
+// One CTA per row: online max/sum pass, then rewrite the row as the CE gradient.
+__global__ void __launch_bounds__(256) ce_rows_kernel(float* __restrict__ logits, int ld, int cols, int diag_off,
+                                                      float inv_batch, float* __restrict__ loss_rows) {
+  __shared__ float scratch[33];
+  const int row = blockIdx.x;
+  float* l = logits + (size_t)row * ld;
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < cols; j += 256) mx = fmaxf(mx, l[j]);
+  mx = block_max<256>(mx, scratch);
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < cols; j += 256) sum += expf(l[j] - mx);
+  sum = block_sum<256>(sum, scratch);
+  const float lse = mx + logf(sum);
+  const int dj = diag_off + row;
+  if (threadIdx.x == 0) loss_rows[row] = lse - l[dj];
+  __syncthreads();
+  for (int j = threadIdx.x; j < cols; j += 256) {
+    const float pr = expf(l[j] - lse);
+    l[j] = (pr - (j == dj ? 1.f : 0.f)) * inv_batch;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- N = 1 heads
+__global__ void rowdot_kernel(const float* __restrict__ X, int ld, int rows, int D, const float* __restrict__ w,
+                              const float* __restrict__ b, float* __restrict__ y) {
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (warp >= rows) return;
+  const float* x = X + (size_t)warp * ld;
+  float acc = 0.f;
+  for (int j = lane; j < D; j += 32) acc = fmaf(x[j], __ldg(w + j), acc);
+  acc = warp_sum(acc);
+  if (lane == 0) y[warp] = acc + (b ? __ldg(b) : 0.f);
+}
+
+// 32 columns x 8 row-slices per CTA; fixed-order smem reduction across the slices.
+__global__ void __launch_bounds__(256) colreduce_kernel(const float* __restrict__ X, int ld, int rows, int cols,
+                                                        const float* __restrict__ u, float* __restrict__ out,
+                                                        int accumulate) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  if (j < cols) {
+    for (int i = ty; i < rows; i += 8) {
+      const float x = X[(size_t)i * ld + j];
+      acc = u ? fmaf(__ldg(u + i), x, acc) : acc + x;
+    }
+  }
+  part[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && j < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][tx];
+    out[j] = accumulate ? out[j] + t : t;
+  }
+}
+
+__global__ void outer_dact_kernel(const float* __restrict__ u, const float* __restrict__ w, int rows, int cols,
+                                  const float* __restrict__ aux, int ld_aux, int dact, float* __restrict__ out,
+                                  int ld_out) {
+  const size_t total = (size_t)rows * cols;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / cols), c = (int)(i - (size_t)r * cols);
+    float v = __ldg(u + r) * __ldg(w + c);
+    if (dact != DACT_NONE) v *= apply_dact(aux[(size_t)r * ld_aux + c], dact);
+    out[(size_t)r * ld_out + c] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- feature loss
+__global__ void __launch_bounds__(256) feature_loss_finalize_kernel(const float* __restrict__ loss_rows, int rows,
+                                                                    const float* __restrict__ pred,
+                                                                    const float* __restrict__ reward, int ld_r,
+                                                                    float inv_batch, float* __restrict__ dpred,
+                                                                    float* __restrict__ metrics) {
+  __shared__ float scratch[33];
+  float ce = 0.f, se = 0.f;
+  for (int i = threadIdx.x; i < rows; i += 256) {
+    ce += loss_rows[i];
+    const float d = pred[i] - reward[(size_t)i * ld_r];
+    se = fmaf(d, d, se);
+    dpred[i] = d * inv_batch;
+  }
+  ce = block_sum<256>(ce, scratch);
+  se = block_sum<256>(se, scratch);
+  if (threadIdx.x == 0) {
+    const float model = ce * inv_batch;
+    const float r = 0.5f * (se * inv_batch);
+    metrics[0] = model + r;
+    metrics[1] = model;
+    metrics[2] = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------- actor
+constexpr float kLogStdMin = -5.f, kLogStdMax = 2.f;  // sac_agent.py:64
+
+__global__ void actor_sample_kernel(const float* __restrict__ head, int B, int A, const float* __restrict__ eps,
+                                    float* __restrict__ action, int lda, float* __restrict__ logp) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const float* h = head + (size_t)b * 2 * A;
+  float lp = 0.f;
+  for (int j = 0; j < A; ++j) {
+    const float mu = h[j];
+    const float ls = kLogStdMin + 0.5f * (kLogStdMax - kLogStdMin) * (tanhf(h[A + j]) + 1.f);
+    const float sd = expf(ls);
+    const float u = mu + eps[(size_t)b * A + j] * sd;
+    const float d = u - mu;
+    // Normal.log_prob: -(u-mu)^2 / (2 var) - log(std) - log(sqrt(2 pi))
+    const float base = -(d * d) / (2.f * sd * sd) - logf(sd) - 0.91893853320467267f;
+    // TanhTransform.log_abs_det_jacobian: 2 (log 2 - u - softplus(-2u)), softplus with torch's threshold 20
+    const float z = -2.f * u;
+    const float sp = z > 20.f ? z : log1pf(expf(z));
+    const float ladj = 2.f * (0.69314718055994531f - u - sp);
+    lp += -ladj + base;
+    action[(size_t)b * lda + j] = tanhf(u);
+  }
+  logp[b] = lp;
+}
+
+__global__ void actor_sample_bwd_kernel(const float* __restrict__ head, int B, int A, const float* __restrict__ eps,
+                                        const float* __restrict__ d_action, int ldd,
+                                        const float* __restrict__ dlogp_scalar, float* __restrict__ dhead) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * A) return;
+  const int b = i / A, j = i - b * A;
+  const float* h = head + (size_t)b * 2 * A;
+  const float glp = *dlogp_scalar;
+  const float mu = h[j];
+  const float t = tanhf(h[A + j]);
+  const float ls = kLogStdMin + 0.5f * (kLogStdMax - kLogStdMin) * (t + 1.f);
+  const float sd = expf(ls);
+  const float e = eps[i];
+  const float a = tanhf(mu + e * sd);
+  // dL/du: through a = tanh(u) and through log pi (d(-ladj)/du = 2 tanh(u); the Gaussian term cancels)
+  const float du = d_action[(size_t)b * ldd + j] * (1.f - a * a) + glp * 2.f * a;
+  const float dsd = du * e - glp / sd;
+  dhead[(size_t)b * 2 * A + j] = du;
+  dhead[(size_t)b * 2 * A + A + j] = dsd * sd * (0.5f * (kLogStdMax - kLogStdMin)) * (1.f - t * t);
+}
+
+// ------------------------------------------------------------------------------------------- critic loss
+__global__ void __launch_bounds__(256) td_critic_loss_kernel(const float* __restrict__ reward,
+                                                             const float* __restrict__ done, int ld_rd,
+                                                             const float* __restrict__ nq1,
+                                                             const float* __restrict__ nq2,
+                                                             const float* __restrict__ logp2,
+                                                             const float* __restrict__ q1, const float* __restrict__ q2,
+                                                             int B, float gamma, const Control* __restrict__ c,
+                                                             float* __restrict__ dq1, float* __restrict__ dq2,
+                                                             float* __restrict__ metrics) {
+  __shared__ float scratch[33];
+  const float alpha = c->alpha;
+  const float inv_b = 1.f / (float)B;
+  float l1 = 0.f, l2 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (int i = threadIdx.x; i < B; i += 256) {
+    const float nq = fminf(nq1[i], nq2[i]) - alpha * logp2[i];
+    const float y = reward[(size_t)i * ld_rd] + (1.f - done[(size_t)i * ld_rd]) * gamma * nq;
+    const float e1 = q1[i] - y, e2 = q2[i] - y;
+    l1 = fmaf(e1, e1, l1);
+    l2 = fmaf(e2, e2, l2);
+    s1 += q1[i];
+    s2 += q2[i];
+    dq1[i] = 2.f * e1 * inv_b;
+    dq2[i] = 2.f * e2 * inv_b;
+  }
+  l1 = block_sum<256>(l1, scratch);
+  l2 = block_sum<256>(l2, scratch);
+  s1 = block_sum<256>(s1, scratch);
+  s2 = block_sum<256>(s2, scratch);
+  if (threadIdx.x == 0) {
+    metrics[0] = l1 * inv_b;
+    metrics[1] = l2 * inv_b;
+    metrics[2] = s1 * inv_b;
+    metrics[3] = s2 * inv_b;
+  }
+}
+
+__global__ void __launch_bounds__(256) actor_alpha_loss_kernel(const float* __restrict__ q1,
+                                                               const float* __restrict__ q2,
+                                                               const float* __restrict__ logp, int B,
+                                                               float target_entropy, int learn_alpha, Control* c,
+                                                               float* __restrict__ dq1, float* __restrict__ dq2,
+                                                               float* __restrict__ dlogp_scalar,
+                                                               float* __restrict__ metrics) {
+  __shared__ float scratch[33];
+  const float alpha = c->alpha;
+  const float inv_b = 1.f / (float)B;
+  float la = 0.f, ent = 0.f, raw = 0.f;
+  for (int i = threadIdx.x; i < B; i += 256) {
+    const float a = q1[i], b = q2[i];
+    la += alpha * logp[i] - fminf(a, b);
+    ent += alpha * (-logp[i] - target_entropy);
+    raw += -logp[i] - target_entropy;
+    // torch.min backward: the smaller input gets the gradient, a tie splits it
+    const float g = -inv_b;
+    dq1[i] = a < b ? g : (a == b ? 0.5f * g : 0.f);
+    dq2[i] = b < a ? g : (a == b ? 0.5f * g : 0.f);
+  }
+  la = block_sum<256>(la, scratch);
+  ent = block_sum<256>(ent, scratch);
+  raw = block_sum<256>(raw, scratch);
+  if (threadIdx.x == 0) {
+    *dlogp_scalar = alpha * inv_b;
+    metrics[0] = la * inv_b;
+    const float alpha_loss = ent * inv_b;
+    metrics[1] = alpha_loss;
+    if (learn_alpha) {
+      // autograd: d/d alpha = fp32 mean(-logp - H); d/d log_alpha = that (cast to float64) * exp(log_alpha)
+      const double g = (double)(raw * inv_b) * exp(c->log_alpha);
+      c->la_m = c->la_m + (1.0 - 0.9) * (g - c->la_m);
+      c->la_v = c->la_v * 0.999 + (1.0 - 0.999) * g * g;
+      const double denom = sqrt(c->la_v) / c->alpha_bc2_sqrt + 1e-8;
+      c->log_alpha = c->log_alpha - c->alpha_step_size * (c->la_m / denom);
+    }
+    metrics[2] = (float)exp(c->log_alpha);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- Adam + Polyak
+__device__ __forceinline__ float adam_elem(float& p, float g, float& m, float& v, float ss, float bc2s) {
+  // torch/optim/adam.py _single_tensor_adam: lerp, mul+addcmul, sqrt/bc2_sqrt + eps, addcdiv.
+  constexpr float w1 = (float)(1.0 - 0.9), b2 = 0.999f, w2 = (float)(1.0 - 0.999), eps = 1e-8f;
+  m = fmaf(w1, g - m, m);
+  v = fmaf(w2 * g, g, v * b2);
+  const float denom = sqrtf(v) / bc2s + eps;
+  p = p - ss * (m / denom);
+  return p;
+}
+
+__global__ void __launch_bounds__(256) adam_polyak_kernel(float4* __restrict__ p, const float4* __restrict__ g,
+                                                          float4* __restrict__ m, float4* __restrict__ v, size_t n4,
+                                                          const AdamHyper* __restrict__ hyper,
+                                                          float4* __restrict__ target, size_t n4_polyak, float tau,
+                                                          const int* __restrict__ polyak_flag) {
+  const float ss = hyper->step_size, bc2s = hyper->bc2_sqrt;
+  const bool do_polyak = target != nullptr && (polyak_flag == nullptr || *polyak_flag != 0);
+  const float omt = 1.f - tau;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 pv = p[i], mv = m[i], vv = v[i];
+    const float4 gv = g[i];
+    adam_elem(pv.x, gv.x, mv.x, vv.x, ss, bc2s);
+    adam_elem(pv.y, gv.y, mv.y, vv.y, ss, bc2s);
+    adam_elem(pv.z, gv.z, mv.z, vv.z, ss, bc2s);
+    adam_elem(pv.w, gv.w, mv.w, vv.w, ss, bc2s);
+    p[i] = pv;
+    m[i] = mv;
+    v[i] = vv;
+    if (do_polyak && i < n4_polyak) {
+      float4 t = target[i];
+      // tau * param + (1 - tau) * target, each op rounded separately (no FMA) like the reference's tensor ops
+      t.x = __fadd_rn(__fmul_rn(tau, pv.x), __fmul_rn(omt, t.x));
+      t.y = __fadd_rn(__fmul_rn(tau, pv.y), __fmul_rn(omt, t.y));
+      t.z = __fadd_rn(__fmul_rn(tau, pv.z), __fmul_rn(omt, t.z));
+      t.w = __fadd_rn(__fmul_rn(tau, pv.w), __fmul_rn(omt, t.w));
+      target[i] = t;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) polyak_kernel(const float4* __restrict__ p, float4* __restrict__ target,
+                                                     size_t n4, float tau, const int* __restrict__ polyak_flag) {
+  if (polyak_flag != nullptr && *polyak_flag == 0) return;
+  const float omt = 1.f - tau;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 pv = p[i];
+    float4 t = target[i];
+    t.x = __fadd_rn(__fmul_rn(tau, pv.x), __fmul_rn(omt, t.x));
+    t.y = __fadd_rn(__fmul_rn(tau, pv.y), __fmul_rn(omt, t.y));
+    t.z = __fadd_rn(__fmul_rn(tau, pv.z), __fmul_rn(omt, t.z));
+    t.w = __fadd_rn(__fmul_rn(tau, pv.w), __fmul_rn(omt, t.w));
+    target[i] = t;
+  }
+}
+
+int grid_for(size_t work_items, int threads, int per_sm = 8) {
+  size_t blocks = (work_items + threads - 1) / threads;
+  const size_t cap = (size_t)kNumSMs * per_sm;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return (int)blocks;
+}
+
+}  // namespace
+
+void launch_tick(Control* c, const TickParams& p, cudaStream_t s) {
+  RLREP_CHECK(p.k_feat <= kMaxFeatureSteps, "too many feature steps per update");
+  tick_kernel<<<1, 32, 0, s>>>(c, p);
+  RLREP_LAUNCHED("tick", s);
+}
+
+void launch_gather(const float* ring, int rec4, const long long* idx, int B, float* out, cudaStream_t s) {
+  gather_kernel<<<grid_for((size_t)B * rec4, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(ring), rec4, idx, B,
+                                                               reinterpret_cast<float4*>(out));
+  RLREP_LAUNCHED("gather", s);
+}
+
+void launch_ring_write(float* ring, int rec4, long long capacity, long long start, const float* rows, int n,
+                       cudaStream_t s) {
+  if (n <= 0) return;
+  ring_write_kernel<<<grid_for((size_t)n * rec4, 256), 256, 0, s>>>(reinterpret_cast<float4*>(ring), rec4, capacity,
+                                                                   start, reinterpret_cast<const float4*>(rows), n);
+  RLREP_LAUNCHED("ring_write", s);
+}
+
+void launch_ce_rows(float* logits, int ld, int rows, int cols, int diag_off, float inv_batch, float* loss_rows,
+                    cudaStream_t s) {
+  ce_rows_kernel<<<rows, 256, 0, s>>>(logits, ld, cols, diag_off, inv_batch, loss_rows);
+  RLREP_LAUNCHED("ce_rows", s);
+}
+
+void launch_rowdot(const float* X, int ld, int rows, int D, const float* w, const float* b, float* y, cudaStream_t s) {
+  rowdot_kernel<<<ceil_div(rows * 32, 256), 256, 0, s>>>(X, ld, rows, D, w, b, y);
+  RLREP_LAUNCHED("rowdot", s);
+}
+
+void launch_colreduce(const float* X, int ld, int rows, int cols, const float* u, float* out, int accumulate,
+                      cudaStream_t s) {
+  colreduce_kernel<<<ceil_div(cols, 32), 256, 0, s>>>(X, ld, rows, cols, u, out, accumulate);
+  RLREP_LAUNCHED("colreduce", s);
+}
+
+void launch_outer_dact(const float* u, const float* w, int rows, int cols, const float* aux, int ld_aux, int dact,
+                       float* out, int ld_out, cudaStream_t s) {
+  outer_dact_kernel<<<grid_for((size_t)rows * cols, 256), 256, 0, s>>>(u, w, rows, cols, aux, ld_aux, dact, out,
+                                                                      ld_out);
+  RLREP_LAUNCHED("outer_dact", s);
+}
+
+void launch_feature_loss_finalize(const float* loss_rows, int rows, const float* pred, const float* reward, int ld_r,
+                                  float inv_batch, float* dpred, float* metrics, cudaStream_t s) {
+  feature_loss_finalize_kernel<<<1, 256, 0, s>>>(loss_rows, rows, pred, reward, ld_r, inv_batch, dpred, metrics);
+  RLREP_LAUNCHED("feature_loss_finalize", s);
+}
+
+void launch_actor_sample(const float* head, int B, int A, const float* eps, float* action, int lda, float* logp,
+                         cudaStream_t s) {
+  actor_sample_kernel<<<ceil_div(B, 128), 128, 0, s>>>(head, B, A, eps, action, lda, logp);
+  RLREP_LAUNCHED("actor_sample", s);
+}
+
+void launch_actor_sample_bwd(const float* head, int B, int A, const float* eps, const float* d_action, int ldd,
+                             const float* dlogp_scalar, float* dhead, cudaStream_t s) {
+  actor_sample_bwd_kernel<<<ceil_div(B * A, 256), 256, 0, s>>>(head, B, A, eps, d_action, ldd, dlogp_scalar, dhead);
+  RLREP_LAUNCHED("actor_sample_bwd", s);
+}
+
+void launch_td_critic_loss(const float* reward, const float* done, int ld_rd, const float* nq1, const float* nq2,
+                           const float* logp2, const float* q1, const float* q2, int B, float gamma, const Control* c,
+                           float* dq1, float* dq2, float* metrics, cudaStream_t s) {
+  td_critic_loss_kernel<<<1, 256, 0, s>>>(reward, done, ld_rd, nq1, nq2, logp2, q1, q2, B, gamma, c, dq1, dq2, metrics);
+  RLREP_LAUNCHED("td_critic_loss", s);
+}
+
+void launch_actor_alpha_loss(const float* q1, const float* q2, const float* logp, int B, float target_entropy,
+                             int learn_alpha, Control* c, float* dq1, float* dq2, float* dlogp_scalar, float* metrics,
+                             cudaStream_t s) {
+  actor_alpha_loss_kernel<<<1, 256, 0, s>>>(q1, q2, logp, B, target_entropy, learn_alpha, c, dq1, dq2, dlogp_scalar,
+                                            metrics);
+  RLREP_LAUNCHED("actor_alpha_loss", s);
+}
+
+void launch_adam_polyak(float* p, const float* g, float* m, float* v, size_t n, const AdamHyper* hyper, float* target,
+                        size_t n_polyak, float tau, const int* polyak_flag, cudaStream_t s) {
+  RLREP_CHECK(n % 4 == 0 && n_polyak % 4 == 0, "optimizer arenas are padded to float4");
+  const size_t n4 = n / 4;
+  adam_polyak_kernel<<<grid_for(n4, 256, 16), 256, 0, s>>>(
+      reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
+      reinterpret_cast<float4*>(v), n4, hyper, reinterpret_cast<float4*>(target), n_polyak / 4, tau, polyak_flag);
+  RLREP_LAUNCHED("adam_polyak", s);
+}
+
+void launch_polyak(const float* p, float* target, size_t n, float tau, const int* polyak_flag, cudaStream_t s) {
+  RLREP_CHECK(n % 4 == 0, "optimizer arenas are padded to float4");
+  polyak_kernel<<<grid_for(n / 4, 256, 16), 256, 0, s>>>(reinterpret_cast<const float4*>(p),
+                                                        reinterpret_cast<float4*>(target), n / 4, tau, polyak_flag);
+  RLREP_LAUNCHED("polyak", s);
+}
+
+}  // namespace rlrep

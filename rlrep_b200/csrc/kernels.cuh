@@ -1,0 +1,99 @@
+// Bandwidth-/latency-bound kernels of the update step (everything that is not a GEMM):
+// replay gather, contrastive log-sum-exp / cross-entropy, reward head, N=1 critic heads, TD target and
+// critic loss, tanh-Gaussian actor sample / log-prob (forward + backward), actor / temperature loss,
+// the fused multi-tensor Adam + Polyak kernel and the per-update control-block "tick".
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace rlrep {
+
+constexpr int kMaxFeatureSteps = 16;
+constexpr int kNumMetrics = 32;
+
+struct AdamHyper {
+  float step_size;  // lr / (1 - beta1^t)
+  float bc2_sqrt;   // sqrt(1 - beta2^t)
+};
+
+// Per-agent control block in device memory.  Everything that changes from one train() call to the next and
+// would otherwise be a kernel argument lives here, so the whole update can be replayed as one CUDA graph.
+struct Control {
+  int steps;              // agent.steps (reference: sac_agent.py:173)
+  int polyak_critic;      // steps % target_update_period == 0 (sac_agent.py:100)
+  long long t_feat, t_critic, t_actor, t_alpha;  // Adam step counters
+  AdamHyper feat[kMaxFeatureSteps];
+  AdamHyper critic, actor;
+  double alpha_step_size, alpha_bc2_sqrt;
+  double log_alpha, la_m, la_v;  // temperature is float64 in the reference (sac_agent.py:66)
+  float alpha;                   // float(exp(log_alpha)) as seen by fp32 kernels
+};
+
+struct TickParams {
+  int k_feat;              // feature Adam steps per train() (0 = agent has no feature optimiser)
+  int period;              // target_update_period
+  double lr_feat, lr_critic, lr_actor, lr_alpha;
+  int critic_steps;        // 1 if the critic optimiser steps this agent (0 for diffsrsac)
+};
+
+void launch_tick(Control* c, const TickParams& p, cudaStream_t s);
+
+// Replay gather: out[b, :] = ring[idx[b], :], rows are rec4 float4 wide (128-bit loads/stores).
+void launch_gather(const float* ring, int rec4, const long long* idx, int B, float* out, cudaStream_t s);
+// Scatter of freshly added rows into the ring at slots (start + i) % capacity.
+void launch_ring_write(float* ring, int rec4, long long capacity, long long start, const float* rows, int n,
+                       cudaStream_t s);
+
+// Contrastive soft-label CE with identity labels (ctrlsac_agent.py:226-231):
+//   loss_i = logsumexp_j(l_ij) - l_{i, diag_off + i};  in place  l_ij <- (softmax_j(l_i)_j - [j == diag_off+i]) * inv_batch
+void launch_ce_rows(float* logits, int ld, int rows, int cols, int diag_off, float inv_batch, float* loss_rows,
+                    cudaStream_t s);
+
+// y[i] = sum_j X[i,j] w[j] + b[0]  (N = 1 linear heads; one warp per row)
+void launch_rowdot(const float* X, int ld, int rows, int D, const float* w, const float* b, float* y, cudaStream_t s);
+// out[j] (+)= sum_i u[i] * X[i,j]   (u == nullptr: plain column sum).  Deterministic.
+void launch_colreduce(const float* X, int ld, int rows, int cols, const float* u, float* out, int accumulate,
+                      cudaStream_t s);
+// out[i,j] = u[i] * w[j] * dact(aux[i,j])   (backward of an N = 1 head into its hidden layer)
+void launch_outer_dact(const float* u, const float* w, int rows, int cols, const float* aux, int ld_aux, int dact,
+                       float* out, int ld_out, cudaStream_t s);
+
+// Reward head loss (ctrlsac_agent.py:233): r_loss = 0.5 * mean((pred - r)^2); dpred = (pred - r) * inv_batch.
+// Also finishes the feature metrics: model_loss = sum(loss_rows) * inv_batch, total = model + r.
+void launch_feature_loss_finalize(const float* loss_rows, int rows, const float* pred, const float* reward, int ld_r,
+                                  float inv_batch, float* dpred, float* metrics /*[total, model, r]*/, cudaStream_t s);
+
+// Actor head -> action / log-prob (agent/sac/actor.py:76-91 + 40-43).
+//   head [B, 2A] = (mu | raw log-std); eps [B, A];  out action [B, lda] (tanh(u)), logp [B]
+void launch_actor_sample(const float* head, int B, int A, const float* eps, float* action, int lda, float* logp,
+                         cudaStream_t s);
+// Backward of the above: dhead [B, 2A] from d_action [B, ldd] and the per-row d_logp scalar (*dlogp_scalar).
+void launch_actor_sample_bwd(const float* head, int B, int A, const float* eps, const float* d_action, int ldd,
+                             const float* dlogp_scalar, float* dhead, cudaStream_t s);
+
+// TD target + twin-critic MSE (ctrlsac_agent.py:263-286; sac_agent.py:112-123):
+//   y = r + (1 - d) * gamma * (min(nq1, nq2) - alpha * logp2)
+//   dq1 = 2 (q1 - y) / B, dq2 likewise;  metrics[0..3] = q1_loss, q2_loss, mean(q1), mean(q2)
+void launch_td_critic_loss(const float* reward, const float* done, int ld_rd, const float* nq1, const float* nq2,
+                           const float* logp2, const float* q1, const float* q2, int B, float gamma, const Control* c,
+                           float* dq1, float* dq2, float* metrics, cudaStream_t s);
+
+// Actor / temperature losses (ctrlsac_agent.py:308-320; sac_agent.py:146-161), single block:
+//   actor_loss = mean(alpha * logp - min(q1, q2));  dq1/dq2 = -[argmin] / B;  *dlogp_scalar = alpha / B
+//   alpha_loss = mean(alpha * (-logp - target_entropy)); fp64 Adam step on log_alpha inside the control block.
+//   metrics[0..2] = actor_loss, alpha_loss, alpha (after the step, like `info['alpha'] = self.alpha`).
+void launch_actor_alpha_loss(const float* q1, const float* q2, const float* logp, int B, float target_entropy,
+                             int learn_alpha, Control* c, float* dq1, float* dq2, float* dlogp_scalar, float* metrics,
+                             cudaStream_t s);
+
+// Fused multi-tensor Adam (+ optional Polyak of a prefix of the arena into its target copy).
+// One launch updates a whole optimiser group laid out as flat arrays p / g / m / v of n floats (n % 4 == 0).
+//   torch.optim.Adam defaults: beta = (0.9, 0.999), eps = 1e-8, no weight decay / amsgrad.
+//   target[0:n_polyak] = tau * p_new + (1 - tau) * target   when *polyak_flag != 0 (or flag == nullptr).
+void launch_adam_polyak(float* p, const float* g, float* m, float* v, size_t n, const AdamHyper* hyper, float* target,
+                        size_t n_polyak, float tau, const int* polyak_flag, cudaStream_t s);
+// Polyak only (critic_target of agents whose critic optimiser never steps).
+void launch_polyak(const float* p, float* target, size_t n, float tau, const int* polyak_flag, cudaStream_t s);
+
+}  // namespace rlrep

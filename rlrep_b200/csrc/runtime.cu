@@ -1,0 +1,265 @@
+// Host runtime: replay ring, GEMM dispatch with cached TMA plans, linear-layer pass helpers, graph replay.
+#include <algorithm>
+
+#include "agent.cuh"
+
+namespace rlrep {
+
+namespace {
+thread_local long long g_launches = 0;
+thread_local bool g_profiling = false;
+thread_local std::vector<cudaEvent_t> g_events;       // g_events[0] = start, then one per launch
+thread_local std::vector<const char*> g_names;
+}  // namespace
+
+long long launch_count() { return g_launches; }
+
+void note_launch(const char* name, cudaStream_t stream) {
+  ++g_launches;
+  if (g_profiling) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) == cudaSuccess) {
+      cudaEventRecord(e, stream);
+      g_events.push_back(e);
+      g_names.push_back(name);
+    }
+  }
+}
+
+void profile_begin(cudaStream_t stream) {
+  for (cudaEvent_t e : g_events) cudaEventDestroy(e);
+  g_events.clear();
+  g_names.clear();
+  cudaEvent_t e;
+  RLREP_CUDA(cudaEventCreate(&e));
+  RLREP_CUDA(cudaEventRecord(e, stream));
+  g_events.push_back(e);
+  g_profiling = true;
+}
+
+std::vector<ProfileEntry> profile_end(cudaStream_t stream) {
+  g_profiling = false;
+  RLREP_CUDA(cudaStreamSynchronize(stream));
+  std::vector<ProfileEntry> out;
+  for (size_t i = 0; i + 1 < g_events.size(); ++i) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, g_events[i], g_events[i + 1]);
+    out.push_back({g_names[i], ms});
+  }
+  for (cudaEvent_t e : g_events) cudaEventDestroy(e);
+  g_events.clear();
+  g_names.clear();
+  return out;
+}
+
+// ================================================================================================ Ring
+namespace {
+constexpr size_t kStageRows = 8192;
+}  // namespace
+
+Ring::Ring(int state_dim, int action_dim, long long cap) : S(state_dim), A(action_dim), capacity(cap) {
+  RLREP_CHECK(S > 0 && A > 0 && cap > 0, "bad ring dimensions");
+  const RecordLayout l = RecordLayout::of(S, A);
+  off_a = l.off_a;
+  off_r = l.off_r;
+  off_d = l.off_d;
+  off_s2 = l.off_s2;
+  R = l.R;
+  RLREP_CUDA(cudaMalloc(&data, (size_t)capacity * R * sizeof(float)));
+  RLREP_CUDA(cudaMemset(data, 0, (size_t)capacity * R * sizeof(float)));
+  stage_rows_ = kStageRows;
+  RLREP_CUDA(cudaMallocHost(&stage_host_, stage_rows_ * R * sizeof(float)));
+  RLREP_CUDA(cudaMalloc(&stage_dev_, stage_rows_ * R * sizeof(float)));
+  idx_cap_ = 1 << 16;
+  RLREP_CUDA(cudaMallocHost(&idx_host_, idx_cap_ * sizeof(long long)));
+  RLREP_CUDA(cudaMalloc(&idx_dev_, idx_cap_ * sizeof(long long)));
+}
+
+Ring::~Ring() {
+  cudaFree(data);
+  cudaFreeHost(stage_host_);
+  cudaFree(stage_dev_);
+  cudaFreeHost(idx_host_);
+  cudaFree(idx_dev_);
+}
+
+void Ring::add_packed(const float* rows_host, int n, cudaStream_t s) {
+  int done = 0;
+  while (done < n) {
+    const int chunk = (int)std::min<size_t>(stage_rows_, (size_t)(n - done));
+    RLREP_CUDA(cudaStreamSynchronize(s));  // staging buffers are reused
+    std::memcpy(stage_host_, rows_host + (size_t)done * R, (size_t)chunk * R * sizeof(float));
+    RLREP_CUDA(cudaMemcpyAsync(stage_dev_, stage_host_, (size_t)chunk * R * sizeof(float), cudaMemcpyHostToDevice, s));
+    launch_ring_write(data, R / 4, capacity, ptr, stage_dev_, chunk, s);
+    ptr = (ptr + chunk) % capacity;
+    size = std::min(size + chunk, capacity);
+    done += chunk;
+  }
+  RLREP_CUDA(cudaStreamSynchronize(s));
+}
+
+void Ring::load_columns(const void* state, const void* action, const void* next_state, const void* reward,
+                        const void* done, long long n, int is_f64, cudaStream_t s) {
+  RLREP_CHECK(n <= capacity, "more rows than ring capacity");
+  auto get = [is_f64](const void* base, long long i) -> float {
+    return is_f64 ? (float)static_cast<const double*>(base)[i] : static_cast<const float*>(base)[i];
+  };
+  ptr = 0;
+  size = 0;
+  long long row = 0;
+  while (row < n) {
+    const int chunk = (int)std::min<long long>((long long)stage_rows_, n - row);
+    RLREP_CUDA(cudaStreamSynchronize(s));
+    std::memset(stage_host_, 0, (size_t)chunk * R * sizeof(float));
+    for (int i = 0; i < chunk; ++i) {
+      float* rec = stage_host_ + (size_t)i * R;
+      const long long r = row + i;
+      for (int j = 0; j < S; ++j) rec[j] = get(state, r * S + j);
+      for (int j = 0; j < A; ++j) rec[off_a + j] = get(action, r * A + j);
+      rec[off_r] = get(reward, r);
+      rec[off_d] = get(done, r);
+      for (int j = 0; j < S; ++j) rec[off_s2 + j] = get(next_state, r * S + j);
+    }
+    RLREP_CUDA(cudaMemcpyAsync(stage_dev_, stage_host_, (size_t)chunk * R * sizeof(float), cudaMemcpyHostToDevice, s));
+    launch_ring_write(data, R / 4, capacity, ptr, stage_dev_, chunk, s);
+    ptr = (ptr + chunk) % capacity;
+    size = std::min(size + chunk, capacity);
+    row += chunk;
+  }
+  RLREP_CUDA(cudaStreamSynchronize(s));
+}
+
+void Ring::gather_from_host_idx(const long long* idx_host, int B, float* out_dev, cudaStream_t s) {
+  RLREP_CHECK(B > 0 && B <= idx_cap_, "batch too large for the ring's index staging");
+  for (int i = 0; i < B; ++i) RLREP_CHECK(idx_host[i] >= 0 && idx_host[i] < size, "replay index out of range");
+  RLREP_CUDA(cudaStreamSynchronize(s));
+  std::memcpy(idx_host_, idx_host, (size_t)B * sizeof(long long));
+  RLREP_CUDA(cudaMemcpyAsync(idx_dev_, idx_host_, (size_t)B * sizeof(long long), cudaMemcpyHostToDevice, s));
+  launch_gather(data, R / 4, idx_dev_, B, out_dev, s);
+}
+
+// ================================================================================================ GemmRunner
+void GemmRunner::init(Precision prec, size_t ws_floats) {
+  prec_ = prec;
+  ws_floats_ = ws_floats;
+  if (ws_floats_) RLREP_CUDA(cudaMalloc(&ws_, ws_floats_ * sizeof(float)));
+}
+GemmRunner::~GemmRunner() {
+  if (ws_) cudaFree(ws_);
+}
+
+void GemmRunner::run(const GemmArgs& a, cudaStream_t s) {
+  const bool tc = prec_ == PREC_TF32 && tc_eligible(a) && a.M >= 64 && a.N >= 32 && a.K >= 64;
+  if (!tc) {
+    launch_simt(a, s);
+    return;
+  }
+  std::string key(sizeof(GemmArgs), '\0');
+  {
+    // field-wise copy into a zeroed buffer so padding bytes never differ
+    GemmArgs* k = reinterpret_cast<GemmArgs*>(&key[0]);
+    k->M = a.M; k->N = a.N; k->K = a.K;
+    k->A = a.A; k->lda = a.lda; k->a_mn = a.a_mn;
+    k->B = a.B; k->ldb = a.ldb; k->b_mn = a.b_mn;
+    k->C = a.C; k->ldc = a.ldc;
+    k->epi.bias = a.epi.bias; k->epi.r1_u = a.epi.r1_u; k->epi.r1_v = a.epi.r1_v; k->epi.aux = a.epi.aux;
+    k->epi.pre_out = a.epi.pre_out; k->epi.ld_aux = a.epi.ld_aux; k->epi.ld_pre = a.epi.ld_pre;
+    k->epi.act = a.epi.act; k->epi.dact = a.epi.dact; k->epi.accumulate = a.epi.accumulate;
+    k->epi.scale = a.epi.scale;
+  }
+  auto it = plans_.find(key);
+  if (it == plans_.end()) it = plans_.emplace(key, make_tc_plan(a, 0, 0, ws_, ws_floats_)).first;
+  launch_tc(it->second, s);
+}
+
+// ================================================================================================ linear passes
+void linear_fwd(GemmRunner& g, cudaStream_t s, int rows, Mat x, const Linear& l, int act, float* y, int ldy, Mat x2,
+                int k1, float* pre_out) {
+  GemmArgs a;
+  a.M = rows; a.N = l.out; a.K = l.in;
+  a.A = x.p; a.lda = x.ld;
+  if (x2.p) { a.A2 = x2.p; a.lda2 = x2.ld; a.K1 = k1; }
+  a.B = l.W; a.ldb = l.in;
+  a.C = y; a.ldc = ldy;
+  a.epi.bias = l.b;
+  a.epi.act = act;
+  if (pre_out) { a.epi.pre_out = pre_out; a.epi.ld_pre = ldy; }
+  g.run(a, s);
+}
+
+void linear_dgrad(GemmRunner& g, cudaStream_t s, int rows, Mat dy, const Linear& l, int dact, Mat aux, float* dx,
+                  int lddx, int col0, int n_cols) {
+  GemmArgs a;
+  a.M = rows; a.N = n_cols < 0 ? l.in : n_cols; a.K = l.out;
+  a.A = dy.p; a.lda = dy.ld;
+  a.B = l.W + col0; a.ldb = l.in; a.b_mn = true;  // W[out, in] read as B(n = in, k = out)
+  a.C = dx; a.ldc = lddx;
+  a.epi.dact = dact;
+  a.epi.aux = aux.p; a.epi.ld_aux = aux.ld;
+  g.run(a, s);
+}
+
+void linear_wgrad(GemmRunner& g, cudaStream_t s, int rows, Mat dy, Mat x, const Linear& l, Mat x2, int k1) {
+  // dW[out, in] = sum_b dy[b, out] x[b, in]:  A = dy (MN-major, k = batch), B = x (MN-major)
+  if (x2.p == nullptr) {
+    GemmArgs a;
+    a.M = l.out; a.N = l.in; a.K = rows;
+    a.A = dy.p; a.lda = dy.ld; a.a_mn = true;
+    a.B = x.p; a.ldb = x.ld; a.b_mn = true;
+    a.C = l.dW; a.ldc = l.in;
+    g.run(a, s);
+  } else {
+    // two input segments -> two column blocks of dW
+    GemmArgs a;
+    a.M = l.out; a.N = k1; a.K = rows;
+    a.A = dy.p; a.lda = dy.ld; a.a_mn = true;
+    a.B = x.p; a.ldb = x.ld; a.b_mn = true;
+    a.C = l.dW; a.ldc = l.in;
+    g.run(a, s);
+    GemmArgs b = a;
+    b.N = l.in - k1;
+    b.B = x2.p; b.ldb = x2.ld;
+    b.C = l.dW + k1;
+    g.run(b, s);
+  }
+  launch_colreduce(dy.p, dy.ld, rows, l.out, nullptr, l.db, 0, s);
+}
+
+// ================================================================================================ GraphReplay
+void GraphReplay::reset() {
+  if (exec_) cudaGraphExecDestroy(exec_);
+  if (graph_) cudaGraphDestroy(graph_);
+  exec_ = nullptr;
+  graph_ = nullptr;
+  calls_ = 0;
+}
+
+void GraphReplay::run(cudaStream_t s, bool enabled, const std::function<void()>& body) {
+  if (!enabled) {
+    body();
+    return;
+  }
+  if (exec_ != nullptr) {
+    RLREP_CUDA(cudaGraphLaunch(exec_, s));
+    return;
+  }
+  if (calls_ == 0) {
+    ++calls_;
+    body();
+    return;
+  }
+  RLREP_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+  try {
+    body();
+  } catch (...) {
+    cudaGraph_t g = nullptr;
+    cudaStreamEndCapture(s, &g);
+    if (g) cudaGraphDestroy(g);
+    throw;
+  }
+  RLREP_CUDA(cudaStreamEndCapture(s, &graph_));
+  RLREP_CUDA(cudaGraphInstantiate(&exec_, graph_, 0));
+  RLREP_CUDA(cudaGraphLaunch(exec_, s));
+}
+
+}  // namespace rlrep

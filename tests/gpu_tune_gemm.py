@@ -29,12 +29,12 @@ for label, M, N, K, a_mn, b_mn in shapes:
         for sk in (1, 2, 4, 8, 16):
             if sk > 1 and M * N >= (1 << 22):
                 continue
-            ms, bno, so = _lib.gemm_bench(A, B, Cm, a_mn=bool(a_mn), b_mn=bool(b_mn), bn=bn, split_k=sk, ws=ws, iters=40)
+            ms, bno, so = _lib.gemm_bench(A, B, Cm, a_mn=bool(a_mn), b_mn=bool(b_mn), bn=bn, split_k=sk, ws=ws, iters=200)
             if so != sk:
                 continue
             res.append((ms * 1e3, bn, sk))
     res.sort()
-    ms_auto, bn_a, sk_a = _lib.gemm_bench(A, B, Cm, a_mn=bool(a_mn), b_mn=bool(b_mn), ws=ws, iters=40)
+    ms_auto, bn_a, sk_a = _lib.gemm_bench(A, B, Cm, a_mn=bool(a_mn), b_mn=bool(b_mn), ws=ws, iters=200)
     flops = 2.0 * M * N * K
     best = res[0]
     print(f"{label}: best {best[0]:.1f}us (bn={best[1]},sk={best[2]}) {flops / best[0] / 1e6:.1f} TF/s | auto {ms_auto * 1e3:.1f}us (bn={bn_a},sk={sk_a}) | top3 "

@@ -1,0 +1,68 @@
+"""Shared helpers of the parity tests: build (CUDA agent, oracle agent) pairs on identical weights and data, step
+them with identically seeded global RNGs, compare info dicts and parameters."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from oracle import rl_oracle as O
+
+
+class Space:
+    def __init__(self, A):
+        self.low, self.high, self.shape = -np.ones(A, np.float32), np.ones(A, np.float32), (A,)
+
+
+def make_pair(alg, S, A, kw, rows, precision="tf32", use_cuda_graph=True, seed=0, oracle_kw=None):
+    from rlrep_b200 import ReplayBuffer
+    from rlrep_b200.agents import AGENTS
+    init = O.init_state(alg, S, A, kw, seed=seed)
+    oracle = O.ORACLES[alg](S, A, init, discount=0.99, tau=0.005, **kw, **(oracle_kw or {}))
+    oring = O.synthetic_ring(S, A, rows, seed=0)
+    agent = AGENTS[alg](state_dim=S, action_dim=A, action_space=Space(A), discount=0.99, tau=0.005,
+                        precision=precision, use_cuda_graph=use_cuda_graph, **kw)
+    agent.load_state_dict(init)
+    buf = ReplayBuffer(S, A, max_size=rows)
+    buf.load(oring.state, oring.action, oring.next_state, oring.reward, oring.done)
+    return agent, buf, oracle, oring
+
+
+def step_both(agent, buf, oracle, oring, B, n, seed=1):
+    """n train() calls on each side under the same global seeds -> (infos_cuda, infos_oracle)."""
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    oi = [oracle.train(oring, B) for _ in range(n)]
+    np.random.seed(seed)
+    torch.manual_seed(seed)
+    ci = [agent.train(buf, B) for _ in range(n)]
+    return ci, oi
+
+
+def worst_info_error(ci, oi, atol=1e-6):
+    worst, where = 0.0, None
+    for step, (c, o) in enumerate(zip(ci, oi)):
+        assert set(c) == set(o), (sorted(c), sorted(o))
+        for k in o:
+            err = max(0.0, abs(c[k] - o[k]) - atol) / (abs(o[k]) + 1e-12)
+            if err > worst:
+                worst, where = err, (step, k, c[k], o[k])
+    return worst, where
+
+
+def worst_param_error(agent, oracle):
+    """Per-tensor relative L2 distance (norm-wise: Adam turns 1-ulp gradient noise into +-2 lr on single elements,
+    SURVEY.md 7.2 #1) -> (worst value, tensor name, fraction of elements beyond 1e-3 relative)."""
+    csd, osd = agent.state_dict(), oracle.state_dict()
+    worst, where = 0.0, None
+    outliers = 0
+    total = 0
+    for k, v in osd.items():
+        assert k in csd, f"{k} missing from the CUDA agent's state_dict"
+        c = csd[k].double().reshape(-1)
+        v = v.double().reshape(-1)
+        d = (c - v).norm().item() / (v.norm().item() + 1e-30)
+        outliers += int(((c - v).abs() > 1e-3 * v.abs() + 1e-6).sum())
+        total += v.numel()
+        if d > worst:
+            worst, where = d, k
+    return worst, where, outliers / max(total, 1)

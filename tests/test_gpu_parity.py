@@ -1,0 +1,154 @@
+"""GPU parity tests (run on the B200 box: `pytest tests -m gpu`).  Everything goes through the C ABI.
+
+Tolerances (north_star): gathers bit-exact; fp32 paths rel 1e-5; TF32 tensor-core paths rel 1e-3.  Parameters are
+compared norm-wise per tensor because Adam turns 1-ulp gradient differences into +-2 lr moves of single
+near-zero-gradient elements.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rl_oracle as O
+from parity_util import Space, make_pair, step_both, worst_info_error, worst_param_error
+
+pytestmark = pytest.mark.gpu
+
+HC = dict(S=17, A=6)
+
+
+# ------------------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 0), (1, 1)])
+@pytest.mark.parametrize("shape", [(256, 2048, 1024), (256, 256, 2048), (2048, 1024, 256), (200, 136, 100),
+                                   (128, 128, 32), (64, 32, 64)])
+def test_gemm_tf32_all_majors(lib, a_mn, b_mn, shape):
+    from rlrep_b200 import _lib
+    M, N, K = shape
+    torch.manual_seed(0)
+    A = torch.randn((K, M) if a_mn else (M, K), device="cuda")
+    B = torch.randn((K, N) if b_mn else (N, K), device="cuda")
+    bias = torch.randn(N, device="cuda")
+    ws = torch.empty(16 * M * N, device="cuda")
+    ref = torch.nn.functional.elu((A.t() if a_mn else A).double() @ (B.t() if b_mn else B).double().t() + bias.double())
+    for bn, sk in ((0, 0), (32, 1), (64, 2), (128, 1), (256, 1)):
+        C = torch.full((M, N), float("nan"), device="cuda")
+        _lib.gemm(A, B, C, a_mn=bool(a_mn), b_mn=bool(b_mn), path="tc", epi=_lib.make_epilogue(bias=bias, act="elu"),
+                  bn=bn, split_k=sk, ws=ws)
+        err = ((C.double() - ref).norm() / ref.norm()).item()
+        assert err < 1e-3, (bn, sk, err)  # TF32: 10-bit mantissa operands, fp32 accumulate
+
+
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 0), (0, 1), (1, 1)])
+def test_gemm_fp32_cuda_cores(lib, a_mn, b_mn):
+    from rlrep_b200 import _lib
+    torch.manual_seed(1)
+    M, N, K = 100, 23, 300
+    A = torch.randn((K, M) if a_mn else (M, K), device="cuda")
+    B = torch.randn((K, N) if b_mn else (N, K), device="cuda")
+    C = torch.empty((M, N), device="cuda")
+    _lib.gemm(A, B, C, a_mn=bool(a_mn), b_mn=bool(b_mn), path="simt")
+    ref = (A.t() if a_mn else A).double() @ (B.t() if b_mn else B).double().t()
+    assert ((C.double() - ref).norm() / ref.norm()).item() < 1e-5
+
+
+def test_gemm_two_segment_input_and_derivative_epilogue(lib):
+    """cat(s, a) read from two buffers (first layers) and the fused activation-derivative epilogue (dgrad)."""
+    from rlrep_b200 import _lib
+    torch.manual_seed(2)
+    X1, X2 = torch.randn(64, 17, device="cuda"), torch.randn(64, 6, device="cuda")
+    W = torch.randn(40, 23, device="cuda")
+    C = torch.empty(64, 40, device="cuda")
+    _lib.gemm(X1, W, C, path="simt", A2=X2, epi=_lib.make_epilogue(act="tanh"))
+    ref = torch.tanh(torch.cat([X1, X2], 1).double() @ W.double().t())
+    assert (C.double() - ref).abs().max().item() < 1e-5
+    H = torch.randn(64, 23, device="cuda")
+    dX = torch.empty(64, 23, device="cuda")
+    _lib.gemm(C, W, dX, b_mn=True, path="simt", epi=_lib.make_epilogue(aux=H, dact="elu_out"))
+    ref = (C.double() @ W.double()) * torch.where(H > 0, torch.ones_like(H), H + 1).double()
+    assert ((dX.double() - ref).norm() / ref.norm()).item() < 1e-5
+
+
+# ------------------------------------------------------------------------------------------------ replay ring
+def test_gather_is_bit_exact_vs_reference_semantics():
+    """buffer.sample == fp32 cast of the fp64 rows at the drawn indices (utils/buffer.py:39-48), bit for bit."""
+    from rlrep_b200 import ReplayBuffer
+    for S, A in ((17, 6), (376, 17), (3, 1)):
+        oring = O.synthetic_ring(S, A, 3000, seed=3)
+        buf = ReplayBuffer(S, A, max_size=3000)
+        buf.load(oring.state, oring.action, oring.next_state, oring.reward, oring.done)
+        np.random.seed(5)
+        want = oring.sample(257)
+        np.random.seed(5)
+        got = buf.sample(257)
+        for name in want._fields:
+            assert torch.equal(getattr(got, name).cpu(), getattr(want, name)), (S, A, name)
+
+
+def test_ring_add_wraps_like_the_reference():
+    from rlrep_b200 import ReplayBuffer
+    S, A, cap = 5, 2, 1500
+    rng = np.random.default_rng(0)
+    ref = O.HostRing(S, A, max_size=cap)
+    buf = ReplayBuffer(S, A, max_size=cap)
+    for _ in range(cap + 700):  # crosses the staging size and wraps the ring
+        row = (rng.standard_normal(S), rng.uniform(-1, 1, A), rng.standard_normal(S), rng.standard_normal(), float(rng.random() < 0.1))
+        ref.add(*row)
+        buf.add(*row)
+    assert (buf.size, buf.ptr) == (ref.size, ref.ptr)
+    ind = np.arange(cap)
+    want, got = ref.take(ind), buf.take(ind)
+    for name in want._fields:
+        assert torch.equal(getattr(got, name).cpu(), getattr(want, name)), name
+
+
+# ------------------------------------------------------------------------------------------------ full update steps
+CASES = {
+    "sac": ("sac", HC, dict(hidden_dim=256), 256),
+    "ctrlsac_small": ("ctrlsac", HC, dict(hidden_dim=64, feature_dim=128, extra_feature_steps=3), 32),
+    "ctrlsac": ("ctrlsac", HC, dict(hidden_dim=1024, feature_dim=2048, extra_feature_steps=3), 256),
+}
+
+
+@pytest.mark.parametrize("case", list(CASES))
+@pytest.mark.parametrize("precision,tol_info,tol_param", [("fp32", 2e-4, 2e-4), ("tf32", 3e-3, 3e-3)])
+def test_train_matches_oracle(case, precision, tol_info, tol_param):
+    alg, shp, kw, B = CASES[case]
+    okw = dict(as_written=False) if alg == "ctrlsac" else {}
+    agent, buf, oracle, oring = make_pair(alg, shp["S"], shp["A"], kw, rows=5000, precision=precision, oracle_kw=okw)
+    n = 4  # crosses the eager call, the graph capture and two replays; Polyak fires on steps 2 and 4
+    ci, oi = step_both(agent, buf, oracle, oring, B, n)
+    wi, where_i = worst_info_error(ci, oi, atol=1e-5)
+    wp, where_p, frac = worst_param_error(agent, oracle)
+    print(f"{case}/{precision}: worst info rel {wi:.2e} at {where_i}; worst param rel-l2 {wp:.2e} at {where_p}; "
+          f"elementwise outliers {frac:.2e}")
+    assert wi < tol_info, where_i
+    assert wp < tol_param, where_p
+    assert agent.gpu_launches_last_train > 0
+
+
+def test_graph_replay_equals_eager():
+    """The CUDA-graph replay must produce bit-identical results to eager launches."""
+    alg, shp, kw, B = CASES["ctrlsac_small"]
+    outs = []
+    for use_graph in (False, True):
+        agent, buf, oracle, oring = make_pair(alg, shp["S"], shp["A"], kw, rows=2000, use_cuda_graph=use_graph)
+        np.random.seed(3)
+        torch.manual_seed(3)
+        infos = [agent.train(buf, B) for _ in range(4)]
+        outs.append((infos, agent.state_dict()))
+    assert outs[0][0] == outs[1][0]
+    for k in outs[0][1]:
+        assert torch.equal(outs[0][1][k], outs[1][1][k]), k
+
+
+def test_select_action_matches_oracle():
+    alg, shp, kw, B = CASES["sac"]
+    agent, buf, oracle, oring = make_pair(alg, shp["S"], shp["A"], kw, rows=100, precision="fp32")
+    s = oring.state[7]
+    a_c = agent.select_action(s)
+    a_o = oracle.select_action(s)
+    assert np.allclose(a_c, a_o, atol=1e-5)
+    torch.manual_seed(9)
+    e_c = agent.select_action(s, explore=True)
+    torch.manual_seed(9)
+    e_o = oracle.select_action(s, explore=True)
+    assert np.allclose(e_c, e_o, atol=1e-5)

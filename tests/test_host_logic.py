@@ -1,0 +1,82 @@
+"""CPU: host-side logic of the agent shims that does not need a device -- RNG consumption order, config mapping,
+initial-weight tables, info-dict keys."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rl_oracle as O
+from rlrep_b200 import _lib
+from rlrep_b200.agents import AGENTS, CTRLSACAgent, SACAgent
+
+
+class Space:
+    def __init__(self, A):
+        self.low, self.high = -np.ones(A, np.float32), np.ones(A, np.float32)
+
+
+class FakeBuffer:
+    size = 5000
+
+
+CASES = {
+    "sac": (dict(hidden_dim=32), 64),
+    "ctrlsac": (dict(hidden_dim=32, feature_dim=64, extra_feature_steps=3), 32),
+}
+
+
+@pytest.mark.parametrize("alg", list(CASES))
+def test_draw_consumes_the_global_rngs_exactly_like_the_reference(alg):
+    """After one train(), numpy's legacy RNG and torch's CPU generator must be in the same state on both sides,
+    and the drawn indices / noise must be the ones the oracle (== reference) consumed."""
+    kw, B = CASES[alg]
+    S, A = 17, 6
+    init = O.init_state(alg, S, A, kw)
+    oracle = O.ORACLES[alg](S, A, init, discount=0.99, tau=0.005, **kw)
+    ring = O.synthetic_ring(S, A, FakeBuffer.size, seed=0)
+    drawn = []
+    orig_take = ring.take
+    ring.take = lambda ind: (drawn.append(np.array(ind)), orig_take(ind))[1]
+    np.random.seed(11)
+    torch.manual_seed(11)
+    oracle.train(ring, B)
+    np_state, torch_state = np.random.get_state()[1].copy(), torch.get_rng_state().clone()
+
+    agent = AGENTS[alg](S, A, Space(A), **kw)
+    np.random.seed(11)
+    torch.manual_seed(11)
+    idx, eps = agent._draw(FakeBuffer(), B)
+    assert np.array_equal(np.random.get_state()[1], np_state)
+    assert torch.equal(torch.get_rng_state(), torch_state)
+    assert np.array_equal(idx, np.concatenate(drawn))
+    assert eps.shape == (2 * B * A,)
+
+
+def test_config_mapping_follows_reference_constructors():
+    a = CTRLSACAgent(17, 6, Space(6), discount="0.99", tau="0.005", hidden_dim=1024, feature_dim=2048,
+                     extra_feature_steps=3)  # main.py passes --discount/--tau as strings
+    c = a._config(256)
+    assert c.alg == _lib.ALG["ctrlsac"] and c.feature_steps == 4 and c.actor_hidden_dim == 256
+    assert c.lr_feature == pytest.approx(1e-4) and c.lr_actor == pytest.approx(1e-4 / 3)  # ctrlsac_agent.py:195-197
+    assert c.discount == pytest.approx(0.99) and c.feature_tau == pytest.approx(0.005)
+    s = SACAgent(17, 6, Space(6), hidden_dim=256)
+    c = s._config(256)
+    assert c.lr_critic == pytest.approx(3e-4) and c.feature_steps == 0 and c.target_update_period == 2
+
+
+@pytest.mark.parametrize("alg", list(CASES))
+def test_initial_state_covers_the_oracle_parameter_table(alg):
+    kw, _ = CASES[alg]
+    agent = AGENTS[alg](17, 6, Space(6), **kw)
+    want = O.init_state(alg, 17, 6, kw)
+    have = agent.state_dict()
+    assert set(want) <= set(have)
+    for k, v in want.items():
+        assert tuple(have[k].shape) == tuple(v.shape), k
+    # actor: orthogonal rows / zero bias (utils/util.py:61-66)
+    w = have["actor.trunk.2.weight"]
+    assert torch.allclose(w @ w.t(), torch.eye(w.shape[0]), atol=1e-4)
+    assert float(have["actor.trunk.0.bias"].abs().max()) == 0.0
+
+
+def test_epilogue_struct_matches_header_layout():
+    assert _lib.Epilogue.scale.offset == 60 and __import__("ctypes").sizeof(_lib.Epilogue) == 64

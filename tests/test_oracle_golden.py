@@ -1,0 +1,65 @@
+"""CPU: the oracle (oracle/rl_oracle.py) against the committed golden fixtures, which were produced by running the
+REAL reference agents in the build container (oracle/make_golden.py).  This is what pins the oracle."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import rl_oracle as O
+
+GOLDEN = Path(__file__).resolve().parent / "golden"
+CASES = sorted(p.stem for p in GOLDEN.glob("*.npz"))
+
+
+def test_fixtures_present():
+    assert {"sac_hc_b256", "ctrlsac_small", "ctrlsac_hc_b256", "vlsac_hc_b64", "vlsac_hum_b128", "spedersac_hc_b64",
+            "diffsrsac_hc_b64"} <= set(CASES)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_oracle_reproduces_reference(name):
+    z = np.load(GOLDEN / f"{name}.npz")
+    meta = json.loads(bytes(z["meta_json"]).decode())
+    infos = json.loads(bytes(z["infos_json"]).decode())
+    alg, S, A, kw, B, rows, n = (meta[k] for k in ("alg", "S", "A", "kwargs", "batch", "rows", "n"))
+    extra = {}
+    if "extra/critic_noise" in z:
+        extra["critic_noise"] = torch.from_numpy(z["extra/critic_noise"])
+    init = O.init_state(alg, S, A, kw, seed=0)
+    oracle = O.ORACLES[alg](S, A, init, discount=0.99, tau=0.005, **kw, **extra)
+    ring = O.synthetic_ring(S, A, rows, seed=0)
+    np.random.seed(1)
+    torch.manual_seed(1)
+    got = [oracle.train(ring, B) for _ in range(n)]
+    for step, (g, w) in enumerate(zip(got, infos)):
+        assert set(g) == set(w)
+        for k in w:
+            # fp32 scalars produced by the same op sequence: identical up to thread-count dependent summation order
+            assert abs(g[k] - w[k]) <= 2e-6 + 2e-5 * abs(w[k]), (step, k, g[k], w[k])
+    sd = oracle.state_dict()
+    for k in meta["keys"]:
+        t = sd[k].detach().double().flatten()
+        stats, sample = z["stats/" + k], z["sample/" + k]
+        stride = max(1, t.numel() // 256)
+        got_sample = t[::stride][:256].numpy()
+        # norm-wise (Adam amplifies 1-ulp gradient noise to 2*lr on isolated elements)
+        assert abs(t.norm().item() - stats[1]) <= 1e-5 * max(stats[1], 1e-6), k
+        assert np.linalg.norm(got_sample - sample) <= 2e-5 * max(np.linalg.norm(sample), 1e-6) + 1e-7, k
+
+
+def test_host_ring_follows_reference_semantics():
+    """add() wrap-around, size saturation and fp64 -> fp32 cast at sample time (utils/buffer.py:28-48)."""
+    ring = O.HostRing(3, 2, max_size=5)
+    for i in range(7):
+        ring.add(np.full(3, i + 0.1), np.full(2, -i), np.full(3, i + 0.5), i * 1.5, float(i == 6))
+    assert ring.size == 5 and ring.ptr == 2
+    b = ring.take(np.array([0, 1, 2]))
+    assert b.state.dtype == torch.float32
+    assert torch.equal(b.state[:, 0], torch.tensor([5.1, 6.1, 2.1], dtype=torch.float64).float())
+    assert b.done[1].item() == 1.0 and b.reward.shape == (3, 1)
+    np.random.seed(0)
+    i1 = np.random.randint(0, 5, size=4)
+    np.random.seed(0)
+    assert torch.equal(ring.sample(4).state, ring.take(i1).state)
