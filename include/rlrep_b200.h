@@ -87,6 +87,11 @@ RLREP_EXPORT int rlrep_gemm_bench(void* stream, int path, int M, int N, int K, c
                                   const rlrep_epilogue* epi, int bn, int split_k, float* ws_dev, size_t ws_floats,
                                   int iters, float* ms_out, int* bn_out, int* split_out);
 
+/* Debug aid (library built with -DRLREP_GEMM_TRACE): %globaltimer stamps (ns) taken by CTA (0,0,0) of the most
+ * recent tcgen05 GEMM at: 0 entry, 1 setup done, 2 first operands landed, 3 last MMA issued, 4 accumulator complete,
+ * 5 staged to shared, 6 cluster/CTA sync passed, 7 stores issued, 8 exit. */
+RLREP_EXPORT int rlrep_gemm_trace(unsigned long long* out16_host);
+
 /* ------------------------------------------------------------------------------------------------
  * Replay ring -- replaces utils/buffer.py:13-48 (ReplayBuffer.__init__ / add / sample).
  * Device-resident fp32 ring of packed records [s | a | r | d | pad | s' | pad]; see rlrep_ring_layout.

@@ -73,6 +73,7 @@ def _declare(lib: C.CDLL) -> None:
         "rlrep_gemm": [vp, i, i, i, i, vp, i, i, vp, i, i, vp, i, i, vp, i, C.POINTER(Epilogue), i, i, vp, sz],
         "rlrep_gemm_bench": [vp, i, i, i, i, vp, i, i, vp, i, i, vp, i, C.POINTER(Epilogue), i, i, vp, sz, i,
                              C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)],
+        "rlrep_gemm_trace": [vp],
         "rlrep_ring_create": [i, i, C.c_longlong, C.POINTER(vp)],
         "rlrep_ring_destroy": [vp],
         "rlrep_ring_layout": [vp] + [C.POINTER(i)] * 5,

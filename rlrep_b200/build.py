@@ -26,7 +26,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-fvisibility=hidden",
     "--expt-relaxed-constexpr",
     "-I", str(HERE.parent / "include"),
-]
+] + (["-DRLREP_GEMM_TRACE"] if os.environ.get("RLREP_GEMM_TRACE") else [])
 
 
 def _nvcc() -> str:

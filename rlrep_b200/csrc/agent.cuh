@@ -197,8 +197,15 @@ void linear_fwd(GemmRunner& g, cudaStream_t s, int rows, Mat x, const Linear& l,
 // dx = (dy W) * dact(aux);  n_cols selects the leading columns [col0, col0+n_cols) of the input gradient.
 void linear_dgrad(GemmRunner& g, cudaStream_t s, int rows, Mat dy, const Linear& l, int dact, Mat aux, float* dx,
                   int lddx, int col0 = 0, int n_cols = -1);
-// dW = dy^T x (x may be two K-major segments), db = colsum(dy)
-void linear_wgrad(GemmRunner& g, cudaStream_t s, int rows, Mat dy, Mat x, const Linear& l, Mat x2 = Mat(), int k1 = 0);
+// dW = dy^T x (x may be two K-major segments); db = colsum(dy) is launched here unless `bias_grad` is false (the
+// caller then batches it with other bias gradients through bias_job + launch_colreduce_multi).
+void linear_wgrad(GemmRunner& g, cudaStream_t s, int rows, Mat dy, Mat x, const Linear& l, Mat x2 = Mat(), int k1 = 0,
+                  bool bias_grad = true);
+inline ColJob bias_job(int rows, Mat dy, const Linear& l) {
+  ColJob j;
+  j.X = dy.p; j.ld = dy.ld; j.rows = rows; j.cols = l.out; j.u = nullptr; j.out = l.db;
+  return j;
+}
 
 // ---------------------------------------------------------------------------------------------- graph replay
 // Captures a launch sequence once and replays it; the sequence must only depend on device-resident state.

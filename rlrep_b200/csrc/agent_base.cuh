@@ -18,6 +18,8 @@ class SacBase : public Agent {
     RLREP_CHECK(S_ > 0 && A_ > 0 && B_ > 0, "bad agent dimensions");
   }
   ~SacBase() override {
+    for (cudaEvent_t e : events_) cudaEventDestroy(e);
+    if (side_) cudaStreamDestroy(side_);
     if (metrics_host_) cudaFreeHost(metrics_host_);
     if (idx_host_) cudaFreeHost(idx_host_);
     if (eps_host_) cudaFreeHost(eps_host_);
@@ -93,8 +95,15 @@ class SacBase : public Agent {
     std::memcpy(eps_host_, eps_host, (size_t)ne * sizeof(float));
     RLREP_CUDA(cudaMemcpyAsync(idx_dev_, idx_host_, (size_t)ni * sizeof(long long), cudaMemcpyHostToDevice, stream));
     RLREP_CUDA(cudaMemcpyAsync(eps_dev_, eps_host_, (size_t)ne * sizeof(float), cudaMemcpyHostToDevice, stream));
+    serial_ = true;  // one stream, so consecutive launch events bracket exactly one kernel
     profile_begin(stream);
-    update(ring);
+    try {
+      update(ring);
+    } catch (...) {
+      serial_ = false;
+      throw;
+    }
+    serial_ = false;
     return profile_end(stream);
   }
 
@@ -118,6 +127,36 @@ class SacBase : public Agent {
  protected:
   // One full train() worth of launches on `stream`, reading idx_dev_ / eps_dev_ and writing metrics_dev_.
   virtual void update(Ring& ring) = 0;
+
+  // Independent kernel chains (phi | mu, target | live critic ...) run on a side stream between fork() and join().
+  // Under graph capture these become parallel branches of the graph; each kernel here is latency- rather than
+  // throughput-bound at B = 256, so overlapping two chains hides most of one of them.
+  cudaStream_t side() {
+    if (serial_) return stream;
+    if (side_ == nullptr) RLREP_CUDA(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
+    return side_;
+  }
+  cudaEvent_t next_event() {
+    if (ev_next_ == events_.size()) {
+      cudaEvent_t e;
+      RLREP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      events_.push_back(e);
+    }
+    return events_[ev_next_++];
+  }
+  void fork() {
+    if (serial_) return;
+    cudaEvent_t e = next_event();
+    RLREP_CUDA(cudaEventRecord(e, stream));
+    RLREP_CUDA(cudaStreamWaitEvent(side(), e, 0));
+  }
+  void join() {
+    if (serial_) return;
+    cudaEvent_t e = next_event();
+    RLREP_CUDA(cudaEventRecord(e, side()));
+    RLREP_CUDA(cudaStreamWaitEvent(stream, e, 0));
+  }
+  void begin_update() { ev_next_ = 0; }
 
   void plan_common(int n_idx, int n_eps, int ring_R) {
     R_ = ring_R;
@@ -172,16 +211,24 @@ class SacBase : public Agent {
     linear_fwd(gemm_, stream, B_, Mat{ah2_, AH_}, l2, ACT_NONE, head_, 2 * A_);
     launch_actor_sample(head_, B_, A_, eps, action_out, A_, logp_out, stream);
   }
+  // one launch for the three actor bias gradients (dY buffers of actor_backward are all still live)
+  void actor_bias_grads() {
+    const Linear l0 = a0_.view(actor_g_), l1 = a1_.view(actor_g_), l2 = a2_.view(actor_g_);
+    const ColJob jobs[3] = {bias_job(B_, Mat{dhead_, 2 * A_}, l2), bias_job(B_, Mat{dah2_, AH_}, l1),
+                            bias_job(B_, Mat{dah1_, AH_}, l0)};
+    launch_colreduce_multi(jobs, 3, stream);
+  }
   // Needs d_action_ [B, A] and *dlogp_; the activations of the matching actor_forward(obs, eps, ...) must still be
   // in ah1_/ah2_/head_.  Leaves the actor gradients in actor_g_.g.
   void actor_backward(Mat obs, const float* eps) {
     const Linear l0 = a0_.view(actor_g_), l1 = a1_.view(actor_g_), l2 = a2_.view(actor_g_);
     launch_actor_sample_bwd(head_, B_, A_, eps, d_action_, A_, dlogp_, dhead_, stream);
-    linear_wgrad(gemm_, stream, B_, Mat{dhead_, 2 * A_}, Mat{ah2_, AH_}, l2);
+    linear_wgrad(gemm_, stream, B_, Mat{dhead_, 2 * A_}, Mat{ah2_, AH_}, l2, Mat(), 0, false);
     linear_dgrad(gemm_, stream, B_, Mat{dhead_, 2 * A_}, l2, DACT_ELU_OUT, Mat{ah2_, AH_}, dah2_, AH_);
-    linear_wgrad(gemm_, stream, B_, Mat{dah2_, AH_}, Mat{ah1_, AH_}, l1);
+    linear_wgrad(gemm_, stream, B_, Mat{dah2_, AH_}, Mat{ah1_, AH_}, l1, Mat(), 0, false);
     linear_dgrad(gemm_, stream, B_, Mat{dah2_, AH_}, l1, DACT_ELU_OUT, Mat{ah1_, AH_}, dah1_, AH_);
-    linear_wgrad(gemm_, stream, B_, Mat{dah1_, AH_}, obs, l0);
+    linear_wgrad(gemm_, stream, B_, Mat{dah1_, AH_}, obs, l0, Mat(), 0, false);
+    actor_bias_grads();
   }
   void actor_adam() {
     launch_adam_polyak(actor_g_.p, actor_g_.g, actor_g_.m, actor_g_.v, actor_g_.n, &ctl->actor, nullptr, 0, 0.f,
@@ -200,6 +247,10 @@ class SacBase : public Agent {
   }
 
   int S_ = 0, A_ = 0, B_ = 0, AH_ = 0, R_ = 0;
+  cudaStream_t side_ = nullptr;
+  std::vector<cudaEvent_t> events_;
+  size_t ev_next_ = 0;
+  bool serial_ = false;
   DeviceArena arena_;
   GemmRunner gemm_;
   GraphReplay graph_;

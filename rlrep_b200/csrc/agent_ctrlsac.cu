@@ -67,6 +67,10 @@ class CtrlSacAgent final : public SacBase {
     arena_.want(&dzmu_, BD);
     arena_.want(&dh2_, BH);
     arena_.want(&dh1_, BH);
+    arena_.want(&dg2_, BH);
+    arena_.want(&dg1_, BH);
+    arena_.want(&hb1_, BH);
+    arena_.want(&hb2_, BH);
     arena_.want(&logits_, (size_t)B_ * B_);
     arena_.want(&loss_rows_, B_);
     arena_.want(&rpred_, B_);
@@ -101,6 +105,7 @@ class CtrlSacAgent final : public SacBase {
 
  protected:
   void update(Ring& ring) override {
+    begin_update();
     launch_tick(ctl, base_tick(), stream);
     for (int k = 0; k < K_; ++k) {
       launch_gather(ring.data, R_ / 4, idx_dev_ + (size_t)k * B_, B_, batch_, stream);
@@ -116,12 +121,13 @@ class CtrlSacAgent final : public SacBase {
   const float* reward() const { return batch_ + off_r_; }
   const float* done() const { return batch_ + off_d_; }
 
-  // phi(x) with x = cat of one or two segments; leaves h1_/h2_ (needed by backward) and writes z [B, D].
-  void phi_forward(Mat x, Mat x2, int k1, float* z) {
+  // phi(x) with x = cat of one or two segments, on stream `s`; hidden activations go to (h1, h2) -- h1_/h2_ when a
+  // backward pass follows -- and the features to z [B, D].
+  void phi_forward(cudaStream_t s, Mat x, Mat x2, int k1, float* z, float* h1, float* h2) {
     const Linear l1 = p1_.view(feat_g_), l2 = p2_.view(feat_g_), l3 = p3_.view(feat_g_);
-    linear_fwd(gemm_, stream, B_, x, l1, ACT_ELU, h1_, H_, x2, k1);
-    linear_fwd(gemm_, stream, B_, Mat{h1_, H_}, l2, ACT_ELU, h2_, H_);
-    linear_fwd(gemm_, stream, B_, Mat{h2_, H_}, l3, ACT_NONE, z, D_);
+    linear_fwd(gemm_, s, B_, x, l1, ACT_ELU, h1, H_, x2, k1);
+    linear_fwd(gemm_, s, B_, Mat{h1, H_}, l2, ACT_ELU, h2, H_);
+    linear_fwd(gemm_, s, B_, Mat{h2, H_}, l3, ACT_NONE, z, D_);
   }
 
   void feature_step(int k) {  // ctrlsac_agent.py:213-251
@@ -129,23 +135,27 @@ class CtrlSacAgent final : public SacBase {
     const Linear n1 = m1_.view(feat_g_), n2 = m2_.view(feat_g_), n3 = m3_.view(feat_g_);
     const Linear th = th_.view(feat_g_);
     const float inv_b = 1.f / (float)B_;
-    // ---- forward
-    phi_forward(sa(), Mat(), 0, zphi_);
-    linear_fwd(gemm_, stream, B_, s2(), n1, ACT_ELU, g1_, H_);
-    linear_fwd(gemm_, stream, B_, Mat{g1_, H_}, n2, ACT_ELU, g2_, H_);
-    linear_fwd(gemm_, stream, B_, Mat{g2_, H_}, n3, ACT_TANH, zmu_, D_);
+    cudaStream_t s0 = stream, s1 = side();
+    // ---- forward: phi on the main stream, mu on the side stream
+    fork();
+    phi_forward(s0, sa(), Mat(), 0, zphi_, h1_, h2_);
+    linear_fwd(gemm_, s1, B_, s2(), n1, ACT_ELU, g1_, H_);
+    linear_fwd(gemm_, s1, B_, Mat{g1_, H_}, n2, ACT_ELU, g2_, H_);
+    linear_fwd(gemm_, s1, B_, Mat{g2_, H_}, n3, ACT_TANH, zmu_, D_);
+    join();
     {  // logits[i, j] = <phi_i, mu_j>  (the reference's [B,1,D]*[1,B,D] broadcast, :229, as a tensor-core GEMM)
       GemmArgs a;
       a.M = B_; a.N = B_; a.K = D_;
       a.A = zphi_; a.lda = D_;
       a.B = zmu_; a.ldb = D_;
       a.C = logits_; a.ldc = B_;
-      gemm_.run(a, stream);
+      gemm_.run(a, s0);
     }
-    launch_ce_rows(logits_, B_, B_, B_, 0, inv_b, loss_rows_, stream);  // logits_ now holds dL/dlogits
-    launch_rowdot(zphi_, D_, B_, D_, th.W, th.b, rpred_, stream);
-    launch_feature_loss_finalize(loss_rows_, B_, rpred_, reward(), R_, inv_b, drp_, metrics_dev_ + 0, stream);
-    // ---- backward into the embeddings
+    launch_ce_rows(logits_, B_, B_, B_, 0, inv_b, loss_rows_, s0);  // logits_ now holds dL/dlogits
+    launch_rowdot(zphi_, D_, B_, D_, th.W, th.b, rpred_, s0);
+    launch_feature_loss_finalize(loss_rows_, B_, rpred_, reward(), R_, inv_b, drp_, metrics_dev_ + 0, s0);
+    // ---- backward: the phi branch (with theta) on the main stream, the mu branch on the side stream
+    fork();
     {  // d z_phi = G mu + drp (x) theta.w
       GemmArgs a;
       a.M = B_; a.N = D_; a.K = B_;
@@ -153,7 +163,18 @@ class CtrlSacAgent final : public SacBase {
       a.B = zmu_; a.ldb = D_; a.b_mn = true;
       a.C = dzphi_; a.ldc = D_;
       a.epi.r1_u = drp_; a.epi.r1_v = th.W;
-      gemm_.run(a, stream);
+      gemm_.run(a, s0);
+    }
+    linear_wgrad(gemm_, s0, B_, Mat{dzphi_, D_}, Mat{h2_, H_}, l3, Mat(), 0, false);
+    linear_dgrad(gemm_, s0, B_, Mat{dzphi_, D_}, l3, DACT_ELU_OUT, Mat{h2_, H_}, dh2_, H_);
+    linear_wgrad(gemm_, s0, B_, Mat{dh2_, H_}, Mat{h1_, H_}, l2, Mat(), 0, false);
+    linear_dgrad(gemm_, s0, B_, Mat{dh2_, H_}, l2, DACT_ELU_OUT, Mat{h1_, H_}, dh1_, H_);
+    linear_wgrad(gemm_, s0, B_, Mat{dh1_, H_}, sa(), l1, Mat(), 0, false);
+    {
+      ColJob jobs[5] = {bias_job(B_, Mat{dzphi_, D_}, l3), bias_job(B_, Mat{dh2_, H_}, l2),
+                        bias_job(B_, Mat{dh1_, H_}, l1), ColJob{zphi_, drp_, th.dW, D_, B_, D_},  // d theta.w
+                        ColJob{drp_, nullptr, th.db, 1, B_, 1}};                                  // d theta.b
+      launch_colreduce_multi(jobs, 5, s0);
     }
     {  // d (pre-tanh mu) = (G^T phi) * (1 - mu^2)
       GemmArgs a;
@@ -162,34 +183,31 @@ class CtrlSacAgent final : public SacBase {
       a.B = zphi_; a.ldb = D_; a.b_mn = true;
       a.C = dzmu_; a.ldc = D_;
       a.epi.dact = DACT_TANH_OUT; a.epi.aux = zmu_; a.epi.ld_aux = D_;
-      gemm_.run(a, stream);
+      gemm_.run(a, s1);
     }
-    launch_colreduce(zphi_, D_, B_, D_, drp_, th.dW, 0, stream);  // d theta.w
-    launch_colreduce(drp_, 1, B_, 1, nullptr, th.db, 0, stream);  // d theta.b
-    // ---- phi backward
-    linear_wgrad(gemm_, stream, B_, Mat{dzphi_, D_}, Mat{h2_, H_}, l3);
-    linear_dgrad(gemm_, stream, B_, Mat{dzphi_, D_}, l3, DACT_ELU_OUT, Mat{h2_, H_}, dh2_, H_);
-    linear_wgrad(gemm_, stream, B_, Mat{dh2_, H_}, Mat{h1_, H_}, l2);
-    linear_dgrad(gemm_, stream, B_, Mat{dh2_, H_}, l2, DACT_ELU_OUT, Mat{h1_, H_}, dh1_, H_);
-    linear_wgrad(gemm_, stream, B_, Mat{dh1_, H_}, sa(), l1);
-    // ---- mu backward
-    linear_wgrad(gemm_, stream, B_, Mat{dzmu_, D_}, Mat{g2_, H_}, n3);
-    linear_dgrad(gemm_, stream, B_, Mat{dzmu_, D_}, n3, DACT_ELU_OUT, Mat{g2_, H_}, dh2_, H_);
-    linear_wgrad(gemm_, stream, B_, Mat{dh2_, H_}, Mat{g1_, H_}, n2);
-    linear_dgrad(gemm_, stream, B_, Mat{dh2_, H_}, n2, DACT_ELU_OUT, Mat{g1_, H_}, dh1_, H_);
-    linear_wgrad(gemm_, stream, B_, Mat{dh1_, H_}, s2(), n1);
+    linear_wgrad(gemm_, s1, B_, Mat{dzmu_, D_}, Mat{g2_, H_}, n3, Mat(), 0, false);
+    linear_dgrad(gemm_, s1, B_, Mat{dzmu_, D_}, n3, DACT_ELU_OUT, Mat{g2_, H_}, dg2_, H_);
+    linear_wgrad(gemm_, s1, B_, Mat{dg2_, H_}, Mat{g1_, H_}, n2, Mat(), 0, false);
+    linear_dgrad(gemm_, s1, B_, Mat{dg2_, H_}, n2, DACT_ELU_OUT, Mat{g1_, H_}, dg1_, H_);
+    linear_wgrad(gemm_, s1, B_, Mat{dg1_, H_}, s2(), n1, Mat(), 0, false);
+    {
+      ColJob jobs[3] = {bias_job(B_, Mat{dzmu_, D_}, n3), bias_job(B_, Mat{dg2_, H_}, n2),
+                        bias_job(B_, Mat{dg1_, H_}, n1)};
+      launch_colreduce_multi(jobs, 3, s1);
+    }
+    join();
     // ---- one fused Adam over phi | mu | theta, plus Polyak of phi_target (:242-244, :253-255)
     launch_adam_polyak(feat_g_.p, feat_g_.g, feat_g_.m, feat_g_.v, feat_g_.n, &ctl->feat[k],
                        cfg.use_feature_target ? feat_g_.target : nullptr, feat_g_.n_target, cfg.feature_tau, nullptr,
-                       stream);
+                       s0);
   }
 
   // twin heads on features z: hid = elu(z [l1|l4]^T + b), q1 = hid[:, :H] . l2, q2 = hid[:, H:] . l5
-  void critic_forward(const float* z, bool target, float* hid, float* q1, float* q2) {
+  void critic_forward(cudaStream_t s, const float* z, bool target, float* hid, float* q1, float* q2) {
     const Linear l14 = c14_.view(crit_g_, target), l2 = c2_.view(crit_g_, target), l5 = c5_.view(crit_g_, target);
-    linear_fwd(gemm_, stream, B_, Mat{z, D_}, l14, ACT_ELU, hid, 2 * H_);
-    launch_rowdot(hid, 2 * H_, B_, H_, l2.W, l2.b, q1, stream);
-    launch_rowdot(hid + H_, 2 * H_, B_, H_, l5.W, l5.b, q2, stream);
+    linear_fwd(gemm_, s, B_, Mat{z, D_}, l14, ACT_ELU, hid, 2 * H_);
+    launch_rowdot(hid, 2 * H_, B_, H_, l2.W, l2.b, q1, s);
+    launch_rowdot(hid + H_, 2 * H_, B_, H_, l5.W, l5.b, q2, s);
   }
   // d hid from (dq1, dq2) through the N = 1 heads and the ELU
   void critic_heads_backward_to_hidden() {
@@ -200,33 +218,40 @@ class CtrlSacAgent final : public SacBase {
 
   void critic_step() {  // ctrlsac_agent.py:257-293
     const float* eps = eps_dev_;
-    actor_forward(s2(), eps, a2_act_, logp2_);                     // a' ~ pi(s'), log pi(a'|s')
-    phi_forward(s2(), Mat{a2_act_, A_}, S_, zmu_);                 // frozen_phi_target(s', a')  (zmu_ is free now)
-    critic_forward(zmu_, /*target=*/true, hid_t_, nq1_, nq2_);
-    phi_forward(sa(), Mat(), 0, zphi_);                            // frozen_phi_target(s, a)
-    critic_forward(zphi_, /*target=*/false, hid_, q1_, q2_);
+    cudaStream_t s0 = stream, s1 = side();
+    fork();
+    // main stream: a' ~ pi(s'), frozen_phi_target(s', a'), target critic
+    actor_forward(s2(), eps, a2_act_, logp2_);
+    phi_forward(s0, s2(), Mat{a2_act_, A_}, S_, zmu_, h1_, h2_);  // zmu_ is free after the feature loop
+    critic_forward(s0, zmu_, /*target=*/true, hid_t_, nq1_, nq2_);
+    // side stream: frozen_phi_target(s, a) and the live critic on it
+    phi_forward(s1, sa(), Mat(), 0, zphi_, hb1_, hb2_);
+    critic_forward(s1, zphi_, /*target=*/false, hid_, q1_, q2_);
+    join();
     launch_td_critic_loss(reward(), done(), R_, nq1_, nq2_, logp2_, q1_, q2_, B_, cfg.discount, ctl, dq1_, dq2_,
-                          metrics_dev_ + 3, stream);
+                          metrics_dev_ + 3, s0);
     // ---- backward (critic parameters only; the features are under no_grad)
     const Linear l14 = c14_.view(crit_g_), l2 = c2_.view(crit_g_), l5 = c5_.view(crit_g_);
     critic_heads_backward_to_hidden();
-    launch_colreduce(hid_, 2 * H_, B_, H_, dq1_, l2.dW, 0, stream);
-    launch_colreduce(dq1_, 1, B_, 1, nullptr, l2.db, 0, stream);
-    launch_colreduce(hid_ + H_, 2 * H_, B_, H_, dq2_, l5.dW, 0, stream);
-    launch_colreduce(dq2_, 1, B_, 1, nullptr, l5.db, 0, stream);
-    linear_wgrad(gemm_, stream, B_, Mat{dhid_, 2 * H_}, Mat{zphi_, D_}, l14);
+    {
+      ColJob jobs[5] = {ColJob{hid_, dq1_, l2.dW, 2 * H_, B_, H_}, ColJob{dq1_, nullptr, l2.db, 1, B_, 1},
+                        ColJob{hid_ + H_, dq2_, l5.dW, 2 * H_, B_, H_}, ColJob{dq2_, nullptr, l5.db, 1, B_, 1},
+                        bias_job(B_, Mat{dhid_, 2 * H_}, l14)};
+      launch_colreduce_multi(jobs, 5, s0);
+    }
+    linear_wgrad(gemm_, s0, B_, Mat{dhid_, 2 * H_}, Mat{zphi_, D_}, l14, Mat(), 0, false);
     // Adam on the critic; its Polyak (sac_agent.py:99-102, every `period` steps) only reads the updated critic and
     // nothing between here and the end of train() writes it, so it rides in the same launch.
     launch_adam_polyak(crit_g_.p, crit_g_.g, crit_g_.m, crit_g_.v, crit_g_.n, &ctl->critic, crit_g_.target,
-                       crit_g_.n_target, cfg.tau, &ctl->polyak_critic, stream);
+                       crit_g_.n_target, cfg.tau, &ctl->polyak_critic, s0);
   }
 
   void actor_step() {  // ctrlsac_agent.py:295-325
     const float* eps = eps_dev_ + (size_t)B_ * A_;
     const Mat s{batch_, R_};
     actor_forward(s, eps, action_, logp_);
-    phi_forward(s, Mat{action_, A_}, S_, zphi_);  // frozen_phi(s, a_pi)
-    critic_forward(zphi_, false, hid_, q1_, q2_);
+    phi_forward(stream, s, Mat{action_, A_}, S_, zphi_, h1_, h2_);  // frozen_phi(s, a_pi)
+    critic_forward(stream, zphi_, false, hid_, q1_, q2_);
     launch_actor_alpha_loss(q1_, q2_, logp_, B_, (float)(-A_), cfg.learn_alpha, ctl, dq1_, dq2_, dlogp_,
                             metrics_dev_ + 7, stream);
     // ---- dgrad only, back to the action input of phi
@@ -246,6 +271,7 @@ class CtrlSacAgent final : public SacBase {
   LinearSlot p1_, p2_, p3_, m1_, m2_, m3_, th_, c14_, c2_, c5_;
   float *h1_ = nullptr, *h2_ = nullptr, *g1_ = nullptr, *g2_ = nullptr, *zphi_ = nullptr, *zmu_ = nullptr;
   float *dzphi_ = nullptr, *dzmu_ = nullptr, *dh2_ = nullptr, *dh1_ = nullptr, *logits_ = nullptr;
+  float *dg2_ = nullptr, *dg1_ = nullptr, *hb1_ = nullptr, *hb2_ = nullptr;
   float *loss_rows_ = nullptr, *rpred_ = nullptr, *drp_ = nullptr, *hid_ = nullptr, *hid_t_ = nullptr,
         *dhid_ = nullptr;
   float *q1_ = nullptr, *q2_ = nullptr, *nq1_ = nullptr, *nq2_ = nullptr, *dq1_ = nullptr, *dq2_ = nullptr;

@@ -67,6 +67,7 @@ class SacAgent final : public SacBase {
 
  protected:
   void update(Ring& ring) override {  // sac_agent.py:169-188
+    begin_update();
     TickParams t = base_tick();
     t.k_feat = 0;
     launch_tick(ctl, t, stream);

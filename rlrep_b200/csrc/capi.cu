@@ -37,6 +37,17 @@ Epilogue to_epilogue(const rlrep_epilogue* e) {
 
 using namespace rlrep;
 
+// Calibration kernels for rlrep_gemm_bench (path 2 / 3): an empty kernel, plain and with programmatic dependent
+// launch, to measure the per-launch floor of a dependent kernel chain on this GPU.
+__global__ void null_kernel(float* p) {
+  if (p == reinterpret_cast<float*>(1)) *p = 0.f;
+}
+__global__ void null_pdl_kernel(float* p) {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  if (p == reinterpret_cast<float*>(1)) *p = 0.f;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 struct rlrep_ring {
   std::unique_ptr<Ring> impl;
 };
@@ -118,7 +129,20 @@ int rlrep_gemm_bench(void* stream, int path, int M, int N, int K, const float* A
   }
   auto launch_once = [&](cudaStream_t s) {
     if (path == 0) launch_tc(p, s);
-    else launch_simt(g, s);
+    else if (path == 1) launch_simt(g, s);
+    else if (path == 2) null_kernel<<<M, 128, 0, s>>>(C);
+    else {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(M);
+      cfg.blockDim = dim3(128);
+      cfg.stream = s;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+      at[0].val.programmaticStreamSerializationAllowed = 1;
+      cfg.attrs = at;
+      cfg.numAttrs = 1;
+      RLREP_CUDA(cudaLaunchKernelEx(&cfg, null_pdl_kernel, C));
+    }
   };
   for (int i = 0; i < 3; ++i) launch_once(st);
   // Replay through a CUDA graph so the number is device time, not the host's launch rate.
@@ -145,6 +169,13 @@ int rlrep_gemm_bench(void* stream, int path, int M, int N, int K, const float* A
   *ms_out = ms / iters;
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
+  RLREP_API_END
+}
+
+int rlrep_gemm_trace(unsigned long long* out16_host) {
+  RLREP_API_BEGIN
+  RLREP_CUDA(cudaDeviceSynchronize());
+  read_gemm_trace(out16_host);
   RLREP_API_END
 }
 

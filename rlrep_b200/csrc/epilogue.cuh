@@ -52,15 +52,41 @@ __device__ __forceinline__ float apply_dact(float h, int dact) {
 }
 
 // One element. `cptr` points at C[m, n]; used only for accumulate.
+// ACT / DACT >= 0 fix the activation / derivative at compile time (tight store loops: the transcendental code of
+// the other cases is not even instantiated); -1 selects them at run time from the struct.
+template <int ACT = -1, int DACT = -1>
 __device__ __forceinline__ float epilogue_apply(const Epilogue& e, float acc, int m, int n, const float* cptr) {
   float v = acc * e.scale;
   if (e.r1_u) v = fmaf(__ldg(e.r1_u + m), __ldg(e.r1_v + n), v);
   if (e.bias) v += __ldg(e.bias + n);
   if (e.pre_out) e.pre_out[(size_t)m * e.ld_pre + n] = v;
-  v = apply_act(v, e.act);
-  if (e.dact != DACT_NONE) v *= apply_dact(e.aux[(size_t)m * e.ld_aux + n], e.dact);
+  if constexpr (ACT < 0) v = apply_act(v, e.act);
+  else if constexpr (ACT != ACT_NONE) v = apply_act(v, ACT);
+  if constexpr (DACT < 0) {
+    if (e.dact != DACT_NONE) v *= apply_dact(e.aux[(size_t)m * e.ld_aux + n], e.dact);
+  } else if constexpr (DACT != DACT_NONE) {
+    v *= apply_dact(e.aux[(size_t)m * e.ld_aux + n], DACT);
+  }
   if (e.accumulate) v += *cptr;
   return v;
 }
+
+// Expands CALL(ACT, DACT) for the (activation, derivative) pair of `e`: the pairs the update step uses get a
+// specialised instantiation, anything else the run-time version CALL(-1, -1).
+#define RLREP_EPILOGUE_SWITCH(e, CALL)                                      \
+  do {                                                                      \
+    switch ((e).act * 8 + (e).dact) {                                       \
+      case ACT_NONE * 8 + DACT_NONE: CALL(ACT_NONE, DACT_NONE); break;      \
+      case ACT_ELU * 8 + DACT_NONE: CALL(ACT_ELU, DACT_NONE); break;        \
+      case ACT_RELU * 8 + DACT_NONE: CALL(ACT_RELU, DACT_NONE); break;      \
+      case ACT_TANH * 8 + DACT_NONE: CALL(ACT_TANH, DACT_NONE); break;      \
+      case ACT_SIN * 8 + DACT_NONE: CALL(ACT_SIN, DACT_NONE); break;        \
+      case ACT_NONE * 8 + DACT_ELU_OUT: CALL(ACT_NONE, DACT_ELU_OUT); break;    \
+      case ACT_NONE * 8 + DACT_RELU_OUT: CALL(ACT_NONE, DACT_RELU_OUT); break;  \
+      case ACT_NONE * 8 + DACT_TANH_OUT: CALL(ACT_NONE, DACT_TANH_OUT); break;  \
+      case ACT_NONE * 8 + DACT_COS_PRE: CALL(ACT_NONE, DACT_COS_PRE); break;    \
+      default: CALL(-1, -1); break;                                         \
+    }                                                                       \
+  } while (0)
 
 }  // namespace rlrep

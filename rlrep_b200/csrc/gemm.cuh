@@ -50,6 +50,8 @@ bool tc_eligible(const GemmArgs& a);
 // bn / split_k = 0 picks them automatically (fill ~148 SMs). ws may be null (forces split_k = 1).
 TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* ws, size_t ws_floats);
 void launch_tc(const TcGemmPlan& p, cudaStream_t stream);
+// Debug builds (-DRLREP_GEMM_TRACE): %globaltimer stamps of CTA (0,0,0) of the last tcgen05 GEMM.
+void read_gemm_trace(unsigned long long* out16);
 
 // ---- CUDA-core path (exact FP32 FFMA; small-K / small-N layers and the strict-fp32 mode) ----
 void launch_simt(const GemmArgs& a, cudaStream_t stream);

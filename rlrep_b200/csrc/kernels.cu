@@ -159,6 +159,34 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const float* __restrict_
   }
 }
 
+struct ColJobs {
+  ColJob j[kMaxColJobs];
+};
+__global__ void __launch_bounds__(256) colreduce_multi_kernel(const ColJobs jobs) {
+  __shared__ float part[8][33];
+  const ColJob& jb = jobs.j[blockIdx.y];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  if (blockIdx.x * 32 >= jb.cols) return;
+  float acc = 0.f;
+  if (j < jb.cols) {
+    const float* x = jb.X + j;
+#pragma unroll 4
+    for (int i = ty; i < jb.rows; i += 8) {
+      const float v = x[(size_t)i * jb.ld];
+      acc = jb.u ? fmaf(__ldg(jb.u + i), v, acc) : acc + v;
+    }
+  }
+  part[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && j < jb.cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) t += part[k][tx];
+    jb.out[j] = t;
+  }
+}
+
 __global__ void outer_dact_kernel(const float* __restrict__ u, const float* __restrict__ w, int rows, int cols,
                                   const float* __restrict__ aux, int ld_aux, int dact, float* __restrict__ out,
                                   int ld_out) {
@@ -423,6 +451,18 @@ void launch_colreduce(const float* X, int ld, int rows, int cols, const float* u
                       cudaStream_t s) {
   colreduce_kernel<<<ceil_div(cols, 32), 256, 0, s>>>(X, ld, rows, cols, u, out, accumulate);
   RLREP_LAUNCHED("colreduce", s);
+}
+
+void launch_colreduce_multi(const ColJob* jobs, int n_jobs, cudaStream_t s) {
+  RLREP_CHECK(n_jobs >= 1 && n_jobs <= kMaxColJobs, "too many column-reduction jobs for one launch");
+  ColJobs js;
+  int max_cols = 0;
+  for (int i = 0; i < n_jobs; ++i) {
+    js.j[i] = jobs[i];
+    if (jobs[i].cols > max_cols) max_cols = jobs[i].cols;
+  }
+  colreduce_multi_kernel<<<dim3(ceil_div(max_cols, 32), n_jobs), 256, 0, s>>>(js);
+  RLREP_LAUNCHED("colreduce_multi", s);
 }
 
 void launch_outer_dact(const float* u, const float* w, int rows, int cols, const float* aux, int ld_aux, int dact,

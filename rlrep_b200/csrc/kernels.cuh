@@ -55,6 +55,15 @@ void launch_rowdot(const float* X, int ld, int rows, int D, const float* w, cons
 // out[j] (+)= sum_i u[i] * X[i,j]   (u == nullptr: plain column sum).  Deterministic.
 void launch_colreduce(const float* X, int ld, int rows, int cols, const float* u, float* out, int accumulate,
                       cudaStream_t s);
+// Several column reductions in one launch (all the bias gradients of a network's backward pass).
+struct ColJob {
+  const float* X;
+  const float* u;  // optional row weights
+  float* out;
+  int ld, rows, cols;
+};
+constexpr int kMaxColJobs = 8;
+void launch_colreduce_multi(const ColJob* jobs, int n_jobs, cudaStream_t s);
 // out[i,j] = u[i] * w[j] * dact(aux[i,j])   (backward of an N = 1 head into its hidden layer)
 void launch_outer_dact(const float* u, const float* w, int rows, int cols, const float* aux, int ld_aux, int dact,
                        float* out, int ld_out, cudaStream_t s);

@@ -199,7 +199,8 @@ void linear_dgrad(GemmRunner& g, cudaStream_t s, int rows, Mat dy, const Linear&
   g.run(a, s);
 }
 
-void linear_wgrad(GemmRunner& g, cudaStream_t s, int rows, Mat dy, Mat x, const Linear& l, Mat x2, int k1) {
+void linear_wgrad(GemmRunner& g, cudaStream_t s, int rows, Mat dy, Mat x, const Linear& l, Mat x2, int k1,
+                  bool bias_grad) {
   // dW[out, in] = sum_b dy[b, out] x[b, in]:  A = dy (MN-major, k = batch), B = x (MN-major)
   if (x2.p == nullptr) {
     GemmArgs a;
@@ -222,7 +223,7 @@ void linear_wgrad(GemmRunner& g, cudaStream_t s, int rows, Mat dy, Mat x, const 
     b.C = l.dW + k1;
     g.run(b, s);
   }
-  launch_colreduce(dy.p, dy.ld, rows, l.out, nullptr, l.db, 0, s);
+  if (bias_grad) launch_colreduce(dy.p, dy.ld, rows, l.out, nullptr, l.db, 0, s);
 }
 
 // ================================================================================================ GraphReplay

@@ -16,7 +16,7 @@ def run_variant(path, a_mn, b_mn, bn, split_k):
     from rlrep_b200 import _lib
     torch.manual_seed(0)
     dev = "cuda"
-    shapes = [(256, 2048, 1024), (256, 256, 2048), (2048, 1024, 256), (128, 128, 32), (200, 136, 100),
+    shapes = [(256, 2048, 1024), (256, 256, 2048), (2048, 1024, 256), (128, 128, 32), (224, 160, 100),
               (256, 1024, 2048), (1024, 23 * 4, 256)]
     out = []
     for (M, N, K) in shapes:

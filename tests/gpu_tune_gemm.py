@@ -26,7 +26,7 @@ for label, M, N, K, a_mn, b_mn in shapes:
     ws = torch.empty(16 * M * N if M * N < (1 << 22) else 1, device=dev)
     res = []
     for bn in (32, 64, 128, 256):
-        for sk in (1, 2, 4, 8, 16):
+        for sk in (1, 2, 4, 8):
             if sk > 1 and M * N >= (1 << 22):
                 continue
             ms, bno, so = _lib.gemm_bench(A, B, Cm, a_mn=bool(a_mn), b_mn=bool(b_mn), bn=bn, split_k=sk, ws=ws, iters=200)

@@ -23,6 +23,10 @@ HC = dict(S=17, A=6)
 def test_gemm_tf32_all_majors(lib, a_mn, b_mn, shape):
     from rlrep_b200 import _lib
     M, N, K = shape
+    if a_mn and M % 32:
+        M = (M + 31) // 32 * 32  # MN-major operands are fetched through a (mn % 32, k, mn / 32) TMA view
+    if b_mn and N % 32:
+        N = (N + 31) // 32 * 32
     torch.manual_seed(0)
     A = torch.randn((K, M) if a_mn else (M, K), device="cuda")
     B = torch.randn((K, N) if b_mn else (N, K), device="cuda")
@@ -48,6 +52,15 @@ def test_gemm_fp32_cuda_cores(lib, a_mn, b_mn):
     _lib.gemm(A, B, C, a_mn=bool(a_mn), b_mn=bool(b_mn), path="simt")
     ref = (A.t() if a_mn else A).double() @ (B.t() if b_mn else B).double().t()
     assert ((C.double() - ref).norm() / ref.norm()).item() < 1e-5
+
+
+def test_gemm_tf32_rejects_unfetchable_operands(lib):
+    from rlrep_b200 import _lib
+    A, B, C = torch.randn(64, 100, device="cuda"), torch.randn(64, 72, device="cuda"), torch.empty(100, 72, device="cuda")
+    with pytest.raises(_lib.RlrepError):  # MN-major with mn % 32 != 0 must be refused loudly (CUDA-core path handles it)
+        _lib.gemm(A, B, C, a_mn=True, b_mn=True, path="tc")
+    _lib.gemm(A, B, C, a_mn=True, b_mn=True, path="simt")
+    assert ((C.double() - A.double().t() @ B.double()).norm() / C.double().norm()).item() < 1e-5
 
 
 def test_gemm_two_segment_input_and_derivative_epilogue(lib):
