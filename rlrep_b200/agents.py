@@ -306,4 +306,59 @@ class CTRLSACAgent(SACAgent):
         return dict(zip(self._h.metric_names, (float(x) for x in m)))
 
 
-AGENTS = {"sac": SACAgent, "ctrlsac": CTRLSACAgent}
+class VLSACAgent(SACAgent):
+    """Drop-in for agent.vlsac.vlsac_agent.VLSACAgent (vlsac_agent.py:66-273, networks/vae.py)."""
+
+    alg = "vlsac"
+    NUM_NOISE = 20  # vlsac_agent.py:24
+
+    def __init__(self, state_dim, action_dim, action_space, lr=1e-4, discount=0.99, target_update_period=2, tau=0.005,
+                 alpha=0.1, auto_entropy_tuning=True, hidden_dim=256, feature_tau=0.001, feature_dim=256,
+                 use_feature_target=True, extra_feature_steps=1, **kw):
+        self.feature_dim, self.feature_tau = int(feature_dim), float(feature_tau)
+        self.use_feature_target, self.extra_feature_steps = bool(use_feature_target), int(extra_feature_steps)
+        super().__init__(state_dim, action_dim, action_space, lr=lr, discount=discount,
+                         target_update_period=target_update_period, tau=tau, alpha=alpha,
+                         auto_entropy_tuning=auto_entropy_tuning, hidden_dim=hidden_dim, **kw)
+        # the critic's fixed noise is drawn once at construction from the global generator (vlsac_agent.py:30-31)
+        self._pending_state["critic.noise"] = torch.randn([self.NUM_NOISE, self.feature_dim])
+
+    def _config(self, batch_size):
+        c = super()._config(batch_size)
+        c.feature_dim = self.feature_dim
+        c.feature_steps = self.extra_feature_steps + 1
+        c.lr_feature = self._lr          # vlsac_agent.py:113-115; actor / alpha keep SACAgent's optimisers (lr)
+        c.feature_tau = self.feature_tau
+        c.use_feature_target = int(self.use_feature_target)
+        c.num_noise = self.NUM_NOISE
+        return c
+
+    def _layers(self):
+        S, A, H, D = self.state_dim, self.action_dim, self._hidden, self.feature_dim
+        V = 256  # networks/vae.py hidden_dim defaults
+        d = "default"
+        return [("encoder.l1", V, 2 * S + A, d), ("encoder.l2", V, V, d), ("encoder.mean_linear", D, V, d),
+                ("encoder.log_std_linear", D, V, d), ("decoder.l1", V, D, d), ("decoder.state_linear", S, V, d),
+                ("decoder.reward_linear", 1, V, d), ("f.l1", V, S + A, d), ("f.l2", V, V, d),
+                ("f.mean_linear", D, V, d), ("f.log_std_linear", D, V, d)] + self._actor_layers(H) + \
+               [("critic.l1", H, D, d), ("critic.l2", H, H, d), ("critic.l3", 1, H, d), ("critic.l4", H, D, d),
+                ("critic.l5", H, H, d), ("critic.l6", 1, H, d)]
+
+    @property
+    def critic_noise(self):
+        return self.state_dict()["critic.noise"]
+
+    def _draw(self, buffer, batch_size):  # SURVEY A.5: K x (randint[B] -> randn[B,D]) -> randn[B,A] -> randn[B,A]
+        K = self.extra_feature_steps + 1
+        idx, eps = [], []
+        for _ in range(K):
+            idx.append(np.random.randint(0, buffer.size, size=batch_size))
+            eps.append(torch.randn(batch_size, self.feature_dim).reshape(-1))
+        eps += [torch.randn(batch_size, self.action_dim).reshape(-1) for _ in range(2)]
+        return np.concatenate(idx), torch.cat(eps).numpy()
+
+    def _info(self, m):
+        return dict(zip(self._h.metric_names, (float(x) for x in m)))
+
+
+AGENTS = {"sac": SACAgent, "ctrlsac": CTRLSACAgent, "vlsac": VLSACAgent}

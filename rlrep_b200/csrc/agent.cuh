@@ -61,8 +61,9 @@ class DeviceArena {
 // ---------------------------------------------------------------------------------------------- parameters
 struct ParamTensor {
   std::string name;  // reference state_dict name, e.g. "phi.l1.weight"
-  int rows = 0, cols = 0;
-  size_t offset = 0;  // floats from the start of the group
+  int rows = 0, cols = 0;  // logical shape (what state_dict sees)
+  int ld = 0;              // row pitch in floats (>= cols); the padding is zero-initialised and never exported
+  size_t offset = 0;       // floats from the start of the group
 };
 
 // A contiguous optimiser group: p | g | m | v (+ target copy of a prefix).  Elementwise Adam/Polyak do not care
@@ -75,16 +76,22 @@ struct ParamGroup {
   float *p = nullptr, *g = nullptr, *m = nullptr, *v = nullptr, *target = nullptr;
   std::string target_prefix_from, target_prefix_to;  // e.g. "phi." -> "phi_target."
 
-  size_t add(const std::string& nm, int rows, int cols) {
+  // ld = row pitch (0 -> cols), alloc_rows = rows actually allocated (0 -> rows); both only ever add zero padding.
+  // exact = true does not round the tensor up to 4 floats (for tensors that must abut the next one; call align4()
+  // after the last of them).
+  size_t add(const std::string& nm, int rows, int cols, int ld = 0, int alloc_rows = 0, bool exact = false) {
     ParamTensor t;
     t.name = nm;
     t.rows = rows;
     t.cols = cols;
+    t.ld = ld > 0 ? ld : cols;
     t.offset = n;
     tensors.push_back(t);
-    n += ((size_t)rows * cols + 3) & ~size_t(3);
+    const size_t sz = (size_t)(alloc_rows > 0 ? alloc_rows : rows) * t.ld;
+    n += exact ? sz : ((sz + 3) & ~size_t(3));
     return t.offset;
   }
+  void align4() { n = (n + 3) & ~size_t(3); }
   // `this` must stay at a fixed address until the arena is committed.
   void want(DeviceArena& a, bool with_opt = true) {
     a.want(&p, n);
@@ -96,12 +103,14 @@ struct ParamGroup {
 // View of one nn.Linear inside a group.
 struct Linear {
   float *W = nullptr, *b = nullptr, *dW = nullptr, *db = nullptr;
-  int out = 0, in = 0;
+  int out = 0, in = 0;    // logical shape of W[out, in]
+  int ld = 0;             // row pitch of W / dW in floats
+  int out_alloc = 0;      // rows allocated (>= out)
 };
 
-struct LinearSlot {  // offsets resolved to pointers after bind()
+struct LinearSlot {  // offsets resolved to pointers after the arena is committed
   size_t w_off = 0, b_off = 0;
-  int out = 0, in = 0;
+  int out = 0, in = 0, ld = 0, out_alloc = 0;
   Linear view(const ParamGroup& g, bool target = false) const {
     Linear l;
     const float* base = target ? g.target : g.p;
@@ -110,16 +119,25 @@ struct LinearSlot {  // offsets resolved to pointers after bind()
     if (!target && g.g) { l.dW = g.g + w_off; l.db = g.g + b_off; }
     l.out = out;
     l.in = in;
+    l.ld = ld > 0 ? ld : in;
+    l.out_alloc = out_alloc > 0 ? out_alloc : out;
     return l;
   }
 };
 
-inline LinearSlot add_linear(ParamGroup& g, const std::string& name, int out, int in) {
+inline int round_up32(int x) { return (x + 31) & ~31; }
+
+// pad = true stores W as [round_up32(out), round_up32(in)] (zero padding) so that every pass of the layer -- also
+// the ones that read W or its input MN-major -- satisfies the tensor-core path's TMA constraints (16-byte row pitch,
+// MN extents that are multiples of 32).  N = 1 heads are stored unpadded (they run on the row-dot kernels).
+inline LinearSlot add_linear(ParamGroup& g, const std::string& name, int out, int in, bool pad = true) {
   LinearSlot s;
   s.out = out;
   s.in = in;
-  s.w_off = g.add(name + ".weight", out, in);
-  s.b_off = g.add(name + ".bias", out, 1);
+  s.ld = pad ? round_up32(in) : in;
+  s.out_alloc = pad ? round_up32(out) : out;
+  s.w_off = g.add(name + ".weight", out, in, s.ld, s.out_alloc);
+  s.b_off = g.add(name + ".bias", out, 1, 1, s.out_alloc);
   return s;
 }
 
@@ -268,5 +286,6 @@ class Agent {
 
 std::unique_ptr<Agent> make_sac_agent(const AgentConfig& cfg, cudaStream_t s);
 std::unique_ptr<Agent> make_ctrlsac_agent(const AgentConfig& cfg, cudaStream_t s);
+std::unique_ptr<Agent> make_vlsac_agent(const AgentConfig& cfg, cudaStream_t s);
 
 }  // namespace rlrep

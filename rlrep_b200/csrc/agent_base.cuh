@@ -175,7 +175,8 @@ class SacBase : public Agent {
     arena_.want(&head_, (size_t)B_ * 2 * A_);
     arena_.want(&action_, (size_t)B_ * A_);
     arena_.want(&logp_, B_);
-    arena_.want(&dhead_, (size_t)B_ * 2 * A_);
+    LDH_ = round_up32(2 * A_);  // padded pitch: the head's wgrad reads dhead MN-major (zero padding columns)
+    arena_.want(&dhead_, (size_t)B_ * LDH_);
     arena_.want(&dah2_, (size_t)B_ * AH_);
     arena_.want(&dah1_, (size_t)B_ * AH_);
     arena_.want(&d_action_, (size_t)B_ * A_);
@@ -214,7 +215,7 @@ class SacBase : public Agent {
   // one launch for the three actor bias gradients (dY buffers of actor_backward are all still live)
   void actor_bias_grads() {
     const Linear l0 = a0_.view(actor_g_), l1 = a1_.view(actor_g_), l2 = a2_.view(actor_g_);
-    const ColJob jobs[3] = {bias_job(B_, Mat{dhead_, 2 * A_}, l2), bias_job(B_, Mat{dah2_, AH_}, l1),
+    const ColJob jobs[3] = {bias_job(B_, Mat{dhead_, LDH_}, l2), bias_job(B_, Mat{dah2_, AH_}, l1),
                             bias_job(B_, Mat{dah1_, AH_}, l0)};
     launch_colreduce_multi(jobs, 3, stream);
   }
@@ -222,9 +223,9 @@ class SacBase : public Agent {
   // in ah1_/ah2_/head_.  Leaves the actor gradients in actor_g_.g.
   void actor_backward(Mat obs, const float* eps) {
     const Linear l0 = a0_.view(actor_g_), l1 = a1_.view(actor_g_), l2 = a2_.view(actor_g_);
-    launch_actor_sample_bwd(head_, B_, A_, eps, d_action_, A_, dlogp_, dhead_, stream);
-    linear_wgrad(gemm_, stream, B_, Mat{dhead_, 2 * A_}, Mat{ah2_, AH_}, l2, Mat(), 0, false);
-    linear_dgrad(gemm_, stream, B_, Mat{dhead_, 2 * A_}, l2, DACT_ELU_OUT, Mat{ah2_, AH_}, dah2_, AH_);
+    launch_actor_sample_bwd(head_, B_, A_, eps, d_action_, A_, dlogp_, dhead_, LDH_, stream);
+    linear_wgrad(gemm_, stream, B_, Mat{dhead_, LDH_}, Mat{ah2_, AH_}, l2, Mat(), 0, false);
+    linear_dgrad(gemm_, stream, B_, Mat{dhead_, LDH_}, l2, DACT_ELU_OUT, Mat{ah2_, AH_}, dah2_, AH_);
     linear_wgrad(gemm_, stream, B_, Mat{dah2_, AH_}, Mat{ah1_, AH_}, l1, Mat(), 0, false);
     linear_dgrad(gemm_, stream, B_, Mat{dah2_, AH_}, l1, DACT_ELU_OUT, Mat{ah1_, AH_}, dah1_, AH_);
     linear_wgrad(gemm_, stream, B_, Mat{dah1_, AH_}, obs, l0, Mat(), 0, false);
@@ -246,7 +247,7 @@ class SacBase : public Agent {
     return t;
   }
 
-  int S_ = 0, A_ = 0, B_ = 0, AH_ = 0, R_ = 0;
+  int S_ = 0, A_ = 0, B_ = 0, AH_ = 0, R_ = 0, LDH_ = 0;
   cudaStream_t side_ = nullptr;
   std::vector<cudaEvent_t> events_;
   size_t ev_next_ = 0;

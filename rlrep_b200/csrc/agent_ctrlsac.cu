@@ -37,7 +37,7 @@ class CtrlSacAgent final : public SacBase {
     m1_ = add_linear(feat_g_, "mu.l1", H_, S_);
     m2_ = add_linear(feat_g_, "mu.l2", H_, H_);
     m3_ = add_linear(feat_g_, "mu.l3", D_, H_);
-    th_ = add_linear(feat_g_, "theta.l", 1, D_);
+    th_ = add_linear(feat_g_, "theta.l", 1, D_, /*pad=*/false);
     feat_g_.want(arena_);
 
     // critic group: l1 | l4 stacked so both heads' hidden layers are ONE [2H, D] GEMM (ctrlsac_agent.py:18-52)
@@ -48,9 +48,9 @@ class CtrlSacAgent final : public SacBase {
     crit_g_.add("critic.l4.weight", H_, D_);
     c14_.b_off = crit_g_.add("critic.l1.bias", H_, 1);
     crit_g_.add("critic.l4.bias", H_, 1);
-    c2_ = add_linear(crit_g_, "critic.l2", 1, H_);
-    c5_ = add_linear(crit_g_, "critic.l5", 1, H_);
-    RLREP_CHECK(((size_t)H_ * D_) % 4 == 0 && H_ % 4 == 0, "hidden_dim must be a multiple of 4");
+    c2_ = add_linear(crit_g_, "critic.l2", 1, H_, false);
+    c5_ = add_linear(crit_g_, "critic.l5", 1, H_, false);
+    RLREP_CHECK(H_ % 32 == 0 && D_ % 32 == 0, "hidden_dim and feature_dim must be multiples of 32");
     crit_g_.n_target = crit_g_.n;
     crit_g_.target_prefix_from = "critic.";
     crit_g_.target_prefix_to = "critic_target.";

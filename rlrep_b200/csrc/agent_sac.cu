@@ -11,7 +11,7 @@ class SacAgent final : public SacBase {
  public:
   SacAgent(const AgentConfig& c, cudaStream_t s) : SacBase(c, s) {
     H_ = c.hidden_dim;
-    RLREP_CHECK(H_ % 4 == 0, "hidden_dim must be a multiple of 4");
+    RLREP_CHECK(H_ % 32 == 0, "hidden_dim must be a multiple of 32");
     const RecordLayout lay = RecordLayout::of(S_, A_);
     off_r_ = lay.off_r;
     off_d_ = lay.off_d;
@@ -22,16 +22,17 @@ class SacAgent final : public SacBase {
     const int in = S_ + A_;
     c0_.out = 2 * H_;
     c0_.in = in;
-    // pad the first stacked matrix so the second one starts where a [2H, in] view expects it
-    RLREP_CHECK(((size_t)H_ * in) % 4 == 0, "hidden_dim * (state_dim + action_dim) must be a multiple of 4");
-    c0_.w_off = crit_g_.add("critic.Q1.0.weight", H_, in);
-    crit_g_.add("critic.Q2.0.weight", H_, in);
+    c0_.ld = round_up32(in);
+    c0_.out_alloc = 2 * H_;
+    RLREP_CHECK(H_ % 32 == 0, "hidden_dim must be a multiple of 32");
+    c0_.w_off = crit_g_.add("critic.Q1.0.weight", H_, in, c0_.ld);
+    crit_g_.add("critic.Q2.0.weight", H_, in, c0_.ld);
     c0_.b_off = crit_g_.add("critic.Q1.0.bias", H_, 1);
     crit_g_.add("critic.Q2.0.bias", H_, 1);
     c1a_ = add_linear(crit_g_, "critic.Q1.2", H_, H_);
     c1b_ = add_linear(crit_g_, "critic.Q2.2", H_, H_);
-    c2a_ = add_linear(crit_g_, "critic.Q1.4", 1, H_);
-    c2b_ = add_linear(crit_g_, "critic.Q2.4", 1, H_);
+    c2a_ = add_linear(crit_g_, "critic.Q1.4", 1, H_, false);
+    c2b_ = add_linear(crit_g_, "critic.Q2.4", 1, H_, false);
     crit_g_.n_target = crit_g_.n;
     crit_g_.target_prefix_from = "critic.";
     crit_g_.target_prefix_to = "critic_target.";

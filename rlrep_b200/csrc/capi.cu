@@ -55,7 +55,7 @@ struct rlrep_ring {
 struct TensorRef {
   std::string name;
   float* ptr;
-  int rows, cols;
+  int rows, cols, ld;
 };
 
 struct rlrep_agent {
@@ -67,13 +67,13 @@ struct rlrep_agent {
 static void index_tensors(rlrep_agent* a) {
   a->tensors.clear();
   for (ParamGroup* g : a->impl->groups()) {
-    for (const ParamTensor& t : g->tensors) a->tensors.push_back({t.name, g->p + t.offset, t.rows, t.cols});
+    for (const ParamTensor& t : g->tensors) a->tensors.push_back({t.name, g->p + t.offset, t.rows, t.cols, t.ld});
     if (g->target) {
       for (const ParamTensor& t : g->tensors) {
         if (t.offset >= g->n_target) continue;
         if (t.name.compare(0, g->target_prefix_from.size(), g->target_prefix_from) != 0) continue;
         a->tensors.push_back({g->target_prefix_to + t.name.substr(g->target_prefix_from.size()), g->target + t.offset,
-                              t.rows, t.cols});
+                              t.rows, t.cols, t.ld});
       }
     }
   }
@@ -257,6 +257,7 @@ int rlrep_agent_create(const rlrep_agent_config* c, void* stream, rlrep_agent** 
   switch (a.alg) {
     case RLREP_ALG_SAC: h->impl = make_sac_agent(a, st); break;
     case RLREP_ALG_CTRLSAC: h->impl = make_ctrlsac_agent(a, st); break;
+    case RLREP_ALG_VLSAC: h->impl = make_vlsac_agent(a, st); break;
     default: throw Error("algorithm not implemented in this build");
   }
   index_tensors(h.get());
@@ -293,7 +294,8 @@ int rlrep_agent_tensor_read(rlrep_agent* agent, int i, float* out_host) {
   RLREP_CHECK(i >= 0 && i < (int)agent->tensors.size(), "tensor index out of range");
   const TensorRef& t = agent->tensors[i];
   cudaStream_t st = agent->impl->stream;
-  RLREP_CUDA(cudaMemcpyAsync(out_host, t.ptr, (size_t)t.rows * t.cols * 4, cudaMemcpyDeviceToHost, st));
+  RLREP_CUDA(cudaMemcpy2DAsync(out_host, (size_t)t.cols * 4, t.ptr, (size_t)t.ld * 4, (size_t)t.cols * 4, t.rows,
+                               cudaMemcpyDeviceToHost, st));
   RLREP_CUDA(cudaStreamSynchronize(st));
   RLREP_API_END
 }
@@ -302,7 +304,8 @@ int rlrep_agent_tensor_write(rlrep_agent* agent, int i, const float* in_host) {
   RLREP_CHECK(i >= 0 && i < (int)agent->tensors.size(), "tensor index out of range");
   const TensorRef& t = agent->tensors[i];
   cudaStream_t st = agent->impl->stream;
-  RLREP_CUDA(cudaMemcpyAsync(t.ptr, in_host, (size_t)t.rows * t.cols * 4, cudaMemcpyHostToDevice, st));
+  RLREP_CUDA(cudaMemcpy2DAsync(t.ptr, (size_t)t.ld * 4, in_host, (size_t)t.cols * 4, (size_t)t.cols * 4, t.rows,
+                               cudaMemcpyHostToDevice, st));
   RLREP_CUDA(cudaStreamSynchronize(st));
   RLREP_API_END
 }

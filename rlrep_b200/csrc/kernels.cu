@@ -253,7 +253,7 @@ __global__ void actor_sample_kernel(const float* __restrict__ head, int B, int A
 
 __global__ void actor_sample_bwd_kernel(const float* __restrict__ head, int B, int A, const float* __restrict__ eps,
                                         const float* __restrict__ d_action, int ldd,
-                                        const float* __restrict__ dlogp_scalar, float* __restrict__ dhead) {
+                                        const float* __restrict__ dlogp_scalar, float* __restrict__ dhead, int ld_dh) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * A) return;
   const int b = i / A, j = i - b * A;
@@ -268,8 +268,8 @@ __global__ void actor_sample_bwd_kernel(const float* __restrict__ head, int B, i
   // dL/du: through a = tanh(u) and through log pi (d(-ladj)/du = 2 tanh(u); the Gaussian term cancels)
   const float du = d_action[(size_t)b * ldd + j] * (1.f - a * a) + glp * 2.f * a;
   const float dsd = du * e - glp / sd;
-  dhead[(size_t)b * 2 * A + j] = du;
-  dhead[(size_t)b * 2 * A + A + j] = dsd * sd * (0.5f * (kLogStdMax - kLogStdMin)) * (1.f - t * t);
+  dhead[(size_t)b * ld_dh + j] = du;
+  dhead[(size_t)b * ld_dh + A + j] = dsd * sd * (0.5f * (kLogStdMax - kLogStdMin)) * (1.f - t * t);
 }
 
 // ------------------------------------------------------------------------------------------- critic loss
@@ -406,6 +406,180 @@ __global__ void __launch_bounds__(256) polyak_kernel(const float4* __restrict__ 
   }
 }
 
+// ------------------------------------------------------------------------------------------- LV-Rep / VL-SAC
+constexpr float kLogSigMin = -20.f, kLogSigMax = 2.f;  // networks/vae.py:9-10
+__device__ __forceinline__ float clamp_ls(float raw) { return fminf(fmaxf(raw, kLogSigMin), kLogSigMax); }
+__device__ __forceinline__ float clamp_grad(float raw) { return (raw >= kLogSigMin && raw <= kLogSigMax) ? 1.f : 0.f; }
+
+struct ColSegments {
+  ColSegment s[3];
+  int n;
+};
+__global__ void pack_columns_kernel(const float* __restrict__ in, int ld_in, float* __restrict__ out, int ld_out, int rows,
+                                    const ColSegments segs, int width) {
+  const size_t total = (size_t)rows * width;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / width);
+    int c = (int)(i - (size_t)r * width);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (k < segs.n) {
+        if (c < segs.s[k].len) {
+          out[(size_t)r * ld_out + segs.s[k].dst + c] = in[(size_t)r * ld_in + segs.s[k].src + c];
+          break;
+        }
+        c -= segs.s[k].len;
+      }
+    }
+  }
+}
+
+__global__ void vae_sample_kernel(const float* __restrict__ head, int ld_head, int B, int D, const float* __restrict__ eps,
+                                  float* __restrict__ z) {
+  const int total = B * D;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / D, d = i - b * D;
+    const float* h = head + (size_t)b * ld_head;
+    z[i] = h[d] + eps[i] * expf(clamp_ls(h[D + d]));
+  }
+}
+
+__global__ void __launch_bounds__(256) vae_recon_loss_kernel(const float* __restrict__ xr, int ld_xr,
+                                                             const float* __restrict__ next_state,
+                                                             const float* __restrict__ reward, int ld_rec, int B, int S,
+                                                             float* __restrict__ dxr, float* __restrict__ partial) {
+  __shared__ float scratch[33];
+  const float gs = 1.f / ((float)B * (float)S), gr = 1.f / (float)B;
+  float se_s = 0.f, se_r = 0.f;
+  const int total = B * ld_xr;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+    const int b = i / ld_xr, c = i - b * ld_xr;
+    float g = 0.f;
+    if (c < S) {
+      const float d = xr[i] - next_state[(size_t)b * ld_rec + c];
+      se_s = fmaf(d, d, se_s);
+      g = d * gs;
+    } else if (c == S) {
+      const float d = xr[i] - reward[(size_t)b * ld_rec];
+      se_r = fmaf(d, d, se_r);
+      g = d * gr;
+    }
+    dxr[i] = g;
+  }
+  se_s = block_sum<256>(se_s, scratch);
+  se_r = block_sum<256>(se_r, scratch);
+  if (threadIdx.x == 0) {
+    partial[2 * blockIdx.x] = se_s;
+    partial[2 * blockIdx.x + 1] = se_r;
+  }
+}
+
+__global__ void __launch_bounds__(256) vae_kl_bwd_kernel(const float* __restrict__ enc_head,
+                                                         const float* __restrict__ prior_head, int ld_head, int B, int D,
+                                                         const float* __restrict__ eps, const float* __restrict__ dz,
+                                                         float* __restrict__ d_enc, float* __restrict__ d_prior,
+                                                         float* __restrict__ partial) {
+  __shared__ float scratch[33];
+  const int total = B * D;
+  const float g = 1.f / (float)total;
+  float kl_sum = 0.f;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += gridDim.x * 256) {
+    const int b = i / D, d = i - b * D;
+    const float* he = enc_head + (size_t)b * ld_head;
+    const float* hp = prior_head + (size_t)b * ld_head;
+    const float m1 = he[d], raw1 = he[D + d], m2 = hp[d], raw2 = hp[D + d];
+    const float ls1 = clamp_ls(raw1), ls2 = clamp_ls(raw2);
+    const float var1 = expf(2.f * ls1), var2 = expf(2.f * ls2);
+    const float diff = m1 - m2;
+    const float q = (var1 + diff * diff) / var2;
+    kl_sum += ls2 - ls1 + 0.5f * q - 0.5f;
+    const float dzi = dz[i];
+    const float dm = g * diff / var2;
+    d_enc[(size_t)b * ld_head + d] = dzi + dm;
+    d_enc[(size_t)b * ld_head + D + d] = (dzi * eps[i] * expf(ls1) + g * (var1 / var2 - 1.f)) * clamp_grad(raw1);
+    d_prior[(size_t)b * ld_head + d] = -dm;
+    d_prior[(size_t)b * ld_head + D + d] = g * (1.f - q) * clamp_grad(raw2);
+  }
+  kl_sum = block_sum<256>(kl_sum, scratch);
+  if (threadIdx.x == 0) partial[blockIdx.x] = kl_sum;
+}
+
+__global__ void vae_finalize_kernel(const float* __restrict__ recon_partial, int n_recon,
+                                    const float* __restrict__ kl_partial, int n_kl, int B, int S, int D,
+                                    float* __restrict__ metrics) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float se_s = 0.f, se_r = 0.f, kl = 0.f;
+  for (int i = 0; i < n_recon; ++i) { se_s += recon_partial[2 * i]; se_r += recon_partial[2 * i + 1]; }
+  for (int i = 0; i < n_kl; ++i) kl += kl_partial[i];
+  const float s_loss = 0.5f * (se_s / ((float)B * (float)S));
+  const float r_loss = 0.5f * (se_r / (float)B);
+  const float ml = r_loss + s_loss;
+  const float kl_mean = kl / ((float)B * (float)D);
+  metrics[0] = ml + kl_mean;
+  metrics[1] = ml;
+  metrics[2] = kl_mean;
+  metrics[3] = s_loss;
+  metrics[4] = r_loss;
+}
+
+__global__ void noise_expand_kernel(const float* __restrict__ head, int ld_head, int B, int D,
+                                    const float* __restrict__ noise, int NN, float* __restrict__ x) {
+  const size_t total = (size_t)B * NN * D;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int d = (int)(i % D);
+    const size_t row = i / D;
+    const int j = (int)(row % NN), b = (int)(row / NN);
+    const float* h = head + (size_t)b * ld_head;
+    x[i] = h[d] + expf(clamp_ls(h[D + d])) * __ldg(noise + (size_t)j * D + d);
+  }
+}
+
+__global__ void noise_expand_bwd_kernel(const float* __restrict__ dx, const float* __restrict__ head, int ld_head, int B,
+                                        int D, const float* __restrict__ noise, int NN, float* __restrict__ d_head) {
+  const int total = B * D;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / D, d = i - b * D;
+    float sm = 0.f, sn = 0.f;
+    for (int j = 0; j < NN; ++j) {
+      const float g = dx[((size_t)b * NN + j) * D + d];
+      sm += g;
+      sn = fmaf(g, __ldg(noise + (size_t)j * D + d), sn);
+    }
+    const float raw = head[(size_t)b * ld_head + D + d];
+    d_head[(size_t)b * ld_head + d] = sm;
+    d_head[(size_t)b * ld_head + D + d] = sn * expf(clamp_ls(raw)) * clamp_grad(raw);
+  }
+}
+
+__global__ void group_mean_kernel(const float* __restrict__ hid, int ld, int B, int NN, int C, float* __restrict__ out) {
+  const int total = B * C;
+  const float inv = 1.f / (float)NN;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / C, c = i - b * C;
+    float acc = 0.f;
+    for (int j = 0; j < NN; ++j) acc += hid[((size_t)b * NN + j) * ld + c];
+    out[i] = acc * inv;
+  }
+}
+
+__global__ void group_mean_bwd_kernel(const float* __restrict__ dmean, const float* __restrict__ hid, int ld, int B, int NN,
+                                      int C, float* __restrict__ dhid, float* __restrict__ colsum_partial) {
+  const int total = B * C;
+  const float inv = 1.f / (float)NN;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / C, c = i - b * C;
+    const float g = dmean[i] * inv;
+    float acc = 0.f;
+    for (int j = 0; j < NN; ++j) {
+      const size_t o = ((size_t)b * NN + j) * ld + c;
+      const float v = g * apply_dact(hid[o], DACT_ELU_OUT);
+      dhid[o] = v;
+      acc += v;
+    }
+    colsum_partial[i] = acc;
+  }
+}
+
 int grid_for(size_t work_items, int threads, int per_sm = 8) {
   size_t blocks = (work_items + threads - 1) / threads;
   const size_t cap = (size_t)kNumSMs * per_sm;
@@ -485,8 +659,9 @@ void launch_actor_sample(const float* head, int B, int A, const float* eps, floa
 }
 
 void launch_actor_sample_bwd(const float* head, int B, int A, const float* eps, const float* d_action, int ldd,
-                             const float* dlogp_scalar, float* dhead, cudaStream_t s) {
-  actor_sample_bwd_kernel<<<ceil_div(B * A, 256), 256, 0, s>>>(head, B, A, eps, d_action, ldd, dlogp_scalar, dhead);
+                             const float* dlogp_scalar, float* dhead, int ld_dhead, cudaStream_t s) {
+  actor_sample_bwd_kernel<<<ceil_div(B * A, 256), 256, 0, s>>>(head, B, A, eps, d_action, ldd, dlogp_scalar, dhead,
+                                                               ld_dhead);
   RLREP_LAUNCHED("actor_sample_bwd", s);
 }
 
@@ -503,6 +678,58 @@ void launch_actor_alpha_loss(const float* q1, const float* q2, const float* logp
   actor_alpha_loss_kernel<<<1, 256, 0, s>>>(q1, q2, logp, B, target_entropy, learn_alpha, c, dq1, dq2, dlogp_scalar,
                                             metrics);
   RLREP_LAUNCHED("actor_alpha_loss", s);
+}
+
+void launch_pack_columns(const float* in, int ld_in, float* out, int ld_out, int rows, const ColSegment* segs, int n_segs,
+                         cudaStream_t s) {
+  RLREP_CHECK(n_segs >= 1 && n_segs <= 3, "pack_columns takes 1..3 segments");
+  ColSegments cs;
+  cs.n = n_segs;
+  int width = 0;
+  for (int i = 0; i < n_segs; ++i) {
+    cs.s[i] = segs[i];
+    width += segs[i].len;
+  }
+  pack_columns_kernel<<<grid_for((size_t)rows * width, 256), 256, 0, s>>>(in, ld_in, out, ld_out, rows, cs, width);
+  RLREP_LAUNCHED("pack_columns", s);
+}
+void launch_vae_sample(const float* head, int ld_head, int B, int D, const float* eps, float* z, cudaStream_t s) {
+  vae_sample_kernel<<<grid_for((size_t)B * D, 256), 256, 0, s>>>(head, ld_head, B, D, eps, z);
+  RLREP_LAUNCHED("vae_sample", s);
+}
+void launch_vae_recon_loss(const float* xr, int ld_xr, const float* next_state, const float* reward, int ld_rec, int B,
+                           int S, float* dxr, float* partial, int n_blocks, cudaStream_t s) {
+  vae_recon_loss_kernel<<<n_blocks, 256, 0, s>>>(xr, ld_xr, next_state, reward, ld_rec, B, S, dxr, partial);
+  RLREP_LAUNCHED("vae_recon_loss", s);
+}
+void launch_vae_kl_bwd(const float* enc_head, const float* prior_head, int ld_head, int B, int D, const float* eps,
+                       const float* dz, float* d_enc, float* d_prior, float* partial, int n_blocks, cudaStream_t s) {
+  vae_kl_bwd_kernel<<<n_blocks, 256, 0, s>>>(enc_head, prior_head, ld_head, B, D, eps, dz, d_enc, d_prior, partial);
+  RLREP_LAUNCHED("vae_kl_bwd", s);
+}
+void launch_vae_finalize(const float* recon_partial, int n_recon, const float* kl_partial, int n_kl, int B, int S, int D,
+                         float* metrics, cudaStream_t s) {
+  vae_finalize_kernel<<<1, 32, 0, s>>>(recon_partial, n_recon, kl_partial, n_kl, B, S, D, metrics);
+  RLREP_LAUNCHED("vae_finalize", s);
+}
+void launch_noise_expand(const float* head, int ld_head, int B, int D, const float* noise, int NN, float* x,
+                         cudaStream_t s) {
+  noise_expand_kernel<<<grid_for((size_t)B * NN * D, 256, 16), 256, 0, s>>>(head, ld_head, B, D, noise, NN, x);
+  RLREP_LAUNCHED("noise_expand", s);
+}
+void launch_noise_expand_bwd(const float* dx, const float* head, int ld_head, int B, int D, const float* noise, int NN,
+                             float* d_head, cudaStream_t s) {
+  noise_expand_bwd_kernel<<<grid_for((size_t)B * D, 256), 256, 0, s>>>(dx, head, ld_head, B, D, noise, NN, d_head);
+  RLREP_LAUNCHED("noise_expand_bwd", s);
+}
+void launch_group_mean(const float* hid, int ld, int B, int NN, int C, float* out, cudaStream_t s) {
+  group_mean_kernel<<<grid_for((size_t)B * C, 256), 256, 0, s>>>(hid, ld, B, NN, C, out);
+  RLREP_LAUNCHED("group_mean", s);
+}
+void launch_group_mean_bwd(const float* dmean, const float* hid, int ld, int B, int NN, int C, float* dhid,
+                           float* colsum_partial, cudaStream_t s) {
+  group_mean_bwd_kernel<<<grid_for((size_t)B * C, 256), 256, 0, s>>>(dmean, hid, ld, B, NN, C, dhid, colsum_partial);
+  RLREP_LAUNCHED("group_mean_bwd", s);
 }
 
 void launch_adam_polyak(float* p, const float* g, float* m, float* v, size_t n, const AdamHyper* hyper, float* target,

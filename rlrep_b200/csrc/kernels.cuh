@@ -77,9 +77,9 @@ void launch_feature_loss_finalize(const float* loss_rows, int rows, const float*
 //   head [B, 2A] = (mu | raw log-std); eps [B, A];  out action [B, lda] (tanh(u)), logp [B]
 void launch_actor_sample(const float* head, int B, int A, const float* eps, float* action, int lda, float* logp,
                          cudaStream_t s);
-// Backward of the above: dhead [B, 2A] from d_action [B, ldd] and the per-row d_logp scalar (*dlogp_scalar).
+// Backward of the above: dhead [B, ld_dhead >= 2A] from d_action [B, ldd] and the per-row d_logp scalar.
 void launch_actor_sample_bwd(const float* head, int B, int A, const float* eps, const float* d_action, int ldd,
-                             const float* dlogp_scalar, float* dhead, cudaStream_t s);
+                             const float* dlogp_scalar, float* dhead, int ld_dhead, cudaStream_t s);
 
 // TD target + twin-critic MSE (ctrlsac_agent.py:263-286; sac_agent.py:112-123):
 //   y = r + (1 - d) * gamma * (min(nq1, nq2) - alpha * logp2)
@@ -95,6 +95,39 @@ void launch_td_critic_loss(const float* reward, const float* done, int ld_rd, co
 void launch_actor_alpha_loss(const float* q1, const float* q2, const float* logp, int B, float target_entropy,
                              int learn_alpha, Control* c, float* dq1, float* dq2, float* dlogp_scalar, float* metrics,
                              cudaStream_t s);
+
+// ---- LV-Rep / VL-SAC (agent/vlsac/vlsac_agent.py, networks/vae.py) ----------------------------------------------
+// out[b, dst + j] = in[b, src + j] for up to three column segments (builds cat(s, a, s') from a replay record).
+struct ColSegment {
+  int src, dst, len;
+};
+void launch_pack_columns(const float* in, int ld_in, float* out, int ld_out, int rows, const ColSegment* segs,
+                         int n_segs, cudaStream_t s);
+// Encoder.sample (vae.py:50-58): z = mean + eps * exp(clamp(raw_log_std, -20, 2)); head = [mean | raw_log_std].
+void launch_vae_sample(const float* head, int ld_head, int B, int D, const float* eps, float* z, cudaStream_t s);
+// Reconstruction losses (vlsac_agent.py:137-140): xr = [s'_hat (S) | r_hat]; dxr = d(0.5 mse_s + 0.5 mse_r);
+// partial[block] = {sum (s'_hat - s')^2, sum (r_hat - r)^2}.  Padding columns of dxr [S+1, ld) are zeroed.
+void launch_vae_recon_loss(const float* xr, int ld_xr, const float* next_state, const float* reward, int ld_rec, int B,
+                           int S, float* dxr, float* partial, int n_blocks, cudaStream_t s);
+// KL(q || p) of two diagonal Gaussians with clamped log-stds (vlsac_agent.py:143-150) and the backward of the whole
+// ELBO into the encoder and prior heads: d_enc = [dz + dKL/dmean1 | (dz eps std1 + dKL/dls1) * clamp'],
+// d_prior = [dKL/dmean2 | dKL/dls2 * clamp'];  partial[block] = sum KL.
+void launch_vae_kl_bwd(const float* enc_head, const float* prior_head, int ld_head, int B, int D, const float* eps,
+                       const float* dz, float* d_enc, float* d_prior, float* partial, int n_blocks, cudaStream_t s);
+// metrics = {vae_loss, ml_loss, kl_loss, s_loss, r_loss}
+void launch_vae_finalize(const float* recon_partial, int n_recon, const float* kl_partial, int n_kl, int B, int S, int D,
+                         float* metrics, cudaStream_t s);
+// Critic input (vlsac_agent.py:44-50): x[b*NN + j, :] = mean[b] + exp(clamp(raw_ls[b])) * noise[j].
+void launch_noise_expand(const float* head, int ld_head, int B, int D, const float* noise, int NN, float* x,
+                         cudaStream_t s);
+// Its backward: d_head = [sum_j dx | (sum_j dx * noise_j) * std * clamp'].
+void launch_noise_expand_bwd(const float* dx, const float* head, int ld_head, int B, int D, const float* noise, int NN,
+                             float* d_head, cudaStream_t s);
+// out[b, c] = mean_j hid[b*NN + j, c]   (vlsac_agent.py:53, :58)
+void launch_group_mean(const float* hid, int ld, int B, int NN, int C, float* out, cudaStream_t s);
+// dhid[b*NN + j, c] = dmean[b, c] / NN * elu'(hid[b*NN + j, c]);  colsum_partial[b, c] = sum_j dhid[b*NN + j, c]
+void launch_group_mean_bwd(const float* dmean, const float* hid, int ld, int B, int NN, int C, float* dhid,
+                           float* colsum_partial, cudaStream_t s);
 
 // Fused multi-tensor Adam (+ optional Polyak of a prefix of the arena into its target copy).
 // One launch updates a whole optimiser group laid out as flat arrays p / g / m / v of n floats (n % 4 == 0).

@@ -179,7 +179,7 @@ void linear_fwd(GemmRunner& g, cudaStream_t s, int rows, Mat x, const Linear& l,
   a.M = rows; a.N = l.out; a.K = l.in;
   a.A = x.p; a.lda = x.ld;
   if (x2.p) { a.A2 = x2.p; a.lda2 = x2.ld; a.K1 = k1; }
-  a.B = l.W; a.ldb = l.in;
+  a.B = l.W; a.ldb = l.ld;
   a.C = y; a.ldc = ldy;
   a.epi.bias = l.b;
   a.epi.act = act;
@@ -192,7 +192,7 @@ void linear_dgrad(GemmRunner& g, cudaStream_t s, int rows, Mat dy, const Linear&
   GemmArgs a;
   a.M = rows; a.N = n_cols < 0 ? l.in : n_cols; a.K = l.out;
   a.A = dy.p; a.lda = dy.ld;
-  a.B = l.W + col0; a.ldb = l.in; a.b_mn = true;  // W[out, in] read as B(n = in, k = out)
+  a.B = l.W + col0; a.ldb = l.ld; a.b_mn = true;  // W[out, in] read as B(n = in, k = out)
   a.C = dx; a.ldc = lddx;
   a.epi.dact = dact;
   a.epi.aux = aux.p; a.epi.ld_aux = aux.ld;
@@ -204,10 +204,15 @@ void linear_wgrad(GemmRunner& g, cudaStream_t s, int rows, Mat dy, Mat x, const 
   // dW[out, in] = sum_b dy[b, out] x[b, in]:  A = dy (MN-major, k = batch), B = x (MN-major)
   if (x2.p == nullptr) {
     GemmArgs a;
-    a.M = l.out; a.N = l.in; a.K = rows;
+    // MN-major operands need extents that are multiples of 32 on the tensor-core path: run over the padded extents
+    // when the buffers are wide enough.  Whatever sits in the padding columns of dy / x only lands in the padding
+    // rows / columns of dW, which no pass ever reads as data (K extents are always the logical ones).
+    a.M = (l.out % 32 != 0 && dy.ld >= l.out_alloc && l.out_alloc % 32 == 0) ? l.out_alloc : l.out;
+    a.N = (l.in % 32 != 0 && x.ld >= l.ld && l.ld % 32 == 0) ? l.ld : l.in;
+    a.K = rows;
     a.A = dy.p; a.lda = dy.ld; a.a_mn = true;
     a.B = x.p; a.ldb = x.ld; a.b_mn = true;
-    a.C = l.dW; a.ldc = l.in;
+    a.C = l.dW; a.ldc = l.ld;
     g.run(a, s);
   } else {
     // two input segments -> two column blocks of dW
@@ -215,7 +220,7 @@ void linear_wgrad(GemmRunner& g, cudaStream_t s, int rows, Mat dy, Mat x, const 
     a.M = l.out; a.N = k1; a.K = rows;
     a.A = dy.p; a.lda = dy.ld; a.a_mn = true;
     a.B = x.p; a.ldb = x.ld; a.b_mn = true;
-    a.C = l.dW; a.ldc = l.in;
+    a.C = l.dW; a.ldc = l.ld;
     g.run(a, s);
     GemmArgs b = a;
     b.N = l.in - k1;

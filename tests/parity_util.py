@@ -17,11 +17,18 @@ def make_pair(alg, S, A, kw, rows, precision="tf32", use_cuda_graph=True, seed=0
     from rlrep_b200 import ReplayBuffer
     from rlrep_b200.agents import AGENTS
     init = O.init_state(alg, S, A, kw, seed=seed)
-    oracle = O.ORACLES[alg](S, A, init, discount=0.99, tau=0.005, **kw, **(oracle_kw or {}))
+    oracle_kw = dict(oracle_kw or {})
+    extra_state = {}
+    if alg == "vlsac":  # the critic's fixed noise is construction-time state on both sides
+        g = torch.Generator().manual_seed(1234)
+        noise = torch.randn(20, kw.get("feature_dim", 256), generator=g)
+        oracle_kw["critic_noise"] = noise
+        extra_state["critic.noise"] = noise
+    oracle = O.ORACLES[alg](S, A, init, discount=0.99, tau=0.005, **kw, **oracle_kw)
     oring = O.synthetic_ring(S, A, rows, seed=0)
     agent = AGENTS[alg](state_dim=S, action_dim=A, action_space=Space(A), discount=0.99, tau=0.005,
                         precision=precision, use_cuda_graph=use_cuda_graph, **kw)
-    agent.load_state_dict(init)
+    agent.load_state_dict({**init, **extra_state})
     buf = ReplayBuffer(S, A, max_size=rows)
     buf.load(oring.state, oring.action, oring.next_state, oring.reward, oring.done)
     return agent, buf, oracle, oring
@@ -57,6 +64,9 @@ def worst_param_error(agent, oracle):
     outliers = 0
     total = 0
     for k, v in osd.items():
+        if k == "log_alpha":
+            assert abs(float(csd[k]) - float(v)) < 1e-4 * max(1.0, abs(float(v))), (float(csd[k]), float(v))
+            continue
         assert k in csd, f"{k} missing from the CUDA agent's state_dict"
         c = csd[k].double().reshape(-1)
         v = v.double().reshape(-1)

@@ -118,6 +118,8 @@ CASES = {
     "sac": ("sac", HC, dict(hidden_dim=256), 256),
     "ctrlsac_small": ("ctrlsac", HC, dict(hidden_dim=64, feature_dim=128, extra_feature_steps=3), 32),
     "ctrlsac": ("ctrlsac", HC, dict(hidden_dim=1024, feature_dim=2048, extra_feature_steps=3), 256),
+    "vlsac_hc": ("vlsac", HC, dict(hidden_dim=256, feature_dim=256, extra_feature_steps=3), 64),
+    "vlsac_hum": ("vlsac", dict(S=376, A=17), dict(hidden_dim=256, feature_dim=256, extra_feature_steps=3), 256),
 }
 
 

@@ -21,6 +21,7 @@ class FakeBuffer:
 CASES = {
     "sac": (dict(hidden_dim=32), 64),
     "ctrlsac": (dict(hidden_dim=32, feature_dim=64, extra_feature_steps=3), 32),
+    "vlsac": (dict(hidden_dim=32, feature_dim=64, extra_feature_steps=3), 32),
 }
 
 
@@ -31,7 +32,8 @@ def test_draw_consumes_the_global_rngs_exactly_like_the_reference(alg):
     kw, B = CASES[alg]
     S, A = 17, 6
     init = O.init_state(alg, S, A, kw)
-    oracle = O.ORACLES[alg](S, A, init, discount=0.99, tau=0.005, **kw)
+    okw = dict(critic_noise=torch.zeros(20, kw["feature_dim"])) if alg == "vlsac" else {}
+    oracle = O.ORACLES[alg](S, A, init, discount=0.99, tau=0.005, **kw, **okw)
     ring = O.synthetic_ring(S, A, FakeBuffer.size, seed=0)
     drawn = []
     orig_take = ring.take
@@ -48,7 +50,8 @@ def test_draw_consumes_the_global_rngs_exactly_like_the_reference(alg):
     assert np.array_equal(np.random.get_state()[1], np_state)
     assert torch.equal(torch.get_rng_state(), torch_state)
     assert np.array_equal(idx, np.concatenate(drawn))
-    assert eps.shape == (2 * B * A,)
+    n_feat_eps = (kw["extra_feature_steps"] + 1) * B * kw["feature_dim"] if alg == "vlsac" else 0
+    assert eps.shape == (n_feat_eps + 2 * B * A,)
 
 
 def test_config_mapping_follows_reference_constructors():
