@@ -1,387 +1,21 @@
-// tcgen05 TF32 GEMM for sm_100a: TMA-fed shared-memory ring -> tcgen05.mma (kind::tf32) with the FP32
-// accumulator in TMEM -> staged, coalesced epilogue with fused bias / activation / activation-derivative.
-//
-// One CTA computes one 128 x BN output tile over a K-slice.  Split-K runs as a THREAD-BLOCK CLUSTER along
-// gridDim.z (1, 2, 4 or 8 CTAs): every CTA stages its partial accumulator in its own shared memory, the cluster
-// synchronises, and CTA r reduces rows [r*128/s, (r+1)*128/s) of the tile by reading all peers' slices over
-// distributed shared memory in a fixed order (deterministic), applies the epilogue and writes C with fully
-// coalesced 16-byte stores.  No global workspace, no second kernel, no atomics.
-//   warp 0     : TMA producer (one elected lane)
-//   warp 1     : MMA issuer (one elected lane)
-//   warps 2..5 : TMEM -> shared staging (warp w owns TMEM lanes 32*(w&3) ..); warp 2 owns TMEM alloc/dealloc
-//   all 16 warps: reduce + epilogue + store (the store phase is issue-bound, so it gets every warp the CTA has)
-//
-// Operands stay FP32 in HBM; the tensor maps are typed TFLOAT32 so the TMA unit rounds to TF32 on the way
-// into shared memory and the weights are never re-materialised in a second precision.
-//
-// Both K-major and MN-major operands are supported (see gemm.cuh), so forward, dgrad and wgrad all run
-// here without transposed copies of weights or activations:
-//   K-major  tile: rows x 32 fp32 (128 B) per k-block, one TMA box, SWIZZLE_128B, SBO = 1024 B;
-//                  the 4 UMMA_K=8 slices of a k-block advance the descriptor start address by 32 B.
-//   MN-major tile: 32 k-rows x 32 fp32 boxes (4 KB each), one per 32 rows of M/N.  tcgen05 accepts exactly one
-//                  layout for MN-major tf32: SWIZZLE_128B_BASE32B (32-byte chunks XOR k-row % 4, 4-row atoms),
-//                  which TMA writes with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.  LBO = 4096 B between boxes,
-//                  SBO = 512 B between 4-k-row groups; the 4 UMMA_K=8 slices advance the start by 1024 B.
+// Host side of the tcgen05 TF32 GEMM (see gemm_tc_kernel.cuh for the kernel): tensor-map construction, the tile /
+// split-K cost model and the dispatch to the per-variant launchers.
 #include <cstdint>
 #include <mutex>
 
 #include "common.cuh"
 #include "gemm.cuh"
-#include "ptx.cuh"
+#include "gemm_tc_kernel.cuh"
 
 namespace rlrep {
 
-// Optional in-kernel timeline (nanoseconds from %globaltimer) of CTA (0,0,0); read back by rlrep_gemm_trace.
-__device__ unsigned long long g_gemm_trace[16];
+namespace tc {
+void (*g_trace_reader)(unsigned long long*) = nullptr;
+}
 
 namespace {
-
-__device__ __forceinline__ void trace(int slot) {
-#ifdef RLREP_GEMM_TRACE
-  if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
-    g_gemm_trace[slot] = t;
-  }
-#endif
-}
-
-constexpr int BM = 128;           // UMMA M (cta_group::1)
-constexpr int BK = 32;            // fp32 elements per k-block = one 128-byte swizzle row
-constexpr int UMMA_K = 8;         // tf32
-constexpr int kThreads = 512;     // 16 warps: 2 issue the pipeline, 4 drain TMEM, all 16 run the store phase
-constexpr int kSmemBudget = 200 * 1024;
-
-__host__ __device__ constexpr int stage_bytes(int bn) { return (BM + bn) * BK * 4; }
-__host__ __device__ constexpr int num_stages(int bn) {
-  return kSmemBudget / stage_bytes(bn) > 8 ? 8 : kSmemBudget / stage_bytes(bn);
-}
-__host__ __device__ constexpr int smem_bytes(int bn) { return num_stages(bn) * stage_bytes(bn) + 1024 + 256; }
-
-__device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
-
-struct TileStore {  // what the store phase needs to know about the tile (run-time so the functions below are shared)
-  uint32_t stage_addr;  // shared-memory address of this CTA's staged fp32 tile
-  int lds;              // staging row pitch in floats
-  int c4_shift;         // log2(BN / 4)
-  int splits;           // cluster size along K
-  int row0, rows_per;   // rows of the tile this CTA reduces and stores
-  int m0, n0, M, N;
-  float* C;
-  int ldc;
-};
-
-template <int S>
-__device__ __forceinline__ float4 load_reduced_n(uint32_t off) {
-  float4 v[S];
-#pragma unroll
-  for (int p = 0; p < S; ++p) v[p] = ptx::ld_dsmem_f4(off, p);  // all peers in flight at once
-  float4 acc = v[0];
-#pragma unroll
-  for (int p = 1; p < S; ++p) {  // fixed order over the cluster => deterministic
-    acc.x += v[p].x; acc.y += v[p].y; acc.z += v[p].z; acc.w += v[p].w;
-  }
-  return acc;
-}
-__device__ __forceinline__ float4 load_reduced(const TileStore& t, uint32_t off) {
-  switch (t.splits) {
-    case 1: return ptx::ld_shared_f4(off);
-    case 2: return load_reduced_n<2>(off);
-    case 4: return load_reduced_n<4>(off);
-    default: return load_reduced_n<8>(off);
-  }
-}
-
-// Store phase, fast path: interior tile, every pointer 16-byte aligned, N % 4 == 0.  ACT / DACT / BIAS / EXTRAS are
-// compile-time so the loop carries only the instructions the layer needs (the step is issue-bound here: few warps
-// per SM, so every instruction counts).  Four float4 per thread are loaded before any is consumed.
-template <int ACT, int DACT, bool BIAS, bool EXTRAS>
-__device__ __noinline__ bool store_tile_fast(const TileStore t, const Epilogue* __restrict__ ep) {
-  const Epilogue& epi = *ep;
-  constexpr int U = 4;
-  const int nthr = blockDim.x;
-  const int total = t.rows_per << t.c4_shift;
-  const int c4_mask = (1 << t.c4_shift) - 1;
-  auto one = [&](int idx, float4 acc) {
-    const int rr = t.row0 + (idx >> t.c4_shift), c4 = idx & c4_mask;
-    const int gm = t.m0 + rr, gn = t.n0 + c4 * 4;
-    float v[4] = {acc.x, acc.y, acc.z, acc.w};
-    if constexpr (EXTRAS) {
-      const float sc = epi.scale;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] *= sc;
-      if (epi.r1_u) {
-        const float u = __ldg(epi.r1_u + gm);
-        const float4 w = __ldg(reinterpret_cast<const float4*>(epi.r1_v + gn));
-        v[0] = fmaf(u, w.x, v[0]); v[1] = fmaf(u, w.y, v[1]); v[2] = fmaf(u, w.z, v[2]); v[3] = fmaf(u, w.w, v[3]);
-      }
-    }
-    if constexpr (BIAS) {
-      if (!EXTRAS || epi.bias != nullptr) {
-        const float4 b = __ldg(reinterpret_cast<const float4*>(epi.bias + gn));
-        v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-      }
-    }
-    if constexpr (EXTRAS) {
-      if (epi.pre_out)
-        *reinterpret_cast<float4*>(epi.pre_out + (size_t)gm * epi.ld_pre + gn) = make_float4(v[0], v[1], v[2], v[3]);
-    }
-    if constexpr (ACT != ACT_NONE) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) v[j] = apply_act(v[j], ACT < 0 ? epi.act : ACT);
-    }
-    if constexpr (DACT != DACT_NONE) {
-      const int dact = DACT < 0 ? epi.dact : DACT;
-      if (dact != DACT_NONE) {
-        const float4 x = *reinterpret_cast<const float4*>(epi.aux + (size_t)gm * epi.ld_aux + gn);
-        v[0] *= apply_dact(x.x, dact); v[1] *= apply_dact(x.y, dact); v[2] *= apply_dact(x.z, dact); v[3] *= apply_dact(x.w, dact);
-      }
-    }
-    float4* cp = reinterpret_cast<float4*>(t.C + (size_t)gm * t.ldc + gn);
-    if constexpr (EXTRAS) {
-      if (epi.accumulate) { const float4 o = *cp; v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w; }
-    }
-    *cp = make_float4(v[0], v[1], v[2], v[3]);
-  };
-  if (t.splits > 1 && total <= nthr * 2 * U) {
-    // The whole slice fits in registers: pull it over DSMEM, tell the cluster we are done with its shared memory
-    // (peers may exit), and only then do the epilogue math and the global stores.
-    float4 acc[2 * U];
-    if (threadIdx.x == 0) trace(9);
-#pragma unroll
-    for (int u = 0; u < 2 * U; ++u) {
-      const int idx = threadIdx.x + u * nthr;
-      if (idx < total)
-        acc[u] = load_reduced(t, t.stage_addr + (((t.row0 + (idx >> t.c4_shift)) * t.lds + (idx & c4_mask) * 4) << 2));
-    }
-    if (threadIdx.x == 0) { if (acc[0].x == 123.456f) trace(15); trace(10); }
-    ptx::cluster_arrive_relaxed();
-    if (threadIdx.x == 0) trace(11);
-#pragma unroll
-    for (int u = 0; u < 2 * U; ++u) {
-      const int idx = threadIdx.x + u * nthr;
-      if (idx < total) one(idx, acc[u]);
-    }
-    return true;
-  }
-  const int chunk = nthr * U;
-  const int main_end = (total / chunk) * chunk;
-  int base = threadIdx.x;
-#pragma unroll 1
-  for (; base < main_end; base += chunk) {
-    float4 acc[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const int idx = base + u * nthr;
-      acc[u] = load_reduced(t, t.stage_addr + (((t.row0 + (idx >> t.c4_shift)) * t.lds + (idx & c4_mask) * 4) << 2));
-    }
-#pragma unroll
-    for (int u = 0; u < U; ++u) one(base + u * nthr, acc[u]);
-  }
-#pragma unroll 1
-  for (int idx = main_end + threadIdx.x; idx < total; idx += nthr)
-    one(idx, load_reduced(t, t.stage_addr + (((t.row0 + (idx >> t.c4_shift)) * t.lds + (idx & c4_mask) * 4) << 2)));
-  return false;
-}
-
-// Store phase, general path: edge tiles, ragged N, unaligned pointers.
-__device__ __noinline__ void store_tile_general(const TileStore t, const Epilogue* __restrict__ ep) {
-  const Epilogue& epi = *ep;
-  const int total = t.rows_per << t.c4_shift;
-  const int c4_mask = (1 << t.c4_shift) - 1;
-#pragma unroll 1
-  for (int idx = threadIdx.x; idx < total; idx += blockDim.x) {
-    const int rr = t.row0 + (idx >> t.c4_shift), c4 = idx & c4_mask;
-    const int gm = t.m0 + rr, gn = t.n0 + c4 * 4;
-    if (gm >= t.M || gn >= t.N) continue;
-    const float4 acc = load_reduced(t, t.stage_addr + ((rr * t.lds + c4 * 4) << 2));
-    float* cp = t.C + (size_t)gm * t.ldc + gn;
-    const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
-#pragma unroll 1
-    for (int j = 0; j < 4; ++j)
-      if (gn + j < t.N) cp[j] = epilogue_apply<-1, -1>(epi, a4[j], gm, gn + j, cp + j);
-  }
-}
-
-// Returns true when the cluster "done with peers' shared memory" arrive has already been issued.
-__device__ __forceinline__ bool store_tile(const TileStore& t, const Epilogue* ep) {
-  const Epilogue& epi = *ep;
-  const bool use_aux = epi.dact != DACT_NONE;
-  const bool fast = t.m0 + BM <= t.M && t.n0 + (4 << t.c4_shift) <= t.N && (t.N & 3) == 0 && (t.ldc & 3) == 0 &&
-                    aligned16(t.C) && (!use_aux || ((epi.ld_aux & 3) == 0 && aligned16(epi.aux))) &&
-                    (!epi.pre_out || ((epi.ld_pre & 3) == 0 && aligned16(epi.pre_out))) &&
-                    (!epi.bias || aligned16(epi.bias)) && (!epi.r1_v || aligned16(epi.r1_v));
-  if (!fast) {
-    store_tile_general(t, ep);
-    return false;
-  }
-  const bool extras = epi.r1_u != nullptr || epi.pre_out != nullptr || epi.accumulate != 0 || epi.scale != 1.0f;
-  const bool bias = epi.bias != nullptr;
-  if (extras) return store_tile_fast<-1, -1, true, true>(t, ep);  // bias pointer may be null there: checked inside
-  bool arrived = false;
-#define RLREP_FAST(A, D)                                             \
-  do {                                                               \
-    if (bias) arrived = store_tile_fast<A, D, true, false>(t, ep);   \
-    else arrived = store_tile_fast<A, D, false, false>(t, ep);       \
-  } while (0)
-  RLREP_EPILOGUE_SWITCH(epi, RLREP_FAST);
-#undef RLREP_FAST
-  return arrived;
-}
-
-template <int BN, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(kThreads, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 float* __restrict__ C, int ldc, int M, int N, int K, int kb_per_split, const Epilogue epi) {
-  constexpr int STAGES = num_stages(BN);
-  constexpr int A_BYTES = BM * BK * 4;
-  constexpr int B_BYTES = BN * BK * 4;
-  constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
-  constexpr int LDS = BN + 4;  // staging row pitch in floats: 16-byte aligned rows, conflict-free float4 access
-  static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN must be a power of two in [32,256]");
-  static_assert(BM * LDS * 4 <= STAGES * (A_BYTES + B_BYTES), "staging tile must fit in the pipeline buffers");
-
-  extern __shared__ uint8_t smem_raw[];
-  // SWIZZLE_128B atoms must sit on 1024-byte boundaries.
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* sA = smem;
-  uint8_t* sB = smem + STAGES * A_BYTES;
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
-  float* stage = reinterpret_cast<float*>(smem);  // reuses the operand ring once the accumulator is complete
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  if (threadIdx.x == 0) trace(0);
-  const int n0 = blockIdx.x * BN;
-  const int m0 = blockIdx.y * BM;
-  const int splits = gridDim.z;
-  const int nkb_total = (K + BK - 1) / BK;
-  const int kb_begin = blockIdx.z * kb_per_split;
-  const int kb_end = min(nkb_total, kb_begin + kb_per_split);
-  const int nkb = kb_end - kb_begin;
-
-  // One TMA round: arm the stage's barrier and fetch the A / B boxes of k-block (kb_begin + it).
-  auto produce = [&](int it) {
-    const int s = it % STAGES;
-    ptx::mbar_arrive_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
-    const int k0 = (kb_begin + it) * BK;
-    uint8_t* a_dst = sA + s * A_BYTES;
-    uint8_t* b_dst = sB + s * B_BYTES;
-    // MN-major operands: one 3-D box {32 (m % 32), 32 (k), rows / 32 (m / 32)} lands as consecutive 4 KB sub-boxes
-    if (!A_MN) ptx::tma_load_2d(a_dst, &tmA, &full_bar[s], k0, m0);
-    else ptx::tma_load_3d(a_dst, &tmA, &full_bar[s], 0, k0, m0 / 32);
-    if (!B_MN) ptx::tma_load_2d(b_dst, &tmB, &full_bar[s], k0, n0);
-    else ptx::tma_load_3d(b_dst, &tmB, &full_bar[s], 0, k0, n0 / 32);
-  };
-  const int first_round = nkb < 1 ? nkb : 1;  // one stage before the setup barrier; TMA issue itself is not free
-  if (warp == 0 && lane == 0) {
-    // The producer owns the barriers: it initialises them and immediately fills the ring (no empty-wait is needed
-    // for the first round), so the first operands are in flight while the other warps allocate TMEM.
-    for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);
-      ptx::mbar_init(&empty_bar[s], 1);
-    }
-    ptx::mbar_init(accum_bar, 1);
-    ptx::fence_mbar_init();
-    for (int it = 0; it < first_round; ++it) produce(it);
-  }
-  if (warp == 2) {
-    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
-    ptx::tmem_relinquish();
-  }
-  ptx::tc_fence_before_sync();
-  __syncthreads();
-  ptx::tc_fence_after_sync();
-  const uint32_t tmem_base = *tmem_slot;
-  if (threadIdx.x == 0) trace(1);
-
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer
-    if (lane == 0) {  // same lane that ran the first round before the setup barrier
-      for (int it = first_round; it < nkb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        ptx::mbar_wait(&empty_bar[s], ph ^ 1);
-        produce(it);
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer
-    if (ptx::elect_one()) {
-      constexpr uint32_t idesc = ptx::make_idesc_tf32(BM, BN, A_MN, B_MN);
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % STAGES;
-        const uint32_t ph = (it / STAGES) & 1;
-        ptx::mbar_wait(&full_bar[s], ph);
-        if (it == 0) trace(2);
-        ptx::tc_fence_after_sync();
-        const uint32_t a_addr = ptx::smem_u32(sA + s * A_BYTES);
-        const uint32_t b_addr = ptx::smem_u32(sB + s * B_BYTES);
-#pragma unroll
-        for (int k = 0; k < BK / UMMA_K; ++k) {
-          const uint64_t adesc = A_MN ? ptx::make_smem_desc(a_addr + k * 1024, 4096, 512, 1)
-                                      : ptx::make_smem_desc(a_addr + k * UMMA_K * 4, 16, 1024, 2);
-          const uint64_t bdesc = B_MN ? ptx::make_smem_desc(b_addr + k * 1024, 4096, 512, 1)
-                                      : ptx::make_smem_desc(b_addr + k * UMMA_K * 4, 16, 1024, 2);
-          ptx::mma_tf32_ss(tmem_base, adesc, bdesc, idesc, (it > 0 || k > 0) ? 1u : 0u);
-        }
-        ptx::mma_commit(&empty_bar[s]);  // frees the smem stage once these MMAs have read it
-      }
-      ptx::mma_commit(accum_bar);  // accumulator complete
-      trace(3);
-    }
-  } else if (warp < 6) {
-    // ------------------------------------------------------------ TMEM -> shared staging (warps 2..5)
-    // accum_bar completing means every MMA has finished reading the operand ring (and every TMA write into it was
-    // consumed before that), so the ring can be overwritten with the fp32 tile.
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int r = 32 * q + lane;
-    ptx::mbar_wait(accum_bar, 0);
-    if (threadIdx.x == 64) trace(4);
-    ptx::tc_fence_after_sync();
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + c * 32, v);
-      ptx::tmem_ld_wait();
-      float4* dst = reinterpret_cast<float4*>(stage + r * LDS + c * 32);
-#pragma unroll
-      for (int j = 0; j < 8; ++j)
-        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                             __uint_as_float(v[4 * j + 3]));
-    }
-    ptx::tc_fence_before_sync();
-  }
-
-  if (threadIdx.x == 64) trace(5);
-  if (splits > 1) ptx::cluster_sync(); else __syncthreads();
-  if (threadIdx.x == 0) trace(6);
-  if (warp == 2) ptx::tmem_dealloc(tmem_base, TMEM_COLS);  // every tcgen05.ld has completed: the tile is in shared memory
-
-  // ---------------------------------------------------------------- reduce + epilogue + coalesced store (all warps)
-  {
-    TileStore t;
-    t.stage_addr = ptx::smem_u32(stage);
-    t.lds = LDS;
-    t.c4_shift = BN == 32 ? 3 : (BN == 64 ? 4 : (BN == 128 ? 5 : 6));
-    t.splits = splits;
-    t.rows_per = BM / splits;
-    t.row0 = (splits > 1 ? (int)ptx::cluster_ctarank() : 0) * t.rows_per;
-    t.m0 = m0; t.n0 = n0; t.M = M; t.N = N;
-    t.C = C; t.ldc = ldc;
-    const bool arrived = store_tile(t, &epi);
-    if (threadIdx.x == 0) trace(7);
-    if (splits > 1) {  // peers may still be reading this CTA's staging tile: do not exit before they are done
-      if (!arrived) ptx::cluster_arrive_relaxed();
-      ptx::cluster_wait();
-    }
-  }
-
-  if (threadIdx.x == 64) trace(8);
-}
+using tc::BK;
+using tc::BM;
 
 // ------------------------------------------------------------------ host side
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -432,40 +66,6 @@ CUtensorMap make_map_mnmajor(const float* base, int K, int mn, int ld, int tile_
   return m;
 }
 
-template <int BN, bool A_MN, bool B_MN>
-void launch_variant(const TcGemmPlan& p, cudaStream_t stream) {
-  auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;
-  static bool attr_set = false;  // per template instantiation
-  if (!attr_set) {
-    RLREP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(BN)));
-    attr_set = true;
-  }
-  const GemmArgs& a = p.args;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(ceil_div(a.N, BN), ceil_div(a.M, BM), p.split_k);
-  cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = smem_bytes(BN);
-  cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 1;
-  attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = p.split_k;
-  cfg.attrs = attr;
-  cfg.numAttrs = 1;
-  RLREP_CUDA(cudaLaunchKernelEx(&cfg, kern, p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, a.K, p.kb_per_split, a.epi));
-  RLREP_LAUNCHED("gemm_tf32", stream);
-}
-
-template <int BN>
-void launch_bn(const TcGemmPlan& p, cudaStream_t stream) {
-  const bool a = p.args.a_mn, b = p.args.b_mn;
-  if (!a && !b) launch_variant<BN, false, false>(p, stream);
-  else if (!a && b) launch_variant<BN, false, true>(p, stream);
-  else if (a && !b) launch_variant<BN, true, false>(p, stream);
-  else launch_variant<BN, true, true>(p, stream);
-}
-
 // Cost model (cycles through one SM) used to pick the tile width and the split-K cluster size: operand bytes from
 // L2 at ~64 B/clk, the cluster reduction over DSMEM at ~20 B/clk, stores at ~32 B/clk, times the number of waves.
 double plan_cost(int M, int N, int nkb, int bn, int s, int* kb_per_out) {
@@ -483,7 +83,8 @@ double plan_cost(int M, int N, int nkb, int bn, int s, int* kb_per_out) {
 }  // namespace
 
 void read_gemm_trace(unsigned long long* out16) {
-  RLREP_CUDA(cudaMemcpyFromSymbol(out16, g_gemm_trace, sizeof(unsigned long long) * 16));
+  RLREP_CHECK(tc::g_trace_reader != nullptr, "no tcgen05 GEMM has been launched yet");
+  tc::g_trace_reader(out16);
 }
 
 bool tc_eligible(const GemmArgs& a) {
@@ -532,11 +133,12 @@ TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* /*ws*/, s
 }
 
 void launch_tc(const TcGemmPlan& p, cudaStream_t stream) {
+  const bool a = p.args.a_mn;
   switch (p.bn) {
-    case 32: launch_bn<32>(p, stream); break;
-    case 64: launch_bn<64>(p, stream); break;
-    case 128: launch_bn<128>(p, stream); break;
-    case 256: launch_bn<256>(p, stream); break;
+    case 32: a ? tc::launch_tc_32_1(p, stream) : tc::launch_tc_32_0(p, stream); break;
+    case 64: a ? tc::launch_tc_64_1(p, stream) : tc::launch_tc_64_0(p, stream); break;
+    case 128: a ? tc::launch_tc_128_1(p, stream) : tc::launch_tc_128_0(p, stream); break;
+    case 256: a ? tc::launch_tc_256_1(p, stream) : tc::launch_tc_256_0(p, stream); break;
     default: throw Error("bad bn");
   }
 }
