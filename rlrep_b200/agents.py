@@ -361,4 +361,139 @@ class VLSACAgent(SACAgent):
         return dict(zip(self._h.metric_names, (float(x) for x in m)))
 
 
-AGENTS = {"sac": SACAgent, "ctrlsac": CTRLSACAgent, "vlsac": VLSACAgent}
+def _trunk_layers(prefix, dims, kind="default"):
+    """Linear layers of util.mlp / spedersac mlp: Sequential indices 0, 2, 4, ... (utils/util.py:85-96)."""
+    return [(f"{prefix}.{2 * i}", dims[i + 1], dims[i], kind) for i in range(len(dims) - 1)]
+
+
+def _rff_critic_layers(D, H):
+    d = "default"
+    return [("critic.l1", H, D, d), ("critic.l2", H, H, d), ("critic.l3", 1, H, d), ("critic.l4", H, D, d),
+            ("critic.l5", H, H, d), ("critic.l6", 1, H, d)]
+
+
+class SPEDERSACAgent(SACAgent):
+    """Drop-in for agent.spedersac.spedersac_agent.SPEDERSACAgent (spedersac_agent.py:97-322)."""
+
+    alg = "spedersac"
+
+    def __init__(self, state_dim, action_dim, action_space, phi_and_mu_lr=-1, phi_hidden_dim=-1, phi_hidden_depth=-1,
+                 mu_hidden_dim=-1, mu_hidden_depth=-1, critic_and_actor_lr=-1, critic_and_actor_hidden_dim=-1,
+                 discount=0.99, target_update_period=2, tau=0.005, alpha=0.1, auto_entropy_tuning=True, hidden_dim=1024,
+                 feature_tau=0.005, feature_dim=2048, use_feature_target=True, extra_feature_steps=1, **kw):
+        if min(phi_and_mu_lr, critic_and_actor_lr) <= 0 or min(phi_hidden_depth, mu_hidden_depth) < 0 or \
+                critic_and_actor_hidden_dim <= 0 or (phi_hidden_depth > 0 and phi_hidden_dim <= 0) or \
+                (mu_hidden_depth > 0 and mu_hidden_dim <= 0):
+            raise ValueError("SPEDERSACAgent needs phi_and_mu_lr, critic_and_actor_lr, the phi / mu trunk sizes and "
+                             "critic_and_actor_hidden_dim (the reference's -1 defaults are placeholders, main.py:95-104)")
+        self.feature_dim, self.feature_tau = int(feature_dim), float(feature_tau)
+        self.use_feature_target, self.extra_feature_steps = bool(use_feature_target), int(extra_feature_steps)
+        self._phi = (int(phi_hidden_dim), int(phi_hidden_depth))
+        self._mu = (int(mu_hidden_dim), int(mu_hidden_depth))
+        self._feat_lr = float(phi_and_mu_lr)
+        super().__init__(state_dim, action_dim, action_space, lr=critic_and_actor_lr, discount=discount,
+                         target_update_period=target_update_period, tau=tau, alpha=alpha,
+                         auto_entropy_tuning=auto_entropy_tuning, hidden_dim=critic_and_actor_hidden_dim, **kw)
+
+    def _config(self, batch_size):
+        c = super()._config(batch_size)  # critic / actor / alpha all at critic_and_actor_lr (:168-179)
+        c.feature_dim = self.feature_dim
+        c.feature_steps = self.extra_feature_steps + 1
+        c.lr_feature = self._feat_lr
+        c.feature_tau = self.feature_tau
+        c.use_feature_target = int(self.use_feature_target)
+        c.phi_hidden_dim, c.phi_hidden_depth = self._phi
+        c.mu_hidden_dim, c.mu_hidden_depth = self._mu
+        return c
+
+    def _layers(self):
+        S, A, H, D = self.state_dim, self.action_dim, self._hidden, self.feature_dim
+        (ph, pd), (mh, md) = self._phi, self._mu
+        return _trunk_layers("phi.trunk", [S + A] + [ph] * pd + [D]) + _trunk_layers("mu.trunk", [S] + [mh] * md + [D]) + \
+            [("theta.l", 1, D, "default")] + self._actor_layers(H) + _rff_critic_layers(D, H)
+
+    def _draw(self, buffer, batch_size):  # SURVEY A.5: K x (randint[B], randint[B]) -> randn[B,A] -> randn[B,A]
+        K = self.extra_feature_steps + 1
+        idx = np.concatenate([np.random.randint(0, buffer.size, size=batch_size) for _ in range(2 * K)])
+        eps = [torch.randn(batch_size, self.action_dim) for _ in range(2)]
+        return idx, torch.stack(eps).numpy().reshape(-1)
+
+    def _info(self, m):
+        return dict(zip(self._h.metric_names, (float(x) for x in m)))
+
+
+class DIFFSRSACAgent(SACAgent):
+    """Drop-in for agent.diffsrsac.diffsrsac_agent.DIFFSRSACAgent (diffsrsac_agent.py:93-343)."""
+
+    alg = "diffsrsac"
+
+    def __init__(self, state_dim, action_dim, action_space, feature_dim=256, phi_and_nabla_mu_lr=0.003,
+                 phi_hidden_dim=256, phi_hidden_depth=1, nabla_mu_hidden_dim=512, nabla_mu_hidden_depth=1,
+                 critic_and_actor_lr=3e-4, discount=0.99, target_update_period=2, tau=0.005, alpha=0.1,
+                 auto_entropy_tuning=True, hidden_dim=256, extra_feature_steps=3, num_noises=1000,
+                 critic_elu_layer_regularizer_lambda=0, DARL_noise_a=0.3, DARL_noise_b=0.1, sigma_scale_factor=0.449,
+                 **kw):
+        if critic_elu_layer_regularizer_lambda != 0:
+            # the reference multiplies the regulariser into losses that are never optimised (SURVEY.md A.6 #1): it can
+            # only change the reported q_loss_reg.  Not reproduced for lambda != 0.
+            raise NotImplementedError("critic_elu_layer_regularizer_lambda != 0")
+        self.feature_dim, self.extra_feature_steps = int(feature_dim), int(extra_feature_steps)
+        self.num_noises, self.sigma_scale_factor = int(num_noises), float(sigma_scale_factor)
+        self._phi = (int(phi_hidden_dim), int(phi_hidden_depth))
+        self._nabla = (int(nabla_mu_hidden_dim), int(nabla_mu_hidden_depth))
+        self._feat_lr = float(phi_and_nabla_mu_lr)
+        self._noise_ab = (float(DARL_noise_a), float(DARL_noise_b))
+        super().__init__(state_dim, action_dim, action_space, lr=critic_and_actor_lr, discount=discount,
+                         target_update_period=target_update_period, tau=tau, alpha=alpha,
+                         auto_entropy_tuning=auto_entropy_tuning, hidden_dim=hidden_dim, **kw)
+        self.noise_alphabars = self.generate_alphabars(*self._noise_ab, self.num_noises)
+        self._pending_state["alphabars"] = self.noise_alphabars.reshape(1, -1)
+
+    @staticmethod
+    def generate_alphabars(a, b, num_alphas):
+        """alpha-bar table from the Beta(a, b) CDF, clipped to [raw[-2], raw[1]] (diffsrsac_agent.py:178-203); host-side
+        construction-time state, like in the reference."""
+        from scipy.stats import beta
+        raw = 1.0 - beta.cdf(np.linspace(0, 1, num_alphas), a, b)
+        return torch.tensor(np.clip(raw, a_min=raw[-2], a_max=raw[1])).float()
+
+    def _config(self, batch_size):
+        c = super()._config(batch_size)
+        c.feature_dim = self.feature_dim
+        c.feature_steps = self.extra_feature_steps + 1
+        c.lr_feature = self._feat_lr
+        c.phi_hidden_dim, c.phi_hidden_depth = self._phi
+        c.nabla_mu_hidden_dim, c.nabla_mu_hidden_depth = self._nabla
+        c.num_noises = self.num_noises
+        c.sigma_scale_factor = self.sigma_scale_factor
+        return c
+
+    def _layers(self):
+        S, A, H, D = self.state_dim, self.action_dim, self._hidden, self.feature_dim
+        (ph, pd), (nh, nd) = self._phi, self._nabla
+        return _trunk_layers("critic_feed_feature.z_vector", [S + A] + [ph] * pd + [D]) + \
+            _trunk_layers("nablamu_net.Mu_z_by_s_layer", [S + 1] + [nh] * nd + [D * S]) + \
+            self._actor_layers(H) + _rff_critic_layers(D, H)
+
+    def _draw(self, buffer, batch_size):
+        """K x (randint[B] -> torch.randint(0, num_noises, (B,)) -> normal[B,S]) -> randn[B,A] -> randn[B,A].
+        Index layout per iteration: B replay rows, then B noise levels."""
+        K, B, S = self.extra_feature_steps + 1, batch_size, self.state_dim
+        idx, eps = [], []
+        for _ in range(K):
+            idx.append(np.random.randint(0, buffer.size, size=B))
+            idx.append(torch.randint(0, self.num_noises, (B,)).numpy())  # diffsrsac_agent.py:276
+            eps.append(torch.normal(mean=torch.zeros(B, S), std=torch.ones(B, S) * self.sigma_scale_factor).reshape(-1))
+        eps += [torch.randn(B, self.action_dim).reshape(-1) for _ in range(2)]
+        return np.concatenate(idx), torch.cat(eps).numpy()
+
+    def _info(self, m):
+        d = dict(zip(self._h.metric_names, (float(x) for x in m)))
+        noreg = float(np.float32(d["q1_loss"]) + np.float32(d["q2_loss"]))
+        # diffsrsac_agent.py:229-239: the regulariser is lambda = 0; 'q2' reports mean(Q1) (SURVEY.md A.6 #5)
+        return {"score_loss": d["score_loss"], "q_loss_reg": noreg, "q_loss_noreg": noreg, "q1": d["q1"], "q2": d["q1"],
+                "actor_loss": d["actor_loss"], "alpha_loss": d["alpha_loss"], "alpha": d["alpha"]}
+
+
+AGENTS = {"sac": SACAgent, "ctrlsac": CTRLSACAgent, "vlsac": VLSACAgent, "spedersac": SPEDERSACAgent,
+          "diffsrsac": DIFFSRSACAgent}

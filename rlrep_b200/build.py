@@ -43,15 +43,30 @@ def _newer(target: Path, deps) -> bool:
     return all(Path(d).stat().st_mtime <= t for d in deps)
 
 
+def _deps(src: Path, seen=None):
+    """Transitive closure of the quoted #includes of `src` inside csrc/ and include/ (so touching agent.cuh does not
+    recompile the GEMM units)."""
+    seen = set() if seen is None else seen
+    for line in src.read_text().splitlines():
+        line = line.strip()
+        if line.startswith('#include "'):
+            name = line.split('"')[1]
+            for base in (CSRC, HERE.parent / "include"):
+                h = base / name
+                if h.exists() and h not in seen:
+                    seen.add(h)
+                    _deps(h, seen)
+    return seen
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
     nvcc = _nvcc()
     OBJ.mkdir(exist_ok=True)
     sources = sorted(CSRC.glob("*.cu"))
-    headers = sorted(CSRC.glob("*.cuh")) + sorted((HERE.parent / "include").glob("*.h")) + [Path(__file__)]
     jobs = []
     for src in sources:
         obj = OBJ / (src.stem + ".o")
-        if force or not _newer(obj, [src, *headers]):
+        if force or not _newer(obj, [src, *_deps(src), Path(__file__)]):
             cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
             if verbose:
                 cmd.insert(1, "-Xptxas=-v")

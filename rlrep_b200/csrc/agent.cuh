@@ -141,6 +141,23 @@ inline LinearSlot add_linear(ParamGroup& g, const std::string& name, int out, in
   return s;
 }
 
+// Two linears that share their input, stored back to back so they run as ONE GEMM: weights [out_a + out_b, in],
+// biases [out_a + out_b].  Rows are padded up to a multiple of 32 after the second block.
+inline LinearSlot add_stacked(ParamGroup& g, const std::string& a, int out_a, const std::string& b, int out_b, int in) {
+  RLREP_CHECK(in % 32 == 0, "stacked heads need an input width that is a multiple of 32");
+  LinearSlot s;
+  s.out = out_a + out_b;
+  s.in = in;
+  s.ld = in;
+  s.out_alloc = round_up32(s.out);
+  s.w_off = g.add(a + ".weight", out_a, in);
+  g.add(b + ".weight", out_b, in, in, s.out_alloc - out_a);
+  s.b_off = g.add(a + ".bias", out_a, 1, 1, out_a, /*exact=*/true);
+  g.add(b + ".bias", out_b, 1, 1, s.out_alloc - out_a, /*exact=*/true);
+  g.align4();
+  return s;
+}
+
 // ---------------------------------------------------------------------------------------------- replay ring
 // Device-resident fp32 ring of packed records  [ s (S) | a (A) | r | d | pad | s' (S) | pad ]  with the s' block
 // and the record size rounded up to 4 floats, so gathers are whole 128-bit loads and cat(s, a) is contiguous.
@@ -287,5 +304,7 @@ class Agent {
 std::unique_ptr<Agent> make_sac_agent(const AgentConfig& cfg, cudaStream_t s);
 std::unique_ptr<Agent> make_ctrlsac_agent(const AgentConfig& cfg, cudaStream_t s);
 std::unique_ptr<Agent> make_vlsac_agent(const AgentConfig& cfg, cudaStream_t s);
+std::unique_ptr<Agent> make_spedersac_agent(const AgentConfig& cfg, cudaStream_t s);
+std::unique_ptr<Agent> make_diffsrsac_agent(const AgentConfig& cfg, cudaStream_t s);
 
 }  // namespace rlrep

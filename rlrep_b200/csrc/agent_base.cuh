@@ -32,7 +32,7 @@ class SacBase : public Agent {
     RLREP_CHECK(n_idx == idx_per_train() && n_eps == eps_per_train(), "wrong number of indices / noise values");
     RLREP_CHECK(n_metrics >= (int)metric_names().size(), "metrics buffer too small");
     for (int i = 0; i < n_idx; ++i)
-      RLREP_CHECK(idx_host[i] >= 0 && idx_host[i] < ring.size, "replay index out of range");
+      RLREP_CHECK(!is_replay_index(i) || (idx_host[i] >= 0 && idx_host[i] < ring.size), "replay index out of range");
     if (ring_bound_ != &ring) {  // graphs bake the ring pointer in
       graph_.reset();
       ring_bound_ = &ring;
@@ -158,7 +158,11 @@ class SacBase : public Agent {
   }
   void begin_update() { ev_next_ = 0; }
 
-  void plan_common(int n_idx, int n_eps, int ring_R) {
+  // Position i of the index array is a replay-ring row (range-checked against the ring); agents that also receive
+  // other host-drawn integers (Diff-SR's noise levels) override this.
+  virtual bool is_replay_index(int /*i*/) const { return true; }
+
+  void plan_common(int n_idx, int n_eps, int ring_R, int batch_rows = 0) {
     R_ = ring_R;
     actor_g_.name = "actor";
     a0_ = add_linear(actor_g_, "actor.trunk.0", AH_, S_);  // agent/sac/actor.py:66-74
@@ -169,7 +173,7 @@ class SacBase : public Agent {
     arena_.want(&metrics_dev_, kNumMetrics);
     arena_.want(&idx_dev_, n_idx);
     arena_.want(&eps_dev_, n_eps);
-    arena_.want(&batch_, (size_t)B_ * R_);
+    arena_.want(&batch_, (size_t)(batch_rows > 0 ? batch_rows : B_) * R_);
     arena_.want(&ah1_, (size_t)B_ * AH_);
     arena_.want(&ah2_, (size_t)B_ * AH_);
     arena_.want(&head_, (size_t)B_ * 2 * A_);

@@ -258,6 +258,8 @@ int rlrep_agent_create(const rlrep_agent_config* c, void* stream, rlrep_agent** 
     case RLREP_ALG_SAC: h->impl = make_sac_agent(a, st); break;
     case RLREP_ALG_CTRLSAC: h->impl = make_ctrlsac_agent(a, st); break;
     case RLREP_ALG_VLSAC: h->impl = make_vlsac_agent(a, st); break;
+    case RLREP_ALG_SPEDERSAC: h->impl = make_spedersac_agent(a, st); break;
+    case RLREP_ALG_DIFFSRSAC: h->impl = make_diffsrsac_agent(a, st); break;
     default: throw Error("algorithm not implemented in this build");
   }
   index_tensors(h.get());

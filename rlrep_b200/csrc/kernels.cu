@@ -4,52 +4,11 @@
 #include "common.cuh"
 #include "epilogue.cuh"
 #include "kernels.cuh"
+#include "reduce.cuh"
 
 namespace rlrep {
 
 namespace {
-
-__device__ __forceinline__ float warp_sum(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ float warp_max(float v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-// Block-wide sum, result valid in every thread.  Fixed reduction tree => deterministic.
-template <int kThreads>
-__device__ __forceinline__ float block_sum(float v, float* scratch /* >= 33 floats */) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  v = warp_sum(v);
-  __syncthreads();
-  if (lane == 0) scratch[warp] = v;
-  __syncthreads();
-  if (warp == 0) {
-    float t = lane < kThreads / 32 ? scratch[lane] : 0.f;
-    t = warp_sum(t);
-    if (lane == 0) scratch[32] = t;
-  }
-  __syncthreads();
-  return scratch[32];
-}
-template <int kThreads>
-__device__ __forceinline__ float block_max(float v, float* scratch) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  v = warp_max(v);
-  __syncthreads();
-  if (lane == 0) scratch[warp] = v;
-  __syncthreads();
-  if (warp == 0) {
-    float t = lane < kThreads / 32 ? scratch[lane] : -INFINITY;
-    t = warp_max(t);
-    if (lane == 0) scratch[32] = t;
-  }
-  __syncthreads();
-  return scratch[32];
-}
 
 // ------------------------------------------------------------------------------------------- tick
 __device__ __forceinline__ AdamHyper adam_hyper(double lr, long long t) {

@@ -129,6 +129,39 @@ void launch_group_mean(const float* hid, int ld, int B, int NN, int C, float* ou
 void launch_group_mean_bwd(const float* dmean, const float* hid, int ld, int B, int NN, int C, float* dhid,
                            float* colsum_partial, cudaStream_t s);
 
+// ---- SPEDER-SAC (agent/spedersac/spedersac_agent.py:181-219) ------------------------------------------------------
+// Features of two batches are stacked: rows [0, B) belong to the update batch, rows [B, 2B) to the second, independent
+// batch (phi~, mu~).  The spectral loss is
+//   model = mean_i(-2 <phi_i, mu_i>) + mean_ij((phi~ mu~^T)(phi~ mu~^T)^T)
+// and its second term equals ||mu~ u||^2 / B^2 with u = colsum(phi~) (sum_ij sum_k pa_ik pa_jk = sum_k (sum_i pa_ik)^2),
+// so no B x B matrix is ever formed.
+//   diag[i] = <phi_i, mu_i>, rpred[i] = <phi_i, theta_w> + theta_b, c[i] = <mu~_i, u>      (one warp per row)
+void launch_speder_rows(const float* zphi, const float* zmu, int D, int B, const float* theta_w, const float* theta_b,
+                        const float* u, float* diag, float* rpred, float* c, cudaStream_t s);
+// drp = (rpred - r) / B;  metrics = {total_loss, model_loss, r_loss}
+void launch_speder_finalize(const float* diag, const float* c, const float* rpred, const float* reward, int ld_r, int B,
+                            float* drp, float* metrics, cudaStream_t s);
+// dzphi[i] = -2/B mu_i + drp_i theta_w;  dzmu[i] = -2/B phi_i;  dzphi[B+i] = 2/B^2 w (w = mu~^T c);  dzmu[B+k] = 2/B^2 c_k u
+void launch_speder_grad(const float* zphi, const float* zmu, int D, int B, const float* drp, const float* theta_w,
+                        const float* c, const float* u, const float* w, float* dzphi, float* dzmu, cudaStream_t s);
+
+// ---- Diff-SR-SAC (agent/diffsrsac/diffsrsac_agent.py:271-318) -----------------------------------------------------
+// DDPM perturbation of s' at the host-drawn noise levels: ab = alphabars[level[b]];
+//   xin[b] = [ sqrt(ab) s' + sqrt(1 - ab) noise | ab | 0 ... ]  (row pitch ld_x),  target = -(s~' - sqrt(ab) s'),
+//   coef[b] = (1 - ab) * sigma.   `noise` is already scaled by sigma (torch.normal(0, sigma) drawn by the host).
+void launch_diffsr_perturb(const float* next_state, int ld_rec, const float* noise, const long long* level,
+                           const float* alphabars, int n_levels, float sigma, int B, int S, float* xin, int ld_x,
+                           float* target, float* coef, cudaStream_t s);
+// score[b, s] = sum_d phi[b, d] flat[b, d*S + s] (the reference's bmm);  diff = target - coef * score;
+// loss_rows[b] = sum_s diff^2;  dscore = d(sum_b loss_rows / B) / dscore = -coef * 2/B * diff.
+void launch_diffsr_score(const float* phi, const float* flat, int D, int S, const float* target, const float* coef, int B,
+                         float* dscore, float* loss_rows, cudaStream_t s);
+// dflat[b, d*S + s] = phi[b, d] dscore[b, s];  dphi[b, d] = sum_s dscore[b, s] flat[b, d*S + s]
+void launch_diffsr_score_bwd(const float* phi, const float* flat, int D, int S, int B, const float* dscore, float* dflat,
+                             float* dphi, cudaStream_t s);
+// out[0] = scale * sum(x[0:n])   (single block, deterministic)
+void launch_sum_scaled(const float* x, int n, float scale, float* out, cudaStream_t s);
+
 // Fused multi-tensor Adam (+ optional Polyak of a prefix of the arena into its target copy).
 // One launch updates a whole optimiser group laid out as flat arrays p / g / m / v of n floats (n % 4 == 0).
 //   torch.optim.Adam defaults: beta = (0.9, 0.999), eps = 1e-8, no weight decay / amsgrad.

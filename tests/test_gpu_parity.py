@@ -120,6 +120,17 @@ CASES = {
     "ctrlsac": ("ctrlsac", HC, dict(hidden_dim=1024, feature_dim=2048, extra_feature_steps=3), 256),
     "vlsac_hc": ("vlsac", HC, dict(hidden_dim=256, feature_dim=256, extra_feature_steps=3), 64),
     "vlsac_hum": ("vlsac", dict(S=376, A=17), dict(hidden_dim=256, feature_dim=256, extra_feature_steps=3), 256),
+    # main.py:95-104 (feature_dim stays at the class default 2048)
+    "spedersac": ("spedersac", HC, dict(feature_dim=2048, extra_feature_steps=5, phi_and_mu_lr=1e-5, phi_hidden_dim=512,
+                                        phi_hidden_depth=1, mu_hidden_dim=512, mu_hidden_depth=0, critic_and_actor_lr=3e-4,
+                                        critic_and_actor_hidden_dim=256), 256),
+    "spedersac_deep": ("spedersac", HC, dict(feature_dim=128, extra_feature_steps=1, phi_and_mu_lr=1e-4, phi_hidden_dim=64,
+                                             phi_hidden_depth=2, mu_hidden_dim=96, mu_hidden_depth=1,
+                                             critic_and_actor_lr=3e-4, critic_and_actor_hidden_dim=64), 48),
+    # main.py:93-94: class defaults (feature_dim 256, phi 256x1, grad-mu 512x1, K = 4)
+    "diffsrsac": ("diffsrsac", HC, dict(hidden_dim=256), 256),
+    "diffsrsac_odd": ("diffsrsac", dict(S=11, A=3), dict(hidden_dim=64, feature_dim=64, phi_hidden_dim=64,
+                                                         nabla_mu_hidden_dim=96, extra_feature_steps=1), 40),
 }
 
 

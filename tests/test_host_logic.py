@@ -22,6 +22,9 @@ CASES = {
     "sac": (dict(hidden_dim=32), 64),
     "ctrlsac": (dict(hidden_dim=32, feature_dim=64, extra_feature_steps=3), 32),
     "vlsac": (dict(hidden_dim=32, feature_dim=64, extra_feature_steps=3), 32),
+    "spedersac": (dict(feature_dim=64, extra_feature_steps=2, phi_and_mu_lr=1e-5, phi_hidden_dim=64, phi_hidden_depth=1,
+                       mu_hidden_dim=64, mu_hidden_depth=0, critic_and_actor_lr=3e-4, critic_and_actor_hidden_dim=32), 32),
+    "diffsrsac": (dict(hidden_dim=32, feature_dim=32, phi_hidden_dim=32, nabla_mu_hidden_dim=64, extra_feature_steps=2), 32),
 }
 
 
@@ -49,8 +52,13 @@ def test_draw_consumes_the_global_rngs_exactly_like_the_reference(alg):
     idx, eps = agent._draw(FakeBuffer(), B)
     assert np.array_equal(np.random.get_state()[1], np_state)
     assert torch.equal(torch.get_rng_state(), torch_state)
+    K = kw.get("extra_feature_steps", 0) + 1
+    if alg == "diffsrsac":  # per feature iteration: B replay rows, then B noise levels (torch.randint, CPU generator)
+        idx = idx.reshape(K, 2, B)
+        assert idx[:, 1].min() >= 0 and idx[:, 1].max() < 1000
+        idx = idx[:, 0].reshape(-1)
     assert np.array_equal(idx, np.concatenate(drawn))
-    n_feat_eps = (kw["extra_feature_steps"] + 1) * B * kw["feature_dim"] if alg == "vlsac" else 0
+    n_feat_eps = {"vlsac": K * B * kw.get("feature_dim", 0), "diffsrsac": K * B * S}.get(alg, 0)
     assert eps.shape == (n_feat_eps + 2 * B * A,)
 
 
