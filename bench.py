@@ -35,12 +35,21 @@ import numpy as np
 ROOT = Path(__file__).resolve().parent
 sys.path.insert(0, str(ROOT))
 
+SPEDER_MAIN = dict(extra_feature_steps=5, phi_and_mu_lr=1e-5, phi_hidden_dim=512, phi_hidden_depth=1, mu_hidden_dim=512,
+                   mu_hidden_depth=0, critic_and_actor_lr=3e-4, critic_and_actor_hidden_dim=256, feature_dim=2048)
+
 WORKLOADS = {
-    # BASELINE.json configs[1]
+    # BASELINE.json configs[1] -- the configuration the metric is quoted on
     "ctrlsac_hc_b256": dict(alg="ctrlsac", S=17, A=6, B=256, rows=1_000_000,
                             kw=dict(hidden_dim=1024, feature_dim=2048, extra_feature_steps=3)),
     # BASELINE.json configs[0] (the reference's own CPU-runnable case)
     "sac_hc_b256": dict(alg="sac", S=17, A=6, B=256, rows=1_000_000, kw=dict(hidden_dim=256)),
+    # BASELINE.json configs[2]
+    "vlsac_hum_b1024": dict(alg="vlsac", S=376, A=17, B=1024, rows=200_000,
+                            kw=dict(hidden_dim=256, feature_dim=256, extra_feature_steps=3)),
+    # the other two state-based agents at what main.py passes (main.py:93-104)
+    "spedersac_hc_b256": dict(alg="spedersac", S=17, A=6, B=256, rows=1_000_000, kw=SPEDER_MAIN),
+    "diffsrsac_hc_b256": dict(alg="diffsrsac", S=17, A=6, B=256, rows=1_000_000, kw=dict(hidden_dim=256)),
 }
 
 
@@ -49,31 +58,29 @@ class Space:
         self.low, self.high, self.shape = -np.ones(A, np.float32), np.ones(A, np.float32), (A,)
 
 
+def module_params(w):
+    from oracle import rl_oracle as O  # layer table only (shapes), no arithmetic
+    return {m: sum(o * i + o for _, o, i in layers) for m, layers in O.layer_table(w["alg"], w["S"], w["A"], w["kw"])}
+
+
 def algorithmic_bytes(w):
     """HBM bytes one update must move (SURVEY.md 8d / BASELINE.md): Adam 28 B/param (p, g, m, v read; p, m, v
     written), Polyak 12 B/param, plus every fp32 weight streamed once per GEMM that uses it."""
-    S, A, kw = w["S"], w["A"], w["kw"]
-    if w["alg"] == "ctrlsac":
-        H, D, K = kw["hidden_dim"], kw["feature_dim"], kw["extra_feature_steps"] + 1
-        phi = (S + A) * H + H + H * H + H + H * D + D
-        mu = S * H + H + H * H + H + H * D + D
-        theta = D + 1
-        critic = 2 * (D * H + H + H + 1)
-        actor = S * 256 + 256 + 256 * 256 + 256 + 256 * 2 * A + 2 * A
-        feat = phi + mu + theta
-        opt = 28 * (K * feat + critic + actor) + 12 * (K * phi + critic / 2)
-        # weight streaming: fwd + dgrad per feature step (phi, mu), critic step: phi x2, critic/target; actor: phi fwd
-        # + dgrad, critic fwd + dgrad, actor fwd + dgrad
-        stream = 4 * (K * 2 * (phi + mu) + 2 * phi + 2 * critic + 2 * phi + 2 * critic + 3 * actor)
-        return dict(optimizer=opt, weights=stream, total=opt + stream, adam_feature_launch=28 * feat + 12 * phi)
-    if w["alg"] == "sac":
-        H = kw["hidden_dim"]
-        critic = 2 * ((S + A) * H + H + H * H + H + H + 1)
-        actor = S * H + H + H * H + H + H * 2 * A + 2 * A
-        opt = 28 * (critic + actor) + 12 * critic / 2
-        stream = 4 * (4 * critic + 3 * actor)
-        return dict(optimizer=opt, weights=stream, total=opt + stream, adam_feature_launch=28 * critic + 12 * critic)
-    raise ValueError(w["alg"])
+    n = module_params(w)
+    alg = w["alg"]
+    K = w["kw"].get("extra_feature_steps", {"sac": -1, "diffsrsac": 3}.get(alg, 1)) + 1  # class defaults
+    feat = {"ctrlsac": ("phi", "mu", "theta"), "vlsac": ("encoder", "decoder", "f"), "spedersac": ("phi", "mu", "theta"),
+            "diffsrsac": ("phi", "nablamu"), "sac": ()}[alg]
+    feat_target = {"ctrlsac": "phi", "vlsac": "f", "spedersac": "phi"}.get(alg)
+    feat_n = sum(n[m] for m in feat)
+    critic_adam = 0 if alg == "diffsrsac" else n["critic"]  # SURVEY.md A.6 #1
+    opt = 28 * (K * feat_n + critic_adam + n["actor"]) + 12 * (K * n.get(feat_target, 0) + n["critic"] / 2)
+    # weight streaming: forward + dgrad per feature step; critic step: feature net x2 + critic + target critic (+ critic
+    # dgrad inside wgrad chain); actor step: feature net fwd + dgrad, critic fwd + dgrad, actor fwd + dgrad (+ a' fwd)
+    used = {"ctrlsac": "phi", "vlsac": "f", "spedersac": "phi", "diffsrsac": "phi"}.get(alg)
+    used_n = n.get(used, 0)
+    stream = 4 * (K * 2 * feat_n + 2 * used_n + 2 * n["critic"] + 2 * used_n + 2 * n["critic"] + 3 * n["actor"])
+    return dict(optimizer=opt, weights=stream, total=opt + stream)
 
 
 # ---------------------------------------------------------------------------------------------------- clocks
@@ -128,12 +135,40 @@ class ClockSampler:
         return out
 
 
+def measure_tf32_peak():
+    """Dense TF32 tensor-core peak the way MEASURED_PEAKS.json measures bf16: torch.matmul (cuBLAS) on 8192^3, best of
+    10 with CUDA events.  Only a roofline denominator -- never on the measured path."""
+    import torch
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn(8192, 8192, device="cuda")
+        b = torch.randn(8192, 8192, device="cuda")
+        c = torch.empty(8192, 8192, device="cuda")
+        for _ in range(3):
+            torch.matmul(a, b, out=c)
+        best = 1e9
+        for _ in range(10):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            torch.matmul(a, b, out=c)
+            e1.record()
+            e1.synchronize()
+            best = min(best, e0.elapsed_time(e1))
+        return 2 * 8192 ** 3 / (best * 1e-3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old
+
+
 # ---------------------------------------------------------------------------------------------------- CPU arm
 def make_oracle(w, as_written=True):
     from oracle import rl_oracle as O
     kw = dict(w["kw"])
     init = O.init_state(w["alg"], w["S"], w["A"], kw, seed=0)
     extra = dict(as_written=as_written) if w["alg"] == "ctrlsac" else {}
+    if w["alg"] == "vlsac":
+        import torch
+        extra["critic_noise"] = torch.randn(20, kw.get("feature_dim", 256), generator=torch.Generator().manual_seed(1234))
     agent = O.ORACLES[w["alg"]](w["S"], w["A"], init, discount=0.99, tau=0.005, **kw, **extra)
     ring = O.synthetic_ring(w["S"], w["A"], min(w["rows"], 200_000), seed=0)
     return agent, ring
@@ -159,7 +194,8 @@ def run_reference(args, w, rank, world):
     if rank != 0:
         return
     ups, ms, cores = time_oracle(w, args.steps, args.warmup, as_written=True)
-    sample = f"{args.steps} full train() calls after {args.warmup} warm-up, as-written [B,B,D] broadcast logits"
+    sample = f"{args.steps} full train() calls after {args.warmup} warm-up, reference arithmetic as written" + \
+        (" ([B,B,D] broadcast logits)" if w["alg"] == "ctrlsac" else "")
     line = {
         "impl": "reference", "metric": "agent updates/sec", "value": ups, "unit": "updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -233,12 +269,15 @@ def run_ours(args, w, rank, world, local_rank):
     else:
         e2e_ms = e2e_s * 1e3
 
-    # ---- (3) per-kernel profile (eager, event behind every launch) -> dominant kernel for the roofline
+    # ---- (3) per-kernel profile (eager, one stream, an event behind every launch).  Every launch carries its
+    # algorithmic bytes / flops (operands read once, results written once), so each kernel gets a roofline fraction.
     roofline, top = None, []
     if rank == 0:
-        cap = 4096
+        cap = 8192
         names = (C.c_char_p * cap)()
         kms = (C.c_float * cap)()
+        kby = (C.c_double * cap)()
+        kfl = (C.c_double * cap)()
         n = C.c_int()
         agg = {}
         reps = 3
@@ -246,12 +285,14 @@ def run_ours(args, w, rank, world, local_rank):
             i1, e1 = agent._draw(buf, B)
             i1 = np.ascontiguousarray(i1, dtype=np.int64)
             e1 = np.ascontiguousarray(e1, dtype=np.float32)
-            _lib.check(h.lib.rlrep_agent_profile_train(h.h, buf._h, i1.ctypes.data, e1.ctypes.data, cap, names, kms,
-                                                       C.byref(n)))
+            _lib.check(h.lib.rlrep_agent_profile_train(h.h, buf._h, i1.ctypes.data, e1.ctypes.data, cap, names, kms, kby,
+                                                       kfl, C.byref(n)))
             for i in range(min(n.value, cap)):
-                a = agg.setdefault(names[i].decode(), [0.0, 0])
+                a = agg.setdefault(names[i].decode(), [0.0, 0, 0.0, 0.0])
                 a[0] += kms[i]
                 a[1] += 1
+                a[2] += kby[i]
+                a[3] += kfl[i]
         total = sum(v[0] for v in agg.values())
         top = sorted(((k, v[0] / reps, v[1] // reps) for k, v in agg.items()), key=lambda x: -x[1])
         peaks = {}
@@ -259,32 +300,50 @@ def run_ours(args, w, rank, world, local_rank):
         if pk.exists():
             peaks = json.loads(pk.read_text())
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        alg_bytes = algorithmic_bytes(w)
-        # dominant bandwidth-bound kernel: the fused Adam+Polyak launch over the feature group
-        adam = agg.get("adam_polyak")
-        if adam:
-            n_launch = adam[1] / reps
-            per_launch_ms = adam[0] / adam[1]
-            # bytes of an average adam_polyak launch: optimiser traffic of the update / launches per update
-            per_launch_bytes = alg_bytes["optimizer"] / n_launch
-            ach = per_launch_bytes / (per_launch_ms * 1e-3) / 1e9
-            roofline = {"bound": "hbm", "kernel": "adam_polyak_kernel", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                        "frac": ach / hbm_peak, "traffic": None, "launches_per_step": n_launch,
-                        "avg_launch_us": per_launch_ms * 1e3,
-                        "peak_source": "MEASURED_PEAKS.json hbm_gbs" if pk.exists() else "fallback 6650",
-                        "share_of_step": adam[0] / total,
-                        "step": {"algorithmic_bytes": alg_bytes["total"],
-                                 "achieved": alg_bytes["total"] / (dev_ms / args.steps * 1e-3) / 1e9,
-                                 "frac": alg_bytes["total"] / (dev_ms / args.steps * 1e-3) / 1e9 / hbm_peak}}
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs" if pk.exists() else "fallback 6650 GB/s (B200_PROFILING.md)"
+        tf32_peak = measure_tf32_peak()  # cuBLAS TF32 8192^3, measured here the way MEASURED_PEAKS.json measures bf16
+        traffic = {}
+        tp = ROOT / "profiles" / "ncu_traffic.json"  # dram__bytes_read+write per launch from the committed ncu captures
+        if tp.exists():
+            traffic = json.loads(tp.read_text()).get(args.workload, {})
+
+        def kernel_roofline(name):
+            ms_sum, count, by, fl = agg[name]
+            t = ms_sum * 1e-3
+            gbs, tfs = by / t / 1e9, fl / t / 1e12
+            f_hbm, f_tc = gbs / hbm_peak, tfs / tf32_peak
+            bound = "hbm" if f_hbm >= f_tc else "tensor"
+            return {"kernel": name, "bound": bound, "achieved": gbs if bound == "hbm" else tfs,
+                    "peak": hbm_peak if bound == "hbm" else tf32_peak, "unit": "GB/s" if bound == "hbm" else "TFLOP/s",
+                    "frac": max(f_hbm, f_tc), "traffic": traffic.get(name), "launches_per_step": count / reps,
+                    "avg_launch_us": ms_sum / count * 1e3, "algorithmic_bytes_per_launch": by / count,
+                    "algorithmic_flops_per_launch": fl / count, "achieved_gbs": gbs, "achieved_tflops": tfs,
+                    "share_of_step": ms_sum / total}
+
+        ranked = [k for k, _, _ in top if agg[k][2] > 0 or agg[k][3] > 0]
+        if ranked:
+            alg_bytes = algorithmic_bytes(w)
+            step_s = dev_ms / args.steps * 1e-3
+            step_flops = sum(v[3] for v in agg.values()) / reps
+            t_hbm, t_tc = alg_bytes["total"] / (hbm_peak * 1e9), step_flops / (tf32_peak * 1e12)
+            roofline = kernel_roofline(ranked[0])  # the kernel with the largest share of the step
+            roofline["peak_source"] = hbm_src if roofline["bound"] == "hbm" else "cuBLAS TF32 8192^3 measured in this run"
+            roofline["tf32_peak_tflops"] = tf32_peak
+            roofline["kernels"] = [kernel_roofline(k) for k in ranked[1:6]]
+            roofline["step"] = {"algorithmic_bytes": alg_bytes["total"], "algorithmic_flops": step_flops,
+                                "bound": "hbm" if t_hbm >= t_tc else "tensor",
+                                "roofline_ms": max(t_hbm, t_tc) * 1e3, "frac": max(t_hbm, t_tc) / step_s,
+                                "achieved_gbs": alg_bytes["total"] / step_s / 1e9,
+                                "achieved_tflops": step_flops / step_s / 1e12}
 
     # ---- (4) CPU baseline: the oracle port on this box's host cores (rank 0, N = 1 only)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        n_cpu = 6 if w["alg"] == "ctrlsac" else 200
+        n_cpu = {"ctrlsac": 6, "vlsac": 30, "spedersac": 60}.get(w["alg"], 200)  # ~10-30 s of CPU work
         ups, ms_cpu, cores = time_oracle(w, n_cpu, 1, as_written=True)
         cpu = {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port",
                "sample": f"{n_cpu} full train() calls of the same workload after 1 warm-up ({ms_cpu:.0f} ms each), "
-                         f"reference arithmetic as written (broadcast logits)"}
+                         f"reference arithmetic as written" + (" (broadcast logits)" if w["alg"] == "ctrlsac" else "")}
 
     if rank == 0:
         ni, ne = h.n_idx, h.n_eps
@@ -295,7 +354,8 @@ def run_ours(args, w, rank, world, local_rank):
             "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
             "config": {"workload": args.workload, **{k: w[k] for k in ("alg", "S", "A", "B")}, **kw,
                        "ring_rows": w["rows"], "parallelism": f"replicas x{world} (no collective)",
-                       "l2": "no flush: per-update working set (params+grads+Adam moments+targets ~200 MB) exceeds the 126 MB L2"},
+                       "l2": ("no flush: per-update working set (params+grads+Adam moments+targets ~200 MB) exceeds the 126 MB L2"
+                              if w["alg"] == "ctrlsac" else "no flush between updates (working set below L2: see DESIGN.md)")},
             "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "updates/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": ni * 8 + ne * 4, "d2h_bytes_per_step": 32 * 4},
             "gpu_launches": launches * args.steps,

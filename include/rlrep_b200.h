@@ -33,7 +33,7 @@ extern "C" {
 #define RLREP_EXPORT
 #endif
 
-#define RLREP_ABI_VERSION 1
+#define RLREP_ABI_VERSION 2
 
 RLREP_EXPORT int rlrep_abi_version(void);
 RLREP_EXPORT const char* rlrep_last_error(void);
@@ -168,12 +168,14 @@ RLREP_EXPORT int rlrep_agent_act(rlrep_agent* agent, const float* state_host, co
 /* Benchmark aids.  train_resident: n_steps updates back to back with all inputs already in HBM (indices / noise of
  * every step uploaded before the timed region), timed with CUDA events on the agent's stream; idx_host is
  * [n_steps * n_idx], eps_host [n_steps * n_eps].  profile_train: one eager train() with an event behind every kernel
- * launch; names[i] / ms[i] describe launch i (n_entries may exceed max_entries; only max_entries are written). */
+ * launch; names[i] / ms[i] describe launch i, bytes[i] / flops[i] (either may be NULL) its ALGORITHMIC work -- operands
+ * read once, results written once, 2 flop per MAC; 0 for latency-bound bookkeeping kernels (n_entries may exceed
+ * max_entries; only max_entries are written). */
 RLREP_EXPORT int rlrep_agent_train_resident(rlrep_agent* agent, rlrep_ring* ring, const int64_t* idx_host,
                                             const float* eps_host, int n_steps, float* total_ms);
 RLREP_EXPORT int rlrep_agent_profile_train(rlrep_agent* agent, rlrep_ring* ring, const int64_t* idx_host,
                                            const float* eps_host, int max_entries, const char** names, float* ms,
-                                           int* n_entries);
+                                           double* bytes, double* flops, int* n_entries);
 /* Kernels launched by the most recent train() (a graph replay counts the kernels it contains). */
 RLREP_EXPORT int rlrep_agent_last_launches(rlrep_agent* agent, int* launches);
 

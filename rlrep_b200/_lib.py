@@ -96,7 +96,8 @@ def _declare(lib: C.CDLL) -> None:
         "rlrep_agent_act": [vp, vp, vp, vp],
         "rlrep_agent_last_launches": [vp, C.POINTER(i)],
         "rlrep_agent_train_resident": [vp, vp, vp, vp, i, C.POINTER(C.c_float)],
-        "rlrep_agent_profile_train": [vp, vp, vp, vp, i, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(i)],
+        "rlrep_agent_profile_train": [vp, vp, vp, vp, i, C.POINTER(C.c_char_p), C.POINTER(C.c_float),
+                                      C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i)],
     }
     lib.rlrep_agent_metric_name.argtypes = [vp, i]
     lib.rlrep_agent_metric_name.restype = C.c_char_p

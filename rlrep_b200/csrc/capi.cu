@@ -377,7 +377,8 @@ int rlrep_agent_train_resident(rlrep_agent* agent, rlrep_ring* ring, const int64
   RLREP_API_END
 }
 int rlrep_agent_profile_train(rlrep_agent* agent, rlrep_ring* ring, const int64_t* idx_host, const float* eps_host,
-                              int max_entries, const char** names, float* ms, int* n_entries) {
+                              int max_entries, const char** names, float* ms, double* bytes, double* flops,
+                              int* n_entries) {
   RLREP_API_BEGIN
   RLREP_CHECK(agent && ring && idx_host && eps_host && names && ms && n_entries, "null argument");
   std::vector<ProfileEntry> prof =
@@ -386,6 +387,8 @@ int rlrep_agent_profile_train(rlrep_agent* agent, rlrep_ring* ring, const int64_
   for (int i = 0; i < n; ++i) {
     names[i] = prof[i].name;  // string literals with static storage
     ms[i] = prof[i].ms;
+    if (bytes) bytes[i] = prof[i].bytes;
+    if (flops) flops[i] = prof[i].flops;
   }
   *n_entries = (int)prof.size();
   RLREP_API_END

@@ -38,12 +38,19 @@ const char* get_last_error();
 
 // Every kernel launch goes through this: checks the launch, counts it (bench.py reports gpu_launches) and, when a
 // profile is being recorded, drops a CUDA event behind it so per-kernel device time can be read back.
-void note_launch(const char* name, cudaStream_t stream);
+// `bytes` / `flops` = ALGORITHMIC work of the launch (operands read once, results written once; 2 flop per MAC), 0 when
+// the kernel is latency-bound bookkeeping; bench.py turns them into per-kernel roofline fractions.
+void note_launch(const char* name, cudaStream_t stream, double bytes = 0.0, double flops = 0.0);
 long long launch_count();
 #define RLREP_LAUNCHED(name, stream)          \
   do {                                        \
     RLREP_CUDA(cudaGetLastError());           \
     ::rlrep::note_launch(name, stream);       \
+  } while (0)
+#define RLREP_LAUNCHED_W(name, stream, bytes, flops)            \
+  do {                                                          \
+    RLREP_CUDA(cudaGetLastError());                             \
+    ::rlrep::note_launch(name, stream, (bytes), (flops));       \
   } while (0)
 
 // Per-kernel timing of an eager (non-graph) launch sequence: begin, run the launches, end -> (name, ms) per launch.
@@ -51,6 +58,7 @@ void profile_begin(cudaStream_t stream);
 struct ProfileEntry {
   const char* name;
   float ms;
+  double bytes, flops;
 };
 std::vector<ProfileEntry> profile_end(cudaStream_t stream);
 

@@ -193,12 +193,12 @@ __global__ void __launch_bounds__(256) skinny_rowthread_kernel(const SimtParams 
 
 void launch_rowwarp(const SimtParams& p, const Epilogue& e, cudaStream_t s) {
   skinny_rowwarp_kernel<<<ceil_div(p.M * 32, 256), 256, 0, s>>>(p, e);
-  RLREP_LAUNCHED("skinny_rowwarp", s);
+  RLREP_LAUNCHED_W("skinny_rowwarp", s, 4.0 * ((double)p.M * p.K + (double)p.N * p.K + (double)p.M * p.N), 2.0 * p.M * p.N * p.K);
 }
 template <int NT>
 void launch_rowthread(const SimtParams& p, const Epilogue& e, int swapped, cudaStream_t s) {
   skinny_rowthread_kernel<NT><<<ceil_div(p.M, 32), 256, 0, s>>>(p, e, swapped);
-  RLREP_LAUNCHED("skinny_rowthread", s);
+  RLREP_LAUNCHED_W("skinny_rowthread", s, 4.0 * ((double)p.M * p.K + (double)p.N * p.K + (double)p.M * p.N), 2.0 * p.M * p.N * p.K);
 }
 
 }  // namespace
@@ -244,7 +244,7 @@ void launch_simt(const GemmArgs& a, cudaStream_t stream) {
   }
   dim3 grid(ceil_div(a.N, TBN), ceil_div(a.M, TBM));
   gemm_tiled_kernel<<<grid, 256, 0, stream>>>(p, a.epi);
-  RLREP_LAUNCHED("gemm_simt", stream);
+  RLREP_LAUNCHED_W("gemm_simt", stream, 4.0 * ((double)p.M * p.K + (double)p.N * p.K + (double)p.M * p.N), 2.0 * p.M * p.N * p.K);
 }
 
 }  // namespace rlrep

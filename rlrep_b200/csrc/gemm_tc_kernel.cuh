@@ -422,7 +422,8 @@ void launch_variant(const TcGemmPlan& p, cudaStream_t stream) {
   cfg.numAttrs = 1;
   RLREP_CUDA(cudaLaunchKernelEx(&cfg, kern, p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, a.K, p.kb_per_split, a.epi));
   g_trace_reader = &read_trace_here;
-  RLREP_LAUNCHED("gemm_tf32", stream);
+  RLREP_LAUNCHED_W("gemm_tf32", stream, 4.0 * ((double)a.M * a.K + (double)a.N * a.K + (double)a.M * a.N),
+                   2.0 * a.M * a.N * a.K);
 }
 
 }  // namespace

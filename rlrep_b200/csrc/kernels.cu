@@ -558,7 +558,7 @@ void launch_tick(Control* c, const TickParams& p, cudaStream_t s) {
 void launch_gather(const float* ring, int rec4, const long long* idx, int B, float* out, cudaStream_t s) {
   gather_kernel<<<grid_for((size_t)B * rec4, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(ring), rec4, idx, B,
                                                                reinterpret_cast<float4*>(out));
-  RLREP_LAUNCHED("gather", s);
+  RLREP_LAUNCHED_W("gather", s, 2.0 * 16.0 * (double)B * rec4, 0.0);
 }
 
 void launch_ring_write(float* ring, int rec4, long long capacity, long long start, const float* rows, int n,
@@ -572,7 +572,7 @@ void launch_ring_write(float* ring, int rec4, long long capacity, long long star
 void launch_ce_rows(float* logits, int ld, int rows, int cols, int diag_off, float inv_batch, float* loss_rows,
                     cudaStream_t s) {
   ce_rows_kernel<<<rows, 256, 0, s>>>(logits, ld, cols, diag_off, inv_batch, loss_rows);
-  RLREP_LAUNCHED("ce_rows", s);
+  RLREP_LAUNCHED_W("ce_rows", s, 3.0 * 4.0 * (double)rows * cols, 0.0);
 }
 
 void launch_rowdot(const float* X, int ld, int rows, int D, const float* w, const float* b, float* y, cudaStream_t s) {
@@ -698,14 +698,17 @@ void launch_adam_polyak(float* p, const float* g, float* m, float* v, size_t n, 
   adam_polyak_kernel<<<grid_for(n4, 256, 16), 256, 0, s>>>(
       reinterpret_cast<float4*>(p), reinterpret_cast<const float4*>(g), reinterpret_cast<float4*>(m),
       reinterpret_cast<float4*>(v), n4, hyper, reinterpret_cast<float4*>(target), n_polyak / 4, tau, polyak_flag);
-  RLREP_LAUNCHED("adam_polyak", s);
+  // 28 B/param (p, g, m, v read; p, m, v written) + 12 B/param of Polyak (p is already in registers: target read +
+  // written = 8 B; counted as 12 like SURVEY.md 8d counts a stand-alone Polyak) -- a gated Polyak fires every 2nd step
+  const double polyak = target ? 12.0 * (double)n_polyak * (polyak_flag ? 0.5 : 1.0) : 0.0;
+  RLREP_LAUNCHED_W("adam_polyak", s, 28.0 * (double)n + polyak, 0.0);
 }
 
 void launch_polyak(const float* p, float* target, size_t n, float tau, const int* polyak_flag, cudaStream_t s) {
   RLREP_CHECK(n % 4 == 0, "optimizer arenas are padded to float4");
   polyak_kernel<<<grid_for(n / 4, 256, 16), 256, 0, s>>>(reinterpret_cast<const float4*>(p),
                                                         reinterpret_cast<float4*>(target), n / 4, tau, polyak_flag);
-  RLREP_LAUNCHED("polyak", s);
+  RLREP_LAUNCHED_W("polyak", s, 12.0 * (double)n * (polyak_flag ? 0.5 : 1.0), 0.0);
 }
 
 }  // namespace rlrep

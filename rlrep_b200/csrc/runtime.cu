@@ -10,11 +10,12 @@ thread_local long long g_launches = 0;
 thread_local bool g_profiling = false;
 thread_local std::vector<cudaEvent_t> g_events;       // g_events[0] = start, then one per launch
 thread_local std::vector<const char*> g_names;
+thread_local std::vector<double> g_bytes, g_flops;
 }  // namespace
 
 long long launch_count() { return g_launches; }
 
-void note_launch(const char* name, cudaStream_t stream) {
+void note_launch(const char* name, cudaStream_t stream, double bytes, double flops) {
   ++g_launches;
   if (g_profiling) {
     cudaEvent_t e;
@@ -22,6 +23,8 @@ void note_launch(const char* name, cudaStream_t stream) {
       cudaEventRecord(e, stream);
       g_events.push_back(e);
       g_names.push_back(name);
+      g_bytes.push_back(bytes);
+      g_flops.push_back(flops);
     }
   }
 }
@@ -30,6 +33,8 @@ void profile_begin(cudaStream_t stream) {
   for (cudaEvent_t e : g_events) cudaEventDestroy(e);
   g_events.clear();
   g_names.clear();
+  g_bytes.clear();
+  g_flops.clear();
   cudaEvent_t e;
   RLREP_CUDA(cudaEventCreate(&e));
   RLREP_CUDA(cudaEventRecord(e, stream));
@@ -44,7 +49,7 @@ std::vector<ProfileEntry> profile_end(cudaStream_t stream) {
   for (size_t i = 0; i + 1 < g_events.size(); ++i) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, g_events[i], g_events[i + 1]);
-    out.push_back({g_names[i], ms});
+    out.push_back({g_names[i], ms, g_bytes[i], g_flops[i]});
   }
   for (cudaEvent_t e : g_events) cudaEventDestroy(e);
   g_events.clear();

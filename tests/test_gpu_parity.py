@@ -178,3 +178,28 @@ def test_select_action_matches_oracle():
     torch.manual_seed(9)
     e_o = oracle.select_action(s, explore=True)
     assert np.allclose(e_c, e_o, atol=1e-5)
+
+
+@pytest.mark.parametrize("case,keys", [("ctrlsac_small", ("total_loss", "q1_loss", "actor_loss")),
+                                       ("sac", ("q_loss", "actor_loss"))])
+def test_loss_curves_track_the_oracle(case, keys):
+    """north_star: '1k-step loss curves track'.  1000 train() calls on both sides under identical seeds; trajectories
+    may drift apart elementwise (Adam amplifies rounding) but the curves must stay together: the
+    50-step moving averages agree within 5 % of the curve's scale everywhere, and the first 20 steps almost exactly."""
+    alg, shp, kw, B = CASES[case]
+    if case == "sac":
+        kw, B = dict(hidden_dim=64), 64
+    okw = dict(as_written=False) if alg == "ctrlsac" else {}
+    agent, buf, oracle, oring = make_pair(alg, shp["S"], shp["A"], kw, rows=5000, precision="fp32", oracle_kw=okw)
+    n = 1000
+    ci, oi = step_both(agent, buf, oracle, oring, B, n)
+    for k in keys:
+        c = np.array([float(d[k]) for d in ci])
+        o = np.array([float(d[k]) for d in oi])
+        scale = np.abs(o).mean() + 1e-6
+        assert np.abs(c[:20] - o[:20]).max() <= 1e-3 * scale, (k, c[:20], o[:20])
+        win = np.ones(50) / 50
+        cm, om = np.convolve(c, win, mode="valid"), np.convolve(o, win, mode="valid")
+        dev = np.abs(cm - om).max() / scale
+        print(f"{case}/{k}: max moving-average deviation {dev:.2e} of scale {scale:.3g}; step-wise max {np.abs(c - o).max():.2e}")
+        assert dev < 5e-2, (k, dev)
