@@ -213,10 +213,13 @@ class GemmRunner {
   ~GemmRunner();
   // Chooses the tcgen05 path when the operands allow it and the shape is worth a 128-row tile, else CUDA cores.
   void run(const GemmArgs& a, cudaStream_t s);
-  int launches = 0;  // kernels launched since the last reset (bench.py's gpu_launches)
+  // Share of the GPU the next GEMMs should plan for: 0.5 inside fork()/join() sections where two independent kernel
+  // chains run on two streams, 1.0 elsewhere.  Part of the plan-cache key.
+  void set_sm_share(double share) { sm_share_ = share; }
 
  private:
   Precision prec_ = PREC_TF32;
+  double sm_share_ = 1.0;
   float* ws_ = nullptr;
   size_t ws_floats_ = 0;
   std::unordered_map<std::string, TcGemmPlan> plans_;

@@ -2,6 +2,8 @@
 // its forward/backward, the control block with the float64 temperature, staging of the host-drawn indices and
 // noise, metrics read-back, and the eager -> capture -> replay protocol of train().
 #pragma once
+#include <cstdlib>
+
 #include "agent.cuh"
 
 namespace rlrep {
@@ -20,6 +22,8 @@ class SacBase : public Agent {
   ~SacBase() override {
     for (cudaEvent_t e : events_) cudaEventDestroy(e);
     if (side_) cudaStreamDestroy(side_);
+    for (cudaStream_t a : aux_)
+      if (a) cudaStreamDestroy(a);
     if (metrics_host_) cudaFreeHost(metrics_host_);
     if (idx_host_) cudaFreeHost(idx_host_);
     if (eps_host_) cudaFreeHost(eps_host_);
@@ -118,7 +122,7 @@ class SacBase : public Agent {
     linear_fwd(gemm_, stream, 1, Mat{act_dev_, S_}, l0, ACT_ELU, act_h1_, AH_);
     linear_fwd(gemm_, stream, 1, Mat{act_h1_, AH_}, l1, ACT_ELU, act_h2_, AH_);
     linear_fwd(gemm_, stream, 1, Mat{act_h2_, AH_}, l2, ACT_NONE, act_head_, 2 * A_);
-    launch_actor_sample(act_head_, 1, A_, act_dev_ + S_, act_out_, A_, act_logp_, stream);
+    launch_actor_sample(act_head_, 2 * A_, 1, A_, act_dev_ + S_, act_out_, A_, act_logp_, stream);
     RLREP_CUDA(cudaMemcpyAsync(act_host_, act_out_, A_ * sizeof(float), cudaMemcpyDeviceToHost, stream));
     RLREP_CUDA(cudaStreamSynchronize(stream));
     std::memcpy(action_host, act_host_, A_ * sizeof(float));
@@ -145,12 +149,14 @@ class SacBase : public Agent {
     return events_[ev_next_++];
   }
   void fork() {
+    gemm_.set_sm_share(dual_share_);
     if (serial_) return;
     cudaEvent_t e = next_event();
     RLREP_CUDA(cudaEventRecord(e, stream));
     RLREP_CUDA(cudaStreamWaitEvent(side(), e, 0));
   }
   void join() {
+    gemm_.set_sm_share(1.0);
     if (serial_) return;
     cudaEvent_t e = next_event();
     RLREP_CUDA(cudaEventRecord(e, side()));
@@ -158,12 +164,36 @@ class SacBase : public Agent {
   }
   void begin_update() { ev_next_ = 0; }
 
+  // Finer-grained DAG edges for work that is off the critical path (weight / bias gradients run beside the dgrad
+  // chain that the next layer is waiting for): aux(i) are extra streams, mark() / wait_for() build the edges, and
+  // join_aux(i) folds an aux stream back into `to` (every forked stream must rejoin before the capture ends).
+  cudaStream_t aux(int i) {
+    if (serial_) return stream;
+    if (aux_[i] == nullptr) RLREP_CUDA(cudaStreamCreateWithFlags(&aux_[i], cudaStreamNonBlocking));
+    return aux_[i];
+  }
+  cudaEvent_t mark(cudaStream_t s) {
+    if (serial_) return nullptr;
+    cudaEvent_t e = next_event();
+    RLREP_CUDA(cudaEventRecord(e, s));
+    return e;
+  }
+  void wait_for(cudaStream_t s, cudaEvent_t e) {
+    if (serial_ || e == nullptr) return;
+    RLREP_CUDA(cudaStreamWaitEvent(s, e, 0));
+  }
+  void join_aux(int i, cudaStream_t to) {
+    if (serial_) return;
+    wait_for(to, mark(aux(i)));
+  }
+
   // Position i of the index array is a replay-ring row (range-checked against the ring); agents that also receive
   // other host-drawn integers (Diff-SR's noise levels) override this.
   virtual bool is_replay_index(int /*i*/) const { return true; }
 
   void plan_common(int n_idx, int n_eps, int ring_R, int batch_rows = 0) {
     R_ = ring_R;
+    LDH_ = round_up32(2 * A_);  // padded pitch of head_ / dhead_ (zero padding columns; weight rows are padded too)
     actor_g_.name = "actor";
     a0_ = add_linear(actor_g_, "actor.trunk.0", AH_, S_);  // agent/sac/actor.py:66-74
     a1_ = add_linear(actor_g_, "actor.trunk.2", AH_, AH_);
@@ -176,14 +206,14 @@ class SacBase : public Agent {
     arena_.want(&batch_, (size_t)(batch_rows > 0 ? batch_rows : B_) * R_);
     arena_.want(&ah1_, (size_t)B_ * AH_);
     arena_.want(&ah2_, (size_t)B_ * AH_);
-    arena_.want(&head_, (size_t)B_ * 2 * A_);
+    arena_.want(&head_, (size_t)B_ * round_up32(2 * A_));  // pitch LDH_: the head runs as an N = 32k tensor-core GEMM
     arena_.want(&action_, (size_t)B_ * A_);
     arena_.want(&logp_, B_);
-    LDH_ = round_up32(2 * A_);  // padded pitch: the head's wgrad reads dhead MN-major (zero padding columns)
     arena_.want(&dhead_, (size_t)B_ * LDH_);
     arena_.want(&dah2_, (size_t)B_ * AH_);
     arena_.want(&dah1_, (size_t)B_ * AH_);
-    arena_.want(&d_action_, (size_t)B_ * A_);
+    LDSA_ = round_up32(S_ + A_);
+    arena_.want(&dsa_, (size_t)B_ * LDSA_);
     arena_.want(&dlogp_, 4);
     arena_.want(&act_dev_, S_ + A_);
     arena_.want(&act_h1_, AH_);
@@ -213,8 +243,8 @@ class SacBase : public Agent {
     const Linear l0 = a0_.view(actor_g_), l1 = a1_.view(actor_g_), l2 = a2_.view(actor_g_);
     linear_fwd(gemm_, stream, B_, obs, l0, ACT_ELU, ah1_, AH_);
     linear_fwd(gemm_, stream, B_, Mat{ah1_, AH_}, l1, ACT_ELU, ah2_, AH_);
-    linear_fwd(gemm_, stream, B_, Mat{ah2_, AH_}, l2, ACT_NONE, head_, 2 * A_);
-    launch_actor_sample(head_, B_, A_, eps, action_out, A_, logp_out, stream);
+    linear_fwd(gemm_, stream, B_, Mat{ah2_, AH_}, l2, ACT_NONE, head_, LDH_);
+    launch_actor_sample(head_, LDH_, B_, A_, eps, action_out, A_, logp_out, stream);
   }
   // one launch for the three actor bias gradients (dY buffers of actor_backward are all still live)
   void actor_bias_grads() {
@@ -223,11 +253,26 @@ class SacBase : public Agent {
                             bias_job(B_, Mat{dah1_, AH_}, l0)};
     launch_colreduce_multi(jobs, 3, stream);
   }
-  // Needs d_action_ [B, A] and *dlogp_; the activations of the matching actor_forward(obs, eps, ...) must still be
+  // Where the first layer of a network fed with cat(obs, action) writes its input gradient so that actor_backward finds
+  // d(action) at dsa_[:, S:S+A].  On the tensor-core path the dgrad runs over ALL (padded) input columns -- N must be a
+  // multiple of 32 there and the few extra columns are free -- otherwise only over the action columns.
+  struct ActionGradDst {
+    float* dx;
+    int ld, col0, n_cols;
+  };
+  ActionGradDst action_grad_dst(const Linear& first) const {
+    if (cfg.precision == PREC_TF32 && first.ld == LDSA_ && B_ >= 64) return {dsa_, LDSA_, 0, LDSA_};
+    return {dsa_ + S_, LDSA_, S_, A_};
+  }
+  void dgrad_to_action(Mat dy, const Linear& first) {
+    const ActionGradDst d = action_grad_dst(first);
+    linear_dgrad(gemm_, stream, B_, dy, first, DACT_NONE, Mat(), d.dx, d.ld, d.col0, d.n_cols);
+  }
+  // Needs d(action) in dsa_[:, S:S+A] and *dlogp_; the activations of the matching actor_forward(obs, eps, ...) must still be
   // in ah1_/ah2_/head_.  Leaves the actor gradients in actor_g_.g.
   void actor_backward(Mat obs, const float* eps) {
     const Linear l0 = a0_.view(actor_g_), l1 = a1_.view(actor_g_), l2 = a2_.view(actor_g_);
-    launch_actor_sample_bwd(head_, B_, A_, eps, d_action_, A_, dlogp_, dhead_, LDH_, stream);
+    launch_actor_sample_bwd(head_, LDH_, B_, A_, eps, dsa_ + S_, LDSA_, dlogp_, dhead_, LDH_, stream);
     linear_wgrad(gemm_, stream, B_, Mat{dhead_, LDH_}, Mat{ah2_, AH_}, l2, Mat(), 0, false);
     linear_dgrad(gemm_, stream, B_, Mat{dhead_, LDH_}, l2, DACT_ELU_OUT, Mat{ah2_, AH_}, dah2_, AH_);
     linear_wgrad(gemm_, stream, B_, Mat{dah2_, AH_}, Mat{ah1_, AH_}, l1, Mat(), 0, false);
@@ -251,11 +296,24 @@ class SacBase : public Agent {
     return t;
   }
 
-  int S_ = 0, A_ = 0, B_ = 0, AH_ = 0, R_ = 0, LDH_ = 0;
+  int S_ = 0, A_ = 0, B_ = 0, AH_ = 0, R_ = 0, LDH_ = 0, LDSA_ = 0;
   cudaStream_t side_ = nullptr;
+  cudaStream_t aux_[2] = {nullptr, nullptr};
+  double aux_share_ = [] {
+    const char* e = std::getenv("RLREP_AUX_SHARE");
+    return e ? std::atof(e) : 0.25;
+  }();
+  bool use_aux_ = [] {
+    const char* e = std::getenv("RLREP_USE_AUX");
+    return e ? std::atoi(e) != 0 : true;
+  }();
   std::vector<cudaEvent_t> events_;
   size_t ev_next_ = 0;
   bool serial_ = false;
+  double dual_share_ = [] {
+    const char* e = std::getenv("RLREP_DUAL_SHARE");
+    return e ? std::atof(e) : 0.5;
+  }();
   DeviceArena arena_;
   GemmRunner gemm_;
   GraphReplay graph_;
@@ -268,7 +326,7 @@ class SacBase : public Agent {
   float *eps_dev_ = nullptr, *eps_host_ = nullptr;
   float* batch_ = nullptr;
   float *ah1_ = nullptr, *ah2_ = nullptr, *head_ = nullptr, *action_ = nullptr, *logp_ = nullptr;
-  float *dhead_ = nullptr, *dah2_ = nullptr, *dah1_ = nullptr, *d_action_ = nullptr, *dlogp_ = nullptr;
+  float *dhead_ = nullptr, *dah2_ = nullptr, *dah1_ = nullptr, *dsa_ = nullptr, *dlogp_ = nullptr;
   float *act_dev_ = nullptr, *act_h1_ = nullptr, *act_h2_ = nullptr, *act_head_ = nullptr, *act_out_ = nullptr,
         *act_logp_ = nullptr, *act_host_ = nullptr;
 };

@@ -165,16 +165,26 @@ class CtrlSacAgent final : public SacBase {
       a.epi.r1_u = drp_; a.epi.r1_v = th.W;
       gemm_.run(a, s0);
     }
-    linear_wgrad(gemm_, s0, B_, Mat{dzphi_, D_}, Mat{h2_, H_}, l3, Mat(), 0, false);
+    // the dgrad chain is the critical path; weight / bias gradients trail it on an aux stream
+    cudaStream_t w0 = use_aux_ ? aux(0) : s0, w1 = use_aux_ ? aux(1) : s1;
+    const double share = dual_share_, wshare = use_aux_ ? aux_share_ : dual_share_;
+    wait_for(w0, mark(s0));
+    gemm_.set_sm_share(wshare);
+    linear_wgrad(gemm_, w0, B_, Mat{dzphi_, D_}, Mat{h2_, H_}, l3, Mat(), 0, false);
+    gemm_.set_sm_share(share);
     linear_dgrad(gemm_, s0, B_, Mat{dzphi_, D_}, l3, DACT_ELU_OUT, Mat{h2_, H_}, dh2_, H_);
-    linear_wgrad(gemm_, s0, B_, Mat{dh2_, H_}, Mat{h1_, H_}, l2, Mat(), 0, false);
+    wait_for(w0, mark(s0));
+    gemm_.set_sm_share(wshare);
+    linear_wgrad(gemm_, w0, B_, Mat{dh2_, H_}, Mat{h1_, H_}, l2, Mat(), 0, false);
+    gemm_.set_sm_share(share);
     linear_dgrad(gemm_, s0, B_, Mat{dh2_, H_}, l2, DACT_ELU_OUT, Mat{h1_, H_}, dh1_, H_);
     linear_wgrad(gemm_, s0, B_, Mat{dh1_, H_}, sa(), l1, Mat(), 0, false);
+    wait_for(w0, mark(s0));
     {
       ColJob jobs[5] = {bias_job(B_, Mat{dzphi_, D_}, l3), bias_job(B_, Mat{dh2_, H_}, l2),
                         bias_job(B_, Mat{dh1_, H_}, l1), ColJob{zphi_, drp_, th.dW, D_, B_, D_},  // d theta.w
                         ColJob{drp_, nullptr, th.db, 1, B_, 1}};                                  // d theta.b
-      launch_colreduce_multi(jobs, 5, s0);
+      launch_colreduce_multi(jobs, 5, w0);
     }
     {  // d (pre-tanh mu) = (G^T phi) * (1 - mu^2)
       GemmArgs a;
@@ -185,15 +195,26 @@ class CtrlSacAgent final : public SacBase {
       a.epi.dact = DACT_TANH_OUT; a.epi.aux = zmu_; a.epi.ld_aux = D_;
       gemm_.run(a, s1);
     }
-    linear_wgrad(gemm_, s1, B_, Mat{dzmu_, D_}, Mat{g2_, H_}, n3, Mat(), 0, false);
+    wait_for(w1, mark(s1));
+    gemm_.set_sm_share(wshare);
+    linear_wgrad(gemm_, w1, B_, Mat{dzmu_, D_}, Mat{g2_, H_}, n3, Mat(), 0, false);
+    gemm_.set_sm_share(share);
     linear_dgrad(gemm_, s1, B_, Mat{dzmu_, D_}, n3, DACT_ELU_OUT, Mat{g2_, H_}, dg2_, H_);
-    linear_wgrad(gemm_, s1, B_, Mat{dg2_, H_}, Mat{g1_, H_}, n2, Mat(), 0, false);
+    wait_for(w1, mark(s1));
+    gemm_.set_sm_share(wshare);
+    linear_wgrad(gemm_, w1, B_, Mat{dg2_, H_}, Mat{g1_, H_}, n2, Mat(), 0, false);
+    gemm_.set_sm_share(share);
     linear_dgrad(gemm_, s1, B_, Mat{dg2_, H_}, n2, DACT_ELU_OUT, Mat{g1_, H_}, dg1_, H_);
     linear_wgrad(gemm_, s1, B_, Mat{dg1_, H_}, s2(), n1, Mat(), 0, false);
+    wait_for(w1, mark(s1));
     {
       ColJob jobs[3] = {bias_job(B_, Mat{dzmu_, D_}, n3), bias_job(B_, Mat{dg2_, H_}, n2),
                         bias_job(B_, Mat{dg1_, H_}, n1)};
-      launch_colreduce_multi(jobs, 3, s1);
+      launch_colreduce_multi(jobs, 3, w1);
+    }
+    if (use_aux_) {
+      join_aux(0, s0);
+      join_aux(1, s0);
     }
     join();
     // ---- one fused Adam over phi | mu | theta, plus Polyak of phi_target (:242-244, :253-255)
@@ -206,8 +227,7 @@ class CtrlSacAgent final : public SacBase {
   void critic_forward(cudaStream_t s, const float* z, bool target, float* hid, float* q1, float* q2) {
     const Linear l14 = c14_.view(crit_g_, target), l2 = c2_.view(crit_g_, target), l5 = c5_.view(crit_g_, target);
     linear_fwd(gemm_, s, B_, Mat{z, D_}, l14, ACT_ELU, hid, 2 * H_);
-    launch_rowdot(hid, 2 * H_, B_, H_, l2.W, l2.b, q1, s);
-    launch_rowdot(hid + H_, 2 * H_, B_, H_, l5.W, l5.b, q2, s);
+    launch_rowdot_pair(RowDotJob{hid, l2.W, l2.b, q1, 2 * H_, H_}, RowDotJob{hid + H_, l5.W, l5.b, q2, 2 * H_, H_}, B_, s);
   }
   // d hid from (dq1, dq2) through the N = 1 heads and the ELU
   void critic_heads_backward_to_hidden() {
@@ -261,7 +281,7 @@ class CtrlSacAgent final : public SacBase {
     linear_dgrad(gemm_, stream, B_, Mat{dhid_, 2 * H_}, l14, DACT_NONE, Mat(), dzphi_, D_);
     linear_dgrad(gemm_, stream, B_, Mat{dzphi_, D_}, l3, DACT_ELU_OUT, Mat{h2_, H_}, dh2_, H_);
     linear_dgrad(gemm_, stream, B_, Mat{dh2_, H_}, l2, DACT_ELU_OUT, Mat{h1_, H_}, dh1_, H_);
-    linear_dgrad(gemm_, stream, B_, Mat{dh1_, H_}, l1, DACT_NONE, Mat(), d_action_, A_, /*col0=*/S_, /*n_cols=*/A_);
+    dgrad_to_action(Mat{dh1_, H_}, l1);
     actor_backward(s, eps);
     actor_adam();
   }

@@ -156,8 +156,9 @@ class DiffSrSacAgent final : public SacBase {
     launch_actor_alpha_loss(critic_.q[0], critic_.q[0] + B_, logp_, B_, (float)(-A_), cfg.learn_alpha, ctl, dq_,
                             dq_ + B_, dlogp_, metrics_dev_ + 5, stream);
     critic_.backward(gemm_, stream, crit_g_, 0, zphi_, dq_, /*wgrad=*/false, dzphi_);
-    trunk_backward(gemm_, stream, B_, phi_, feat_g_, false, Mat{dzphi_, D_}, s, phi_acts_, false, nullptr, d_action_, A_,
-                   S_, A_);
+    const ActionGradDst ad = action_grad_dst(phi_.l[0].view(feat_g_));
+    trunk_backward(gemm_, stream, B_, phi_, feat_g_, false, Mat{dzphi_, D_}, s, phi_acts_, false, nullptr, ad.dx, ad.ld,
+                   ad.col0, ad.n_cols);
     actor_backward(s, eps);
     actor_adam();
     // update_target (sac_agent.py:99-102) still runs on the never-trained critic: tau*x + (1-tau)*x != x in fp32

@@ -126,7 +126,7 @@ class SacAgent final : public SacBase {
     launch_actor_alpha_loss(q1_, q2_, logp_, B_, (float)(-A_), cfg.learn_alpha, ctl, dq1_, dq2_, dlogp_,
                             metrics_dev_ + 4, stream);
     critic_backward_to_hid0(false);
-    linear_dgrad(gemm_, stream, B_, Mat{dhid0_, 2 * H_}, c0_.view(crit_g_), DACT_NONE, Mat(), d_action_, A_, S_, A_);
+    dgrad_to_action(Mat{dhid0_, 2 * H_}, c0_.view(crit_g_));
     actor_backward(s, eps);
     actor_adam();
   }

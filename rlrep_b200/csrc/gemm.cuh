@@ -42,13 +42,15 @@ struct TcGemmPlan {
   int bn = 0;
   int split_k = 1;
   int kb_per_split = 0;
-  float* ws = nullptr;  // split-K partials [split_k, M, N]
+  int stages = 0;       // TMA ring depth (shallow for short K-slices so two CTAs share an SM)
+  float* ws = nullptr;  // unused (split-K reduces over DSMEM); kept for ABI stability of rlrep_gemm
 };
 
 // True when the operands satisfy TMA's constraints (16-byte aligned base, ld % 4 == 0, no A2 segment).
 bool tc_eligible(const GemmArgs& a);
-// bn / split_k = 0 picks them automatically (fill ~148 SMs). ws may be null (forces split_k = 1).
-TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* ws, size_t ws_floats);
+// bn / split_k = 0 picks them automatically from a cost model whose wave count comes from the occupancy API.
+// sm_share in (0, 1]: fraction of the GPU this GEMM may count on (0.5 when two kernel chains run on two streams).
+TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* ws, size_t ws_floats, double sm_share = 1.0);
 void launch_tc(const TcGemmPlan& p, cudaStream_t stream);
 // Debug builds (-DRLREP_GEMM_TRACE): %globaltimer stamps of CTA (0,0,0) of the last tcgen05 GEMM.
 void read_gemm_trace(unsigned long long* out16);

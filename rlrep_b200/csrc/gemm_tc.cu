@@ -1,7 +1,11 @@
 // Host side of the tcgen05 TF32 GEMM (see gemm_tc_kernel.cuh for the kernel): tensor-map construction, the tile /
 // split-K cost model and the dispatch to the per-variant launchers.
+#include <algorithm>
+#include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <mutex>
+#include <unordered_map>
 
 #include "common.cuh"
 #include "gemm.cuh"
@@ -66,18 +70,56 @@ CUtensorMap make_map_mnmajor(const float* base, int K, int mn, int ld, int tile_
   return m;
 }
 
+int max_clusters(int bn, bool a_mn, bool b_mn, int s, int stages) {
+  static std::mutex mu;
+  static std::unordered_map<int, int> cache;
+  const int key = (bn << 12) | (a_mn << 11) | (b_mn << 10) | (s << 5) | stages;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  int n = 0;
+  switch (bn) {
+    case 32: n = a_mn ? tc::max_clusters_32_1(b_mn, s, stages) : tc::max_clusters_32_0(b_mn, s, stages); break;
+    case 64: n = a_mn ? tc::max_clusters_64_1(b_mn, s, stages) : tc::max_clusters_64_0(b_mn, s, stages); break;
+    case 128: n = a_mn ? tc::max_clusters_128_1(b_mn, s, stages) : tc::max_clusters_128_0(b_mn, s, stages); break;
+    default: n = a_mn ? tc::max_clusters_256_1(b_mn, s, stages) : tc::max_clusters_256_0(b_mn, s, stages); break;
+  }
+  cache[key] = n;
+  return n;
+}
+
+// Ring depth.  A short K-slice is one burst of loads: a ring that fits twice into an SM (2 x ~113 KB) lets two CTAs
+// -- of this GEMM or of one running concurrently on another stream -- share the SM; long slices get the deepest ring.
+int pick_stages(int bn, int kb_per) {
+  static const int shallow_on = [] {
+    const char* e = std::getenv("RLREP_TC_SHALLOW");
+    return e ? std::atoi(e) : 1;
+  }();
+  const int deepest = tc::num_stages(bn), fewest = tc::min_stages(bn);
+  const int shallow = (113 * 1024 - 1280) / tc::stage_bytes(bn);
+  if (!shallow_on || shallow < fewest || kb_per > 2 * shallow) return deepest;
+  return std::max(fewest, std::min(shallow, kb_per));
+}
+
 // Cost model (cycles through one SM) used to pick the tile width and the split-K cluster size: operand bytes from
-// L2 at ~64 B/clk, the cluster reduction over DSMEM at ~20 B/clk, stores at ~32 B/clk, times the number of waves.
-double plan_cost(int M, int N, int nkb, int bn, int s, int* kb_per_out) {
+// L2 at ~48 B/clk, the cluster reduction over DSMEM at ~16 B/clk, stores at ~32 B/clk and a fixed per-CTA cost that
+// grows with the cluster size, times the number of waves.  The wave count uses the occupancy API's answer for how
+// many clusters of this shape the GPU holds at once (8-CTA clusters must fit in a GPC: far fewer than 148 / 8), scaled
+// by the share of the GPU the caller expects to have.
+double plan_cost(const GemmArgs& a, int nkb, int bn, int s, double sm_share, int* kb_per_out, int* stages_out) {
   const int kb_per = ceil_div(nkb, s);
+  const int stages = pick_stages(bn, kb_per);
   *kb_per_out = kb_per;
-  const int ctas = ceil_div(M, BM) * ceil_div(N, bn) * s;
-  const int waves = ceil_div(ctas, kNumSMs);
-  const double load = (double)(BM + bn) * BK * 4 * kb_per / 64.0;
+  *stages_out = stages;
+  const int clusters = ceil_div(a.M, BM) * ceil_div(a.N, bn);
+  const double cap = std::max(1.0, max_clusters(bn, a.a_mn, a.b_mn, s, stages) * sm_share);
+  const double waves = std::ceil(clusters / cap);
+  const double load = (double)(BM + bn) * BK * 4 * kb_per / 48.0;
   const double tile = (double)BM * bn * 4;
-  const double reduce = s > 1 ? tile / 20.0 : 0.0;
+  const double reduce = s > 1 ? tile / 16.0 : 0.0;
   const double store = tile / s / 32.0;
-  return waves * (load + reduce + store + 1500.0);  // 1500: per-CTA fixed cost (barrier init, TMEM alloc, drain)
+  const double fixed = 1500.0 + (s == 2 ? 300.0 : s == 4 ? 600.0 : s == 8 ? 900.0 : 0.0);
+  return waves * (load + reduce + store + fixed);
 }
 
 }  // namespace
@@ -96,7 +138,7 @@ bool tc_eligible(const GemmArgs& a) {
   return a.A2 == nullptr && ok(a.A, a.lda) && ok(a.B, a.ldb) && a.M > 0 && a.N > 0 && a.K > 0;
 }
 
-TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* /*ws*/, size_t /*ws_floats*/) {
+TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* /*ws*/, size_t /*ws_floats*/, double sm_share) {
   RLREP_CHECK(tc_eligible(a), "operands violate TMA alignment (16-byte base, ld % 4 == 0)");
   RLREP_CHECK(bn == 0 || bn == 32 || bn == 64 || bn == 128 || bn == 256, "bn must be 32/64/128/256");
   RLREP_CHECK(split_k == 0 || split_k == 1 || split_k == 2 || split_k == 4 || split_k == 8,
@@ -110,14 +152,15 @@ TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* /*ws*/, s
     if (bn == 0 && cand_bn > 32 && cand_bn / 2 >= a.N) continue;  // tile mostly out of bounds
     for (int s : {1, 2, 4, 8}) {
       if (split_k != 0 && s != split_k) continue;
-      int kb_per = 0;
-      const double c = plan_cost(a.M, a.N, nkb, cand_bn, s, &kb_per);
-      if (s > 1 && (s - 1) * kb_per >= nkb) continue;  // would leave an empty split
+      int kb_per = 0, stages = 0;
+      if (s > 1 && (s - 1) * ceil_div(nkb, s) >= nkb) continue;  // would leave an empty split
+      const double c = plan_cost(a, nkb, cand_bn, s, sm_share, &kb_per, &stages);
       if (c < best) {
         best = c;
         p.bn = cand_bn;
         p.split_k = s;
         p.kb_per_split = kb_per;
+        p.stages = stages;
       }
     }
   }
@@ -125,6 +168,7 @@ TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* /*ws*/, s
     p.bn = bn ? bn : 32;
     p.split_k = 1;
     p.kb_per_split = nkb;
+    p.stages = pick_stages(p.bn, nkb);
   }
   // K-major operand: matrix [rows = M|N, cols = K]; MN-major: matrix [rows = K, cols = M|N].
   p.tmA = a.a_mn ? make_map_mnmajor(a.A, a.K, a.M, a.lda, BM) : make_map_kmajor(a.A, a.M, a.K, a.lda, BM);

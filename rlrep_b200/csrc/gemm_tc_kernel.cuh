@@ -45,10 +45,15 @@ __host__ __device__ constexpr int stage_bytes(int bn) { return (BM + bn) * BK * 
 __host__ __device__ constexpr int num_stages(int bn) {
   return kSmemBudget / stage_bytes(bn) > 8 ? 8 : kSmemBudget / stage_bytes(bn);
 }
-__host__ __device__ constexpr int smem_bytes(int bn) { return num_stages(bn) * stage_bytes(bn) + 1024 + 256; }
+__host__ __device__ constexpr int smem_bytes(int bn, int stages) { return stages * stage_bytes(bn) + 1024 + 256; }
+__host__ __device__ constexpr int smem_bytes(int bn) { return smem_bytes(bn, num_stages(bn)); }
+// Fewest stages whose ring still holds the fp32 staging tile [BM, bn + 4] of the store phase.
+__host__ __device__ constexpr int min_stages(int bn) { return (BM * (bn + 4) * 4 + stage_bytes(bn) - 1) / stage_bytes(bn); }
 
 // One launcher per (BN, A-major) pair, each defined in its own translation unit (gemm_tc_inst_*.cu).
-#define RLREP_TC_DECL(BN, AMN) void launch_tc_##BN##_##AMN(const TcGemmPlan& p, cudaStream_t stream);
+#define RLREP_TC_DECL(BN, AMN)                                           \
+  void launch_tc_##BN##_##AMN(const TcGemmPlan& p, cudaStream_t stream); \
+  int max_clusters_##BN##_##AMN(bool b_mn, int split_k, int stages);
 RLREP_TC_DECL(32, 0) RLREP_TC_DECL(32, 1) RLREP_TC_DECL(64, 0) RLREP_TC_DECL(64, 1)
 RLREP_TC_DECL(128, 0) RLREP_TC_DECL(128, 1) RLREP_TC_DECL(256, 0) RLREP_TC_DECL(256, 1)
 #undef RLREP_TC_DECL
@@ -248,14 +253,17 @@ __device__ __forceinline__ bool store_tile(const TileStore& t, const Epilogue* e
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 float* __restrict__ C, int ldc, int M, int N, int K, int kb_per_split, const Epilogue epi) {
-  constexpr int STAGES = num_stages(BN);
+                 float* __restrict__ C, int ldc, int M, int N, int K, int kb_per_split, int stages,
+                 const Epilogue epi) {
+  // `stages` is a launch parameter: short K-slices run with a shallow ring so that two CTAs (of this or of a
+  // concurrent GEMM on another stream) fit on one SM; long ones get the deepest ring that fits.
+  const int STAGES = stages;
   constexpr int A_BYTES = BM * BK * 4;
   constexpr int B_BYTES = BN * BK * 4;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
   constexpr int LDS = BN + 4;  // staging row pitch in floats: 16-byte aligned rows, conflict-free float4 access
   static_assert(BN == 32 || BN == 64 || BN == 128 || BN == 256, "BN must be a power of two in [32,256]");
-  static_assert(BM * LDS * 4 <= STAGES * (A_BYTES + B_BYTES), "staging tile must fit in the pipeline buffers");
+  static_assert(min_stages(BN) <= num_stages(BN), "staging tile must fit in the pipeline buffers");
 
   extern __shared__ uint8_t smem_raw[];
   // SWIZZLE_128B atoms must sit on 1024-byte boundaries.
@@ -263,8 +271,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* sA = smem;
   uint8_t* sB = smem + STAGES * A_BYTES;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* accum_bar = empty_bar + STAGES;
+  uint64_t* empty_bar = full_bar + 8;  // barrier slots are laid out for the maximum ring depth
+  uint64_t* accum_bar = empty_bar + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
   float* stage = reinterpret_cast<float*>(smem);  // reuses the operand ring once the accumulator is complete
 
@@ -400,30 +408,55 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 template <int BN, bool A_MN, bool B_MN>
-void launch_variant(const TcGemmPlan& p, cudaStream_t stream) {
+void fill_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, dim3 grid, int split_k, int stages,
+                        cudaStream_t stream) {
   auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
     RLREP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(BN)));
     attr_set = true;
   }
-  const GemmArgs& a = p.args;
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(ceil_div(a.N, BN), ceil_div(a.M, BM), p.split_k);
+  cfg = {};
+  cfg.gridDim = grid;
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = smem_bytes(BN);
+  cfg.dynamicSmemBytes = smem_bytes(BN, stages);
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1;
   attr[0].val.clusterDim.y = 1;
-  attr[0].val.clusterDim.z = p.split_k;
+  attr[0].val.clusterDim.z = split_k;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  RLREP_CUDA(cudaLaunchKernelEx(&cfg, kern, p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, a.K, p.kb_per_split, a.epi));
+}
+
+template <int BN, bool A_MN, bool B_MN>
+void launch_variant(const TcGemmPlan& p, cudaStream_t stream) {
+  const GemmArgs& a = p.args;
+  RLREP_CHECK(p.stages >= min_stages(BN) && p.stages <= num_stages(BN), "bad pipeline depth");
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[2];
+  fill_launch_config<BN, A_MN, B_MN>(cfg, attr, dim3(ceil_div(a.N, BN), ceil_div(a.M, BM), p.split_k), p.split_k,
+                                     p.stages, stream);
+  RLREP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, A_MN, B_MN>, p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, a.K,
+                                p.kb_per_split, p.stages, a.epi));
   g_trace_reader = &read_trace_here;
   RLREP_LAUNCHED_W("gemm_tf32", stream, 4.0 * ((double)a.M * a.K + (double)a.N * a.K + (double)a.M * a.N),
                    2.0 * a.M * a.N * a.K);
+}
+
+// How many clusters of `split_k` CTAs of this variant the GPU can hold at once (occupancy API; clusters must fit in
+// one GPC, so this is NOT 148 / split_k) -- the denominator of the cost model's wave count.
+template <int BN, bool A_MN, bool B_MN>
+int max_clusters_variant(int split_k, int stages) {
+  cudaLaunchConfig_t cfg;
+  cudaLaunchAttribute attr[2];
+  fill_launch_config<BN, A_MN, B_MN>(cfg, attr, dim3(1, 1, split_k), split_k, stages, nullptr);
+  int n = 0;
+  if (cudaOccupancyMaxActiveClusters(&n, gemm_tf32_kernel<BN, A_MN, B_MN>, &cfg) != cudaSuccess || n <= 0) {
+    cudaGetLastError();
+    n = kNumSMs / split_k;
+  }
+  return n;
 }
 
 }  // namespace
@@ -432,6 +465,10 @@ void launch_variant(const TcGemmPlan& p, cudaStream_t stream) {
   void launch_tc_##BN##_##AMN(const TcGemmPlan& p, cudaStream_t stream) {     \
     if (p.args.b_mn) launch_variant<BN, (AMN) != 0, true>(p, stream);         \
     else launch_variant<BN, (AMN) != 0, false>(p, stream);                    \
+  }                                                                           \
+  int max_clusters_##BN##_##AMN(bool b_mn, int split_k, int stages) {         \
+    return b_mn ? max_clusters_variant<BN, (AMN) != 0, true>(split_k, stages) \
+                : max_clusters_variant<BN, (AMN) != 0, false>(split_k, stages); \
   }
 #endif  // RLREP_TC_DEVICE_CODE
 

@@ -83,15 +83,35 @@ __global__ void __launch_bounds__(256) ce_rows_kernel(float* __restrict__ logits
 }
 
 // ------------------------------------------------------------------------------------------- N = 1 heads
-__global__ void rowdot_kernel(const float* __restrict__ X, int ld, int rows, int D, const float* __restrict__ w,
-                              const float* __restrict__ b, float* __restrict__ y) {
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (warp >= rows) return;
-  const float* x = X + (size_t)warp * ld;
+// One 128-thread CTA per (row, job): 256 rows spread over 256+ CTAs, every thread has its few 128-bit loads in flight
+// at once, then a fixed-order block reduction.  Two jobs (the twin Q heads) share one launch through blockIdx.y.
+struct RowDotJobs {
+  RowDotJob j[2];
+};
+__global__ void __launch_bounds__(128) rowdot_kernel(const RowDotJobs jobs, int rows) {
+  __shared__ float scratch[33];
+  const RowDotJob& jb = jobs.j[blockIdx.y];
+  const int row = blockIdx.x;
+  const float* x = jb.X + (size_t)row * jb.ld;
+  const float* w = jb.w;
+  const int D = jb.D;
   float acc = 0.f;
-  for (int j = lane; j < D; j += 32) acc = fmaf(x[j], __ldg(w + j), acc);
-  acc = warp_sum(acc);
-  if (lane == 0) y[warp] = acc + (b ? __ldg(b) : 0.f);
+  if (((jb.ld | D) & 3) == 0 && ((reinterpret_cast<uintptr_t>(jb.X) | reinterpret_cast<uintptr_t>(w)) & 15) == 0) {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (int j = threadIdx.x; j < D / 4; j += 128) {
+      const float4 xv = x4[j];
+      const float4 wv = __ldg(w4 + j);
+      a0 = fmaf(xv.x, wv.x, a0); a1 = fmaf(xv.y, wv.y, a1); a2 = fmaf(xv.z, wv.z, a2); a3 = fmaf(xv.w, wv.w, a3);
+    }
+    acc = (a0 + a1) + (a2 + a3);
+  } else {
+    for (int j = threadIdx.x; j < D; j += 128) acc = fmaf(x[j], __ldg(w + j), acc);
+  }
+  acc = block_sum<128>(acc, scratch);
+  if (threadIdx.x == 0) jb.y[row] = acc + (jb.b ? __ldg(jb.b) : 0.f);
 }
 
 // 32 columns x 8 row-slices per CTA; fixed-order smem reduction across the slices.
@@ -121,8 +141,10 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const float* __restrict_
 struct ColJobs {
   ColJob j[kMaxColJobs];
 };
-__global__ void __launch_bounds__(256) colreduce_multi_kernel(const ColJobs jobs) {
-  __shared__ float part[8][33];
+// 32 columns x 32 row-slices per 1024-thread CTA: at B = 256 every thread issues its 8 loads back to back (one
+// memory round trip for the whole reduction instead of 32 dependent-latency steps), then a fixed-order smem tree.
+__global__ void __launch_bounds__(1024) colreduce_multi_kernel(const ColJobs jobs) {
+  __shared__ float part[32][33];
   const ColJob& jb = jobs.j[blockIdx.y];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + tx;
@@ -130,8 +152,22 @@ __global__ void __launch_bounds__(256) colreduce_multi_kernel(const ColJobs jobs
   float acc = 0.f;
   if (j < jb.cols) {
     const float* x = jb.X + j;
-#pragma unroll 4
-    for (int i = ty; i < jb.rows; i += 8) {
+    int i = ty;
+    for (; i + 7 * 32 < jb.rows; i += 8 * 32) {
+      float v[8], w[8];
+#pragma unroll
+      for (int q = 0; q < 8; ++q) v[q] = x[(size_t)(i + q * 32) * jb.ld];
+      if (jb.u) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) w[q] = __ldg(jb.u + i + q * 32);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc = fmaf(w[q], v[q], acc);
+      } else {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) acc += v[q];
+      }
+    }
+    for (; i < jb.rows; i += 32) {
       const float v = x[(size_t)i * jb.ld];
       acc = jb.u ? fmaf(__ldg(jb.u + i), v, acc) : acc + v;
     }
@@ -141,7 +177,7 @@ __global__ void __launch_bounds__(256) colreduce_multi_kernel(const ColJobs jobs
   if (ty == 0 && j < jb.cols) {
     float t = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += part[k][tx];
+    for (int k = 0; k < 32; ++k) t += part[k][tx];
     jb.out[j] = t;
   }
 }
@@ -186,11 +222,12 @@ __global__ void __launch_bounds__(256) feature_loss_finalize_kernel(const float*
 // ------------------------------------------------------------------------------------------- actor
 constexpr float kLogStdMin = -5.f, kLogStdMax = 2.f;  // sac_agent.py:64
 
-__global__ void actor_sample_kernel(const float* __restrict__ head, int B, int A, const float* __restrict__ eps,
-                                    float* __restrict__ action, int lda, float* __restrict__ logp) {
+__global__ void actor_sample_kernel(const float* __restrict__ head, int ld_head, int B, int A,
+                                    const float* __restrict__ eps, float* __restrict__ action, int lda,
+                                    float* __restrict__ logp) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  const float* h = head + (size_t)b * 2 * A;
+  const float* h = head + (size_t)b * ld_head;
   float lp = 0.f;
   for (int j = 0; j < A; ++j) {
     const float mu = h[j];
@@ -210,13 +247,13 @@ __global__ void actor_sample_kernel(const float* __restrict__ head, int B, int A
   logp[b] = lp;
 }
 
-__global__ void actor_sample_bwd_kernel(const float* __restrict__ head, int B, int A, const float* __restrict__ eps,
-                                        const float* __restrict__ d_action, int ldd,
+__global__ void actor_sample_bwd_kernel(const float* __restrict__ head, int ld_head, int B, int A,
+                                        const float* __restrict__ eps, const float* __restrict__ d_action, int ldd,
                                         const float* __restrict__ dlogp_scalar, float* __restrict__ dhead, int ld_dh) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * A) return;
   const int b = i / A, j = i - b * A;
-  const float* h = head + (size_t)b * 2 * A;
+  const float* h = head + (size_t)b * ld_head;
   const float glp = *dlogp_scalar;
   const float mu = h[j];
   const float t = tanhf(h[A + j]);
@@ -329,23 +366,26 @@ __global__ void __launch_bounds__(256) adam_polyak_kernel(float4* __restrict__ p
   const bool do_polyak = target != nullptr && (polyak_flag == nullptr || *polyak_flag != 0);
   const float omt = 1.f - tau;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
-    float4 pv = p[i], mv = m[i], vv = v[i];
-    const float4 gv = g[i];
+    // m, v, g and the Polyak target are touched once per optimiser step: stream them through L2 (evict-first) so the
+    // weights p -- which every GEMM until the next step re-reads -- stay L2-resident instead of being flushed by the
+    // optimiser's own 200 MB sweep.
+    float4 pv = p[i], mv = __ldcs(m + i), vv = __ldcs(v + i);
+    const float4 gv = __ldcs(g + i);
     adam_elem(pv.x, gv.x, mv.x, vv.x, ss, bc2s);
     adam_elem(pv.y, gv.y, mv.y, vv.y, ss, bc2s);
     adam_elem(pv.z, gv.z, mv.z, vv.z, ss, bc2s);
     adam_elem(pv.w, gv.w, mv.w, vv.w, ss, bc2s);
     p[i] = pv;
-    m[i] = mv;
-    v[i] = vv;
+    __stcs(m + i, mv);
+    __stcs(v + i, vv);
     if (do_polyak && i < n4_polyak) {
-      float4 t = target[i];
+      float4 t = __ldcs(target + i);
       // tau * param + (1 - tau) * target, each op rounded separately (no FMA) like the reference's tensor ops
       t.x = __fadd_rn(__fmul_rn(tau, pv.x), __fmul_rn(omt, t.x));
       t.y = __fadd_rn(__fmul_rn(tau, pv.y), __fmul_rn(omt, t.y));
       t.z = __fadd_rn(__fmul_rn(tau, pv.z), __fmul_rn(omt, t.z));
       t.w = __fadd_rn(__fmul_rn(tau, pv.w), __fmul_rn(omt, t.w));
-      target[i] = t;
+      __stcs(target + i, t);
     }
   }
 }
@@ -576,7 +616,17 @@ void launch_ce_rows(float* logits, int ld, int rows, int cols, int diag_off, flo
 }
 
 void launch_rowdot(const float* X, int ld, int rows, int D, const float* w, const float* b, float* y, cudaStream_t s) {
-  rowdot_kernel<<<ceil_div(rows * 32, 256), 256, 0, s>>>(X, ld, rows, D, w, b, y);
+  RowDotJobs js;
+  js.j[0] = RowDotJob{X, w, b, y, ld, D};
+  js.j[1] = js.j[0];
+  rowdot_kernel<<<dim3(rows, 1), 128, 0, s>>>(js, rows);
+  RLREP_LAUNCHED("rowdot", s);
+}
+void launch_rowdot_pair(const RowDotJob& a, const RowDotJob& b, int rows, cudaStream_t s) {
+  RowDotJobs js;
+  js.j[0] = a;
+  js.j[1] = b;
+  rowdot_kernel<<<dim3(rows, 2), 128, 0, s>>>(js, rows);
   RLREP_LAUNCHED("rowdot", s);
 }
 
@@ -594,7 +644,7 @@ void launch_colreduce_multi(const ColJob* jobs, int n_jobs, cudaStream_t s) {
     js.j[i] = jobs[i];
     if (jobs[i].cols > max_cols) max_cols = jobs[i].cols;
   }
-  colreduce_multi_kernel<<<dim3(ceil_div(max_cols, 32), n_jobs), 256, 0, s>>>(js);
+  colreduce_multi_kernel<<<dim3(ceil_div(max_cols, 32), n_jobs), 1024, 0, s>>>(js);
   RLREP_LAUNCHED("colreduce_multi", s);
 }
 
@@ -611,16 +661,16 @@ void launch_feature_loss_finalize(const float* loss_rows, int rows, const float*
   RLREP_LAUNCHED("feature_loss_finalize", s);
 }
 
-void launch_actor_sample(const float* head, int B, int A, const float* eps, float* action, int lda, float* logp,
-                         cudaStream_t s) {
-  actor_sample_kernel<<<ceil_div(B, 128), 128, 0, s>>>(head, B, A, eps, action, lda, logp);
+void launch_actor_sample(const float* head, int ld_head, int B, int A, const float* eps, float* action, int lda,
+                         float* logp, cudaStream_t s) {
+  actor_sample_kernel<<<ceil_div(B, 32), 32, 0, s>>>(head, ld_head, B, A, eps, action, lda, logp);
   RLREP_LAUNCHED("actor_sample", s);
 }
 
-void launch_actor_sample_bwd(const float* head, int B, int A, const float* eps, const float* d_action, int ldd,
-                             const float* dlogp_scalar, float* dhead, int ld_dhead, cudaStream_t s) {
-  actor_sample_bwd_kernel<<<ceil_div(B * A, 256), 256, 0, s>>>(head, B, A, eps, d_action, ldd, dlogp_scalar, dhead,
-                                                               ld_dhead);
+void launch_actor_sample_bwd(const float* head, int ld_head, int B, int A, const float* eps, const float* d_action,
+                             int ldd, const float* dlogp_scalar, float* dhead, int ld_dhead, cudaStream_t s) {
+  actor_sample_bwd_kernel<<<ceil_div(B * A, 128), 128, 0, s>>>(head, ld_head, B, A, eps, d_action, ldd, dlogp_scalar,
+                                                               dhead, ld_dhead);
   RLREP_LAUNCHED("actor_sample_bwd", s);
 }
 

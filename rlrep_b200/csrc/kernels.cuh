@@ -50,8 +50,17 @@ void launch_ring_write(float* ring, int rec4, long long capacity, long long star
 void launch_ce_rows(float* logits, int ld, int rows, int cols, int diag_off, float inv_batch, float* loss_rows,
                     cudaStream_t s);
 
-// y[i] = sum_j X[i,j] w[j] + b[0]  (N = 1 linear heads; one warp per row)
+// y[i] = sum_j X[i,j] w[j] + b[0]  (N = 1 linear heads; one CTA per row)
 void launch_rowdot(const float* X, int ld, int rows, int D, const float* w, const float* b, float* y, cudaStream_t s);
+// Two such heads over the same rows in one launch (the twin Q heads).
+struct RowDotJob {
+  const float* X;
+  const float* w;
+  const float* b;
+  float* y;
+  int ld, D;
+};
+void launch_rowdot_pair(const RowDotJob& a, const RowDotJob& b, int rows, cudaStream_t s);
 // out[j] (+)= sum_i u[i] * X[i,j]   (u == nullptr: plain column sum).  Deterministic.
 void launch_colreduce(const float* X, int ld, int rows, int cols, const float* u, float* out, int accumulate,
                       cudaStream_t s);
@@ -74,12 +83,12 @@ void launch_feature_loss_finalize(const float* loss_rows, int rows, const float*
                                   float inv_batch, float* dpred, float* metrics /*[total, model, r]*/, cudaStream_t s);
 
 // Actor head -> action / log-prob (agent/sac/actor.py:76-91 + 40-43).
-//   head [B, 2A] = (mu | raw log-std); eps [B, A];  out action [B, lda] (tanh(u)), logp [B]
-void launch_actor_sample(const float* head, int B, int A, const float* eps, float* action, int lda, float* logp,
-                         cudaStream_t s);
+//   head [B, ld_head >= 2A] = (mu | raw log-std); eps [B, A];  out action [B, lda] (tanh(u)), logp [B]
+void launch_actor_sample(const float* head, int ld_head, int B, int A, const float* eps, float* action, int lda,
+                         float* logp, cudaStream_t s);
 // Backward of the above: dhead [B, ld_dhead >= 2A] from d_action [B, ldd] and the per-row d_logp scalar.
-void launch_actor_sample_bwd(const float* head, int B, int A, const float* eps, const float* d_action, int ldd,
-                             const float* dlogp_scalar, float* dhead, int ld_dhead, cudaStream_t s);
+void launch_actor_sample_bwd(const float* head, int ld_head, int B, int A, const float* eps, const float* d_action,
+                             int ldd, const float* dlogp_scalar, float* dhead, int ld_dhead, cudaStream_t s);
 
 // TD target + twin-critic MSE (ctrlsac_agent.py:263-286; sac_agent.py:112-123):
 //   y = r + (1 - d) * gamma * (min(nq1, nq2) - alpha * logp2)

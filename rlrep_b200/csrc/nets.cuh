@@ -118,8 +118,8 @@ struct RffCritic {
     linear_fwd(g, s, B, Mat{z, D}, l14, ACT_SIN, sn[slot], 2 * H, Mat(), 0, pre[slot]);
     linear_fwd(g, s, B, Mat{sn[slot], 2 * H}, l2, ACT_ELU, hid2[slot], H);
     linear_fwd(g, s, B, Mat{sn[slot] + H, 2 * H}, l5, ACT_ELU, hid2[slot] + (size_t)B * H, H);
-    launch_rowdot(hid2[slot], H, B, H, l3.W, l3.b, q[slot], s);
-    launch_rowdot(hid2[slot] + (size_t)B * H, H, B, H, l6.W, l6.b, q[slot] + B, s);
+    launch_rowdot_pair(RowDotJob{hid2[slot], l3.W, l3.b, q[slot], H, H},
+                       RowDotJob{hid2[slot] + (size_t)B * H, l6.W, l6.b, q[slot] + B, H, H}, B, s);
   }
 
   // (dq1 | dq2) [2B] -> parameter gradients (wgrad) and / or the gradient w.r.t. z (dz [B, D]).

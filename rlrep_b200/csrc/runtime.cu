@@ -154,7 +154,9 @@ GemmRunner::~GemmRunner() {
 }
 
 void GemmRunner::run(const GemmArgs& a, cudaStream_t s) {
-  const bool tc = prec_ == PREC_TF32 && tc_eligible(a) && a.M >= 64 && a.N >= 32 && a.K >= 64;
+  // Short-K layers (K = 17 / 23 inputs) also go to the tensor cores: the tensor maps carry the LOGICAL K, so TMA
+  // zero-fills the rest of the 32-wide k-block whatever sits behind the operands in memory.
+  const bool tc = prec_ == PREC_TF32 && tc_eligible(a) && a.M >= 64 && a.N >= 32 && a.K >= 8;
   if (!tc) {
     launch_simt(a, s);
     return;
@@ -171,9 +173,10 @@ void GemmRunner::run(const GemmArgs& a, cudaStream_t s) {
     k->epi.pre_out = a.epi.pre_out; k->epi.ld_aux = a.epi.ld_aux; k->epi.ld_pre = a.epi.ld_pre;
     k->epi.act = a.epi.act; k->epi.dact = a.epi.dact; k->epi.accumulate = a.epi.accumulate;
     k->epi.scale = a.epi.scale;
+    k->K1 = sm_share_ < 0.75 ? 1 : 0;  // (K1 is unused on this path) plans differ with the share of the GPU
   }
   auto it = plans_.find(key);
-  if (it == plans_.end()) it = plans_.emplace(key, make_tc_plan(a, 0, 0, ws_, ws_floats_)).first;
+  if (it == plans_.end()) it = plans_.emplace(key, make_tc_plan(a, 0, 0, ws_, ws_floats_, sm_share_)).first;
   launch_tc(it->second, s);
 }
 
@@ -181,7 +184,10 @@ void GemmRunner::run(const GemmArgs& a, cudaStream_t s) {
 void linear_fwd(GemmRunner& g, cudaStream_t s, int rows, Mat x, const Linear& l, int act, float* y, int ldy, Mat x2,
                 int k1, float* pre_out) {
   GemmArgs a;
-  a.M = rows; a.N = l.out; a.K = l.in;
+  // Narrow heads (N = 2A = 12 ...) run over the padded extent when the output pitch has room for it: the padding rows
+  // of W and b are zero and stay zero (their gradients are exactly zero), so the extra columns are written as zeros.
+  const bool pad_n = l.out < 32 && l.out_alloc >= 32 && ldy >= l.out_alloc && rows >= 64 && pre_out == nullptr;
+  a.M = rows; a.N = pad_n ? l.out_alloc : l.out; a.K = l.in;
   a.A = x.p; a.lda = x.ld;
   if (x2.p) { a.A2 = x2.p; a.lda2 = x2.ld; a.K1 = k1; }
   a.B = l.W; a.ldb = l.ld;
