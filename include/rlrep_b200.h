@@ -139,6 +139,20 @@ typedef struct rlrep_agent_config {
 } rlrep_agent_config;
 
 RLREP_EXPORT int rlrep_agent_create(const rlrep_agent_config* cfg, void* stream, rlrep_agent** out);
+
+/* Batch-sharded CTRL-SAC over N GPUs, one process per GPU (BASELINE config 4; the reference has no distributed code --
+ * this is the data-parallel form of ctrlsac_agent.py:213-362 on a global batch of N * cfg->batch_size rows: all-gather of
+ * mu(s'), reduce-scatter of its gradient, all-reduce of parameter gradients and loss sums over NCCL).  Rank 0 obtains a
+ * 128-byte id, ships it to the other ranks out of band (torch.distributed, MPI, a file), every rank creates its
+ * communicator and then its handle.  rlrep_agent_train takes the rank's OWN rows: idx [K * batch_size] and eps
+ * [2 * batch_size * action_dim] are the rank's slices of the global draws; metrics are global and identical on all ranks. */
+typedef struct rlrep_comm rlrep_comm;
+RLREP_EXPORT int rlrep_comm_unique_id(unsigned char* out128);
+RLREP_EXPORT int rlrep_comm_create(const unsigned char* id128, int rank, int world, rlrep_comm** out);
+RLREP_EXPORT int rlrep_comm_destroy(rlrep_comm* comm);
+RLREP_EXPORT int rlrep_comm_info(rlrep_comm* comm, int* rank, int* world, int* nccl_version, long long* collectives);
+RLREP_EXPORT int rlrep_agent_create_sharded(const rlrep_agent_config* cfg, rlrep_comm* comm, void* stream,
+                                            rlrep_agent** out);
 RLREP_EXPORT int rlrep_agent_destroy(rlrep_agent* agent);
 
 /* Parameters and Polyak targets under the reference's state_dict names ("phi.l1.weight", "critic_target.l2.bias",

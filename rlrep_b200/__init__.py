@@ -11,7 +11,8 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
     if name in ("ReplayBuffer", "Batch"):
         from . import buffer
         return getattr(buffer, name)
-    if name in ("SACAgent", "CTRLSACAgent", "VLSACAgent", "SPEDERSACAgent", "DIFFSRSACAgent", "AGENTS"):
+    if name in ("SACAgent", "CTRLSACAgent", "VLSACAgent", "SPEDERSACAgent", "DIFFSRSACAgent", "ShardedCTRLSACAgent",
+                "AGENTS"):
         from . import agents
         return getattr(agents, name)
     raise AttributeError(name)

@@ -83,6 +83,11 @@ def _declare(lib: C.CDLL) -> None:
         "rlrep_ring_gather": [vp, vp, i, vp, vp],
         "rlrep_agent_create": [C.POINTER(AgentConfig), vp, C.POINTER(vp)],
         "rlrep_agent_destroy": [vp],
+        "rlrep_comm_unique_id": [vp],
+        "rlrep_comm_create": [vp, i, i, C.POINTER(vp)],
+        "rlrep_comm_destroy": [vp],
+        "rlrep_comm_info": [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i), C.POINTER(C.c_longlong)],
+        "rlrep_agent_create_sharded": [C.POINTER(AgentConfig), vp, vp, C.POINTER(vp)],
         "rlrep_agent_num_tensors": [vp, C.POINTER(i)],
         "rlrep_agent_tensor_info": [vp, i, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(i), C.POINTER(i)],
         "rlrep_agent_tensor_read": [vp, i, vp],

@@ -35,13 +35,16 @@ def _default_linear(out_f, in_f):
 class _Handle:
     """Owns one `rlrep_agent*` and exposes tensors / scalars."""
 
-    def __init__(self, cfg: _lib.AgentConfig):
+    def __init__(self, cfg: _lib.AgentConfig, comm=None):
         if not torch.cuda.is_available():
             raise _lib.RlrepError("rlrep_b200 agents need a CUDA device (there is no CPU fallback)")
         self.lib = _lib.load()
         self.stream = torch.cuda.current_stream().cuda_stream
         h = C.c_void_p()
-        _lib.check(self.lib.rlrep_agent_create(C.byref(cfg), self.stream, C.byref(h)))
+        if comm is None:
+            _lib.check(self.lib.rlrep_agent_create(C.byref(cfg), self.stream, C.byref(h)))
+        else:  # batch-sharded handle: cfg.batch_size is the rank's share of the global batch
+            _lib.check(self.lib.rlrep_agent_create_sharded(C.byref(cfg), comm, self.stream, C.byref(h)))
         self.h = h
         n = C.c_int()
         _lib.check(self.lib.rlrep_agent_num_tensors(self.h, C.byref(n)))
@@ -174,10 +177,13 @@ class SACAgent:
             self._pending_state.pop("log_alpha", None)
             self._h.close()
         self._batch = int(batch_size or 256)
-        self._h = _Handle(self._config(self._batch))
+        self._h = self._make_handle(self._batch)
         self.load_state_dict(self._pending_state, strict=False)
         self._pending_state = None
         return self._h
+
+    def _make_handle(self, batch):
+        return _Handle(self._config(batch))
 
     def state_dict(self):
         """All parameters and Polyak targets under the reference's state_dict names, plus float64 `log_alpha`."""
@@ -304,6 +310,72 @@ class CTRLSACAgent(SACAgent):
 
     def _info(self, m):
         return dict(zip(self._h.metric_names, (float(x) for x in m)))
+
+
+class ShardedCTRLSACAgent(CTRLSACAgent):
+    """CTRL-SAC with the batch of every train() call split by rows over the ranks of a torch.distributed process group
+    (one process per GPU; BASELINE config 4).  The reference has no distributed code: this is its update
+    on the GLOBAL batch, computed cooperatively -- mu(s') is all-gathered so that every rank owns complete rows of the
+    contrastive logits, its gradient is reduce-scattered, parameter gradients and loss sums are all-reduced (NCCL over
+    NVLink inside the C library), and every rank applies the same Adam step.
+
+    Every rank must be constructed with the same arguments, load the same weights and run with the same numpy / torch
+    seeds: `train(buffer, batch_size)` draws the GLOBAL indices and noise exactly like the reference does and keeps the
+    rank's rows; `batch_size` is the global batch and must be divisible by the world size.  The returned info dict is
+    global and identical on all ranks."""
+
+    def __init__(self, *args, process_group=None, **kw):
+        import torch.distributed as dist
+        if not dist.is_initialized():
+            raise _lib.RlrepError("ShardedCTRLSACAgent needs an initialised torch.distributed process group")
+        self._pg = process_group
+        self.rank, self.world = dist.get_rank(process_group), dist.get_world_size(process_group)
+        self._comm = None
+        kw.setdefault("use_cuda_graph", False)
+        super().__init__(*args, **kw)
+
+    def _comm_handle(self):
+        """rank 0 creates the NCCL unique id, torch.distributed ships it, every rank joins (rlrep_comm_create)."""
+        if self._comm is not None:
+            return self._comm
+        import torch.distributed as dist
+        lib = _lib.load()
+        idbuf = (C.c_ubyte * 128)()
+        if self.rank == 0:
+            _lib.check(lib.rlrep_comm_unique_id(idbuf))
+        box = [bytes(idbuf) if self.rank == 0 else None]
+        src = dist.get_global_rank(self._pg, 0) if self._pg is not None else 0
+        dist.broadcast_object_list(box, src=src, group=self._pg)
+        idbuf = (C.c_ubyte * 128).from_buffer_copy(box[0])
+        comm = C.c_void_p()
+        _lib.check(lib.rlrep_comm_create(idbuf, self.rank, self.world, C.byref(comm)))
+        self._comm = comm
+        return comm
+
+    def local_batch(self, batch_size):
+        if batch_size % self.world != 0:
+            raise ValueError(f"global batch {batch_size} is not divisible by the world size {self.world}")
+        return batch_size // self.world
+
+    def _make_handle(self, batch):
+        return _Handle(self._config(self.local_batch(batch)), comm=self._comm_handle())
+
+    def _draw(self, buffer, batch_size):
+        """Global draws in the reference's order, then this rank's rows of each of them."""
+        idx, eps = super()._draw(buffer, batch_size)
+        K, b = self.extra_feature_steps + 1, self.local_batch(batch_size)
+        lo, hi = self.rank * b, (self.rank + 1) * b
+        idx = idx.reshape(K, batch_size)[:, lo:hi].reshape(-1)
+        eps = eps.reshape(2, batch_size, self.action_dim)[:, lo:hi].reshape(-1)
+        return idx, eps
+
+    def close(self):
+        if self._h is not None:
+            self._h.close()
+            self._h = None
+        if self._comm is not None:
+            _lib.load().rlrep_comm_destroy(self._comm)
+            self._comm = None
 
 
 class VLSACAgent(SACAgent):

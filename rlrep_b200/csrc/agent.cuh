@@ -309,5 +309,8 @@ std::unique_ptr<Agent> make_ctrlsac_agent(const AgentConfig& cfg, cudaStream_t s
 std::unique_ptr<Agent> make_vlsac_agent(const AgentConfig& cfg, cudaStream_t s);
 std::unique_ptr<Agent> make_spedersac_agent(const AgentConfig& cfg, cudaStream_t s);
 std::unique_ptr<Agent> make_diffsrsac_agent(const AgentConfig& cfg, cudaStream_t s);
+class Comm;
+// cfg.batch = rows per rank; the global batch is cfg.batch * comm->world (agent_ctrlsac_dp.cu)
+std::unique_ptr<Agent> make_ctrlsac_sharded_agent(const AgentConfig& cfg, cudaStream_t s, Comm* comm);
 
 }  // namespace rlrep

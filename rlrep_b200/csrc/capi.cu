@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "agent.cuh"
+#include "comm.cuh"
 #include "common.cuh"
 #include "gemm.cuh"
 #include "rlrep_b200.h"
@@ -50,6 +51,10 @@ __global__ void null_pdl_kernel(float* p) {
 
 struct rlrep_ring {
   std::unique_ptr<Ring> impl;
+};
+
+struct rlrep_comm {
+  std::unique_ptr<Comm> impl;
 };
 
 struct TensorRef {
@@ -224,7 +229,50 @@ int rlrep_ring_gather(rlrep_ring* ring, const int64_t* idx_host, int B, float* o
 }
 
 // ------------------------------------------------------------------------------------------------ agents
+// ------------------------------------------------------------------------------------------------ communicator
+int rlrep_comm_unique_id(unsigned char* out128) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(out128 != nullptr, "null argument");
+  Comm::unique_id(out128);
+  RLREP_API_END
+}
+int rlrep_comm_create(const unsigned char* id128, int rank, int world, rlrep_comm** out) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(id128 != nullptr && out != nullptr, "null argument");
+  std::unique_ptr<rlrep_comm> c(new rlrep_comm);
+  c->impl.reset(new Comm(id128, rank, world));
+  *out = c.release();
+  RLREP_API_END
+}
+int rlrep_comm_destroy(rlrep_comm* comm) {
+  RLREP_API_BEGIN
+  delete comm;
+  RLREP_API_END
+}
+int rlrep_comm_info(rlrep_comm* comm, int* rank, int* world, int* nccl_version, long long* collectives) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(comm != nullptr, "null argument");
+  if (rank) *rank = comm->impl->rank;
+  if (world) *world = comm->impl->world;
+  if (nccl_version) *nccl_version = Comm::version();
+  if (collectives) *collectives = comm->impl->collectives;
+  RLREP_API_END
+}
+
+static int create_agent(const rlrep_agent_config* c, rlrep_comm* comm, void* stream, rlrep_agent** out);
+
 int rlrep_agent_create(const rlrep_agent_config* c, void* stream, rlrep_agent** out) {
+  return create_agent(c, nullptr, stream, out);
+}
+int rlrep_agent_create_sharded(const rlrep_agent_config* c, rlrep_comm* comm, void* stream, rlrep_agent** out) {
+  if (comm == nullptr) {
+    set_last_error("rlrep_agent_create_sharded: null communicator");
+    return 1;
+  }
+  return create_agent(c, comm, stream, out);
+}
+
+static int create_agent(const rlrep_agent_config* c, rlrep_comm* comm, void* stream, rlrep_agent** out) {
   RLREP_API_BEGIN
   RLREP_CHECK(c != nullptr && out != nullptr, "null argument");
   AgentConfig a;
@@ -254,7 +302,10 @@ int rlrep_agent_create(const rlrep_agent_config* c, void* stream, rlrep_agent** 
     RLREP_CUDA(cudaStreamCreateWithFlags(&h->owned_stream, cudaStreamNonBlocking));
     st = h->owned_stream;
   }
-  switch (a.alg) {
+  if (comm != nullptr) {
+    RLREP_CHECK(a.alg == RLREP_ALG_CTRLSAC, "batch sharding is implemented for ctrlsac (the path with a B x B exchange)");
+    h->impl = make_ctrlsac_sharded_agent(a, st, comm->impl.get());
+  } else switch (a.alg) {
     case RLREP_ALG_SAC: h->impl = make_sac_agent(a, st); break;
     case RLREP_ALG_CTRLSAC: h->impl = make_ctrlsac_agent(a, st); break;
     case RLREP_ALG_VLSAC: h->impl = make_vlsac_agent(a, st); break;

@@ -275,12 +275,12 @@ __global__ void __launch_bounds__(256) td_critic_loss_kernel(const float* __rest
                                                              const float* __restrict__ nq2,
                                                              const float* __restrict__ logp2,
                                                              const float* __restrict__ q1, const float* __restrict__ q2,
-                                                             int B, float gamma, const Control* __restrict__ c,
-                                                             float* __restrict__ dq1, float* __restrict__ dq2,
-                                                             float* __restrict__ metrics) {
+                                                             int B, int norm_B, float gamma,
+                                                             const Control* __restrict__ c, float* __restrict__ dq1,
+                                                             float* __restrict__ dq2, float* __restrict__ metrics) {
   __shared__ float scratch[33];
   const float alpha = c->alpha;
-  const float inv_b = 1.f / (float)B;
+  const float inv_b = 1.f / (float)norm_B;
   float l1 = 0.f, l2 = 0.f, s1 = 0.f, s2 = 0.f;
   for (int i = threadIdx.x; i < B; i += 256) {
     const float nq = fminf(nq1[i], nq2[i]) - alpha * logp2[i];
@@ -344,6 +344,55 @@ __global__ void __launch_bounds__(256) actor_alpha_loss_kernel(const float* __re
     }
     metrics[2] = (float)exp(c->log_alpha);
   }
+}
+
+// Batch-sharded variant of the kernel above (agent_ctrlsac_dp.cu): the rank's rows contribute partial means over the
+// GLOBAL batch; the temperature step runs after the partials have been all-reduced.
+__global__ void __launch_bounds__(256) actor_loss_partial_kernel(const float* __restrict__ q1,
+                                                                 const float* __restrict__ q2,
+                                                                 const float* __restrict__ logp, int B, int norm_B,
+                                                                 float target_entropy, const Control* __restrict__ c,
+                                                                 float* __restrict__ dq1, float* __restrict__ dq2,
+                                                                 float* __restrict__ dlogp_scalar,
+                                                                 float* __restrict__ partial) {
+  __shared__ float scratch[33];
+  const float alpha = c->alpha;
+  const float inv_b = 1.f / (float)norm_B;
+  float la = 0.f, raw = 0.f;
+  for (int i = threadIdx.x; i < B; i += 256) {
+    const float a = q1[i], b = q2[i];
+    la += alpha * logp[i] - fminf(a, b);
+    raw += -logp[i] - target_entropy;
+    const float g = -inv_b;
+    dq1[i] = a < b ? g : (a == b ? 0.5f * g : 0.f);
+    dq2[i] = b < a ? g : (a == b ? 0.5f * g : 0.f);
+  }
+  la = block_sum<256>(la, scratch);
+  raw = block_sum<256>(raw, scratch);
+  if (threadIdx.x == 0) {
+    *dlogp_scalar = alpha * inv_b;
+    partial[0] = la * inv_b;   // this rank's share of mean(alpha * logp - min(q1, q2))
+    partial[1] = raw * inv_b;  // this rank's share of mean(-logp - target_entropy)
+  }
+}
+__global__ void alpha_step_kernel(const float* __restrict__ reduced, int learn_alpha, Control* c,
+                                  float* __restrict__ metrics) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  metrics[0] = reduced[0];
+  metrics[1] = c->alpha * reduced[1];  // mean(alpha * (-logp - H).detach())
+  if (learn_alpha) {
+    const double g = (double)reduced[1] * exp(c->log_alpha);
+    c->la_m = c->la_m + (1.0 - 0.9) * (g - c->la_m);
+    c->la_v = c->la_v * 0.999 + (1.0 - 0.999) * g * g;
+    const double denom = sqrt(c->la_v) / c->alpha_bc2_sqrt + 1e-8;
+    c->log_alpha = c->log_alpha - c->alpha_step_size * (c->la_m / denom);
+  }
+  metrics[2] = (float)exp(c->log_alpha);
+}
+// x[i, j] *= dact(aux[i, j])  (the tanh derivative of mu after the reduce-scatter of its gradient)
+__global__ void mul_dact_kernel(float* __restrict__ x, const float* __restrict__ aux, size_t n, int dact) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+    x[i] *= apply_dact(aux[i], dact);
 }
 
 // ------------------------------------------------------------------------------------------- Adam + Polyak
@@ -676,8 +725,9 @@ void launch_actor_sample_bwd(const float* head, int ld_head, int B, int A, const
 
 void launch_td_critic_loss(const float* reward, const float* done, int ld_rd, const float* nq1, const float* nq2,
                            const float* logp2, const float* q1, const float* q2, int B, float gamma, const Control* c,
-                           float* dq1, float* dq2, float* metrics, cudaStream_t s) {
-  td_critic_loss_kernel<<<1, 256, 0, s>>>(reward, done, ld_rd, nq1, nq2, logp2, q1, q2, B, gamma, c, dq1, dq2, metrics);
+                           float* dq1, float* dq2, float* metrics, cudaStream_t s, int norm_B) {
+  td_critic_loss_kernel<<<1, 256, 0, s>>>(reward, done, ld_rd, nq1, nq2, logp2, q1, q2, B, norm_B > 0 ? norm_B : B, gamma,
+                                          c, dq1, dq2, metrics);
   RLREP_LAUNCHED("td_critic_loss", s);
 }
 
@@ -687,6 +737,21 @@ void launch_actor_alpha_loss(const float* q1, const float* q2, const float* logp
   actor_alpha_loss_kernel<<<1, 256, 0, s>>>(q1, q2, logp, B, target_entropy, learn_alpha, c, dq1, dq2, dlogp_scalar,
                                             metrics);
   RLREP_LAUNCHED("actor_alpha_loss", s);
+}
+
+void launch_actor_loss_partial(const float* q1, const float* q2, const float* logp, int B, int norm_B,
+                               float target_entropy, const Control* c, float* dq1, float* dq2, float* dlogp_scalar,
+                               float* partial, cudaStream_t s) {
+  actor_loss_partial_kernel<<<1, 256, 0, s>>>(q1, q2, logp, B, norm_B, target_entropy, c, dq1, dq2, dlogp_scalar, partial);
+  RLREP_LAUNCHED("actor_loss_partial", s);
+}
+void launch_alpha_step(const float* reduced, int learn_alpha, Control* c, float* metrics, cudaStream_t s) {
+  alpha_step_kernel<<<1, 32, 0, s>>>(reduced, learn_alpha, c, metrics);
+  RLREP_LAUNCHED("alpha_step", s);
+}
+void launch_mul_dact(float* x, const float* aux, size_t n, int dact, cudaStream_t s) {
+  mul_dact_kernel<<<grid_for(n, 256), 256, 0, s>>>(x, aux, n, dact);
+  RLREP_LAUNCHED_W("mul_dact", s, 12.0 * (double)n, 0.0);
 }
 
 void launch_pack_columns(const float* in, int ld_in, float* out, int ld_out, int rows, const ColSegment* segs, int n_segs,

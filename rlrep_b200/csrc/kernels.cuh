@@ -95,7 +95,7 @@ void launch_actor_sample_bwd(const float* head, int ld_head, int B, int A, const
 //   dq1 = 2 (q1 - y) / B, dq2 likewise;  metrics[0..3] = q1_loss, q2_loss, mean(q1), mean(q2)
 void launch_td_critic_loss(const float* reward, const float* done, int ld_rd, const float* nq1, const float* nq2,
                            const float* logp2, const float* q1, const float* q2, int B, float gamma, const Control* c,
-                           float* dq1, float* dq2, float* metrics, cudaStream_t s);
+                           float* dq1, float* dq2, float* metrics, cudaStream_t s, int norm_B = 0);
 
 // Actor / temperature losses (ctrlsac_agent.py:308-320; sac_agent.py:146-161), single block:
 //   actor_loss = mean(alpha * logp - min(q1, q2));  dq1/dq2 = -[argmin] / B;  *dlogp_scalar = alpha / B
@@ -104,6 +104,16 @@ void launch_td_critic_loss(const float* reward, const float* done, int ld_rd, co
 void launch_actor_alpha_loss(const float* q1, const float* q2, const float* logp, int B, float target_entropy,
                              int learn_alpha, Control* c, float* dq1, float* dq2, float* dlogp_scalar, float* metrics,
                              cudaStream_t s);
+
+// Batch-sharded pieces (agent_ctrlsac_dp.cu).  norm_B = GLOBAL batch: every mean is a partial sum / norm_B that the
+// caller all-reduces.  partial = {share of actor_loss, share of mean(-logp - target_entropy)}; alpha_step consumes the
+// all-reduced pair: metrics = {actor_loss, alpha_loss, alpha} and the float64 Adam step on log_alpha.
+void launch_actor_loss_partial(const float* q1, const float* q2, const float* logp, int B, int norm_B,
+                               float target_entropy, const Control* c, float* dq1, float* dq2, float* dlogp_scalar,
+                               float* partial, cudaStream_t s);
+void launch_alpha_step(const float* reduced, int learn_alpha, Control* c, float* metrics, cudaStream_t s);
+// x *= dact(aux), elementwise over n floats
+void launch_mul_dact(float* x, const float* aux, size_t n, int dact, cudaStream_t s);
 
 // ---- LV-Rep / VL-SAC (agent/vlsac/vlsac_agent.py, networks/vae.py) ----------------------------------------------
 // out[b, dst + j] = in[b, src + j] for up to three column segments (builds cat(s, a, s') from a replay record).
