@@ -50,6 +50,10 @@ WORKLOADS = {
     # the other two state-based agents at what main.py passes (main.py:93-104)
     "spedersac_hc_b256": dict(alg="spedersac", S=17, A=6, B=256, rows=1_000_000, kw=SPEDER_MAIN),
     "diffsrsac_hc_b256": dict(alg="diffsrsac", S=17, A=6, B=256, rows=1_000_000, kw=dict(hidden_dim=256)),
+    # BASELINE.json configs[3]: large-batch CTRL, GLOBAL batch 16384 split by rows over the ranks (strong scaling:
+    # the total work is fixed; 2048 rows per GPU at N = 8), mu(s') all-gathered over NVLink
+    "ctrlsac_b16384_sharded": dict(alg="ctrlsac", S=17, A=6, B=16384, rows=1_000_000, sharded=True,
+                                   kw=dict(hidden_dim=1024, feature_dim=2048, extra_feature_steps=3)),
 }
 
 
@@ -135,6 +139,15 @@ class ClockSampler:
         return out
 
 
+_REAL_STDOUT = None
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def measure_tf32_peak():
     """Dense TF32 tensor-core peak the way MEASURED_PEAKS.json measures bf16: torch.matmul (cuBLAS) on 8192^3, best of
     10 with CUDA events.  Only a roofline denominator -- never on the measured path."""
@@ -193,9 +206,11 @@ def run_reference(args, w, rank, world):
     """--impl reference: the reference's CPU implementation of the path (oracle port, as written) on host cores."""
     if rank != 0:
         return
-    ups, ms, cores = time_oracle(w, args.steps, args.warmup, as_written=True)
-    sample = f"{args.steps} full train() calls after {args.warmup} warm-up, reference arithmetic as written" + \
-        (" ([B,B,D] broadcast logits)" if w["alg"] == "ctrlsac" else "")
+    as_written = not w.get("sharded")  # the [B,B,D] broadcast needs 2.2 TB at B = 16384: matmul-restated there
+    ups, ms, cores = time_oracle(w, args.steps, args.warmup, as_written=as_written)
+    sample = f"{args.steps} full train() calls after {args.warmup} warm-up, reference arithmetic " + \
+        ("as written ([B,B,D] broadcast logits)" if w["alg"] == "ctrlsac" and as_written else
+         "with the logits restated as a matmul (SURVEY.md 8c)" if w["alg"] == "ctrlsac" else "as written")
     line = {
         "impl": "reference", "metric": "agent updates/sec", "value": ups, "unit": "updates/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
@@ -204,7 +219,7 @@ def run_reference(args, w, rank, world):
         "cpu_baseline": {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------- GPU arm
@@ -216,17 +231,29 @@ def run_ours(args, w, rank, world, local_rank):
     from oracle import rl_oracle as O  # synthetic data generator + deterministic initial weights only
 
     torch.cuda.set_device(local_rank)
+    sharded = bool(w.get("sharded"))
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    elif sharded:  # the sharded agent at N = 1 still goes through a (single-rank) process group and communicator
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29517")
+        dist.init_process_group("gloo", rank=0, world_size=1)
     S, A, B, kw = w["S"], w["A"], w["B"], w["kw"]
-    agent = AGENTS[w["alg"]](S, A, Space(A), discount=0.99, tau=0.005, precision=args.precision, **kw)
-    agent.load_state_dict(O.init_state(w["alg"], S, A, kw, seed=rank))  # independent seeds per replica
-    ring = O.synthetic_ring(S, A, w["rows"], seed=rank)
+    if sharded:
+        from rlrep_b200.agents import ShardedCTRLSACAgent
+        # one logical agent over all ranks: identical weights, identical seeds, the global batch split by rows
+        agent = ShardedCTRLSACAgent(S, A, Space(A), discount=0.99, tau=0.005, precision=args.precision, **kw)
+        seed = 0
+    else:
+        agent = AGENTS[w["alg"]](S, A, Space(A), discount=0.99, tau=0.005, precision=args.precision, **kw)
+        seed = rank  # independent replicas: own weights, own data, own seeds
+    agent.load_state_dict(O.init_state(w["alg"], S, A, kw, seed=seed))
+    ring = O.synthetic_ring(S, A, w["rows"], seed=seed)
     buf = ReplayBuffer(S, A, max_size=w["rows"])
     buf.load(ring.state, ring.action, ring.next_state, ring.reward, ring.done)
     del ring
-    np.random.seed(1 + rank)
-    torch.manual_seed(1 + rank)
+    np.random.seed(1 + seed)
+    torch.manual_seed(1 + seed)
 
     def barrier():
         torch.cuda.synchronize()
@@ -272,6 +299,13 @@ def run_ours(args, w, rank, world, local_rank):
     # ---- (3) per-kernel profile (eager, one stream, an event behind every launch).  Every launch carries its
     # algorithmic bytes / flops (operands read once, results written once), so each kernel gets a roofline fraction.
     roofline, top = None, []
+    if rank != 0 and sharded:  # the sharded update contains collectives: every rank has to take part in the profiled calls
+        for _ in range(3):
+            i1, e1 = agent._draw(buf, B)
+            i1 = np.ascontiguousarray(i1, dtype=np.int64)
+            e1 = np.ascontiguousarray(e1, dtype=np.float32)
+            _lib.check(h.lib.rlrep_agent_profile_train(h.h, buf._h, i1.ctypes.data, e1.ctypes.data, 0, None, None, None,
+                                                       None, C.byref(C.c_int())))
     if rank == 0:
         cap = 8192
         names = (C.c_char_p * cap)()
@@ -338,7 +372,7 @@ def run_ours(args, w, rank, world, local_rank):
 
     # ---- (4) CPU baseline: the oracle port on this box's host cores (rank 0, N = 1 only)
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and not sharded:
         n_cpu = {"ctrlsac": 6, "vlsac": 30, "spedersac": 60}.get(w["alg"], 200)  # ~10-30 s of CPU work
         ups, ms_cpu, cores = time_oracle(w, n_cpu, 1, as_written=True)
         cpu = {"value": ups, "unit": "updates/s", "cores": cores, "kind": "port",
@@ -347,16 +381,20 @@ def run_ours(args, w, rank, world, local_rank):
 
     if rank == 0:
         ni, ne = h.n_idx, h.n_eps
+        n_agents = 1 if sharded else world  # a sharded run is ONE agent's update, however many GPUs compute it
         line = {
-            "metric": "agent updates/sec", "value": world * args.steps / (dev_ms * 1e-3), "unit": "updates/s",
+            "metric": "agent updates/sec", "value": n_agents * args.steps / (dev_ms * 1e-3), "unit": "updates/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
             "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
             "config": {"workload": args.workload, **{k: w[k] for k in ("alg", "S", "A", "B")}, **kw,
-                       "ring_rows": w["rows"], "parallelism": f"replicas x{world} (no collective)",
+                       "ring_rows": w["rows"],
+                       "parallelism": (f"one agent, batch sharded by rows over {world} GPU(s): {B // world} rows/GPU, NCCL "
+                                       f"all-gather of mu(s'), reduce-scatter of d mu, all-reduce of gradients"
+                                       if sharded else f"replicas x{world} (no collective)"),
                        "l2": ("no flush: per-update working set (params+grads+Adam moments+targets ~200 MB) exceeds the 126 MB L2"
                               if w["alg"] == "ctrlsac" else "no flush between updates (working set below L2: see DESIGN.md)")},
-            "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "updates/s", "ms_per_step": e2e_ms / args.steps,
+            "e2e": {"value": n_agents * args.steps / (e2e_ms * 1e-3), "unit": "updates/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": ni * 8 + ne * 4, "d2h_bytes_per_step": 32 * 4},
             "gpu_launches": launches * args.steps,
             "gpu_launches_per_step": launches,
@@ -366,12 +404,18 @@ def run_ours(args, w, rank, world, local_rank):
             "top_kernels_us_per_step": [[k, round(v * 1e3, 1), c] for k, v, c in top[:8]],
             "last_info": info,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    # stdout carries the JSON line and nothing else: native libraries (NCCL's version banner ...) write to fd 1 directly,
+    # so fd 1 is pointed at stderr for the duration of the run and the JSON line goes to the saved real stdout.
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
@@ -386,8 +430,10 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
-        if args.steps > 40 and w["alg"] == "ctrlsac":
-            args.steps = 40  # bounded sample: ~1-2 s of CPU work per update
+        if w.get("sharded"):
+            args.steps, args.warmup = min(args.steps, 2), 0  # ~17 TFLOP per update on the host cores: a bounded sample
+        elif args.steps > 40 and w["alg"] == "ctrlsac":
+            args.steps = 40  # bounded sample: ~0.5-2 s of CPU work per update
         run_reference(args, w, rank, world)
         return
     run_ours(args, w, rank, world, local_rank)

@@ -15,7 +15,8 @@
 //   critic / actor plain data parallelism: means are over the global batch (every partial is divided by Bg), gradients
 //                  and loss sums are all-reduced; the float64 temperature step runs on the all-reduced mean.
 // Kernels are the single-GPU ones; b = 2048 rows per rank makes every GEMM throughput-bound, so the step runs eagerly
-// on one stream (no graph, no side streams).
+// (no graph).  The mu branch with its two collectives runs on a side stream so that the NVLink transfers overlap the
+// phi branch's GEMMs.
 #include "agent_base.cuh"
 #include "comm.cuh"
 
@@ -34,6 +35,7 @@ class CtrlSacShardedAgent final : public SacBase {
     rank_ = comm_->rank;
     Bg_ = B_ * N_;
     cfg.use_graph = 0;
+    dual_share_ = 1.0;  // throughput-bound GEMMs: plan each one for the whole GPU even when two branches overlap
     RLREP_CHECK(K_ >= 1 && K_ <= kMaxFeatureSteps, "extra_feature_steps out of range");
     RLREP_CHECK(H_ % 32 == 0 && D_ % 32 == 0 && B_ % 32 == 0, "hidden_dim, feature_dim and the per-rank batch must be multiples of 32");
     const RecordLayout lay = RecordLayout::of(S_, A_);
@@ -104,7 +106,6 @@ class CtrlSacShardedAgent final : public SacBase {
  protected:
   void update(Ring& ring) override {
     begin_update();
-    serial_ = true;  // one stream: the collectives order every rank's launches identically
     launch_tick(ctl, base_tick(), stream);
     for (int k = 0; k < K_; ++k) {
       launch_gather(ring.data, R_ / 4, idx_dev_ + (size_t)k * B_, B_, batch_, stream);
@@ -134,13 +135,16 @@ class CtrlSacShardedAgent final : public SacBase {
     const Linear n1 = m1_.view(feat_g_), n2 = m2_.view(feat_g_), n3 = m3_.view(feat_g_);
     const Linear th = th_.view(feat_g_);
     const float inv_bg = 1.f / (float)Bg_;
-    cudaStream_t s = stream;
-    // mu first, so its all-gather is in flight while phi runs
-    linear_fwd(gemm_, s, B_, s2(), n1, ACT_ELU, g1_, H_);
-    linear_fwd(gemm_, s, B_, Mat{g1_, H_}, n2, ACT_ELU, g2_, H_);
-    linear_fwd(gemm_, s, B_, Mat{g2_, H_}, n3, ACT_TANH, zmu_, D_);
-    comm_->all_gather(zmu_, zmu_all_, (size_t)B_ * D_, s);
+    cudaStream_t s = stream, s1 = side();
+    // mu and its all-gather on the side stream, phi on the main stream: the NVLink transfer hides behind phi's GEMMs.
+    // Every rank issues the collectives in the same host order, which is all NCCL asks for.
+    fork();
+    linear_fwd(gemm_, s1, B_, s2(), n1, ACT_ELU, g1_, H_);
+    linear_fwd(gemm_, s1, B_, Mat{g1_, H_}, n2, ACT_ELU, g2_, H_);
+    linear_fwd(gemm_, s1, B_, Mat{g2_, H_}, n3, ACT_TANH, zmu_, D_);
+    comm_->all_gather(zmu_, zmu_all_, (size_t)B_ * D_, s1);
     phi_forward(sa(), Mat(), 0, zphi_);
+    join();
     {  // logits_local[i, j] = <phi_i, mu_all_j>
       GemmArgs a;
       a.M = B_; a.N = Bg_; a.K = D_;
@@ -169,8 +173,9 @@ class CtrlSacShardedAgent final : public SacBase {
       a.C = dmu_all_; a.ldc = D_;
       gemm_.run(a, s);
     }
-    comm_->reduce_scatter(dmu_all_, dzmu_, (size_t)B_ * D_, s);
-    // phi backward overlaps the reduce-scatter on the device only as far as the stream allows; kept simple here
+    // side stream: reduce-scatter of d mu and the mu backward; main stream: the phi backward
+    fork();
+    comm_->reduce_scatter(dmu_all_, dzmu_, (size_t)B_ * D_, s1);
     linear_wgrad(gemm_, s, B_, Mat{dzphi_, D_}, Mat{h2_, H_}, l3, Mat(), 0, false);
     linear_dgrad(gemm_, s, B_, Mat{dzphi_, D_}, l3, DACT_ELU_OUT, Mat{h2_, H_}, dh2_, H_);
     linear_wgrad(gemm_, s, B_, Mat{dh2_, H_}, Mat{h1_, H_}, l2, Mat(), 0, false);
@@ -182,17 +187,18 @@ class CtrlSacShardedAgent final : public SacBase {
                         ColJob{drp_, nullptr, th.db, 1, B_, 1}};
       launch_colreduce_multi(jobs, 5, s);
     }
-    launch_mul_dact(dzmu_, zmu_, (size_t)B_ * D_, DACT_TANH_OUT, s);
-    linear_wgrad(gemm_, s, B_, Mat{dzmu_, D_}, Mat{g2_, H_}, n3, Mat(), 0, false);
-    linear_dgrad(gemm_, s, B_, Mat{dzmu_, D_}, n3, DACT_ELU_OUT, Mat{g2_, H_}, dg2_, H_);
-    linear_wgrad(gemm_, s, B_, Mat{dg2_, H_}, Mat{g1_, H_}, n2, Mat(), 0, false);
-    linear_dgrad(gemm_, s, B_, Mat{dg2_, H_}, n2, DACT_ELU_OUT, Mat{g1_, H_}, dg1_, H_);
-    linear_wgrad(gemm_, s, B_, Mat{dg1_, H_}, s2(), n1, Mat(), 0, false);
+    launch_mul_dact(dzmu_, zmu_, (size_t)B_ * D_, DACT_TANH_OUT, s1);
+    linear_wgrad(gemm_, s1, B_, Mat{dzmu_, D_}, Mat{g2_, H_}, n3, Mat(), 0, false);
+    linear_dgrad(gemm_, s1, B_, Mat{dzmu_, D_}, n3, DACT_ELU_OUT, Mat{g2_, H_}, dg2_, H_);
+    linear_wgrad(gemm_, s1, B_, Mat{dg2_, H_}, Mat{g1_, H_}, n2, Mat(), 0, false);
+    linear_dgrad(gemm_, s1, B_, Mat{dg2_, H_}, n2, DACT_ELU_OUT, Mat{g1_, H_}, dg1_, H_);
+    linear_wgrad(gemm_, s1, B_, Mat{dg1_, H_}, s2(), n1, Mat(), 0, false);
     {
       ColJob jobs[3] = {bias_job(B_, Mat{dzmu_, D_}, n3), bias_job(B_, Mat{dg2_, H_}, n2),
                         bias_job(B_, Mat{dg1_, H_}, n1)};
-      launch_colreduce_multi(jobs, 3, s);
+      launch_colreduce_multi(jobs, 3, s1);
     }
+    join();
     comm_->all_reduce(feat_g_.g, feat_g_.n, s);
     launch_adam_polyak(feat_g_.p, feat_g_.g, feat_g_.m, feat_g_.v, feat_g_.n, &ctl->feat[k],
                        cfg.use_feature_target ? feat_g_.target : nullptr, feat_g_.n_target, cfg.feature_tau, nullptr, s);

@@ -431,7 +431,7 @@ int rlrep_agent_profile_train(rlrep_agent* agent, rlrep_ring* ring, const int64_
                               int max_entries, const char** names, float* ms, double* bytes, double* flops,
                               int* n_entries) {
   RLREP_API_BEGIN
-  RLREP_CHECK(agent && ring && idx_host && eps_host && names && ms && n_entries, "null argument");
+  RLREP_CHECK(agent && ring && idx_host && eps_host && n_entries && (max_entries == 0 || (names && ms)), "null argument");
   std::vector<ProfileEntry> prof =
       agent->impl->profile_train(*ring->impl, reinterpret_cast<const long long*>(idx_host), eps_host);
   const int n = (int)std::min<size_t>(prof.size(), (size_t)max_entries);

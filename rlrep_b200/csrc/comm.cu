@@ -100,14 +100,18 @@ int Comm::version() {
 void Comm::all_gather(const float* send, float* recv, size_t count_per_rank, cudaStream_t s) {
   check(nccl().AllGather(send, recv, count_per_rank, kNcclFloat32, comm_, s), "ncclAllGather");
   ++collectives;
+  // profile entries named nccl_* are NCCL's kernels, not this library's; bytes = what this rank receives over NVLink
+  note_launch("nccl_all_gather", s, 4.0 * (double)count_per_rank * (world - 1), 0.0);
 }
 void Comm::reduce_scatter(const float* send, float* recv, size_t recv_count, cudaStream_t s) {
   check(nccl().ReduceScatter(send, recv, recv_count, kNcclFloat32, kNcclSum, comm_, s), "ncclReduceScatter");
   ++collectives;
+  note_launch("nccl_reduce_scatter", s, 4.0 * (double)recv_count * (world - 1), 0.0);
 }
 void Comm::all_reduce(float* buf, size_t count, cudaStream_t s) {
   check(nccl().AllReduce(buf, buf, count, kNcclFloat32, kNcclSum, comm_, s), "ncclAllReduce");
   ++collectives;
+  note_launch("nccl_all_reduce", s, 2.0 * 4.0 * (double)count * (world - 1) / world, 0.0);
 }
 
 }  // namespace rlrep
