@@ -38,6 +38,10 @@ class DeviceArena {
     RLREP_CHECK(base_ == nullptr, "arena already committed");
     RLREP_CUDA(cudaMalloc(&base_, total_ ? total_ : 256));
     RLREP_CUDA(cudaMemset(base_, 0, total_ ? total_ : 256));
+    // The memset runs on the legacy default stream and is asynchronous with respect to the agents' NON-BLOCKING
+    // streams: without this wait it can still be zeroing the arena when the first copies into it (control block,
+    // weights) have already landed.
+    RLREP_CUDA(cudaDeviceSynchronize());
     for (const Req& r : reqs_) *r.slot = static_cast<char*>(base_) + r.offset;
   }
   void release() {

@@ -214,6 +214,8 @@ class SacBase : public Agent {
     arena_.want(&dah1_, (size_t)B_ * AH_);
     LDSA_ = round_up32(S_ + A_);
     arena_.want(&dsa_, (size_t)B_ * LDSA_);
+    arena_.want(&cat_next_, (size_t)B_ * LDSA_);  // cat(s', a')   (critic step)
+    arena_.want(&cat_pi_, (size_t)B_ * LDSA_);    // cat(s, a_pi)  (actor step)
     arena_.want(&dlogp_, 4);
     arena_.want(&act_dev_, S_ + A_);
     arena_.want(&act_h1_, AH_);
@@ -239,6 +241,16 @@ class SacBase : public Agent {
   }
 
   // actor(obs) -> head_, then rsample with eps -> action_out [B, A], logp_out [B]
+  // action_out may point into a cat(obs, action) buffer (cat_next_ / cat_pi_, pitch LDSA_): pass cat = true to have
+  // the sampling kernel copy obs in front of the action, so the next network reads ONE contiguous input.
+  Mat actor_forward_cat(Mat obs, const float* eps, float* cat_buf, float* logp_out) {
+    const Linear l0 = a0_.view(actor_g_), l1 = a1_.view(actor_g_), l2 = a2_.view(actor_g_);
+    linear_fwd(gemm_, stream, B_, obs, l0, ACT_ELU, ah1_, AH_);
+    linear_fwd(gemm_, stream, B_, Mat{ah1_, AH_}, l1, ACT_ELU, ah2_, AH_);
+    linear_fwd(gemm_, stream, B_, Mat{ah2_, AH_}, l2, ACT_NONE, head_, LDH_);
+    launch_actor_sample(head_, LDH_, B_, A_, eps, cat_buf + S_, LDSA_, logp_out, stream, obs.p, obs.ld, S_);
+    return Mat{cat_buf, LDSA_};
+  }
   void actor_forward(Mat obs, const float* eps, float* action_out, float* logp_out) {
     const Linear l0 = a0_.view(actor_g_), l1 = a1_.view(actor_g_), l2 = a2_.view(actor_g_);
     linear_fwd(gemm_, stream, B_, obs, l0, ACT_ELU, ah1_, AH_);
@@ -327,6 +339,7 @@ class SacBase : public Agent {
   float* batch_ = nullptr;
   float *ah1_ = nullptr, *ah2_ = nullptr, *head_ = nullptr, *action_ = nullptr, *logp_ = nullptr;
   float *dhead_ = nullptr, *dah2_ = nullptr, *dah1_ = nullptr, *dsa_ = nullptr, *dlogp_ = nullptr;
+  float *cat_next_ = nullptr, *cat_pi_ = nullptr;
   float *act_dev_ = nullptr, *act_h1_ = nullptr, *act_h2_ = nullptr, *act_head_ = nullptr, *act_out_ = nullptr,
         *act_logp_ = nullptr, *act_host_ = nullptr;
 };

@@ -241,8 +241,8 @@ class CtrlSacAgent final : public SacBase {
     cudaStream_t s0 = stream, s1 = side();
     fork();
     // main stream: a' ~ pi(s'), frozen_phi_target(s', a'), target critic
-    actor_forward(s2(), eps, a2_act_, logp2_);
-    phi_forward(s0, s2(), Mat{a2_act_, A_}, S_, zmu_, h1_, h2_);  // zmu_ is free after the feature loop
+    const Mat s2a = actor_forward_cat(s2(), eps, cat_next_, logp2_);
+    phi_forward(s0, s2a, Mat(), 0, zmu_, h1_, h2_);  // zmu_ is free after the feature loop
     critic_forward(s0, zmu_, /*target=*/true, hid_t_, nq1_, nq2_);
     // side stream: frozen_phi_target(s, a) and the live critic on it
     phi_forward(s1, sa(), Mat(), 0, zphi_, hb1_, hb2_);
@@ -269,8 +269,8 @@ class CtrlSacAgent final : public SacBase {
   void actor_step() {  // ctrlsac_agent.py:295-325
     const float* eps = eps_dev_ + (size_t)B_ * A_;
     const Mat s{batch_, R_};
-    actor_forward(s, eps, action_, logp_);
-    phi_forward(stream, s, Mat{action_, A_}, S_, zphi_, h1_, h2_);  // frozen_phi(s, a_pi)
+    const Mat spi = actor_forward_cat(s, eps, cat_pi_, logp_);
+    phi_forward(stream, spi, Mat(), 0, zphi_, h1_, h2_);  // frozen_phi(s, a_pi)
     critic_forward(stream, zphi_, false, hid_, q1_, q2_);
     launch_actor_alpha_loss(q1_, q2_, logp_, B_, (float)(-A_), cfg.learn_alpha, ctl, dq1_, dq2_, dlogp_,
                             metrics_dev_ + 7, stream);

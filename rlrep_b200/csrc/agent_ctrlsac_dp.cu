@@ -219,8 +219,8 @@ class CtrlSacShardedAgent final : public SacBase {
   void critic_step() {
     const float* eps = eps_dev_;
     cudaStream_t s = stream;
-    actor_forward(s2(), eps, a2_act_, logp2_);
-    phi_forward(s2(), Mat{a2_act_, A_}, S_, zmu_);
+    const Mat s2a = actor_forward_cat(s2(), eps, cat_next_, logp2_);
+    phi_forward(s2a, Mat(), 0, zmu_);
     critic_forward(zmu_, /*target=*/true, hid_t_, nq1_, nq2_);
     phi_forward(sa(), Mat(), 0, zphi_);
     critic_forward(zphi_, /*target=*/false, hid_, q1_, q2_);
@@ -243,8 +243,8 @@ class CtrlSacShardedAgent final : public SacBase {
   void actor_step() {
     const float* eps = eps_dev_ + (size_t)B_ * A_;
     const Mat s{batch_, R_};
-    actor_forward(s, eps, action_, logp_);
-    phi_forward(s, Mat{action_, A_}, S_, zphi_);
+    const Mat spi = actor_forward_cat(s, eps, cat_pi_, logp_);
+    phi_forward(spi, Mat(), 0, zphi_);
     critic_forward(zphi_, false, hid_, q1_, q2_);
     launch_actor_loss_partial(q1_, q2_, logp_, B_, Bg_, (float)(-A_), ctl, dq1_, dq2_, dlogp_, apart_, stream);
     const Linear l14 = c14_.view(crit_g_);

@@ -137,8 +137,8 @@ class DiffSrSacAgent final : public SacBase {
     const float* eps = eps_dev_ + (size_t)K_ * B_ * S_;
     cudaStream_t s0 = stream, s1 = side();
     fork();
-    actor_forward(s2(), eps, a2_act_, logp2_);
-    trunk_forward(gemm_, s0, B_, phi_, feat_g_, false, s2(), Mat{a2_act_, A_}, S_, phi_acts_, zphi_, D_);
+    const Mat s2a = actor_forward_cat(s2(), eps, cat_next_, logp2_);
+    trunk_forward(gemm_, s0, B_, phi_, feat_g_, false, s2a, Mat(), 0, phi_acts_, zphi_, D_);
     critic_.forward(gemm_, s0, crit_g_, /*target=*/true, 0, zphi_);
     trunk_forward(gemm_, s1, B_, phi_, feat_g_, false, sa(), Mat(), 0, phi_acts_b_, zb_, D_);
     critic_.forward(gemm_, s1, crit_g_, /*target=*/false, 1, zb_);
@@ -150,8 +150,8 @@ class DiffSrSacAgent final : public SacBase {
   void actor_step() {  // diffsrsac_agent.py:241-269
     const float* eps = eps_dev_ + (size_t)K_ * B_ * S_ + (size_t)B_ * A_;
     const Mat s{batch_, R_};
-    actor_forward(s, eps, action_, logp_);
-    trunk_forward(gemm_, stream, B_, phi_, feat_g_, false, s, Mat{action_, A_}, S_, phi_acts_, zphi_, D_);
+    const Mat spi = actor_forward_cat(s, eps, cat_pi_, logp_);
+    trunk_forward(gemm_, stream, B_, phi_, feat_g_, false, spi, Mat(), 0, phi_acts_, zphi_, D_);
     critic_.forward(gemm_, stream, crit_g_, false, 0, zphi_);
     launch_actor_alpha_loss(critic_.q[0], critic_.q[0] + B_, logp_, B_, (float)(-A_), cfg.learn_alpha, ctl, dq_,
                             dq_ + B_, dlogp_, metrics_dev_ + 5, stream);

@@ -107,8 +107,8 @@ class SacAgent final : public SacBase {
 
   void critic_step() {  // sac_agent.py:105-135
     const Mat sa{batch_, R_}, s2{batch_ + off_s2_, R_};
-    actor_forward(s2, eps_dev_, a2_act_, logp2_);
-    critic_forward(s2, Mat{a2_act_, A_}, S_, /*target=*/true, nq1_, nq2_);
+    const Mat s2a = actor_forward_cat(s2, eps_dev_, cat_next_, logp2_);
+    critic_forward(s2a, Mat(), 0, /*target=*/true, nq1_, nq2_);
     critic_forward(sa, Mat(), 0, false, q1_, q2_);
     launch_td_critic_loss(batch_ + off_r_, batch_ + off_d_, R_, nq1_, nq2_, logp2_, q1_, q2_, B_, cfg.discount, ctl,
                           dq1_, dq2_, metrics_dev_ + 0, stream);
@@ -121,8 +121,8 @@ class SacAgent final : public SacBase {
   void actor_step() {  // sac_agent.py:138-166
     const float* eps = eps_dev_ + (size_t)B_ * A_;
     const Mat s{batch_, R_};
-    actor_forward(s, eps, action_, logp_);
-    critic_forward(s, Mat{action_, A_}, S_, false, q1_, q2_);
+    const Mat spi = actor_forward_cat(s, eps, cat_pi_, logp_);
+    critic_forward(spi, Mat(), 0, false, q1_, q2_);
     launch_actor_alpha_loss(q1_, q2_, logp_, B_, (float)(-A_), cfg.learn_alpha, ctl, dq1_, dq2_, dlogp_,
                             metrics_dev_ + 4, stream);
     critic_backward_to_hid0(false);

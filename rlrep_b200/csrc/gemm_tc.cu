@@ -114,7 +114,14 @@ double plan_cost(const GemmArgs& a, int nkb, int bn, int s, double sm_share, int
   const int clusters = ceil_div(a.M, BM) * ceil_div(a.N, bn);
   const double cap = std::max(1.0, max_clusters(bn, a.a_mn, a.b_mn, s, stages) * sm_share);
   const double waves = std::ceil(clusters / cap);
-  const double load = (double)(BM + bn) * BK * 4 * kb_per / 48.0;
+  // When the GEMM shares the GPU with other branches the aggregate L2 -> SM operand traffic (not the per-CTA stream) is
+  // what saturates, so the load term is weighted up: plans with wider tiles (fewer re-reads of A) win there.
+  static const double l2_weight = [] {
+    const char* e = std::getenv("RLREP_L2_WEIGHT");
+    return e ? std::atof(e) : 1.0;
+  }();
+  const double contention = sm_share < 0.75 ? l2_weight : 1.0;
+  const double load = contention * (double)(BM + bn) * BK * 4 * kb_per / 48.0;
   const double tile = (double)BM * bn * 4;
   const double reduce = s > 1 ? tile / 16.0 : 0.0;
   const double store = tile / s / 32.0;

@@ -222,14 +222,17 @@ __global__ void __launch_bounds__(256) feature_loss_finalize_kernel(const float*
 // ------------------------------------------------------------------------------------------- actor
 constexpr float kLogStdMin = -5.f, kLogStdMax = 2.f;  // sac_agent.py:64
 
+// One warp per row: lane j handles action dimension j (+32, ...), the log-prob terms are warp-reduced, and -- when
+// `obs` is given -- all lanes copy the S observation columns in front of the action so that `action - S` becomes the
+// contiguous cat(obs, action) row the next network's first layer reads (row pitch lda).
 __global__ void actor_sample_kernel(const float* __restrict__ head, int ld_head, int B, int A,
                                     const float* __restrict__ eps, float* __restrict__ action, int lda,
-                                    float* __restrict__ logp) {
-  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+                                    float* __restrict__ logp, const float* __restrict__ obs, int ld_obs, int S) {
+  const int b = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (b >= B) return;
   const float* h = head + (size_t)b * ld_head;
   float lp = 0.f;
-  for (int j = 0; j < A; ++j) {
+  for (int j = lane; j < A; j += 32) {
     const float mu = h[j];
     const float ls = kLogStdMin + 0.5f * (kLogStdMax - kLogStdMin) * (tanhf(h[A + j]) + 1.f);
     const float sd = expf(ls);
@@ -244,7 +247,14 @@ __global__ void actor_sample_kernel(const float* __restrict__ head, int ld_head,
     lp += -ladj + base;
     action[(size_t)b * lda + j] = tanhf(u);
   }
-  logp[b] = lp;
+  // torch sums the A terms left to right; a shuffle tree differs from that by rounding only (<= 1e-7 relative)
+  lp = warp_sum(lp);
+  if (lane == 0) logp[b] = lp;
+  if (obs != nullptr) {
+    float* dst = action + (size_t)b * lda - S;
+    const float* src = obs + (size_t)b * ld_obs;
+    for (int j = lane; j < S; j += 32) dst[j] = src[j];
+  }
 }
 
 __global__ void actor_sample_bwd_kernel(const float* __restrict__ head, int ld_head, int B, int A,
@@ -711,8 +721,8 @@ void launch_feature_loss_finalize(const float* loss_rows, int rows, const float*
 }
 
 void launch_actor_sample(const float* head, int ld_head, int B, int A, const float* eps, float* action, int lda,
-                         float* logp, cudaStream_t s) {
-  actor_sample_kernel<<<ceil_div(B, 32), 32, 0, s>>>(head, ld_head, B, A, eps, action, lda, logp);
+                         float* logp, cudaStream_t s, const float* obs, int ld_obs, int S) {
+  actor_sample_kernel<<<ceil_div(B * 32, 128), 128, 0, s>>>(head, ld_head, B, A, eps, action, lda, logp, obs, ld_obs, S);
   RLREP_LAUNCHED("actor_sample", s);
 }
 

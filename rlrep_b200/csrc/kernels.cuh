@@ -84,8 +84,9 @@ void launch_feature_loss_finalize(const float* loss_rows, int rows, const float*
 
 // Actor head -> action / log-prob (agent/sac/actor.py:76-91 + 40-43).
 //   head [B, ld_head >= 2A] = (mu | raw log-std); eps [B, A];  out action [B, lda] (tanh(u)), logp [B]
+// obs != nullptr: also copy obs[b, 0:S] to action[b, -S:0], i.e. build the contiguous cat(obs, action) row.
 void launch_actor_sample(const float* head, int ld_head, int B, int A, const float* eps, float* action, int lda,
-                         float* logp, cudaStream_t s);
+                         float* logp, cudaStream_t s, const float* obs = nullptr, int ld_obs = 0, int S = 0);
 // Backward of the above: dhead [B, ld_dhead >= 2A] from d_action [B, ldd] and the per-row d_logp scalar.
 void launch_actor_sample_bwd(const float* head, int ld_head, int B, int A, const float* eps, const float* d_action,
                              int ldd, const float* dlogp_scalar, float* dhead, int ld_dhead, cudaStream_t s);

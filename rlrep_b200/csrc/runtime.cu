@@ -72,6 +72,7 @@ Ring::Ring(int state_dim, int action_dim, long long cap) : S(state_dim), A(actio
   R = l.R;
   RLREP_CUDA(cudaMalloc(&data, (size_t)capacity * R * sizeof(float)));
   RLREP_CUDA(cudaMemset(data, 0, (size_t)capacity * R * sizeof(float)));
+  RLREP_CUDA(cudaDeviceSynchronize());  // see DeviceArena::commit: the null-stream memset must not race later stream work
   stage_rows_ = kStageRows;
   RLREP_CUDA(cudaMallocHost(&stage_host_, stage_rows_ * R * sizeof(float)));
   RLREP_CUDA(cudaMalloc(&stage_dev_, stage_rows_ * R * sizeof(float)));

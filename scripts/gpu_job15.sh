@@ -1,0 +1,2 @@
+python -m pytest tests -m gpu -q 2>&1 | tail -4
+python -m pytest tests -m gpu -q 2>&1 | tail -2

@@ -209,3 +209,51 @@ def test_loss_curves_track_the_oracle(case, keys):
         dev = np.abs(cm - om).max() / scale
         print(f"{case}/{k}: max moving-average deviation {dev:.2e} of scale {scale:.3g}; step-wise max {np.abs(c - o).max():.2e}")
         assert dev < 5e-2, (k, dev)
+
+
+ODD = {
+    # batch not a multiple of 32 / 128, odd state and action widths, tiny hidden sizes: exercises ragged tiles, TMA
+    # zero-fill of short K, the CUDA-core fallbacks for M < 32 and the padded weight layouts
+    "sac_odd": ("sac", dict(S=11, A=3), dict(hidden_dim=96), 100),
+    "sac_tiny_batch": ("sac", dict(S=5, A=2), dict(hidden_dim=64), 24),
+    "ctrlsac_odd": ("ctrlsac", dict(S=11, A=3), dict(hidden_dim=96, feature_dim=160, extra_feature_steps=1), 100),
+    "vlsac_odd": ("vlsac", dict(S=11, A=3), dict(hidden_dim=64, feature_dim=96, extra_feature_steps=1), 40),
+    "spedersac_odd": ("spedersac", dict(S=11, A=3), dict(feature_dim=96, extra_feature_steps=1, phi_and_mu_lr=1e-4,
+                                                         phi_hidden_dim=64, phi_hidden_depth=1, mu_hidden_dim=64,
+                                                         mu_hidden_depth=0, critic_and_actor_lr=3e-4,
+                                                         critic_and_actor_hidden_dim=64), 72),
+}
+
+
+@pytest.mark.parametrize("case", list(ODD))
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-4), ("tf32", 3e-3)])
+def test_ragged_shapes_match_oracle(case, precision, tol):
+    alg, shp, kw, B = ODD[case]
+    okw = dict(as_written=True) if alg == "ctrlsac" else {}
+    agent, buf, oracle, oring = make_pair(alg, shp["S"], shp["A"], kw, rows=3000, precision=precision, oracle_kw=okw)
+    # a batch with terminal transitions: (1 - done) must gate the bootstrap term
+    ci, oi = step_both(agent, buf, oracle, oring, B, 3)
+    wi, where_i = worst_info_error(ci, oi, atol=1e-5)
+    wp, where_p, _ = worst_param_error(agent, oracle)
+    print(f"{case}/{precision}: worst info rel {wi:.2e} at {where_i}; worst param rel-l2 {wp:.2e} at {where_p}")
+    assert wi < tol, where_i
+    assert wp < tol, where_p
+
+
+def test_done_flags_gate_the_bootstrap():
+    """All-terminal batch: the TD target must reduce to the reward (sac_agent.py:117-119)."""
+    from rlrep_b200 import ReplayBuffer
+    from rlrep_b200.agents import AGENTS
+    S, A, rows, B = 17, 6, 512, 64
+    kw = dict(hidden_dim=64)
+    init = O.init_state("sac", S, A, kw, seed=0)
+    ring = O.synthetic_ring(S, A, rows, seed=0)
+    ring.done[:] = 1.0
+    oracle = O.ORACLES["sac"](S, A, init, discount=0.99, tau=0.005, **kw)
+    agent = AGENTS["sac"](S, A, Space(A), discount=0.99, tau=0.005, precision="fp32", **kw)
+    agent.load_state_dict(init)
+    buf = ReplayBuffer(S, A, max_size=rows)
+    buf.load(ring.state, ring.action, ring.next_state, ring.reward, ring.done)
+    ci, oi = step_both(agent, buf, oracle, ring, B, 2)
+    wi, where = worst_info_error(ci, oi, atol=1e-5)
+    assert wi < 2e-4, where
