@@ -190,6 +190,26 @@ RLREP_EXPORT int rlrep_agent_train_resident(rlrep_agent* agent, rlrep_ring* ring
 RLREP_EXPORT int rlrep_agent_profile_train(rlrep_agent* agent, rlrep_ring* ring, const int64_t* idx_host,
                                            const float* eps_host, int max_entries, const char** names, float* ms,
                                            double* bytes, double* flops, int* n_entries);
+/* ------------------------------------------------------------------------------------------------
+ * DrQ-v2 pixel encoder -- replaces `Encoder.forward` / its autograd backward and `RandomShiftsAug`
+ * (agent/diffsrdrq/network_arch/drqv2.py:21-57,138-167; agent/mulvdrq/drqv2.py:19-96).  First building block of the
+ * pixel agents; the agents themselves are not assembled yet.
+ * Layer l = 0..3 is `convnet.{2l}`; weights are exchanged in the reference's layout [32, C_in, 3, 3] / [32].
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rlrep_conv_encoder rlrep_conv_encoder;
+RLREP_EXPORT int rlrep_conv_encoder_create(int batch, int in_channels, int height, int precision, void* stream,
+                                           rlrep_conv_encoder** out);
+RLREP_EXPORT int rlrep_conv_encoder_destroy(rlrep_conv_encoder* enc);
+/* what: 0 = weight, 1 = bias, 2 = weight gradient, 3 = bias gradient (host buffers, reference layout) */
+RLREP_EXPORT int rlrep_conv_encoder_read(rlrep_conv_encoder* enc, int layer, int what, float* out_host);
+RLREP_EXPORT int rlrep_conv_encoder_write(rlrep_conv_encoder* enc, int layer, int what, const float* in_host);
+/* obs_dev uint8 [B, C, H, H]; shifts_dev int32 [B, 2] = (x, y) shift in [0, 8] or NULL; feat_dev fp32 [B, 32*35*35] in
+ * the reference's flatten order.  backward consumes d(feat) of the same shape and leaves dW / db readable. */
+RLREP_EXPORT int rlrep_conv_encoder_forward(rlrep_conv_encoder* enc, const unsigned char* obs_dev, const int* shifts_dev,
+                                            float* feat_dev);
+RLREP_EXPORT int rlrep_conv_encoder_backward(rlrep_conv_encoder* enc, const float* dfeat_dev);
+RLREP_EXPORT int rlrep_conv_encoder_feature_dim(rlrep_conv_encoder* enc, int* dim);
+
 /* Kernels launched by the most recent train() (a graph replay counts the kernels it contains). */
 RLREP_EXPORT int rlrep_agent_last_launches(rlrep_agent* agent, int* launches);
 

@@ -83,6 +83,13 @@ def _declare(lib: C.CDLL) -> None:
         "rlrep_ring_gather": [vp, vp, i, vp, vp],
         "rlrep_agent_create": [C.POINTER(AgentConfig), vp, C.POINTER(vp)],
         "rlrep_agent_destroy": [vp],
+        "rlrep_conv_encoder_create": [i, i, i, i, vp, C.POINTER(vp)],
+        "rlrep_conv_encoder_destroy": [vp],
+        "rlrep_conv_encoder_read": [vp, i, i, vp],
+        "rlrep_conv_encoder_write": [vp, i, i, vp],
+        "rlrep_conv_encoder_forward": [vp, vp, vp, vp],
+        "rlrep_conv_encoder_backward": [vp, vp],
+        "rlrep_conv_encoder_feature_dim": [vp, C.POINTER(i)],
         "rlrep_comm_unique_id": [vp],
         "rlrep_comm_create": [vp, i, i, C.POINTER(vp)],
         "rlrep_comm_destroy": [vp],

@@ -8,6 +8,7 @@
 #include "agent.cuh"
 #include "comm.cuh"
 #include "common.cuh"
+#include "conv.cuh"
 #include "gemm.cuh"
 #include "rlrep_b200.h"
 
@@ -229,6 +230,107 @@ int rlrep_ring_gather(rlrep_ring* ring, const int64_t* idx_host, int B, float* o
 }
 
 // ------------------------------------------------------------------------------------------------ agents
+// ------------------------------------------------------------------------------------------------ pixel encoder
+struct rlrep_conv_encoder {
+  std::unique_ptr<ConvEncoder> impl;
+  cudaStream_t owned_stream = nullptr;
+};
+
+// Reference layout [32, C, 3, 3] <-> stored layout: layer 0 as is, layers 1-3 as [32, (ky, kx, c)].
+static void conv_layout(int layer, int k, bool to_stored, const float* in, float* out) {
+  if (layer == 0) {
+    std::copy(in, in + (size_t)32 * k, out);
+    return;
+  }
+  for (int o = 0; o < 32; ++o)
+    for (int c = 0; c < 32; ++c)
+      for (int t = 0; t < 9; ++t) {
+        const size_t ref = ((size_t)o * 32 + c) * 9 + t, st = (size_t)o * 288 + (size_t)t * 32 + c;
+        if (to_stored) out[st] = in[ref];
+        else out[ref] = in[st];
+      }
+}
+
+int rlrep_conv_encoder_create(int batch, int in_channels, int height, int precision, void* stream,
+                              rlrep_conv_encoder** out) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(out != nullptr, "null out pointer");
+  std::unique_ptr<rlrep_conv_encoder> h(new rlrep_conv_encoder);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (st == nullptr) {
+    RLREP_CUDA(cudaStreamCreateWithFlags(&h->owned_stream, cudaStreamNonBlocking));
+    st = h->owned_stream;
+  }
+  h->impl.reset(new ConvEncoder(batch, in_channels, height, static_cast<Precision>(precision), st));
+  *out = h.release();
+  RLREP_API_END
+}
+int rlrep_conv_encoder_destroy(rlrep_conv_encoder* enc) {
+  RLREP_API_BEGIN
+  if (enc) {
+    if (enc->impl) cudaStreamSynchronize(enc->impl->stream());
+    enc->impl.reset();
+    if (enc->owned_stream) cudaStreamDestroy(enc->owned_stream);
+  }
+  delete enc;
+  RLREP_API_END
+}
+int rlrep_conv_encoder_read(rlrep_conv_encoder* enc, int layer, int what, float* out_host) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(enc && out_host && layer >= 0 && layer < 4 && what >= 0 && what < 4, "bad argument");
+  const Linear l = enc->impl->layer(layer);
+  const int k = enc->impl->layer_k(layer);
+  cudaStream_t st = enc->impl->stream();
+  if (what == 1 || what == 3) {
+    RLREP_CUDA(cudaMemcpyAsync(out_host, what == 1 ? l.b : l.db, 32 * sizeof(float), cudaMemcpyDeviceToHost, st));
+    RLREP_CUDA(cudaStreamSynchronize(st));
+  } else {
+    std::vector<float> tmp((size_t)32 * k);
+    RLREP_CUDA(cudaMemcpy2DAsync(tmp.data(), (size_t)k * 4, what == 0 ? l.W : l.dW, (size_t)l.ld * 4, (size_t)k * 4, 32,
+                                 cudaMemcpyDeviceToHost, st));
+    RLREP_CUDA(cudaStreamSynchronize(st));
+    conv_layout(layer, k, false, tmp.data(), out_host);
+  }
+  RLREP_API_END
+}
+int rlrep_conv_encoder_write(rlrep_conv_encoder* enc, int layer, int what, const float* in_host) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(enc && in_host && layer >= 0 && layer < 4 && (what == 0 || what == 1), "bad argument");
+  const Linear l = enc->impl->layer(layer);
+  const int k = enc->impl->layer_k(layer);
+  cudaStream_t st = enc->impl->stream();
+  if (what == 1) {
+    RLREP_CUDA(cudaMemcpyAsync(l.b, in_host, 32 * sizeof(float), cudaMemcpyHostToDevice, st));
+  } else {
+    std::vector<float> tmp((size_t)32 * k);
+    conv_layout(layer, k, true, in_host, tmp.data());
+    RLREP_CUDA(cudaMemcpy2DAsync(l.W, (size_t)l.ld * 4, tmp.data(), (size_t)k * 4, (size_t)k * 4, 32,
+                                 cudaMemcpyHostToDevice, st));
+    RLREP_CUDA(cudaStreamSynchronize(st));
+  }
+  RLREP_CUDA(cudaStreamSynchronize(st));
+  RLREP_API_END
+}
+int rlrep_conv_encoder_forward(rlrep_conv_encoder* enc, const unsigned char* obs_dev, const int* shifts_dev,
+                               float* feat_dev) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(enc && obs_dev && feat_dev, "null argument");
+  enc->impl->forward(obs_dev, shifts_dev, feat_dev);
+  RLREP_API_END
+}
+int rlrep_conv_encoder_backward(rlrep_conv_encoder* enc, const float* dfeat_dev) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(enc && dfeat_dev, "null argument");
+  enc->impl->backward(dfeat_dev);
+  RLREP_API_END
+}
+int rlrep_conv_encoder_feature_dim(rlrep_conv_encoder* enc, int* dim) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(enc && dim, "null argument");
+  *dim = enc->impl->feature_dim();
+  RLREP_API_END
+}
+
 // ------------------------------------------------------------------------------------------------ communicator
 int rlrep_comm_unique_id(unsigned char* out128) {
   RLREP_API_BEGIN

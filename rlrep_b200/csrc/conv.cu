@@ -1,0 +1,177 @@
+// DrQ-v2 pixel encoder (reference: agent/diffsrdrq/network_arch/drqv2.py:21-57,138-167; the same 4-conv stack is
+// agent/mulvdrq/drqv2.py:52-96): RandomShiftsAug (replicate-pad 4 + integer shift) -> x / 255 - 0.5 ->
+// Conv 3x3 s2 (C -> 32) + ReLU -> 3 x [Conv 3x3 s1 (32 -> 32) + ReLU] -> flatten, forward and backward.
+//
+// First building block of the pixel agents (kernel K15).  Version 1 is a lowering onto
+// the library's tcgen05 GEMM: activations are kept NHWC ([B, H, W, 32] == a row-major [B*H*W, 32] matrix, so a GEMM
+// output IS the next layer's activation), each layer is   im2col (explicit, fp32)  ->  GEMM [B*Ho*Wo, 9*Cin] x [32, 9*Cin]^T
+// with the bias + ReLU epilogue; the backward pass is  wgrad = dY^T col,  dcol = dY W,  col2im (gather form, fused with
+// the ReLU mask of the layer below).  The augmentation, the uint8 -> float conversion and the normalisation are fused
+// into the first im2col, so the frames are read once as bytes.  The explicit column matrices cost ~10x the algorithmic
+// HBM traffic of the convolutions; replacing them with TMA im2col loads inside the GEMM's producer is the planned v2.
+#include "conv.cuh"
+
+#include <algorithm>
+
+namespace rlrep {
+
+namespace {
+
+constexpr int kPad = 4;  // RandomShiftsAug(pad=4)
+
+__global__ void im2col_u8_aug_kernel(const unsigned char* __restrict__ obs, const int* __restrict__ shifts, int B, int C,
+                                     int H, int Ho, float* __restrict__ col, int ldk) {
+  // one thread per (output pixel, k): k = c * 9 + ky * 3 + kx  (the reference's weight layout [32, C, 3, 3] flattened)
+  const int K = C * 9;
+  const long long total = (long long)B * Ho * Ho * ldk;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % ldk);
+    const long long row = i / ldk;
+    float v = 0.f;
+    if (k < K) {
+      const int ox = (int)(row % Ho), oy = (int)((row / Ho) % Ho), b = (int)(row / ((long long)Ho * Ho));
+      const int c = k / 9, ky = (k % 9) / 3, kx = k % 3;
+      int iy = 2 * oy + ky, ix = 2 * ox + kx;
+      if (shifts != nullptr) {  // padded[i + sy, j + sx] with replicate padding == clamp(i + sy - pad)
+        ix = min(max(ix + shifts[2 * b] - kPad, 0), H - 1);
+        iy = min(max(iy + shifts[2 * b + 1] - kPad, 0), H - 1);
+      }
+      const float p = (float)obs[(((long long)b * C + c) * H + iy) * H + ix];
+      v = __fsub_rn(__fdiv_rn(p, 255.0f), 0.5f);  // obs / 255.0 - 0.5, op by op like torch
+    }
+    col[i] = v;
+  }
+}
+
+// act [B, H, H, 32] -> col [B*Ho*Ho, 288], k = (ky*3 + kx) * 32 + c; one float4 per thread (8 per tap)
+__global__ void im2col_nhwc32_kernel(const float4* __restrict__ act, int B, int H, int Ho, float4* __restrict__ col) {
+  const long long total = (long long)B * Ho * Ho * 72;  // 288 / 4 float4 per row
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % 72);
+    const long long row = i / 72;
+    const int tap = q >> 3, c4 = q & 7;
+    const int ky = tap / 3, kx = tap % 3;
+    const int ox = (int)(row % Ho), oy = (int)((row / Ho) % Ho), b = (int)(row / ((long long)Ho * Ho));
+    col[i] = act[(((long long)b * H + oy + ky) * H + ox + kx) * 8 + c4];
+  }
+}
+
+// dX[b, iy, ix, c] = relu'(X) * sum over taps of dcol[(b, iy - ky, ix - kx), tap, c]   (gather form: deterministic)
+__global__ void col2im_nhwc32_kernel(const float4* __restrict__ dcol, const float4* __restrict__ x, int B, int H, int Ho,
+                                     float4* __restrict__ dx) {
+  const long long total = (long long)B * H * H * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i & 7);
+    const long long pix = i >> 3;
+    const int ix = (int)(pix % H), iy = (int)((pix / H) % H), b = (int)(pix / ((long long)H * H));
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int oy = iy - ky;
+      if (oy < 0 || oy >= Ho) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int ox = ix - kx;
+        if (ox < 0 || ox >= Ho) continue;
+        const float4 g = dcol[(((long long)b * Ho + oy) * Ho + ox) * 72 + (ky * 3 + kx) * 8 + c4];
+        acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+      }
+    }
+    const float4 xv = x[i];
+    dx[i] = make_float4(xv.x > 0.f ? acc.x : 0.f, xv.y > 0.f ? acc.y : 0.f, xv.z > 0.f ? acc.z : 0.f,
+                        xv.w > 0.f ? acc.w : 0.f);
+  }
+}
+
+// NHWC [B, P, 32] <-> the reference's flatten order [B, 32, P] (P = Ho*Ho); the backward direction also applies the
+// ReLU mask of the last layer.
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, int B, int P, float* __restrict__ out) {
+  const long long total = (long long)B * P * 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % P);
+    const int c = (int)((i / P) % 32);
+    const long long b = i / ((long long)P * 32);
+    out[i] = in[(b * P + p) * 32 + c];
+  }
+}
+__global__ void nchw_to_nhwc_relu_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ act, int B, int P,
+                                             float* __restrict__ dact) {
+  const long long total = (long long)B * P * 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i & 31);
+    const long long bp = i >> 5;
+    const int p = (int)(bp % P);
+    const long long b = bp / P;
+    dact[i] = act[i] > 0.f ? dfeat[(b * 32 + c) * P + p] : 0.f;
+  }
+}
+
+int grid_for(long long work, int threads) {
+  const long long want = (work + threads - 1) / threads;
+  return (int)std::min<long long>(want, (long long)kNumSMs * 16);
+}
+
+}  // namespace
+
+ConvEncoder::ConvEncoder(int batch, int in_channels, int height, Precision prec, cudaStream_t s)
+    : B_(batch), C_(in_channels), H_(height), stream_(s) {
+  RLREP_CHECK(B_ > 0 && C_ > 0 && H_ >= 16, "bad encoder dimensions");
+  hw_[0] = (H_ - 3) / 2 + 1;  // 84 -> 41
+  for (int l = 1; l < 4; ++l) hw_[l] = hw_[l - 1] - 2;  // 39, 37, 35
+  K1_ = C_ * 9;
+  ldk1_ = round_up32(K1_);
+  g_.name = "encoder";
+  // layer 1 keeps the reference's [32, C*3*3] layout; layers 2-4 are stored [32, (ky, kx, c)] (permuted at the API)
+  conv_[0] = add_linear(g_, "convnet.0", 32, K1_);
+  for (int l = 1; l < 4; ++l) conv_[l] = add_linear(g_, "convnet." + std::to_string(2 * l), 32, 288);
+  g_.want(arena_);
+  arena_.want(&col_[0], rows(0) * ldk1_);
+  for (int l = 1; l < 4; ++l) arena_.want(&col_[l], rows(l) * 288);
+  for (int l = 0; l < 4; ++l) {
+    arena_.want(&act_[l], rows(l) * 32);
+    arena_.want(&dact_[l], rows(l) * 32);
+  }
+  arena_.want(&dcol_, rows(1) * 288);
+  arena_.want(&bias_partial_, kBiasChunks * 32);
+  arena_.commit();
+  gemm_.init(prec, 0);
+}
+
+void ConvEncoder::forward(const unsigned char* obs_dev, const int* shifts_dev, float* feat_dev) {
+  cudaStream_t s = stream_;
+  im2col_u8_aug_kernel<<<grid_for((long long)rows(0) * ldk1_, 256), 256, 0, s>>>(obs_dev, shifts_dev, B_, C_, H_, hw_[0],
+                                                                               col_[0], ldk1_);
+  RLREP_LAUNCHED_W("im2col_u8_aug", s, (double)B_ * C_ * H_ * H_ + 4.0 * rows(0) * ldk1_, 0.0);
+  linear_fwd(gemm_, s, (int)rows(0), Mat{col_[0], ldk1_}, conv_[0].view(g_), ACT_RELU, act_[0], 32);
+  for (int l = 1; l < 4; ++l) {
+    im2col_nhwc32_kernel<<<grid_for((long long)rows(l) * 72, 256), 256, 0, s>>>(
+        reinterpret_cast<const float4*>(act_[l - 1]), B_, hw_[l - 1], hw_[l], reinterpret_cast<float4*>(col_[l]));
+    RLREP_LAUNCHED_W("im2col_nhwc32", s, 4.0 * (rows(l - 1) * 32 + rows(l) * 288), 0.0);
+    linear_fwd(gemm_, s, (int)rows(l), Mat{col_[l], 288}, conv_[l].view(g_), ACT_RELU, act_[l], 32);
+  }
+  const int P = hw_[3] * hw_[3];
+  nhwc_to_nchw_kernel<<<grid_for((long long)B_ * P * 32, 256), 256, 0, s>>>(act_[3], B_, P, feat_dev);
+  RLREP_LAUNCHED_W("nhwc_to_nchw", s, 8.0 * B_ * P * 32, 0.0);
+}
+
+void ConvEncoder::backward(const float* dfeat_dev) {
+  cudaStream_t s = stream_;
+  const int P = hw_[3] * hw_[3];
+  nchw_to_nhwc_relu_bwd_kernel<<<grid_for((long long)B_ * P * 32, 256), 256, 0, s>>>(dfeat_dev, act_[3], B_, P, dact_[3]);
+  RLREP_LAUNCHED_W("nchw_to_nhwc_relu_bwd", s, 12.0 * B_ * P * 32, 0.0);
+  for (int l = 3; l >= 0; --l) {
+    const Linear w = conv_[l].view(g_);
+    const Mat dy{dact_[l], 32};
+    const Mat col = l == 0 ? Mat{col_[0], ldk1_} : Mat{col_[l], 288};
+    linear_wgrad(gemm_, s, (int)rows(l), dy, col, w, Mat(), 0, /*bias_grad=*/false);
+    launch_colsum_tall(dy.p, 32, rows(l), 32, bias_partial_, kBiasChunks, w.db, s);
+    if (l == 0) break;
+    linear_dgrad(gemm_, s, (int)rows(l), dy, w, DACT_NONE, Mat(), dcol_, 288);
+    col2im_nhwc32_kernel<<<grid_for((long long)rows(l - 1) * 8, 256), 256, 0, s>>>(
+        reinterpret_cast<const float4*>(dcol_), reinterpret_cast<const float4*>(act_[l - 1]), B_, hw_[l - 1], hw_[l],
+        reinterpret_cast<float4*>(dact_[l - 1]));
+    RLREP_LAUNCHED_W("col2im_nhwc32", s, 4.0 * (rows(l) * 288 + 2.0 * rows(l - 1) * 32), 0.0);
+  }
+}
+
+}  // namespace rlrep

@@ -1,0 +1,39 @@
+// DrQ-v2 pixel encoder handle (see conv.cu).
+#pragma once
+#include "agent.cuh"
+
+namespace rlrep {
+
+class ConvEncoder {
+ public:
+  ConvEncoder(int batch, int in_channels, int height, Precision prec, cudaStream_t s);
+  // obs uint8 [B, C, H, H] (device), shifts int32 [B, 2] = (x, y) in [0, 8] or nullptr (no augmentation);
+  // feat fp32 [B, 32 * 35 * 35] in the reference's flatten order (channel, row, column)
+  void forward(const unsigned char* obs_dev, const int* shifts_dev, float* feat_dev);
+  // dfeat [B, 32 * 35 * 35] -> dW / db of the four layers (activations of the last forward are reused)
+  void backward(const float* dfeat_dev);
+
+  int batch() const { return B_; }
+  int feature_dim() const { return 32 * hw_[3] * hw_[3]; }
+  int layer_k(int l) const { return l == 0 ? K1_ : 288; }
+  Linear layer(int l) const { return conv_[l].view(g_); }
+  cudaStream_t stream() const { return stream_; }
+  long long rows(int l) const { return (long long)B_ * hw_[l] * hw_[l]; }
+
+ private:
+  int B_, C_, H_, K1_ = 0, ldk1_ = 0;
+  int hw_[4] = {0, 0, 0, 0};
+  cudaStream_t stream_;
+  DeviceArena arena_;
+  GemmRunner gemm_;
+  ParamGroup g_;
+  LinearSlot conv_[4];
+  float* col_[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* act_[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* dact_[4] = {nullptr, nullptr, nullptr, nullptr};
+  float* dcol_ = nullptr;
+  static constexpr int kBiasChunks = 296;  // 2 x 148 SMs
+  float* bias_partial_ = nullptr;
+};
+
+}  // namespace rlrep

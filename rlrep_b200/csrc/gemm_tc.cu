@@ -70,19 +70,19 @@ CUtensorMap make_map_mnmajor(const float* base, int K, int mn, int ld, int tile_
   return m;
 }
 
-int max_clusters(int bn, bool a_mn, bool b_mn, int s, int stages) {
+int max_clusters(int bn, bool a_mn, bool b_mn, int s, int stages, bool push) {
   static std::mutex mu;
   static std::unordered_map<int, int> cache;
-  const int key = (bn << 12) | (a_mn << 11) | (b_mn << 10) | (s << 5) | stages;
+  const int key = (bn << 13) | (push << 12) | (a_mn << 11) | (b_mn << 10) | (s << 5) | stages;
   std::lock_guard<std::mutex> lock(mu);
   auto it = cache.find(key);
   if (it != cache.end()) return it->second;
   int n = 0;
   switch (bn) {
-    case 32: n = a_mn ? tc::max_clusters_32_1(b_mn, s, stages) : tc::max_clusters_32_0(b_mn, s, stages); break;
-    case 64: n = a_mn ? tc::max_clusters_64_1(b_mn, s, stages) : tc::max_clusters_64_0(b_mn, s, stages); break;
-    case 128: n = a_mn ? tc::max_clusters_128_1(b_mn, s, stages) : tc::max_clusters_128_0(b_mn, s, stages); break;
-    default: n = a_mn ? tc::max_clusters_256_1(b_mn, s, stages) : tc::max_clusters_256_0(b_mn, s, stages); break;
+    case 32: n = a_mn ? tc::max_clusters_32_1(b_mn, s, stages, push) : tc::max_clusters_32_0(b_mn, s, stages, push); break;
+    case 64: n = a_mn ? tc::max_clusters_64_1(b_mn, s, stages, push) : tc::max_clusters_64_0(b_mn, s, stages, push); break;
+    case 128: n = a_mn ? tc::max_clusters_128_1(b_mn, s, stages, push) : tc::max_clusters_128_0(b_mn, s, stages, push); break;
+    default: n = a_mn ? tc::max_clusters_256_1(b_mn, s, stages, push) : tc::max_clusters_256_0(b_mn, s, stages, push); break;
   }
   cache[key] = n;
   return n;
@@ -90,7 +90,16 @@ int max_clusters(int bn, bool a_mn, bool b_mn, int s, int stages) {
 
 // Ring depth.  A short K-slice is one burst of loads: a ring that fits twice into an SM (2 x ~113 KB) lets two CTAs
 // -- of this GEMM or of one running concurrently on another stream -- share the SM; long slices get the deepest ring.
-int pick_stages(int bn, int kb_per) {
+bool use_push(int bn, int s) {
+  static const int push_on = [] {
+    const char* e = std::getenv("RLREP_TC_PUSH");
+    return e ? std::atoi(e) : 1;
+  }();
+  return push_on && s > 1 && tc::push_possible(bn);
+}
+
+int pick_stages(int bn, int kb_per, bool push) {
+  if (push) return std::max(2, std::min(kb_per, tc::max_stages_push(bn)));
   static const int shallow_on = [] {
     const char* e = std::getenv("RLREP_TC_SHALLOW");
     return e ? std::atoi(e) : 1;
@@ -108,11 +117,12 @@ int pick_stages(int bn, int kb_per) {
 // by the share of the GPU the caller expects to have.
 double plan_cost(const GemmArgs& a, int nkb, int bn, int s, double sm_share, int* kb_per_out, int* stages_out) {
   const int kb_per = ceil_div(nkb, s);
-  const int stages = pick_stages(bn, kb_per);
+  const bool push = use_push(bn, s);
+  const int stages = pick_stages(bn, kb_per, push);
   *kb_per_out = kb_per;
   *stages_out = stages;
   const int clusters = ceil_div(a.M, BM) * ceil_div(a.N, bn);
-  const double cap = std::max(1.0, max_clusters(bn, a.a_mn, a.b_mn, s, stages) * sm_share);
+  const double cap = std::max(1.0, max_clusters(bn, a.a_mn, a.b_mn, s, stages, push) * sm_share);
   const double waves = std::ceil(clusters / cap);
   // When the GEMM shares the GPU with other branches the aggregate L2 -> SM operand traffic (not the per-CTA stream) is
   // what saturates, so the load term is weighted up: plans with wider tiles (fewer re-reads of A) win there.
@@ -123,7 +133,9 @@ double plan_cost(const GemmArgs& a, int nkb, int bn, int s, double sm_share, int
   const double contention = sm_share < 0.75 ? l2_weight : 1.0;
   const double load = contention * (double)(BM + bn) * BK * 4 * kb_per / 48.0;
   const double tile = (double)BM * bn * 4;
-  const double reduce = s > 1 ? tile / 16.0 : 0.0;
+  // pull: every CTA reads its rows from all peers over DSMEM (dependent loads, ~16 B/clk); push: posted remote
+  // stores overlapped with the TMEM drain (~2x cheaper end to end, measured)
+  const double reduce = s > 1 ? tile / (push ? 32.0 : 16.0) : 0.0;
   const double store = tile / s / 32.0;
   const double fixed = 1500.0 + (s == 2 ? 300.0 : s == 4 ? 600.0 : s == 8 ? 900.0 : 0.0);
   return waves * (load + reduce + store + fixed);
@@ -168,6 +180,7 @@ TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* /*ws*/, s
         p.split_k = s;
         p.kb_per_split = kb_per;
         p.stages = stages;
+        p.push = use_push(cand_bn, s);
       }
     }
   }
@@ -175,7 +188,8 @@ TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* /*ws*/, s
     p.bn = bn ? bn : 32;
     p.split_k = 1;
     p.kb_per_split = nkb;
-    p.stages = pick_stages(p.bn, nkb);
+    p.stages = pick_stages(p.bn, nkb, false);
+    p.push = false;
   }
   // K-major operand: matrix [rows = M|N, cols = K]; MN-major: matrix [rows = K, cols = M|N].
   p.tmA = a.a_mn ? make_map_mnmajor(a.A, a.K, a.M, a.lda, BM) : make_map_kmajor(a.A, a.M, a.K, a.lda, BM);

@@ -42,10 +42,26 @@ constexpr int kThreads = 512;     // 16 warps: 2 issue the pipeline, 4 drain TME
 constexpr int kSmemBudget = 200 * 1024;
 
 __host__ __device__ constexpr int stage_bytes(int bn) { return (BM + bn) * BK * 4; }
+__host__ __device__ constexpr int min_stages_fwd(int bn) { return bn >= 256 ? 3 : 2; }
 __host__ __device__ constexpr int num_stages(int bn) {
   return kSmemBudget / stage_bytes(bn) > 8 ? 8 : kSmemBudget / stage_bytes(bn);
 }
-__host__ __device__ constexpr int smem_bytes(int bn, int stages) { return stages * stage_bytes(bn) + 1024 + 256; }
+// Split-K "push" mode: every CTA owns BM / splits rows of the tile; the TMEM-drain warps write each partial row straight
+// into the OWNER's shared memory (st.shared::cluster), one cluster barrier later the owner sums its `splits` slots
+// locally in a fixed order.  The slots live behind the operand ring (peers may push while this CTA is still in its main
+// loop).  Compared with staging locally and pulling over DSMEM this removes the dependent remote-load latency, the
+// second cluster barrier and the local staging pass from the tail of every split-K GEMM.
+__host__ __device__ constexpr int slots_bytes(int bn) { return BM * (bn + 4) * 4; }
+__host__ __device__ constexpr int smem_bytes(int bn, int stages, bool push = false) {
+  return stages * stage_bytes(bn) + 1024 + 256 + (push ? slots_bytes(bn) : 0);
+}
+constexpr int kMaxSmem = 227 * 1024;
+__host__ __device__ constexpr bool push_possible(int bn) { return smem_bytes(bn, min_stages_fwd(bn), true) <= kMaxSmem; }
+__host__ __device__ constexpr int max_stages_push(int bn) {
+  return (kMaxSmem - 1024 - 256 - slots_bytes(bn)) / stage_bytes(bn) > 8
+             ? 8
+             : (kMaxSmem - 1024 - 256 - slots_bytes(bn)) / stage_bytes(bn);
+}
 __host__ __device__ constexpr int smem_bytes(int bn) { return smem_bytes(bn, num_stages(bn)); }
 // Fewest stages whose ring still holds the fp32 staging tile [BM, bn + 4] of the store phase.
 __host__ __device__ constexpr int min_stages(int bn) { return (BM * (bn + 4) * 4 + stage_bytes(bn) - 1) / stage_bytes(bn); }
@@ -53,7 +69,7 @@ __host__ __device__ constexpr int min_stages(int bn) { return (BM * (bn + 4) * 4
 // One launcher per (BN, A-major) pair, each defined in its own translation unit (gemm_tc_inst_*.cu).
 #define RLREP_TC_DECL(BN, AMN)                                           \
   void launch_tc_##BN##_##AMN(const TcGemmPlan& p, cudaStream_t stream); \
-  int max_clusters_##BN##_##AMN(bool b_mn, int split_k, int stages);
+  int max_clusters_##BN##_##AMN(bool b_mn, int split_k, int stages, bool push);
 RLREP_TC_DECL(32, 0) RLREP_TC_DECL(32, 1) RLREP_TC_DECL(64, 0) RLREP_TC_DECL(64, 1)
 RLREP_TC_DECL(128, 0) RLREP_TC_DECL(128, 1) RLREP_TC_DECL(256, 0) RLREP_TC_DECL(256, 1)
 #undef RLREP_TC_DECL
@@ -82,7 +98,9 @@ __device__ __forceinline__ void trace(int slot) {
 __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 struct TileStore {  // what the store phase needs to know about the tile (run-time so the functions below are shared)
-  uint32_t stage_addr;  // shared-memory address of this CTA's staged fp32 tile
+  uint32_t stage_addr;  // shared-memory address of this CTA's staged fp32 tile (pull) / of its reduction slots (push)
+  uint32_t peer_stride; // push mode: bytes between the slots of consecutive source CTAs (0 = pull over DSMEM)
+  int row_bias;         // row of the staged tile that local row 0 of this CTA's slice maps to (pull: row0, push: 0)
   int lds;              // staging row pitch in floats
   int c4_shift;         // log2(BN / 4)
   int splits;           // cluster size along K
@@ -104,7 +122,26 @@ __device__ __forceinline__ float4 load_reduced_n(uint32_t off) {
   }
   return acc;
 }
+template <int S>
+__device__ __forceinline__ float4 load_reduced_local(uint32_t off, uint32_t stride) {
+  float4 v[S];
+#pragma unroll
+  for (int p = 0; p < S; ++p) v[p] = ptx::ld_shared_f4(off + p * stride);
+  float4 acc = v[0];
+#pragma unroll
+  for (int p = 1; p < S; ++p) {  // same fixed order as the DSMEM pull: bit-identical results in both modes
+    acc.x += v[p].x; acc.y += v[p].y; acc.z += v[p].z; acc.w += v[p].w;
+  }
+  return acc;
+}
 __device__ __forceinline__ float4 load_reduced(const TileStore& t, uint32_t off) {
+  if (t.peer_stride != 0) {
+    switch (t.splits) {
+      case 2: return load_reduced_local<2>(off, t.peer_stride);
+      case 4: return load_reduced_local<4>(off, t.peer_stride);
+      default: return load_reduced_local<8>(off, t.peer_stride);
+    }
+  }
   switch (t.splits) {
     case 1: return ptx::ld_shared_f4(off);
     case 2: return load_reduced_n<2>(off);
@@ -164,7 +201,7 @@ __device__ __noinline__ bool store_tile_fast(const TileStore t, const Epilogue* 
     }
     *cp = make_float4(v[0], v[1], v[2], v[3]);
   };
-  if (t.splits > 1 && total <= nthr * 2 * U) {
+  if (t.splits > 1 && t.peer_stride == 0 && total <= nthr * 2 * U) {
     // The whole slice fits in registers: pull it over DSMEM, tell the cluster we are done with its shared memory
     // (peers may exit), and only then do the epilogue math and the global stores.
     float4 acc[2 * U];
@@ -173,7 +210,7 @@ __device__ __noinline__ bool store_tile_fast(const TileStore t, const Epilogue* 
     for (int u = 0; u < 2 * U; ++u) {
       const int idx = threadIdx.x + u * nthr;
       if (idx < total)
-        acc[u] = load_reduced(t, t.stage_addr + (((t.row0 + (idx >> t.c4_shift)) * t.lds + (idx & c4_mask) * 4) << 2));
+        acc[u] = load_reduced(t, t.stage_addr + (((t.row_bias + (idx >> t.c4_shift)) * t.lds + (idx & c4_mask) * 4) << 2));
     }
     if (threadIdx.x == 0) { if (acc[0].x == 123.456f) trace(15); trace(10); }
     ptx::cluster_arrive_relaxed();
@@ -194,14 +231,14 @@ __device__ __noinline__ bool store_tile_fast(const TileStore t, const Epilogue* 
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int idx = base + u * nthr;
-      acc[u] = load_reduced(t, t.stage_addr + (((t.row0 + (idx >> t.c4_shift)) * t.lds + (idx & c4_mask) * 4) << 2));
+      acc[u] = load_reduced(t, t.stage_addr + (((t.row_bias + (idx >> t.c4_shift)) * t.lds + (idx & c4_mask) * 4) << 2));
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) one(base + u * nthr, acc[u]);
   }
 #pragma unroll 1
   for (int idx = main_end + threadIdx.x; idx < total; idx += nthr)
-    one(idx, load_reduced(t, t.stage_addr + (((t.row0 + (idx >> t.c4_shift)) * t.lds + (idx & c4_mask) * 4) << 2)));
+    one(idx, load_reduced(t, t.stage_addr + (((t.row_bias + (idx >> t.c4_shift)) * t.lds + (idx & c4_mask) * 4) << 2)));
   return false;
 }
 
@@ -215,7 +252,7 @@ __device__ __noinline__ void store_tile_general(const TileStore t, const Epilogu
     const int rr = t.row0 + (idx >> t.c4_shift), c4 = idx & c4_mask;
     const int gm = t.m0 + rr, gn = t.n0 + c4 * 4;
     if (gm >= t.M || gn >= t.N) continue;
-    const float4 acc = load_reduced(t, t.stage_addr + ((rr * t.lds + c4 * 4) << 2));
+    const float4 acc = load_reduced(t, t.stage_addr + (((rr - t.row0 + t.row_bias) * t.lds + c4 * 4) << 2));
     float* cp = t.C + (size_t)gm * t.ldc + gn;
     const float a4[4] = {acc.x, acc.y, acc.z, acc.w};
 #pragma unroll 1
@@ -253,7 +290,7 @@ __device__ __forceinline__ bool store_tile(const TileStore& t, const Epilogue* e
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 float* __restrict__ C, int ldc, int M, int N, int K, int kb_per_split, int stages,
+                 float* __restrict__ C, int ldc, int M, int N, int K, int kb_per_split, int stages, int push,
                  const Epilogue epi) {
   // `stages` is a launch parameter: short K-slices run with a shallow ring so that two CTAs (of this or of a
   // concurrent GEMM on another stream) fit on one SM; long ones get the deepest ring that fits.
@@ -275,6 +312,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* accum_bar = empty_bar + 8;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
   float* stage = reinterpret_cast<float*>(smem);  // reuses the operand ring once the accumulator is complete
+  // push mode: reduction slots [splits][BM / splits][LDS] behind the barriers (16-byte aligned: the ring is 1 KB aligned)
+  float* slots = reinterpret_cast<float*>(smem + STAGES * (A_BYTES + B_BYTES) + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -366,16 +405,35 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     ptx::mbar_wait(accum_bar, 0);
     if (threadIdx.x == 64) trace(4);
     ptx::tc_fence_after_sync();
+    if (push) {
+      // row r of the tile belongs to CTA r / rows_per of the cluster: write it into that CTA's slot for this source
+      const int rows_per = BM / splits;
+      const uint32_t owner = r / rows_per;
+      const uint32_t my_rank = ptx::cluster_ctarank();
+      const uint32_t dst_row = ptx::smem_u32(slots) + ((my_rank * rows_per + (r - owner * rows_per)) * LDS) * 4;
 #pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-      uint32_t v[32];
-      ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + c * 32, v);
-      ptx::tmem_ld_wait();
-      float4* dst = reinterpret_cast<float4*>(stage + r * LDS + c * 32);
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + c * 32, v);
+        ptx::tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 8; ++j)
-        dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
-                             __uint_as_float(v[4 * j + 3]));
+        for (int j = 0; j < 8; ++j)
+          ptx::st_dsmem_f4(dst_row + (c * 32 + 4 * j) * 4, owner,
+                           make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                                       __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3])));
+      }
+    } else {
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + c * 32, v);
+        ptx::tmem_ld_wait();
+        float4* dst = reinterpret_cast<float4*>(stage + r * LDS + c * 32);
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          dst[j] = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                               __uint_as_float(v[4 * j + 3]));
+      }
     }
     ptx::tc_fence_before_sync();
   }
@@ -388,17 +446,19 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // ---------------------------------------------------------------- reduce + epilogue + coalesced store (all warps)
   {
     TileStore t;
-    t.stage_addr = ptx::smem_u32(stage);
+    t.stage_addr = push ? ptx::smem_u32(slots) : ptx::smem_u32(stage);
     t.lds = LDS;
+    t.peer_stride = push ? (uint32_t)((BM / splits) * LDS * 4) : 0u;
     t.c4_shift = BN == 32 ? 3 : (BN == 64 ? 4 : (BN == 128 ? 5 : 6));
     t.splits = splits;
     t.rows_per = BM / splits;
     t.row0 = (splits > 1 ? (int)ptx::cluster_ctarank() : 0) * t.rows_per;
+    t.row_bias = push ? 0 : t.row0;
     t.m0 = m0; t.n0 = n0; t.M = M; t.N = N;
     t.C = C; t.ldc = ldc;
     const bool arrived = store_tile(t, &epi);
     if (threadIdx.x == 0) trace(7);
-    if (splits > 1) {  // peers may still be reading this CTA's staging tile: do not exit before they are done
+    if (splits > 1 && !push) {  // peers may still be reading this CTA's staging tile: do not exit before they are done
       if (!arrived) ptx::cluster_arrive_relaxed();
       ptx::cluster_wait();
     }
@@ -409,17 +469,17 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
 template <int BN, bool A_MN, bool B_MN>
 void fill_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, dim3 grid, int split_k, int stages,
-                        cudaStream_t stream) {
+                        bool push, cudaStream_t stream) {
   auto kern = gemm_tf32_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;  // per template instantiation
   if (!attr_set) {
-    RLREP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(BN)));
+    RLREP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     attr_set = true;
   }
   cfg = {};
   cfg.gridDim = grid;
   cfg.blockDim = dim3(kThreads);
-  cfg.dynamicSmemBytes = smem_bytes(BN, stages);
+  cfg.dynamicSmemBytes = smem_bytes(BN, stages, push);
   cfg.stream = stream;
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 1;
@@ -432,13 +492,14 @@ void fill_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, dim3
 template <int BN, bool A_MN, bool B_MN>
 void launch_variant(const TcGemmPlan& p, cudaStream_t stream) {
   const GemmArgs& a = p.args;
-  RLREP_CHECK(p.stages >= min_stages(BN) && p.stages <= num_stages(BN), "bad pipeline depth");
+  RLREP_CHECK(p.stages >= (p.push ? 2 : min_stages(BN)) && p.stages <= num_stages(BN), "bad pipeline depth");
+  RLREP_CHECK(!p.push || (p.split_k > 1 && smem_bytes(BN, p.stages, true) <= kMaxSmem), "bad push-mode plan");
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[2];
   fill_launch_config<BN, A_MN, B_MN>(cfg, attr, dim3(ceil_div(a.N, BN), ceil_div(a.M, BM), p.split_k), p.split_k,
-                                     p.stages, stream);
+                                     p.stages, p.push, stream);
   RLREP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, A_MN, B_MN>, p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, a.K,
-                                p.kb_per_split, p.stages, a.epi));
+                                p.kb_per_split, p.stages, p.push ? 1 : 0, a.epi));
   g_trace_reader = &read_trace_here;
   RLREP_LAUNCHED_W("gemm_tf32", stream, 4.0 * ((double)a.M * a.K + (double)a.N * a.K + (double)a.M * a.N),
                    2.0 * a.M * a.N * a.K);
@@ -447,10 +508,10 @@ void launch_variant(const TcGemmPlan& p, cudaStream_t stream) {
 // How many clusters of `split_k` CTAs of this variant the GPU can hold at once (occupancy API; clusters must fit in
 // one GPC, so this is NOT 148 / split_k) -- the denominator of the cost model's wave count.
 template <int BN, bool A_MN, bool B_MN>
-int max_clusters_variant(int split_k, int stages) {
+int max_clusters_variant(int split_k, int stages, bool push) {
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[2];
-  fill_launch_config<BN, A_MN, B_MN>(cfg, attr, dim3(1, 1, split_k), split_k, stages, nullptr);
+  fill_launch_config<BN, A_MN, B_MN>(cfg, attr, dim3(1, 1, split_k), split_k, stages, push, nullptr);
   int n = 0;
   if (cudaOccupancyMaxActiveClusters(&n, gemm_tf32_kernel<BN, A_MN, B_MN>, &cfg) != cudaSuccess || n <= 0) {
     cudaGetLastError();
@@ -466,9 +527,9 @@ int max_clusters_variant(int split_k, int stages) {
     if (p.args.b_mn) launch_variant<BN, (AMN) != 0, true>(p, stream);         \
     else launch_variant<BN, (AMN) != 0, false>(p, stream);                    \
   }                                                                           \
-  int max_clusters_##BN##_##AMN(bool b_mn, int split_k, int stages) {         \
-    return b_mn ? max_clusters_variant<BN, (AMN) != 0, true>(split_k, stages) \
-                : max_clusters_variant<BN, (AMN) != 0, false>(split_k, stages); \
+  int max_clusters_##BN##_##AMN(bool b_mn, int split_k, int stages, bool push) {          \
+    return b_mn ? max_clusters_variant<BN, (AMN) != 0, true>(split_k, stages, push)       \
+                : max_clusters_variant<BN, (AMN) != 0, false>(split_k, stages, push);     \
   }
 #endif  // RLREP_TC_DEVICE_CODE
 

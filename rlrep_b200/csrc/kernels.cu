@@ -138,6 +138,35 @@ __global__ void __launch_bounds__(256) colreduce_kernel(const float* __restrict_
   }
 }
 
+// Column sums over very tall matrices (conv bias gradients: 4e5 rows x 32 columns): stage 1 reduces a row chunk per
+// CTA into partial[chunk, cols], stage 2 sums the chunks in a fixed order.
+__global__ void __launch_bounds__(256) colsum_tall_stage1_kernel(const float* __restrict__ X, int ld, long long rows,
+                                                                 int cols, int rows_per_cta, float* __restrict__ partial) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  const long long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
+  float acc = 0.f;
+  if (j < cols)
+    for (long long i = r0 + ty; i < r1; i += 8) acc += X[i * ld + j];
+  part[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && j < cols) {
+    float t = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) t += part[q][tx];
+    partial[(long long)blockIdx.y * cols + j] = t;
+  }
+}
+__global__ void colsum_tall_stage2_kernel(const float* __restrict__ partial, int chunks, int cols, float* __restrict__ out) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= cols) return;
+  float t = 0.f;
+  for (int c = 0; c < chunks; ++c) t += partial[(long long)c * cols + j];
+  out[j] = t;
+}
+
 struct ColJobs {
   ColJob j[kMaxColJobs];
 };
@@ -693,6 +722,15 @@ void launch_colreduce(const float* X, int ld, int rows, int cols, const float* u
                       cudaStream_t s) {
   colreduce_kernel<<<ceil_div(cols, 32), 256, 0, s>>>(X, ld, rows, cols, u, out, accumulate);
   RLREP_LAUNCHED("colreduce", s);
+}
+
+void launch_colsum_tall(const float* X, int ld, long long rows, int cols, float* partial, int chunks, float* out,
+                        cudaStream_t s) {
+  const int rows_per = (int)((rows + chunks - 1) / chunks);
+  colsum_tall_stage1_kernel<<<dim3(ceil_div(cols, 32), chunks), 256, 0, s>>>(X, ld, rows, cols, rows_per, partial);
+  RLREP_LAUNCHED_W("colsum_tall", s, 4.0 * (double)rows * cols, 0.0);
+  colsum_tall_stage2_kernel<<<ceil_div(cols, 128), 128, 0, s>>>(partial, chunks, cols, out);
+  RLREP_LAUNCHED("colsum_tall_final", s);
 }
 
 void launch_colreduce_multi(const ColJob* jobs, int n_jobs, cudaStream_t s) {

@@ -64,6 +64,9 @@ void launch_rowdot_pair(const RowDotJob& a, const RowDotJob& b, int rows, cudaSt
 // out[j] (+)= sum_i u[i] * X[i,j]   (u == nullptr: plain column sum).  Deterministic.
 void launch_colreduce(const float* X, int ld, int rows, int cols, const float* u, float* out, int accumulate,
                       cudaStream_t s);
+// out[j] = sum_i X[i, j] for very tall X (rows ~ 1e5..1e6): `chunks` CTAs per 32 columns, partial is [chunks, cols].
+void launch_colsum_tall(const float* X, int ld, long long rows, int cols, float* partial, int chunks, float* out,
+                        cudaStream_t s);
 // Several column reductions in one launch (all the bias gradients of a network's backward pass).
 struct ColJob {
   const float* X;

@@ -174,6 +174,13 @@ __device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
   return v;
 }
 // 16-byte load from the shared memory of CTA `cta_rank` of this cluster, at the same offset as local address `addr`.
+// 128-bit store into the shared memory of CTA `cta_rank` of this cluster at the same offset as `addr` has here.
+__device__ __forceinline__ void st_dsmem_f4(uint32_t addr, uint32_t cta_rank, float4 v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(cta_rank));
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(remote), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w)
+               : "memory");
+}
 __device__ __forceinline__ float4 ld_dsmem_f4(uint32_t addr, uint32_t cta_rank) {
   uint32_t remote;
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(addr), "r"(cta_rank));
