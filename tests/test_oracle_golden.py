@@ -10,12 +10,14 @@ import torch
 from oracle import rl_oracle as O
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
-CASES = sorted(p.stem for p in GOLDEN.glob("*.npz"))
+CASES = sorted(p.stem for p in GOLDEN.glob("*.npz") if not p.stem.startswith("drqv2"))
+DRQ_CASES = sorted(p.stem for p in GOLDEN.glob("drqv2*.npz"))
 
 
 def test_fixtures_present():
     assert {"sac_hc_b256", "ctrlsac_small", "ctrlsac_hc_b256", "vlsac_hc_b64", "vlsac_hum_b128", "spedersac_hc_b64",
             "diffsrsac_hc_b64"} <= set(CASES)
+    assert {"drqv2_b8", "drqv2_b16_c3"} <= set(DRQ_CASES)
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -63,3 +65,30 @@ def test_host_ring_follows_reference_semantics():
     i1 = np.random.randint(0, 5, size=4)
     np.random.seed(0)
     assert torch.equal(ring.sample(4).state, ring.take(i1).state)
+
+
+@pytest.mark.parametrize("name", DRQ_CASES)
+def test_drq_oracle_reproduces_reference(name):
+    """Plain DrQ-v2 pixel update (agent/diffsrdrq/drqv2.py:93-148): oracle/drq_oracle.py against fixtures produced by
+    the real reference class (oracle/make_golden_drq.py)."""
+    from oracle import drq_oracle as D
+    z = np.load(GOLDEN / f"{name}.npz")
+    meta = json.loads(bytes(z["meta_json"]).decode())
+    infos = json.loads(bytes(z["infos_json"]).decode())
+    C, A, bn, H, B, n = (meta[k] for k in ("C", "A", "bn_dim", "hidden_dim", "batch", "n"))
+    oracle = D.OracleDrQv2(A, D.init_state(C, A, bn, H, seed=0))
+    batches = [D.synthetic_pixel_batch(B, C, 84, A, seed=10 + i) for i in range(n)]
+    torch.manual_seed(1)
+    got = [oracle.train_step(b, step=1000 * i) for i, b in enumerate(batches)]
+    assert [bool(g) for g in got] == [bool(w) for w in infos]  # update_every = 2: every other call is a no-op
+    for step, (g, w) in enumerate(zip(got, infos)):
+        assert set(g) == set(w)
+        for k in w:
+            assert abs(g[k] - w[k]) <= 2e-6 + 2e-5 * abs(w[k]), (step, k, g[k], w[k])
+    sd = oracle.state_dict()
+    for k in meta["keys"]:
+        t = sd[k].detach().double().flatten()
+        stats, sample = z["stats/" + k], z["sample/" + k]
+        stride = max(1, t.numel() // 256)
+        assert abs(t.norm().item() - stats[1]) <= 1e-5 * max(stats[1], 1e-6), k
+        assert np.linalg.norm(t[::stride][:256].numpy() - sample) <= 2e-5 * max(np.linalg.norm(sample), 1e-6) + 1e-7, k
