@@ -210,6 +210,36 @@ RLREP_EXPORT int rlrep_conv_encoder_forward(rlrep_conv_encoder* enc, const unsig
 RLREP_EXPORT int rlrep_conv_encoder_backward(rlrep_conv_encoder* enc, const float* dfeat_dev);
 RLREP_EXPORT int rlrep_conv_encoder_feature_dim(rlrep_conv_encoder* enc, int* dim);
 
+/* ------------------------------------------------------------------------------------------------
+ * Plain DrQ-v2 pixel agent -- replaces `DrQv2(obs_space, action_space, args)` and the updating half of
+ * `DrQv2.train_step(replay_iter, step)` (agent/diffsrdrq/drqv2.py:12-148).  The caller keeps `_step` / `update_every`,
+ * evaluates the std-dev schedule and draws the randomness in the reference's order on the CPU generator:
+ * RandomShiftsAug's integer shifts for img then next_img ((x, y) per sample), then the standard-normal draws of the next
+ * action and of the actor step.  Tensors are exposed under the reference's module names ("encoder.convnet.0.weight",
+ * "critic.trunk.1.weight", "actor.policy.4.bias", "critic_target.Q2.2.weight", ...); conv weights of layers 2-4 are
+ * stored as [32, (ky, kx, c_in)] (rlrep_b200/pixel.py permutes them to and from the reference's [32, c_in, 3, 3]).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rlrep_drq rlrep_drq;
+typedef struct rlrep_drq_config {
+  int batch_size, channels, height, action_dim, bn_dim, hidden_dim;
+  double encoder_lr, actor_lr, critic_lr;
+  float tau, stddev_clip;
+  int precision;
+} rlrep_drq_config;
+RLREP_EXPORT int rlrep_drq_create(const rlrep_drq_config* cfg, void* stream, rlrep_drq** out);
+RLREP_EXPORT int rlrep_drq_destroy(rlrep_drq* drq);
+RLREP_EXPORT int rlrep_drq_num_tensors(rlrep_drq* drq, int* n);
+RLREP_EXPORT int rlrep_drq_tensor_info(rlrep_drq* drq, int i, const char** name, float** ptr_dev, int* rows, int* cols);
+RLREP_EXPORT int rlrep_drq_tensor_read(rlrep_drq* drq, int i, float* out_host);
+RLREP_EXPORT int rlrep_drq_tensor_write(rlrep_drq* drq, int i, const float* in_host);
+RLREP_EXPORT int rlrep_drq_sync_targets(rlrep_drq* drq);
+/* img / next_img uint8 [B, C, H, H]; action [B, A]; reward, discount [B]; shifts int32 [2][B][2]; eps [2][B][A];
+ * metrics_host[5] = {critic_loss, mean(q_pred), mean(q_target), mean(reward), actor_loss}.  All host pointers. */
+RLREP_EXPORT int rlrep_drq_update(rlrep_drq* drq, const unsigned char* img, const float* action, const float* reward,
+                                  const float* discount, const unsigned char* next_img, const int* shifts,
+                                  const float* eps, float stddev, float* metrics_host);
+RLREP_EXPORT int rlrep_drq_last_launches(rlrep_drq* drq, int* launches);
+
 /* Kernels launched by the most recent train() (a graph replay counts the kernels it contains). */
 RLREP_EXPORT int rlrep_agent_last_launches(rlrep_agent* agent, int* launches);
 

@@ -90,6 +90,15 @@ def _declare(lib: C.CDLL) -> None:
         "rlrep_conv_encoder_forward": [vp, vp, vp, vp],
         "rlrep_conv_encoder_backward": [vp, vp],
         "rlrep_conv_encoder_feature_dim": [vp, C.POINTER(i)],
+        "rlrep_drq_create": [vp, vp, C.POINTER(vp)],
+        "rlrep_drq_destroy": [vp],
+        "rlrep_drq_num_tensors": [vp, C.POINTER(i)],
+        "rlrep_drq_tensor_info": [vp, i, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(i), C.POINTER(i)],
+        "rlrep_drq_tensor_read": [vp, i, vp],
+        "rlrep_drq_tensor_write": [vp, i, vp],
+        "rlrep_drq_sync_targets": [vp],
+        "rlrep_drq_update": [vp, vp, vp, vp, vp, vp, vp, vp, C.c_float, vp],
+        "rlrep_drq_last_launches": [vp, C.POINTER(i)],
         "rlrep_comm_unique_id": [vp],
         "rlrep_comm_create": [vp, i, i, C.POINTER(vp)],
         "rlrep_comm_destroy": [vp],

@@ -9,6 +9,7 @@
 #include "comm.cuh"
 #include "common.cuh"
 #include "conv.cuh"
+#include "drq.cuh"
 #include "gemm.cuh"
 #include "rlrep_b200.h"
 
@@ -328,6 +329,106 @@ int rlrep_conv_encoder_feature_dim(rlrep_conv_encoder* enc, int* dim) {
   RLREP_API_BEGIN
   RLREP_CHECK(enc && dim, "null argument");
   *dim = enc->impl->feature_dim();
+  RLREP_API_END
+}
+
+// ------------------------------------------------------------------------------------------------ DrQ-v2 pixel agent
+struct rlrep_drq {
+  std::unique_ptr<DrqV2> impl;
+  std::vector<TensorRef> tensors;
+  cudaStream_t owned_stream = nullptr;
+};
+
+int rlrep_drq_create(const rlrep_drq_config* c, void* stream, rlrep_drq** out) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(c != nullptr && out != nullptr, "null argument");
+  DrqConfig d;
+  d.batch = c->batch_size; d.channels = c->channels; d.height = c->height; d.action_dim = c->action_dim;
+  d.bn_dim = c->bn_dim; d.hidden_dim = c->hidden_dim;
+  d.encoder_lr = c->encoder_lr; d.actor_lr = c->actor_lr; d.critic_lr = c->critic_lr;
+  d.tau = c->tau; d.stddev_clip = c->stddev_clip; d.precision = c->precision;
+  std::unique_ptr<rlrep_drq> h(new rlrep_drq);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (st == nullptr) {
+    RLREP_CUDA(cudaStreamCreateWithFlags(&h->owned_stream, cudaStreamNonBlocking));
+    st = h->owned_stream;
+  }
+  h->impl.reset(new DrqV2(d, st));
+  for (ParamGroup* g : h->impl->groups()) {
+    const std::string prefix = g->name == "encoder" ? "encoder." : "";
+    for (const ParamTensor& t : g->tensors) h->tensors.push_back({prefix + t.name, g->p + t.offset, t.rows, t.cols, t.ld});
+    // gradients of the most recent update, for gradient-level parity tests ("grad/<name>")
+    for (const ParamTensor& t : g->tensors)
+      h->tensors.push_back({"grad/" + prefix + t.name, g->g + t.offset, t.rows, t.cols, t.ld});
+    if (g->target)
+      for (const ParamTensor& t : g->tensors)
+        h->tensors.push_back({g->target_prefix_to + t.name.substr(g->target_prefix_from.size()), g->target + t.offset,
+                              t.rows, t.cols, t.ld});
+  }
+  *out = h.release();
+  RLREP_API_END
+}
+int rlrep_drq_destroy(rlrep_drq* drq) {
+  RLREP_API_BEGIN
+  if (drq) {
+    if (drq->impl) cudaStreamSynchronize(drq->impl->stream());
+    drq->impl.reset();
+    if (drq->owned_stream) cudaStreamDestroy(drq->owned_stream);
+  }
+  delete drq;
+  RLREP_API_END
+}
+int rlrep_drq_num_tensors(rlrep_drq* drq, int* n) {
+  RLREP_API_BEGIN
+  *n = (int)drq->tensors.size();
+  RLREP_API_END
+}
+int rlrep_drq_tensor_info(rlrep_drq* drq, int i, const char** name, float** ptr_dev, int* rows, int* cols) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(i >= 0 && i < (int)drq->tensors.size(), "tensor index out of range");
+  const TensorRef& t = drq->tensors[i];
+  if (name) *name = t.name.c_str();
+  if (ptr_dev) *ptr_dev = t.ptr;
+  if (rows) *rows = t.rows;
+  if (cols) *cols = t.cols;
+  RLREP_API_END
+}
+int rlrep_drq_tensor_read(rlrep_drq* drq, int i, float* out_host) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(i >= 0 && i < (int)drq->tensors.size(), "tensor index out of range");
+  const TensorRef& t = drq->tensors[i];
+  cudaStream_t st = drq->impl->stream();
+  RLREP_CUDA(cudaMemcpy2DAsync(out_host, (size_t)t.cols * 4, t.ptr, (size_t)t.ld * 4, (size_t)t.cols * 4, t.rows,
+                               cudaMemcpyDeviceToHost, st));
+  RLREP_CUDA(cudaStreamSynchronize(st));
+  RLREP_API_END
+}
+int rlrep_drq_tensor_write(rlrep_drq* drq, int i, const float* in_host) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(i >= 0 && i < (int)drq->tensors.size(), "tensor index out of range");
+  const TensorRef& t = drq->tensors[i];
+  cudaStream_t st = drq->impl->stream();
+  RLREP_CUDA(cudaMemcpy2DAsync(t.ptr, (size_t)t.ld * 4, in_host, (size_t)t.cols * 4, (size_t)t.cols * 4, t.rows,
+                               cudaMemcpyHostToDevice, st));
+  RLREP_CUDA(cudaStreamSynchronize(st));
+  RLREP_API_END
+}
+int rlrep_drq_sync_targets(rlrep_drq* drq) {
+  RLREP_API_BEGIN
+  drq->impl->sync_targets_from_params();
+  RLREP_API_END
+}
+int rlrep_drq_update(rlrep_drq* drq, const unsigned char* img, const float* action, const float* reward,
+                     const float* discount, const unsigned char* next_img, const int* shifts, const float* eps,
+                     float stddev, float* metrics_host) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(drq && img && action && reward && discount && next_img && shifts && eps && metrics_host, "null argument");
+  drq->impl->update(img, action, reward, discount, next_img, shifts, eps, stddev, metrics_host);
+  RLREP_API_END
+}
+int rlrep_drq_last_launches(rlrep_drq* drq, int* launches) {
+  RLREP_API_BEGIN
+  *launches = drq->impl->last_launches;
   RLREP_API_END
 }
 

@@ -122,7 +122,7 @@ ConvEncoder::ConvEncoder(int batch, int in_channels, int height, Precision prec,
   ldk1_ = round_up32(K1_);
   g_.name = "encoder";
   // layer 1 keeps the reference's [32, C*3*3] layout; layers 2-4 are stored [32, (ky, kx, c)] (permuted at the API)
-  conv_[0] = add_linear(g_, "convnet.0", 32, K1_);
+  conv_[0] = add_linear(g_, "convnet.0", 32, K1_);  // exported as "encoder.convnet.N" by the DrQ handle
   for (int l = 1; l < 4; ++l) conv_[l] = add_linear(g_, "convnet." + std::to_string(2 * l), 32, 288);
   g_.want(arena_);
   arena_.want(&col_[0], rows(0) * ldk1_);

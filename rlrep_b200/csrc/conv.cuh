@@ -18,6 +18,7 @@ class ConvEncoder {
   int layer_k(int l) const { return l == 0 ? K1_ : 288; }
   Linear layer(int l) const { return conv_[l].view(g_); }
   cudaStream_t stream() const { return stream_; }
+  ParamGroup& group() { return g_; }  // p | g | m | v of the four conv layers (the owner runs Adam over it)
   long long rows(int l) const { return (long long)B_ * hw_[l] * hw_[l]; }
 
  private:

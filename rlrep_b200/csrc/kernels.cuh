@@ -185,6 +185,28 @@ void launch_diffsr_score_bwd(const float* phi, const float* flat, int D, int S, 
 // out[0] = scale * sum(x[0:n])   (single block, deterministic)
 void launch_sum_scaled(const float* x, int n, float scale, float* out, cudaStream_t s);
 
+// ---- DrQ-v2 pixel update (agent/diffsrdrq/network_arch/drqv2.py:60-135, drqv2.py:112-148) ----------------------------
+// y[:, 0:n] = tanh(LayerNorm_n(x) * gamma + beta) (eps 1e-5); xhat / rstd are kept for the backward pass when non-null.
+void launch_ln_tanh_fwd(const float* x, int ld_x, int B, int n, const float* gamma, const float* beta, float* y, int ld_y,
+                        float* xhat, int ld_h, float* rstd, cudaStream_t s);
+// Backward of the above: dx [B, ld_dx] (columns >= n zeroed), g_beta = dz and g_gamma = dz * xhat (their column sums are
+// the LayerNorm parameter gradients).
+void launch_ln_tanh_bwd(const float* dy, int ld_dy, const float* y, int ld_y, const float* xhat, int ld_h, const float* rstd,
+                        int B, int n, const float* gamma, float* dx, int ld_dx, float* g_beta, float* g_gamma, int ld_g,
+                        cudaStream_t s);
+// Actor head + TruncatedNormal.sample(clip): mu = tanh(raw); action = clamp(mu + clamp(eps * std, +-clip), +-(1 - 1e-6)).
+void launch_trunc_normal_sample(const float* raw, int ld_raw, int B, int A, const float* eps, float std, float clip,
+                                float* mu, float* action, int ld_a, cudaStream_t s);
+// Straight-through clamp: d raw = d action * (1 - mu^2); columns [A, ld_out) zeroed.
+void launch_trunc_normal_bwd(const float* d_action, int ld_da, const float* mu, int B, int A, float* draw, int ld_out,
+                             cudaStream_t s);
+// y = r + discount * min(tq1, tq2); loss = mse over the stacked twin Q (mean over 2B); dq = 2 (q - y) / (2B);
+// metrics = {critic_loss, mean(q_pred), mean(q_target), mean(reward)}
+void launch_drq_critic_loss(const float* reward, const float* discount, const float* tq1, const float* tq2, const float* q1,
+                            const float* q2, int B, float* dq1, float* dq2, float* metrics, cudaStream_t s);
+// actor_loss = -mean(min(q1, q2)); dq = -1/B on the argmin; metrics = {actor_loss}
+void launch_drq_actor_loss(const float* q1, const float* q2, int B, float* dq1, float* dq2, float* metrics, cudaStream_t s);
+
 // Fused multi-tensor Adam (+ optional Polyak of a prefix of the arena into its target copy).
 // One launch updates a whole optimiser group laid out as flat arrays p / g / m / v of n floats (n % 4 == 0).
 //   torch.optim.Adam defaults: beta = (0.9, 0.999), eps = 1e-8, no weight decay / amsgrad.

@@ -98,3 +98,169 @@ class ConvEncoder:
         _lib.check(self.lib.rlrep_conv_encoder_backward(self._h, dfeat.data_ptr()))
         cur.wait_stream(self._stream)
         self._keep_d = dfeat
+
+
+class DrqConfig(C.Structure):
+    """Mirror of `rlrep_drq_config` (include/rlrep_b200.h)."""
+    _fields_ = [("batch_size", C.c_int), ("channels", C.c_int), ("height", C.c_int), ("action_dim", C.c_int),
+                ("bn_dim", C.c_int), ("hidden_dim", C.c_int), ("encoder_lr", C.c_double), ("actor_lr", C.c_double),
+                ("critic_lr", C.c_double), ("tau", C.c_float), ("stddev_clip", C.c_float), ("precision", C.c_int)]
+
+
+def _schedule(spec):
+    """helper_functions/util.py:142-148 `setup_schedule`."""
+    import re
+    init, final, duration = [float(g) for g in re.match(r"linear\((.+),(.+),(.+)\)", spec).groups()]
+
+    def fn(step):
+        mix = np.clip(step / duration, 0.0, 1.0)
+        return (1.0 - mix) * init + mix * final
+    return fn
+
+
+class DrQv2:
+    """Drop-in for the update path of agent.diffsrdrq.drqv2.DrQv2 (drqv2.py:12-148): same constructor
+    (`obs_space`, `action_space`, `args` with tau / update_every / critic_loss / stddev_schedule / stddev_clip / bn_dim /
+    actor_hidden_dim / critic_hidden_dim / encoder_lr / actor_lr / critic_lr) and `train_step(replay_iter, step)` with the
+    reference's metric keys.  The batch comes from the caller's replay iterator as in the reference
+    (img_stack uint8 [B, 9, 84, 84], action, reward, discount, next_img_stack, next_img_step).  `select_action` (B = 1
+    inference) is not part of this round."""
+
+    def __init__(self, obs_space, action_space, args, *, precision="tf32"):
+        if not torch.cuda.is_available():
+            raise _lib.RlrepError("rlrep_b200.DrQv2 needs a CUDA device (there is no CPU fallback)")
+        if getattr(args, "critic_loss", "mse") != "mse":
+            raise NotImplementedError("critic_loss='huber' (configs/drqv2.yaml ships 'mse')")
+        if args.actor_hidden_dim != args.critic_hidden_dim:
+            raise NotImplementedError("actor_hidden_dim != critic_hidden_dim")
+        self.args = args
+        self.obs_dim = tuple(int(x) for x in obs_space.shape)
+        self.action_dim = int(action_space.shape[0])
+        self.tau, self.update_every = float(args.tau), int(args.update_every)
+        self.stddev_schedule, self.stddev_clip = _schedule(args.stddev_schedule), float(args.stddev_clip)
+        self.bn_dim, self.hidden_dim = int(args.bn_dim), int(args.actor_hidden_dim)
+        self._precision = precision
+        self._step = 1
+        self.lib = _lib.load()
+        self._h = None
+        self._batch = None
+        self._pending = {}
+
+    # ---- handle ------------------------------------------------------------------------------------------------
+    def _ensure(self, batch):
+        if self._h is not None:
+            if batch != self._batch:
+                raise _lib.RlrepError(f"batch size is fixed per handle (was {self._batch}, got {batch})")
+            return
+        c, h, _ = self.obs_dim
+        cfg = DrqConfig(batch_size=batch, channels=c, height=h, action_dim=self.action_dim, bn_dim=self.bn_dim,
+                        hidden_dim=self.hidden_dim, encoder_lr=float(self.args.encoder_lr),
+                        actor_lr=float(self.args.actor_lr), critic_lr=float(self.args.critic_lr), tau=self.tau,
+                        stddev_clip=self.stddev_clip, precision=_lib.PRECISION[self._precision])
+        hd = C.c_void_p()
+        _lib.check(self.lib.rlrep_drq_create(C.byref(cfg), None, C.byref(hd)))
+        self._h, self._batch = hd, batch
+        n = C.c_int()
+        _lib.check(self.lib.rlrep_drq_num_tensors(hd, C.byref(n)))
+        self._index = {}
+        for i in range(n.value):
+            name, ptr, rows, cols = C.c_char_p(), C.c_void_p(), C.c_int(), C.c_int()
+            _lib.check(self.lib.rlrep_drq_tensor_info(hd, i, C.byref(name), C.byref(ptr), C.byref(rows), C.byref(cols)))
+            self._index[name.value.decode()] = (i, rows.value, cols.value)
+        if self._pending:
+            sd, self._pending = self._pending, {}
+            self.load_state_dict(sd)
+
+    def close(self):
+        h, self._h = self._h, None
+        if h:
+            self.lib.rlrep_drq_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights under the reference's module names ----------------------------------------------------------------
+    def _ref_shape(self, name, rows, cols):
+        if ".convnet." in name and name.endswith("weight"):
+            return (32, cols // 9, 3, 3)
+        if name.endswith("bias") or ".trunk.1." in name:
+            return (rows,)
+        return (rows, cols)
+
+    def state_dict(self):
+        if self._h is None:
+            return dict(self._pending)
+        return self._read_all(lambda name: not name.startswith("grad/"))
+
+    def grads(self):
+        """Gradients left by the most recent update (critic / encoder: critic step; actor: actor step), reference names."""
+        return {k[5:]: v for k, v in self._read_all(lambda name: name.startswith("grad/")).items()}
+
+    def _read_all(self, keep):
+        sd = {}
+        for name, (i, rows, cols) in self._index.items():
+            if not keep(name):
+                continue
+            out = np.empty(rows * cols, dtype=np.float32)
+            _lib.check(self.lib.rlrep_drq_tensor_read(self._h, i, out.ctypes.data))
+            t = torch.from_numpy(out)
+            if ".convnet." in name and name.endswith("weight") and not name.endswith("convnet.0.weight"):
+                t = t.reshape(32, 3, 3, 32).permute(0, 3, 1, 2).contiguous()  # stored (ky, kx, c) -> reference (c, ky, kx)
+            sd[name] = t.reshape(self._ref_shape(name, rows, cols))
+        return sd
+
+    def load_state_dict(self, sd, sync_targets=None):
+        if self._h is None:
+            self._pending.update({k: torch.as_tensor(v).detach().clone() for k, v in sd.items()})
+            return
+        for k, v in sd.items():
+            i, rows, cols = self._index[k]
+            t = torch.as_tensor(v).detach().cpu().float()
+            if tuple(t.shape) != self._ref_shape(k, rows, cols):
+                raise ValueError(f"{k}: expected {self._ref_shape(k, rows, cols)}, got {tuple(t.shape)}")
+            if ".convnet." in k and k.endswith("weight") and not k.endswith("convnet.0.weight"):
+                t = t.permute(0, 2, 3, 1)
+            arr = np.ascontiguousarray(t.reshape(-1).numpy())
+            _lib.check(self.lib.rlrep_drq_tensor_write(self._h, i, arr.ctypes.data))
+        if sync_targets or (sync_targets is None and not any(k.startswith("critic_target.") for k in sd)):
+            _lib.check(self.lib.rlrep_drq_sync_targets(self._h))
+
+    @property
+    def gpu_launches_last_update(self):
+        v = C.c_int()
+        _lib.check(self.lib.rlrep_drq_last_launches(self._h, C.byref(v)))
+        return v.value
+
+    # ---- reference surface ---------------------------------------------------------------------------------------
+    def _draw(self, n):
+        """RNG consumption of one updating train_step, in the reference's order: RandomShiftsAug's
+        `torch.randint(0, 9, (n,1,1,2), dtype=float32)` for img then next_img (network_arch/drqv2.py:43-47), then
+        `_standard_normal([n, A])` for the next action and for the actor step (TruncatedNormal.sample, :72-75)."""
+        shifts = torch.stack([torch.randint(0, 9, size=(n, 1, 1, 2), dtype=torch.float32).reshape(n, 2) for _ in range(2)])
+        z = torch.zeros(n, self.action_dim)
+        eps = torch.stack([torch.normal(z, torch.ones_like(z)) for _ in range(2)])
+        return shifts.to(torch.int32).numpy(), eps.numpy()
+
+    def train_step(self, replay_iter, step):
+        self._step += 1
+        if self._step % self.update_every != 0:
+            return {}
+        batch = next(replay_iter)
+        img, action, reward, discount, next_img = (np.ascontiguousarray(torch.as_tensor(t).cpu().numpy()) for t in batch[:5])
+        n = img.shape[0]
+        self._ensure(n)
+        shifts, eps = self._draw(n)
+        stddev = float(self.stddev_schedule(step))
+        m = np.zeros(8, dtype=np.float32)
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32).reshape(-1)
+        action, reward, discount = f32(action), f32(reward), f32(discount)
+        shifts, eps = np.ascontiguousarray(shifts), np.ascontiguousarray(eps)
+        assert img.dtype == np.uint8 and next_img.dtype == np.uint8, "frame stacks must be uint8 like the reference's buffers"
+        _lib.check(self.lib.rlrep_drq_update(self._h, img.ctypes.data, action.ctypes.data, reward.ctypes.data,
+                                             discount.ctypes.data, next_img.ctypes.data, shifts.ctypes.data,
+                                             eps.ctypes.data, stddev, m.ctypes.data))
+        return {"loss/actor_loss": float(m[4]), "info/policy_std": stddev, "loss/critic_loss": float(m[0]),
+                "info/q_pred": float(m[1]), "info/q_target": float(m[2]), "info/reward": float(m[3])}
