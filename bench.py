@@ -50,6 +50,9 @@ WORKLOADS = {
     # the other two state-based agents at what main.py passes (main.py:93-104)
     "spedersac_hc_b256": dict(alg="spedersac", S=17, A=6, B=256, rows=1_000_000, kw=SPEDER_MAIN),
     "diffsrsac_hc_b256": dict(alg="diffsrsac", S=17, A=6, B=256, rows=1_000_000, kw=dict(hidden_dim=256)),
+    # first pixel agent (plain DrQ-v2 `train_step`, configs/drqv2.yaml shapes); one replica per GPU
+    # at N > 1 is the population harness of BASELINE.json configs[4]
+    "drqv2_pixels_b256": dict(alg="drqv2", C=9, A=4, B=256, bn=50, H=1024, rows=0, kw={}),
     # BASELINE.json configs[3]: large-batch CTRL, GLOBAL batch 16384 split by rows over the ranks (strong scaling:
     # the total work is fixed; 2048 rows per GPU at N = 8), mu(s') all-gathered over NVLink
     "ctrlsac_b16384_sharded": dict(alg="ctrlsac", S=17, A=6, B=16384, rows=1_000_000, sharded=True,
@@ -220,6 +223,147 @@ def run_reference(args, w, rank, world):
         "e2e": {"value": ups, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     emit(line)
+
+
+# ---------------------------------------------------------------------------------------------------- pixel arm
+def drq_args(w):
+    import types
+    return types.SimpleNamespace(tau=0.01, update_every=1, critic_loss="mse", stddev_schedule="linear(1.0,0.1,500000)",
+                                 stddev_clip=0.3, bn_dim=w["bn"], actor_hidden_dim=w["H"], critic_hidden_dim=w["H"],
+                                 encoder_lr=1e-4, actor_lr=1e-4, critic_lr=1e-4)
+
+
+class _Box:
+    def __init__(self, shape):
+        self.shape = shape
+
+
+def run_drq(args, w, rank, world, local_rank):
+    """DrQ-v2 pixel update: one step = one updating `train_step` on a [B, 9, 84, 84] uint8 batch (synthetic frames)."""
+    import torch
+    import torch.distributed as dist
+    from oracle import drq_oracle as D  # synthetic batch + deterministic initial weights (data, not arithmetic)
+    from rlrep_b200 import _lib
+    from rlrep_b200.pixel import DrQv2
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    C_, A, B = w["C"], w["A"], w["B"]
+    agent = DrQv2(_Box((C_, 84, 84)), _Box((A,)), drq_args(w), precision=args.precision)
+    agent.load_state_dict(D.init_state(C_, A, w["bn"], w["H"], seed=rank))
+    batches = [tuple(D.synthetic_pixel_batch(B, C_, 84, A, seed=100 * rank + i)) for i in range(4)]
+    torch.manual_seed(1 + rank)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        agent.train_step(iter([batches[i % 4]]), step=i)
+    ms = C.c_float()
+    barrier()
+    with ClockSampler(local_rank) as clk:  # (1) device-timed on the batch already resident in HBM
+        _lib.check(agent.lib.rlrep_drq_update_resident(agent._h, args.steps, 1.0, C.byref(ms)))
+        barrier()
+    dev_ms, clocks = float(ms.value), clk.summary()
+    barrier()
+    t0 = time.perf_counter()  # (2) end to end: host batch -> pinned staging -> H2D -> update -> metrics D2H
+    info = None
+    for i in range(args.steps):
+        info = agent.train_step(iter([batches[i % 4]]), step=i)
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3
+    launches = agent.gpu_launches_last_update
+    if world > 1:
+        t = torch.tensor([dev_ms, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dev_ms, e2e_ms = t.tolist()
+    roofline, top, cpu = None, [], None
+    if rank == 0:
+        cap = 4096
+        names, kms = (C.c_char_p * cap)(), (C.c_float * cap)()
+        kby, kfl, n = (C.c_double * cap)(), (C.c_double * cap)(), C.c_int()
+        agg = {}
+        for _ in range(3):
+            _lib.check(agent.lib.rlrep_drq_profile_update(agent._h, 1.0, cap, names, kms, kby, kfl, C.byref(n)))
+            for i in range(min(n.value, cap)):
+                a = agg.setdefault(names[i].decode(), [0.0, 0, 0.0, 0.0])
+                a[0] += kms[i]; a[1] += 1; a[2] += kby[i]; a[3] += kfl[i]
+        total = sum(v[0] for v in agg.values())
+        top = sorted(((k, v[0] / 3, v[1] // 3) for k, v in agg.items()), key=lambda x: -x[1])
+        pk = ROOT / "MEASURED_PEAKS.json"
+        hbm_peak = float(json.loads(pk.read_text()).get("hbm_gbs", 6650.0)) if pk.exists() else 6650.0
+        tf32_peak = measure_tf32_peak()
+        step_s = dev_ms / args.steps * 1e-3
+        by, fl = sum(v[2] for v in agg.values()) / 3, sum(v[3] for v in agg.values()) / 3
+        k0 = top[0][0]
+        t0k = agg[k0][0] * 1e-3
+        f_h, f_t = agg[k0][2] / t0k / 1e9 / hbm_peak, agg[k0][3] / t0k / 1e12 / tf32_peak
+        roofline = {"kernel": k0, "bound": "hbm" if f_h >= f_t else "tensor",
+                    "achieved": agg[k0][2] / t0k / 1e9 if f_h >= f_t else agg[k0][3] / t0k / 1e12,
+                    "peak": hbm_peak if f_h >= f_t else tf32_peak, "unit": "GB/s" if f_h >= f_t else "TFLOP/s",
+                    "frac": max(f_h, f_t), "traffic": None, "share_of_step": agg[k0][0] / total,
+                    "launches_per_step": agg[k0][1] / 3, "tf32_peak_tflops": tf32_peak,
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs / cuBLAS TF32 8192^3 measured in this run",
+                    "note": "v1 lowers the convolutions onto explicit im2col + GEMM: the column matrices are ~10x the "
+                            "algorithmic traffic of the convolutions (DESIGN.md section 8)",
+                    "step": {"algorithmic_bytes_of_launches": by, "algorithmic_flops": fl,
+                             "roofline_ms": max(by / (hbm_peak * 1e9), fl / (tf32_peak * 1e12)) * 1e3,
+                             "frac": max(by / (hbm_peak * 1e9), fl / (tf32_peak * 1e12)) / step_s}}
+        if world == 1 and not args.no_cpu_baseline:
+            torch.set_num_threads(os.cpu_count() or 1)
+            oracle = D.OracleDrQv2(A, D.init_state(C_, A, w["bn"], w["H"], seed=0), update_every=1)
+            ob = D.synthetic_pixel_batch(B, C_, 84, A, seed=0)
+            oracle.train_step(ob, 0)
+            t1 = time.perf_counter()
+            n_cpu = 20
+            for _ in range(n_cpu):
+                oracle.train_step(ob, 0)
+            dt = (time.perf_counter() - t1) / n_cpu
+            cpu = {"value": 1.0 / dt, "unit": "updates/s", "cores": torch.get_num_threads(), "kind": "port",
+                   "sample": f"{n_cpu} updates of the same workload after 1 warm-up ({dt * 1e3:.0f} ms each), reference "
+                             f"arithmetic as written (grid_sample augmentation, F.conv2d, autograd, torch.optim.Adam)"}
+        img_bytes = 2 * B * C_ * 84 * 84
+        line = {"metric": "agent updates/sec", "value": world * args.steps / (dev_ms * 1e-3), "unit": "updates/s",
+                "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+                "config": {"workload": args.workload, "alg": "drqv2", "obs": [C_, 84, 84], "A": A, "B": B, "bn_dim": w["bn"],
+                           "hidden_dim": w["H"], "parallelism": f"replicas x{world} (no collective)",
+                           "l2": "no flush: the update streams ~3 GB of column matrices and activations (>> 126 MB L2)"},
+                "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "updates/s", "ms_per_step": e2e_ms / args.steps,
+                        "h2d_bytes_per_step": img_bytes + 4 * (4 * B + 3 * B * A + 2 * B), "d2h_bytes_per_step": 32},
+                "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches, "clocks": clocks,
+                "roofline": roofline, "cpu_baseline": cpu,
+                "top_kernels_us_per_step": [[k, round(v * 1e3, 1), c] for k, v, c in top[:8]], "last_info": info}
+        emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_drq_reference(args, w, rank):
+    if rank != 0:
+        return
+    import torch
+    from oracle import drq_oracle as D
+    torch.set_num_threads(os.cpu_count() or 1)
+    oracle = D.OracleDrQv2(w["A"], D.init_state(w["C"], w["A"], w["bn"], w["H"], seed=0), update_every=1)
+    ob = D.synthetic_pixel_batch(w["B"], w["C"], 84, w["A"], seed=0)
+    torch.manual_seed(1)
+    for _ in range(args.warmup):
+        oracle.train_step(ob, 0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        oracle.train_step(ob, 0)
+    dt = (time.perf_counter() - t0) / args.steps
+    emit({"impl": "reference", "metric": "agent updates/sec", "value": 1.0 / dt, "unit": "updates/s", "n_gpus": args.gpus,
+          "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
+          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": args.workload, "alg": "drqv2"},
+          "cpu_baseline": {"value": 1.0 / dt, "unit": "updates/s", "cores": torch.get_num_threads(), "kind": "port",
+                           "sample": f"{args.steps} updates after {args.warmup} warm-up"},
+          "e2e": {"value": 1.0 / dt, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
 
 
 # ---------------------------------------------------------------------------------------------------- GPU arm
@@ -429,6 +573,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if w["alg"] == "drqv2":
+        if args.impl == "reference":
+            args.steps = min(args.steps, 20)
+            run_drq_reference(args, w, rank)
+        else:
+            run_drq(args, w, rank, world, local_rank)
+        return
     if args.impl == "reference":
         if w.get("sharded"):
             args.steps, args.warmup = min(args.steps, 2), 0  # ~17 TFLOP per update on the host cores: a bounded sample

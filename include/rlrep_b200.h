@@ -238,6 +238,11 @@ RLREP_EXPORT int rlrep_drq_sync_targets(rlrep_drq* drq);
 RLREP_EXPORT int rlrep_drq_update(rlrep_drq* drq, const unsigned char* img, const float* action, const float* reward,
                                   const float* discount, const unsigned char* next_img, const int* shifts,
                                   const float* eps, float stddev, float* metrics_host);
+/* Benchmark aids on the batch uploaded by the last rlrep_drq_update: n_steps updates back to back with CUDA-event timing;
+ * one update with an event behind every launch (same contract as rlrep_agent_profile_train). */
+RLREP_EXPORT int rlrep_drq_update_resident(rlrep_drq* drq, int n_steps, float stddev, float* total_ms);
+RLREP_EXPORT int rlrep_drq_profile_update(rlrep_drq* drq, float stddev, int max_entries, const char** names, float* ms,
+                                          double* bytes, double* flops, int* n_entries);
 RLREP_EXPORT int rlrep_drq_last_launches(rlrep_drq* drq, int* launches);
 
 /* Kernels launched by the most recent train() (a graph replay counts the kernels it contains). */

@@ -180,6 +180,30 @@ void DrqV2::actor_forward(const float* latent, const float* eps, float stddev, i
   launch_trunc_normal_sample(raw_, LA_, B_, A_, eps, stddev, cfg_.stddev_clip, mu_, cat_[set] + bn_, LC_, stream_);
 }
 
+float DrqV2::update_resident(int n_steps, float stddev) {
+  RLREP_CHECK(n_steps > 0, "bad step count");
+  cudaEvent_t e0, e1;
+  RLREP_CUDA(cudaEventCreate(&e0));
+  RLREP_CUDA(cudaEventCreate(&e1));
+  RLREP_CUDA(cudaStreamSynchronize(stream_));
+  RLREP_CUDA(cudaEventRecord(e0, stream_));
+  for (int i = 0; i < n_steps; ++i) launch_update(stddev);
+  RLREP_CUDA(cudaEventRecord(e1, stream_));
+  RLREP_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  RLREP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return ms;
+}
+
+std::vector<ProfileEntry> DrqV2::profile_update(float stddev) {
+  RLREP_CUDA(cudaStreamSynchronize(stream_));
+  profile_begin(stream_);
+  launch_update(stddev);
+  return profile_end(stream_);
+}
+
 void DrqV2::update(const unsigned char* img, const float* action, const float* reward, const float* discount,
                    const unsigned char* next_img, const int* shifts, const float* eps, float stddev, float* metrics_out) {
   cudaStream_t s = stream_;
@@ -200,6 +224,16 @@ void DrqV2::update(const unsigned char* img, const float* action, const float* r
   put(reward_dev_, reward, B_ * sizeof(float));
   put(discount_dev_, discount, B_ * sizeof(float));
   const long long before = launch_count();
+  launch_update(stddev);
+  last_launches = (int)(launch_count() - before);
+  RLREP_CUDA(cudaMemcpyAsync(metrics_host_, metrics_dev_, 8 * sizeof(float), cudaMemcpyDeviceToHost, s));
+  RLREP_CUDA(cudaStreamSynchronize(s));
+  std::memcpy(metrics_out, metrics_host_, 5 * sizeof(float));
+}
+
+// Every launch of one update on the batch currently resident in the device buffers.
+void DrqV2::launch_update(float stddev) {
+  cudaStream_t s = stream_;
 
   TickParams t;
   t.k_feat = 1;  // the encoder's Adam step uses the "feature" slot of the control block
@@ -273,11 +307,6 @@ void DrqV2::update(const unsigned char* img, const float* action, const float* r
     launch_colreduce_multi(jobs, 6, s);
   }
   launch_adam_polyak(actor_g_.p, actor_g_.g, actor_g_.m, actor_g_.v, actor_g_.n, &ctl_->actor, nullptr, 0, 0.f, nullptr, s);
-
-  last_launches = (int)(launch_count() - before);
-  RLREP_CUDA(cudaMemcpyAsync(metrics_host_, metrics_dev_, 8 * sizeof(float), cudaMemcpyDeviceToHost, s));
-  RLREP_CUDA(cudaStreamSynchronize(s));
-  std::memcpy(metrics_out, metrics_host_, 5 * sizeof(float));
 }
 
 }  // namespace rlrep

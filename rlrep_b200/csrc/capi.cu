@@ -426,6 +426,27 @@ int rlrep_drq_update(rlrep_drq* drq, const unsigned char* img, const float* acti
   drq->impl->update(img, action, reward, discount, next_img, shifts, eps, stddev, metrics_host);
   RLREP_API_END
 }
+int rlrep_drq_update_resident(rlrep_drq* drq, int n_steps, float stddev, float* total_ms) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(drq && total_ms, "null argument");
+  *total_ms = drq->impl->update_resident(n_steps, stddev);
+  RLREP_API_END
+}
+int rlrep_drq_profile_update(rlrep_drq* drq, float stddev, int max_entries, const char** names, float* ms, double* bytes,
+                             double* flops, int* n_entries) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(drq && n_entries && (max_entries == 0 || (names && ms)), "null argument");
+  std::vector<ProfileEntry> prof = drq->impl->profile_update(stddev);
+  const int n = (int)std::min<size_t>(prof.size(), (size_t)max_entries);
+  for (int i = 0; i < n; ++i) {
+    names[i] = prof[i].name;
+    ms[i] = prof[i].ms;
+    if (bytes) bytes[i] = prof[i].bytes;
+    if (flops) flops[i] = prof[i].flops;
+  }
+  *n_entries = (int)prof.size();
+  RLREP_API_END
+}
 int rlrep_drq_last_launches(rlrep_drq* drq, int* launches) {
   RLREP_API_BEGIN
   *launches = drq->impl->last_launches;

@@ -27,12 +27,17 @@ class DrqV2 {
   // metrics_out[5] = {critic_loss, mean(q_pred), mean(q_target), mean(reward), actor_loss}.
   void update(const unsigned char* img, const float* action, const float* reward, const float* discount,
               const unsigned char* next_img, const int* shifts, const float* eps, float stddev, float* metrics_out);
+  // Benchmark aids on the batch uploaded by the last update(): n_steps updates back to back, CUDA-event time of the loop
+  // in milliseconds; one update with an event behind every launch.
+  float update_resident(int n_steps, float stddev);
+  std::vector<ProfileEntry> profile_update(float stddev);
   void sync_targets_from_params();
   std::vector<ParamGroup*> groups() { return {&enc_->group(), &actor_g_, &crit_g_}; }
   cudaStream_t stream() const { return stream_; }
   int last_launches = 0;
 
  private:
+  void launch_update(float stddev);
   void trunk_forward(const LinearSlot& t, const ParamGroup& g, bool target, size_t ln_w, size_t ln_b, const float* x,
                      float* pre, float* out, int ld_out, float* xhat, float* rstd);
   void q_forward(bool target, int set);
