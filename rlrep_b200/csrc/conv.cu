@@ -106,6 +106,17 @@ __global__ void nchw_to_nhwc_relu_bwd_kernel(const float* __restrict__ dfeat, co
   }
 }
 
+// dW[o, k] = sum_p C[p*32 + o, p*ldk + k]: the diagonal blocks of the folded weight-gradient GEMM (see backward())
+__global__ void diag_block_sum_kernel(const float* __restrict__ C, int ldc, int P, int ldk, float* __restrict__ dW,
+                                      int ld_dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 32 * ldk) return;
+  const int o = i / ldk, k = i - o * ldk;
+  float acc = 0.f;
+  for (int p = 0; p < P; ++p) acc += C[(size_t)(p * 32 + o) * ldc + p * ldk + k];  // fixed order
+  dW[(size_t)o * ld_dw + k] = acc;
+}
+
 int grid_for(long long work, int threads) {
   const long long want = (work + threads - 1) / threads;
   return (int)std::min<long long>(want, (long long)kNumSMs * 16);
@@ -133,6 +144,7 @@ ConvEncoder::ConvEncoder(int batch, int in_channels, int height, Precision prec,
   }
   arena_.want(&dcol_, rows(1) * 288);
   arena_.want(&bias_partial_, kBiasChunks * 32);
+  arena_.want(&wfold_, (size_t)32 * kFold * 288 * kFold);
   arena_.commit();
   gemm_.init(prec, 0);
 }
@@ -163,7 +175,22 @@ void ConvEncoder::backward(const float* dfeat_dev) {
     const Linear w = conv_[l].view(g_);
     const Mat dy{dact_[l], 32};
     const Mat col = l == 0 ? Mat{col_[0], ldk1_} : Mat{col_[l], 288};
-    linear_wgrad(gemm_, s, (int)rows(l), dy, col, w, Mat(), 0, /*bias_grad=*/false);
+    // dW = dY^T col is a [32, 9 C_in] output over K = B*Ho*Wo ~ 4e5 rows: 32 of the tile's 128 rows and at most 8
+    // split-K CTAs per N-tile would leave the GPU idle.  Fold kFold consecutive rows into one: dY as [rows / F, 32 F],
+    // col as [rows / F, ldk F]; their product is an [32 F, ldk F] matrix whose F diagonal blocks sum to dW.  Same
+    // tensor-core work as before (the tile is now full), K shrinks F-fold and the N-tiles multiply F-fold.
+    if (rows(l) % kFold == 0) {
+      GemmArgs a;
+      a.M = 32 * kFold; a.N = col.ld * kFold; a.K = (int)(rows(l) / kFold);
+      a.A = dy.p; a.lda = 32 * kFold; a.a_mn = true;
+      a.B = col.p; a.ldb = col.ld * kFold; a.b_mn = true;
+      a.C = wfold_; a.ldc = a.N;
+      gemm_.run(a, s);
+      diag_block_sum_kernel<<<ceil_div(32 * col.ld, 256), 256, 0, s>>>(wfold_, a.N, kFold, col.ld, w.dW, w.ld);
+      RLREP_LAUNCHED("diag_block_sum", s);
+    } else {
+      linear_wgrad(gemm_, s, (int)rows(l), dy, col, w, Mat(), 0, /*bias_grad=*/false);
+    }
     launch_colsum_tall(dy.p, 32, rows(l), 32, bias_partial_, kBiasChunks, w.db, s);
     if (l == 0) break;
     linear_dgrad(gemm_, s, (int)rows(l), dy, w, DACT_NONE, Mat(), dcol_, 288);

@@ -35,6 +35,8 @@ class ConvEncoder {
   float* dcol_ = nullptr;
   static constexpr int kBiasChunks = 296;  // 2 x 148 SMs
   float* bias_partial_ = nullptr;
+  static constexpr int kFold = 4;  // rows folded per GEMM row in the weight-gradient GEMMs (conv.cu backward())
+  float* wfold_ = nullptr;
 };
 
 }  // namespace rlrep
