@@ -238,6 +238,10 @@ RLREP_EXPORT int rlrep_drq_sync_targets(rlrep_drq* drq);
 RLREP_EXPORT int rlrep_drq_update(rlrep_drq* drq, const unsigned char* img, const float* action, const float* reward,
                                   const float* discount, const unsigned char* next_img, const int* shifts,
                                   const float* eps, float stddev, float* metrics_host);
+/* select_action (drqv2.py:74-82): obs uint8 [C, H, H]; eps_host == NULL -> dist.mean, else TruncatedNormal.sample(clip=None)
+ * with eps[action_dim] ~ N(0, 1) and the schedule's stddev.  Not to be interleaved with rlrep_drq_update. */
+RLREP_EXPORT int rlrep_drq_act(rlrep_drq* drq, const unsigned char* obs_host, const float* eps_host, float stddev,
+                               float* action_host);
 /* Benchmark aids on the batch uploaded by the last rlrep_drq_update: n_steps updates back to back with CUDA-event timing;
  * one update with an event behind every launch (same contract as rlrep_agent_profile_train). */
 RLREP_EXPORT int rlrep_drq_update_resident(rlrep_drq* drq, int n_steps, float stddev, float* total_ms);

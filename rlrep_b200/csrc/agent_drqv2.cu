@@ -8,6 +8,8 @@
 // Adam(encoder);  actor step on the detached latent: actor -> sample -> critic (new weights) -> -mean(min Q) ->
 // dgrad through the critic to the action, backward through the actor -> Adam(actor).
 // Randomness (two shift draws, two [B, A] normal draws) and the std-dev schedule value come from the host.
+#include <algorithm>
+#include <cmath>
 #include <cstring>
 
 #include "agent.cuh"
@@ -101,7 +103,7 @@ DrqV2::DrqV2(const DrqConfig& c, cudaStream_t s)
   const size_t img_bytes = (size_t)B_ * c.channels * c.height * c.height;
   stage_bytes_ = 2 * img_bytes + (size_t)4 * B_ * sizeof(int) + ((size_t)2 * B_ * A_ + (size_t)B_ * A_ + 2 * B_) * sizeof(float);
   RLREP_CUDA(cudaMallocHost(&stage_host_, stage_bytes_));
-  RLREP_CUDA(cudaMallocHost(&metrics_host_, 8 * sizeof(float)));
+  RLREP_CUDA(cudaMallocHost(&metrics_host_, (size_t)std::max(8, A_) * sizeof(float)));
   Control h;
   std::memset(&h, 0, sizeof(h));
   RLREP_CUDA(cudaMemcpyAsync(ctl_, &h, sizeof(h), cudaMemcpyHostToDevice, stream_));
@@ -178,6 +180,30 @@ void DrqV2::actor_forward(const float* latent, const float* eps, float stddev, i
   linear_fwd(gemm_, stream_, B_, Mat{ap1_, H_}, l1, ACT_RELU, ap2_, H_);
   linear_fwd(gemm_, stream_, B_, Mat{ap2_, H_}, l2, ACT_NONE, raw_, LA_);
   launch_trunc_normal_sample(raw_, LA_, B_, A_, eps, stddev, cfg_.stddev_clip, mu_, cat_[set] + bn_, LC_, stream_);
+}
+
+// select_action (drqv2.py:74-82): encoder (no augmentation) -> actor -> mu (deterministic) or
+// TruncatedNormal.sample(clip=None) with the caller's standard-normal draw.  Runs the batch-sized kernels with the
+// observation in row 0 (the other rows carry stale frames and are ignored), so it must not be interleaved with an
+// update -- the reference's agent is single-threaded as well.
+void DrqV2::act(const unsigned char* obs_host, const float* eps_host, float stddev, float* action_host) {
+  cudaStream_t s = stream_;
+  const size_t one = (size_t)cfg_.channels * cfg_.height * cfg_.height;
+  RLREP_CUDA(cudaStreamSynchronize(s));
+  std::memcpy(stage_host_, obs_host, one);
+  float* eps_stage = reinterpret_cast<float*>(stage_host_ + ((one + 15) & ~size_t(15)));
+  for (int j = 0; j < A_; ++j) eps_stage[j] = eps_host ? eps_host[j] : 0.f;
+  RLREP_CUDA(cudaMemcpyAsync(img_dev_, stage_host_, one, cudaMemcpyHostToDevice, s));
+  RLREP_CUDA(cudaMemcpyAsync(eps_dev_, eps_stage, A_ * sizeof(float), cudaMemcpyHostToDevice, s));
+  enc_->forward(img_dev_, nullptr, latent_);
+  const float saved_clip = cfg_.stddev_clip;
+  cfg_.stddev_clip = INFINITY;  // clip=None
+  actor_forward(latent_, eps_dev_, eps_host ? stddev : 0.f, 0, false);
+  cfg_.stddev_clip = saved_clip;
+  RLREP_CUDA(cudaMemcpy2DAsync(metrics_host_, A_ * sizeof(float), cat_[0] + bn_, LC_ * sizeof(float), A_ * sizeof(float), 1,
+                               cudaMemcpyDeviceToHost, s));
+  RLREP_CUDA(cudaStreamSynchronize(s));
+  std::memcpy(action_host, metrics_host_, A_ * sizeof(float));
 }
 
 float DrqV2::update_resident(int n_steps, float stddev) {

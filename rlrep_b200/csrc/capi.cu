@@ -426,6 +426,12 @@ int rlrep_drq_update(rlrep_drq* drq, const unsigned char* img, const float* acti
   drq->impl->update(img, action, reward, discount, next_img, shifts, eps, stddev, metrics_host);
   RLREP_API_END
 }
+int rlrep_drq_act(rlrep_drq* drq, const unsigned char* obs_host, const float* eps_host, float stddev, float* action_host) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(drq && obs_host && action_host, "null argument");
+  drq->impl->act(obs_host, eps_host, stddev, action_host);
+  RLREP_API_END
+}
 int rlrep_drq_update_resident(rlrep_drq* drq, int n_steps, float stddev, float* total_ms) {
   RLREP_API_BEGIN
   RLREP_CHECK(drq && total_ms, "null argument");

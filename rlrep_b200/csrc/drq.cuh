@@ -31,6 +31,8 @@ class DrqV2 {
   // in milliseconds; one update with an event behind every launch.
   float update_resident(int n_steps, float stddev);
   std::vector<ProfileEntry> profile_update(float stddev);
+  // obs uint8 [C, H, H]; eps [A] standard normal or nullptr (deterministic: the mean); action [A]
+  void act(const unsigned char* obs_host, const float* eps_host, float stddev, float* action_host);
   void sync_targets_from_params();
   std::vector<ParamGroup*> groups() { return {&enc_->group(), &actor_g_, &crit_g_}; }
   cudaStream_t stream() const { return stream_; }

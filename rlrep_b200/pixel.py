@@ -122,9 +122,9 @@ class DrQv2:
     """Drop-in for the update path of agent.diffsrdrq.drqv2.DrQv2 (drqv2.py:12-148): same constructor
     (`obs_space`, `action_space`, `args` with tau / update_every / critic_loss / stddev_schedule / stddev_clip / bn_dim /
     actor_hidden_dim / critic_hidden_dim / encoder_lr / actor_lr / critic_lr) and `train_step(replay_iter, step)` with the
-    reference's metric keys.  The batch comes from the caller's replay iterator as in the reference
-    (img_stack uint8 [B, 9, 84, 84], action, reward, discount, next_img_stack, next_img_step).  `select_action` (B = 1
-    inference) is not part of this round."""
+    reference's metric keys, plus `select_action(obs, step, deterministic)`.  The batch comes from the caller's replay
+    iterator as in the reference (img_stack uint8 [B, 9, 84, 84], action, reward, discount, next_img_stack,
+    next_img_step)."""
 
     def __init__(self, obs_space, action_space, args, *, precision="tf32"):
         if not torch.cuda.is_available():
@@ -243,6 +243,27 @@ class DrQv2:
         z = torch.zeros(n, self.action_dim)
         eps = torch.stack([torch.normal(z, torch.ones_like(z)) for _ in range(2)])
         return shifts.to(torch.int32).numpy(), eps.numpy()
+
+    def select_action(self, obs, step, deterministic=False):
+        """drqv2.py:74-82.  `obs` is one uint8 frame stack [C, H, W]; the handle must exist (weights loaded after the
+        first train_step, or call `prepare(batch_size)` first)."""
+        if self._h is None:
+            raise _lib.RlrepError("call prepare(batch_size) or train_step once before select_action")
+        o = np.ascontiguousarray(torch.as_tensor(obs).cpu().numpy())
+        assert o.dtype == np.uint8 and tuple(o.shape) == self.obs_dim
+        stddev = float(self.stddev_schedule(step))
+        eps = None
+        if not deterministic:  # TruncatedNormal.sample(clip=None): one _standard_normal([1, A]) draw
+            z = torch.zeros(1, self.action_dim)
+            eps = np.ascontiguousarray(torch.normal(z, torch.ones_like(z)).numpy().reshape(-1))
+        out = np.empty(self.action_dim, dtype=np.float32)
+        _lib.check(self.lib.rlrep_drq_act(self._h, o.ctypes.data, eps.ctypes.data if eps is not None else None, stddev,
+                                          out.ctypes.data))
+        return out
+
+    def prepare(self, batch_size):
+        """Create the device handle for `batch_size` ahead of the first train_step."""
+        self._ensure(int(batch_size))
 
     def train_step(self, replay_iter, step):
         self._step += 1

@@ -130,3 +130,22 @@ def test_drq_update_matches_oracle(C, A, bn, H, B, precision):
     assert worst["after_adam"][0] < tol["after_adam"], worst["after_adam"]
     assert worst_p < tol["param"], wname
     agent.close()
+
+
+def test_drq_select_action_matches_oracle():
+    from oracle import drq_oracle as D
+    from rlrep_b200.pixel import DrQv2
+    C, A, bn, H, B = 9, 4, 50, 256, 8
+    init = D.init_state(C, A, bn, H, seed=0)
+    oracle = D.OracleDrQv2(A, init)
+    agent = DrQv2(Box((C, 84, 84)), Box((A,)), _args(bn, H), precision="fp32")
+    agent.load_state_dict(init)
+    agent.prepare(B)
+    obs = D.synthetic_pixel_batch(1, C, 84, A, seed=3).img[0]
+    assert np.allclose(agent.select_action(obs, 1000, deterministic=True), oracle.select_action(obs, 1000, True), atol=2e-5)
+    torch.manual_seed(4)
+    a_c = agent.select_action(obs, 250000)
+    torch.manual_seed(4)
+    a_o = oracle.select_action(obs, 250000)
+    assert np.allclose(a_c, a_o, atol=2e-5), (a_c, a_o)
+    agent.close()
