@@ -207,6 +207,9 @@ class SacBase : public Agent {
     arena_.want(&ah1_, (size_t)B_ * AH_);
     arena_.want(&ah2_, (size_t)B_ * AH_);
     arena_.want(&head_, (size_t)B_ * round_up32(2 * A_));  // pitch LDH_: the head runs as an N = 32k tensor-core GEMM
+    arena_.want(&bh1_, (size_t)B_ * AH_);
+    arena_.want(&bh2_, (size_t)B_ * AH_);
+    arena_.want(&bhead_, (size_t)B_ * round_up32(2 * A_));
     arena_.want(&action_, (size_t)B_ * A_);
     arena_.want(&logp_, B_);
     arena_.want(&dhead_, (size_t)B_ * LDH_);
@@ -243,12 +246,18 @@ class SacBase : public Agent {
   // actor(obs) -> head_, then rsample with eps -> action_out [B, A], logp_out [B]
   // action_out may point into a cat(obs, action) buffer (cat_next_ / cat_pi_, pitch LDSA_): pass cat = true to have
   // the sampling kernel copy obs in front of the action, so the next network reads ONE contiguous input.
-  Mat actor_forward_cat(Mat obs, const float* eps, float* cat_buf, float* logp_out) {
+  // `set` selects the activation buffers: 0 = the set actor_backward() reads (the actor step's forward), 1 = a scratch
+  // set for forwards without a backward (a' = pi(s') of the critic step), so both can be in flight at once.
+  Mat actor_forward_cat(Mat obs, const float* eps, float* cat_buf, float* logp_out, cudaStream_t s = nullptr, int set = 0) {
+    if (s == nullptr) s = stream;
     const Linear l0 = a0_.view(actor_g_), l1 = a1_.view(actor_g_), l2 = a2_.view(actor_g_);
-    linear_fwd(gemm_, stream, B_, obs, l0, ACT_ELU, ah1_, AH_);
-    linear_fwd(gemm_, stream, B_, Mat{ah1_, AH_}, l1, ACT_ELU, ah2_, AH_);
-    linear_fwd(gemm_, stream, B_, Mat{ah2_, AH_}, l2, ACT_NONE, head_, LDH_);
-    launch_actor_sample(head_, LDH_, B_, A_, eps, cat_buf + S_, LDSA_, logp_out, stream, obs.p, obs.ld, S_);
+    float* h1 = set == 0 ? ah1_ : bh1_;
+    float* h2 = set == 0 ? ah2_ : bh2_;
+    float* hd = set == 0 ? head_ : bhead_;
+    linear_fwd(gemm_, s, B_, obs, l0, ACT_ELU, h1, AH_);
+    linear_fwd(gemm_, s, B_, Mat{h1, AH_}, l1, ACT_ELU, h2, AH_);
+    linear_fwd(gemm_, s, B_, Mat{h2, AH_}, l2, ACT_NONE, hd, LDH_);
+    launch_actor_sample(hd, LDH_, B_, A_, eps, cat_buf + S_, LDSA_, logp_out, s, obs.p, obs.ld, S_);
     return Mat{cat_buf, LDSA_};
   }
   void actor_forward(Mat obs, const float* eps, float* action_out, float* logp_out) {
@@ -257,13 +266,6 @@ class SacBase : public Agent {
     linear_fwd(gemm_, stream, B_, Mat{ah1_, AH_}, l1, ACT_ELU, ah2_, AH_);
     linear_fwd(gemm_, stream, B_, Mat{ah2_, AH_}, l2, ACT_NONE, head_, LDH_);
     launch_actor_sample(head_, LDH_, B_, A_, eps, action_out, A_, logp_out, stream);
-  }
-  // one launch for the three actor bias gradients (dY buffers of actor_backward are all still live)
-  void actor_bias_grads() {
-    const Linear l0 = a0_.view(actor_g_), l1 = a1_.view(actor_g_), l2 = a2_.view(actor_g_);
-    const ColJob jobs[3] = {bias_job(B_, Mat{dhead_, LDH_}, l2), bias_job(B_, Mat{dah2_, AH_}, l1),
-                            bias_job(B_, Mat{dah1_, AH_}, l0)};
-    launch_colreduce_multi(jobs, 3, stream);
   }
   // Where the first layer of a network fed with cat(obs, action) writes its input gradient so that actor_backward finds
   // d(action) at dsa_[:, S:S+A].  On the tensor-core path the dgrad runs over ALL (padded) input columns -- N must be a
@@ -284,13 +286,23 @@ class SacBase : public Agent {
   // in ah1_/ah2_/head_.  Leaves the actor gradients in actor_g_.g.
   void actor_backward(Mat obs, const float* eps) {
     const Linear l0 = a0_.view(actor_g_), l1 = a1_.view(actor_g_), l2 = a2_.view(actor_g_);
+    // dgrad chain on the main stream; weight / bias gradients trail it on an aux branch
+    cudaStream_t w = use_aux_ ? aux(1) : stream;
     launch_actor_sample_bwd(head_, LDH_, B_, A_, eps, dsa_ + S_, LDSA_, dlogp_, dhead_, LDH_, stream);
-    linear_wgrad(gemm_, stream, B_, Mat{dhead_, LDH_}, Mat{ah2_, AH_}, l2, Mat(), 0, false);
+    wait_for(w, mark(stream));
+    linear_wgrad(gemm_, w, B_, Mat{dhead_, LDH_}, Mat{ah2_, AH_}, l2, Mat(), 0, false);
     linear_dgrad(gemm_, stream, B_, Mat{dhead_, LDH_}, l2, DACT_ELU_OUT, Mat{ah2_, AH_}, dah2_, AH_);
-    linear_wgrad(gemm_, stream, B_, Mat{dah2_, AH_}, Mat{ah1_, AH_}, l1, Mat(), 0, false);
+    wait_for(w, mark(stream));
+    linear_wgrad(gemm_, w, B_, Mat{dah2_, AH_}, Mat{ah1_, AH_}, l1, Mat(), 0, false);
     linear_dgrad(gemm_, stream, B_, Mat{dah2_, AH_}, l1, DACT_ELU_OUT, Mat{ah1_, AH_}, dah1_, AH_);
     linear_wgrad(gemm_, stream, B_, Mat{dah1_, AH_}, obs, l0, Mat(), 0, false);
-    actor_bias_grads();
+    wait_for(w, mark(stream));
+    {
+      const ColJob jobs[3] = {bias_job(B_, Mat{dhead_, LDH_}, l2), bias_job(B_, Mat{dah2_, AH_}, l1),
+                              bias_job(B_, Mat{dah1_, AH_}, l0)};
+      launch_colreduce_multi(jobs, 3, w);
+    }
+    if (use_aux_) join_aux(1, stream);
   }
   void actor_adam() {
     launch_adam_polyak(actor_g_.p, actor_g_.g, actor_g_.m, actor_g_.v, actor_g_.n, &ctl->actor, nullptr, 0, 0.f,
@@ -339,7 +351,7 @@ class SacBase : public Agent {
   float* batch_ = nullptr;
   float *ah1_ = nullptr, *ah2_ = nullptr, *head_ = nullptr, *action_ = nullptr, *logp_ = nullptr;
   float *dhead_ = nullptr, *dah2_ = nullptr, *dah1_ = nullptr, *dsa_ = nullptr, *dlogp_ = nullptr;
-  float *cat_next_ = nullptr, *cat_pi_ = nullptr;
+  float *cat_next_ = nullptr, *cat_pi_ = nullptr, *bh1_ = nullptr, *bh2_ = nullptr, *bhead_ = nullptr;
   float *act_dev_ = nullptr, *act_h1_ = nullptr, *act_h2_ = nullptr, *act_head_ = nullptr, *act_out_ = nullptr,
         *act_logp_ = nullptr, *act_host_ = nullptr;
 };

@@ -71,6 +71,9 @@ class CtrlSacAgent final : public SacBase {
     arena_.want(&dg1_, BH);
     arena_.want(&hb1_, BH);
     arena_.want(&hb2_, BH);
+    arena_.want(&hc1_, BH);
+    arena_.want(&hc2_, BH);
+    arena_.want(&zpi_, BD);
     arena_.want(&logits_, (size_t)B_ * B_);
     arena_.want(&loss_rows_, B_);
     arena_.want(&rpred_, B_);
@@ -240,8 +243,17 @@ class CtrlSacAgent final : public SacBase {
     const float* eps = eps_dev_;
     cudaStream_t s0 = stream, s1 = side();
     fork();
+    if (use_aux_) {
+      // Hoisted out of the actor step: a_pi ~ pi(s) and frozen_phi(s, a_pi) read only the actor, phi, the batch and the
+      // noise -- nothing the critic step writes -- so they run beside it on an aux branch; the actor step joins it
+      // before it evaluates the UPDATED critic on these features (reference order, ctrlsac_agent.py:299-305).
+      cudaStream_t a0 = aux(0);
+      wait_for(a0, mark(s0));
+      const Mat spi = actor_forward_cat(Mat{batch_, R_}, eps_dev_ + (size_t)B_ * A_, cat_pi_, logp_, a0, /*set=*/0);
+      phi_forward(a0, spi, Mat(), 0, zpi_, hc1_, hc2_);
+    }
     // main stream: a' ~ pi(s'), frozen_phi_target(s', a'), target critic
-    const Mat s2a = actor_forward_cat(s2(), eps, cat_next_, logp2_);
+    const Mat s2a = actor_forward_cat(s2(), eps, cat_next_, logp2_, s0, /*set=*/1);
     phi_forward(s0, s2a, Mat(), 0, zmu_, h1_, h2_);  // zmu_ is free after the feature loop
     critic_forward(s0, zmu_, /*target=*/true, hid_t_, nq1_, nq2_);
     // side stream: frozen_phi_target(s, a) and the live critic on it
@@ -269,9 +281,13 @@ class CtrlSacAgent final : public SacBase {
   void actor_step() {  // ctrlsac_agent.py:295-325
     const float* eps = eps_dev_ + (size_t)B_ * A_;
     const Mat s{batch_, R_};
-    const Mat spi = actor_forward_cat(s, eps, cat_pi_, logp_);
-    phi_forward(stream, spi, Mat(), 0, zphi_, h1_, h2_);  // frozen_phi(s, a_pi)
-    critic_forward(stream, zphi_, false, hid_, q1_, q2_);
+    if (use_aux_) {
+      join_aux(0, stream);  // a_pi, log pi and frozen_phi(s, a_pi) were computed beside the critic step
+    } else {
+      const Mat spi = actor_forward_cat(s, eps, cat_pi_, logp_);
+      phi_forward(stream, spi, Mat(), 0, zpi_, hc1_, hc2_);  // frozen_phi(s, a_pi)
+    }
+    critic_forward(stream, zpi_, false, hid_, q1_, q2_);
     launch_actor_alpha_loss(q1_, q2_, logp_, B_, (float)(-A_), cfg.learn_alpha, ctl, dq1_, dq2_, dlogp_,
                             metrics_dev_ + 7, stream);
     // ---- dgrad only, back to the action input of phi
@@ -279,8 +295,8 @@ class CtrlSacAgent final : public SacBase {
     const Linear l1 = p1_.view(feat_g_), l2 = p2_.view(feat_g_), l3 = p3_.view(feat_g_);
     critic_heads_backward_to_hidden();
     linear_dgrad(gemm_, stream, B_, Mat{dhid_, 2 * H_}, l14, DACT_NONE, Mat(), dzphi_, D_);
-    linear_dgrad(gemm_, stream, B_, Mat{dzphi_, D_}, l3, DACT_ELU_OUT, Mat{h2_, H_}, dh2_, H_);
-    linear_dgrad(gemm_, stream, B_, Mat{dh2_, H_}, l2, DACT_ELU_OUT, Mat{h1_, H_}, dh1_, H_);
+    linear_dgrad(gemm_, stream, B_, Mat{dzphi_, D_}, l3, DACT_ELU_OUT, Mat{hc2_, H_}, dh2_, H_);
+    linear_dgrad(gemm_, stream, B_, Mat{dh2_, H_}, l2, DACT_ELU_OUT, Mat{hc1_, H_}, dh1_, H_);
     dgrad_to_action(Mat{dh1_, H_}, l1);
     actor_backward(s, eps);
     actor_adam();
@@ -291,7 +307,7 @@ class CtrlSacAgent final : public SacBase {
   LinearSlot p1_, p2_, p3_, m1_, m2_, m3_, th_, c14_, c2_, c5_;
   float *h1_ = nullptr, *h2_ = nullptr, *g1_ = nullptr, *g2_ = nullptr, *zphi_ = nullptr, *zmu_ = nullptr;
   float *dzphi_ = nullptr, *dzmu_ = nullptr, *dh2_ = nullptr, *dh1_ = nullptr, *logits_ = nullptr;
-  float *dg2_ = nullptr, *dg1_ = nullptr, *hb1_ = nullptr, *hb2_ = nullptr;
+  float *dg2_ = nullptr, *dg1_ = nullptr, *hb1_ = nullptr, *hb2_ = nullptr, *hc1_ = nullptr, *hc2_ = nullptr, *zpi_ = nullptr;
   float *loss_rows_ = nullptr, *rpred_ = nullptr, *drp_ = nullptr, *hid_ = nullptr, *hid_t_ = nullptr,
         *dhid_ = nullptr;
   float *q1_ = nullptr, *q2_ = nullptr, *nq1_ = nullptr, *nq2_ = nullptr, *dq1_ = nullptr, *dq2_ = nullptr;
