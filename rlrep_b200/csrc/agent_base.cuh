@@ -210,7 +210,6 @@ class SacBase : public Agent {
     arena_.want(&bh1_, (size_t)B_ * AH_);
     arena_.want(&bh2_, (size_t)B_ * AH_);
     arena_.want(&bhead_, (size_t)B_ * round_up32(2 * A_));
-    arena_.want(&action_, (size_t)B_ * A_);
     arena_.want(&logp_, B_);
     arena_.want(&dhead_, (size_t)B_ * LDH_);
     arena_.want(&dah2_, (size_t)B_ * AH_);
@@ -260,13 +259,6 @@ class SacBase : public Agent {
     launch_actor_sample(hd, LDH_, B_, A_, eps, cat_buf + S_, LDSA_, logp_out, s, obs.p, obs.ld, S_);
     return Mat{cat_buf, LDSA_};
   }
-  void actor_forward(Mat obs, const float* eps, float* action_out, float* logp_out) {
-    const Linear l0 = a0_.view(actor_g_), l1 = a1_.view(actor_g_), l2 = a2_.view(actor_g_);
-    linear_fwd(gemm_, stream, B_, obs, l0, ACT_ELU, ah1_, AH_);
-    linear_fwd(gemm_, stream, B_, Mat{ah1_, AH_}, l1, ACT_ELU, ah2_, AH_);
-    linear_fwd(gemm_, stream, B_, Mat{ah2_, AH_}, l2, ACT_NONE, head_, LDH_);
-    launch_actor_sample(head_, LDH_, B_, A_, eps, action_out, A_, logp_out, stream);
-  }
   // Where the first layer of a network fed with cat(obs, action) writes its input gradient so that actor_backward finds
   // d(action) at dsa_[:, S:S+A].  On the tensor-core path the dgrad runs over ALL (padded) input columns -- N must be a
   // multiple of 32 there and the few extra columns are free -- otherwise only over the action columns.
@@ -282,7 +274,7 @@ class SacBase : public Agent {
     const ActionGradDst d = action_grad_dst(first);
     linear_dgrad(gemm_, stream, B_, dy, first, DACT_NONE, Mat(), d.dx, d.ld, d.col0, d.n_cols);
   }
-  // Needs d(action) in dsa_[:, S:S+A] and *dlogp_; the activations of the matching actor_forward(obs, eps, ...) must still be
+  // Needs d(action) in dsa_[:, S:S+A] and *dlogp_; the activations of the matching actor_forward_cat(obs, eps, ..., set 0) must still be
   // in ah1_/ah2_/head_.  Leaves the actor gradients in actor_g_.g.
   void actor_backward(Mat obs, const float* eps) {
     const Linear l0 = a0_.view(actor_g_), l1 = a1_.view(actor_g_), l2 = a2_.view(actor_g_);
@@ -349,7 +341,7 @@ class SacBase : public Agent {
   long long *idx_dev_ = nullptr, *idx_host_ = nullptr;
   float *eps_dev_ = nullptr, *eps_host_ = nullptr;
   float* batch_ = nullptr;
-  float *ah1_ = nullptr, *ah2_ = nullptr, *head_ = nullptr, *action_ = nullptr, *logp_ = nullptr;
+  float *ah1_ = nullptr, *ah2_ = nullptr, *head_ = nullptr, *logp_ = nullptr;
   float *dhead_ = nullptr, *dah2_ = nullptr, *dah1_ = nullptr, *dsa_ = nullptr, *dlogp_ = nullptr;
   float *cat_next_ = nullptr, *cat_pi_ = nullptr, *bh1_ = nullptr, *bh2_ = nullptr, *bhead_ = nullptr;
   float *act_dev_ = nullptr, *act_h1_ = nullptr, *act_h2_ = nullptr, *act_head_ = nullptr, *act_out_ = nullptr,

@@ -87,7 +87,6 @@ class CtrlSacAgent final : public SacBase {
     arena_.want(&nq2_, B_);
     arena_.want(&dq1_, B_);
     arena_.want(&dq2_, B_);
-    arena_.want(&a2_act_, (size_t)B_ * A_);
     arena_.want(&logp2_, B_);
     finish_setup((size_t)8 << 20);
 
@@ -311,7 +310,7 @@ class CtrlSacAgent final : public SacBase {
   float *loss_rows_ = nullptr, *rpred_ = nullptr, *drp_ = nullptr, *hid_ = nullptr, *hid_t_ = nullptr,
         *dhid_ = nullptr;
   float *q1_ = nullptr, *q2_ = nullptr, *nq1_ = nullptr, *nq2_ = nullptr, *dq1_ = nullptr, *dq2_ = nullptr;
-  float *a2_act_ = nullptr, *logp2_ = nullptr;
+  float *logp2_ = nullptr;
   std::vector<std::string> names_;
 };
 

@@ -84,7 +84,6 @@ class CtrlSacShardedAgent final : public SacBase {
     arena_.want(&hid_, 2 * BH); arena_.want(&hid_t_, 2 * BH); arena_.want(&dhid_, 2 * BH);
     arena_.want(&q1_, B_); arena_.want(&q2_, B_); arena_.want(&nq1_, B_); arena_.want(&nq2_, B_);
     arena_.want(&dq1_, B_); arena_.want(&dq2_, B_);
-    arena_.want(&a2_act_, (size_t)B_ * A_);
     arena_.want(&logp2_, B_);
     arena_.want(&apart_, 4);
     finish_setup(0);
@@ -269,7 +268,7 @@ class CtrlSacShardedAgent final : public SacBase {
   float *zmu_all_ = nullptr, *dmu_all_ = nullptr, *logits_ = nullptr;
   float *loss_rows_ = nullptr, *rpred_ = nullptr, *drp_ = nullptr, *hid_ = nullptr, *hid_t_ = nullptr, *dhid_ = nullptr;
   float *q1_ = nullptr, *q2_ = nullptr, *nq1_ = nullptr, *nq2_ = nullptr, *dq1_ = nullptr, *dq2_ = nullptr;
-  float *a2_act_ = nullptr, *logp2_ = nullptr, *apart_ = nullptr;
+  float *logp2_ = nullptr, *apart_ = nullptr;
   std::vector<std::string> names_;
 };
 

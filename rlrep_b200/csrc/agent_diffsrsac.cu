@@ -53,6 +53,8 @@ class DiffSrSacAgent final : public SacBase {
     ld_flat_ = round_up32(D_ * S_);
     phi_acts_.want(arena_, phi_, B_, true);
     phi_acts_b_.want(arena_, phi_, B_, false);
+    phi_acts_c_.want(arena_, phi_, B_, true);
+    arena_.want(&zpi_, (size_t)B_ * D_);
     nabla_acts_.want(arena_, nabla_, B_, true);
     arena_.want(&xin_, (size_t)B_ * ld_x_);
     arena_.want(&target_, (size_t)B_ * S_);
@@ -65,7 +67,6 @@ class DiffSrSacAgent final : public SacBase {
     arena_.want(&dscore_, (size_t)B_ * S_);
     arena_.want(&loss_rows_, B_);
     arena_.want(&dq_, 2 * B_);
-    arena_.want(&a2_act_, (size_t)B_ * A_);
     arena_.want(&logp2_, B_);
     finish_setup(0);
 
@@ -137,7 +138,15 @@ class DiffSrSacAgent final : public SacBase {
     const float* eps = eps_dev_ + (size_t)K_ * B_ * S_;
     cudaStream_t s0 = stream, s1 = side();
     fork();
-    const Mat s2a = actor_forward_cat(s2(), eps, cat_next_, logp2_);
+    if (use_aux_) {
+      // Hoisted out of the actor step (see agent_ctrlsac.cu): a_pi ~ pi(s) and phi(s, a_pi) read nothing the critic step
+      // writes, so they run beside it on an aux branch; the actor step joins before it evaluates the updated critic.
+      cudaStream_t a0 = aux(0);
+      wait_for(a0, mark(s0));
+      const Mat spi = actor_forward_cat(Mat{batch_, R_}, eps_dev_ + (size_t)K_ * B_ * S_ + (size_t)B_ * A_, cat_pi_, logp_, a0, /*set=*/0);
+      trunk_forward(gemm_, a0, B_, phi_, feat_g_, false, spi, Mat(), 0, phi_acts_c_, zpi_, D_);
+    }
+    const Mat s2a = actor_forward_cat(s2(), eps, cat_next_, logp2_, s0, /*set=*/1);
     trunk_forward(gemm_, s0, B_, phi_, feat_g_, false, s2a, Mat(), 0, phi_acts_, zphi_, D_);
     critic_.forward(gemm_, s0, crit_g_, /*target=*/true, 0, zphi_);
     trunk_forward(gemm_, s1, B_, phi_, feat_g_, false, sa(), Mat(), 0, phi_acts_b_, zb_, D_);
@@ -150,14 +159,18 @@ class DiffSrSacAgent final : public SacBase {
   void actor_step() {  // diffsrsac_agent.py:241-269
     const float* eps = eps_dev_ + (size_t)K_ * B_ * S_ + (size_t)B_ * A_;
     const Mat s{batch_, R_};
-    const Mat spi = actor_forward_cat(s, eps, cat_pi_, logp_);
-    trunk_forward(gemm_, stream, B_, phi_, feat_g_, false, spi, Mat(), 0, phi_acts_, zphi_, D_);
-    critic_.forward(gemm_, stream, crit_g_, false, 0, zphi_);
+    if (use_aux_) {
+      join_aux(0, stream);
+    } else {
+      const Mat spi = actor_forward_cat(s, eps, cat_pi_, logp_);
+      trunk_forward(gemm_, stream, B_, phi_, feat_g_, false, spi, Mat(), 0, phi_acts_c_, zpi_, D_);
+    }
+    critic_.forward(gemm_, stream, crit_g_, false, 0, zpi_);
     launch_actor_alpha_loss(critic_.q[0], critic_.q[0] + B_, logp_, B_, (float)(-A_), cfg.learn_alpha, ctl, dq_,
                             dq_ + B_, dlogp_, metrics_dev_ + 5, stream);
-    critic_.backward(gemm_, stream, crit_g_, 0, zphi_, dq_, /*wgrad=*/false, dzphi_);
+    critic_.backward(gemm_, stream, crit_g_, 0, zpi_, dq_, /*wgrad=*/false, dzphi_);
     const ActionGradDst ad = action_grad_dst(phi_.l[0].view(feat_g_));
-    trunk_backward(gemm_, stream, B_, phi_, feat_g_, false, Mat{dzphi_, D_}, s, phi_acts_, false, nullptr, ad.dx, ad.ld,
+    trunk_backward(gemm_, stream, B_, phi_, feat_g_, false, Mat{dzphi_, D_}, s, phi_acts_c_, false, nullptr, ad.dx, ad.ld,
                    ad.col0, ad.n_cols);
     actor_backward(s, eps);
     actor_adam();
@@ -169,11 +182,12 @@ class DiffSrSacAgent final : public SacBase {
   ParamGroup feat_g_, crit_g_, table_g_;
   size_t table_off_ = 0;
   Trunk phi_, nabla_;
-  TrunkActs phi_acts_, phi_acts_b_, nabla_acts_;
+  TrunkActs phi_acts_, phi_acts_b_, phi_acts_c_, nabla_acts_;
+  float* zpi_ = nullptr;
   RffCritic critic_;
   float *xin_ = nullptr, *target_ = nullptr, *coef_ = nullptr, *zphi_ = nullptr, *zb_ = nullptr, *dzphi_ = nullptr;
   float *flat_ = nullptr, *dflat_ = nullptr, *dscore_ = nullptr, *loss_rows_ = nullptr;
-  float *dq_ = nullptr, *a2_act_ = nullptr, *logp2_ = nullptr;
+  float *dq_ = nullptr, *logp2_ = nullptr;
   std::vector<std::string> names_;
 };
 

@@ -51,7 +51,6 @@ class SacAgent final : public SacBase {
     arena_.want(&nq2_, B_);
     arena_.want(&dq1_, B_);
     arena_.want(&dq2_, B_);
-    arena_.want(&a2_act_, (size_t)B_ * A_);
     arena_.want(&logp2_, B_);
     finish_setup((size_t)4 << 20);
     names_ = {"q1_loss", "q2_loss", "q1", "q2", "actor_loss", "alpha_loss", "alpha"};
@@ -137,7 +136,7 @@ class SacAgent final : public SacBase {
   float *hid0_ = nullptr, *hid1a_ = nullptr, *hid1b_ = nullptr, *dhid0_ = nullptr, *dhid1a_ = nullptr,
         *dhid1b_ = nullptr;
   float *q1_ = nullptr, *q2_ = nullptr, *nq1_ = nullptr, *nq2_ = nullptr, *dq1_ = nullptr, *dq2_ = nullptr;
-  float *a2_act_ = nullptr, *logp2_ = nullptr;
+  float *logp2_ = nullptr;
   std::vector<std::string> names_;
 };
 

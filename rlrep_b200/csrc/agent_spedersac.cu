@@ -53,6 +53,8 @@ class SpederSacAgent final : public SacBase {
     phi_acts_.want(arena_, phi_, 2 * B_, true);
     mu_acts_.want(arena_, mu_, 2 * B_, true);
     phi_acts_b_.want(arena_, phi_, B_, false);
+    phi_acts_c_.want(arena_, phi_, B_, true);
+    arena_.want(&zpi_, (size_t)B_ * D_);
     arena_.want(&zphi_, BD2);
     arena_.want(&zmu_, BD2);
     arena_.want(&dzphi_, BD2);
@@ -65,7 +67,6 @@ class SpederSacAgent final : public SacBase {
     arena_.want(&rpred_, B_);
     arena_.want(&drp_, B_);
     arena_.want(&dq_, 2 * B_);
-    arena_.want(&a2_act_, (size_t)B_ * A_);
     arena_.want(&logp2_, B_);
     finish_setup(0);
 
@@ -144,7 +145,15 @@ class SpederSacAgent final : public SacBase {
     const float* eps = eps_dev_;
     cudaStream_t s0 = stream, s1 = side();
     fork();
-    const Mat s2a = actor_forward_cat(s2(), eps, cat_next_, logp2_);
+    if (use_aux_) {
+      // Hoisted out of the actor step (see agent_ctrlsac.cu): a_pi ~ pi(s) and phi(s, a_pi) read nothing the critic step
+      // writes, so they run beside it on an aux branch; the actor step joins before it evaluates the updated critic.
+      cudaStream_t a0 = aux(0);
+      wait_for(a0, mark(s0));
+      const Mat spi = actor_forward_cat(Mat{batch_, R_}, eps_dev_ + (size_t)B_ * A_, cat_pi_, logp_, a0, /*set=*/0);
+      trunk_forward(gemm_, a0, B_, phi_, feat_g_, false, spi, Mat(), 0, phi_acts_c_, zpi_, D_);
+    }
+    const Mat s2a = actor_forward_cat(s2(), eps, cat_next_, logp2_, s0, /*set=*/1);
     trunk_forward(gemm_, s0, B_, phi_, feat_g_, false, s2a, Mat(), 0, phi_acts_, zmu_, D_);
     critic_.forward(gemm_, s0, crit_g_, /*target=*/true, 0, zmu_);
     trunk_forward(gemm_, s1, B_, phi_, feat_g_, false, sa(), Mat(), 0, phi_acts_b_, zb_, D_);
@@ -160,14 +169,18 @@ class SpederSacAgent final : public SacBase {
   void actor_step() {  // spedersac_agent.py:259-289
     const float* eps = eps_dev_ + (size_t)B_ * A_;
     const Mat s{batch_, R_};
-    const Mat spi = actor_forward_cat(s, eps, cat_pi_, logp_);
-    trunk_forward(gemm_, stream, B_, phi_, feat_g_, false, spi, Mat(), 0, phi_acts_, zphi_, D_);
-    critic_.forward(gemm_, stream, crit_g_, false, 0, zphi_);
+    if (use_aux_) {
+      join_aux(0, stream);
+    } else {
+      const Mat spi = actor_forward_cat(s, eps, cat_pi_, logp_);
+      trunk_forward(gemm_, stream, B_, phi_, feat_g_, false, spi, Mat(), 0, phi_acts_c_, zpi_, D_);
+    }
+    critic_.forward(gemm_, stream, crit_g_, false, 0, zpi_);
     launch_actor_alpha_loss(critic_.q[0], critic_.q[0] + B_, logp_, B_, (float)(-A_), cfg.learn_alpha, ctl, dq_,
                             dq_ + B_, dlogp_, metrics_dev_ + 7, stream);
-    critic_.backward(gemm_, stream, crit_g_, 0, zphi_, dq_, /*wgrad=*/false, dzphi_);
+    critic_.backward(gemm_, stream, crit_g_, 0, zpi_, dq_, /*wgrad=*/false, dzphi_);
     const ActionGradDst ad = action_grad_dst(phi_.l[0].view(feat_g_));
-    trunk_backward(gemm_, stream, B_, phi_, feat_g_, false, Mat{dzphi_, D_}, s, phi_acts_, false, nullptr, ad.dx, ad.ld,
+    trunk_backward(gemm_, stream, B_, phi_, feat_g_, false, Mat{dzphi_, D_}, s, phi_acts_c_, false, nullptr, ad.dx, ad.ld,
                    ad.col0, ad.n_cols);
     actor_backward(s, eps);
     actor_adam();
@@ -176,12 +189,13 @@ class SpederSacAgent final : public SacBase {
   int H_ = 0, D_ = 0, K_ = 0, off_r_ = 0, off_d_ = 0, off_s2_ = 0;
   ParamGroup feat_g_, crit_g_;
   Trunk phi_, mu_;
-  TrunkActs phi_acts_, mu_acts_, phi_acts_b_;
+  TrunkActs phi_acts_, mu_acts_, phi_acts_b_, phi_acts_c_;
+  float* zpi_ = nullptr;
   LinearSlot th_;
   RffCritic critic_;
   float *zphi_ = nullptr, *zmu_ = nullptr, *dzphi_ = nullptr, *dzmu_ = nullptr, *zb_ = nullptr;
   float *u_ = nullptr, *w_ = nullptr, *diag_ = nullptr, *c_ = nullptr, *rpred_ = nullptr, *drp_ = nullptr;
-  float *dq_ = nullptr, *a2_act_ = nullptr, *logp2_ = nullptr;
+  float *dq_ = nullptr, *logp2_ = nullptr;
   std::vector<std::string> names_;
 };
 
