@@ -191,6 +191,17 @@ TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* /*ws*/, s
     p.stages = pick_stages(p.bn, nkb, false);
     p.push = false;
   }
+  {
+    // Opt-in (RLREP_TC_PERSIST=1): the persistent variant is correct (the GEMM / conv / DrQ parity tests pass with
+    // it) but not yet faster -- its row-per-thread epilogue issues 32 partial-line stores per instruction, which costs
+    // more than the per-tile setup it saves (round 1: DrQ-v2 7.4 vs 5.5 ms/update, 2048x16384x2048 347 vs 335 us).
+    static const int persist_on = [] {
+      const char* e = std::getenv("RLREP_TC_PERSIST");
+      return e ? std::atoi(e) : 0;
+    }();
+    const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, p.bn);
+    p.persistent = persist_on && p.split_k == 1 && tiles >= 2 * kNumSMs;
+  }
   // K-major operand: matrix [rows = M|N, cols = K]; MN-major: matrix [rows = K, cols = M|N].
   p.tmA = a.a_mn ? make_map_mnmajor(a.A, a.K, a.M, a.lda, BM) : make_map_kmajor(a.A, a.M, a.K, a.lda, BM);
   p.tmB = a.b_mn ? make_map_mnmajor(a.B, a.K, a.N, a.ldb, p.bn) : make_map_kmajor(a.B, a.N, a.K, a.ldb, p.bn);

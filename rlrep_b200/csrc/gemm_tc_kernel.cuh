@@ -26,6 +26,7 @@
 // This header holds the device code and the per-variant launcher; it is included by the gemm_tc_inst_*.cu units (one
 // per (BN, A-major) pair so the 16 kernel variants compile in parallel) and by gemm_tc.cu for the tile constants.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 
 #include "common.cuh"
@@ -467,6 +468,168 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (threadIdx.x == 64) trace(8);
 }
 
+// ------------------------------------------------------------------------------------------------ persistent variant
+// For GEMMs with many output tiles and no split-K (the conv lowering: 3,000+ tiles of 3..9 k-blocks; the batch-sharded
+// contrastive logits: 1,024 tiles): one CTA per SM walks the tiles, so barrier setup / TMEM allocation happen once, the
+// operand ring keeps streaming across tile boundaries, and the accumulator is DOUBLE-BUFFERED in TMEM -- while four
+// epilogue warps drain tile i (tcgen05.ld -> epilogue math -> 128-byte global stores, one output row per thread), the MMA
+// warp is already accumulating tile i + 1 into the other half of TMEM.
+//   warp 0: TMA producer | warp 1: MMA issuer (owns TMEM alloc / dealloc) | warps 2..5: epilogue (TMEM lane quarter w & 3)
+// Status: opt-in (RLREP_TC_PERSIST=1), see make_tc_plan -- functionally verified, epilogue store pattern still to be
+// transposed through shared memory before it pays off.
+constexpr int kPersistThreads = 192;
+
+template <int BN, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                            float* __restrict__ C, int ldc, int M, int N, int K, const Epilogue epi) {
+  constexpr int STAGES = num_stages(BN);
+  constexpr int A_BYTES = BM * BK * 4;
+  constexpr int B_BYTES = BN * BK * 4;
+  constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
+  static_assert(TMEM_COLS <= 512, "two accumulators must fit in TMEM");
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + STAGES * A_BYTES;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * (A_BYTES + B_BYTES));
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* acc_full = empty_bar + 8;   // [2] accumulator complete (MMA -> epilogue)
+  uint64_t* acc_empty = acc_full + 2;   // [2] accumulator drained (epilogue -> MMA), 4 arrivals (one per epilogue warp)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
+  const int total = tiles_m * tiles_n;
+  const int nkb = (K + BK - 1) / BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&acc_full[a], 1);
+      ptx::mbar_init(&acc_empty[a], 4);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer: the ring runs across tile boundaries
+    if (lane == 0) {
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+        const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;  // m fastest: concurrent CTAs share the B tile in L2
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          ptx::mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);  // fresh barrier: parity 1 passes immediately
+          ptx::mbar_arrive_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
+          const int k0 = kb * BK;
+          if (!A_MN) ptx::tma_load_2d(sA + s * A_BYTES, &tmA, &full_bar[s], k0, m0);
+          else ptx::tma_load_3d(sA + s * A_BYTES, &tmA, &full_bar[s], 0, k0, m0 / 32);
+          if (!B_MN) ptx::tma_load_2d(sB + s * B_BYTES, &tmB, &full_bar[s], k0, n0);
+          else ptx::tma_load_3d(sB + s * B_BYTES, &tmB, &full_bar[s], 0, k0, n0 / 32);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer: alternates between the two accumulators
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_tf32(BM, BN, A_MN, B_MN);
+      int it = 0, tc = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++tc) {
+        const int acc = tc & 1;
+        ptx::mbar_wait(&acc_empty[acc], ((tc >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator
+        ptx::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < nkb; ++kb, ++it) {
+          const int s = it % STAGES;
+          ptx::mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          ptx::tc_fence_after_sync();
+          const uint32_t a_addr = ptx::smem_u32(sA + s * A_BYTES);
+          const uint32_t b_addr = ptx::smem_u32(sB + s * B_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adesc = A_MN ? ptx::make_smem_desc(a_addr + k * 1024, 4096, 512, 1)
+                                        : ptx::make_smem_desc(a_addr + k * UMMA_K * 4, 16, 1024, 2);
+            const uint64_t bdesc = B_MN ? ptx::make_smem_desc(b_addr + k * 1024, 4096, 512, 1)
+                                        : ptx::make_smem_desc(b_addr + k * UMMA_K * 4, 16, 1024, 2);
+            ptx::mma_tf32_ss(d_tmem, adesc, bdesc, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          ptx::mma_commit(&empty_bar[s]);
+        }
+        ptx::mma_commit(&acc_full[acc]);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue warps 2..5: one output row per thread
+    const int q = warp & 3;
+    const bool vec_ok = (ldc & 3) == 0 && aligned16(C);
+    int tc = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++tc) {
+      const int acc = tc & 1;
+      const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
+      ptx::mbar_wait(&acc_full[acc], (tc >> 1) & 1);
+      ptx::tc_fence_after_sync();
+      const int gm = m0 + 32 * q + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t v[32];
+        ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + acc * BN + c * 32, v);
+        ptx::tmem_ld_wait();
+        const int gn0 = n0 + c * 32;
+        if (gm < M && gn0 < N) {
+          float* crow = C + (size_t)gm * ldc + gn0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int gn = gn0 + 4 * j;
+            if (gn >= N) break;
+            float o[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e)
+              o[e] = gn + e < N ? epilogue_apply<-1, -1>(epi, __uint_as_float(v[4 * j + e]), gm, gn + e, crow + 4 * j + e) : 0.f;
+            if (vec_ok && gn + 3 < N) {
+              *reinterpret_cast<float4*>(crow + 4 * j) = make_float4(o[0], o[1], o[2], o[3]);
+            } else {
+              for (int e = 0; e < 4 && gn + e < N; ++e) crow[4 * j + e] = o[e];
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <int BN, bool A_MN, bool B_MN>
+void launch_variant_persistent(const TcGemmPlan& p, cudaStream_t stream) {
+  auto kern = gemm_tf32_persistent_kernel<BN, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLREP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(BN)));
+    attr_set = true;
+  }
+  const GemmArgs& a = p.args;
+  const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN);
+  kern<<<std::min(tiles, kNumSMs), kPersistThreads, smem_bytes(BN), stream>>>(p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, a.K, a.epi);
+  RLREP_LAUNCHED_W("gemm_tf32_persistent", stream, 4.0 * ((double)a.M * a.K + (double)a.N * a.K + (double)a.M * a.N),
+                   2.0 * a.M * a.N * a.K);
+}
+
 template <int BN, bool A_MN, bool B_MN>
 void fill_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, dim3 grid, int split_k, int stages,
                         bool push, cudaStream_t stream) {
@@ -524,6 +687,11 @@ int max_clusters_variant(int split_k, int stages, bool push) {
 
 #define RLREP_TC_DEFINE(BN, AMN)                                              \
   void launch_tc_##BN##_##AMN(const TcGemmPlan& p, cudaStream_t stream) {     \
+    if (p.persistent) {                                                       \
+      if (p.args.b_mn) launch_variant_persistent<BN, (AMN) != 0, true>(p, stream);   \
+      else launch_variant_persistent<BN, (AMN) != 0, false>(p, stream);       \
+      return;                                                                 \
+    }                                                                         \
     if (p.args.b_mn) launch_variant<BN, (AMN) != 0, true>(p, stream);         \
     else launch_variant<BN, (AMN) != 0, false>(p, stream);                    \
   }                                                                           \

@@ -1,0 +1,9 @@
+timeout 400 python -m pytest tests/test_gpu_parity.py tests/test_gpu_conv.py tests/test_gpu_drq.py -m gpu -q -x -k "gemm or conv or drq" 2>&1 | tail -5
+for p in 1 0; do
+echo "== persist=$p"
+RLREP_TC_PERSIST=$p python bench.py --workload drqv2_pixels_b256 --steps 30 --warmup 3 --no-cpu-baseline | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(round(d['value'],1),'upd/s', round(d['ms_per_step'],3),'ms; e2e', round(d['e2e']['value'],1)); print(d['top_kernels_us_per_step'][:4])"
+done
+python tests/gpu_tune_gemm.py 2>&1 | grep "big" | cut -c1-250
+RLREP_TC_PERSIST=0 python tests/gpu_tune_gemm.py 2>&1 | grep "big" | cut -c1-250
