@@ -193,8 +193,10 @@ TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* /*ws*/, s
   }
   {
     // Opt-in (RLREP_TC_PERSIST=1): the persistent variant is correct (the GEMM / conv / DrQ parity tests pass with
-    // it) but not yet faster -- its row-per-thread epilogue issues 32 partial-line stores per instruction, which costs
-    // more than the per-tile setup it saves (round 1: DrQ-v2 7.4 vs 5.5 ms/update, 2048x16384x2048 347 vs 335 us).
+    // it) but not yet faster (round 1: DrQ-v2 7.5 vs 5.5 ms/update, 2048x16384x2048 350-370 vs 325-345 us): with one
+    // CTA per SM there is a single TMA -> MMA -> epilogue pipeline per SM, while the one-tile-per-CTA kernel keeps two
+    // or three co-resident CTAs per SM overlapping each other's latencies.  Next step: two MMA/epilogue pipelines per
+    // CTA (or 2 CTAs per SM with half-depth rings).
     static const int persist_on = [] {
       const char* e = std::getenv("RLREP_TC_PERSIST");
       return e ? std::atoi(e) : 0;

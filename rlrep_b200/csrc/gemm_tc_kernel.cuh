@@ -475,8 +475,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 // epilogue warps drain tile i (tcgen05.ld -> epilogue math -> 128-byte global stores, one output row per thread), the MMA
 // warp is already accumulating tile i + 1 into the other half of TMEM.
 //   warp 0: TMA producer | warp 1: MMA issuer (owns TMEM alloc / dealloc) | warps 2..5: epilogue (TMEM lane quarter w & 3)
-// Status: opt-in (RLREP_TC_PERSIST=1), see make_tc_plan -- functionally verified, epilogue store pattern still to be
-// transposed through shared memory before it pays off.
+// Status: opt-in (RLREP_TC_PERSIST=1), see make_tc_plan -- functionally verified, not yet faster than one tile per CTA.
 constexpr int kPersistThreads = 192;
 
 template <int BN, bool A_MN, bool B_MN>
@@ -497,6 +496,9 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   uint64_t* acc_full = empty_bar + 8;   // [2] accumulator complete (MMA -> epilogue)
   uint64_t* acc_empty = acc_full + 2;   // [2] accumulator drained (epilogue -> MMA), 4 arrivals (one per epilogue warp)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  // per-epilogue-warp transpose buffers [4][32 rows][36 floats] behind the barriers: a thread holds one ROW of the
+  // accumulator chunk, but stores want consecutive lanes on consecutive 16-byte pieces of the same output row
+  float* tbuf = reinterpret_cast<float*>(smem + STAGES * (A_BYTES + B_BYTES) + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (M + BM - 1) / BM, tiles_n = (N + BN - 1) / BN;
@@ -574,6 +576,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     // ------------------------------------------------------------ epilogue warps 2..5: one output row per thread
     const int q = warp & 3;
     const bool vec_ok = (ldc & 3) == 0 && aligned16(C);
+    float* tw = tbuf + q * (32 * 36);
     int tc = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++tc) {
       const int acc = tc & 1;
@@ -587,22 +590,35 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + acc * BN + c * 32, v);
         ptx::tmem_ld_wait();
         const int gn0 = n0 + c * 32;
-        if (gm < M && gn0 < N) {
-          float* crow = C + (size_t)gm * ldc + gn0;
+        if (vec_ok && gn0 + 32 <= N) {
+          // transpose through shared memory: lane = row on the way in, (row group, 16-byte piece) on the way out, so
+          // every store instruction writes four complete 128-byte row segments
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            const int gn = gn0 + 4 * j;
-            if (gn >= N) break;
-            float o[4];
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(tw + lane * 36 + 4 * j) =
+                make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                            __uint_as_float(v[4 * j + 3]));
+          __syncwarp();
+          const int piece = lane & 7, rsub = lane >> 3;
 #pragma unroll
-            for (int e = 0; e < 4; ++e)
-              o[e] = gn + e < N ? epilogue_apply<-1, -1>(epi, __uint_as_float(v[4 * j + e]), gm, gn + e, crow + 4 * j + e) : 0.f;
-            if (vec_ok && gn + 3 < N) {
-              *reinterpret_cast<float4*>(crow + 4 * j) = make_float4(o[0], o[1], o[2], o[3]);
-            } else {
-              for (int e = 0; e < 4 && gn + e < N; ++e) crow[4 * j + e] = o[e];
+          for (int r4 = 0; r4 < 8; ++r4) {
+            const int r = r4 * 4 + rsub;
+            const int om = m0 + 32 * q + r, on = gn0 + 4 * piece;
+            if (om < M) {
+              const float4 a4 = *reinterpret_cast<const float4*>(tw + r * 36 + 4 * piece);
+              float* cp = C + (size_t)om * ldc + on;
+              const float in[4] = {a4.x, a4.y, a4.z, a4.w};
+              float o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) o[e] = epilogue_apply<-1, -1>(epi, in[e], om, on + e, cp + e);
+              *reinterpret_cast<float4*>(cp) = make_float4(o[0], o[1], o[2], o[3]);
             }
           }
+          __syncwarp();
+        } else if (gm < M && gn0 < N) {
+          float* crow = C + (size_t)gm * ldc + gn0;
+          for (int e = 0; e < 32 && gn0 + e < N; ++e)
+            crow[e] = epilogue_apply<-1, -1>(epi, __uint_as_float(v[e]), gm, gn0 + e, crow + e);
         }
       }
       ptx::tc_fence_before_sync();
@@ -620,12 +636,12 @@ void launch_variant_persistent(const TcGemmPlan& p, cudaStream_t stream) {
   auto kern = gemm_tf32_persistent_kernel<BN, A_MN, B_MN>;
   static bool attr_set = false;
   if (!attr_set) {
-    RLREP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(BN)));
+    RLREP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(BN) + 4 * 32 * 36 * 4));
     attr_set = true;
   }
   const GemmArgs& a = p.args;
   const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN);
-  kern<<<std::min(tiles, kNumSMs), kPersistThreads, smem_bytes(BN), stream>>>(p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, a.K, a.epi);
+  kern<<<std::min(tiles, kNumSMs), kPersistThreads, smem_bytes(BN) + 4 * 32 * 36 * 4, stream>>>(p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, a.K, a.epi);
   RLREP_LAUNCHED_W("gemm_tf32_persistent", stream, 4.0 * ((double)a.M * a.K + (double)a.N * a.K + (double)a.M * a.N),
                    2.0 * a.M * a.N * a.K);
 }
