@@ -127,8 +127,8 @@ class DrQv2:
     next_img_step)."""
 
     def __init__(self, obs_space, action_space, args, *, precision="tf32"):
-        if not torch.cuda.is_available():
-            raise _lib.RlrepError("rlrep_b200.DrQv2 needs a CUDA device (there is no CPU fallback)")
+        # construction is lazy like the state-based agents: the device handle is created by the first call that needs
+        # it (and raises there without a CUDA device -- there is no CPU fallback)
         if getattr(args, "critic_loss", "mse") != "mse":
             raise NotImplementedError("critic_loss='huber' (configs/drqv2.yaml ships 'mse')")
         if args.actor_hidden_dim != args.critic_hidden_dim:
@@ -141,7 +141,7 @@ class DrQv2:
         self.bn_dim, self.hidden_dim = int(args.bn_dim), int(args.actor_hidden_dim)
         self._precision = precision
         self._step = 1
-        self.lib = _lib.load()
+        self.lib = None
         self._h = None
         self._batch = None
         self._pending = {}
@@ -152,6 +152,9 @@ class DrQv2:
             if batch != self._batch:
                 raise _lib.RlrepError(f"batch size is fixed per handle (was {self._batch}, got {batch})")
             return
+        if not torch.cuda.is_available():
+            raise _lib.RlrepError("rlrep_b200.DrQv2 needs a CUDA device (there is no CPU fallback)")
+        self.lib = _lib.load()
         c, h, _ = self.obs_dim
         cfg = DrqConfig(batch_size=batch, channels=c, height=h, action_dim=self.action_dim, bn_dim=self.bn_dim,
                         hidden_dim=self.hidden_dim, encoder_lr=float(self.args.encoder_lr),
@@ -173,7 +176,7 @@ class DrQv2:
 
     def close(self):
         h, self._h = self._h, None
-        if h:
+        if h and self.lib is not None:
             self.lib.rlrep_drq_destroy(h)
 
     def __del__(self):

@@ -91,3 +91,37 @@ def test_initial_state_covers_the_oracle_parameter_table(alg):
 
 def test_epilogue_struct_matches_header_layout():
     assert _lib.Epilogue.scale.offset == 60 and __import__("ctypes").sizeof(_lib.Epilogue) == 64
+
+
+def test_drqv2_draw_consumes_the_generator_like_the_reference():
+    """One updating train_step of the plain DrQ-v2 pixel agent: two RandomShiftsAug integer draws (float dtype, like
+    network_arch/drqv2.py:43-47) and two _standard_normal([B, A]) draws, in that order; non-updating calls draw
+    nothing.  Checked against the oracle, which is bit-identical to the real reference class (tests/golden/drqv2_*)."""
+    import types
+    from oracle import drq_oracle as D
+    from rlrep_b200.pixel import DrQv2
+    C_, A, bn, H, B = 3, 4, 16, 32, 4
+
+    class Box:
+        def __init__(self, shape):
+            self.shape = shape
+    args = types.SimpleNamespace(tau=0.01, update_every=2, critic_loss="mse", stddev_schedule="linear(1.0,0.1,500000)",
+                                 stddev_clip=0.3, bn_dim=bn, actor_hidden_dim=H, critic_hidden_dim=H, encoder_lr=1e-4,
+                                 actor_lr=1e-4, critic_lr=1e-4)
+    agent = DrQv2(Box((C_, 84, 84)), Box((A,)), args)  # lazy: no device needed until the first update
+    oracle = D.OracleDrQv2(A, D.init_state(C_, A, bn, H, seed=0))
+    batch = D.synthetic_pixel_batch(B, C_, 84, A, seed=0)
+    torch.manual_seed(7)
+    assert oracle.train_step(batch, 0) != {}  # _step 1 -> 2: updates
+    state_after_update = torch.get_rng_state().clone()
+    assert oracle.train_step(batch, 0) == {}  # _step 3: no update, no draws
+    assert torch.equal(torch.get_rng_state(), state_after_update)
+    torch.manual_seed(7)
+    shifts, eps = agent._draw(B)
+    assert torch.equal(torch.get_rng_state(), state_after_update)
+    assert shifts.shape == (2, B, 2) and shifts.dtype == np.int32 and shifts.min() >= 0 and shifts.max() <= 8
+    assert eps.shape == (2, B, A)
+    torch.manual_seed(7)
+    want = torch.stack([D.draw_shift(B).reshape(B, 2) for _ in range(2)]).to(torch.int32).numpy()
+    assert np.array_equal(shifts, want)
+    assert agent.stddev_schedule(250000) == pytest.approx(0.55)
