@@ -10,14 +10,16 @@ import torch
 from oracle import rl_oracle as O
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
-CASES = sorted(p.stem for p in GOLDEN.glob("*.npz") if not p.stem.startswith("drqv2"))
+CASES = sorted(p.stem for p in GOLDEN.glob("*.npz") if not p.stem.startswith(("drqv2", "mulvdrq")))
 DRQ_CASES = sorted(p.stem for p in GOLDEN.glob("drqv2*.npz"))
+MULV_CASES = sorted(p.stem for p in GOLDEN.glob("mulvdrq*.npz"))
 
 
 def test_fixtures_present():
     assert {"sac_hc_b256", "ctrlsac_small", "ctrlsac_hc_b256", "vlsac_hc_b64", "vlsac_hum_b128", "spedersac_hc_b64",
             "diffsrsac_hc_b64"} <= set(CASES)
     assert {"drqv2_b8", "drqv2_b16_c3"} <= set(DRQ_CASES)
+    assert {"mulvdrq_b4"} <= set(MULV_CASES)
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -85,6 +87,33 @@ def test_drq_oracle_reproduces_reference(name):
         assert set(g) == set(w)
         for k in w:
             assert abs(g[k] - w[k]) <= 2e-6 + 2e-5 * abs(w[k]), (step, k, g[k], w[k])
+    sd = oracle.state_dict()
+    for k in meta["keys"]:
+        t = sd[k].detach().double().flatten()
+        stats, sample = z["stats/" + k], z["sample/" + k]
+        stride = max(1, t.numel() // 256)
+        assert abs(t.norm().item() - stats[1]) <= 1e-5 * max(stats[1], 1e-6), k
+        assert np.linalg.norm(t[::stride][:256].numpy() - sample) <= 2e-5 * max(np.linalg.norm(sample), 1e-6) + 1e-7, k
+
+
+@pytest.mark.parametrize("name", MULV_CASES)
+def test_mulvdrq_oracle_reproduces_reference(name):
+    """muLV-Rep DrQ-v2 pixel update (agent/mulvdrq/drqv2.py:313-461): oracle/mulv_oracle.py against fixtures produced by
+    the real reference class (oracle/make_golden_mulv.py).  Groundwork for SURVEY 8a row a16 (no CUDA path yet)."""
+    from oracle import mulv_oracle as M
+    z = np.load(GOLDEN / f"{name}.npz")
+    meta = json.loads(bytes(z["meta_json"]).decode())
+    infos = json.loads(bytes(z["infos_json"]).decode())
+    C, A, Fd, H, B, n = (meta[k] for k in ("C", "A", "feat_dim", "hid_dim", "batch", "n"))
+    oracle = M.OracleMuLVDrQ(A, M.init_state(C, A, Fd, H, seed=0))
+    batches = [M.synthetic_pixel_batch(B, C, 84, A, seed=20 + i) for i in range(n)]
+    torch.manual_seed(1)
+    got = [oracle.update(b, step=2 * i) for i, b in enumerate(batches)]
+    for step, (g, w) in enumerate(zip(got, infos)):
+        assert set(g) == set(w)
+        for k in w:
+            assert abs(g[k] - w[k]) <= 2e-6 + 2e-5 * abs(w[k]), (step, k, g[k], w[k])
+    assert oracle.update(batches[0], step=1) == {}  # up_every = 2: odd steps are no-ops and draw nothing
     sd = oracle.state_dict()
     for k in meta["keys"]:
         t = sd[k].detach().double().flatten()
