@@ -53,6 +53,9 @@ WORKLOADS = {
     # first pixel agent (plain DrQ-v2 `train_step`, configs/drqv2.yaml shapes); one replica per GPU
     # at N > 1 is the population harness of BASELINE.json configs[4]
     "drqv2_pixels_b256": dict(alg="drqv2", C=9, A=4, B=256, bn=50, H=1024, rows=0, kw={}),
+    # muLV-Rep DrQ-v2 `update` at mulv_config.py's shapes (b_size 256, feat_dim 100, hid_dim 1024) --
+    # the per-member update of BASELINE.json configs[4]; one replica per GPU at N > 1
+    "mulvdrq_pixels_b256": dict(alg="mulvdrq", C=9, A=4, B=256, F=100, H=1024, rows=0, kw={}),
     # BASELINE.json configs[3]: large-batch CTRL, GLOBAL batch 16384 split by rows over the ranks (strong scaling:
     # the total work is fixed; 2048 rows per GPU at N = 8), mu(s') all-gathered over NVLink
     "ctrlsac_b16384_sharded": dict(alg="ctrlsac", S=17, A=6, B=16384, rows=1_000_000, sharded=True,
@@ -238,19 +241,61 @@ class _Box:
         self.shape = shape
 
 
+MULV_CFG = dict(aug=True, pre_aug=False, back_q2feat=True, tanh=True, both_q=False, q_activ="relu", q_loss="huber",
+                q_up_n=1, l2_norm=0.0, c_targ_tau=0.01, up_every=1, stddev_schedule="linear(1.0,0.1,500000)",
+                stddev_clip=0.3, lr=1e-4, vae_w=0.5, mse_w=1.0, c_noise=0.1)
+
+
+class _PixelArm:
+    """The two pixel agents behind one face: step(i) = one updating call through the public API with host batches."""
+
+    def __init__(self, w, precision, seed):
+        from rlrep_b200 import _lib
+        self.w, self.lib_mod = w, _lib
+        C_, A = w["C"], w["A"]
+        if w["alg"] == "drqv2":
+            from oracle import drq_oracle as D  # synthetic batch + deterministic initial weights (data, not arithmetic)
+            from rlrep_b200.pixel import DrQv2
+            self.agent = DrQv2(_Box((C_, 84, 84)), _Box((A,)), drq_args(w), precision=precision)
+            self.agent.load_state_dict(D.init_state(C_, A, w["bn"], w["H"], seed=seed))
+            self.step = lambda batch, i: self.agent.train_step(iter([batch]), step=i)
+            self.prefix = "rlrep_drq"
+            self.h2d = 2 * w["B"] * C_ * 84 * 84 + 4 * (4 * w["B"] + 3 * w["B"] * A + 2 * w["B"])
+        else:
+            from oracle import mulv_oracle as D
+            from rlrep_b200.pixel import MuLVDrQv2
+            self.agent = MuLVDrQv2((C_, 84, 84), (A,), dict(MULV_CFG, feat_dim=w["F"], hid_dim=w["H"]), precision=precision)
+            self.agent.load_state_dict(D.init_state(C_, A, w["F"], w["H"], seed=seed))
+            self.step = lambda batch, i: self.agent.update(iter([batch]), step=i)
+            self.prefix = "rlrep_mulv"
+            self.h2d = (2 * C_ + 3) * w["B"] * 84 * 84 + 4 * (4 * w["B"] + w["B"] * w["F"] + 3 * w["B"] * A +
+                                                              3 * 20 * w["F"] + 2 * w["B"])
+        self.D = D
+
+    def fn(self, name):
+        return getattr(self.agent.lib, f"{self.prefix}_{name}")
+
+    def make_oracle(self):
+        w, D = self.w, self.D
+        if w["alg"] == "drqv2":
+            o = D.OracleDrQv2(w["A"], D.init_state(w["C"], w["A"], w["bn"], w["H"], seed=0), update_every=1)
+            return lambda b: o.train_step(b, 0)
+        o = D.OracleMuLVDrQ(w["A"], D.init_state(w["C"], w["A"], w["F"], w["H"], seed=0), up_every=1)
+        return lambda b: o.update(b, 0)
+
+
 def run_drq(args, w, rank, world, local_rank):
-    """DrQ-v2 pixel update: one step = one updating `train_step` on a [B, 9, 84, 84] uint8 batch (synthetic frames)."""
+    """Pixel update (plain DrQ-v2 or muLV-Rep DrQ-v2): one step = one updating call on a [B, 9, 84, 84] uint8 batch
+    (synthetic frames)."""
     import torch
     import torch.distributed as dist
-    from oracle import drq_oracle as D  # synthetic batch + deterministic initial weights (data, not arithmetic)
     from rlrep_b200 import _lib
-    from rlrep_b200.pixel import DrQv2
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     C_, A, B = w["C"], w["A"], w["B"]
-    agent = DrQv2(_Box((C_, 84, 84)), _Box((A,)), drq_args(w), precision=args.precision)
-    agent.load_state_dict(D.init_state(C_, A, w["bn"], w["H"], seed=rank))
+    arm = _PixelArm(w, args.precision, rank)
+    agent, D = arm.agent, arm.D
     batches = [tuple(D.synthetic_pixel_batch(B, C_, 84, A, seed=100 * rank + i)) for i in range(4)]
     torch.manual_seed(1 + rank)
 
@@ -261,18 +306,18 @@ def run_drq(args, w, rank, world, local_rank):
         torch.cuda.synchronize()
 
     for i in range(max(args.warmup, 3)):
-        agent.train_step(iter([batches[i % 4]]), step=i)
+        arm.step(batches[i % 4], i)
     ms = C.c_float()
     barrier()
     with ClockSampler(local_rank) as clk:  # (1) device-timed on the batch already resident in HBM
-        _lib.check(agent.lib.rlrep_drq_update_resident(agent._h, args.steps, 1.0, C.byref(ms)))
+        _lib.check(arm.fn("update_resident")(agent._h, args.steps, 1.0, C.byref(ms)))
         barrier()
     dev_ms, clocks = float(ms.value), clk.summary()
     barrier()
     t0 = time.perf_counter()  # (2) end to end: host batch -> pinned staging -> H2D -> update -> metrics D2H
     info = None
     for i in range(args.steps):
-        info = agent.train_step(iter([batches[i % 4]]), step=i)
+        info = arm.step(batches[i % 4], i)
     barrier()
     e2e_ms = (time.perf_counter() - t0) * 1e3
     launches = agent.gpu_launches_last_update
@@ -287,7 +332,7 @@ def run_drq(args, w, rank, world, local_rank):
         kby, kfl, n = (C.c_double * cap)(), (C.c_double * cap)(), C.c_int()
         agg = {}
         for _ in range(3):
-            _lib.check(agent.lib.rlrep_drq_profile_update(agent._h, 1.0, cap, names, kms, kby, kfl, C.byref(n)))
+            _lib.check(arm.fn("profile_update")(agent._h, 1.0, cap, names, kms, kby, kfl, C.byref(n)))
             for i in range(min(n.value, cap)):
                 a = agg.setdefault(names[i].decode(), [0.0, 0, 0.0, 0.0])
                 a[0] += kms[i]; a[1] += 1; a[2] += kby[i]; a[3] += kfl[i]
@@ -314,27 +359,26 @@ def run_drq(args, w, rank, world, local_rank):
                              "frac": max(by / (hbm_peak * 1e9), fl / (tf32_peak * 1e12)) / step_s}}
         if world == 1 and not args.no_cpu_baseline:
             torch.set_num_threads(os.cpu_count() or 1)
-            oracle = D.OracleDrQv2(A, D.init_state(C_, A, w["bn"], w["H"], seed=0), update_every=1)
+            oracle_step = arm.make_oracle()
             ob = D.synthetic_pixel_batch(B, C_, 84, A, seed=0)
-            oracle.train_step(ob, 0)
+            oracle_step(ob)
             t1 = time.perf_counter()
-            n_cpu = 20
+            n_cpu = 20 if w["alg"] == "drqv2" else 8
             for _ in range(n_cpu):
-                oracle.train_step(ob, 0)
+                oracle_step(ob)
             dt = (time.perf_counter() - t1) / n_cpu
             cpu = {"value": 1.0 / dt, "unit": "updates/s", "cores": torch.get_num_threads(), "kind": "port",
                    "sample": f"{n_cpu} updates of the same workload after 1 warm-up ({dt * 1e3:.0f} ms each), reference "
                              f"arithmetic as written (grid_sample augmentation, F.conv2d, autograd, torch.optim.Adam)"}
-        img_bytes = 2 * B * C_ * 84 * 84
         line = {"metric": "agent updates/sec", "value": world * args.steps / (dev_ms * 1e-3), "unit": "updates/s",
                 "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": dev_ms / args.steps,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
-                "config": {"workload": args.workload, "alg": "drqv2", "obs": [C_, 84, 84], "A": A, "B": B, "bn_dim": w["bn"],
-                           "hidden_dim": w["H"], "parallelism": f"replicas x{world} (no collective)",
+                "config": {"workload": args.workload, "alg": w["alg"], "obs": [C_, 84, 84], "A": A, "B": B,
+                           "feature_dim": w.get("bn", w.get("F")), "hidden_dim": w["H"], "parallelism": f"replicas x{world} (no collective)",
                            "l2": "no flush: the update streams ~3 GB of column matrices and activations (>> 126 MB L2)"},
                 "e2e": {"value": world * args.steps / (e2e_ms * 1e-3), "unit": "updates/s", "ms_per_step": e2e_ms / args.steps,
-                        "h2d_bytes_per_step": img_bytes + 4 * (4 * B + 3 * B * A + 2 * B), "d2h_bytes_per_step": 32},
+                        "h2d_bytes_per_step": arm.h2d, "d2h_bytes_per_step": 32},
                 "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches, "clocks": clocks,
                 "roofline": roofline, "cpu_baseline": cpu,
                 "top_kernels_us_per_step": [[k, round(v * 1e3, 1), c] for k, v, c in top[:8]], "last_info": info}
@@ -347,20 +391,26 @@ def run_drq_reference(args, w, rank):
     if rank != 0:
         return
     import torch
-    from oracle import drq_oracle as D
     torch.set_num_threads(os.cpu_count() or 1)
-    oracle = D.OracleDrQv2(w["A"], D.init_state(w["C"], w["A"], w["bn"], w["H"], seed=0), update_every=1)
+    if w["alg"] == "drqv2":
+        from oracle import drq_oracle as D
+        o = D.OracleDrQv2(w["A"], D.init_state(w["C"], w["A"], w["bn"], w["H"], seed=0), update_every=1)
+        oracle_step = lambda b: o.train_step(b, 0)
+    else:
+        from oracle import mulv_oracle as D
+        o = D.OracleMuLVDrQ(w["A"], D.init_state(w["C"], w["A"], w["F"], w["H"], seed=0), up_every=1)
+        oracle_step = lambda b: o.update(b, 0)
     ob = D.synthetic_pixel_batch(w["B"], w["C"], 84, w["A"], seed=0)
     torch.manual_seed(1)
     for _ in range(args.warmup):
-        oracle.train_step(ob, 0)
+        oracle_step(ob)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        oracle.train_step(ob, 0)
+        oracle_step(ob)
     dt = (time.perf_counter() - t0) / args.steps
     emit({"impl": "reference", "metric": "agent updates/sec", "value": 1.0 / dt, "unit": "updates/s", "n_gpus": args.gpus,
           "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak",
-          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": args.workload, "alg": "drqv2"},
+          "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": args.workload, "alg": w["alg"]},
           "cpu_baseline": {"value": 1.0 / dt, "unit": "updates/s", "cores": torch.get_num_threads(), "kind": "port",
                            "sample": f"{args.steps} updates after {args.warmup} warm-up"},
           "e2e": {"value": 1.0 / dt, "unit": "updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}})
@@ -573,9 +623,9 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if w["alg"] == "drqv2":
+    if w["alg"] in ("drqv2", "mulvdrq"):
         if args.impl == "reference":
-            args.steps = min(args.steps, 20)
+            args.steps, args.warmup = min(args.steps, 20 if w["alg"] == "drqv2" else 8), min(args.warmup, 2)
             run_drq_reference(args, w, rank)
         else:
             run_drq(args, w, rank, world, local_rank)

@@ -249,6 +249,45 @@ RLREP_EXPORT int rlrep_drq_profile_update(rlrep_drq* drq, float stddev, int max_
                                           double* bytes, double* flops, int* n_entries);
 RLREP_EXPORT int rlrep_drq_last_launches(rlrep_drq* drq, int* launches);
 
+/* ------------------------------------------------------------------------------------------------
+ * muLV-Rep DrQ-v2 pixel agent -- replaces `DrQV2Agent(obs_shape, action_shape, cfg)` and the updating half of
+ * `DrQV2Agent.update(replay_iter, step)` + `update_actor` (agent/mulvdrq/drqv2.py:198-461) on `mulv_config.py`'s default
+ * path (aug, no pre_aug, back_q2feat, tanh heads, ReLU critic, Huber loss, soft target updates).  The caller keeps
+ * `up_every`, evaluates the std-dev schedule and draws the randomness in the reference's order on the CPU generator:
+ * shift draws for img then next_img, randn[B, feat_dim] (feat_encoder.sample), the next action's standard normals,
+ * randn[num_noise, feat_dim] for critic_target, for critic, the actor step's standard normals, randn for its critic.
+ * Tensors carry the reference's module names ("encoder.convnet.0.weight", "feat_encoder.mean_linear.0.weight",
+ * "feat_f_target.log_std_linear.1.bias", "decoder.deconvnet.6.weight", ...).  Conv weights of layers 2-4 are stored
+ * [32, (ky, kx, c_in)], transposed-conv weights [(ky, kx, c_out), c_in]; rlrep_b200/pixel.py permutes them to and from
+ * the reference's layouts.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rlrep_mulv rlrep_mulv;
+typedef struct rlrep_mulv_config {
+  int batch_size, channels, height, action_dim, feat_dim, hidden_dim, num_noise;
+  double lr;
+  float tau, stddev_clip, vae_w, mse_w, c_noise;
+  int precision;
+} rlrep_mulv_config;
+RLREP_EXPORT int rlrep_mulv_create(const rlrep_mulv_config* cfg, void* stream, rlrep_mulv** out);
+RLREP_EXPORT int rlrep_mulv_destroy(rlrep_mulv* h);
+RLREP_EXPORT int rlrep_mulv_num_tensors(rlrep_mulv* h, int* n);
+RLREP_EXPORT int rlrep_mulv_tensor_info(rlrep_mulv* h, int i, const char** name, float** ptr_dev, int* rows, int* cols);
+RLREP_EXPORT int rlrep_mulv_tensor_read(rlrep_mulv* h, int i, float* out_host);
+RLREP_EXPORT int rlrep_mulv_tensor_write(rlrep_mulv* h, int i, const float* in_host);
+RLREP_EXPORT int rlrep_mulv_sync_targets(rlrep_mulv* h);
+/* img / next_img uint8 [B, C, 84, 84]; img_step1 uint8 [B, 3, 84, 84] (last frame of the one-step-ahead observation);
+ * action [B, A]; reward, discount [B]; shifts int32 [2][B][2]; eps_z [B, feat_dim]; eps_act [2][B][A];
+ * noise [3][num_noise][feat_dim]; metrics_host[8] = {critic_loss, mean(q1), mean(q2), mean(target_q), s_loss, r_loss,
+ * kl_loss, actor_loss}.  All host pointers. */
+RLREP_EXPORT int rlrep_mulv_update(rlrep_mulv* h, const unsigned char* img, const float* action, const float* reward,
+                                   const float* discount, const unsigned char* next_img, const unsigned char* img_step1,
+                                   const int* shifts, const float* eps_z, const float* eps_act, const float* noise,
+                                   float stddev, float* metrics_host);
+RLREP_EXPORT int rlrep_mulv_update_resident(rlrep_mulv* h, int n_steps, float stddev, float* total_ms);
+RLREP_EXPORT int rlrep_mulv_profile_update(rlrep_mulv* h, float stddev, int max_entries, const char** names, float* ms,
+                                           double* bytes, double* flops, int* n_entries);
+RLREP_EXPORT int rlrep_mulv_last_launches(rlrep_mulv* h, int* launches);
+
 /* Kernels launched by the most recent train() (a graph replay counts the kernels it contains). */
 RLREP_EXPORT int rlrep_agent_last_launches(rlrep_agent* agent, int* launches);
 

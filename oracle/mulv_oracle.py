@@ -190,6 +190,9 @@ class OracleMuLVDrQ:
         for g in groups:
             self.opt[g].zero_grad(set_to_none=True)
         loss.backward()
+        # gradients of this update, for gradient-level parity tests (the actor step below also back-propagates into
+        # feat_f and critic, whose .grad is then no longer the model step's)
+        self.last_grads = {k: v.grad.detach().clone() for k, v in p.items() if v.grad is not None and not k.startswith("actor.")}
         for g in groups:
             self.opt[g].step()
         # ---- update_actor(state.detach(), step), drqv2.py:284-311
@@ -201,10 +204,12 @@ class OracleMuLVDrQ:
         actor_loss = -torch.min(aq1, aq2).mean()
         self.opt["actor"].zero_grad(set_to_none=True)
         actor_loss.backward()
+        self.last_grads.update({k: v.grad.detach().clone() for k, v in p.items() if k.startswith("actor.")})
         self.opt["actor"].step()
         with torch.no_grad():  # soft updates, agent_utils.py:42-45
             for k, t in self.tgt.items():
                 src = next(TARGETS[pre] + k[len(pre):] for pre in TARGETS if k.startswith(pre))
                 t.copy_(self.tau * self.p[src] + (1 - self.tau) * t)
         return {"actor_loss": actor_loss.item(), "critic_loss": critic_loss.item(), "s_loss": s_loss.item(),
-                "r_loss": r_loss.item(), "kl_loss": kl_loss.item()}
+                "r_loss": r_loss.item(), "kl_loss": kl_loss.item(), "critic_q1": q1.mean().item(),
+                "critic_q2": q2.mean().item(), "critic_target_q": target_q.mean().item()}

@@ -103,6 +103,18 @@ def _declare(lib: C.CDLL) -> None:
         "rlrep_drq_update_resident": [vp, i, C.c_float, C.POINTER(C.c_float)],
         "rlrep_drq_profile_update": [vp, C.c_float, i, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_double),
                                      C.POINTER(C.c_double), C.POINTER(i)],
+        "rlrep_mulv_create": [vp, vp, C.POINTER(vp)],
+        "rlrep_mulv_destroy": [vp],
+        "rlrep_mulv_num_tensors": [vp, C.POINTER(i)],
+        "rlrep_mulv_tensor_info": [vp, i, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(i), C.POINTER(i)],
+        "rlrep_mulv_tensor_read": [vp, i, vp],
+        "rlrep_mulv_tensor_write": [vp, i, vp],
+        "rlrep_mulv_sync_targets": [vp],
+        "rlrep_mulv_update": [vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, C.c_float, vp],
+        "rlrep_mulv_last_launches": [vp, C.POINTER(i)],
+        "rlrep_mulv_update_resident": [vp, i, C.c_float, C.POINTER(C.c_float)],
+        "rlrep_mulv_profile_update": [vp, C.c_float, i, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_double),
+                                      C.POINTER(C.c_double), C.POINTER(i)],
         "rlrep_comm_unique_id": [vp],
         "rlrep_comm_create": [vp, i, i, C.POINTER(vp)],
         "rlrep_comm_destroy": [vp],

@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "conv.cuh"
 #include "drq.cuh"
+#include "mulv.cuh"
 #include "gemm.cuh"
 #include "rlrep_b200.h"
 
@@ -456,6 +457,133 @@ int rlrep_drq_profile_update(rlrep_drq* drq, float stddev, int max_entries, cons
 int rlrep_drq_last_launches(rlrep_drq* drq, int* launches) {
   RLREP_API_BEGIN
   *launches = drq->impl->last_launches;
+  RLREP_API_END
+}
+
+// ------------------------------------------------------------------------------------------------ muLV-Rep DrQ-v2 pixel agent
+struct rlrep_mulv {
+  std::unique_ptr<MulvDrq> impl;
+  std::vector<TensorRef> tensors;
+  cudaStream_t owned_stream = nullptr;
+};
+
+int rlrep_mulv_create(const rlrep_mulv_config* c, void* stream, rlrep_mulv** out) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(c != nullptr && out != nullptr, "null argument");
+  MulvConfig d;
+  d.batch = c->batch_size; d.channels = c->channels; d.height = c->height; d.action_dim = c->action_dim;
+  d.feat_dim = c->feat_dim; d.hidden_dim = c->hidden_dim; d.num_noise = c->num_noise;
+  d.lr = c->lr; d.tau = c->tau; d.stddev_clip = c->stddev_clip; d.vae_w = c->vae_w; d.mse_w = c->mse_w;
+  d.c_noise = c->c_noise; d.precision = c->precision;
+  std::unique_ptr<rlrep_mulv> h(new rlrep_mulv);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (st == nullptr) {
+    RLREP_CUDA(cudaStreamCreateWithFlags(&h->owned_stream, cudaStreamNonBlocking));
+    st = h->owned_stream;
+  }
+  h->impl.reset(new MulvDrq(d, st));
+  for (ParamGroup* g : h->impl->groups()) {
+    // the conv stacks name their tensors relative to the module ("convnet.0.weight"); the other groups carry full names
+    const bool rel = g->name == "encoder" || g->name == "predict_encoder" || g->name == "decoder";
+    const std::string prefix = rel ? g->name + "." : "";
+    for (const ParamTensor& t : g->tensors) h->tensors.push_back({prefix + t.name, g->p + t.offset, t.rows, t.cols, t.ld});
+    for (const ParamTensor& t : g->tensors)
+      h->tensors.push_back({"grad/" + prefix + t.name, g->g + t.offset, t.rows, t.cols, t.ld});
+    if (g->target)
+      for (const ParamTensor& t : g->tensors)
+        h->tensors.push_back({g->target_prefix_to + t.name.substr(g->target_prefix_from.size()), g->target + t.offset,
+                              t.rows, t.cols, t.ld});
+  }
+  *out = h.release();
+  RLREP_API_END
+}
+int rlrep_mulv_destroy(rlrep_mulv* h) {
+  RLREP_API_BEGIN
+  if (h) {
+    if (h->impl) cudaStreamSynchronize(h->impl->stream());
+    h->impl.reset();
+    if (h->owned_stream) cudaStreamDestroy(h->owned_stream);
+  }
+  delete h;
+  RLREP_API_END
+}
+int rlrep_mulv_num_tensors(rlrep_mulv* h, int* n) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(h && n, "null argument");
+  *n = (int)h->tensors.size();
+  RLREP_API_END
+}
+int rlrep_mulv_tensor_info(rlrep_mulv* h, int i, const char** name, float** ptr_dev, int* rows, int* cols) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(h && i >= 0 && i < (int)h->tensors.size(), "tensor index out of range");
+  const TensorRef& t = h->tensors[i];
+  if (name) *name = t.name.c_str();
+  if (ptr_dev) *ptr_dev = t.ptr;
+  if (rows) *rows = t.rows;
+  if (cols) *cols = t.cols;
+  RLREP_API_END
+}
+int rlrep_mulv_tensor_read(rlrep_mulv* h, int i, float* out_host) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(h && out_host && i >= 0 && i < (int)h->tensors.size(), "tensor index out of range");
+  const TensorRef& t = h->tensors[i];
+  cudaStream_t st = h->impl->stream();
+  RLREP_CUDA(cudaMemcpy2DAsync(out_host, (size_t)t.cols * 4, t.ptr, (size_t)t.ld * 4, (size_t)t.cols * 4, t.rows,
+                               cudaMemcpyDeviceToHost, st));
+  RLREP_CUDA(cudaStreamSynchronize(st));
+  RLREP_API_END
+}
+int rlrep_mulv_tensor_write(rlrep_mulv* h, int i, const float* in_host) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(h && in_host && i >= 0 && i < (int)h->tensors.size(), "tensor index out of range");
+  const TensorRef& t = h->tensors[i];
+  cudaStream_t st = h->impl->stream();
+  RLREP_CUDA(cudaMemcpy2DAsync(t.ptr, (size_t)t.ld * 4, in_host, (size_t)t.cols * 4, (size_t)t.cols * 4, t.rows,
+                               cudaMemcpyHostToDevice, st));
+  RLREP_CUDA(cudaStreamSynchronize(st));
+  RLREP_API_END
+}
+int rlrep_mulv_sync_targets(rlrep_mulv* h) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(h, "null argument");
+  h->impl->sync_targets_from_params();
+  RLREP_API_END
+}
+int rlrep_mulv_update(rlrep_mulv* h, const unsigned char* img, const float* action, const float* reward,
+                      const float* discount, const unsigned char* next_img, const unsigned char* img_step1,
+                      const int* shifts, const float* eps_z, const float* eps_act, const float* noise, float stddev,
+                      float* metrics_host) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(h && img && action && reward && discount && next_img && img_step1 && shifts && eps_z && eps_act && noise &&
+                  metrics_host, "null argument");
+  h->impl->update(img, action, reward, discount, next_img, img_step1, shifts, eps_z, eps_act, noise, stddev, metrics_host);
+  RLREP_API_END
+}
+int rlrep_mulv_update_resident(rlrep_mulv* h, int n_steps, float stddev, float* total_ms) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(h && total_ms, "null argument");
+  *total_ms = h->impl->update_resident(n_steps, stddev);
+  RLREP_API_END
+}
+int rlrep_mulv_profile_update(rlrep_mulv* h, float stddev, int max_entries, const char** names, float* ms, double* bytes,
+                              double* flops, int* n_entries) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(h && n_entries && (max_entries == 0 || (names && ms)), "null argument");
+  std::vector<ProfileEntry> prof = h->impl->profile_update(stddev);
+  const int n = (int)std::min<size_t>(prof.size(), (size_t)max_entries);
+  for (int i = 0; i < n; ++i) {
+    names[i] = prof[i].name;
+    ms[i] = prof[i].ms;
+    if (bytes) bytes[i] = prof[i].bytes;
+    if (flops) flops[i] = prof[i].flops;
+  }
+  *n_entries = (int)prof.size();
+  RLREP_API_END
+}
+int rlrep_mulv_last_launches(rlrep_mulv* h, int* launches) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(h && launches, "null argument");
+  *launches = h->impl->last_launches;
   RLREP_API_END
 }
 

@@ -92,24 +92,24 @@ __global__ void col2im_nhwc32_kernel(const float4* __restrict__ dcol, const floa
 
 // NHWC [B, P, 32] <-> the reference's flatten order [B, 32, P] (P = Ho*Ho); the backward direction also applies the
 // ReLU mask of the last layer.
-__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, int B, int P, float* __restrict__ out) {
+__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, int B, int P, float* __restrict__ out, long long ld) {
   const long long total = (long long)B * P * 32;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int p = (int)(i % P);
     const int c = (int)((i / P) % 32);
     const long long b = i / ((long long)P * 32);
-    out[i] = in[(b * P + p) * 32 + c];
+    out[b * ld + (long long)c * P + p] = in[(b * P + p) * 32 + c];
   }
 }
-__global__ void nchw_to_nhwc_relu_bwd_kernel(const float* __restrict__ dfeat, const float* __restrict__ act, int B, int P,
-                                             float* __restrict__ dact) {
+__global__ void nchw_to_nhwc_relu_bwd_kernel(const float* __restrict__ dfeat, long long ld, const float* __restrict__ act,
+                                             int B, int P, float* __restrict__ dact) {
   const long long total = (long long)B * P * 32;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = (int)(i & 31);
     const long long bp = i >> 5;
     const int p = (int)(bp % P);
     const long long b = bp / P;
-    dact[i] = act[i] > 0.f ? dfeat[(b * 32 + c) * P + p] : 0.f;
+    dact[i] = act[i] > 0.f ? dfeat[b * ld + (long long)c * P + p] : 0.f;
   }
 }
 
@@ -131,7 +131,7 @@ int grid_for(long long work, int threads) {
 
 }  // namespace
 
-ConvEncoder::ConvEncoder(int batch, int in_channels, int height, Precision prec, cudaStream_t s)
+ConvEncoder::ConvEncoder(int batch, int in_channels, int height, Precision prec, cudaStream_t s, bool with_target)
     : B_(batch), C_(in_channels), H_(height), stream_(s) {
   RLREP_CHECK(B_ > 0 && C_ > 0 && H_ >= 16, "bad encoder dimensions");
   hw_[0] = (H_ - 3) / 2 + 1;  // 84 -> 41
@@ -142,6 +142,7 @@ ConvEncoder::ConvEncoder(int batch, int in_channels, int height, Precision prec,
   // layer 1 keeps the reference's [32, C*3*3] layout; layers 2-4 are stored [32, (ky, kx, c)] (permuted at the API)
   conv_[0] = add_linear(g_, "convnet.0", 32, K1_);  // exported as "encoder.convnet.N" by the DrQ handle
   for (int l = 1; l < 4; ++l) conv_[l] = add_linear(g_, "convnet." + std::to_string(2 * l), 32, 288);
+  if (with_target) g_.n_target = g_.n;
   g_.want(arena_);
   arena_.want(&col_[0], rows(0) * ldk1_);
   for (int l = 1; l < 4; ++l) arena_.want(&col_[l], rows(l) * 288);
@@ -156,27 +157,30 @@ ConvEncoder::ConvEncoder(int batch, int in_channels, int height, Precision prec,
   gemm_.init(prec, 0);
 }
 
-void ConvEncoder::forward(const unsigned char* obs_dev, const int* shifts_dev, float* feat_dev) {
+void ConvEncoder::forward(const unsigned char* obs_dev, const int* shifts_dev, float* feat_dev, int ld_feat, bool target) {
   cudaStream_t s = stream_;
+  RLREP_CHECK(!target || g_.n_target == g_.n, "this encoder has no target copy");
   im2col_u8_aug_kernel<<<grid_for((long long)rows(0) * 32, 256), 256, 0, s>>>(obs_dev, shifts_dev, B_, C_, H_, hw_[0],
                                                                              col_[0], ldk1_);
   RLREP_LAUNCHED_W("im2col_u8_aug", s, (double)B_ * C_ * H_ * H_ + 4.0 * rows(0) * ldk1_, 0.0);
-  linear_fwd(gemm_, s, (int)rows(0), Mat{col_[0], ldk1_}, conv_[0].view(g_), ACT_RELU, act_[0], 32);
+  linear_fwd(gemm_, s, (int)rows(0), Mat{col_[0], ldk1_}, conv_[0].view(g_, target), ACT_RELU, act_[0], 32);
   for (int l = 1; l < 4; ++l) {
     im2col_nhwc32_kernel<<<grid_for((long long)rows(l) * 72, 256), 256, 0, s>>>(
         reinterpret_cast<const float4*>(act_[l - 1]), B_, hw_[l - 1], hw_[l], reinterpret_cast<float4*>(col_[l]));
     RLREP_LAUNCHED_W("im2col_nhwc32", s, 4.0 * (rows(l - 1) * 32 + rows(l) * 288), 0.0);
-    linear_fwd(gemm_, s, (int)rows(l), Mat{col_[l], 288}, conv_[l].view(g_), ACT_RELU, act_[l], 32);
+    linear_fwd(gemm_, s, (int)rows(l), Mat{col_[l], 288}, conv_[l].view(g_, target), ACT_RELU, act_[l], 32);
   }
   const int P = hw_[3] * hw_[3];
-  nhwc_to_nchw_kernel<<<grid_for((long long)B_ * P * 32, 256), 256, 0, s>>>(act_[3], B_, P, feat_dev);
+  nhwc_to_nchw_kernel<<<grid_for((long long)B_ * P * 32, 256), 256, 0, s>>>(act_[3], B_, P, feat_dev,
+                                                                              ld_feat > 0 ? ld_feat : (long long)P * 32);
   RLREP_LAUNCHED_W("nhwc_to_nchw", s, 8.0 * B_ * P * 32, 0.0);
 }
 
-void ConvEncoder::backward(const float* dfeat_dev) {
+void ConvEncoder::backward(const float* dfeat_dev, int ld_dfeat) {
   cudaStream_t s = stream_;
   const int P = hw_[3] * hw_[3];
-  nchw_to_nhwc_relu_bwd_kernel<<<grid_for((long long)B_ * P * 32, 256), 256, 0, s>>>(dfeat_dev, act_[3], B_, P, dact_[3]);
+  nchw_to_nhwc_relu_bwd_kernel<<<grid_for((long long)B_ * P * 32, 256), 256, 0, s>>>(
+      dfeat_dev, ld_dfeat > 0 ? ld_dfeat : (long long)P * 32, act_[3], B_, P, dact_[3]);
   RLREP_LAUNCHED_W("nchw_to_nhwc_relu_bwd", s, 12.0 * B_ * P * 32, 0.0);
   for (int l = 3; l >= 0; --l) {
     const Linear w = conv_[l].view(g_);

@@ -6,12 +6,14 @@ namespace rlrep {
 
 class ConvEncoder {
  public:
-  ConvEncoder(int batch, int in_channels, int height, Precision prec, cudaStream_t s);
+  // with_target: the group also carries a Polyak target copy of all four layers (muLV-Rep's encoder_target)
+  ConvEncoder(int batch, int in_channels, int height, Precision prec, cudaStream_t s, bool with_target = false);
   // obs uint8 [B, C, H, H] (device), shifts int32 [B, 2] = (x, y) in [0, 8] or nullptr (no augmentation);
-  // feat fp32 [B, 32 * 35 * 35] in the reference's flatten order (channel, row, column)
-  void forward(const unsigned char* obs_dev, const int* shifts_dev, float* feat_dev);
-  // dfeat [B, 32 * 35 * 35] -> dW / db of the four layers (activations of the last forward are reused)
-  void backward(const float* dfeat_dev);
+  // feat fp32 [B, 32 * 35 * 35] in the reference's flatten order (channel, row, column), row pitch ld_feat (0 = dense);
+  // target = true runs the target copy of the weights
+  void forward(const unsigned char* obs_dev, const int* shifts_dev, float* feat_dev, int ld_feat = 0, bool target = false);
+  // dfeat [B, 32 * 35 * 35] (row pitch ld_dfeat) -> dW / db of the four layers (activations of the last forward are reused)
+  void backward(const float* dfeat_dev, int ld_dfeat = 0);
 
   int batch() const { return B_; }
   int feature_dim() const { return 32 * hw_[3] * hw_[3]; }

@@ -1,0 +1,359 @@
+// muLV-Rep pixel decoder (reference: agent/mulvdrq/drqv2.py:98-117): x.view(B, 32, 35, 35) ->
+// 3 x [ConvTranspose2d(32, 32, 3, stride 1) + ReLU] -> ConvTranspose2d(32, 32, 3, stride 2) + ReLU ->
+// Conv2d(32, 3, kernel 2, padding 1): 35 -> 37 -> 39 -> 41 -> 83 -> 84, forward, L1 loss and backward.
+//
+// A transposed convolution is the data-gradient of a convolution, so it runs on the encoder's machinery with the roles
+// swapped (conv.cu): activations NHWC, forward  colT [B*Hi*Hi, 9*32] = X [B*Hi*Hi, 32] x Wd^T  (tcgen05 GEMM, K = 32)
+// followed by the gather-form col2im (+ bias + ReLU, stride 1 or 2);  backward  dcolT = im2col(dY) (stride 1 or 2),
+// dX = dcolT Wd (x ReLU mask),  dWd = dcolT^T X.  Wd[(ky*3 + kx)*32 + co, ci] = W_ref[ci, co, ky, kx] (permuted at the
+// API).  The 3-channel output layer is a direct CUDA-core kernel (384 FMAs per pixel) fused with nothing; its weight
+// gradient is a two-pass deterministic reduction.
+#include "deconv.cuh"
+
+#include <algorithm>
+
+#include "reduce.cuh"
+
+namespace rlrep {
+
+namespace {
+
+int grid_for(long long work, int threads) {
+  const long long want = (work + threads - 1) / threads;
+  return (int)std::max<long long>(1, std::min<long long>(want, (long long)kNumSMs * 16));
+}
+
+// [B, 32, P] (row pitch ld) -> NHWC [B, P, 32]
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, long long ld, int B, int P, float* __restrict__ out) {
+  const long long total = (long long)B * P * 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i & 31);
+    const long long bp = i >> 5;
+    const int p = (int)(bp % P);
+    const long long b = bp / P;
+    out[i] = in[b * ld + (long long)c * P + p];
+  }
+}
+__global__ void nhwc_to_nchw_pitch_kernel(const float* __restrict__ in, int B, int P, float* __restrict__ out, long long ld) {
+  const long long total = (long long)B * P * 32;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int p = (int)(i % P);
+    const int c = (int)((i / P) % 32);
+    const long long b = i / ((long long)P * 32);
+    out[b * ld + (long long)c * P + p] = in[(b * P + p) * 32 + c];
+  }
+}
+
+// Y[b, y, x, co] = relu(bias[co] + sum over taps with (y - ky) = S*iy, (x - kx) = S*ix of colT[(b, iy, ix), tap, co])
+template <int S>
+__global__ void col2im_bias_relu_kernel(const float4* __restrict__ colT, const float4* __restrict__ bias, int B, int Hi,
+                                        int Ho, float4* __restrict__ y) {
+  const long long total = (long long)B * Ho * Ho * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i & 7);
+    const long long pix = i >> 3;
+    const int ox = (int)(pix % Ho), oy = (int)((pix / Ho) % Ho), b = (int)(pix / ((long long)Ho * Ho));
+    float4 acc = __ldg(bias + c4);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int ty = oy - ky;
+      if (ty < 0 || (S == 2 && (ty & 1))) continue;
+      const int iy = ty / S;
+      if (iy >= Hi) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int tx = ox - kx;
+        if (tx < 0 || (S == 2 && (tx & 1))) continue;
+        const int ix = tx / S;
+        if (ix >= Hi) continue;
+        const float4 g = colT[(((long long)b * Hi + iy) * Hi + ix) * 72 + (ky * 3 + kx) * 8 + c4];
+        acc.x += g.x; acc.y += g.y; acc.z += g.z; acc.w += g.w;
+      }
+    }
+    y[i] = make_float4(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f), fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f));
+  }
+}
+
+// dcolT[(b, iy, ix), tap, c] = dY[b, S*iy + ky, S*ix + kx, c]
+template <int S>
+__global__ void im2col_strided_kernel(const float4* __restrict__ dy, int B, int Hi, int Ho, float4* __restrict__ col) {
+  const long long total = (long long)B * Hi * Hi * 72;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % 72);
+    const long long row = i / 72;
+    const int tap = q >> 3, c4 = q & 7;
+    const int ky = tap / 3, kx = tap % 3;
+    const int ix = (int)(row % Hi), iy = (int)((row / Hi) % Hi), b = (int)(row / ((long long)Hi * Hi));
+    col[i] = dy[(((long long)b * Ho + S * iy + ky) * Ho + S * ix + kx) * 8 + c4];
+  }
+}
+
+// Output layer Conv2d(32 -> 3, kernel 2, padding 1) on X [B, 83, 83, 32]: one thread per output pixel;
+// pred [B*84*84, 4] (channel 3 unused).  w_s[(tap*32 + c)*3 + o] = W[o, c, ky, kx] staged in shared memory.
+__global__ void __launch_bounds__(256) out_conv_fwd_kernel(const float4* __restrict__ x, const float* __restrict__ W,
+                                                           const float* __restrict__ bias, int B, int Hi, int Ho,
+                                                           float4* __restrict__ pred) {
+  __shared__ float w_s[4 * 32 * 3];
+  for (int i = threadIdx.x; i < 384; i += 256) {
+    const int o = i % 3, c = (i / 3) % 32, tap = i / 96;
+    w_s[i] = W[(o * 32 + c) * 4 + tap];
+  }
+  __syncthreads();
+  const float b0 = bias[0], b1 = bias[1], b2 = bias[2];
+  const long long total = (long long)B * Ho * Ho;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ox = (int)(i % Ho), oy = (int)((i / Ho) % Ho), b = (int)(i / ((long long)Ho * Ho));
+    float a0 = b0, a1 = b1, a2 = b2;
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) {
+      const int iy = oy + (tap >> 1) - 1, ix = ox + (tap & 1) - 1;
+      if (iy < 0 || iy >= Hi || ix < 0 || ix >= Hi) continue;
+      const float4* px = x + (((long long)b * Hi + iy) * Hi + ix) * 8;
+      const float* w = w_s + tap * 96;
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 v = px[c4];
+        const float* wc = w + c4 * 12;
+        a0 = fmaf(v.x, wc[0], a0); a1 = fmaf(v.x, wc[1], a1); a2 = fmaf(v.x, wc[2], a2);
+        a0 = fmaf(v.y, wc[3], a0); a1 = fmaf(v.y, wc[4], a1); a2 = fmaf(v.y, wc[5], a2);
+        a0 = fmaf(v.z, wc[6], a0); a1 = fmaf(v.z, wc[7], a1); a2 = fmaf(v.z, wc[8], a2);
+        a0 = fmaf(v.w, wc[9], a0); a1 = fmaf(v.w, wc[10], a1); a2 = fmaf(v.w, wc[11], a2);
+      }
+    }
+    pred[i] = make_float4(a0, a1, a2, 0.f);
+  }
+}
+
+// dpred = scale * sign(pred - (t / 255 - 0.5)); partial[block] = sum |diff|.  target uint8 [B, 3, Ho, Ho].
+__global__ void __launch_bounds__(256) l1_loss_kernel(const float4* __restrict__ pred, const unsigned char* __restrict__ tgt,
+                                                      int B, int Ho, float scale, float4* __restrict__ dpred,
+                                                      float* __restrict__ partial) {
+  __shared__ float scratch[33];
+  const long long P = (long long)Ho * Ho, total = (long long)B * P;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / P, p = i - b * P;
+    const float4 v = pred[i];
+    const unsigned char* t = tgt + b * 3 * P + p;
+    const float d0 = v.x - __fsub_rn(__fdiv_rn((float)t[0], 255.0f), 0.5f);
+    const float d1 = v.y - __fsub_rn(__fdiv_rn((float)t[P], 255.0f), 0.5f);
+    const float d2 = v.z - __fsub_rn(__fdiv_rn((float)t[2 * P], 255.0f), 0.5f);
+    acc += fabsf(d0) + fabsf(d1) + fabsf(d2);
+    dpred[i] = make_float4(d0 > 0.f ? scale : (d0 < 0.f ? -scale : 0.f), d1 > 0.f ? scale : (d1 < 0.f ? -scale : 0.f),
+                           d2 > 0.f ? scale : (d2 < 0.f ? -scale : 0.f), 0.f);
+  }
+  acc = block_sum<256>(acc, scratch);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+// out[0] = 10 * sum(partial) / count  (fixed order)
+__global__ void l1_finalize_kernel(const float* __restrict__ partial, int n, float inv_count, float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float s = 0.f;
+  for (int i = 0; i < n; ++i) s += partial[i];
+  out[0] = 10.f * s * inv_count;
+}
+
+// dX[b, iy, ix, c] = relu'(X) * sum_{tap, o} dpred[b, iy - ky + 1, ix - kx + 1, o] * W[o, c, ky, kx]
+__global__ void __launch_bounds__(256) out_conv_dgrad_kernel(const float4* __restrict__ dpred, const float* __restrict__ W,
+                                                             const float4* __restrict__ x, int B, int Hi, int Ho,
+                                                             float4* __restrict__ dx) {
+  __shared__ float w_s[4 * 32 * 3];
+  for (int i = threadIdx.x; i < 384; i += 256) {
+    const int o = i % 3, c = (i / 3) % 32, tap = i / 96;
+    w_s[i] = W[(o * 32 + c) * 4 + tap];
+  }
+  __syncthreads();
+  const long long total = (long long)B * Hi * Hi * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i & 7);
+    const long long pix = i >> 3;
+    const int ix = (int)(pix % Hi), iy = (int)((pix / Hi) % Hi), b = (int)(pix / ((long long)Hi * Hi));
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) {
+      const int oy = iy - (tap >> 1) + 1, ox = ix - (tap & 1) + 1;
+      if (oy < 0 || oy >= Ho || ox < 0 || ox >= Ho) continue;
+      const float4 g = dpred[((long long)b * Ho + oy) * Ho + ox];
+      const float* w = w_s + tap * 96 + c4 * 12;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) acc[j] = fmaf(g.x, w[3 * j], fmaf(g.y, w[3 * j + 1], fmaf(g.z, w[3 * j + 2], acc[j])));
+    }
+    const float4 xv = x[i];
+    dx[i] = make_float4(xv.x > 0.f ? acc[0] : 0.f, xv.y > 0.f ? acc[1] : 0.f, xv.z > 0.f ? acc[2] : 0.f,
+                        xv.w > 0.f ? acc[3] : 0.f);
+  }
+}
+
+// Pass 1 of dW[o, c, tap] = sum_pixels dpred[pix, o] * X[pix + tap - 1, c] and db[o] = sum dpred[pix, o]:
+// lane = input channel, one warp walks output pixels; partial[block] = [12 * 32 weight sums | 3 bias sums | pad] (388).
+__global__ void __launch_bounds__(256) out_conv_wgrad_kernel(const float4* __restrict__ dpred, const float* __restrict__ x,
+                                                             int B, int Hi, int Ho, float* __restrict__ partial) {
+  __shared__ float red[8][12 * 32 + 4];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const long long total = (long long)B * Ho * Ho;
+  const long long gw = (long long)blockIdx.x * 8 + warp, nw = (long long)gridDim.x * 8;
+  float acc[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) acc[j] = 0.f;
+  float bsum = 0.f;
+  for (long long i = gw; i < total; i += nw) {
+    const int ox = (int)(i % Ho), oy = (int)((i / Ho) % Ho), b = (int)(i / ((long long)Ho * Ho));
+    const float4 g = dpred[i];
+    if (lane < 3) bsum += lane == 0 ? g.x : (lane == 1 ? g.y : g.z);
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) {
+      const int iy = oy + (tap >> 1) - 1, ix = ox + (tap & 1) - 1;
+      if (iy < 0 || iy >= Hi || ix < 0 || ix >= Hi) continue;
+      const float v = x[(((long long)b * Hi + iy) * Hi + ix) * 32 + lane];
+      acc[tap * 3 + 0] = fmaf(g.x, v, acc[tap * 3 + 0]);
+      acc[tap * 3 + 1] = fmaf(g.y, v, acc[tap * 3 + 1]);
+      acc[tap * 3 + 2] = fmaf(g.z, v, acc[tap * 3 + 2]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 12; ++j) red[warp][j * 32 + lane] = acc[j];
+  if (lane < 3) red[warp][384 + lane] = bsum;
+  __syncthreads();
+  for (int k = threadIdx.x; k < 387; k += 256) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][k];
+    partial[(size_t)blockIdx.x * 388 + k] = s;
+  }
+}
+// Pass 2: dW[o, c, tap] (reference layout [3, 32, 2, 2]) and db[o] from the per-block partials, fixed order.
+__global__ void out_conv_wgrad_finish_kernel(const float* __restrict__ partial, int n_blocks, float* __restrict__ dW,
+                                             float* __restrict__ db) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= 387) return;
+  float s = 0.f;
+  for (int i = 0; i < n_blocks; ++i) s += partial[(size_t)i * 388 + k];
+  if (k < 384) {
+    const int j = k / 32, c = k % 32, tap = j / 3, o = j % 3;
+    dW[(o * 32 + c) * 4 + tap] = s;
+  } else {
+    db[k - 384] = s;
+  }
+}
+
+// [B*P, 4] -> [B, 3, P]
+__global__ void pred_to_nchw_kernel(const float4* __restrict__ pred, int B, long long P, float* __restrict__ out) {
+  const long long total = (long long)B * P;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / P, p = i - b * P;
+    const float4 v = pred[i];
+    out[b * 3 * P + p] = v.x;
+    out[b * 3 * P + P + p] = v.y;
+    out[b * 3 * P + 2 * P + p] = v.z;
+  }
+}
+
+}  // namespace
+
+ConvDecoder::ConvDecoder(int batch, Precision prec, cudaStream_t s) : B_(batch), stream_(s) {
+  RLREP_CHECK(B_ > 0, "bad decoder batch");
+  g_.name = "decoder";
+  for (int l = 0; l < 4; ++l) {  // stored [(ky, kx, co), ci]; exported as the reference's [ci, co, ky, kx]
+    w_off_[l] = g_.add("deconvnet." + std::to_string(2 * l) + ".weight", 288, 32);
+    b_off_[l] = g_.add("deconvnet." + std::to_string(2 * l) + ".bias", 32, 1);
+  }
+  w_off_[4] = g_.add("deconvnet.8.weight", 3, 128);  // the reference's [3, 32, 2, 2] flattened
+  b_off_[4] = g_.add("deconvnet.8.bias", 3, 1);
+  g_.want(arena_);
+  for (int i = 0; i < 5; ++i) {
+    arena_.want(&act_[i], rows(i) * 32);
+    arena_.want(&dact_[i], rows(i) * 32);
+  }
+  arena_.want(&col_, rows(3) * 288);  // the largest GEMM side: 41 x 41 pixels per image
+  arena_.want(&pred_, rows(5) * 4);
+  arena_.want(&dpred_, rows(5) * 4);
+  arena_.want(&loss_partial_, kLossBlocks);
+  arena_.want(&wg_partial_, (size_t)kWgBlocks * 388);
+  arena_.want(&bias_partial_, kBiasChunks * 32);
+  arena_.commit();
+  gemm_.init(prec, 0);
+}
+
+Linear ConvDecoder::layer(int l) const {
+  Linear w;
+  w.W = g_.p + w_off_[l];
+  w.dW = g_.g + w_off_[l];
+  w.b = nullptr;  // the bias is added after col2im, not per tap
+  w.db = nullptr;
+  w.out = 288; w.in = 32; w.ld = 32; w.out_alloc = 288;
+  return w;
+}
+
+void ConvDecoder::forward(const float* x_dev, int ld_x) {
+  cudaStream_t s = stream_;
+  const int P0 = hw_[0] * hw_[0];
+  nchw_to_nhwc_kernel<<<grid_for((long long)B_ * P0 * 32, 256), 256, 0, s>>>(x_dev, ld_x > 0 ? ld_x : (long long)P0 * 32, B_,
+                                                                            P0, act_[0]);
+  RLREP_LAUNCHED_W("nchw_to_nhwc", s, 8.0 * B_ * P0 * 32, 0.0);
+  for (int l = 0; l < 4; ++l) {
+    const int Hi = hw_[l], Ho = hw_[l + 1];
+    linear_fwd(gemm_, s, (int)rows(l), Mat{act_[l], 32}, layer(l), ACT_NONE, col_, 288);
+    const float4* colT = reinterpret_cast<const float4*>(col_);
+    const float4* bias = reinterpret_cast<const float4*>(g_.p + b_off_[l]);
+    float4* y = reinterpret_cast<float4*>(act_[l + 1]);
+    if (l < 3) col2im_bias_relu_kernel<1><<<grid_for(rows(l + 1) * 8, 256), 256, 0, s>>>(colT, bias, B_, Hi, Ho, y);
+    else col2im_bias_relu_kernel<2><<<grid_for(rows(l + 1) * 8, 256), 256, 0, s>>>(colT, bias, B_, Hi, Ho, y);
+    RLREP_LAUNCHED_W("col2im_bias_relu", s, 4.0 * (rows(l) * 288 + rows(l + 1) * 32), 0.0);
+  }
+  out_conv_fwd_kernel<<<grid_for(rows(5), 256), 256, 0, s>>>(reinterpret_cast<const float4*>(act_[4]), g_.p + w_off_[4],
+                                                            g_.p + b_off_[4], B_, hw_[4], hw_[5],
+                                                            reinterpret_cast<float4*>(pred_));
+  RLREP_LAUNCHED_W("out_conv_fwd", s, 4.0 * (rows(4) * 32 + rows(5) * 4), 2.0 * rows(5) * 384);
+}
+
+void ConvDecoder::l1_loss(const unsigned char* target_dev, float grad_scale, float* loss_out_dev) {
+  cudaStream_t s = stream_;
+  const float count = (float)rows(5) * 3.f;
+  l1_loss_kernel<<<kLossBlocks, 256, 0, s>>>(reinterpret_cast<const float4*>(pred_), target_dev, B_, hw_[5],
+                                            grad_scale * 10.f / count, reinterpret_cast<float4*>(dpred_), loss_partial_);
+  RLREP_LAUNCHED_W("l1_loss", s, rows(5) * 35.0, 0.0);
+  l1_finalize_kernel<<<1, 32, 0, s>>>(loss_partial_, kLossBlocks, 1.f / count, loss_out_dev);
+  RLREP_LAUNCHED("l1_finalize", s);
+}
+
+void ConvDecoder::backward(float* dx_dev, int ld_dx) {
+  cudaStream_t s = stream_;
+  // ---- output layer
+  out_conv_wgrad_kernel<<<kWgBlocks, 256, 0, s>>>(reinterpret_cast<const float4*>(dpred_), act_[4], B_, hw_[4], hw_[5],
+                                                 wg_partial_);
+  RLREP_LAUNCHED_W("out_conv_wgrad", s, 4.0 * (rows(4) * 32 + rows(5) * 4), 2.0 * rows(5) * 384);
+  out_conv_wgrad_finish_kernel<<<2, 256, 0, s>>>(wg_partial_, kWgBlocks, g_.g + w_off_[4], g_.g + b_off_[4]);
+  RLREP_LAUNCHED("out_conv_wgrad_finish", s);
+  out_conv_dgrad_kernel<<<grid_for(rows(4) * 8, 256), 256, 0, s>>>(
+      reinterpret_cast<const float4*>(dpred_), g_.p + w_off_[4], reinterpret_cast<const float4*>(act_[4]), B_, hw_[4],
+      hw_[5], reinterpret_cast<float4*>(dact_[4]));
+  RLREP_LAUNCHED_W("out_conv_dgrad", s, 4.0 * (rows(5) * 4 + 2.0 * rows(4) * 32), 2.0 * rows(4) * 384);
+  // ---- transposed convolutions, last to first; dact_[l + 1] already carries the ReLU mask of its layer
+  for (int l = 3; l >= 0; --l) {
+    const int Hi = hw_[l], Ho = hw_[l + 1];
+    const Linear w = layer(l);
+    launch_colsum_tall(dact_[l + 1], 32, rows(l + 1), 32, bias_partial_, kBiasChunks, g_.g + b_off_[l], s);
+    const float4* dy = reinterpret_cast<const float4*>(dact_[l + 1]);
+    float4* col = reinterpret_cast<float4*>(col_);
+    if (l < 3) im2col_strided_kernel<1><<<grid_for(rows(l) * 72, 256), 256, 0, s>>>(dy, B_, Hi, Ho, col);
+    else im2col_strided_kernel<2><<<grid_for(rows(l) * 72, 256), 256, 0, s>>>(dy, B_, Hi, Ho, col);
+    RLREP_LAUNCHED_W("im2col_strided", s, 4.0 * (rows(l + 1) * 32 + rows(l) * 288), 0.0);
+    linear_wgrad(gemm_, s, (int)rows(l), Mat{col_, 288}, Mat{act_[l], 32}, w, Mat(), 0, /*bias_grad=*/false);
+    // the decoder input (l == 0) is a plain linear output: no ReLU mask
+    linear_dgrad(gemm_, s, (int)rows(l), Mat{col_, 288}, w, l > 0 ? DACT_RELU_OUT : DACT_NONE,
+                 l > 0 ? Mat{act_[l], 32} : Mat(), dact_[l], 32);
+  }
+  const int P0 = hw_[0] * hw_[0];
+  nhwc_to_nchw_pitch_kernel<<<grid_for((long long)B_ * P0 * 32, 256), 256, 0, s>>>(dact_[0], B_, P0, dx_dev,
+                                                                                  ld_dx > 0 ? ld_dx : (long long)P0 * 32);
+  RLREP_LAUNCHED_W("nhwc_to_nchw", s, 8.0 * B_ * P0 * 32, 0.0);
+}
+
+void ConvDecoder::copy_pred(float* pred_nchw_dev) {
+  const long long P = (long long)hw_[5] * hw_[5];
+  pred_to_nchw_kernel<<<grid_for((long long)B_ * P, 256), 256, 0, stream_>>>(reinterpret_cast<const float4*>(pred_), B_, P,
+                                                                            pred_nchw_dev);
+  RLREP_LAUNCHED("pred_to_nchw", stream_);
+}
+
+}  // namespace rlrep

@@ -1,0 +1,44 @@
+// muLV-Rep pixel decoder handle (see deconv.cu).
+#pragma once
+#include "agent.cuh"
+
+namespace rlrep {
+
+class ConvDecoder {
+ public:
+  ConvDecoder(int batch, Precision prec, cudaStream_t s);
+  // x fp32 [B, 32 * 35 * 35] in the reference's (channel, row, column) order, row pitch ld_x -> prediction [B, 3, 84, 84]
+  // kept inside the handle (read it with copy_pred)
+  void forward(const float* x_dev, int ld_x);
+  // s_loss = 10 * mean |pred - (target / 255 - 0.5)| (drqv2.py:359-362); target uint8 [B, 3, 84, 84].  Leaves
+  // d loss / d pred * grad_scale inside the handle for backward(); loss_out[0] = s_loss.
+  void l1_loss(const unsigned char* target_dev, float grad_scale, float* loss_out_dev);
+  // parameter gradients of the five layers and dx [B, 32 * 35 * 35] (row pitch ld_dx)
+  void backward(float* dx_dev, int ld_dx);
+  void copy_pred(float* pred_nchw_dev);  // [B, 3, 84, 84]
+
+  ParamGroup& group() { return g_; }
+  int batch() const { return B_; }
+  cudaStream_t stream() const { return stream_; }
+
+ private:
+  long long rows(int i) const { return (long long)B_ * hw_[i] * hw_[i]; }
+  Linear layer(int l) const;
+
+  static constexpr int kLossBlocks = 592;  // 4 x 148 SMs
+  int B_;
+  int hw_[6] = {35, 37, 39, 41, 83, 84};  // act_[i] is [B, hw_[i], hw_[i], 32]; the prediction is [B, 84, 84, 3(+1)]
+  cudaStream_t stream_;
+  DeviceArena arena_;
+  GemmRunner gemm_;
+  ParamGroup g_;
+  size_t w_off_[5] = {0, 0, 0, 0, 0}, b_off_[5] = {0, 0, 0, 0, 0};
+  float* act_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  float* dact_[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+  float *col_ = nullptr, *pred_ = nullptr, *dpred_ = nullptr, *loss_partial_ = nullptr, *wg_partial_ = nullptr;
+  float* bias_partial_ = nullptr;
+  static constexpr int kBiasChunks = 296;
+  static constexpr int kWgBlocks = 592;
+};
+
+}  // namespace rlrep

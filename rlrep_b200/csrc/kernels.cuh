@@ -207,6 +207,40 @@ void launch_drq_critic_loss(const float* reward, const float* discount, const fl
 // actor_loss = -mean(min(q1, q2)); dq = -1/B on the argmin; metrics = {actor_loss}
 void launch_drq_actor_loss(const float* q1, const float* q2, int B, float* dq1, float* dq2, float* metrics, cudaStream_t s);
 
+// ---- muLV-Rep DrQ-v2 pixel update (agent/mulvdrq/drqv2.py:313-461, vae.py:13-124; kernels_mulv.cu) ----------------------
+// Gaussian heads are two [B, ld] matrices: mean (after tanh(LayerNorm)) and raw log-std (after LayerNorm; consumers clamp
+// to [-20, 2]); padding columns [D, ld) are zero.
+// y[:, 0:n] = act(LayerNorm_n(x) * gamma + beta), act = tanh or identity; columns [n, zero_to) of y zeroed.
+void launch_ln_act_fwd(const float* x, int ld_x, int B, int n, const float* gamma, const float* beta, bool use_tanh,
+                       float* y, int ld_y, int zero_to, float* xhat, int ld_h, float* rstd, cudaStream_t s);
+// Backward: dx (columns [n, zero_to) zeroed); column sums of g_beta / g_gamma are the LayerNorm parameter gradients.
+void launch_ln_act_bwd(const float* dy, int ld_dy, const float* y, int ld_y, const float* xhat, int ld_h, const float* rstd,
+                       int B, int n, const float* gamma, bool use_tanh, float* dx, int ld_dx, int zero_to, float* g_beta,
+                       float* g_gamma, int ld_g, cudaStream_t s);
+// z[b, 0:D] = m + eps * exp(clamp(raw)) (Normal.rsample, vae.py:50-58); eps [B, D]; z [B, ld_z], padding zeroed.
+void launch_gauss_sample(const float* m, const float* raw, int ld, int B, int D, const float* eps, float* z, int ld_z,
+                         cudaStream_t s);
+// w * KL(head 1 || head 2).mean() and the backward of the sample (dz) into head 1; head 2 also receives the critic's
+// gradient (dcm, dcraw; nullable).  partial[block] = unweighted sum of KL elements.
+void launch_gauss_kl_bwd(const float* m1, const float* raw1, const float* m2, const float* raw2, int ld, int B, int D,
+                         const float* eps, const float* dz, float w, const float* dcm, const float* dcraw, float* dm1,
+                         float* draw1, float* dm2, float* draw2, float* partial, int n_blocks, cudaStream_t s);
+// Critic input (drqv2.py:177-183): x[b*NN + j] = m[b] + exp(clamp(raw[b])) * noise[j] * c_noise; x [B*NN, ld_x].
+void launch_gauss_noise_expand(const float* m, const float* raw, int ld, int B, int D, const float* noise, int NN,
+                               float c_noise, float* x, int ld_x, cudaStream_t s);
+void launch_gauss_noise_expand_bwd(const float* dx, int ld_x, const float* raw, int ld, int B, int D, const float* noise,
+                                   int NN, float c_noise, float* dm, float* draw, cudaStream_t s);
+// launch_group_mean_bwd with the activation derivative as a parameter (the pixel critic uses ReLU).
+void launch_group_mean_bwd_dact(const float* dmean, const float* hid, int ld, int B, int NN, int C, int dact, float* dhid,
+                                float* colsum_partial, cudaStream_t s);
+// y = r + discount * min(tq1, tq2); loss = smooth_l1(q1, y) + smooth_l1(q2, y); dq = clamp(q - y, +-1) / B;
+// metrics = {critic_loss, mean(q1), mean(q2), mean(y)}
+void launch_huber_critic_loss(const float* reward, const float* discount, const float* tq1, const float* tq2,
+                              const float* q1, const float* q2, int B, float* dq1, float* dq2, float* metrics,
+                              cudaStream_t s);
+// out[0] = mse(r_hat, r); dr = w * 2 (r_hat - r) / B
+void launch_reward_mse(const float* r_hat, const float* reward, int B, float w, float* dr, float* out, cudaStream_t s);
+
 // Fused multi-tensor Adam (+ optional Polyak of a prefix of the arena into its target copy).
 // One launch updates a whole optimiser group laid out as flat arrays p / g / m / v of n floats (n % 4 == 0).
 //   torch.optim.Adam defaults: beta = (0.9, 0.999), eps = 1e-8, no weight decay / amsgrad.

@@ -288,3 +288,197 @@ class DrQv2:
                                              eps.ctypes.data, stddev, m.ctypes.data))
         return {"loss/actor_loss": float(m[4]), "info/policy_std": stddev, "loss/critic_loss": float(m[0]),
                 "info/q_pred": float(m[1]), "info/q_target": float(m[2]), "info/reward": float(m[3])}
+
+
+class MulvConfig(C.Structure):
+    """Mirror of `rlrep_mulv_config` (include/rlrep_b200.h)."""
+    _fields_ = [("batch_size", C.c_int), ("channels", C.c_int), ("height", C.c_int), ("action_dim", C.c_int),
+                ("feat_dim", C.c_int), ("hidden_dim", C.c_int), ("num_noise", C.c_int), ("lr", C.c_double),
+                ("tau", C.c_float), ("stddev_clip", C.c_float), ("vae_w", C.c_float), ("mse_w", C.c_float),
+                ("c_noise", C.c_float), ("precision", C.c_int)]
+
+
+def _cfg_get(cfg, key, default=None):
+    """mulv_config.py's `config` is an attribute-access dict; plain namespaces work too."""
+    if isinstance(cfg, dict):
+        return cfg.get(key, default)
+    return getattr(cfg, key, default)
+
+
+class MuLVDrQv2:
+    """Drop-in for the update path of agent.mulvdrq.drqv2.DrQV2Agent (drqv2.py:198-461): same constructor
+    (`obs_shape`, `action_shape`, `cfg` -- the attribute dict of mulv_config.py) and `update(replay_iter, step)`.  Only
+    the shipped configuration path is built (aug, no pre_aug, back_q2feat, tanh heads, ReLU critic, Huber loss,
+    c_targ_tau < 1, q_up_n = 1, l2_norm = 0); anything else raises.  The batch comes from the caller's replay iterator
+    as in the reference: (img uint8 [B, 9, 84, 84], action, reward, discount, next_img, img_step1)."""
+
+    METRICS = ("critic_loss", "critic_q1", "critic_q2", "critic_target_q", "s_loss", "r_loss", "kl_loss", "actor_loss")
+
+    def __init__(self, obs_shape, action_shape, cfg, *, precision="tf32"):
+        get = lambda k, d=None: _cfg_get(cfg, k, d)
+        unsupported = [k for k, want in (("aug", True), ("pre_aug", False), ("back_q2feat", True), ("tanh", True),
+                                         ("both_q", False), ("q_activ", "relu"), ("q_loss", "huber"), ("q_up_n", 1),
+                                         ("l2_norm", 0.0)) if get(k, want) != want]
+        if unsupported or not float(get("c_targ_tau", 0.01)) < 1.0:
+            raise NotImplementedError(f"only mulv_config.py's default path is built (differs in: {unsupported})")
+        self.cfg = cfg
+        self.obs_shape = tuple(int(x) for x in obs_shape)
+        self.action_dim = int(action_shape[0])
+        self.up_every = int(get("up_every", 2))
+        self.stddev_schedule = _schedule(get("stddev_schedule", "linear(1.0,0.1,500000)"))
+        self.feat_dim, self.hidden_dim, self.num_noise = int(get("feat_dim", 100)), int(get("hid_dim", 1024)), 20
+        self._precision = precision
+        self.lib = None
+        self._h = None
+        self._batch = None
+        self._pending = {}
+
+    def _ensure(self, batch):
+        if self._h is not None:
+            if batch != self._batch:
+                raise _lib.RlrepError(f"batch size is fixed per handle (was {self._batch}, got {batch})")
+            return
+        if not torch.cuda.is_available():
+            raise _lib.RlrepError("rlrep_b200.MuLVDrQv2 needs a CUDA device (there is no CPU fallback)")
+        self.lib = _lib.load()
+        get = lambda k, d: _cfg_get(self.cfg, k, d)
+        c, h, _ = self.obs_shape
+        cfg = MulvConfig(batch_size=batch, channels=c, height=h, action_dim=self.action_dim, feat_dim=self.feat_dim,
+                         hidden_dim=self.hidden_dim, num_noise=self.num_noise, lr=float(get("lr", 1e-4)),
+                         tau=float(get("c_targ_tau", 0.01)), stddev_clip=float(get("stddev_clip", 0.3)),
+                         vae_w=float(get("vae_w", 0.5)), mse_w=float(get("mse_w", 1.0)), c_noise=float(get("c_noise", 0.1)),
+                         precision=_lib.PRECISION[self._precision])
+        hd = C.c_void_p()
+        _lib.check(self.lib.rlrep_mulv_create(C.byref(cfg), None, C.byref(hd)))
+        self._h, self._batch = hd, batch
+        n = C.c_int()
+        _lib.check(self.lib.rlrep_mulv_num_tensors(hd, C.byref(n)))
+        self._index = {}
+        for i in range(n.value):
+            name, ptr, rows, cols = C.c_char_p(), C.c_void_p(), C.c_int(), C.c_int()
+            _lib.check(self.lib.rlrep_mulv_tensor_info(hd, i, C.byref(name), C.byref(ptr), C.byref(rows), C.byref(cols)))
+            self._index[name.value.decode()] = (i, rows.value, cols.value)
+        if self._pending:
+            sd, self._pending = self._pending, {}
+            self.load_state_dict(sd)
+
+    def prepare(self, batch_size):
+        self._ensure(int(batch_size))
+
+    def close(self):
+        h, self._h = self._h, None
+        if h and self.lib is not None:
+            self.lib.rlrep_mulv_destroy(h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- weights under the reference's module names ----------------------------------------------------------------
+    @staticmethod
+    def _kind(name):
+        if name.endswith("weight"):
+            if ".deconvnet.8." in name:
+                return "outconv"
+            if ".deconvnet." in name:
+                return "deconv"
+            if ".convnet." in name:
+                return "conv0" if name.endswith("convnet.0.weight") else "conv"
+            if ".trunk.1." in name or "_linear.1." in name:
+                return "vec"
+            return "mat"
+        return "vec"
+
+    def _ref_shape(self, name, rows, cols):
+        return {"outconv": (3, 32, 2, 2), "deconv": (32, 32, 3, 3), "conv0": (32, cols // 9, 3, 3),
+                "conv": (32, cols // 9, 3, 3), "vec": (rows,), "mat": (rows, cols)}[self._kind(name)]
+
+    def _read_all(self, keep):
+        sd = {}
+        for name, (i, rows, cols) in self._index.items():
+            if not keep(name):
+                continue
+            out = np.empty(rows * cols, dtype=np.float32)
+            _lib.check(self.lib.rlrep_mulv_tensor_read(self._h, i, out.ctypes.data))
+            t, kind = torch.from_numpy(out), self._kind(name)
+            if kind == "conv":      # stored [32, (ky, kx, c)] -> reference [32, c, ky, kx]
+                t = t.reshape(32, 3, 3, 32).permute(0, 3, 1, 2).contiguous()
+            elif kind == "deconv":  # stored [(ky, kx, c_out), c_in] -> reference [c_in, c_out, ky, kx]
+                t = t.reshape(3, 3, 32, 32).permute(3, 2, 0, 1).contiguous()
+            sd[name] = t.reshape(self._ref_shape(name, rows, cols))
+        return sd
+
+    def state_dict(self):
+        if self._h is None:
+            return dict(self._pending)
+        return self._read_all(lambda name: not name.startswith("grad/"))
+
+    def grads(self):
+        """Gradients left by the most recent update (actor: actor step; everything else: the model/critic step)."""
+        return {k[5:]: v for k, v in self._read_all(lambda name: name.startswith("grad/")).items()}
+
+    def load_state_dict(self, sd, sync_targets=None):
+        if self._h is None:
+            self._pending.update({k: torch.as_tensor(v).detach().clone() for k, v in sd.items()})
+            return
+        for k, v in sd.items():
+            i, rows, cols = self._index[k]
+            t = torch.as_tensor(v).detach().cpu().float()
+            if tuple(t.shape) != self._ref_shape(k, rows, cols):
+                raise ValueError(f"{k}: expected {self._ref_shape(k, rows, cols)}, got {tuple(t.shape)}")
+            kind = self._kind(k)
+            if kind == "conv":
+                t = t.permute(0, 2, 3, 1)
+            elif kind == "deconv":
+                t = t.permute(2, 3, 1, 0)
+            arr = np.ascontiguousarray(t.reshape(-1).numpy())
+            _lib.check(self.lib.rlrep_mulv_tensor_write(self._h, i, arr.ctypes.data))
+        if sync_targets or (sync_targets is None and not any("_target." in k for k in sd)):
+            _lib.check(self.lib.rlrep_mulv_sync_targets(self._h))
+
+    @property
+    def gpu_launches_last_update(self):
+        v = C.c_int()
+        _lib.check(self.lib.rlrep_mulv_last_launches(self._h, C.byref(v)))
+        return v.value
+
+    # ---- reference surface ---------------------------------------------------------------------------------------
+    def _draw(self, n):
+        """RNG consumption of one updating `update`, in the reference's order: the two shift draws,
+        randn[n, F] (feat_encoder.sample, vae.py:50-58), the next action's normals, randn[20, F] for critic_target and for
+        critic (drqv2.py:181), the actor step's normals, randn[20, F] for its critic."""
+        F, A, NN = self.feat_dim, self.action_dim, self.num_noise
+        shifts = torch.stack([torch.randint(0, 9, size=(n, 1, 1, 2), dtype=torch.float32).reshape(n, 2) for _ in range(2)])
+        eps_z = torch.randn(n, F)
+        za = torch.zeros(n, A)
+        e0 = torch.normal(za, torch.ones_like(za))
+        n0 = torch.randn(NN, F)
+        n1 = torch.randn(NN, F)
+        e1 = torch.normal(za, torch.ones_like(za))
+        n2 = torch.randn(NN, F)
+        return (shifts.to(torch.int32).numpy(), eps_z.numpy(), torch.stack([e0, e1]).numpy(),
+                torch.stack([n0, n1, n2]).numpy())
+
+    def update(self, replay_iter, step):
+        if step % self.up_every != 0:
+            return {}
+        batch = next(replay_iter)
+        img, action, reward, discount, next_img, img_step1 = (np.ascontiguousarray(torch.as_tensor(t).cpu().numpy())
+                                                              for t in batch[:6])
+        n = img.shape[0]
+        self._ensure(n)
+        assert img.dtype == np.uint8 and next_img.dtype == np.uint8 and img_step1.dtype == np.uint8, \
+            "frames must be uint8 like the reference's buffers"
+        step1 = np.ascontiguousarray(img_step1[:, -3:, :, :])  # drqv2.py:330: only the newest frame is predicted
+        shifts, eps_z, eps_act, noise = (np.ascontiguousarray(a) for a in self._draw(n))
+        stddev = float(self.stddev_schedule(step))
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32).reshape(-1)
+        action, reward, discount = f32(action), f32(reward), f32(discount)
+        m = np.zeros(8, dtype=np.float32)
+        _lib.check(self.lib.rlrep_mulv_update(self._h, img.ctypes.data, action.ctypes.data, reward.ctypes.data,
+                                              discount.ctypes.data, next_img.ctypes.data, step1.ctypes.data,
+                                              shifts.ctypes.data, eps_z.ctypes.data, eps_act.ctypes.data,
+                                              noise.ctypes.data, stddev, m.ctypes.data))
+        return {k: float(v) for k, v in zip(self.METRICS, m)}
