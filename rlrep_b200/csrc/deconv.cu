@@ -88,8 +88,9 @@ __global__ void im2col_strided_kernel(const float4* __restrict__ dy, int B, int 
   }
 }
 
-// Output layer Conv2d(32 -> 3, kernel 2, padding 1) on X [B, 83, 83, 32]: one thread per output pixel;
-// pred [B*84*84, 4] (channel 3 unused).  w_s[(tap*32 + c)*3 + o] = W[o, c, ky, kx] staged in shared memory.
+// Output layer Conv2d(32 -> 3, kernel 2, padding 1) on X [B, 83, 83, 32]: eight lanes per output pixel (one float4 of
+// channels each, so a tap is one coalesced 128-byte row), shuffle-reduced; pred [B*84*84, 4] (channel 3 unused).
+// w_s[(tap*32 + c)*3 + o] = W[o, c, ky, kx] staged in shared memory.
 __global__ void __launch_bounds__(256) out_conv_fwd_kernel(const float4* __restrict__ x, const float* __restrict__ W,
                                                            const float* __restrict__ bias, int B, int Hi, int Ho,
                                                            float4* __restrict__ pred) {
@@ -100,27 +101,32 @@ __global__ void __launch_bounds__(256) out_conv_fwd_kernel(const float4* __restr
   }
   __syncthreads();
   const float b0 = bias[0], b1 = bias[1], b2 = bias[2];
-  const long long total = (long long)B * Ho * Ho;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int ox = (int)(i % Ho), oy = (int)((i / Ho) % Ho), b = (int)(i / ((long long)Ho * Ho));
-    float a0 = b0, a1 = b1, a2 = b2;
+  const long long total = (long long)B * Ho * Ho;  // pixels; the grid-stride loop keeps whole warps together
+  const int c4 = threadIdx.x & 7;
+  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < ((total + 3) & ~3LL);
+       i += ((long long)gridDim.x * blockDim.x) >> 3) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    if (i < total) {
+      const int ox = (int)(i % Ho), oy = (int)((i / Ho) % Ho), b = (int)(i / ((long long)Ho * Ho));
 #pragma unroll
-    for (int tap = 0; tap < 4; ++tap) {
-      const int iy = oy + (tap >> 1) - 1, ix = ox + (tap & 1) - 1;
-      if (iy < 0 || iy >= Hi || ix < 0 || ix >= Hi) continue;
-      const float4* px = x + (((long long)b * Hi + iy) * Hi + ix) * 8;
-      const float* w = w_s + tap * 96;
-#pragma unroll
-      for (int c4 = 0; c4 < 8; ++c4) {
-        const float4 v = px[c4];
-        const float* wc = w + c4 * 12;
+      for (int tap = 0; tap < 4; ++tap) {
+        const int iy = oy + (tap >> 1) - 1, ix = ox + (tap & 1) - 1;
+        if (iy < 0 || iy >= Hi || ix < 0 || ix >= Hi) continue;
+        const float4 v = x[(((long long)b * Hi + iy) * Hi + ix) * 8 + c4];
+        const float* wc = w_s + tap * 96 + c4 * 12;
         a0 = fmaf(v.x, wc[0], a0); a1 = fmaf(v.x, wc[1], a1); a2 = fmaf(v.x, wc[2], a2);
         a0 = fmaf(v.y, wc[3], a0); a1 = fmaf(v.y, wc[4], a1); a2 = fmaf(v.y, wc[5], a2);
         a0 = fmaf(v.z, wc[6], a0); a1 = fmaf(v.z, wc[7], a1); a2 = fmaf(v.z, wc[8], a2);
         a0 = fmaf(v.w, wc[9], a0); a1 = fmaf(v.w, wc[10], a1); a2 = fmaf(v.w, wc[11], a2);
       }
     }
-    pred[i] = make_float4(a0, a1, a2, 0.f);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {  // fixed-order reduction over the eight channel groups of the pixel
+      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    }
+    if (c4 == 0 && i < total) pred[i] = make_float4(a0 + b0, a1 + b1, a2 + b2, 0.f);
   }
 }
 
@@ -185,29 +191,40 @@ __global__ void __launch_bounds__(256) out_conv_dgrad_kernel(const float4* __res
 }
 
 // Pass 1 of dW[o, c, tap] = sum_pixels dpred[pix, o] * X[pix + tap - 1, c] and db[o] = sum dpred[pix, o]:
-// lane = input channel, one warp walks output pixels; partial[block] = [12 * 32 weight sums | 3 bias sums | pad] (388).
+// lane = input channel; each warp walks a CONTIGUOUS span of output pixels (the rows it touches stay in L1 from one
+// output row to the next); partial[block] = [12 * 32 weight sums | 3 bias sums | pad] (388 floats).
 __global__ void __launch_bounds__(256) out_conv_wgrad_kernel(const float4* __restrict__ dpred, const float* __restrict__ x,
                                                              int B, int Hi, int Ho, float* __restrict__ partial) {
   __shared__ float red[8][12 * 32 + 4];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long total = (long long)B * Ho * Ho;
-  const long long gw = (long long)blockIdx.x * 8 + warp, nw = (long long)gridDim.x * 8;
+  const long long nw = (long long)gridDim.x * 8, gw = (long long)blockIdx.x * 8 + warp;
+  const long long span = (total + nw - 1) / nw;
+  const long long p0 = gw * span, p1 = p0 + span < total ? p0 + span : total;
   float acc[12];
 #pragma unroll
   for (int j = 0; j < 12; ++j) acc[j] = 0.f;
   float bsum = 0.f;
-  for (long long i = gw; i < total; i += nw) {
-    const int ox = (int)(i % Ho), oy = (int)((i / Ho) % Ho), b = (int)(i / ((long long)Ho * Ho));
+  int ox = (int)(p0 % Ho), oy = (int)((p0 / Ho) % Ho), b = (int)(p0 / ((long long)Ho * Ho));
+  for (long long i = p0; i < p1; ++i) {
     const float4 g = dpred[i];
+    float v[4];
+#pragma unroll
+    for (int tap = 0; tap < 4; ++tap) {  // the four loads are independent: issued back to back
+      const int iy = oy + (tap >> 1) - 1, ix = ox + (tap & 1) - 1;
+      const bool ok = iy >= 0 && iy < Hi && ix >= 0 && ix < Hi;
+      v[tap] = ok ? x[(((long long)b * Hi + iy) * Hi + ix) * 32 + lane] : 0.f;
+    }
     if (lane < 3) bsum += lane == 0 ? g.x : (lane == 1 ? g.y : g.z);
 #pragma unroll
     for (int tap = 0; tap < 4; ++tap) {
-      const int iy = oy + (tap >> 1) - 1, ix = ox + (tap & 1) - 1;
-      if (iy < 0 || iy >= Hi || ix < 0 || ix >= Hi) continue;
-      const float v = x[(((long long)b * Hi + iy) * Hi + ix) * 32 + lane];
-      acc[tap * 3 + 0] = fmaf(g.x, v, acc[tap * 3 + 0]);
-      acc[tap * 3 + 1] = fmaf(g.y, v, acc[tap * 3 + 1]);
-      acc[tap * 3 + 2] = fmaf(g.z, v, acc[tap * 3 + 2]);
+      acc[tap * 3 + 0] = fmaf(g.x, v[tap], acc[tap * 3 + 0]);
+      acc[tap * 3 + 1] = fmaf(g.y, v[tap], acc[tap * 3 + 1]);
+      acc[tap * 3 + 2] = fmaf(g.z, v[tap], acc[tap * 3 + 2]);
+    }
+    if (++ox == Ho) {
+      ox = 0;
+      if (++oy == Ho) { oy = 0; ++b; }
     }
   }
 #pragma unroll
@@ -234,6 +251,16 @@ __global__ void out_conv_wgrad_finish_kernel(const float* __restrict__ partial, 
   } else {
     db[k - 384] = s;
   }
+}
+
+// dW[n, c] = sum_p C[(p*288 + n)*ldc + p*32 + c]: the diagonal blocks of the folded weight-gradient GEMM (backward())
+__global__ void diag_block_sum_288x32_kernel(const float* __restrict__ C, int ldc, int P, float* __restrict__ dW) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 288 * 32) return;
+  const int n = i >> 5, c = i & 31;
+  float acc = 0.f;
+  for (int p = 0; p < P; ++p) acc += C[(size_t)(p * 288 + n) * ldc + p * 32 + c];  // fixed order
+  dW[i] = acc;
 }
 
 // [B*P, 4] -> [B, 3, P]
@@ -270,6 +297,7 @@ ConvDecoder::ConvDecoder(int batch, Precision prec, cudaStream_t s) : B_(batch),
   arena_.want(&loss_partial_, kLossBlocks);
   arena_.want(&wg_partial_, (size_t)kWgBlocks * 388);
   arena_.want(&bias_partial_, kBiasChunks * 32);
+  arena_.want(&wfold_, (size_t)288 * kFold * 32 * kFold);
   arena_.commit();
   gemm_.init(prec, 0);
 }
@@ -300,7 +328,7 @@ void ConvDecoder::forward(const float* x_dev, int ld_x) {
     else col2im_bias_relu_kernel<2><<<grid_for(rows(l + 1) * 8, 256), 256, 0, s>>>(colT, bias, B_, Hi, Ho, y);
     RLREP_LAUNCHED_W("col2im_bias_relu", s, 4.0 * (rows(l) * 288 + rows(l + 1) * 32), 0.0);
   }
-  out_conv_fwd_kernel<<<grid_for(rows(5), 256), 256, 0, s>>>(reinterpret_cast<const float4*>(act_[4]), g_.p + w_off_[4],
+  out_conv_fwd_kernel<<<grid_for(rows(5) * 8, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(act_[4]), g_.p + w_off_[4],
                                                             g_.p + b_off_[4], B_, hw_[4], hw_[5],
                                                             reinterpret_cast<float4*>(pred_));
   RLREP_LAUNCHED_W("out_conv_fwd", s, 4.0 * (rows(4) * 32 + rows(5) * 4), 2.0 * rows(5) * 384);
@@ -338,7 +366,21 @@ void ConvDecoder::backward(float* dx_dev, int ld_dx) {
     if (l < 3) im2col_strided_kernel<1><<<grid_for(rows(l) * 72, 256), 256, 0, s>>>(dy, B_, Hi, Ho, col);
     else im2col_strided_kernel<2><<<grid_for(rows(l) * 72, 256), 256, 0, s>>>(dy, B_, Hi, Ho, col);
     RLREP_LAUNCHED_W("im2col_strided", s, 4.0 * (rows(l + 1) * 32 + rows(l) * 288), 0.0);
-    linear_wgrad(gemm_, s, (int)rows(l), Mat{col_, 288}, Mat{act_[l], 32}, w, Mat(), 0, /*bias_grad=*/false);
+    // dWd = dcolT^T X is a [288, 32] output over K = B*Hi*Hi rows: three M-tiles x at most 8 split-K CTAs would leave
+    // the GPU idle.  Fold kFold consecutive rows into one (conv.cu does the same): [rows/F, 288 F]^T [rows/F, 32 F] is a
+    // [288 F, 32 F] matrix whose F diagonal blocks sum to dWd -- F x the tensor-core work, F x F the parallelism.
+    if (rows(l) % kFold == 0) {
+      GemmArgs a;
+      a.M = 288 * kFold; a.N = 32 * kFold; a.K = (int)(rows(l) / kFold);
+      a.A = col_; a.lda = 288 * kFold; a.a_mn = true;
+      a.B = act_[l]; a.ldb = 32 * kFold; a.b_mn = true;
+      a.C = wfold_; a.ldc = a.N;
+      gemm_.run(a, s);
+      diag_block_sum_288x32_kernel<<<ceil_div(288 * 32, 256), 256, 0, s>>>(wfold_, a.N, kFold, w.dW);
+      RLREP_LAUNCHED("diag_block_sum", s);
+    } else {
+      linear_wgrad(gemm_, s, (int)rows(l), Mat{col_, 288}, Mat{act_[l], 32}, w, Mat(), 0, /*bias_grad=*/false);
+    }
     // the decoder input (l == 0) is a plain linear output: no ReLU mask
     linear_dgrad(gemm_, s, (int)rows(l), Mat{col_, 288}, w, l > 0 ? DACT_RELU_OUT : DACT_NONE,
                  l > 0 ? Mat{act_[l], 32} : Mat(), dact_[l], 32);

@@ -39,6 +39,8 @@ class ConvDecoder {
   float* bias_partial_ = nullptr;
   static constexpr int kBiasChunks = 296;
   static constexpr int kWgBlocks = 592;
+  static constexpr int kFold = 4;  // rows folded per GEMM row in the weight-gradient GEMMs (deconv.cu backward())
+  float* wfold_ = nullptr;
 };
 
 }  // namespace rlrep

@@ -159,12 +159,23 @@ __global__ void __launch_bounds__(256) colsum_tall_stage1_kernel(const float* __
     partial[(long long)blockIdx.y * cols + j] = t;
   }
 }
-__global__ void colsum_tall_stage2_kernel(const float* __restrict__ partial, int chunks, int cols, float* __restrict__ out) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
-  if (j >= cols) return;
+// 32 columns x 8 chunk-slices per CTA: eight independent partial sums per column, combined in a fixed order
+__global__ void __launch_bounds__(256) colsum_tall_stage2_kernel(const float* __restrict__ partial, int chunks, int cols,
+                                                                 float* __restrict__ out) {
+  __shared__ float part[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int j = blockIdx.x * 32 + tx;
   float t = 0.f;
-  for (int c = 0; c < chunks; ++c) t += partial[(long long)c * cols + j];
-  out[j] = t;
+  if (j < cols)
+    for (int c = ty; c < chunks; c += 8) t += partial[(long long)c * cols + j];
+  part[ty][tx] = t;
+  __syncthreads();
+  if (ty == 0 && j < cols) {
+    float v = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) v += part[q][tx];
+    out[j] = v;
+  }
 }
 
 struct ColJobs {
@@ -729,7 +740,7 @@ void launch_colsum_tall(const float* X, int ld, long long rows, int cols, float*
   const int rows_per = (int)((rows + chunks - 1) / chunks);
   colsum_tall_stage1_kernel<<<dim3(ceil_div(cols, 32), chunks), 256, 0, s>>>(X, ld, rows, cols, rows_per, partial);
   RLREP_LAUNCHED_W("colsum_tall", s, 4.0 * (double)rows * cols, 0.0);
-  colsum_tall_stage2_kernel<<<ceil_div(cols, 128), 128, 0, s>>>(partial, chunks, cols, out);
+  colsum_tall_stage2_kernel<<<ceil_div(cols, 32), 256, 0, s>>>(partial, chunks, cols, out);
   RLREP_LAUNCHED("colsum_tall_final", s);
 }
 
