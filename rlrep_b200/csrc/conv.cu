@@ -11,6 +11,8 @@
 // HBM traffic of the convolutions; replacing them with TMA im2col loads inside the GEMM's producer is the planned v2.
 #include "conv.cuh"
 
+#include <cstdlib>
+
 #include <algorithm>
 
 namespace rlrep {
@@ -150,7 +152,10 @@ ConvEncoder::ConvEncoder(int batch, int in_channels, int height, Precision prec,
     arena_.want(&act_[l], rows(l) * 32);
     arena_.want(&dact_[l], rows(l) * 32);
   }
-  arena_.want(&dcol_, rows(1) * 288);
+  // RLREP_CONV_V1=1 keeps the explicit  dcol = dY W  +  col2im  data gradient (A/B runs); default: implicit
+  implicit_dgrad_ = !(std::getenv("RLREP_CONV_V1") && std::atoi(std::getenv("RLREP_CONV_V1")) != 0);
+  if (implicit_dgrad_) corr_.want(arena_, B_, hw_[1]);
+  else arena_.want(&dcol_, rows(1) * 288);
   arena_.want(&bias_partial_, kBiasChunks * 32);
   arena_.want(&wfold_, (size_t)32 * kFold * 288 * kFold);
   arena_.commit();
@@ -204,6 +209,12 @@ void ConvEncoder::backward(const float* dfeat_dev, int ld_dfeat) {
     }
     launch_colsum_tall(dy.p, 32, rows(l), 32, bias_partial_, kBiasChunks, w.db, s);
     if (l == 0) break;
+    if (implicit_dgrad_) {
+      // dX = full correlation of dY with W (x ReLU mask), the taps walked by the GEMM's TMA producer (conv_implicit.cu)
+      full_correlation_3x3(gemm_, s, B_, hw_[l], dact_[l], w.W, FC_CONV_DGRAD, nullptr, ACT_NONE, act_[l - 1],
+                           dact_[l - 1], corr_);
+      continue;
+    }
     linear_dgrad(gemm_, s, (int)rows(l), dy, w, DACT_NONE, Mat(), dcol_, 288);
     col2im_nhwc32_kernel<<<grid_for((long long)rows(l - 1) * 8, 256), 256, 0, s>>>(
         reinterpret_cast<const float4*>(dcol_), reinterpret_cast<const float4*>(act_[l - 1]), B_, hw_[l - 1], hw_[l],

@@ -1,6 +1,7 @@
 // DrQ-v2 pixel encoder handle (see conv.cu).
 #pragma once
 #include "agent.cuh"
+#include "conv_implicit.cuh"
 
 namespace rlrep {
 
@@ -35,6 +36,8 @@ class ConvEncoder {
   float* act_[4] = {nullptr, nullptr, nullptr, nullptr};
   float* dact_[4] = {nullptr, nullptr, nullptr, nullptr};
   float* dcol_ = nullptr;
+  bool implicit_dgrad_ = true;
+  FullCorrScratch corr_;
   static constexpr int kBiasChunks = 296;  // 2 x 148 SMs
   float* bias_partial_ = nullptr;
   static constexpr int kFold = 4;  // rows folded per GEMM row in the weight-gradient GEMMs (conv.cu backward())

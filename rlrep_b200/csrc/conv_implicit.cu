@@ -1,0 +1,89 @@
+// Full correlation  out[oy, ox] = sum_taps in[oy - ky, ox - kx] W[ky, kx]  (the data gradient of a 3x3 convolution, and
+// the forward pass of a stride-1 ConvTranspose2d) WITHOUT a column matrix.
+//
+// Version 1 ran it as  col = X W^T  ([B*Hi*Hi, 32] x [288, 32]^T, a K = 32 GEMM with 30k one-k-block tiles) followed by
+// a gather-form col2im: ~500 us per layer at B = 256, 6x the HBM time of its traffic, because every 128 x 32 tile pays
+// the whole TMA -> MMA -> epilogue latency for a single k-block.  Here the input is copied once onto a zero-padded
+// grid (Hi + 4 wide, so that every tap of every valid output is an in-grid read), and the GEMM's TMA producer walks the
+// nine taps by SHIFTING ITS ROW COORDINATE on that grid (GemmArgs::conv_w): one K = 288 GEMM, A re-read from L2 only,
+// output on the same grid, then one compaction pass that also applies the ReLU mask.  Taps are visited in flipped
+// order (t -> 8 - t) so all shifts are non-negative; the weights are repacked to match ([32, 9 * 32], 37 KB).
+#include "conv_implicit.cuh"
+
+#include <algorithm>
+
+namespace rlrep {
+
+namespace {
+
+int grid_for(long long work, int threads) {
+  const long long want = (work + threads - 1) / threads;
+  return (int)std::max<long long>(1, std::min<long long>(want, (long long)kNumSMs * 16));
+}
+
+// padded[b, y, x] = in[b, y - 2, x - 2] inside, zero on the two-pixel frame; Wp = Hi + 4
+__global__ void pad_grid_kernel(const float4* __restrict__ in, int B, int Hi, float4* __restrict__ padded) {
+  const int Wp = Hi + 4;
+  const long long total = (long long)B * Wp * Wp * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i & 7);
+    const long long pix = i >> 3;
+    const int x = (int)(pix % Wp) - 2, y = (int)((pix / Wp) % Wp) - 2, b = (int)(pix / ((long long)Wp * Wp));
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (x >= 0 && x < Hi && y >= 0 && y < Hi) v = in[(((long long)b * Hi + y) * Hi + x) * 8 + c4];
+    padded[i] = v;
+  }
+}
+
+// w_flip[n, t * 32 + c] = Wt[n, 8 - t, c] for the two weight layouts (conv_implicit.cuh)
+__global__ void repack_flip_kernel(const float* __restrict__ W, int weights, float* __restrict__ w_flip) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 32 * 288) return;
+  const int n = i / 288, r = i - n * 288, t = r >> 5, c = r & 31;
+  const int tap = 8 - t;
+  w_flip[i] = weights == FC_CONV_DGRAD ? W[c * 288 + tap * 32 + n] : W[(tap * 32 + n) * 32 + c];
+}
+
+// out[b, y, x] = grid[b, y, x] (y, x < Ho) * (mask > 0)
+__global__ void compact_grid_kernel(const float4* __restrict__ grid, int B, int Wp, int Ho, const float4* __restrict__ mask,
+                                    float4* __restrict__ out) {
+  const long long total = (long long)B * Ho * Ho * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i & 7);
+    const long long pix = i >> 3;
+    const int x = (int)(pix % Ho), y = (int)((pix / Ho) % Ho), b = (int)(pix / ((long long)Ho * Ho));
+    float4 v = grid[(((long long)b * Wp + y) * Wp + x) * 8 + c4];
+    if (mask != nullptr) {
+      const float4 m = mask[i];
+      v = make_float4(m.x > 0.f ? v.x : 0.f, m.y > 0.f ? v.y : 0.f, m.z > 0.f ? v.z : 0.f, m.w > 0.f ? v.w : 0.f);
+    }
+    out[i] = v;
+  }
+}
+
+}  // namespace
+
+void full_correlation_3x3(GemmRunner& g, cudaStream_t s, int B, int Hi, const float* in, const float* W, int weights,
+                          const float* bias, int act, const float* mask, float* out, FullCorrScratch& sc) {
+  const int Wp = Hi + 4, Ho = Hi + 2;
+  const long long rows = (long long)B * Wp * Wp;
+  pad_grid_kernel<<<grid_for(rows * 8, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(in), B, Hi,
+                                                         reinterpret_cast<float4*>(sc.padded));
+  RLREP_LAUNCHED_W("pad_grid", s, 4.0 * 32 * ((double)B * Hi * Hi + rows), 0.0);
+  repack_flip_kernel<<<ceil_div(32 * 288, 256), 256, 0, s>>>(W, weights, sc.w_flip);
+  RLREP_LAUNCHED("repack_flip", s);
+  GemmArgs a;
+  a.M = (int)rows; a.N = 32; a.K = 288;
+  a.A = sc.padded; a.lda = 32; a.conv_w = Wp;
+  a.B = sc.w_flip; a.ldb = 288;
+  a.C = sc.out_grid; a.ldc = 32;
+  a.epi.bias = bias;
+  a.epi.act = act;
+  g.run(a, s);
+  compact_grid_kernel<<<grid_for((long long)B * Ho * Ho * 8, 256), 256, 0, s>>>(
+      reinterpret_cast<const float4*>(sc.out_grid), B, Wp, Ho, reinterpret_cast<const float4*>(mask),
+      reinterpret_cast<float4*>(out));
+  RLREP_LAUNCHED_W("compact_grid", s, 4.0 * 32 * ((double)B * Ho * Ho * (mask ? 3 : 2)), 0.0);
+}
+
+}  // namespace rlrep

@@ -10,6 +10,8 @@
 // gradient is a two-pass deterministic reduction.
 #include "deconv.cuh"
 
+#include <cstdlib>
+
 #include <algorithm>
 
 #include "reduce.cuh"
@@ -298,6 +300,8 @@ ConvDecoder::ConvDecoder(int batch, Precision prec, cudaStream_t s) : B_(batch),
   arena_.want(&wg_partial_, (size_t)kWgBlocks * 388);
   arena_.want(&bias_partial_, kBiasChunks * 32);
   arena_.want(&wfold_, (size_t)288 * kFold * 32 * kFold);
+  implicit_fwd_ = !(std::getenv("RLREP_CONV_V1") && std::atoi(std::getenv("RLREP_CONV_V1")) != 0);
+  if (implicit_fwd_) corr_.want(arena_, B_, hw_[2]);
   arena_.commit();
   gemm_.init(prec, 0);
 }
@@ -320,6 +324,11 @@ void ConvDecoder::forward(const float* x_dev, int ld_x) {
   RLREP_LAUNCHED_W("nchw_to_nhwc", s, 8.0 * B_ * P0 * 32, 0.0);
   for (int l = 0; l < 4; ++l) {
     const int Hi = hw_[l], Ho = hw_[l + 1];
+    if (implicit_fwd_ && l < 3) {  // stride 1: a full correlation, the taps walked by the GEMM's TMA producer
+      full_correlation_3x3(gemm_, s, B_, Hi, act_[l], g_.p + w_off_[l], FC_DECONV_FWD, g_.p + b_off_[l], ACT_RELU, nullptr,
+                           act_[l + 1], corr_);
+      continue;
+    }
     linear_fwd(gemm_, s, (int)rows(l), Mat{act_[l], 32}, layer(l), ACT_NONE, col_, 288);
     const float4* colT = reinterpret_cast<const float4*>(col_);
     const float4* bias = reinterpret_cast<const float4*>(g_.p + b_off_[l]);

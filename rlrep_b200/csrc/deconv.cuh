@@ -1,6 +1,7 @@
 // muLV-Rep pixel decoder handle (see deconv.cu).
 #pragma once
 #include "agent.cuh"
+#include "conv_implicit.cuh"
 
 namespace rlrep {
 
@@ -41,6 +42,8 @@ class ConvDecoder {
   static constexpr int kWgBlocks = 592;
   static constexpr int kFold = 4;  // rows folded per GEMM row in the weight-gradient GEMMs (deconv.cu backward())
   float* wfold_ = nullptr;
+  bool implicit_fwd_ = true;
+  FullCorrScratch corr_;
 };
 
 }  // namespace rlrep

@@ -27,6 +27,11 @@ struct GemmArgs {
   const float* A2 = nullptr;
   int lda2 = 0;
   int K1 = 0;
+  // Implicit 3x3 convolution over an NHWC matrix (K-major A only): conv_w > 0 makes A a [M, 32] matrix of pixels on a
+  // grid conv_w wide and k-block t (K = 9 * 32) reads rows m + (t / 3) * conv_w + (t % 3), i.e.
+  //   C[m, n] = sum_{ky, kx, c} A[m + ky * conv_w + kx, c] * B(n, (ky * 3 + kx) * 32 + c)
+  // with rows past M read as zero.  No column matrix is materialised: the TMA producer shifts its row coordinate.
+  int conv_w = 0;
   const float* B = nullptr;
   int ldb = 0;
   bool b_mn = false;

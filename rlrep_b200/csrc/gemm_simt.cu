@@ -23,6 +23,7 @@ constexpr int TBM = 64, TBN = 64, TBK = 16;
 
 struct SimtParams {
   int M, N, K, K1;
+  int conv_w;          // implicit 3x3 convolution over a K-major [M, 32] pixel matrix (gemm.cuh); 0 = plain GEMM
   const float* A;
   long long sam, sak;  // A(m,k) = A[m*sam + k*sak]
   const float* A2;
@@ -78,9 +79,15 @@ __global__ void __launch_bounds__(256) gemm_tiled_kernel(const SimtParams p, con
 #pragma unroll
     for (int i = 0; i < PER; ++i) {
       const int m = m0 + a_mm[i], k = k0 + a_kk[i];
-      const bool ok = m < p.M && k < p.K;
+      bool ok = m < p.M && k < p.K;
       const bool seg2 = p.A2 != nullptr && k >= p.K1;
       const float* src = seg2 ? p.A2 + (long long)m * p.sam2 + (k - p.K1) : p.A + (long long)m * p.sam + (long long)k * p.sak;
+      if (p.conv_w > 0) {
+        const int t = k >> 5;
+        const long long row = (long long)m + (t / 3) * p.conv_w + (t % 3);
+        ok = ok && row < p.M;
+        src = p.A + row * p.sam + (k & 31);
+      }
       ra[i] = ok ? __ldg(ok ? src : p.A) : 0.f;
     }
 #pragma unroll
@@ -207,7 +214,9 @@ void launch_simt(const GemmArgs& a, cudaStream_t stream) {
   RLREP_CHECK(a.M > 0 && a.N > 0 && a.K > 0, "empty GEMM");
   RLREP_CHECK(a.A2 == nullptr || !a.a_mn, "two-segment A requires a K-major A");
   SimtParams p;
+  RLREP_CHECK(a.conv_w == 0 || (!a.a_mn && a.A2 == nullptr && a.K == 9 * 32), "implicit convolution needs a K-major [M, 32] A");
   p.M = a.M; p.N = a.N; p.K = a.K; p.K1 = a.A2 ? a.K1 : a.K;
+  p.conv_w = a.conv_w;
   p.A = a.A;
   p.sam = a.a_mn ? 1 : a.lda;
   p.sak = a.a_mn ? a.lda : 1;
@@ -220,7 +229,7 @@ void launch_simt(const GemmArgs& a, cudaStream_t stream) {
   p.scm = a.ldc;
   p.scn = 1;
   const bool plain_epi = a.epi.pre_out == nullptr;  // pre_out uses (m, n) addressing the skinny kernels do not remap
-  if (a.A2 == nullptr && plain_epi && a.N <= 32 && !a.a_mn && a.K >= 64) {
+  if (a.A2 == nullptr && plain_epi && a.N <= 32 && !a.a_mn && a.K >= 64 && a.conv_w == 0) {
     launch_rowwarp(p, a.epi, stream);
     return;
   }

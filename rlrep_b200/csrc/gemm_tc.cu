@@ -154,6 +154,7 @@ bool tc_eligible(const GemmArgs& a) {
   // reaches past the last row of the matrix.
   if (a.a_mn && (a.M & 31) != 0) return false;
   if (a.b_mn && (a.N & 31) != 0) return false;
+  if (a.conv_w > 0 && (a.a_mn || a.K != 9 * 32)) return false;
   return a.A2 == nullptr && ok(a.A, a.lda) && ok(a.B, a.ldb) && a.M > 0 && a.N > 0 && a.K > 0;
 }
 
@@ -202,10 +203,12 @@ TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* /*ws*/, s
       return e ? std::atoi(e) : 0;
     }();
     const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, p.bn);
-    p.persistent = persist_on && p.split_k == 1 && tiles >= 2 * kNumSMs;
+    p.persistent = persist_on && p.split_k == 1 && tiles >= 2 * kNumSMs && a.conv_w == 0;
   }
   // K-major operand: matrix [rows = M|N, cols = K]; MN-major: matrix [rows = K, cols = M|N].
-  p.tmA = a.a_mn ? make_map_mnmajor(a.A, a.K, a.M, a.lda, BM) : make_map_kmajor(a.A, a.M, a.K, a.lda, BM);
+  // implicit convolution: A is the [M, 32] pixel matrix itself (rows past M zero-fill), not an [M, 288] column matrix
+  p.tmA = a.a_mn ? make_map_mnmajor(a.A, a.K, a.M, a.lda, BM)
+                 : make_map_kmajor(a.A, a.M, a.conv_w > 0 ? 32 : a.K, a.lda, BM);
   p.tmB = a.b_mn ? make_map_mnmajor(a.B, a.K, a.N, a.ldb, p.bn) : make_map_kmajor(a.B, a.N, a.K, a.ldb, p.bn);
   return p;
 }

@@ -291,7 +291,7 @@ __device__ __forceinline__ bool store_tile(const TileStore& t, const Epilogue* e
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 float* __restrict__ C, int ldc, int M, int N, int K, int kb_per_split, int stages, int push,
+                 float* __restrict__ C, int ldc, int M, int N, int K, int kb_per_split, int stages, int push, int conv_w,
                  const Epilogue epi) {
   // `stages` is a launch parameter: short K-slices run with a shallow ring so that two CTAs (of this or of a
   // concurrent GEMM on another stream) fit on one SM; long ones get the deepest ring that fits.
@@ -335,8 +335,14 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint8_t* a_dst = sA + s * A_BYTES;
     uint8_t* b_dst = sB + s * B_BYTES;
     // MN-major operands: one 3-D box {32 (m % 32), 32 (k), rows / 32 (m / 32)} lands as consecutive 4 KB sub-boxes
-    if (!A_MN) ptx::tma_load_2d(a_dst, &tmA, &full_bar[s], k0, m0);
-    else ptx::tma_load_3d(a_dst, &tmA, &full_bar[s], 0, k0, m0 / 32);
+    // implicit convolution (conv_w > 0): k-block t is tap (t / 3, t % 3) -- the same 32 channels, rows shifted on the grid
+    if (!A_MN) {
+      const int t = kb_begin + it;
+      if (conv_w > 0) ptx::tma_load_2d(a_dst, &tmA, &full_bar[s], 0, m0 + (t / 3) * conv_w + (t % 3));
+      else ptx::tma_load_2d(a_dst, &tmA, &full_bar[s], k0, m0);
+    } else {
+      ptx::tma_load_3d(a_dst, &tmA, &full_bar[s], 0, k0, m0 / 32);
+    }
     if (!B_MN) ptx::tma_load_2d(b_dst, &tmB, &full_bar[s], k0, n0);
     else ptx::tma_load_3d(b_dst, &tmB, &full_bar[s], 0, k0, n0 / 32);
   };
@@ -678,9 +684,11 @@ void launch_variant(const TcGemmPlan& p, cudaStream_t stream) {
   fill_launch_config<BN, A_MN, B_MN>(cfg, attr, dim3(ceil_div(a.N, BN), ceil_div(a.M, BM), p.split_k), p.split_k,
                                      p.stages, p.push, stream);
   RLREP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, A_MN, B_MN>, p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, a.K,
-                                p.kb_per_split, p.stages, p.push ? 1 : 0, a.epi));
+                                p.kb_per_split, p.stages, p.push ? 1 : 0, a.conv_w, a.epi));
   g_trace_reader = &read_trace_here;
-  RLREP_LAUNCHED_W("gemm_tf32", stream, 4.0 * ((double)a.M * a.K + (double)a.N * a.K + (double)a.M * a.N),
+  // implicit convolution: A is the [M, 32] pixel matrix, read once from HBM (the nine shifted re-reads hit L2)
+  RLREP_LAUNCHED_W("gemm_tf32", stream,
+                   4.0 * ((double)a.M * (a.conv_w > 0 ? 32 : a.K) + (double)a.N * a.K + (double)a.M * a.N),
                    2.0 * a.M * a.N * a.K);
 }
 
