@@ -195,7 +195,7 @@ void DrqV2::act(const unsigned char* obs_host, const float* eps_host, float stdd
   for (int j = 0; j < A_; ++j) eps_stage[j] = eps_host ? eps_host[j] : 0.f;
   RLREP_CUDA(cudaMemcpyAsync(img_dev_, stage_host_, one, cudaMemcpyHostToDevice, s));
   RLREP_CUDA(cudaMemcpyAsync(eps_dev_, eps_stage, A_ * sizeof(float), cudaMemcpyHostToDevice, s));
-  enc_->forward(img_dev_, nullptr, latent_);
+  enc_->forward(img_dev_, nullptr, latent_, 0, false, /*no_grad=*/true);
   const float saved_clip = cfg_.stddev_clip;
   cfg_.stddev_clip = INFINITY;  // clip=None
   actor_forward(latent_, eps_dev_, eps_host ? stddev : 0.f, 0, false);
@@ -272,7 +272,7 @@ void DrqV2::launch_update(float stddev) {
   launch_tick(ctl_, t, s);
 
   // ---- critic step (drqv2.py:112-133).  next_img first: its activations are not needed again, img's are.
-  enc_->forward(next_img_dev_, shifts_dev_ + 2 * B_, next_latent_);
+  enc_->forward(next_img_dev_, shifts_dev_ + 2 * B_, next_latent_, 0, false, /*no_grad=*/true);
   enc_->forward(img_dev_, shifts_dev_, latent_);
   actor_forward(next_latent_, eps_dev_, stddev, /*set=*/0, /*keep=*/false);
   trunk_forward(ct_, crit_g_, /*target=*/true, cln_w_, cln_b_, next_latent_, tpre_[0], cat_[0], LC_, nullptr, nullptr);

@@ -162,7 +162,8 @@ ConvEncoder::ConvEncoder(int batch, int in_channels, int height, Precision prec,
   gemm_.init(prec, 0);
 }
 
-void ConvEncoder::forward(const unsigned char* obs_dev, const int* shifts_dev, float* feat_dev, int ld_feat, bool target) {
+void ConvEncoder::forward(const unsigned char* obs_dev, const int* shifts_dev, float* feat_dev, int ld_feat, bool target,
+                          bool no_grad) {
   cudaStream_t s = stream_;
   RLREP_CHECK(!target || g_.n_target == g_.n, "this encoder has no target copy");
   im2col_u8_aug_kernel<<<grid_for((long long)rows(0) * 32, 256), 256, 0, s>>>(obs_dev, shifts_dev, B_, C_, H_, hw_[0],
@@ -170,6 +171,12 @@ void ConvEncoder::forward(const unsigned char* obs_dev, const int* shifts_dev, f
   RLREP_LAUNCHED_W("im2col_u8_aug", s, (double)B_ * C_ * H_ * H_ + 4.0 * rows(0) * ldk1_, 0.0);
   linear_fwd(gemm_, s, (int)rows(0), Mat{col_[0], ldk1_}, conv_[0].view(g_, target), ACT_RELU, act_[0], 32);
   for (int l = 1; l < 4; ++l) {
+    if ((target || no_grad) && implicit_dgrad_) {
+      // no backward pass follows (target / no-grad evaluation), so no column matrix is needed: implicit convolution
+      const Linear w = conv_[l].view(g_, target);
+      valid_conv_3x3(gemm_, s, B_, hw_[l - 1], act_[l - 1], w.W, w.ld, w.b, ACT_RELU, act_[l], corr_);
+      continue;
+    }
     im2col_nhwc32_kernel<<<grid_for((long long)rows(l) * 72, 256), 256, 0, s>>>(
         reinterpret_cast<const float4*>(act_[l - 1]), B_, hw_[l - 1], hw_[l], reinterpret_cast<float4*>(col_[l]));
     RLREP_LAUNCHED_W("im2col_nhwc32", s, 4.0 * (rows(l - 1) * 32 + rows(l) * 288), 0.0);

@@ -11,8 +11,10 @@ class ConvEncoder {
   ConvEncoder(int batch, int in_channels, int height, Precision prec, cudaStream_t s, bool with_target = false);
   // obs uint8 [B, C, H, H] (device), shifts int32 [B, 2] = (x, y) in [0, 8] or nullptr (no augmentation);
   // feat fp32 [B, 32 * 35 * 35] in the reference's flatten order (channel, row, column), row pitch ld_feat (0 = dense);
-  // target = true runs the target copy of the weights
-  void forward(const unsigned char* obs_dev, const int* shifts_dev, float* feat_dev, int ld_feat = 0, bool target = false);
+  // target = true runs the target copy of the weights; no_grad = true promises that no backward() follows this
+  // forward (layers 2-4 then run as implicit convolutions, without column matrices)
+  void forward(const unsigned char* obs_dev, const int* shifts_dev, float* feat_dev, int ld_feat = 0, bool target = false,
+               bool no_grad = false);
   // dfeat [B, 32 * 35 * 35] (row pitch ld_dfeat) -> dW / db of the four layers (activations of the last forward are reused)
   void backward(const float* dfeat_dev, int ld_dfeat = 0);
 

@@ -86,4 +86,20 @@ void full_correlation_3x3(GemmRunner& g, cudaStream_t s, int B, int Hi, const fl
   RLREP_LAUNCHED_W("compact_grid", s, 4.0 * 32 * ((double)B * Ho * Ho * (mask ? 3 : 2)), 0.0);
 }
 
+void valid_conv_3x3(GemmRunner& g, cudaStream_t s, int B, int Hi, const float* in, const float* W, int ldw,
+                    const float* bias, int act, float* out, FullCorrScratch& sc) {
+  const int Ho = Hi - 2;
+  GemmArgs a;
+  a.M = B * Hi * Hi; a.N = 32; a.K = 288;
+  a.A = in; a.lda = 32; a.conv_w = Hi;
+  a.B = W; a.ldb = ldw;
+  a.C = sc.out_grid; a.ldc = 32;
+  a.epi.bias = bias;
+  a.epi.act = act;
+  g.run(a, s);
+  compact_grid_kernel<<<grid_for((long long)B * Ho * Ho * 8, 256), 256, 0, s>>>(
+      reinterpret_cast<const float4*>(sc.out_grid), B, Hi, Ho, nullptr, reinterpret_cast<float4*>(out));
+  RLREP_LAUNCHED_W("compact_grid", s, 4.0 * 32 * ((double)B * Ho * Ho * 2), 0.0);
+}
+
 }  // namespace rlrep

@@ -27,4 +27,10 @@ enum FullCorrWeights : int {
 void full_correlation_3x3(GemmRunner& g, cudaStream_t s, int B, int Hi, const float* in, const float* W, int weights,
                           const float* bias, int act, const float* mask, float* out, FullCorrScratch& scratch);
 
+// Valid 3x3 convolution of a dense NHWC map without a column matrix: out[b, oy, ox, n] = act(bias[n] + sum_{ky, kx, c}
+// in[b, oy + ky, ox + kx, c] * W[n, (ky, kx), c]), in [B, Hi, Hi, 32], out [B, Hi - 2, Hi - 2, 32].  The GEMM runs on the
+// input's own grid (rows whose window crosses the border are computed and dropped by the compaction).
+void valid_conv_3x3(GemmRunner& g, cudaStream_t s, int B, int Hi, const float* in, const float* W, int ldw,
+                    const float* bias, int act, float* out, FullCorrScratch& scratch);
+
 }  // namespace rlrep
