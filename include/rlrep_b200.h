@@ -91,6 +91,9 @@ RLREP_EXPORT int rlrep_gemm_bench(void* stream, int path, int M, int N, int K, c
  * recent tcgen05 GEMM at: 0 entry, 1 setup done, 2 first operands landed, 3 last MMA issued, 4 accumulator complete,
  * 5 staged to shared, 6 cluster/CTA sync passed, 7 stores issued, 8 exit. */
 RLREP_EXPORT int rlrep_gemm_trace(unsigned long long* out16_host);
+/* Debug aid: device buffer of 80 uint64 into which CTA 0 of the persistent GEMM variant stamps %globaltimer for its first
+ * 16 tiles (role * 16 + tile; roles: TMA issued, operands landed, accumulator committed, epilogue start, epilogue end). */
+RLREP_EXPORT int rlrep_gemm_set_debug_buffer(unsigned long long* dev80);
 
 /* ------------------------------------------------------------------------------------------------
  * Replay ring -- replaces utils/buffer.py:13-48 (ReplayBuffer.__init__ / add / sample).

@@ -103,6 +103,7 @@ def _declare(lib: C.CDLL) -> None:
         "rlrep_drq_update_resident": [vp, i, C.c_float, C.POINTER(C.c_float)],
         "rlrep_drq_profile_update": [vp, C.c_float, i, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_double),
                                      C.POINTER(C.c_double), C.POINTER(i)],
+        "rlrep_gemm_set_debug_buffer": [vp],
         "rlrep_mulv_create": [vp, vp, C.POINTER(vp)],
         "rlrep_mulv_destroy": [vp],
         "rlrep_mulv_num_tensors": [vp, C.POINTER(i)],

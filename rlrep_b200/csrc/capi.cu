@@ -180,6 +180,11 @@ int rlrep_gemm_bench(void* stream, int path, int M, int N, int K, const float* A
   RLREP_API_END
 }
 
+int rlrep_gemm_set_debug_buffer(unsigned long long* dev80) {
+  RLREP_API_BEGIN
+  set_gemm_debug_buffer(dev80);
+  RLREP_API_END
+}
 int rlrep_gemm_trace(unsigned long long* out16_host) {
   RLREP_API_BEGIN
   RLREP_CUDA(cudaDeviceSynchronize());

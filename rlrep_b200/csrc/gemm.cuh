@@ -61,6 +61,8 @@ TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* ws, size_
 void launch_tc(const TcGemmPlan& p, cudaStream_t stream);
 // Debug builds (-DRLREP_GEMM_TRACE): %globaltimer stamps of CTA (0,0,0) of the last tcgen05 GEMM.
 void read_gemm_trace(unsigned long long* out16);
+// Debug aid: device buffer of 80 uint64 the persistent kernel's CTA 0 stamps its first 16 tiles into (nullptr = off).
+void set_gemm_debug_buffer(unsigned long long* dev80);
 
 // ---- CUDA-core path (exact FP32 FFMA; small-K / small-N layers and the strict-fp32 mode) ----
 void launch_simt(const GemmArgs& a, cudaStream_t stream);

@@ -15,6 +15,7 @@ namespace rlrep {
 
 namespace tc {
 void (*g_trace_reader)(unsigned long long*) = nullptr;
+unsigned long long* g_persist_dbg = nullptr;
 }
 
 namespace {
@@ -143,6 +144,8 @@ double plan_cost(const GemmArgs& a, int nkb, int bn, int s, double sm_share, int
 
 }  // namespace
 
+void set_gemm_debug_buffer(unsigned long long* dev80) { tc::g_persist_dbg = dev80; }
+
 void read_gemm_trace(unsigned long long* out16) {
   RLREP_CHECK(tc::g_trace_reader != nullptr, "no tcgen05 GEMM has been launched yet");
   tc::g_trace_reader(out16);
@@ -193,17 +196,20 @@ TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* /*ws*/, s
     p.push = false;
   }
   {
-    // Opt-in (RLREP_TC_PERSIST=1): the persistent variant is correct (the GEMM / conv / DrQ parity tests pass with
-    // it) but not yet faster (round 1: DrQ-v2 7.5 vs 5.5 ms/update, 2048x16384x2048 350-370 vs 325-345 us): with one
-    // CTA per SM there is a single TMA -> MMA -> epilogue pipeline per SM, while the one-tile-per-CTA kernel keeps two
-    // or three co-resident CTAs per SM overlapping each other's latencies.  Next step: two MMA/epilogue pipelines per
-    // CTA (or 2 CTAs per SM with half-depth rings).
-    static const int persist_on = [] {
+    // Persistent variant (one CTA per SM walks the tiles, double-buffered TMEM accumulator): used for the conv-shaped
+    // GEMMs -- thousands of narrow tiles with a handful of k-blocks each -- where one tile per CTA pays the whole
+    // setup -> TMA -> MMA -> epilogue latency for almost no work (measured at M = 430k: K=288, N=32 150 -> 87 us, now
+    // L2-bandwidth bound; K=32, N=288 570 -> 309 us).  Wide tiles keep the one-tile-per-CTA kernel: two or three
+    // co-resident CTAs overlap each other there, and the persistent epilogue (1.3 us per 128 x 32 chunk) would dominate.
+    // RLREP_TC_PERSIST=0 disables it, =1 forces it for every GEMM with at least two waves of tiles.
+    static const int persist_mode = [] {
       const char* e = std::getenv("RLREP_TC_PERSIST");
-      return e ? std::atoi(e) : 0;
+      return e ? std::atoi(e) : -1;
     }();
     const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, p.bn);
-    p.persistent = persist_on && p.split_k == 1 && tiles >= 2 * kNumSMs && a.conv_w == 0;
+    if (persist_mode == 0) p.persistent = false;
+    else if (persist_mode > 0) p.persistent = p.split_k == 1 && tiles >= 2 * kNumSMs;
+    else p.persistent = p.split_k == 1 && p.bn <= 64 && tiles >= 4 * kNumSMs && nkb <= 16;
   }
   // K-major operand: matrix [rows = M|N, cols = K]; MN-major: matrix [rows = K, cols = M|N].
   // implicit convolution: A is the [M, 32] pixel matrix itself (rows past M zero-fill), not an [M, 288] column matrix

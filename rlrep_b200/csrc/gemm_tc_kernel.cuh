@@ -80,6 +80,10 @@ RLREP_TC_DECL(128, 0) RLREP_TC_DECL(128, 1) RLREP_TC_DECL(256, 0) RLREP_TC_DECL(
 // through the reader the last launch registered (rlrep_gemm_trace).
 __device__ unsigned long long g_gemm_trace[16];
 extern void (*g_trace_reader)(unsigned long long*);
+// Debug aid for the persistent kernel: when set (rlrep_gemm_set_debug_buffer), CTA 0 stamps %globaltimer for its first 16
+// tiles into dbg[role * 16 + tile], role = 0 TMA issued, 1 first operands landed, 2 accumulator committed, 3 epilogue
+// sees the accumulator, 4 epilogue done.
+extern unsigned long long* g_persist_dbg;
 static void read_trace_here(unsigned long long* out16) {
   RLREP_CUDA(cudaMemcpyFromSymbol(out16, g_gemm_trace, sizeof(unsigned long long) * 16));
 }
@@ -474,6 +478,28 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (threadIdx.x == 64) trace(8);
 }
 
+// 32 x 32 chunk of the persistent kernel's epilogue: rows come out of the warp's transpose buffer, lanes cover four rows x
+// eight 16-byte pieces per store instruction.
+template <int ACT, int DACT>
+__device__ __forceinline__ void persist_store_rows(const Epilogue& epi, const float* tw, float* __restrict__ C, int ldc,
+                                                   int M, int m_base, int gn0, int lane) {
+  const int piece = lane & 7, rsub = lane >> 3;
+#pragma unroll
+  for (int r4 = 0; r4 < 8; ++r4) {
+    const int r = r4 * 4 + rsub;
+    const int om = m_base + r, on = gn0 + 4 * piece;
+    if (om < M) {
+      const float4 a4 = *reinterpret_cast<const float4*>(tw + r * 36 + 4 * piece);
+      float* cp = C + (size_t)om * ldc + on;
+      const float in[4] = {a4.x, a4.y, a4.z, a4.w};
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = epilogue_apply<ACT, DACT>(epi, in[e], om, on + e, cp + e);
+      *reinterpret_cast<float4*>(cp) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ persistent variant
 // For GEMMs with many output tiles and no split-K (the conv lowering: 3,000+ tiles of 3..9 k-blocks; the batch-sharded
 // contrastive logits: 1,024 tiles): one CTA per SM walks the tiles, so barrier setup / TMEM allocation happen once, the
@@ -487,8 +513,16 @@ constexpr int kPersistThreads = 192;
 template <int BN, bool A_MN, bool B_MN>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                            float* __restrict__ C, int ldc, int M, int N, int K, const Epilogue epi) {
+                            float* __restrict__ C, int ldc, int M, int N, int K, int conv_w, const Epilogue epi,
+                            unsigned long long* __restrict__ dbg) {
   constexpr int STAGES = num_stages(BN);
+  auto stamp = [&](int role, int tile) {
+    if (dbg != nullptr && blockIdx.x == 0 && tile < 16) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)::"memory");
+      dbg[role * 16 + tile] = t;
+    }
+  };
   constexpr int A_BYTES = BM * BK * 4;
   constexpr int B_BYTES = BN * BK * 4;
   constexpr uint32_t TMEM_COLS = 2 * BN < 32 ? 32 : 2 * BN;
@@ -534,16 +568,21 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer: the ring runs across tile boundaries
     if (lane == 0) {
-      int it = 0;
-      for (int t = blockIdx.x; t < total; t += gridDim.x) {
+      int it = 0, tcp = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++tcp) {
         const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;  // m fastest: concurrent CTAs share the B tile in L2
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES;
           ptx::mbar_wait(&empty_bar[s], ((it / STAGES) & 1) ^ 1);  // fresh barrier: parity 1 passes immediately
+          if (kb == 0) stamp(0, tcp);
           ptx::mbar_arrive_expect_tx(&full_bar[s], A_BYTES + B_BYTES);
           const int k0 = kb * BK;
-          if (!A_MN) ptx::tma_load_2d(sA + s * A_BYTES, &tmA, &full_bar[s], k0, m0);
-          else ptx::tma_load_3d(sA + s * A_BYTES, &tmA, &full_bar[s], 0, k0, m0 / 32);
+          if (!A_MN) {
+            if (conv_w > 0) ptx::tma_load_2d(sA + s * A_BYTES, &tmA, &full_bar[s], 0, m0 + (kb / 3) * conv_w + (kb % 3));
+            else ptx::tma_load_2d(sA + s * A_BYTES, &tmA, &full_bar[s], k0, m0);
+          } else {
+            ptx::tma_load_3d(sA + s * A_BYTES, &tmA, &full_bar[s], 0, k0, m0 / 32);
+          }
           if (!B_MN) ptx::tma_load_2d(sB + s * B_BYTES, &tmB, &full_bar[s], k0, n0);
           else ptx::tma_load_3d(sB + s * B_BYTES, &tmB, &full_bar[s], 0, k0, n0 / 32);
         }
@@ -562,6 +601,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         for (int kb = 0; kb < nkb; ++kb, ++it) {
           const int s = it % STAGES;
           ptx::mbar_wait(&full_bar[s], (it / STAGES) & 1);
+          if (kb == 0) stamp(1, tc);
           ptx::tc_fence_after_sync();
           const uint32_t a_addr = ptx::smem_u32(sA + s * A_BYTES);
           const uint32_t b_addr = ptx::smem_u32(sB + s * B_BYTES);
@@ -576,6 +616,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
           ptx::mma_commit(&empty_bar[s]);
         }
         ptx::mma_commit(&acc_full[acc]);
+        stamp(2, tc);
       }
     }
   } else {
@@ -588,6 +629,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       const int acc = tc & 1;
       const int m0 = (t % tiles_m) * BM, n0 = (t / tiles_m) * BN;
       ptx::mbar_wait(&acc_full[acc], (tc >> 1) & 1);
+      if (threadIdx.x == 64) stamp(3, tc);
       ptx::tc_fence_after_sync();
       const int gm = m0 + 32 * q + lane;
 #pragma unroll 1
@@ -605,21 +647,11 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                 make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                             __uint_as_float(v[4 * j + 3]));
           __syncwarp();
-          const int piece = lane & 7, rsub = lane >> 3;
-#pragma unroll
-          for (int r4 = 0; r4 < 8; ++r4) {
-            const int r = r4 * 4 + rsub;
-            const int om = m0 + 32 * q + r, on = gn0 + 4 * piece;
-            if (om < M) {
-              const float4 a4 = *reinterpret_cast<const float4*>(tw + r * 36 + 4 * piece);
-              float* cp = C + (size_t)om * ldc + on;
-              const float in[4] = {a4.x, a4.y, a4.z, a4.w};
-              float o[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) o[e] = epilogue_apply<-1, -1>(epi, in[e], om, on + e, cp + e);
-              *reinterpret_cast<float4*>(cp) = make_float4(o[0], o[1], o[2], o[3]);
-            }
-          }
+          // compile-time (activation, derivative) pairs: the run-time version drags every transcendental into an
+          // unrolled 32-element body that no longer fits the instruction cache (measured 5.6 us per 128 x 32 tile)
+#define RLREP_PSTORE(A, D) persist_store_rows<A, D>(epi, tw, C, ldc, M, m0 + 32 * q, gn0, lane)
+          RLREP_EPILOGUE_SWITCH(epi, RLREP_PSTORE);
+#undef RLREP_PSTORE
           __syncwarp();
         } else if (gm < M && gn0 < N) {
           float* crow = C + (size_t)gm * ldc + gn0;
@@ -630,6 +662,7 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
       ptx::tc_fence_before_sync();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);
+      if (threadIdx.x == 64) stamp(4, tc);
     }
   }
   ptx::tc_fence_before_sync();
@@ -647,8 +680,9 @@ void launch_variant_persistent(const TcGemmPlan& p, cudaStream_t stream) {
   }
   const GemmArgs& a = p.args;
   const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN);
-  kern<<<std::min(tiles, kNumSMs), kPersistThreads, smem_bytes(BN) + 4 * 32 * 36 * 4, stream>>>(p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, a.K, a.epi);
-  RLREP_LAUNCHED_W("gemm_tf32_persistent", stream, 4.0 * ((double)a.M * a.K + (double)a.N * a.K + (double)a.M * a.N),
+  kern<<<std::min(tiles, kNumSMs), kPersistThreads, smem_bytes(BN) + 4 * 32 * 36 * 4, stream>>>(p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, a.K, a.conv_w, a.epi, g_persist_dbg);
+  RLREP_LAUNCHED_W("gemm_tf32_persistent", stream,
+                   4.0 * ((double)a.M * (a.conv_w > 0 ? 32 : a.K) + (double)a.N * a.K + (double)a.M * a.N),
                    2.0 * a.M * a.N * a.K);
 }
 
