@@ -286,6 +286,10 @@ RLREP_EXPORT int rlrep_mulv_update(rlrep_mulv* h, const unsigned char* img, cons
                                    const float* discount, const unsigned char* next_img, const unsigned char* img_step1,
                                    const int* shifts, const float* eps_z, const float* eps_act, const float* noise,
                                    float stddev, float* metrics_host);
+/* act (drqv2.py:270-282): obs uint8 [C, 84, 84]; eps_host == NULL -> dist.mean (eval_mode), else
+ * TruncatedNormal.sample(clip=None) with eps[action_dim] ~ N(0, 1).  Not to be interleaved with rlrep_mulv_update. */
+RLREP_EXPORT int rlrep_mulv_act(rlrep_mulv* h, const unsigned char* obs_host, const float* eps_host, float stddev,
+                                float* action_host);
 RLREP_EXPORT int rlrep_mulv_update_resident(rlrep_mulv* h, int n_steps, float stddev, float* total_ms);
 RLREP_EXPORT int rlrep_mulv_profile_update(rlrep_mulv* h, float stddev, int max_entries, const char** names, float* ms,
                                            double* bytes, double* flops, int* n_entries);

@@ -145,6 +145,17 @@ class OracleMuLVDrQ:
     def _target(self, prefix):
         return {TARGETS[prefix] + k[len(prefix):]: v for k, v in self.tgt.items() if k.startswith(prefix)}
 
+    def act(self, obs, step, eval_mode, num_expl_steps=2000):  # drqv2.py:270-282
+        with torch.no_grad():
+            state = conv_encoder(self.p, "encoder", torch.as_tensor(obs).unsqueeze(0))
+            mu = actor_dist(self.p, state)
+            if eval_mode:
+                return mu.numpy()[0]
+            action = trunc_sample(mu, self.sched(step), None)
+            if step < num_expl_steps:
+                action.uniform_(-1.0, 1.0)
+            return action.numpy()[0]
+
     def update(self, batch: PixelBatch, step):  # drqv2.py:313-461
         if step % self.up_every != 0:
             return {}

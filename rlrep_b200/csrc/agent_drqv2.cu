@@ -15,6 +15,7 @@
 #include "agent.cuh"
 #include "conv.cuh"
 #include "drq.cuh"
+#include "staging.cuh"
 
 namespace rlrep {
 
@@ -237,11 +238,7 @@ void DrqV2::update(const unsigned char* img, const float* action, const float* r
   // ---- stage the step's inputs through one pinned buffer (H2D inside the step, like the reference's .to(device))
   RLREP_CUDA(cudaStreamSynchronize(s));
   unsigned char* st = stage_host_;
-  auto put = [&](void* dev, const void* src, size_t bytes) {
-    std::memcpy(st, src, bytes);
-    RLREP_CUDA(cudaMemcpyAsync(dev, st, bytes, cudaMemcpyHostToDevice, s));
-    st += bytes;
-  };
+  auto put = [&](void* dev, const void* src, size_t bytes) { stage_h2d(st, dev, src, bytes, s); };
   put(img_dev_, img, img_bytes);
   put(next_img_dev_, next_img, img_bytes);
   put(shifts_dev_, shifts, (size_t)4 * B_ * sizeof(int));

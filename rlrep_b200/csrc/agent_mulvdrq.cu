@@ -17,6 +17,8 @@
 // (state | action | state1): feat_encoder reads all of it, feat_f and the actor trunk read its leading columns.
 #include "mulv.cuh"
 
+#include "staging.cuh"
+
 #include <algorithm>
 #include <cmath>
 #include <cstring>
@@ -171,7 +173,7 @@ MulvDrq::MulvDrq(const MulvConfig& c, cudaStream_t s)
   stage_bytes_ = 2 * img_bytes + step1_bytes + (size_t)4 * B_ * sizeof(int) +
                  ((size_t)B_ * D_ + (size_t)2 * B_ * A_ + (size_t)3 * NN_ * D_ + (size_t)B_ * A_ + 2 * B_) * sizeof(float);
   RLREP_CUDA(cudaMallocHost(&stage_host_, stage_bytes_));
-  RLREP_CUDA(cudaMallocHost(&metrics_host_, 8 * sizeof(float)));
+  RLREP_CUDA(cudaMallocHost(&metrics_host_, (size_t)std::max(8, A_) * sizeof(float)));
   Control h;
   std::memset(&h, 0, sizeof(h));
   RLREP_CUDA(cudaMemcpyAsync(ctl_, &h, sizeof(h), cudaMemcpyHostToDevice, stream_));
@@ -284,6 +286,26 @@ void MulvDrq::actor_forward(const float* latent, int ld_latent, const float* eps
   launch_trunc_normal_sample(raw_a_, LA_, B_, A_, eps, stddev, cfg_.stddev_clip, mu_, action_out, ld_action, s);
 }
 
+// encoder (no augmentation) -> actor -> mean, or TruncatedNormal.sample(clip=None) with the caller's standard-normal draw
+void MulvDrq::act(const unsigned char* obs_host, const float* eps_host, float stddev, float* action_host) {
+  cudaStream_t s = stream_;
+  const size_t one = (size_t)cfg_.channels * cfg_.height * cfg_.height;
+  RLREP_CUDA(cudaStreamSynchronize(s));
+  std::memcpy(stage_host_, obs_host, one);
+  float* eps_stage = reinterpret_cast<float*>(stage_host_ + ((one + 15) & ~size_t(15)));
+  for (int j = 0; j < A_; ++j) eps_stage[j] = eps_host ? eps_host[j] : 0.f;
+  RLREP_CUDA(cudaMemcpyAsync(img_dev_, stage_host_, one, cudaMemcpyHostToDevice, s));
+  RLREP_CUDA(cudaMemcpyAsync(eps_act_dev_, eps_stage, A_ * sizeof(float), cudaMemcpyHostToDevice, s));
+  enc_->forward(img_dev_, nullptr, enc_in_, LDE_, false, /*no_grad=*/true);
+  const float saved_clip = cfg_.stddev_clip;
+  cfg_.stddev_clip = INFINITY;  // clip=None
+  actor_forward(enc_in_, LDE_, eps_act_dev_, eps_host ? stddev : 0.f, daction_, LA_, false);
+  cfg_.stddev_clip = saved_clip;
+  RLREP_CUDA(cudaMemcpyAsync(metrics_host_, daction_, A_ * sizeof(float), cudaMemcpyDeviceToHost, s));
+  RLREP_CUDA(cudaStreamSynchronize(s));
+  std::memcpy(action_host, metrics_host_, A_ * sizeof(float));
+}
+
 float MulvDrq::update_resident(int n_steps, float stddev) {
   RLREP_CHECK(n_steps > 0, "bad step count");
   cudaEvent_t e0, e1;
@@ -316,11 +338,7 @@ void MulvDrq::update(const unsigned char* img, const float* action, const float*
   const size_t step1_bytes = (size_t)B_ * 3 * cfg_.height * cfg_.height;
   RLREP_CUDA(cudaStreamSynchronize(s));
   unsigned char* st = stage_host_;
-  auto put = [&](void* dev, const void* src, size_t bytes) {
-    std::memcpy(st, src, bytes);
-    RLREP_CUDA(cudaMemcpyAsync(dev, st, bytes, cudaMemcpyHostToDevice, s));
-    st += bytes;
-  };
+  auto put = [&](void* dev, const void* src, size_t bytes) { stage_h2d(st, dev, src, bytes, s); };
   put(img_dev_, img, img_bytes);
   put(next_img_dev_, next_img, img_bytes);
   put(step1_dev_, img_step1, step1_bytes);

@@ -564,6 +564,12 @@ int rlrep_mulv_update(rlrep_mulv* h, const unsigned char* img, const float* acti
   h->impl->update(img, action, reward, discount, next_img, img_step1, shifts, eps_z, eps_act, noise, stddev, metrics_host);
   RLREP_API_END
 }
+int rlrep_mulv_act(rlrep_mulv* h, const unsigned char* obs_host, const float* eps_host, float stddev, float* action_host) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(h && obs_host && action_host, "null argument");
+  h->impl->act(obs_host, eps_host, stddev, action_host);
+  RLREP_API_END
+}
 int rlrep_mulv_update_resident(rlrep_mulv* h, int n_steps, float stddev, float* total_ms) {
   RLREP_API_BEGIN
   RLREP_CHECK(h && total_ms, "null argument");

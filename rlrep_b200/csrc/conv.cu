@@ -22,15 +22,14 @@ namespace {
 constexpr int kPad = 4;  // RandomShiftsAug(pad=4)
 
 __global__ void im2col_u8_aug_kernel(const unsigned char* __restrict__ obs, const int* __restrict__ shifts, int B, int C,
-                                     int H, int Ho, float* __restrict__ col, int ldk) {
-  // one warp per output pixel (the row decomposition is warp-uniform), lanes over k = c * 9 + ky * 3 + kx -- the
-  // reference's weight layout [32, C, 3, 3] flattened; 128-byte coalesced stores, byte loads served by L1 / L2
-  const int K = C * 9;
-  const long long rows = (long long)B * Ho * Ho;
-  const int lane = threadIdx.x & 31;
-  const long long warp0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = ((long long)gridDim.x * blockDim.x) >> 5;
-  for (long long row = warp0; row < rows; row += nwarps) {
+                                     int H, int Ho, float4* __restrict__ col, int ldk) {
+  // one thread per (output pixel, four consecutive k), k = c * 9 + ky * 3 + kx -- the reference's weight layout
+  // [32, C, 3, 3] flattened; 16-byte stores, consecutive threads on consecutive pieces of a row; byte loads served by L1
+  const int K = C * 9, q4 = ldk >> 2;
+  const long long total = (long long)B * Ho * Ho * q4;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % q4);
+    const long long row = i / q4;
     const int ox = (int)(row % Ho), oy = (int)((row / Ho) % Ho), b = (int)(row / ((long long)Ho * Ho));
     int sx = 0, sy = 0;
     if (shifts != nullptr) {  // padded[i + sy, j + sx] with replicate padding == clamp(i + sy - pad)
@@ -38,17 +37,19 @@ __global__ void im2col_u8_aug_kernel(const unsigned char* __restrict__ obs, cons
       sy = shifts[2 * b + 1] - kPad;
     }
     const unsigned char* img = obs + (long long)b * C * H * H;
-    float* out = col + row * ldk;
-    for (int k = lane; k < ldk; k += 32) {
-      float v = 0.f;
+    float v[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = 4 * q + e;
+      v[e] = 0.f;
       if (k < K) {
         const int c = k / 9, r9 = k - 9 * c, ky = r9 / 3, kx = r9 - 3 * ky;
         const int iy = min(max(2 * oy + ky + sy, 0), H - 1), ix = min(max(2 * ox + kx + sx, 0), H - 1);
         const float p = (float)img[((long long)c * H + iy) * H + ix];
-        v = __fsub_rn(__fdiv_rn(p, 255.0f), 0.5f);  // obs / 255.0 - 0.5, op by op like torch
+        v[e] = __fsub_rn(__fdiv_rn(p, 255.0f), 0.5f);  // obs / 255.0 - 0.5, op by op like torch
       }
-      out[k] = v;
     }
+    col[i] = make_float4(v[0], v[1], v[2], v[3]);
   }
 }
 
@@ -166,8 +167,8 @@ void ConvEncoder::forward(const unsigned char* obs_dev, const int* shifts_dev, f
                           bool no_grad) {
   cudaStream_t s = stream_;
   RLREP_CHECK(!target || g_.n_target == g_.n, "this encoder has no target copy");
-  im2col_u8_aug_kernel<<<grid_for((long long)rows(0) * 32, 256), 256, 0, s>>>(obs_dev, shifts_dev, B_, C_, H_, hw_[0],
-                                                                             col_[0], ldk1_);
+  im2col_u8_aug_kernel<<<grid_for((long long)rows(0) * (ldk1_ / 4), 256), 256, 0, s>>>(
+      obs_dev, shifts_dev, B_, C_, H_, hw_[0], reinterpret_cast<float4*>(col_[0]), ldk1_);
   RLREP_LAUNCHED_W("im2col_u8_aug", s, (double)B_ * C_ * H_ * H_ + 4.0 * rows(0) * ldk1_, 0.0);
   linear_fwd(gemm_, s, (int)rows(0), Mat{col_[0], ldk1_}, conv_[0].view(g_, target), ACT_RELU, act_[0], 32);
   for (int l = 1; l < 4; ++l) {

@@ -42,6 +42,9 @@ class MulvDrq {
   void update(const unsigned char* img, const float* action, const float* reward, const float* discount,
               const unsigned char* next_img, const unsigned char* img_step1, const int* shifts, const float* eps_z,
               const float* eps_act, const float* noise, float stddev, float* metrics_out);
+  // act (drqv2.py:270-282): obs uint8 [C, H, H]; eps [A] standard normal or nullptr (eval_mode: the mean); action [A].
+  // Runs the batch-sized kernels with the observation in row 0; not to be interleaved with update().
+  void act(const unsigned char* obs_host, const float* eps_host, float stddev, float* action_host);
   float update_resident(int n_steps, float stddev);
   std::vector<ProfileEntry> profile_update(float stddev);
   void sync_targets_from_params();

@@ -461,6 +461,26 @@ class MuLVDrQv2:
         return (shifts.to(torch.int32).numpy(), eps_z.numpy(), torch.stack([e0, e1]).numpy(),
                 torch.stack([n0, n1, n2]).numpy())
 
+    def act(self, obs, step, eval_mode):
+        """drqv2.py:270-282.  `obs` is one uint8 frame stack [C, H, W]; the handle must exist (`prepare(batch_size)` or one
+        `update`).  Exploration (`step < num_expl_steps`, not eval_mode) replaces the sample by U(-1, 1) after drawing it,
+        like the reference."""
+        if self._h is None:
+            raise _lib.RlrepError("call prepare(batch_size) or update once before act")
+        o = np.ascontiguousarray(torch.as_tensor(obs).cpu().numpy())
+        assert o.dtype == np.uint8 and tuple(o.shape) == self.obs_shape
+        stddev = float(self.stddev_schedule(step))
+        eps = None
+        if not eval_mode:  # TruncatedNormal.sample(clip=None): one _standard_normal([1, A]) draw
+            z = torch.zeros(1, self.action_dim)
+            eps = np.ascontiguousarray(torch.normal(z, torch.ones_like(z)).numpy().reshape(-1))
+        out = np.empty(self.action_dim, dtype=np.float32)
+        _lib.check(self.lib.rlrep_mulv_act(self._h, o.ctypes.data, eps.ctypes.data if eps is not None else None, stddev,
+                                           out.ctypes.data))
+        if not eval_mode and step < int(_cfg_get(self.cfg, "num_expl_steps", 2000)):
+            out = torch.empty(self.action_dim).uniform_(-1.0, 1.0).numpy()
+        return out
+
     def update(self, replay_iter, step):
         if step % self.up_every != 0:
             return {}

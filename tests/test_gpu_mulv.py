@@ -87,3 +87,23 @@ def test_mulv_update_matches_oracle(C, A, F, H, B, precision):
     assert max(after.values()) < tol["after"], after
     assert pworst2[0] < 2 * tol["param"], pworst2
     agent.close()
+
+
+def test_mulv_act_matches_oracle():
+    from oracle import mulv_oracle as M
+    from rlrep_b200.pixel import MuLVDrQv2
+    C, A, F, H, B = 9, 4, 100, 64, 4
+    init = M.init_state(C, A, F, H, seed=0)
+    oracle = M.OracleMuLVDrQ(A, init)
+    agent = MuLVDrQv2((C, 84, 84), (A,), _cfg(F, H), precision="fp32")
+    agent.load_state_dict(init)
+    agent.prepare(B)
+    obs = M.synthetic_pixel_batch(1, C, 84, A, seed=3).img[0]
+    assert np.allclose(agent.act(obs, 1000, True), oracle.act(obs, 1000, True), atol=2e-5)
+    for step in (250000, 100):  # past / inside the exploration phase (uniform actions replace the sample)
+        torch.manual_seed(4)
+        a_c = agent.act(obs, step, False)
+        torch.manual_seed(4)
+        a_o = oracle.act(obs, step, False)
+        assert np.allclose(a_c, a_o, atol=2e-5), (step, a_c, a_o)
+    agent.close()
