@@ -125,3 +125,40 @@ def test_drqv2_draw_consumes_the_generator_like_the_reference():
     want = torch.stack([D.draw_shift(B).reshape(B, 2) for _ in range(2)]).to(torch.int32).numpy()
     assert np.array_equal(shifts, want)
     assert agent.stddev_schedule(250000) == pytest.approx(0.55)
+
+
+def test_mulvdrq_host_logic():
+    """muLV-Rep DrQ-v2 shim without a device: RNG consumption of one update equals the oracle's (which is pinned to the
+    real reference class, tests/golden/mulvdrq_b4.npz), `up_every` gating draws nothing, unsupported configuration
+    switches raise, weight layouts round-trip through the pending state_dict, and the first device call raises without
+    CUDA (no CPU fallback)."""
+    from oracle import mulv_oracle as M
+    from rlrep_b200 import RlrepError
+    from rlrep_b200.pixel import MuLVDrQv2
+    C_, A, F, H, B = 3, 4, 20, 32, 2
+    cfg = dict(feat_dim=F, hid_dim=H, up_every=2)
+    agent = MuLVDrQv2((C_, 84, 84), (A,), cfg)  # lazy: no device needed until the first update
+    oracle = M.OracleMuLVDrQ(A, M.init_state(C_, A, F, H, seed=0))
+    batch = M.synthetic_pixel_batch(B, C_, 84, A, seed=0)
+    torch.manual_seed(7)
+    assert oracle.update(batch, 0) != {}
+    after = torch.get_rng_state().clone()
+    assert oracle.update(batch, 1) == {} and torch.equal(torch.get_rng_state(), after)
+    torch.manual_seed(7)
+    shifts, eps_z, eps_act, noise = agent._draw(B)
+    assert torch.equal(torch.get_rng_state(), after)
+    assert shifts.shape == (2, B, 2) and eps_z.shape == (B, F) and eps_act.shape == (2, B, A) and noise.shape == (3, 20, F)
+    assert agent.update(iter([]), step=1) == {}  # odd step: returns before touching the iterator or the device
+    with pytest.raises(NotImplementedError):
+        MuLVDrQv2((C_, 84, 84), (A,), dict(cfg, q_loss="mse"))
+    with pytest.raises(NotImplementedError):
+        MuLVDrQv2((C_, 84, 84), (A,), dict(cfg, pre_aug=True))
+    sd = M.init_state(C_, A, F, H, seed=1)
+    agent.load_state_dict(sd)  # kept pending until the handle exists
+    assert set(agent.state_dict()) == set(sd)
+    assert agent._kind("decoder.deconvnet.2.weight") == "deconv" and agent._kind("decoder.deconvnet.8.weight") == "outconv"
+    assert agent._kind("feat_f_target.log_std_linear.1.weight") == "vec" and agent._kind("critic.l1.weight") == "mat"
+    assert agent._ref_shape("predict_encoder.convnet.0.weight", 32, 27) == (32, 3, 3, 3)
+    if not torch.cuda.is_available():
+        with pytest.raises(RlrepError):
+            agent.update(iter([tuple(batch)]), step=0)
