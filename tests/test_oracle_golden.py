@@ -10,9 +10,10 @@ import torch
 from oracle import rl_oracle as O
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
-CASES = sorted(p.stem for p in GOLDEN.glob("*.npz") if not p.stem.startswith(("drqv2", "mulvdrq")))
+CASES = sorted(p.stem for p in GOLDEN.glob("*.npz") if not p.stem.startswith(("drqv2", "mulvdrq", "ldiffsr")))
 DRQ_CASES = sorted(p.stem for p in GOLDEN.glob("drqv2*.npz"))
 MULV_CASES = sorted(p.stem for p in GOLDEN.glob("mulvdrq*.npz"))
+LDIFFSR_CASES = sorted(p.stem for p in GOLDEN.glob("ldiffsr*.npz"))
 
 
 def test_fixtures_present():
@@ -20,6 +21,7 @@ def test_fixtures_present():
             "diffsrsac_hc_b64"} <= set(CASES)
     assert {"drqv2_b8", "drqv2_b16_c3"} <= set(DRQ_CASES)
     assert {"mulvdrq_b4"} <= set(MULV_CASES)
+    assert {"ldiffsr_b4"} <= set(LDIFFSR_CASES)
 
 
 @pytest.mark.parametrize("name", CASES)
@@ -114,6 +116,34 @@ def test_mulvdrq_oracle_reproduces_reference(name):
         for k in w:
             assert abs(g[k] - w[k]) <= 2e-6 + 2e-5 * abs(w[k]), (step, k, g[k], w[k])
     assert oracle.update(batches[0], step=1) == {}  # up_every = 2: odd steps are no-ops and draw nothing
+    sd = oracle.state_dict()
+    for k in meta["keys"]:
+        t = sd[k].detach().double().flatten()
+        stats, sample = z["stats/" + k], z["sample/" + k]
+        stride = max(1, t.numel() // 256)
+        assert abs(t.norm().item() - stats[1]) <= 1e-5 * max(stats[1], 1e-6), k
+        assert np.linalg.norm(t[::stride][:256].numpy() - sample) <= 2e-5 * max(np.linalg.norm(sample), 1e-6) + 1e-7, k
+
+
+@pytest.mark.parametrize("name", LDIFFSR_CASES)
+def test_ldiffsr_oracle_reproduces_reference(name):
+    """Latent Diff-SR DrQ-v2 pixel update (agent/diffsrdrq/latent_diff_sr.py:306-390): oracle/ldiffsr_oracle.py against
+    the fixture produced by the real reference class (oracle/make_golden_ldiffsr.py; bit-identical at generation time,
+    dropout masks included).  Groundwork for SURVEY 8a row a17, second half (no CUDA path yet)."""
+    from oracle import ldiffsr_oracle as O
+    z = np.load(GOLDEN / f"{name}.npz")
+    meta = json.loads(bytes(z["meta_json"]).decode())
+    infos = json.loads(bytes(z["infos_json"]).decode())
+    d, B, n = O.Dims(*meta["dims"]), meta["batch"], meta["n"]
+    oracle = O.OracleLatentDiffSR(d, O.init_state(d, seed=0))
+    batches = [O.synthetic_pixel_batch(B, 9, 84, d.A, seed=40 + i) for i in range(n)]
+    torch.manual_seed(1)
+    got = [oracle.train_step(b, step=1000 * i) for i, b in enumerate(batches)]
+    assert [bool(g) for g in got] == [bool(w) for w in infos] == [True, False, True, False]
+    for step, (g, w) in enumerate(zip(got, infos)):
+        assert set(g) == set(w)
+        for k in w:
+            assert abs(g[k] - w[k]) <= 2e-6 + 2e-5 * abs(w[k]), (step, k, g[k], w[k])
     sd = oracle.state_dict()
     for k in meta["keys"]:
         t = sd[k].detach().double().flatten()
