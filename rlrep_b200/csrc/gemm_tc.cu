@@ -200,7 +200,8 @@ TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* /*ws*/, s
     // GEMMs -- thousands of narrow tiles with a handful of k-blocks each -- where one tile per CTA pays the whole
     // setup -> TMA -> MMA -> epilogue latency for almost no work (measured at M = 430k: K=288, N=32 150 -> 87 us, now
     // L2-bandwidth bound; K=32, N=288 570 -> 309 us).  Wide tiles keep the one-tile-per-CTA kernel: two or three
-    // co-resident CTAs overlap each other there, and the persistent epilogue (1.3 us per 128 x 32 chunk) would dominate.
+    // co-resident CTAs overlap each other there, and the persistent epilogue (1.3 us per 128 x 32 chunk) would dominate
+    // -- except for one- or two-k-block GEMMs (the stride-2 transposed conv's K = 32), where any tile width wins.
     // RLREP_TC_PERSIST=0 disables it, =1 forces it for every GEMM with at least two waves of tiles.
     static const int persist_mode = [] {
       const char* e = std::getenv("RLREP_TC_PERSIST");
@@ -209,7 +210,7 @@ TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* /*ws*/, s
     const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, p.bn);
     if (persist_mode == 0) p.persistent = false;
     else if (persist_mode > 0) p.persistent = p.split_k == 1 && tiles >= 2 * kNumSMs;
-    else p.persistent = p.split_k == 1 && p.bn <= 64 && tiles >= 4 * kNumSMs && nkb <= 16;
+    else p.persistent = p.split_k == 1 && tiles >= 4 * kNumSMs && ((p.bn <= 64 && nkb <= 16) || nkb <= 2);
   }
   // K-major operand: matrix [rows = M|N, cols = K]; MN-major: matrix [rows = K, cols = M|N].
   // implicit convolution: A is the [M, 32] pixel matrix itself (rows past M zero-fill), not an [M, 288] column matrix
