@@ -162,3 +162,53 @@ def test_mulvdrq_host_logic():
     if not torch.cuda.is_available():
         with pytest.raises(RlrepError):
             agent.update(iter([tuple(batch)]), step=0)
+
+
+def _shifted_row_gemm(A, Wk, conv_w):
+    """CPU model of GemmArgs::conv_w (gemm.cuh): C[m, n] = sum_{t < 9, c < 32} A[m + (t // 3) * conv_w + t % 3, c] *
+    Wk[n, t * 32 + c], rows past the end of A read as zero -- what the TMA producer's shifted row coordinate computes."""
+    M = A.shape[0]
+    Apad = torch.cat([A, torch.zeros(2 * conv_w + 2, A.shape[1], dtype=A.dtype)])
+    out = torch.zeros(M, Wk.shape[0], dtype=A.dtype)
+    for t in range(9):
+        s = (t // 3) * conv_w + t % 3
+        out += Apad[s:s + M] @ Wk[:, t * 32:(t + 1) * 32].T
+    return out
+
+
+def test_implicit_convolution_algebra():
+    """The index algebra behind conv_implicit.cu, checked in float64 against torch's own operators:
+    (1) valid 3x3 convolution = shifted-row GEMM on the input's own grid + compaction of the top-left (H-2)^2 block;
+    (2) full correlation (the data gradient of that convolution, and a stride-1 ConvTranspose2d forward) = the same
+        GEMM on a grid zero-padded by 2 with the taps flipped (t -> 8 - t) + compaction of the top-left (H+2)^2 block,
+        for both weight layouts the kernels repack from (FC_CONV_DGRAD, FC_DECONV_FWD)."""
+    import torch.nn.functional as F
+    torch.manual_seed(0)
+    B, H = 2, 7
+    x = torch.randn(B, 32, H, H, dtype=torch.float64)
+    w = torch.randn(32, 32, 3, 3, dtype=torch.float64)  # conv weight [co, ci, ky, kx]
+    nhwc = lambda t: t.permute(0, 2, 3, 1).reshape(-1, t.shape[1])  # [B*H*W, C]
+    # (1) stored conv weight [co, (ky, kx, ci)]
+    wk = w.permute(0, 2, 3, 1).reshape(32, 288)
+    grid = _shifted_row_gemm(nhwc(x), wk, H).reshape(B, H, H, 32)[:, :H - 2, :H - 2]
+    assert torch.allclose(grid.permute(0, 3, 1, 2), F.conv2d(x, w), atol=1e-10)
+    # (2a) data gradient of the convolution: dX = full correlation of dY with W; repack [ci, (8 - t) -> t, co]
+    dy = torch.randn(B, 32, H, H, dtype=torch.float64)
+    want = F.conv_transpose2d(dy, w)  # == conv2d's input gradient for stride 1, no padding
+    Wp = H + 4
+    padded = F.pad(dy, (2, 2, 2, 2))
+    flip = torch.empty(32, 288, dtype=torch.float64)
+    for t in range(9):
+        tap = 8 - t
+        flip[:, t * 32:(t + 1) * 32] = wk[:, tap * 32:(tap + 1) * 32].T  # w_flip[ci, t*32 + co] = W[co, tap*32 + ci]
+    grid = _shifted_row_gemm(nhwc(padded), flip, Wp).reshape(B, Wp, Wp, 32)[:, :H + 2, :H + 2]
+    assert torch.allclose(grid.permute(0, 3, 1, 2), want, atol=1e-10)
+    # (2b) ConvTranspose2d forward with the decoder's stored layout Wd[(ky, kx, co), ci] = W_ref[ci, co, ky, kx]
+    wt = torch.randn(32, 32, 3, 3, dtype=torch.float64)  # reference layout [ci, co, ky, kx]
+    wd = wt.permute(2, 3, 1, 0).reshape(288, 32)
+    flip2 = torch.empty(32, 288, dtype=torch.float64)
+    for t in range(9):
+        tap = 8 - t
+        flip2[:, t * 32:(t + 1) * 32] = wd[tap * 32:(tap + 1) * 32, :]  # w_flip[co, t*32 + ci] = Wd[tap*32 + co, ci]
+    grid = _shifted_row_gemm(nhwc(F.pad(x, (2, 2, 2, 2))), flip2, Wp).reshape(B, Wp, Wp, 32)[:, :H + 2, :H + 2]
+    assert torch.allclose(grid.permute(0, 3, 1, 2), F.conv_transpose2d(x, wt), atol=1e-10)
