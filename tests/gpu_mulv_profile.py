@@ -1,5 +1,5 @@
 """Per-launch profile of one muLV-Rep DrQ-v2 update at full size: prints every launch above 40 us with its algorithmic
-flops / bytes (2MNK identifies a GEMM's shape) and the per-kernel totals.  python scripts/gpu_mulv_profile.py [B] [H]"""
+flops / bytes (2MNK identifies a GEMM's shape) and the per-kernel totals.  python tests/gpu_mulv_profile.py [B] [H]"""
 import ctypes as C
 import sys
 from pathlib import Path
