@@ -295,6 +295,46 @@ RLREP_EXPORT int rlrep_mulv_profile_update(rlrep_mulv* h, float stddev, int max_
                                            double* bytes, double* flops, int* n_entries);
 RLREP_EXPORT int rlrep_mulv_last_launches(rlrep_mulv* h, int* launches);
 
+/* ------------------------------------------------------------------------------------------------
+ * DRAFT (branch draft/ldiffsr-agent, not verified on hardware): latent Diff-SR DrQ-v2 pixel agent -- replaces
+ * `LatentDiffSRDrQv2(obs_space, action_space, args)` and the updating half of `train_step(replay_iter, step)`
+ * (agent/diffsrdrq/latent_diff_sr.py:13-139, :306-390) on configs/latent_diff_sr.yaml's path.  The caller keeps `_step` /
+ * `update_every`, evaluates the std-dev schedule and draws ALL randomness in the reference's order on the CPU generator
+ * (shift draws, posterior noise, diffusion levels and noise, the dropout masks of the online score network, the action
+ * normals); see rlrep_b200/pixel.py:LatentDiffSRDrQv2._draw.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rlrep_ldiff rlrep_ldiff;
+typedef struct rlrep_ldiff_config {
+  int batch_size, action_dim, latent_dim, feature_dim, bn_dim, psi_hidden_dim, psi_hidden_depth, zeta_hidden_dim,
+      zeta_hidden_depth, hidden_dim;
+  double ae_lr, score_lr, actor_lr, critic_lr, weight_decay;
+  float tau, kl_coef, ae_coef, stddev_clip;
+  int precision;
+} rlrep_ldiff_config;
+typedef struct rlrep_ldiff_inputs { /* host pointers; N = 4 * batch frames, L = latent_dim */
+  const unsigned char* frames;      /* [N, 3, 84, 84]: the 3B frames of img_stack, then the B newest next frames */
+  const unsigned char* next_frames; /* [3B, 3, 84, 84] */
+  const int* shifts;                /* [N, 2] per-frame shift; (4, 4) = no augmentation */
+  const int* next_shifts;           /* [3B, 2] */
+  const float *action, *reward, *discount;
+  const float* eps_post;            /* [N, L] */
+  const float *alphabar, *temb, *noise; /* [B], [B, L/2], [B, L] */
+  const float* psi_masks;           /* [psi_depth][2B, psi_hidden]: rows [0, B) score step, [B, 2B) critic step */
+  const float* zeta_masks;          /* [zeta_depth][B, zeta_hidden] */
+  const float* eps_act;             /* [2][B][A] */
+  float stddev;
+} rlrep_ldiff_inputs;
+RLREP_EXPORT int rlrep_ldiff_create(const rlrep_ldiff_config* cfg, void* stream, rlrep_ldiff** out);
+RLREP_EXPORT int rlrep_ldiff_destroy(rlrep_ldiff* h);
+RLREP_EXPORT int rlrep_ldiff_num_tensors(rlrep_ldiff* h, int* n);
+RLREP_EXPORT int rlrep_ldiff_tensor_info(rlrep_ldiff* h, int i, const char** name, float** ptr_dev, int* rows, int* cols);
+RLREP_EXPORT int rlrep_ldiff_tensor_read(rlrep_ldiff* h, int i, float* out_host);
+RLREP_EXPORT int rlrep_ldiff_tensor_write(rlrep_ldiff* h, int i, const float* in_host);
+RLREP_EXPORT int rlrep_ldiff_sync_targets(rlrep_ldiff* h);
+/* metrics_host[8] = {recon_loss, kl_loss, score_loss, critic_loss, mean(q_pred), mean(q_target), mean(reward), actor_loss} */
+RLREP_EXPORT int rlrep_ldiff_update(rlrep_ldiff* h, const rlrep_ldiff_inputs* in, float* metrics_host);
+RLREP_EXPORT int rlrep_ldiff_last_launches(rlrep_ldiff* h, int* launches);
+
 /* Kernels launched by the most recent train() (a graph replay counts the kernels it contains). */
 RLREP_EXPORT int rlrep_agent_last_launches(rlrep_agent* agent, int* launches);
 

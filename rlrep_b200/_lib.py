@@ -104,6 +104,15 @@ def _declare(lib: C.CDLL) -> None:
         "rlrep_drq_profile_update": [vp, C.c_float, i, C.POINTER(C.c_char_p), C.POINTER(C.c_float), C.POINTER(C.c_double),
                                      C.POINTER(C.c_double), C.POINTER(i)],
         "rlrep_gemm_set_debug_buffer": [vp],
+        "rlrep_ldiff_create": [vp, vp, C.POINTER(vp)],
+        "rlrep_ldiff_destroy": [vp],
+        "rlrep_ldiff_num_tensors": [vp, C.POINTER(i)],
+        "rlrep_ldiff_tensor_info": [vp, i, C.POINTER(C.c_char_p), C.POINTER(vp), C.POINTER(i), C.POINTER(i)],
+        "rlrep_ldiff_tensor_read": [vp, i, vp],
+        "rlrep_ldiff_tensor_write": [vp, i, vp],
+        "rlrep_ldiff_sync_targets": [vp],
+        "rlrep_ldiff_update": [vp, vp, vp],
+        "rlrep_ldiff_last_launches": [vp, C.POINTER(i)],
         "rlrep_mulv_create": [vp, vp, C.POINTER(vp)],
         "rlrep_mulv_destroy": [vp],
         "rlrep_mulv_num_tensors": [vp, C.POINTER(i)],

@@ -191,6 +191,9 @@ class Ring {
   int off_a, off_r, off_d, off_s2;
   long long capacity, size = 0, ptr = 0;
   float* data = nullptr;  // [capacity, R]
+  // Unique per Ring object for the life of the process: captured graphs bake `data` in, and a new ring can be allocated
+  // at the address of a destroyed one, so agents key their graph on this id rather than on the object's address.
+  const unsigned long long generation;
 
   // rows_host: n packed records (already laid out [n, R]); written at ptr.. with wrap-around.
   void add_packed(const float* rows_host, int n, cudaStream_t s);

@@ -37,10 +37,7 @@ class SacBase : public Agent {
     RLREP_CHECK(n_metrics >= (int)metric_names().size(), "metrics buffer too small");
     for (int i = 0; i < n_idx; ++i)
       RLREP_CHECK(!is_replay_index(i) || (idx_host[i] >= 0 && idx_host[i] < ring.size), "replay index out of range");
-    if (ring_bound_ != &ring) {  // graphs bake the ring pointer in
-      graph_.reset();
-      ring_bound_ = &ring;
-    }
+    bind_ring(ring);
     RLREP_CUDA(cudaStreamSynchronize(stream));  // pinned staging is reused across calls
     std::memcpy(idx_host_, idx_host, (size_t)n_idx * sizeof(long long));
     std::memcpy(eps_host_, eps_host, (size_t)n_eps * sizeof(float));
@@ -59,10 +56,7 @@ class SacBase : public Agent {
   float train_resident(Ring& ring, const long long* idx_host, const float* eps_host, int n_steps) override {
     const int ni = idx_per_train(), ne = eps_per_train();
     RLREP_CHECK(ring.S == S_ && ring.A == A_ && n_steps > 0, "bad arguments");
-    if (ring_bound_ != &ring) {
-      graph_.reset();
-      ring_bound_ = &ring;
-    }
+    bind_ring(ring);
     long long* idx_all = nullptr;
     float* eps_all = nullptr;
     RLREP_CUDA(cudaMalloc(&idx_all, (size_t)n_steps * ni * sizeof(long long)));
@@ -129,6 +123,14 @@ class SacBase : public Agent {
   }
 
  protected:
+  // Captured graphs bake ring.data into their gather nodes: a different ring (also one that happens to live at a freed
+  // ring's address) invalidates the graph.
+  void bind_ring(const Ring& ring) {
+    if (ring_bound_ != ring.generation) {
+      graph_.reset();
+      ring_bound_ = ring.generation;
+    }
+  }
   // One full train() worth of launches on `stream`, reading idx_dev_ / eps_dev_ and writing metrics_dev_.
   virtual void update(Ring& ring) = 0;
 
@@ -333,7 +335,7 @@ class SacBase : public Agent {
   DeviceArena arena_;
   GemmRunner gemm_;
   GraphReplay graph_;
-  Ring* ring_bound_ = nullptr;
+  unsigned long long ring_bound_ = 0;  // Ring::generation the captured graph was built against
   int launches_per_train_ = 0;
   ParamGroup actor_g_;
   LinearSlot a0_, a1_, a2_;

@@ -11,6 +11,7 @@
 #include "conv.cuh"
 #include "drq.cuh"
 #include "mulv.cuh"
+#include "ldiffsr.cuh"
 #include "gemm.cuh"
 #include "rlrep_b200.h"
 
@@ -592,6 +593,123 @@ int rlrep_mulv_profile_update(rlrep_mulv* h, float stddev, int max_entries, cons
   RLREP_API_END
 }
 int rlrep_mulv_last_launches(rlrep_mulv* h, int* launches) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(h && launches, "null argument");
+  *launches = h->impl->last_launches;
+  RLREP_API_END
+}
+
+// ------------------------------------------------------------------------------------------------ latent Diff-SR DrQ-v2 (DRAFT)
+struct rlrep_ldiff {
+  std::unique_ptr<LatentDiffSR> impl;
+  std::vector<TensorRef> tensors;
+  cudaStream_t owned_stream = nullptr;
+};
+
+int rlrep_ldiff_create(const rlrep_ldiff_config* c, void* stream, rlrep_ldiff** out) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(c != nullptr && out != nullptr, "null argument");
+  LdiffConfig d;
+  d.batch = c->batch_size; d.action_dim = c->action_dim; d.latent = c->latent_dim; d.feat = c->feature_dim; d.bn = c->bn_dim;
+  d.psi_h = c->psi_hidden_dim; d.psi_d = c->psi_hidden_depth; d.zeta_h = c->zeta_hidden_dim; d.zeta_d = c->zeta_hidden_depth;
+  d.hidden = c->hidden_dim; d.ae_lr = c->ae_lr; d.score_lr = c->score_lr; d.actor_lr = c->actor_lr; d.critic_lr = c->critic_lr;
+  d.weight_decay = c->weight_decay; d.tau = c->tau; d.kl_coef = c->kl_coef; d.ae_coef = c->ae_coef;
+  d.stddev_clip = c->stddev_clip; d.precision = c->precision;
+  std::unique_ptr<rlrep_ldiff> h(new rlrep_ldiff);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (st == nullptr) {
+    RLREP_CUDA(cudaStreamCreateWithFlags(&h->owned_stream, cudaStreamNonBlocking));
+    st = h->owned_stream;
+  }
+  h->impl.reset(new LatentDiffSR(d, st));
+  for (ParamGroup* g : h->impl->groups()) {
+    // the conv stacks name their tensors relative to the module ("convnet.0.weight" -> vae.encoder.convs.0.weight)
+    const bool enc = g->name == "vae.encoder", dec = g->name == "vae.decoder";
+    auto full = [&](const std::string& n, const std::string& prefix) {
+      if (enc) return prefix + "encoder.convs." + n.substr(std::string("convnet.").size());
+      if (dec) return prefix + "decoder.deconvs." + n.substr(std::string("deconvnet.").size());
+      return n;
+    };
+    for (const ParamTensor& t : g->tensors) h->tensors.push_back({full(t.name, "vae."), g->p + t.offset, t.rows, t.cols, t.ld});
+    if (g->g)
+      for (const ParamTensor& t : g->tensors)
+        h->tensors.push_back({"grad/" + full(t.name, "vae."), g->g + t.offset, t.rows, t.cols, t.ld});
+    if (g->target)
+      for (const ParamTensor& t : g->tensors) {
+        const std::string nm = (enc || dec) ? full(t.name, "vae_target.")
+                                            : g->target_prefix_to + t.name.substr(g->target_prefix_from.size());
+        h->tensors.push_back({nm, g->target + t.offset, t.rows, t.cols, t.ld});
+      }
+  }
+  *out = h.release();
+  RLREP_API_END
+}
+int rlrep_ldiff_destroy(rlrep_ldiff* h) {
+  RLREP_API_BEGIN
+  if (h) {
+    if (h->impl) cudaStreamSynchronize(h->impl->stream());
+    h->impl.reset();
+    if (h->owned_stream) cudaStreamDestroy(h->owned_stream);
+  }
+  delete h;
+  RLREP_API_END
+}
+int rlrep_ldiff_num_tensors(rlrep_ldiff* h, int* n) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(h && n, "null argument");
+  *n = (int)h->tensors.size();
+  RLREP_API_END
+}
+int rlrep_ldiff_tensor_info(rlrep_ldiff* h, int i, const char** name, float** ptr_dev, int* rows, int* cols) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(h && i >= 0 && i < (int)h->tensors.size(), "tensor index out of range");
+  const TensorRef& t = h->tensors[i];
+  if (name) *name = t.name.c_str();
+  if (ptr_dev) *ptr_dev = t.ptr;
+  if (rows) *rows = t.rows;
+  if (cols) *cols = t.cols;
+  RLREP_API_END
+}
+int rlrep_ldiff_tensor_read(rlrep_ldiff* h, int i, float* out_host) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(h && out_host && i >= 0 && i < (int)h->tensors.size(), "tensor index out of range");
+  const TensorRef& t = h->tensors[i];
+  cudaStream_t st = h->impl->stream();
+  RLREP_CUDA(cudaMemcpy2DAsync(out_host, (size_t)t.cols * 4, t.ptr, (size_t)t.ld * 4, (size_t)t.cols * 4, t.rows,
+                               cudaMemcpyDeviceToHost, st));
+  RLREP_CUDA(cudaStreamSynchronize(st));
+  RLREP_API_END
+}
+int rlrep_ldiff_tensor_write(rlrep_ldiff* h, int i, const float* in_host) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(h && in_host && i >= 0 && i < (int)h->tensors.size(), "tensor index out of range");
+  const TensorRef& t = h->tensors[i];
+  cudaStream_t st = h->impl->stream();
+  RLREP_CUDA(cudaMemcpy2DAsync(t.ptr, (size_t)t.ld * 4, in_host, (size_t)t.cols * 4, (size_t)t.cols * 4, t.rows,
+                               cudaMemcpyHostToDevice, st));
+  RLREP_CUDA(cudaStreamSynchronize(st));
+  RLREP_API_END
+}
+int rlrep_ldiff_sync_targets(rlrep_ldiff* h) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(h, "null argument");
+  h->impl->sync_targets_from_params();
+  RLREP_API_END
+}
+int rlrep_ldiff_update(rlrep_ldiff* h, const rlrep_ldiff_inputs* in, float* metrics_host) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(h && in && metrics_host, "null argument");
+  LatentDiffSR::Inputs x;
+  x.frames = in->frames; x.next_frames = in->next_frames; x.shifts = in->shifts; x.next_shifts = in->next_shifts;
+  x.action = in->action; x.reward = in->reward; x.discount = in->discount; x.eps_post = in->eps_post;
+  x.alphabar = in->alphabar; x.temb = in->temb; x.noise = in->noise; x.psi_masks = in->psi_masks;
+  x.zeta_masks = in->zeta_masks; x.eps_act = in->eps_act; x.stddev = in->stddev;
+  RLREP_CHECK(x.frames && x.next_frames && x.shifts && x.next_shifts && x.action && x.reward && x.discount && x.eps_post &&
+                  x.alphabar && x.temb && x.noise && x.psi_masks && x.zeta_masks && x.eps_act, "null input pointer");
+  h->impl->update(x, metrics_host);
+  RLREP_API_END
+}
+int rlrep_ldiff_last_launches(rlrep_ldiff* h, int* launches) {
   RLREP_API_BEGIN
   RLREP_CHECK(h && launches, "null argument");
   *launches = h->impl->last_launches;

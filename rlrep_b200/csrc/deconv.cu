@@ -93,13 +93,15 @@ __global__ void im2col_strided_kernel(const float4* __restrict__ dy, int B, int 
 // Output layer Conv2d(32 -> 3, kernel 2, padding 1) on X [B, 83, 83, 32]: eight lanes per output pixel (one float4 of
 // channels each, so a tap is one coalesced 128-byte row), shuffle-reduced; pred [B*84*84, 4] (channel 3 unused).
 // w_s[(tap*32 + c)*3 + o] = W[o, c, ky, kx] staged in shared memory.
+template <int KS>
 __global__ void __launch_bounds__(256) out_conv_fwd_kernel(const float4* __restrict__ x, const float* __restrict__ W,
                                                            const float* __restrict__ bias, int B, int Hi, int Ho,
                                                            float4* __restrict__ pred) {
-  __shared__ float w_s[4 * 32 * 3];
-  for (int i = threadIdx.x; i < 384; i += 256) {
+  constexpr int T = KS * KS;
+  __shared__ float w_s[T * 32 * 3];
+  for (int i = threadIdx.x; i < T * 96; i += 256) {
     const int o = i % 3, c = (i / 3) % 32, tap = i / 96;
-    w_s[i] = W[(o * 32 + c) * 4 + tap];
+    w_s[i] = W[(o * 32 + c) * T + tap];
   }
   __syncthreads();
   const float b0 = bias[0], b1 = bias[1], b2 = bias[2];
@@ -111,8 +113,8 @@ __global__ void __launch_bounds__(256) out_conv_fwd_kernel(const float4* __restr
     if (i < total) {
       const int ox = (int)(i % Ho), oy = (int)((i / Ho) % Ho), b = (int)(i / ((long long)Ho * Ho));
 #pragma unroll
-      for (int tap = 0; tap < 4; ++tap) {
-        const int iy = oy + (tap >> 1) - 1, ix = ox + (tap & 1) - 1;
+      for (int tap = 0; tap < T; ++tap) {
+        const int iy = oy + (tap / KS) - 1, ix = ox + (tap % KS) - 1;
         if (iy < 0 || iy >= Hi || ix < 0 || ix >= Hi) continue;
         const float4 v = x[(((long long)b * Hi + iy) * Hi + ix) * 8 + c4];
         const float* wc = w_s + tap * 96 + c4 * 12;
@@ -153,6 +155,40 @@ __global__ void __launch_bounds__(256) l1_loss_kernel(const float4* __restrict__
   acc = block_sum<256>(acc, scratch);
   if (threadIdx.x == 0) partial[blockIdx.x] = acc;
 }
+// Latent Diff-SR reconstruction loss (latent_diff_sr.py:242): sum((pred - target)^2) / n_frames with
+// target = frame / 255 - 0.5 and frame = the shift-augmented uint8 frame (replicate padding == clamped lookup; a null
+// shift table means no augmentation).  dpred = scale * 2 * diff; partial[block] = sum diff^2.
+__global__ void __launch_bounds__(256) mse_sum_loss_kernel(const float4* __restrict__ pred, const unsigned char* __restrict__ tgt,
+                                                           const int* __restrict__ shifts, int B, int Ho, float scale,
+                                                           float4* __restrict__ dpred, float* __restrict__ partial) {
+  __shared__ float scratch[33];
+  const long long P = (long long)Ho * Ho, total = (long long)B * P;
+  float acc = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long b = i / P, p = i - b * P;
+    int y = (int)(p / Ho), x = (int)(p - (long long)y * Ho);
+    if (shifts != nullptr) {
+      x = min(max(x + shifts[2 * b] - 4, 0), Ho - 1);
+      y = min(max(y + shifts[2 * b + 1] - 4, 0), Ho - 1);
+    }
+    const float4 v = pred[i];
+    const unsigned char* t = tgt + b * 3 * P + (long long)y * Ho + x;
+    const float d0 = v.x - __fsub_rn(__fdiv_rn((float)t[0], 255.0f), 0.5f);
+    const float d1 = v.y - __fsub_rn(__fdiv_rn((float)t[P], 255.0f), 0.5f);
+    const float d2 = v.z - __fsub_rn(__fdiv_rn((float)t[2 * P], 255.0f), 0.5f);
+    acc = fmaf(d0, d0, fmaf(d1, d1, fmaf(d2, d2, acc)));
+    dpred[i] = make_float4(2.f * scale * d0, 2.f * scale * d1, 2.f * scale * d2, 0.f);
+  }
+  acc = block_sum<256>(acc, scratch);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+__global__ void mse_sum_finalize_kernel(const float* __restrict__ partial, int n, float inv_frames, float* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  float s = 0.f;
+  for (int i = 0; i < n; ++i) s += partial[i];
+  out[0] = s * inv_frames;
+}
+
 // out[0] = 10 * sum(partial) / count  (fixed order)
 __global__ void l1_finalize_kernel(const float* __restrict__ partial, int n, float inv_count, float* __restrict__ out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
@@ -162,13 +198,15 @@ __global__ void l1_finalize_kernel(const float* __restrict__ partial, int n, flo
 }
 
 // dX[b, iy, ix, c] = relu'(X) * sum_{tap, o} dpred[b, iy - ky + 1, ix - kx + 1, o] * W[o, c, ky, kx]
+template <int KS>
 __global__ void __launch_bounds__(256) out_conv_dgrad_kernel(const float4* __restrict__ dpred, const float* __restrict__ W,
                                                              const float4* __restrict__ x, int B, int Hi, int Ho,
                                                              float4* __restrict__ dx) {
-  __shared__ float w_s[4 * 32 * 3];
-  for (int i = threadIdx.x; i < 384; i += 256) {
+  constexpr int T = KS * KS;
+  __shared__ float w_s[T * 32 * 3];
+  for (int i = threadIdx.x; i < T * 96; i += 256) {
     const int o = i % 3, c = (i / 3) % 32, tap = i / 96;
-    w_s[i] = W[(o * 32 + c) * 4 + tap];
+    w_s[i] = W[(o * 32 + c) * T + tap];
   }
   __syncthreads();
   const long long total = (long long)B * Hi * Hi * 8;
@@ -178,8 +216,8 @@ __global__ void __launch_bounds__(256) out_conv_dgrad_kernel(const float4* __res
     const int ix = (int)(pix % Hi), iy = (int)((pix / Hi) % Hi), b = (int)(pix / ((long long)Hi * Hi));
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
-    for (int tap = 0; tap < 4; ++tap) {
-      const int oy = iy - (tap >> 1) + 1, ox = ix - (tap & 1) + 1;
+    for (int tap = 0; tap < T; ++tap) {
+      const int oy = iy - (tap / KS) + 1, ox = ix - (tap % KS) + 1;
       if (oy < 0 || oy >= Ho || ox < 0 || ox >= Ho) continue;
       const float4 g = dpred[((long long)b * Ho + oy) * Ho + ox];
       const float* w = w_s + tap * 96 + c4 * 12;
@@ -195,31 +233,33 @@ __global__ void __launch_bounds__(256) out_conv_dgrad_kernel(const float4* __res
 // Pass 1 of dW[o, c, tap] = sum_pixels dpred[pix, o] * X[pix + tap - 1, c] and db[o] = sum dpred[pix, o]:
 // lane = input channel; each warp walks a CONTIGUOUS span of output pixels (the rows it touches stay in L1 from one
 // output row to the next); partial[block] = [12 * 32 weight sums | 3 bias sums | pad] (388 floats).
+template <int KS>
 __global__ void __launch_bounds__(256) out_conv_wgrad_kernel(const float4* __restrict__ dpred, const float* __restrict__ x,
                                                              int B, int Hi, int Ho, float* __restrict__ partial) {
-  __shared__ float red[8][12 * 32 + 4];
+  constexpr int T = KS * KS, NA = 3 * T, PS = NA * 32 + 4;  // accumulators per lane, partial stride
+  __shared__ float red[8][PS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const long long total = (long long)B * Ho * Ho;
   const long long nw = (long long)gridDim.x * 8, gw = (long long)blockIdx.x * 8 + warp;
   const long long span = (total + nw - 1) / nw;
   const long long p0 = gw * span, p1 = p0 + span < total ? p0 + span : total;
-  float acc[12];
+  float acc[NA];
 #pragma unroll
-  for (int j = 0; j < 12; ++j) acc[j] = 0.f;
+  for (int j = 0; j < NA; ++j) acc[j] = 0.f;
   float bsum = 0.f;
   int ox = (int)(p0 % Ho), oy = (int)((p0 / Ho) % Ho), b = (int)(p0 / ((long long)Ho * Ho));
   for (long long i = p0; i < p1; ++i) {
     const float4 g = dpred[i];
-    float v[4];
+    float v[T];
 #pragma unroll
-    for (int tap = 0; tap < 4; ++tap) {  // the four loads are independent: issued back to back
-      const int iy = oy + (tap >> 1) - 1, ix = ox + (tap & 1) - 1;
+    for (int tap = 0; tap < T; ++tap) {  // the loads are independent: issued back to back
+      const int iy = oy + (tap / KS) - 1, ix = ox + (tap % KS) - 1;
       const bool ok = iy >= 0 && iy < Hi && ix >= 0 && ix < Hi;
       v[tap] = ok ? x[(((long long)b * Hi + iy) * Hi + ix) * 32 + lane] : 0.f;
     }
     if (lane < 3) bsum += lane == 0 ? g.x : (lane == 1 ? g.y : g.z);
 #pragma unroll
-    for (int tap = 0; tap < 4; ++tap) {
+    for (int tap = 0; tap < T; ++tap) {
       acc[tap * 3 + 0] = fmaf(g.x, v[tap], acc[tap * 3 + 0]);
       acc[tap * 3 + 1] = fmaf(g.y, v[tap], acc[tap * 3 + 1]);
       acc[tap * 3 + 2] = fmaf(g.z, v[tap], acc[tap * 3 + 2]);
@@ -230,28 +270,30 @@ __global__ void __launch_bounds__(256) out_conv_wgrad_kernel(const float4* __res
     }
   }
 #pragma unroll
-  for (int j = 0; j < 12; ++j) red[warp][j * 32 + lane] = acc[j];
-  if (lane < 3) red[warp][384 + lane] = bsum;
+  for (int j = 0; j < NA; ++j) red[warp][j * 32 + lane] = acc[j];
+  if (lane < 3) red[warp][NA * 32 + lane] = bsum;
   __syncthreads();
-  for (int k = threadIdx.x; k < 387; k += 256) {
+  for (int k = threadIdx.x; k < NA * 32 + 3; k += 256) {
     float s = 0.f;
 #pragma unroll
     for (int w = 0; w < 8; ++w) s += red[w][k];
-    partial[(size_t)blockIdx.x * 388 + k] = s;
+    partial[(size_t)blockIdx.x * PS + k] = s;
   }
 }
 // Pass 2: dW[o, c, tap] (reference layout [3, 32, 2, 2]) and db[o] from the per-block partials, fixed order.
+template <int KS>
 __global__ void out_conv_wgrad_finish_kernel(const float* __restrict__ partial, int n_blocks, float* __restrict__ dW,
                                              float* __restrict__ db) {
+  constexpr int T = KS * KS, NA = 3 * T, PS = NA * 32 + 4;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= 387) return;
+  if (k >= NA * 32 + 3) return;
   float s = 0.f;
-  for (int i = 0; i < n_blocks; ++i) s += partial[(size_t)i * 388 + k];
-  if (k < 384) {
+  for (int i = 0; i < n_blocks; ++i) s += partial[(size_t)i * PS + k];
+  if (k < NA * 32) {
     const int j = k / 32, c = k % 32, tap = j / 3, o = j % 3;
-    dW[(o * 32 + c) * 4 + tap] = s;
+    dW[(o * 32 + c) * T + tap] = s;
   } else {
-    db[k - 384] = s;
+    db[k - NA * 32] = s;
   }
 }
 
@@ -279,15 +321,20 @@ __global__ void pred_to_nchw_kernel(const float4* __restrict__ pred, int B, long
 
 }  // namespace
 
-ConvDecoder::ConvDecoder(int batch, Precision prec, cudaStream_t s) : B_(batch), stream_(s) {
-  RLREP_CHECK(B_ > 0, "bad decoder batch");
+ConvDecoder::ConvDecoder(int batch, Precision prec, cudaStream_t s, int out_kernel, bool with_target)
+    : B_(batch), ks_(out_kernel), stream_(s) {
+  RLREP_CHECK(B_ > 0 && (ks_ == 2 || ks_ == 3), "bad decoder batch / output kernel size");
+  // out_kernel 2: muLV-Rep (stride-2 layer 41 -> 83, Conv2d k2 p1 -> 84); out_kernel 3: the latent Diff-SR VAE
+  // (stride-2 layer with output_padding 1: 41 -> 84, Conv2d k3 p1 -> 84)
+  if (ks_ == 3) hw_[4] = 84;
   g_.name = "decoder";
   for (int l = 0; l < 4; ++l) {  // stored [(ky, kx, co), ci]; exported as the reference's [ci, co, ky, kx]
     w_off_[l] = g_.add("deconvnet." + std::to_string(2 * l) + ".weight", 288, 32);
     b_off_[l] = g_.add("deconvnet." + std::to_string(2 * l) + ".bias", 32, 1);
   }
-  w_off_[4] = g_.add("deconvnet.8.weight", 3, 128);  // the reference's [3, 32, 2, 2] flattened
+  w_off_[4] = g_.add("deconvnet.8.weight", 3, 32 * ks_ * ks_);  // the reference's [3, 32, k, k] flattened
   b_off_[4] = g_.add("deconvnet.8.bias", 3, 1);
+  if (with_target) g_.n_target = g_.n;
   g_.want(arena_);
   for (int i = 0; i < 5; ++i) {
     arena_.want(&act_[i], rows(i) * 32);
@@ -297,7 +344,7 @@ ConvDecoder::ConvDecoder(int batch, Precision prec, cudaStream_t s) : B_(batch),
   arena_.want(&pred_, rows(5) * 4);
   arena_.want(&dpred_, rows(5) * 4);
   arena_.want(&loss_partial_, kLossBlocks);
-  arena_.want(&wg_partial_, (size_t)kWgBlocks * 388);
+  arena_.want(&wg_partial_, (size_t)kWgBlocks * (96 * ks_ * ks_ + 4));
   arena_.want(&bias_partial_, kBiasChunks * 32);
   arena_.want(&wfold_, (size_t)288 * kFold * 32 * kFold);
   implicit_fwd_ = !(std::getenv("RLREP_CONV_V1") && std::atoi(std::getenv("RLREP_CONV_V1")) != 0);
@@ -337,9 +384,14 @@ void ConvDecoder::forward(const float* x_dev, int ld_x) {
     else col2im_bias_relu_kernel<2><<<grid_for(rows(l + 1) * 8, 256), 256, 0, s>>>(colT, bias, B_, Hi, Ho, y);
     RLREP_LAUNCHED_W("col2im_bias_relu", s, 4.0 * (rows(l) * 288 + rows(l + 1) * 32), 0.0);
   }
-  out_conv_fwd_kernel<<<grid_for(rows(5) * 8, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(act_[4]), g_.p + w_off_[4],
-                                                            g_.p + b_off_[4], B_, hw_[4], hw_[5],
-                                                            reinterpret_cast<float4*>(pred_));
+  if (ks_ == 2)
+    out_conv_fwd_kernel<2><<<grid_for(rows(5) * 8, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(act_[4]),
+                                                                    g_.p + w_off_[4], g_.p + b_off_[4], B_, hw_[4], hw_[5],
+                                                                    reinterpret_cast<float4*>(pred_));
+  else
+    out_conv_fwd_kernel<3><<<grid_for(rows(5) * 8, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(act_[4]),
+                                                                    g_.p + w_off_[4], g_.p + b_off_[4], B_, hw_[4], hw_[5],
+                                                                    reinterpret_cast<float4*>(pred_));
   RLREP_LAUNCHED_W("out_conv_fwd", s, 4.0 * (rows(4) * 32 + rows(5) * 4), 2.0 * rows(5) * 384);
 }
 
@@ -353,17 +405,36 @@ void ConvDecoder::l1_loss(const unsigned char* target_dev, float grad_scale, flo
   RLREP_LAUNCHED("l1_finalize", s);
 }
 
+void ConvDecoder::mse_sum_loss(const unsigned char* target_dev, const int* shifts_dev, float grad_scale, float* loss_out_dev) {
+  cudaStream_t s = stream_;
+  mse_sum_loss_kernel<<<kLossBlocks, 256, 0, s>>>(reinterpret_cast<const float4*>(pred_), target_dev, shifts_dev, B_, hw_[5],
+                                                 grad_scale / (float)B_, reinterpret_cast<float4*>(dpred_), loss_partial_);
+  RLREP_LAUNCHED_W("mse_sum_loss", s, rows(5) * 35.0, 0.0);
+  mse_sum_finalize_kernel<<<1, 32, 0, s>>>(loss_partial_, kLossBlocks, 1.f / (float)B_, loss_out_dev);
+  RLREP_LAUNCHED("mse_sum_finalize", s);
+}
+
 void ConvDecoder::backward(float* dx_dev, int ld_dx) {
   cudaStream_t s = stream_;
   // ---- output layer
-  out_conv_wgrad_kernel<<<kWgBlocks, 256, 0, s>>>(reinterpret_cast<const float4*>(dpred_), act_[4], B_, hw_[4], hw_[5],
-                                                 wg_partial_);
+  if (ks_ == 2)
+    out_conv_wgrad_kernel<2><<<kWgBlocks, 256, 0, s>>>(reinterpret_cast<const float4*>(dpred_), act_[4], B_, hw_[4], hw_[5],
+                                                      wg_partial_);
+  else
+    out_conv_wgrad_kernel<3><<<kWgBlocks, 256, 0, s>>>(reinterpret_cast<const float4*>(dpred_), act_[4], B_, hw_[4], hw_[5],
+                                                      wg_partial_);
   RLREP_LAUNCHED_W("out_conv_wgrad", s, 4.0 * (rows(4) * 32 + rows(5) * 4), 2.0 * rows(5) * 384);
-  out_conv_wgrad_finish_kernel<<<2, 256, 0, s>>>(wg_partial_, kWgBlocks, g_.g + w_off_[4], g_.g + b_off_[4]);
+  if (ks_ == 2) out_conv_wgrad_finish_kernel<2><<<2, 256, 0, s>>>(wg_partial_, kWgBlocks, g_.g + w_off_[4], g_.g + b_off_[4]);
+  else out_conv_wgrad_finish_kernel<3><<<4, 256, 0, s>>>(wg_partial_, kWgBlocks, g_.g + w_off_[4], g_.g + b_off_[4]);
   RLREP_LAUNCHED("out_conv_wgrad_finish", s);
-  out_conv_dgrad_kernel<<<grid_for(rows(4) * 8, 256), 256, 0, s>>>(
-      reinterpret_cast<const float4*>(dpred_), g_.p + w_off_[4], reinterpret_cast<const float4*>(act_[4]), B_, hw_[4],
-      hw_[5], reinterpret_cast<float4*>(dact_[4]));
+  if (ks_ == 2)
+    out_conv_dgrad_kernel<2><<<grid_for(rows(4) * 8, 256), 256, 0, s>>>(
+        reinterpret_cast<const float4*>(dpred_), g_.p + w_off_[4], reinterpret_cast<const float4*>(act_[4]), B_, hw_[4],
+        hw_[5], reinterpret_cast<float4*>(dact_[4]));
+  else
+    out_conv_dgrad_kernel<3><<<grid_for(rows(4) * 8, 256), 256, 0, s>>>(
+        reinterpret_cast<const float4*>(dpred_), g_.p + w_off_[4], reinterpret_cast<const float4*>(act_[4]), B_, hw_[4],
+        hw_[5], reinterpret_cast<float4*>(dact_[4]));
   RLREP_LAUNCHED_W("out_conv_dgrad", s, 4.0 * (rows(5) * 4 + 2.0 * rows(4) * 32), 2.0 * rows(4) * 384);
   // ---- transposed convolutions, last to first; dact_[l + 1] already carries the ReLU mask of its layer
   for (int l = 3; l >= 0; --l) {

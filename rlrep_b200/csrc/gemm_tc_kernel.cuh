@@ -26,6 +26,7 @@
 // This header holds the device code and the per-variant launcher; it is included by the gemm_tc_inst_*.cu units (one
 // per (BN, A-major) pair so the 16 kernel variants compile in parallel) and by gemm_tc.cu for the tile constants.
 #pragma once
+#include <cstdlib>
 #include <algorithm>
 #include <cstdint>
 
@@ -300,6 +301,12 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // `stages` is a launch parameter: short K-slices run with a shallow ring so that two CTAs (of this or of a
   // concurrent GEMM on another stream) fit on one SM; long ones get the deepest ring that fits.
   const int STAGES = stages;
+  // DRAFT (branch draft/pdl-gemm-chain, not verified on hardware): bit 1 of `push` marks a launch with programmatic
+  // stream serialization.  Such a CTA may start while the previous kernel of the stream is still running: it does its
+  // prologue (barrier init, TMEM allocation), lets ITS dependents start theirs (launch_dependents), and only then waits
+  // for the previous grid's memory (griddepcontrol.wait) before the first operand load.
+  const bool pdl = (push & 2) != 0;
+  push &= 1;
   constexpr int A_BYTES = BM * BK * 4;
   constexpr int B_BYTES = BN * BK * 4;
   constexpr uint32_t TMEM_COLS = BN < 32 ? 32 : BN;
@@ -350,7 +357,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (!B_MN) ptx::tma_load_2d(b_dst, &tmB, &full_bar[s], k0, n0);
     else ptx::tma_load_3d(b_dst, &tmB, &full_bar[s], 0, k0, n0 / 32);
   };
-  const int first_round = nkb < 1 ? nkb : 1;  // one stage before the setup barrier; TMA issue itself is not free
+  // one stage before the setup barrier (TMA issue itself is not free) -- except under PDL, where no global read may
+  // precede griddepcontrol.wait
+  const int first_round = pdl ? 0 : (nkb < 1 ? nkb : 1);
   if (warp == 0 && lane == 0) {
     // The producer owns the barriers: it initialises them and immediately fills the ring (no empty-wait is needed
     // for the first round), so the first operands are in flight while the other warps allocate TMEM.
@@ -371,6 +380,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   ptx::tc_fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
   if (threadIdx.x == 0) trace(1);
+  if (pdl) {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");  // every thread: the epilogue reads aux / bias / C as well
+  }
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -686,6 +699,15 @@ void launch_variant_persistent(const TcGemmPlan& p, cudaStream_t stream) {
                    2.0 * a.M * a.N * a.K);
 }
 
+// DRAFT: RLREP_PDL=1 launches every one-tile GEMM with programmatic stream serialization (default off).
+inline bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("RLREP_PDL");
+    return e != nullptr && std::atoi(e) != 0;
+  }();
+  return on;
+}
+
 template <int BN, bool A_MN, bool B_MN>
 void fill_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, dim3 grid, int split_k, int stages,
                         bool push, cudaStream_t stream) {
@@ -706,6 +728,11 @@ void fill_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, dim3
   attr[0].val.clusterDim.z = split_k;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  if (pdl_enabled() && stream != nullptr) {
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.numAttrs = 2;
+  }
 }
 
 template <int BN, bool A_MN, bool B_MN>
@@ -718,7 +745,7 @@ void launch_variant(const TcGemmPlan& p, cudaStream_t stream) {
   fill_launch_config<BN, A_MN, B_MN>(cfg, attr, dim3(ceil_div(a.N, BN), ceil_div(a.M, BM), p.split_k), p.split_k,
                                      p.stages, p.push, stream);
   RLREP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, A_MN, B_MN>, p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, a.K,
-                                p.kb_per_split, p.stages, p.push ? 1 : 0, a.conv_w, a.epi));
+                                p.kb_per_split, p.stages, (p.push ? 1 : 0) | (pdl_enabled() ? 2 : 0), a.conv_w, a.epi));
   g_trace_reader = &read_trace_here;
   // implicit convolution: A is the [M, 32] pixel matrix, read once from HBM (the nine shifted re-reads hit L2)
   RLREP_LAUNCHED_W("gemm_tf32", stream,

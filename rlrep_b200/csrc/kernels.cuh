@@ -241,6 +241,32 @@ void launch_huber_critic_loss(const float* reward, const float* discount, const 
 // out[0] = mse(r_hat, r); dr = w * 2 (r_hat - r) / B
 void launch_reward_mse(const float* r_hat, const float* reward, int B, float w, float* dr, float* out, cudaStream_t s);
 
+// ---- DRAFT: latent Diff-SR DrQ-v2 pixel update (agent/diffsrdrq/latent_diff_sr.py; kernels_ldiff.cu) -------------------
+// LayerNorm + {0 none, 1 tanh, 2 swish}; same contract as launch_ln_act_fwd / _bwd (the backward also needs beta for swish).
+void launch_ln_act2_fwd(const float* x, int ld_x, int B, int n, const float* gamma, const float* beta, int act, float* y,
+                        int ld_y, int zero_to, float* xhat, int ld_h, float* rstd, cudaStream_t s);
+void launch_ln_act2_bwd(const float* dy, int ld_dy, const float* y, int ld_y, const float* xhat, int ld_h, const float* rstd,
+                        int B, int n, const float* gamma, const float* beta, int act, float* dx, int ld_dx, int zero_to,
+                        float* g_beta, float* g_gamma, int ld_g, cudaStream_t s);
+void launch_mish_fwd(const float* x, size_t n, float* y, cudaStream_t s);
+void launch_mish_bwd(const float* dy, const float* x, size_t n, float* dx, cudaStream_t s);
+// out = (accumulate ? out : 0) + x * (mask ? mask * inv_keep : 1): dropout with a host-drawn Bernoulli mask, and its backward
+void launch_mask_scale(const float* x, const float* mask, float inv_keep, size_t n, int accumulate, float* out, cudaStream_t s);
+// Diagonal-Gaussian posterior (vae_1d.py:24-48): h [N, 2L] = (mean | raw logvar, clamped to [-30, 20]); z = mean + std eps;
+// partial[block] = sum of 0.5 (mean^2 + var - 1 - logvar)
+void launch_posterior_fwd(const float* h, int N, int L, const float* eps, float* mean_out, float* z, float* partial,
+                          int n_blocks, cudaStream_t s);
+// dh from dz (gradient w.r.t. the sample), an optional gradient w.r.t. the mean of the first n_extra elements, and the
+// KL term with weight w_kl (= kl weight / N rows)
+void launch_posterior_bwd(const float* h, int N, int L, const float* eps, const float* dz, const float* dmean_extra,
+                          int n_extra, float w_kl, float* dh, cudaStream_t s);
+// zeta input [sqrt(ab) x + sqrt(1 - ab) noise | t_emb | 0] with row pitch ld; target = -noise; coef = sqrt(1 - ab) / feat
+void launch_ldiff_perturb(const float* x, const float* noise, const float* ab, const float* temb, int B, int L, int T,
+                          float inv_feat, float* zin, int ld, float* target, float* coef, cudaStream_t s);
+void launch_ldiff_perturb_bwd(const float* dzin, int ld, const float* ab, int B, int L, float* dx, cudaStream_t s);
+void launch_add_inplace(float* y, const float* x, size_t n, cudaStream_t s);
+void launch_scale_inplace(float* p, size_t n, float scale, cudaStream_t s);  // n % 4 == 0
+
 // Fused multi-tensor Adam (+ optional Polyak of a prefix of the arena into its target copy).
 // One launch updates a whole optimiser group laid out as flat arrays p / g / m / v of n floats (n % 4 == 0).
 //   torch.optim.Adam defaults: beta = (0.9, 0.999), eps = 1e-8, no weight decay / amsgrad.

@@ -1,5 +1,6 @@
 // Host runtime: replay ring, GEMM dispatch with cached TMA plans, linear-layer pass helpers, graph replay.
 #include <algorithm>
+#include <atomic>
 
 #include "agent.cuh"
 
@@ -62,7 +63,12 @@ namespace {
 constexpr size_t kStageRows = 8192;
 }  // namespace
 
-Ring::Ring(int state_dim, int action_dim, long long cap) : S(state_dim), A(action_dim), capacity(cap) {
+namespace {
+std::atomic<unsigned long long> g_ring_generation{0};
+}  // namespace
+
+Ring::Ring(int state_dim, int action_dim, long long cap)
+    : S(state_dim), A(action_dim), capacity(cap), generation(++g_ring_generation) {
   RLREP_CHECK(S > 0 && A > 0 && cap > 0, "bad ring dimensions");
   const RecordLayout l = RecordLayout::of(S, A);
   off_a = l.off_a;
@@ -92,7 +98,10 @@ Ring::~Ring() {
 void Ring::add_packed(const float* rows_host, int n, cudaStream_t s) {
   int done = 0;
   while (done < n) {
-    const int chunk = (int)std::min<size_t>(stage_rows_, (size_t)(n - done));
+    // One launch writes slot (ptr + b) % capacity for every staged row b: a chunk longer than the ring would map several
+    // rows to one slot inside ONE launch (a race; the reference keeps the newest row, utils/buffer.py:28-36), so chunks
+    // never exceed the capacity and consecutive chunks are stream-ordered.
+    const int chunk = (int)std::min<size_t>(std::min<size_t>(stage_rows_, (size_t)capacity), (size_t)(n - done));
     RLREP_CUDA(cudaStreamSynchronize(s));  // staging buffers are reused
     std::memcpy(stage_host_, rows_host + (size_t)done * R, (size_t)chunk * R * sizeof(float));
     RLREP_CUDA(cudaMemcpyAsync(stage_dev_, stage_host_, (size_t)chunk * R * sizeof(float), cudaMemcpyHostToDevice, s));

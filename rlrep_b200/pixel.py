@@ -502,3 +502,189 @@ class MuLVDrQv2:
                                               shifts.ctypes.data, eps_z.ctypes.data, eps_act.ctypes.data,
                                               noise.ctypes.data, stddev, m.ctypes.data))
         return {k: float(v) for k, v in zip(self.METRICS, m)}
+
+
+# ======================================================================================================================
+# DRAFT (branch draft/ldiffsr-agent): host mirror of agent/diffsrdrq/latent_diff_sr.py:LatentDiffSRDrQv2.  The device path
+# behind it (csrc/agent_ldiffsr.cu) compiles but has NOT been run on hardware yet; the RNG bookkeeping below is checked on
+# the CPU against the oracle (tests/test_host_logic.py).
+class LdiffConfig(C.Structure):
+    """Mirror of `rlrep_ldiff_config` (include/rlrep_b200.h)."""
+    _fields_ = [("batch_size", C.c_int), ("action_dim", C.c_int), ("latent_dim", C.c_int), ("feature_dim", C.c_int),
+                ("bn_dim", C.c_int), ("psi_hidden_dim", C.c_int), ("psi_hidden_depth", C.c_int), ("zeta_hidden_dim", C.c_int),
+                ("zeta_hidden_depth", C.c_int), ("hidden_dim", C.c_int), ("ae_lr", C.c_double), ("score_lr", C.c_double),
+                ("actor_lr", C.c_double), ("critic_lr", C.c_double), ("weight_decay", C.c_double), ("tau", C.c_float),
+                ("kl_coef", C.c_float), ("ae_coef", C.c_float), ("stddev_clip", C.c_float), ("precision", C.c_int)]
+
+
+class LdiffInputs(C.Structure):
+    """Mirror of `rlrep_ldiff_inputs`."""
+    _fields_ = [(n, C.c_void_p) for n in ("frames", "next_frames", "shifts", "next_shifts", "action", "reward", "discount",
+                                          "eps_post", "alphabar", "temb", "noise", "psi_masks", "zeta_masks", "eps_act")] + \
+               [("stddev", C.c_float)]
+
+
+class LatentDiffSRDrQv2:
+    """Drop-in for the update path of agent.diffsrdrq.latent_diff_sr.LatentDiffSRDrQv2: same constructor
+    (`obs_space`, `action_space`, `args`) and `train_step(replay_iter, step)` with the reference's metric keys.  Only
+    configs/latent_diff_sr.yaml's path is built (use_repr_target, back_critic_grad, critic_loss mse, reg_coef 0,
+    grad_norm null, extra_repr_step 1, do_scale false, repr_coef 1, ae_lr == score_lr)."""
+
+    def __init__(self, obs_space, action_space, args, *, precision="tf32"):
+        a = args
+        bad = [k for k, want in (("use_repr_target", True), ("back_critic_grad", True), ("critic_loss", "mse"),
+                                 ("reg_coef", 0.0), ("grad_norm", None), ("extra_repr_step", 1), ("do_scale", False),
+                                 ("repr_coef", 1.0), ("ae_num_layers", 4), ("ae_num_filters", 32),
+                                 ("noise_schedule", "linear")) if getattr(a, k, want) != want]
+        if bad or float(a.ae_lr) != float(a.score_lr) or a.bn_dim is None:
+            raise NotImplementedError(f"only configs/latent_diff_sr.yaml's path is built (differs in: {bad})")
+        self.args = a
+        self.obs_dim = tuple(int(x) for x in obs_space.shape)
+        if self.obs_dim != (9, 84, 84):
+            raise NotImplementedError("three stacked 3 x 84 x 84 frames")
+        self.action_dim = int(action_space.shape[0])
+        self.update_every = int(a.update_every)
+        self.stddev_schedule = _schedule(a.stddev_schedule)
+        self.L, self.feat = int(a.latent_dim), int(a.feature_dim)
+        self.psi = (int(a.psi_hidden_dim), int(a.psi_hidden_depth))
+        self.zeta = (int(a.zeta_hidden_dim), int(a.zeta_hidden_depth))
+        betas = np.linspace(float(a.noise_param1), float(a.noise_param2), int(a.num_noises))  # util.py:118-134
+        self.alphabars = torch.as_tensor(np.cumprod(1 - betas, axis=0), dtype=torch.float32)
+        self.num_noises = int(a.num_noises)
+        self._precision = precision
+        self._step = 1
+        self.lib = None
+        self._h = None
+        self._batch = None
+        self._pending = {}
+
+    def _draw(self, n):
+        """RNG consumption of one updating train_step in the reference's order (oracle/ldiffsr_oracle.py header)."""
+        L, A, keep = self.L, self.action_dim, 0.9
+        shifts = [torch.randint(0, 9, size=(n, 1, 1, 2), dtype=torch.float32).reshape(n, 2) for _ in range(2)]
+        eps_post = torch.randn(4 * n, L)
+        noise_idx = torch.randint(0, self.num_noises, (n,))
+        noise = torch.randn(n, L)
+        mask = lambda h: torch.empty(n, h).bernoulli_(keep)  # what F.dropout draws (checked in tests/test_host_logic.py)
+        psi_score = [mask(self.psi[0]) for _ in range(self.psi[1])]
+        zeta = [mask(self.zeta[0]) for _ in range(self.zeta[1])]
+        psi_critic = [mask(self.psi[0]) for _ in range(self.psi[1])]
+        za = torch.zeros(n, A)
+        eps_act = [torch.normal(za, torch.ones_like(za)) for _ in range(2)]
+        half = (L // 2) // 2  # SinusoidalPosEmb(latent_dim // 2), score_mlp.py:94-106
+        emb = torch.exp(torch.arange(half) * -(np.log(10000) / (half - 1)))
+        emb = noise_idx[..., None] * emb[None, :]
+        temb = torch.cat((emb.sin(), emb.cos()), dim=-1)
+        return dict(shifts=torch.stack(shifts).to(torch.int32).numpy(), eps_post=eps_post.numpy(),
+                    alphabar=self.alphabars[noise_idx].numpy(), temb=temb.float().numpy(), noise=noise.numpy(),
+                    psi_masks=torch.stack([torch.cat([s, c]) for s, c in zip(psi_score, psi_critic)]).numpy(),
+                    zeta_masks=torch.stack(zeta).numpy(), eps_act=torch.stack(eps_act).numpy())
+
+    def _ensure(self, batch):
+        if self._h is not None:
+            if batch != self._batch:
+                raise _lib.RlrepError(f"batch size is fixed per handle (was {self._batch}, got {batch})")
+            return
+        if not torch.cuda.is_available():
+            raise _lib.RlrepError("rlrep_b200.LatentDiffSRDrQv2 needs a CUDA device (there is no CPU fallback)")
+        self.lib = _lib.load()
+        a = self.args
+        cfg = LdiffConfig(batch_size=batch, action_dim=self.action_dim, latent_dim=self.L, feature_dim=self.feat,
+                          bn_dim=int(a.bn_dim), psi_hidden_dim=self.psi[0], psi_hidden_depth=self.psi[1],
+                          zeta_hidden_dim=self.zeta[0], zeta_hidden_depth=self.zeta[1], hidden_dim=int(a.actor_hidden_dim),
+                          ae_lr=float(a.ae_lr), score_lr=float(a.score_lr), actor_lr=float(a.actor_lr),
+                          critic_lr=float(a.critic_lr), weight_decay=0.01, tau=float(a.tau), kl_coef=float(a.kl_coef),
+                          ae_coef=float(a.ae_coef), stddev_clip=float(a.stddev_clip), precision=_lib.PRECISION[self._precision])
+        hd = C.c_void_p()
+        _lib.check(self.lib.rlrep_ldiff_create(C.byref(cfg), None, C.byref(hd)))
+        self._h, self._batch = hd, batch
+        n = C.c_int()
+        _lib.check(self.lib.rlrep_ldiff_num_tensors(hd, C.byref(n)))
+        self._index = {}
+        for i in range(n.value):
+            name, ptr, rows, cols = C.c_char_p(), C.c_void_p(), C.c_int(), C.c_int()
+            _lib.check(self.lib.rlrep_ldiff_tensor_info(hd, i, C.byref(name), C.byref(ptr), C.byref(rows), C.byref(cols)))
+            self._index[name.value.decode()] = (i, rows.value, cols.value)
+        if self._pending:
+            sd, self._pending = self._pending, {}
+            self.load_state_dict(sd)
+
+    @staticmethod
+    def _kind(name):
+        if name.endswith("weight"):
+            if ".deconvs.8." in name:
+                return "outconv"
+            if ".deconvs." in name:
+                return "deconv"
+            if ".convs." in name:
+                return "conv0" if name.endswith("convs.0.weight") else "conv"
+            if any(s in name for s in (".ln.", ".layer_norm.", "psi_bottleneck1.1.", "psi_bottleneck2.1.", "trunk.1.")):
+                return "vec"
+            return "mat"
+        return "vec"
+
+    def _ref_shape(self, name, rows, cols):
+        return {"outconv": (3, 32, 3, 3), "deconv": (32, 32, 3, 3), "conv0": (32, cols // 9, 3, 3), "conv": (32, cols // 9, 3, 3),
+                "vec": (rows,), "mat": (rows, cols)}[self._kind(name)]
+
+    def state_dict(self):
+        if self._h is None:
+            return dict(self._pending)
+        sd = {}
+        for name, (i, rows, cols) in self._index.items():
+            if name.startswith("grad/"):
+                continue
+            out = np.empty(rows * cols, dtype=np.float32)
+            _lib.check(self.lib.rlrep_ldiff_tensor_read(self._h, i, out.ctypes.data))
+            t, kind = torch.from_numpy(out), self._kind(name)
+            if kind == "conv":
+                t = t.reshape(32, 3, 3, 32).permute(0, 3, 1, 2).contiguous()
+            elif kind == "deconv":
+                t = t.reshape(3, 3, 32, 32).permute(3, 2, 0, 1).contiguous()
+            sd[name] = t.reshape(self._ref_shape(name, rows, cols))
+        return sd
+
+    def load_state_dict(self, sd, sync_targets=None):
+        if self._h is None:
+            self._pending.update({k: torch.as_tensor(v).detach().clone() for k, v in sd.items()})
+            return
+        for k, v in sd.items():
+            i, rows, cols = self._index[k]
+            t = torch.as_tensor(v).detach().cpu().float()
+            kind = self._kind(k)
+            if kind == "conv":
+                t = t.permute(0, 2, 3, 1)
+            elif kind == "deconv":
+                t = t.permute(2, 3, 1, 0)
+            arr = np.ascontiguousarray(t.reshape(-1).numpy())
+            _lib.check(self.lib.rlrep_ldiff_tensor_write(self._h, i, arr.ctypes.data))
+        if sync_targets or (sync_targets is None and not any("_target." in k for k in sd)):
+            _lib.check(self.lib.rlrep_ldiff_sync_targets(self._h))
+
+    def train_step(self, replay_iter, step):
+        self._step += 1
+        if self._step % self.update_every != 0:
+            return {}
+        batch = next(replay_iter)
+        img, action, reward, discount, next_img, next_step = (np.ascontiguousarray(torch.as_tensor(t).cpu().numpy())
+                                                              for t in batch[:6])
+        n = img.shape[0]
+        self._ensure(n)
+        d = self._draw(n)
+        frames = np.ascontiguousarray(np.concatenate([img.reshape(3 * n, 3, 84, 84), next_step[:, -3:]], axis=0))
+        next_frames = np.ascontiguousarray(next_img.reshape(3 * n, 3, 84, 84))
+        ident = np.full((n, 2), 4, dtype=np.int32)
+        shifts = np.ascontiguousarray(np.concatenate([np.repeat(d["shifts"][0], 3, axis=0), ident], axis=0), dtype=np.int32)
+        next_shifts = np.ascontiguousarray(np.repeat(d["shifts"][1], 3, axis=0), dtype=np.int32)
+        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
+        keep = dict(frames=frames, next_frames=next_frames, shifts=shifts, next_shifts=next_shifts, action=f32(action),
+                    reward=f32(reward).reshape(-1), discount=f32(discount).reshape(-1), eps_post=f32(d["eps_post"]),
+                    alphabar=f32(d["alphabar"]), temb=f32(d["temb"]), noise=f32(d["noise"]), psi_masks=f32(d["psi_masks"]),
+                    zeta_masks=f32(d["zeta_masks"]), eps_act=f32(d["eps_act"]))
+        stddev = float(self.stddev_schedule(step))
+        inp = LdiffInputs(stddev=stddev, **{k: v.ctypes.data for k, v in keep.items()})
+        m = np.zeros(8, dtype=np.float32)
+        _lib.check(self.lib.rlrep_ldiff_update(self._h, C.byref(inp), m.ctypes.data))
+        return {"loss/recon_loss": float(m[0]), "loss/kl_loss": float(m[1]), "loss/score_loss": float(m[2]), "loss/reg_loss": 0.0,
+                "loss/critic_loss": float(m[3]), "info/q_pred": float(m[4]), "info/q_target": float(m[5]),
+                "info/reward": float(m[6]), "loss/actor_loss": float(m[7]), "info/policy_std": stddev}

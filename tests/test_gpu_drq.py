@@ -73,7 +73,7 @@ def test_drq_first_update_metrics_and_gradients(C, A, bn, H, B, precision):
         worst[k.split(".")[0]] = max(worst[k.split(".")[0]], e)
     print(f"drqv2 grads C={C} B={B} H={H} {precision}: forward metrics {fwd:.1e}, actor_loss {act:.1e}, "
           + ", ".join(f"{k} grads {v:.1e}" for k, v in worst.items()))
-    t = dict(fp32=(2e-4, 2e-5, 2e-3, 5e-3), tf32=(5e-3, 5e-2, 1e-1, 8e-2))[precision]
+    t = dict(fp32=(1e-5, 2e-5, 2e-3, 5e-3), tf32=(1e-3, 5e-2, 1e-1, 8e-2))[precision]  # losses: the north_star bars
     assert fwd < t[0] and act < (2e-3 if precision == "fp32" else 2e-2)
     assert worst["critic"] < t[1] and worst["actor"] < t[2] and worst["encoder"] < t[3], worst
     agent.close()
@@ -86,7 +86,7 @@ def test_drq_first_update_metrics_and_gradients(C, A, bn, H, B, precision):
 # pre-activation of ALL rows (measured: rel-L2 4.7e-5 on critic.trunk.0.weight moves the next actor_loss by 2.5e-3).
 # The gradient-level test above is the tight one; this one checks the call protocol, Adam / Polyak bookkeeping and
 # that nothing drifts beyond that mechanism.  Parameters are compared norm-wise.
-TOL = {"fp32": dict(fwd=2e-4, after_adam=2e-2, param=5e-3), "tf32": dict(fwd=5e-3, after_adam=1e-1, param=4e-2)}
+TOL = {"fp32": dict(fwd=1e-5, after_adam=2e-2, param=5e-3), "tf32": dict(fwd=1e-3, after_adam=1e-1, param=4e-2)}
 FORWARD_KEYS = ("loss/critic_loss", "info/q_pred", "info/q_target", "info/reward", "info/policy_std")
 
 

@@ -1,0 +1,62 @@
+"""DRAFT (branch draft/ldiffsr-agent): GPU parity of the latent Diff-SR DrQ-v2 pixel update against oracle/ldiffsr_oracle.py
+(bit-identical to the reference class).  Not run yet -- the device path was written after the round's GPU budget was spent."""
+import types
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# Dims(A, L, feat, bn, psi_h, psi_d, zeta_h, zeta_d, H), batch
+CONFIGS = [((4, 64, 32, 32, 32, 2, 32, 4, 64), 4), ((4, 64, 64, 64, 64, 2, 64, 4, 128), 32)]
+GROUPS = ("vae", "score", "critic", "actor")
+
+
+class Box:
+    def __init__(self, shape):
+        self.shape = shape
+
+
+def _args(d):
+    return types.SimpleNamespace(use_repr_target=True, back_critic_grad=True, critic_loss="mse", reg_coef=0.0, grad_norm=None,
+                                 extra_repr_step=1, do_scale=False, repr_coef=1.0, ae_num_layers=4, ae_num_filters=32,
+                                 noise_schedule="linear", ae_lr=3e-4, score_lr=3e-4, actor_lr=1e-4, critic_lr=1e-4, bn_dim=d.bn,
+                                 update_every=1, stddev_schedule="linear(1.0,0.1,500000)", stddev_clip=0.3, latent_dim=d.L,
+                                 feature_dim=d.feat, psi_hidden_dim=d.psi_h, psi_hidden_depth=d.psi_d, zeta_hidden_dim=d.zeta_h,
+                                 zeta_hidden_depth=d.zeta_d, actor_hidden_dim=d.H, critic_hidden_dim=d.H, noise_param1=1e-4,
+                                 noise_param2=0.02, num_noises=1000, tau=0.01, kl_coef=1.0, ae_coef=1.0)
+
+
+def _rel(a, b):
+    return ((a.double() - b.double()).norm() / (b.double().norm() + 1e-30)).item()
+
+
+@pytest.mark.parametrize("dims,B", CONFIGS)
+@pytest.mark.parametrize("precision", ["fp32", "tf32"])
+def test_ldiffsr_update_matches_oracle(dims, B, precision):
+    from oracle import ldiffsr_oracle as O
+    from rlrep_b200.pixel import LatentDiffSRDrQv2
+    d = O.Dims(*dims)
+    init = O.init_state(d, seed=0)
+    oracle = O.OracleLatentDiffSR(d, init, update_every=1)
+    agent = LatentDiffSRDrQv2(Box((9, 84, 84)), Box((d.A,)), _args(d), precision=precision)
+    agent.load_state_dict(init)
+    batch = O.synthetic_pixel_batch(B, 9, 84, d.A, seed=50)
+    torch.manual_seed(1)
+    o = oracle.train_step(batch, step=0)
+    after = torch.get_rng_state()
+    torch.manual_seed(1)
+    c = agent.train_step(iter([tuple(batch)]), step=0)
+    assert torch.equal(torch.get_rng_state(), after)
+    keys = ("loss/recon_loss", "loss/kl_loss", "loss/score_loss", "loss/critic_loss", "info/q_pred", "info/q_target",
+            "info/reward", "loss/actor_loss")
+    err = {k: max(0.0, abs(c[k] - o[k]) - 1e-5) / (abs(o[k]) + 1e-12) for k in keys}
+    csd, osd = agent.state_dict(), oracle.state_dict()
+    assert set(osd) <= set(csd), sorted(set(osd) - set(csd))[:10]
+    perr = sorted(((_rel(csd[k], v), k) for k, v in osd.items()), reverse=True)
+    print(f"\nldiffsr dims={dims} B={B} {precision}: metrics " + ", ".join(f"{k} {v:.1e}" for k, v in err.items())
+          + "\n  worst params: " + ", ".join(f"{k} {e:.1e}" for e, k in perr[:8]))
+    tol = dict(fp32=(2e-4, 2e-3), tf32=(2e-2, 4e-2))[precision]
+    assert max(err.values()) < tol[0], err
+    assert perr[0][0] < tol[1], perr[0]

@@ -20,7 +20,7 @@ FORWARD = ("critic_loss", "critic_q1", "critic_q2", "critic_target_q", "s_loss",
 # Parameters after the update are compared norm-wise: Adam's first step is lr * sign(g) for every element, so elements whose
 # gradient is within rounding distance of zero (inputs that are almost always behind a ReLU) move by +-lr on either side
 # (measured 7.7e-4 on actor.trunk.0.weight [100, 39200] at the full size, 1e-4 elsewhere).
-TOL = {"fp32": dict(fwd=2e-4, grad=5e-3, critic=5e-3, actor=5e-3, param=2e-3, after=2e-2),
+TOL = {"fp32": dict(fwd=1e-5, grad=5e-3, critic=5e-3, actor=5e-3, param=2e-3, after=2e-2),
        "tf32": dict(fwd=1e-2, grad=1e-1, critic=2.5e-1, actor=1.5e-1, param=2e-2, after=1e-1)}
 
 
@@ -39,7 +39,10 @@ def _rel(a, b):
 def test_mulv_update_matches_oracle(C, A, F, H, B, precision):
     from oracle import mulv_oracle as M
     from rlrep_b200.pixel import MuLVDrQv2
-    tol = TOL[precision]
+    tol = dict(TOL[precision])
+    if precision == "tf32" and B >= 256:
+        tol["fwd"] = 1e-3  # the north_star TF32 bar on the losses at mulv_config.py's own size; at B <= 32 the Q means are
+        #                    ~1e-2 in magnitude and a few TF32 roundings of single rows show at 2e-3
     init = M.init_state(C, A, F, H, seed=0)
     oracle = M.OracleMuLVDrQ(A, init)
     agent = MuLVDrQv2((C, 84, 84), (A,), _cfg(F, H), precision=precision)

@@ -212,3 +212,45 @@ def test_implicit_convolution_algebra():
         flip2[:, t * 32:(t + 1) * 32] = wd[tap * 32:(tap + 1) * 32, :]  # w_flip[co, t*32 + ci] = Wd[tap*32 + co, ci]
     grid = _shifted_row_gemm(nhwc(F.pad(x, (2, 2, 2, 2))), flip2, Wp).reshape(B, Wp, Wp, 32)[:, :H + 2, :H + 2]
     assert torch.allclose(grid.permute(0, 3, 1, 2), F.conv_transpose2d(x, wt), atol=1e-10)
+
+
+def test_latent_diffsr_draw_consumes_the_generator_like_the_reference():
+    """DRAFT shim (branch draft/ldiffsr-agent): the host-side randomness of one updating train_step -- shifts, posterior
+    noise, diffusion levels / noise, the dropout masks of the online score network (drawn as Bernoulli(0.9) tensors, which
+    is what F.dropout consumes), the action normals -- leaves the CPU generator exactly where the oracle (bit-identical
+    to the reference class, tests/golden/ldiffsr_b4.npz) leaves it, and the masks are the ones the oracle applied."""
+    import types
+    import torch.nn.functional as F
+    from oracle import ldiffsr_oracle as O
+    from rlrep_b200.pixel import LatentDiffSRDrQv2
+    d = O.Dims(4, 16, 32, 24, 32, 2, 32, 4, 64)
+
+    class Box:
+        def __init__(self, shape):
+            self.shape = shape
+    args = types.SimpleNamespace(use_repr_target=True, back_critic_grad=True, critic_loss="mse", reg_coef=0.0, grad_norm=None,
+                                 extra_repr_step=1, do_scale=False, repr_coef=1.0, ae_num_layers=4, ae_num_filters=32,
+                                 noise_schedule="linear", ae_lr=3e-4, score_lr=3e-4, actor_lr=1e-4, critic_lr=1e-4, bn_dim=d.bn,
+                                 update_every=2, stddev_schedule="linear(1.0,0.1,500000)", stddev_clip=0.3, latent_dim=d.L,
+                                 feature_dim=d.feat, psi_hidden_dim=d.psi_h, psi_hidden_depth=d.psi_d, zeta_hidden_dim=d.zeta_h,
+                                 zeta_hidden_depth=d.zeta_d, actor_hidden_dim=d.H, critic_hidden_dim=d.H, noise_param1=1e-4,
+                                 noise_param2=0.02, num_noises=1000, tau=0.01, kl_coef=1.0, ae_coef=1.0)
+    agent = LatentDiffSRDrQv2(Box((9, 84, 84)), Box((d.A,)), args)
+    oracle = O.OracleLatentDiffSR(d, O.init_state(d, seed=0))
+    B = 3
+    batch = O.synthetic_pixel_batch(B, 9, 84, d.A, seed=0)
+    torch.manual_seed(11)
+    assert oracle.train_step(batch, 0) != {}
+    after = torch.get_rng_state().clone()
+    torch.manual_seed(11)
+    draws = agent._draw(B)
+    assert torch.equal(torch.get_rng_state(), after)
+    assert draws["psi_masks"].shape == (d.psi_d, 2 * B, d.psi_h) and draws["zeta_masks"].shape == (d.zeta_d, B, d.zeta_h)
+    assert draws["eps_post"].shape == (4 * B, d.L) and draws["temb"].shape == (B, d.L // 2)
+    assert set(np.unique(draws["psi_masks"])) <= {0.0, 1.0}
+    torch.manual_seed(5)
+    y = F.dropout(torch.ones(6, 10), 0.1, True)
+    torch.manual_seed(5)
+    assert torch.equal((y > 0).float(), torch.empty(6, 10).bernoulli_(0.9))
+    with pytest.raises(NotImplementedError):
+        LatentDiffSRDrQv2(Box((9, 84, 84)), Box((d.A,)), types.SimpleNamespace(**{**vars(args), "grad_norm": 1.0}))
