@@ -87,6 +87,21 @@ RLREP_EXPORT int rlrep_gemm_bench(void* stream, int path, int M, int N, int K, c
                                   const rlrep_epilogue* epi, int bn, int split_k, float* ws_dev, size_t ws_floats,
                                   int iters, float* ms_out, int* bn_out, int* split_out);
 
+/* GEMM chain: a DAG of dependent GEMMs (the layers of a few small MLPs, forward or backward) executed by ONE persistent
+ * tcgen05 kernel -- one CTA per SM walks a static item list, a dependent tile starts when the tiles it reads are complete
+ * (csrc/gemm_chain.cuh).  The agent handles use this internally for every group of GEMMs between two elementwise kernels
+ * when the batch is small; these three calls expose it for tests and tuning.  Usage (per thread): begin, add every GEMM in
+ * program order (dependencies are inferred from the operands' address ranges), run.  `bn` / `split_k` = 0 lets the planner
+ * choose per GEMM.  run launches the chain `iters` times (>= 1) and reports the CUDA-event average in milliseconds. */
+RLREP_EXPORT int rlrep_gemm_chain_begin(void);
+RLREP_EXPORT int rlrep_gemm_chain_add(int M, int N, int K, const float* A_dev, int lda, int a_mn, const float* B_dev,
+                                      int ldb, int b_mn, float* C_dev, int ldc, const rlrep_epilogue* epi);
+RLREP_EXPORT int rlrep_gemm_chain_run(void* stream, int bn, int split_k, int iters, float* ms_out, int* levels_out);
+/* Debug aid: device buffer of 148 CTAs x 16 items x 10 slots uint64 %globaltimer stamps written by every chain launch
+ * (NULL = off).  Events per item: 0 picked up, 1 dependencies satisfied, 2 TMA issued, 3 first operands landed,
+ * 4 accumulator committed, 5 epilogue start, 6 split-K arrival, 7 tile published. */
+RLREP_EXPORT int rlrep_gemm_chain_set_debug(unsigned long long* dev);
+
 /* Debug aid (library built with -DRLREP_GEMM_TRACE): %globaltimer stamps (ns) taken by CTA (0,0,0) of the most
  * recent tcgen05 GEMM at: 0 entry, 1 setup done, 2 first operands landed, 3 last MMA issued, 4 accumulator complete,
  * 5 staged to shared, 6 cluster/CTA sync passed, 7 stores issued, 8 exit. */
@@ -169,6 +184,16 @@ RLREP_EXPORT int rlrep_agent_tensor_write(rlrep_agent* agent, int i, const float
 RLREP_EXPORT int rlrep_agent_sync_targets(rlrep_agent* agent);
 RLREP_EXPORT int rlrep_agent_get_log_alpha(rlrep_agent* agent, double* log_alpha);
 RLREP_EXPORT int rlrep_agent_set_log_alpha(rlrep_agent* agent, double log_alpha);
+/* Optimiser / schedule state that is not a tensor: the agent's `steps` counter (gates the critic Polyak, sac_agent.py:100),
+ * the Adam step counters of the four optimisers (bias correction) and the float64 temperature with its Adam moments.
+ * Together with the "optim.m/<name>" / "optim.v/<name>" tensors it lets a checkpoint resume exactly where it stopped. */
+typedef struct rlrep_optim_state {
+  int steps;
+  long long t_feature, t_critic, t_actor, t_alpha;
+  double log_alpha, log_alpha_m, log_alpha_v;
+} rlrep_optim_state;
+RLREP_EXPORT int rlrep_agent_get_optim_state(rlrep_agent* agent, rlrep_optim_state* out);
+RLREP_EXPORT int rlrep_agent_set_optim_state(rlrep_agent* agent, const rlrep_optim_state* in);
 RLREP_EXPORT int rlrep_agent_get_steps(rlrep_agent* agent, int* steps);
 
 /* One `agent.train(buffer, batch_size)`.  The caller draws the randomness exactly like the reference does
@@ -336,6 +361,11 @@ RLREP_EXPORT int rlrep_ldiff_update(rlrep_ldiff* h, const rlrep_ldiff_inputs* in
 RLREP_EXPORT int rlrep_ldiff_last_launches(rlrep_ldiff* h, int* launches);
 
 /* Kernels launched by the most recent train() (a graph replay counts the kernels it contains). */
+/* Batched policy evaluation (utils/util.py:40-57 `eval_policy` over vectorised environments, or any caller that has many
+ * observations at once): states_host [rows, state_dim], eps_host [rows, action_dim] or NULL (deterministic),
+ * actions_host [rows, action_dim].  One kernel launch per 1024 rows; rlrep_agent_act is the rows = 1 case. */
+RLREP_EXPORT int rlrep_agent_act_batch(rlrep_agent* agent, const float* states_host, const float* eps_host, int rows,
+                                       float* actions_host);
 RLREP_EXPORT int rlrep_agent_last_launches(rlrep_agent* agent, int* launches);
 
 #ifdef __cplusplus

@@ -18,4 +18,7 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
     if name in ("ConvEncoder", "DrQv2", "MuLVDrQv2", "LatentDiffSRDrQv2"):
         from . import pixel
         return getattr(pixel, name)
+    if name == "Population":
+        from . import population
+        return population.Population
     raise AttributeError(name)

@@ -16,6 +16,13 @@ class RlrepError(RuntimeError):
     pass
 
 
+class OptimState(C.Structure):
+    """Mirror of `rlrep_optim_state` (include/rlrep_b200.h)."""
+    _fields_ = [("steps", C.c_int), ("t_feature", C.c_longlong), ("t_critic", C.c_longlong), ("t_actor", C.c_longlong),
+                ("t_alpha", C.c_longlong), ("log_alpha", C.c_double), ("log_alpha_m", C.c_double),
+                ("log_alpha_v", C.c_double)]
+
+
 class AgentConfig(C.Structure):
     """Mirror of `rlrep_agent_config` (include/rlrep_b200.h)."""
     _fields_ = [
@@ -74,6 +81,10 @@ def _declare(lib: C.CDLL) -> None:
         "rlrep_gemm_bench": [vp, i, i, i, i, vp, i, i, vp, i, i, vp, i, C.POINTER(Epilogue), i, i, vp, sz, i,
                              C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int)],
         "rlrep_gemm_trace": [vp],
+        "rlrep_gemm_chain_begin": [],
+        "rlrep_gemm_chain_set_debug": [vp],
+        "rlrep_gemm_chain_add": [i, i, i, vp, i, i, vp, i, i, vp, i, C.POINTER(Epilogue)],
+        "rlrep_gemm_chain_run": [vp, i, i, i, C.POINTER(C.c_float), C.POINTER(C.c_int)],
         "rlrep_ring_create": [i, i, C.c_longlong, C.POINTER(vp)],
         "rlrep_ring_destroy": [vp],
         "rlrep_ring_layout": [vp] + [C.POINTER(i)] * 5,
@@ -139,9 +150,12 @@ def _declare(lib: C.CDLL) -> None:
         "rlrep_agent_get_log_alpha": [vp, C.POINTER(C.c_double)],
         "rlrep_agent_set_log_alpha": [vp, C.c_double],
         "rlrep_agent_get_steps": [vp, C.POINTER(i)],
+        "rlrep_agent_get_optim_state": [vp, C.POINTER(OptimState)],
+        "rlrep_agent_set_optim_state": [vp, C.POINTER(OptimState)],
         "rlrep_agent_train_counts": [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i)],
         "rlrep_agent_train": [vp, vp, vp, i, vp, i, vp, i],
         "rlrep_agent_act": [vp, vp, vp, vp],
+        "rlrep_agent_act_batch": [vp, vp, vp, i, vp],
         "rlrep_agent_last_launches": [vp, C.POINTER(i)],
         "rlrep_agent_train_resident": [vp, vp, vp, vp, i, C.POINTER(C.c_float)],
         "rlrep_agent_profile_train": [vp, vp, vp, vp, i, C.POINTER(C.c_char_p), C.POINTER(C.c_float),
@@ -202,6 +216,27 @@ def gemm(A, B, C_out, *, a_mn=False, b_mn=False, path="tc", epi: Epilogue | None
                         split_k, ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0)
     check(rc)
     return C_out
+
+
+def gemm_chain(specs, *, bn=0, split_k=0, iters=1):
+    """Runs a DAG of GEMMs as ONE persistent chain kernel (csrc/gemm_chain.cuh).  specs = [(A, B, C_out, dict(a_mn=, b_mn=,
+    epi=))] in program order; dependencies are inferred from the tensors' addresses.  Returns (ms per launch, levels)."""
+    lib = load()
+    check(lib.rlrep_gemm_chain_begin())
+    keep = []
+    for A, B, C_out, kw in specs:
+        a_mn, b_mn = bool(kw.get("a_mn", False)), bool(kw.get("b_mn", False))
+        M = A.shape[1] if a_mn else A.shape[0]
+        K = A.shape[0] if a_mn else A.shape[1]
+        N = B.shape[1] if b_mn else B.shape[0]
+        assert (B.shape[0] if b_mn else B.shape[1]) == K
+        epi = kw.get("epi") or make_epilogue()
+        keep.append(epi)
+        check(lib.rlrep_gemm_chain_add(M, N, K, A.data_ptr(), A.stride(0), int(a_mn), B.data_ptr(), B.stride(0), int(b_mn),
+                                       C_out.data_ptr(), C_out.stride(0), C.byref(epi)))
+    ms, levels = C.c_float(), C.c_int()
+    check(lib.rlrep_gemm_chain_run(current_stream_ptr(), bn, split_k, iters, C.byref(ms), C.byref(levels)))
+    return ms.value, levels.value
 
 
 def gemm_bench(A, B, C_out, *, a_mn=False, b_mn=False, path="tc", epi=None, bn=0, split_k=0, ws=None, iters=50):

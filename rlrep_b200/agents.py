@@ -100,6 +100,21 @@ class _Handle:
         _lib.check(self.lib.rlrep_agent_set_log_alpha(self.h, float(v)))
 
     @property
+    def optim_state(self) -> dict:
+        st = _lib.OptimState()
+        _lib.check(self.lib.rlrep_agent_get_optim_state(self.h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in _lib.OptimState._fields_}
+
+    @optim_state.setter
+    def optim_state(self, d):
+        st = _lib.OptimState()
+        _lib.check(self.lib.rlrep_agent_get_optim_state(self.h, C.byref(st)))
+        for k, _ in _lib.OptimState._fields_:
+            if k in d:
+                setattr(st, k, type(getattr(st, k))(d[k]))
+        _lib.check(self.lib.rlrep_agent_set_optim_state(self.h, C.byref(st)))
+
+    @property
     def last_launches(self) -> int:
         v = C.c_int()
         _lib.check(self.lib.rlrep_agent_last_launches(self.h, C.byref(v)))
@@ -170,16 +185,21 @@ class SACAgent:
     def _ensure(self, batch_size=None):
         if self._h is not None and (batch_size is None or batch_size == self._batch):
             return self._h
+        carried = None
         if self._h is not None:
-            if self.steps > 0:
-                raise _lib.RlrepError(f"batch_size is fixed per agent handle (was {self._batch}, got {batch_size})")
+            # A different batch size (the reference accepts any, per call): activation buffers, TMA descriptors and the
+            # captured graph are per batch size, so the handle is rebuilt and EVERYTHING that is state -- weights, targets,
+            # Adam moments, step counters, the float64 temperature -- is carried over.
             self._pending_state = self.state_dict()
             self._pending_state.pop("log_alpha", None)
+            carried = self.optimizer_state_dict()
             self._h.close()
         self._batch = int(batch_size or 256)
         self._h = self._make_handle(self._batch)
         self.load_state_dict(self._pending_state, strict=False)
         self._pending_state = None
+        if carried is not None:
+            self.load_optimizer_state_dict(carried)
         return self._h
 
     def _make_handle(self, batch):
@@ -189,9 +209,45 @@ class SACAgent:
         """All parameters and Polyak targets under the reference's state_dict names, plus float64 `log_alpha`."""
         if self._h is None:
             return dict(self._pending_state)
-        sd = {name: self._h.read(name) for name in self._h.index}
+        sd = {name: self._h.read(name) for name in self._h.index if not name.startswith("optim.")}
         sd["log_alpha"] = torch.tensor(self._h.log_alpha, dtype=torch.float64)
         return sd
+
+    def optimizer_state_dict(self):
+        """Adam moments of every parameter (`optim.m/<name>`, `optim.v/<name>` = torch.optim.Adam's exp_avg / exp_avg_sq)
+        plus `control`: the agent's `steps`, the four optimisers' step counters and the temperature's float64 moments."""
+        h = self._ensure()
+        sd = {name: h.read(name) for name in h.index if name.startswith("optim.")}
+        sd["control"] = dict(h.optim_state, agent_steps=self.steps)
+        return sd
+
+    def load_optimizer_state_dict(self, sd):
+        h = self._ensure()
+        for k, v in sd.items():
+            if k != "control":
+                h.write(k, v)
+        ctl = dict(sd.get("control", {}))
+        self.steps = int(ctl.pop("agent_steps", self.steps))
+        h.optim_state = ctl
+
+    def save(self, path):
+        """Checkpoint (the reference parses --save_model but never writes one, main.py:37): a torch.save'd dict with the
+        parameters / targets under the reference's state_dict names, so reference modules can load their slices with
+        `module.load_state_dict({k[len(prefix):]: v ...})`, plus the optimiser state needed to resume exactly."""
+        torch.save({"format": "rlrep_b200/1", "alg": self.alg, "state_dim": self.state_dim, "action_dim": self.action_dim,
+                    "batch_size": self._batch, "state_dict": self.state_dict(), "optimizer": self.optimizer_state_dict()},
+                   path)
+
+    def load(self, path, load_optimizer=True):
+        ck = torch.load(path, map_location="cpu", weights_only=False)
+        if ck.get("format") != "rlrep_b200/1" or ck.get("alg") != self.alg:
+            raise _lib.RlrepError(f"{path}: not a rlrep_b200 checkpoint of a {self.alg} agent")
+        if (ck["state_dim"], ck["action_dim"]) != (self.state_dim, self.action_dim):
+            raise _lib.RlrepError(f"{path}: saved for state/action dims {(ck['state_dim'], ck['action_dim'])}")
+        self._ensure(ck.get("batch_size") if self._h is None else None)
+        self.load_state_dict(ck["state_dict"], strict=False, sync_targets=False)
+        if load_optimizer:
+            self.load_optimizer_state_dict(ck["optimizer"])
 
     def load_state_dict(self, sd, strict=True, sync_targets=None):
         """Write weights.  Targets not present in `sd` are re-synchronised from their source networks."""
@@ -228,6 +284,18 @@ class SACAgent:
             eps = np.ascontiguousarray(torch.randn(1, self.action_dim).numpy().reshape(-1))
         _lib.check(h.lib.rlrep_agent_act(h.h, s.ctypes.data, eps.ctypes.data if eps is not None else None,
                                          out.ctypes.data))
+        return np.clip(out, self.action_range[0], self.action_range[1])
+
+    def select_actions(self, states, explore=False):
+        """Batched `select_action`: states [N, state_dim] -> actions [N, action_dim] in one kernel launch per 1024 rows
+        (`rlrep_agent_act_batch`).  With explore=True the noise is ONE torch.randn([N, action_dim]) draw from the CPU
+        generator (row i is what the i-th of N consecutive select_action(explore=True) calls would draw)."""
+        h = self._ensure()
+        s = np.ascontiguousarray(np.asarray(states, dtype=np.float32).reshape(-1, self.state_dim))
+        out = np.empty((s.shape[0], self.action_dim), dtype=np.float32)
+        eps = np.ascontiguousarray(torch.randn(s.shape[0], self.action_dim).numpy()) if explore else None
+        _lib.check(h.lib.rlrep_agent_act_batch(h.h, s.ctypes.data, eps.ctypes.data if eps is not None else None,
+                                               s.shape[0], out.ctypes.data))
         return np.clip(out, self.action_range[0], self.action_range[1])
 
     def _draw(self, buffer, batch_size):
@@ -565,6 +633,34 @@ class DIFFSRSACAgent(SACAgent):
         # diffsrsac_agent.py:229-239: the regulariser is lambda = 0; 'q2' reports mean(Q1)
         return {"score_loss": d["score_loss"], "q_loss_reg": noreg, "q_loss_noreg": noreg, "q1": d["q1"], "q2": d["q1"],
                 "actor_loss": d["actor_loss"], "alpha_loss": d["alpha_loss"], "alpha": d["alpha"]}
+
+
+def eval_policy(agent, envs, eval_episodes=10):
+    """`utils.util.eval_policy` (utils/util.py:40-57) over a LIST of environment copies stepped in lockstep: all live
+    episodes' observations go through one `agent.select_actions` call per step instead of one launch per environment.
+    `envs` are gym-style (`reset() -> obs`, `step(a) -> obs, reward, done, info`); returns (average return, all returns)
+    over `eval_episodes` episodes, episodes assigned to environments round-robin like the reference's sequential loop."""
+    returns, pending = [], int(eval_episodes)
+    live = {}
+    for k, env in enumerate(envs):
+        if pending > 0:
+            live[k] = [env.reset(), 0.0]
+            pending -= 1
+    while live:
+        keys = sorted(live)
+        actions = agent.select_actions(np.stack([np.asarray(live[k][0], dtype=np.float32) for k in keys]))
+        for k, a in zip(keys, actions):
+            obs, reward, done, _ = envs[k].step(a)
+            live[k][0] = obs
+            live[k][1] += float(reward)
+            if done:
+                returns.append(live[k][1])
+                if pending > 0:
+                    live[k] = [envs[k].reset(), 0.0]
+                    pending -= 1
+                else:
+                    del live[k]
+    return float(np.mean(returns)), returns
 
 
 AGENTS = {"sac": SACAgent, "ctrlsac": CTRLSACAgent, "vlsac": VLSACAgent, "spedersac": SPEDERSACAgent,

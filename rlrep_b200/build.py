@@ -86,12 +86,14 @@ def build(force: bool = False, verbose: bool = False) -> Path:
                     raise RuntimeError(f"nvcc failed on {src.name}")
     objs = [str(OBJ / (s.stem + ".o")) for s in sources]
     if force or jobs or not LIB.exists():
-        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(LIB), *objs,
+        tmp = LIB.with_suffix(".so.tmp")  # link beside the target, then rename: a reader never sees a half-written library
+        cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", str(tmp), *objs,
                "-cudart", "static", "-Xlinker", "--no-undefined", "-lpthread", "-ldl", "-lrt"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)
             raise RuntimeError("link failed")
+        os.replace(tmp, LIB)
     return LIB
 
 

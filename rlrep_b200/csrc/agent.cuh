@@ -13,6 +13,7 @@
 
 #include "common.cuh"
 #include "gemm.cuh"
+#include "gemm_chain.cuh"
 #include "kernels.cuh"
 
 namespace rlrep {
@@ -224,7 +225,22 @@ class GemmRunner {
   // chains run on two streams, 1.0 elsewhere.  Part of the plan-cache key.
   void set_sm_share(double share) { sm_share_ = share; }
 
+  // GEMM chains (gemm_chain.cuh): between begin_chain(s) and end_chain() every run() is RECORDED instead of launched --
+  // whatever stream it names -- and end_chain() executes the recorded DAG as one persistent kernel on `s` (dependencies are
+  // inferred from the operands' addresses; the program is built on first use and cached by GEMM sequence).  A GEMM that
+  // cannot join a chain (CUDA-core shapes) closes the chain recorded so far and runs on `s` in program order.  Callers
+  // must not launch kernels that consume a recorded GEMM's output before end_chain().
+  bool chains_enabled() const { return prec_ == PREC_TF32 && chains_on_; }
+  void begin_chain(cudaStream_t s);
+  void end_chain();
+
  private:
+  void flush_chain();
+  bool chains_on_ = true;
+  bool recording_ = false;
+  cudaStream_t chain_stream_ = nullptr;
+  std::vector<GemmArgs> pending_;
+  std::vector<std::unique_ptr<GemmChain>> chains_;
   Precision prec_ = PREC_TF32;
   double sm_share_ = 1.0;
   float* ws_ = nullptr;
@@ -303,6 +319,8 @@ class Agent {
   virtual const std::vector<std::string>& metric_names() const = 0;
   virtual std::vector<ParamGroup*> groups() = 0;
   virtual void act(const float* state_host, const float* eps_host, float* action_host) = 0;
+  // `rows` observations [rows, S] (and noise [rows, A] or nullptr) -> actions [rows, A]: batched policy evaluation
+  virtual void act_batch(const float* states_host, const float* eps_host, int rows, float* actions_host) = 0;
   virtual void sync_targets_from_params() = 0;  // target <- param copies (after loading weights)
 
   AgentConfig cfg;

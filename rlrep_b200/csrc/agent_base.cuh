@@ -27,7 +27,8 @@ class SacBase : public Agent {
     if (metrics_host_) cudaFreeHost(metrics_host_);
     if (idx_host_) cudaFreeHost(idx_host_);
     if (eps_host_) cudaFreeHost(eps_host_);
-    if (act_host_) cudaFreeHost(act_host_);
+    if (act_in_host_) cudaFreeHost(act_in_host_);
+    if (act_out_host_) cudaFreeHost(act_out_host_);
   }
 
   void train(Ring& ring, const long long* idx_host, int n_idx, const float* eps_host, int n_eps, float* metrics_host,
@@ -106,20 +107,29 @@ class SacBase : public Agent {
   }
 
   // select_action (sac_agent.py:89-96): eps == nullptr -> tanh(mu), else tanh(mu + std * eps).  Clamping to the
-  // action range is done by the caller (the range belongs to the environment, not to this handle).
+  // action range is done by the caller (the range belongs to the environment, not to this handle).  `rows` observations
+  // are evaluated by ONE kernel launch per chunk of kActRows; the kernel reads them from, and writes the actions to, mapped
+  // pinned host memory, so a call is: memcpy into the staging buffer, one launch, one stream synchronise.
   void act(const float* state_host, const float* eps_host, float* action_host) override {
-    RLREP_CUDA(cudaStreamSynchronize(stream));
-    std::memcpy(act_host_, state_host, S_ * sizeof(float));
-    for (int j = 0; j < A_; ++j) act_host_[S_ + j] = eps_host ? eps_host[j] : 0.f;
-    RLREP_CUDA(cudaMemcpyAsync(act_dev_, act_host_, (S_ + A_) * sizeof(float), cudaMemcpyHostToDevice, stream));
+    act_batch(state_host, eps_host, 1, action_host);
+  }
+  void act_batch(const float* states_host, const float* eps_host, int rows, float* actions_host) override {
+    RLREP_CHECK(rows >= 0 && states_host && actions_host, "bad arguments");
     const Linear l0 = a0_.view(actor_g_), l1 = a1_.view(actor_g_), l2 = a2_.view(actor_g_);
-    linear_fwd(gemm_, stream, 1, Mat{act_dev_, S_}, l0, ACT_ELU, act_h1_, AH_);
-    linear_fwd(gemm_, stream, 1, Mat{act_h1_, AH_}, l1, ACT_ELU, act_h2_, AH_);
-    linear_fwd(gemm_, stream, 1, Mat{act_h2_, AH_}, l2, ACT_NONE, act_head_, 2 * A_);
-    launch_actor_sample(act_head_, 2 * A_, 1, A_, act_dev_ + S_, act_out_, A_, act_logp_, stream);
-    RLREP_CUDA(cudaMemcpyAsync(act_host_, act_out_, A_ * sizeof(float), cudaMemcpyDeviceToHost, stream));
-    RLREP_CUDA(cudaStreamSynchronize(stream));
-    std::memcpy(action_host, act_host_, A_ * sizeof(float));
+    const int W = S_ + A_;
+    for (int done = 0; done < rows; done += kActRows) {
+      const int n = std::min(kActRows, rows - done);
+      RLREP_CUDA(cudaStreamSynchronize(stream));  // the staging buffers are reused
+      for (int r = 0; r < n; ++r) {
+        float* dst = act_in_host_ + (size_t)r * W;
+        std::memcpy(dst, states_host + (size_t)(done + r) * S_, S_ * sizeof(float));
+        if (eps_host) std::memcpy(dst + S_, eps_host + (size_t)(done + r) * A_, A_ * sizeof(float));
+      }
+      launch_actor_act(act_in_dev_, n, S_, A_, AH_, l0.W, l0.ld, l0.b, l1.W, l1.ld, l1.b, l2.W, l2.ld, l2.b,
+                       eps_host != nullptr, act_out_dev_, stream);
+      RLREP_CUDA(cudaStreamSynchronize(stream));
+      std::memcpy(actions_host + (size_t)done * A_, act_out_host_, (size_t)n * A_ * sizeof(float));
+    }
   }
 
  protected:
@@ -221,16 +231,15 @@ class SacBase : public Agent {
     arena_.want(&cat_next_, (size_t)B_ * LDSA_);  // cat(s', a')   (critic step)
     arena_.want(&cat_pi_, (size_t)B_ * LDSA_);    // cat(s, a_pi)  (actor step)
     arena_.want(&dlogp_, 4);
-    arena_.want(&act_dev_, S_ + A_);
-    arena_.want(&act_h1_, AH_);
-    arena_.want(&act_h2_, AH_);
-    arena_.want(&act_head_, 2 * A_);
-    arena_.want(&act_out_, A_);
-    arena_.want(&act_logp_, 4);
     RLREP_CUDA(cudaMallocHost(&metrics_host_, kNumMetrics * sizeof(float)));
     RLREP_CUDA(cudaMallocHost(&idx_host_, (size_t)(n_idx > 0 ? n_idx : 1) * sizeof(long long)));
     RLREP_CUDA(cudaMallocHost(&eps_host_, (size_t)(n_eps > 0 ? n_eps : 1) * sizeof(float)));
-    RLREP_CUDA(cudaMallocHost(&act_host_, (size_t)(S_ + A_) * sizeof(float)));
+    // select_action staging: mapped pinned memory the policy kernel reads / writes directly
+    RLREP_CUDA(cudaHostAlloc(&act_in_host_, (size_t)kActRows * (S_ + A_) * sizeof(float), cudaHostAllocMapped));
+    RLREP_CUDA(cudaHostAlloc(&act_out_host_, (size_t)kActRows * A_ * sizeof(float), cudaHostAllocMapped));
+    std::memset(act_in_host_, 0, (size_t)kActRows * (S_ + A_) * sizeof(float));
+    RLREP_CUDA(cudaHostGetDevicePointer(&act_in_dev_, act_in_host_, 0));
+    RLREP_CUDA(cudaHostGetDevicePointer(&act_out_dev_, act_out_host_, 0));
   }
 
   void finish_setup(size_t gemm_ws_floats) {
@@ -260,6 +269,35 @@ class SacBase : public Agent {
     linear_fwd(gemm_, s, B_, Mat{h2, AH_}, l2, ACT_NONE, hd, LDH_);
     launch_actor_sample(hd, LDH_, B_, A_, eps, cat_buf + S_, LDSA_, logp_out, s, obs.p, obs.ld, S_);
     return Mat{cat_buf, LDSA_};
+  }
+  // The two halves of actor_forward_cat for callers that run the trunk GEMMs of several networks as one GEMM chain.
+  void actor_trunk(Mat obs, int set, cudaStream_t s) {
+    const Linear l0 = a0_.view(actor_g_), l1 = a1_.view(actor_g_), l2 = a2_.view(actor_g_);
+    float* h1 = set == 0 ? ah1_ : bh1_;
+    float* h2 = set == 0 ? ah2_ : bh2_;
+    float* hd = set == 0 ? head_ : bhead_;
+    linear_fwd(gemm_, s, B_, obs, l0, ACT_ELU, h1, AH_);
+    linear_fwd(gemm_, s, B_, Mat{h1, AH_}, l1, ACT_ELU, h2, AH_);
+    linear_fwd(gemm_, s, B_, Mat{h2, AH_}, l2, ACT_NONE, hd, LDH_);
+  }
+  Mat actor_sample_cat(Mat obs, const float* eps, float* cat_buf, float* logp_out, int set, cudaStream_t s) {
+    launch_actor_sample(set == 0 ? head_ : bhead_, LDH_, B_, A_, eps, cat_buf + S_, LDSA_, logp_out, s, obs.p, obs.ld, S_);
+    return Mat{cat_buf, LDSA_};
+  }
+  // actor_backward with the five GEMMs as one chain on the main stream (no aux branches)
+  void actor_backward_chained(Mat obs, const float* eps) {
+    const Linear l0 = a0_.view(actor_g_), l1 = a1_.view(actor_g_), l2 = a2_.view(actor_g_);
+    launch_actor_sample_bwd(head_, LDH_, B_, A_, eps, dsa_ + S_, LDSA_, dlogp_, dhead_, LDH_, stream);
+    gemm_.begin_chain(stream);
+    linear_wgrad(gemm_, stream, B_, Mat{dhead_, LDH_}, Mat{ah2_, AH_}, l2, Mat(), 0, false);
+    linear_dgrad(gemm_, stream, B_, Mat{dhead_, LDH_}, l2, DACT_ELU_OUT, Mat{ah2_, AH_}, dah2_, AH_);
+    linear_wgrad(gemm_, stream, B_, Mat{dah2_, AH_}, Mat{ah1_, AH_}, l1, Mat(), 0, false);
+    linear_dgrad(gemm_, stream, B_, Mat{dah2_, AH_}, l1, DACT_ELU_OUT, Mat{ah1_, AH_}, dah1_, AH_);
+    linear_wgrad(gemm_, stream, B_, Mat{dah1_, AH_}, obs, l0, Mat(), 0, false);
+    gemm_.end_chain();
+    const ColJob jobs[3] = {bias_job(B_, Mat{dhead_, LDH_}, l2), bias_job(B_, Mat{dah2_, AH_}, l1),
+                            bias_job(B_, Mat{dah1_, AH_}, l0)};
+    launch_colreduce_multi(jobs, 3, stream);
   }
   // Where the first layer of a network fed with cat(obs, action) writes its input gradient so that actor_backward finds
   // d(action) at dsa_[:, S:S+A].  On the tensor-core path the dgrad runs over ALL (padded) input columns -- N must be a
@@ -325,6 +363,13 @@ class SacBase : public Agent {
     const char* e = std::getenv("RLREP_USE_AUX");
     return e ? std::atoi(e) != 0 : true;
   }();
+  // Batches up to this size run their GEMM groups as chains (gemm_chain.cuh); larger batches are throughput- rather than
+  // latency-bound and keep one kernel per GEMM.
+  int chain_max_batch_ = [] {
+    const char* e = std::getenv("RLREP_CHAIN_MAX_B");
+    return e ? std::atoi(e) : 512;
+  }();
+  bool chained() const { return gemm_.chains_enabled() && B_ <= chain_max_batch_; }
   std::vector<cudaEvent_t> events_;
   size_t ev_next_ = 0;
   bool serial_ = false;
@@ -346,8 +391,8 @@ class SacBase : public Agent {
   float *ah1_ = nullptr, *ah2_ = nullptr, *head_ = nullptr, *logp_ = nullptr;
   float *dhead_ = nullptr, *dah2_ = nullptr, *dah1_ = nullptr, *dsa_ = nullptr, *dlogp_ = nullptr;
   float *cat_next_ = nullptr, *cat_pi_ = nullptr, *bh1_ = nullptr, *bh2_ = nullptr, *bhead_ = nullptr;
-  float *act_dev_ = nullptr, *act_h1_ = nullptr, *act_h2_ = nullptr, *act_head_ = nullptr, *act_out_ = nullptr,
-        *act_logp_ = nullptr, *act_host_ = nullptr;
+  static constexpr int kActRows = 1024;  // observations per select_action launch
+  float *act_in_host_ = nullptr, *act_out_host_ = nullptr, *act_in_dev_ = nullptr, *act_out_dev_ = nullptr;
 };
 
 }  // namespace rlrep

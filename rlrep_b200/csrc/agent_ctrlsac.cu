@@ -109,12 +109,19 @@ class CtrlSacAgent final : public SacBase {
   void update(Ring& ring) override {
     begin_update();
     launch_tick(ctl, base_tick(), stream);
+    const bool chain = chained();
     for (int k = 0; k < K_; ++k) {
       launch_gather(ring.data, R_ / 4, idx_dev_ + (size_t)k * B_, B_, batch_, stream);
-      feature_step(k);
+      if (chain) feature_step_chained(k);
+      else feature_step(k);
     }
-    critic_step();
-    actor_step();
+    if (chain) {
+      critic_step_chained();
+      actor_step_chained();
+    } else {
+      critic_step();
+      actor_step();
+    }
   }
 
  private:
@@ -223,6 +230,130 @@ class CtrlSacAgent final : public SacBase {
     launch_adam_polyak(feat_g_.p, feat_g_.g, feat_g_.m, feat_g_.v, feat_g_.n, &ctl->feat[k],
                        cfg.use_feature_target ? feat_g_.target : nullptr, feat_g_.n_target, cfg.feature_tau, nullptr,
                        s0);
+  }
+
+  // ---------------------------------------------------------------------------------------------- chained variants
+  // Same arithmetic, same kernels for everything that is not a GEMM; every group of GEMMs between two elementwise kernels
+  // runs as ONE persistent chain kernel (gemm_chain.cuh) on the main stream instead of one launch per GEMM on up to four
+  // streams: 57 launches per update instead of 149, and a dependent GEMM starts when its input tiles are complete.
+  void feature_step_chained(int k) {  // ctrlsac_agent.py:213-251
+    const Linear l1 = p1_.view(feat_g_), l2 = p2_.view(feat_g_), l3 = p3_.view(feat_g_);
+    const Linear n1 = m1_.view(feat_g_), n2 = m2_.view(feat_g_), n3 = m3_.view(feat_g_);
+    const Linear th = th_.view(feat_g_);
+    const float inv_b = 1.f / (float)B_;
+    cudaStream_t s0 = stream;
+    gemm_.begin_chain(s0);
+    phi_forward(s0, sa(), Mat(), 0, zphi_, h1_, h2_);
+    linear_fwd(gemm_, s0, B_, s2(), n1, ACT_ELU, g1_, H_);
+    linear_fwd(gemm_, s0, B_, Mat{g1_, H_}, n2, ACT_ELU, g2_, H_);
+    linear_fwd(gemm_, s0, B_, Mat{g2_, H_}, n3, ACT_TANH, zmu_, D_);
+    {  // logits[i, j] = <phi_i, mu_j>
+      GemmArgs a;
+      a.M = B_; a.N = B_; a.K = D_;
+      a.A = zphi_; a.lda = D_;
+      a.B = zmu_; a.ldb = D_;
+      a.C = logits_; a.ldc = B_;
+      gemm_.run(a, s0);
+    }
+    gemm_.end_chain();
+    launch_ce_rows(logits_, B_, B_, B_, 0, inv_b, loss_rows_, s0);  // logits_ now holds dL/dlogits
+    launch_rowdot(zphi_, D_, B_, D_, th.W, th.b, rpred_, s0);
+    launch_feature_loss_finalize(loss_rows_, B_, rpred_, reward(), R_, inv_b, drp_, metrics_dev_ + 0, s0);
+    gemm_.begin_chain(s0);
+    {  // d z_phi = G mu + drp (x) theta.w
+      GemmArgs a;
+      a.M = B_; a.N = D_; a.K = B_;
+      a.A = logits_; a.lda = B_;
+      a.B = zmu_; a.ldb = D_; a.b_mn = true;
+      a.C = dzphi_; a.ldc = D_;
+      a.epi.r1_u = drp_; a.epi.r1_v = th.W;
+      gemm_.run(a, s0);
+    }
+    {  // d (pre-tanh mu) = (G^T phi) * (1 - mu^2)
+      GemmArgs a;
+      a.M = B_; a.N = D_; a.K = B_;
+      a.A = logits_; a.lda = B_; a.a_mn = true;
+      a.B = zphi_; a.ldb = D_; a.b_mn = true;
+      a.C = dzmu_; a.ldc = D_;
+      a.epi.dact = DACT_TANH_OUT; a.epi.aux = zmu_; a.epi.ld_aux = D_;
+      gemm_.run(a, s0);
+    }
+    linear_dgrad(gemm_, s0, B_, Mat{dzphi_, D_}, l3, DACT_ELU_OUT, Mat{h2_, H_}, dh2_, H_);
+    linear_dgrad(gemm_, s0, B_, Mat{dzmu_, D_}, n3, DACT_ELU_OUT, Mat{g2_, H_}, dg2_, H_);
+    linear_wgrad(gemm_, s0, B_, Mat{dzphi_, D_}, Mat{h2_, H_}, l3, Mat(), 0, false);
+    linear_wgrad(gemm_, s0, B_, Mat{dzmu_, D_}, Mat{g2_, H_}, n3, Mat(), 0, false);
+    linear_dgrad(gemm_, s0, B_, Mat{dh2_, H_}, l2, DACT_ELU_OUT, Mat{h1_, H_}, dh1_, H_);
+    linear_dgrad(gemm_, s0, B_, Mat{dg2_, H_}, n2, DACT_ELU_OUT, Mat{g1_, H_}, dg1_, H_);
+    linear_wgrad(gemm_, s0, B_, Mat{dh2_, H_}, Mat{h1_, H_}, l2, Mat(), 0, false);
+    linear_wgrad(gemm_, s0, B_, Mat{dg2_, H_}, Mat{g1_, H_}, n2, Mat(), 0, false);
+    linear_wgrad(gemm_, s0, B_, Mat{dh1_, H_}, sa(), l1, Mat(), 0, false);
+    linear_wgrad(gemm_, s0, B_, Mat{dg1_, H_}, s2(), n1, Mat(), 0, false);
+    gemm_.end_chain();
+    {
+      ColJob jobs[8] = {bias_job(B_, Mat{dzphi_, D_}, l3), bias_job(B_, Mat{dh2_, H_}, l2),
+                        bias_job(B_, Mat{dh1_, H_}, l1), ColJob{zphi_, drp_, th.dW, D_, B_, D_},  // d theta.w
+                        ColJob{drp_, nullptr, th.db, 1, B_, 1},                                   // d theta.b
+                        bias_job(B_, Mat{dzmu_, D_}, n3), bias_job(B_, Mat{dg2_, H_}, n2),
+                        bias_job(B_, Mat{dg1_, H_}, n1)};
+      launch_colreduce_multi(jobs, 8, s0);
+    }
+    launch_adam_polyak(feat_g_.p, feat_g_.g, feat_g_.m, feat_g_.v, feat_g_.n, &ctl->feat[k],
+                       cfg.use_feature_target ? feat_g_.target : nullptr, feat_g_.n_target, cfg.feature_tau, nullptr,
+                       s0);
+  }
+
+  void critic_step_chained() {  // ctrlsac_agent.py:257-293
+    cudaStream_t s0 = stream;
+    const float* eps_next = eps_dev_;
+    const float* eps_pi = eps_dev_ + (size_t)B_ * A_;
+    const Linear l14t = c14_.view(crit_g_, true), l14 = c14_.view(crit_g_), l2 = c2_.view(crit_g_), l5 = c5_.view(crit_g_);
+    const Linear l2t = c2_.view(crit_g_, true), l5t = c5_.view(crit_g_, true);
+    // a' ~ pi(s') for the TD target and a_pi ~ pi(s) for the actor step (reads nothing the critic step writes)
+    gemm_.begin_chain(s0);
+    actor_trunk(s2(), /*set=*/1, s0);
+    actor_trunk(Mat{batch_, R_}, /*set=*/0, s0);
+    gemm_.end_chain();
+    const Mat s2a = actor_sample_cat(s2(), eps_next, cat_next_, logp2_, 1, s0);
+    const Mat spi = actor_sample_cat(Mat{batch_, R_}, eps_pi, cat_pi_, logp_, 0, s0);
+    gemm_.begin_chain(s0);
+    phi_forward(s0, s2a, Mat(), 0, zmu_, h1_, h2_);  // frozen_phi_target(s', a'); zmu_ is free after the feature loop
+    linear_fwd(gemm_, s0, B_, Mat{zmu_, D_}, l14t, ACT_ELU, hid_t_, 2 * H_);
+    phi_forward(s0, sa(), Mat(), 0, zphi_, hb1_, hb2_);  // frozen_phi_target(s, a)
+    linear_fwd(gemm_, s0, B_, Mat{zphi_, D_}, l14, ACT_ELU, hid_, 2 * H_);
+    phi_forward(s0, spi, Mat(), 0, zpi_, hc1_, hc2_);  // frozen_phi(s, a_pi), consumed by the actor step
+    gemm_.end_chain();
+    launch_rowdot_pair(RowDotJob{hid_t_, l2t.W, l2t.b, nq1_, 2 * H_, H_}, RowDotJob{hid_t_ + H_, l5t.W, l5t.b, nq2_, 2 * H_, H_}, B_, s0);
+    launch_rowdot_pair(RowDotJob{hid_, l2.W, l2.b, q1_, 2 * H_, H_}, RowDotJob{hid_ + H_, l5.W, l5.b, q2_, 2 * H_, H_}, B_, s0);
+    launch_td_critic_loss(reward(), done(), R_, nq1_, nq2_, logp2_, q1_, q2_, B_, cfg.discount, ctl, dq1_, dq2_,
+                          metrics_dev_ + 3, s0);
+    critic_heads_backward_to_hidden();
+    {
+      ColJob jobs[5] = {ColJob{hid_, dq1_, l2.dW, 2 * H_, B_, H_}, ColJob{dq1_, nullptr, l2.db, 1, B_, 1},
+                        ColJob{hid_ + H_, dq2_, l5.dW, 2 * H_, B_, H_}, ColJob{dq2_, nullptr, l5.db, 1, B_, 1},
+                        bias_job(B_, Mat{dhid_, 2 * H_}, l14)};
+      launch_colreduce_multi(jobs, 5, s0);
+    }
+    linear_wgrad(gemm_, s0, B_, Mat{dhid_, 2 * H_}, Mat{zphi_, D_}, l14, Mat(), 0, false);
+    launch_adam_polyak(crit_g_.p, crit_g_.g, crit_g_.m, crit_g_.v, crit_g_.n, &ctl->critic, crit_g_.target,
+                       crit_g_.n_target, cfg.tau, &ctl->polyak_critic, s0);
+  }
+
+  void actor_step_chained() {  // ctrlsac_agent.py:295-325
+    const float* eps = eps_dev_ + (size_t)B_ * A_;
+    critic_forward(stream, zpi_, false, hid_, q1_, q2_);  // the UPDATED critic on frozen_phi(s, a_pi)
+    launch_actor_alpha_loss(q1_, q2_, logp_, B_, (float)(-A_), cfg.learn_alpha, ctl, dq1_, dq2_, dlogp_,
+                            metrics_dev_ + 7, stream);
+    const Linear l14 = c14_.view(crit_g_);
+    const Linear l1 = p1_.view(feat_g_), l2 = p2_.view(feat_g_), l3 = p3_.view(feat_g_);
+    critic_heads_backward_to_hidden();
+    gemm_.begin_chain(stream);
+    linear_dgrad(gemm_, stream, B_, Mat{dhid_, 2 * H_}, l14, DACT_NONE, Mat(), dzphi_, D_);
+    linear_dgrad(gemm_, stream, B_, Mat{dzphi_, D_}, l3, DACT_ELU_OUT, Mat{hc2_, H_}, dh2_, H_);
+    linear_dgrad(gemm_, stream, B_, Mat{dh2_, H_}, l2, DACT_ELU_OUT, Mat{hc1_, H_}, dh1_, H_);
+    dgrad_to_action(Mat{dh1_, H_}, l1);
+    gemm_.end_chain();
+    actor_backward_chained(Mat{batch_, R_}, eps);
+    actor_adam();
   }
 
   // twin heads on features z: hid = elu(z [l1|l4]^T + b), q1 = hid[:, :H] . l2, q2 = hid[:, H:] . l5

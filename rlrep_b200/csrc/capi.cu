@@ -6,6 +6,7 @@
 #include <vector>
 
 #include "agent.cuh"
+#include "gemm_chain.cuh"
 #include "comm.cuh"
 #include "common.cuh"
 #include "conv.cuh"
@@ -53,11 +54,34 @@ __global__ void null_pdl_kernel(float* p) {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
 
+// Every handle remembers the CUDA device it was created on, and every entry point that takes a handle runs on that device
+// whatever the calling thread's current device is (worker threads of a population start on device 0): scoped
+// cudaSetDevice, restored on exit.
+static int current_device() {
+  int d = 0;
+  cudaGetDevice(&d);
+  return d;
+}
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int want) {
+    if (want < 0) return;
+    int cur = 0;
+    if (cudaGetDevice(&cur) == cudaSuccess && cur != want && cudaSetDevice(want) == cudaSuccess) prev = cur;
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
+#define RLREP_API_BEGIN_ON(h) RLREP_API_BEGIN DeviceGuard _device_guard((h) != nullptr ? (h)->device : -1);
+
 struct rlrep_ring {
+  int device = current_device();
   std::unique_ptr<Ring> impl;
 };
 
 struct rlrep_comm {
+  int device = current_device();
   std::unique_ptr<Comm> impl;
 };
 
@@ -68,6 +92,7 @@ struct TensorRef {
 };
 
 struct rlrep_agent {
+  int device = current_device();
   std::unique_ptr<Agent> impl;
   std::vector<TensorRef> tensors;
   cudaStream_t owned_stream = nullptr;  // created when the caller passed the (uncapturable) legacy default stream
@@ -77,6 +102,13 @@ static void index_tensors(rlrep_agent* a) {
   a->tensors.clear();
   for (ParamGroup* g : a->impl->groups()) {
     for (const ParamTensor& t : g->tensors) a->tensors.push_back({t.name, g->p + t.offset, t.rows, t.cols, t.ld});
+    // Adam moments under "optim.m/<name>" / "optim.v/<name>": with rlrep_agent_get/set_optim_state they make a checkpoint
+    // resume bit-identically to an uninterrupted run (torch.optim.Adam's exp_avg / exp_avg_sq of the same parameter)
+    if (g->m && g->v)
+      for (const ParamTensor& t : g->tensors) {
+        a->tensors.push_back({"optim.m/" + t.name, g->m + t.offset, t.rows, t.cols, t.ld});
+        a->tensors.push_back({"optim.v/" + t.name, g->v + t.offset, t.rows, t.cols, t.ld});
+      }
     if (g->target) {
       for (const ParamTensor& t : g->tensors) {
         if (t.offset >= g->n_target) continue;
@@ -111,6 +143,60 @@ int rlrep_gemm(void* stream, int path, int M, int N, int K, const float* A, int 
   } else {
     launch_simt(g, st);
   }
+  RLREP_API_END
+}
+
+namespace {
+thread_local std::vector<GemmArgs> g_chain_seq;
+}
+
+int rlrep_gemm_chain_set_debug(unsigned long long* dev) {
+  RLREP_API_BEGIN
+  set_chain_debug_buffer(dev);
+  RLREP_API_END
+}
+
+int rlrep_gemm_chain_begin(void) {
+  RLREP_API_BEGIN
+  g_chain_seq.clear();
+  RLREP_API_END
+}
+
+int rlrep_gemm_chain_add(int M, int N, int K, const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn,
+                         float* C, int ldc, const rlrep_epilogue* epi) {
+  RLREP_API_BEGIN
+  GemmArgs g;
+  g.M = M; g.N = N; g.K = K;
+  g.A = A; g.lda = lda; g.a_mn = a_mn != 0;
+  g.B = B; g.ldb = ldb; g.b_mn = b_mn != 0;
+  g.C = C; g.ldc = ldc;
+  g.epi = to_epilogue(epi);
+  RLREP_CHECK(chain_eligible(g), "operands violate the tensor-core path's constraints (see rlrep_gemm, path 0)");
+  g_chain_seq.push_back(g);
+  RLREP_API_END
+}
+
+int rlrep_gemm_chain_run(void* stream, int bn, int split_k, int iters, float* ms_out, int* levels_out) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(!g_chain_seq.empty() && iters >= 1, "empty chain");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GemmChain chain;
+  chain.build(g_chain_seq, bn, split_k);
+  if (levels_out) *levels_out = chain.levels();
+  cudaEvent_t e0, e1;
+  RLREP_CUDA(cudaEventCreate(&e0));
+  RLREP_CUDA(cudaEventCreate(&e1));
+  chain.launch(st);  // the first launch also warms the instruction cache; it is part of the result, not of the timing
+  RLREP_CUDA(cudaEventRecord(e0, st));
+  for (int i = 1; i < iters; ++i) chain.launch(st);
+  RLREP_CUDA(cudaEventRecord(e1, st));
+  RLREP_CUDA(cudaStreamSynchronize(st));
+  float ms = 0.f;
+  RLREP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  if (ms_out) *ms_out = iters > 1 ? ms / (iters - 1) : 0.f;
+  g_chain_seq.clear();
   RLREP_API_END
 }
 
@@ -203,35 +289,35 @@ int rlrep_ring_create(int state_dim, int action_dim, long long capacity, rlrep_r
   RLREP_API_END
 }
 int rlrep_ring_destroy(rlrep_ring* ring) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(ring)
   delete ring;
   RLREP_API_END
 }
 int rlrep_ring_layout(const rlrep_ring* ring, int* record_floats, int* off_action, int* off_reward, int* off_done,
                       int* off_next_state) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(ring)
   const Ring& r = *ring->impl;
   *record_floats = r.R; *off_action = r.off_a; *off_reward = r.off_r; *off_done = r.off_d; *off_next_state = r.off_s2;
   RLREP_API_END
 }
 int rlrep_ring_state(const rlrep_ring* ring, long long* size, long long* ptr, long long* capacity) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(ring)
   *size = ring->impl->size; *ptr = ring->impl->ptr; *capacity = ring->impl->capacity;
   RLREP_API_END
 }
 int rlrep_ring_add_packed(rlrep_ring* ring, const float* rows_host, int n, void* stream) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(ring)
   ring->impl->add_packed(rows_host, n, static_cast<cudaStream_t>(stream));
   RLREP_API_END
 }
 int rlrep_ring_load(rlrep_ring* ring, const void* state, const void* action, const void* next_state,
                     const void* reward, const void* done, long long n, int is_f64, void* stream) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(ring)
   ring->impl->load_columns(state, action, next_state, reward, done, n, is_f64, static_cast<cudaStream_t>(stream));
   RLREP_API_END
 }
 int rlrep_ring_gather(rlrep_ring* ring, const int64_t* idx_host, int B, float* out_dev, void* stream) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(ring)
   ring->impl->gather_from_host_idx(reinterpret_cast<const long long*>(idx_host), B, out_dev,
                                    static_cast<cudaStream_t>(stream));
   RLREP_API_END
@@ -240,6 +326,7 @@ int rlrep_ring_gather(rlrep_ring* ring, const int64_t* idx_host, int B, float* o
 // ------------------------------------------------------------------------------------------------ agents
 // ------------------------------------------------------------------------------------------------ pixel encoder
 struct rlrep_conv_encoder {
+  int device = current_device();
   std::unique_ptr<ConvEncoder> impl;
   cudaStream_t owned_stream = nullptr;
 };
@@ -274,7 +361,7 @@ int rlrep_conv_encoder_create(int batch, int in_channels, int height, int precis
   RLREP_API_END
 }
 int rlrep_conv_encoder_destroy(rlrep_conv_encoder* enc) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(enc)
   if (enc) {
     if (enc->impl) cudaStreamSynchronize(enc->impl->stream());
     enc->impl.reset();
@@ -284,7 +371,7 @@ int rlrep_conv_encoder_destroy(rlrep_conv_encoder* enc) {
   RLREP_API_END
 }
 int rlrep_conv_encoder_read(rlrep_conv_encoder* enc, int layer, int what, float* out_host) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(enc)
   RLREP_CHECK(enc && out_host && layer >= 0 && layer < 4 && what >= 0 && what < 4, "bad argument");
   const Linear l = enc->impl->layer(layer);
   const int k = enc->impl->layer_k(layer);
@@ -302,7 +389,7 @@ int rlrep_conv_encoder_read(rlrep_conv_encoder* enc, int layer, int what, float*
   RLREP_API_END
 }
 int rlrep_conv_encoder_write(rlrep_conv_encoder* enc, int layer, int what, const float* in_host) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(enc)
   RLREP_CHECK(enc && in_host && layer >= 0 && layer < 4 && (what == 0 || what == 1), "bad argument");
   const Linear l = enc->impl->layer(layer);
   const int k = enc->impl->layer_k(layer);
@@ -321,19 +408,19 @@ int rlrep_conv_encoder_write(rlrep_conv_encoder* enc, int layer, int what, const
 }
 int rlrep_conv_encoder_forward(rlrep_conv_encoder* enc, const unsigned char* obs_dev, const int* shifts_dev,
                                float* feat_dev) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(enc)
   RLREP_CHECK(enc && obs_dev && feat_dev, "null argument");
   enc->impl->forward(obs_dev, shifts_dev, feat_dev);
   RLREP_API_END
 }
 int rlrep_conv_encoder_backward(rlrep_conv_encoder* enc, const float* dfeat_dev) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(enc)
   RLREP_CHECK(enc && dfeat_dev, "null argument");
   enc->impl->backward(dfeat_dev);
   RLREP_API_END
 }
 int rlrep_conv_encoder_feature_dim(rlrep_conv_encoder* enc, int* dim) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(enc)
   RLREP_CHECK(enc && dim, "null argument");
   *dim = enc->impl->feature_dim();
   RLREP_API_END
@@ -341,6 +428,7 @@ int rlrep_conv_encoder_feature_dim(rlrep_conv_encoder* enc, int* dim) {
 
 // ------------------------------------------------------------------------------------------------ DrQ-v2 pixel agent
 struct rlrep_drq {
+  int device = current_device();
   std::unique_ptr<DrqV2> impl;
   std::vector<TensorRef> tensors;
   cudaStream_t owned_stream = nullptr;
@@ -376,7 +464,7 @@ int rlrep_drq_create(const rlrep_drq_config* c, void* stream, rlrep_drq** out) {
   RLREP_API_END
 }
 int rlrep_drq_destroy(rlrep_drq* drq) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(drq)
   if (drq) {
     if (drq->impl) cudaStreamSynchronize(drq->impl->stream());
     drq->impl.reset();
@@ -386,12 +474,12 @@ int rlrep_drq_destroy(rlrep_drq* drq) {
   RLREP_API_END
 }
 int rlrep_drq_num_tensors(rlrep_drq* drq, int* n) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(drq)
   *n = (int)drq->tensors.size();
   RLREP_API_END
 }
 int rlrep_drq_tensor_info(rlrep_drq* drq, int i, const char** name, float** ptr_dev, int* rows, int* cols) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(drq)
   RLREP_CHECK(i >= 0 && i < (int)drq->tensors.size(), "tensor index out of range");
   const TensorRef& t = drq->tensors[i];
   if (name) *name = t.name.c_str();
@@ -401,7 +489,7 @@ int rlrep_drq_tensor_info(rlrep_drq* drq, int i, const char** name, float** ptr_
   RLREP_API_END
 }
 int rlrep_drq_tensor_read(rlrep_drq* drq, int i, float* out_host) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(drq)
   RLREP_CHECK(i >= 0 && i < (int)drq->tensors.size(), "tensor index out of range");
   const TensorRef& t = drq->tensors[i];
   cudaStream_t st = drq->impl->stream();
@@ -411,7 +499,7 @@ int rlrep_drq_tensor_read(rlrep_drq* drq, int i, float* out_host) {
   RLREP_API_END
 }
 int rlrep_drq_tensor_write(rlrep_drq* drq, int i, const float* in_host) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(drq)
   RLREP_CHECK(i >= 0 && i < (int)drq->tensors.size(), "tensor index out of range");
   const TensorRef& t = drq->tensors[i];
   cudaStream_t st = drq->impl->stream();
@@ -421,33 +509,33 @@ int rlrep_drq_tensor_write(rlrep_drq* drq, int i, const float* in_host) {
   RLREP_API_END
 }
 int rlrep_drq_sync_targets(rlrep_drq* drq) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(drq)
   drq->impl->sync_targets_from_params();
   RLREP_API_END
 }
 int rlrep_drq_update(rlrep_drq* drq, const unsigned char* img, const float* action, const float* reward,
                      const float* discount, const unsigned char* next_img, const int* shifts, const float* eps,
                      float stddev, float* metrics_host) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(drq)
   RLREP_CHECK(drq && img && action && reward && discount && next_img && shifts && eps && metrics_host, "null argument");
   drq->impl->update(img, action, reward, discount, next_img, shifts, eps, stddev, metrics_host);
   RLREP_API_END
 }
 int rlrep_drq_act(rlrep_drq* drq, const unsigned char* obs_host, const float* eps_host, float stddev, float* action_host) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(drq)
   RLREP_CHECK(drq && obs_host && action_host, "null argument");
   drq->impl->act(obs_host, eps_host, stddev, action_host);
   RLREP_API_END
 }
 int rlrep_drq_update_resident(rlrep_drq* drq, int n_steps, float stddev, float* total_ms) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(drq)
   RLREP_CHECK(drq && total_ms, "null argument");
   *total_ms = drq->impl->update_resident(n_steps, stddev);
   RLREP_API_END
 }
 int rlrep_drq_profile_update(rlrep_drq* drq, float stddev, int max_entries, const char** names, float* ms, double* bytes,
                              double* flops, int* n_entries) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(drq)
   RLREP_CHECK(drq && n_entries && (max_entries == 0 || (names && ms)), "null argument");
   std::vector<ProfileEntry> prof = drq->impl->profile_update(stddev);
   const int n = (int)std::min<size_t>(prof.size(), (size_t)max_entries);
@@ -461,13 +549,14 @@ int rlrep_drq_profile_update(rlrep_drq* drq, float stddev, int max_entries, cons
   RLREP_API_END
 }
 int rlrep_drq_last_launches(rlrep_drq* drq, int* launches) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(drq)
   *launches = drq->impl->last_launches;
   RLREP_API_END
 }
 
 // ------------------------------------------------------------------------------------------------ muLV-Rep DrQ-v2 pixel agent
 struct rlrep_mulv {
+  int device = current_device();
   std::unique_ptr<MulvDrq> impl;
   std::vector<TensorRef> tensors;
   cudaStream_t owned_stream = nullptr;
@@ -504,7 +593,7 @@ int rlrep_mulv_create(const rlrep_mulv_config* c, void* stream, rlrep_mulv** out
   RLREP_API_END
 }
 int rlrep_mulv_destroy(rlrep_mulv* h) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(h)
   if (h) {
     if (h->impl) cudaStreamSynchronize(h->impl->stream());
     h->impl.reset();
@@ -514,13 +603,13 @@ int rlrep_mulv_destroy(rlrep_mulv* h) {
   RLREP_API_END
 }
 int rlrep_mulv_num_tensors(rlrep_mulv* h, int* n) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(h)
   RLREP_CHECK(h && n, "null argument");
   *n = (int)h->tensors.size();
   RLREP_API_END
 }
 int rlrep_mulv_tensor_info(rlrep_mulv* h, int i, const char** name, float** ptr_dev, int* rows, int* cols) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(h)
   RLREP_CHECK(h && i >= 0 && i < (int)h->tensors.size(), "tensor index out of range");
   const TensorRef& t = h->tensors[i];
   if (name) *name = t.name.c_str();
@@ -530,7 +619,7 @@ int rlrep_mulv_tensor_info(rlrep_mulv* h, int i, const char** name, float** ptr_
   RLREP_API_END
 }
 int rlrep_mulv_tensor_read(rlrep_mulv* h, int i, float* out_host) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(h)
   RLREP_CHECK(h && out_host && i >= 0 && i < (int)h->tensors.size(), "tensor index out of range");
   const TensorRef& t = h->tensors[i];
   cudaStream_t st = h->impl->stream();
@@ -540,7 +629,7 @@ int rlrep_mulv_tensor_read(rlrep_mulv* h, int i, float* out_host) {
   RLREP_API_END
 }
 int rlrep_mulv_tensor_write(rlrep_mulv* h, int i, const float* in_host) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(h)
   RLREP_CHECK(h && in_host && i >= 0 && i < (int)h->tensors.size(), "tensor index out of range");
   const TensorRef& t = h->tensors[i];
   cudaStream_t st = h->impl->stream();
@@ -550,7 +639,7 @@ int rlrep_mulv_tensor_write(rlrep_mulv* h, int i, const float* in_host) {
   RLREP_API_END
 }
 int rlrep_mulv_sync_targets(rlrep_mulv* h) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(h)
   RLREP_CHECK(h, "null argument");
   h->impl->sync_targets_from_params();
   RLREP_API_END
@@ -559,27 +648,27 @@ int rlrep_mulv_update(rlrep_mulv* h, const unsigned char* img, const float* acti
                       const float* discount, const unsigned char* next_img, const unsigned char* img_step1,
                       const int* shifts, const float* eps_z, const float* eps_act, const float* noise, float stddev,
                       float* metrics_host) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(h)
   RLREP_CHECK(h && img && action && reward && discount && next_img && img_step1 && shifts && eps_z && eps_act && noise &&
                   metrics_host, "null argument");
   h->impl->update(img, action, reward, discount, next_img, img_step1, shifts, eps_z, eps_act, noise, stddev, metrics_host);
   RLREP_API_END
 }
 int rlrep_mulv_act(rlrep_mulv* h, const unsigned char* obs_host, const float* eps_host, float stddev, float* action_host) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(h)
   RLREP_CHECK(h && obs_host && action_host, "null argument");
   h->impl->act(obs_host, eps_host, stddev, action_host);
   RLREP_API_END
 }
 int rlrep_mulv_update_resident(rlrep_mulv* h, int n_steps, float stddev, float* total_ms) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(h)
   RLREP_CHECK(h && total_ms, "null argument");
   *total_ms = h->impl->update_resident(n_steps, stddev);
   RLREP_API_END
 }
 int rlrep_mulv_profile_update(rlrep_mulv* h, float stddev, int max_entries, const char** names, float* ms, double* bytes,
                               double* flops, int* n_entries) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(h)
   RLREP_CHECK(h && n_entries && (max_entries == 0 || (names && ms)), "null argument");
   std::vector<ProfileEntry> prof = h->impl->profile_update(stddev);
   const int n = (int)std::min<size_t>(prof.size(), (size_t)max_entries);
@@ -593,7 +682,7 @@ int rlrep_mulv_profile_update(rlrep_mulv* h, float stddev, int max_entries, cons
   RLREP_API_END
 }
 int rlrep_mulv_last_launches(rlrep_mulv* h, int* launches) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(h)
   RLREP_CHECK(h && launches, "null argument");
   *launches = h->impl->last_launches;
   RLREP_API_END
@@ -601,6 +690,7 @@ int rlrep_mulv_last_launches(rlrep_mulv* h, int* launches) {
 
 // ------------------------------------------------------------------------------------------------ latent Diff-SR DrQ-v2 (DRAFT)
 struct rlrep_ldiff {
+  int device = current_device();
   std::unique_ptr<LatentDiffSR> impl;
   std::vector<TensorRef> tensors;
   cudaStream_t owned_stream = nullptr;
@@ -645,7 +735,7 @@ int rlrep_ldiff_create(const rlrep_ldiff_config* c, void* stream, rlrep_ldiff** 
   RLREP_API_END
 }
 int rlrep_ldiff_destroy(rlrep_ldiff* h) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(h)
   if (h) {
     if (h->impl) cudaStreamSynchronize(h->impl->stream());
     h->impl.reset();
@@ -655,13 +745,13 @@ int rlrep_ldiff_destroy(rlrep_ldiff* h) {
   RLREP_API_END
 }
 int rlrep_ldiff_num_tensors(rlrep_ldiff* h, int* n) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(h)
   RLREP_CHECK(h && n, "null argument");
   *n = (int)h->tensors.size();
   RLREP_API_END
 }
 int rlrep_ldiff_tensor_info(rlrep_ldiff* h, int i, const char** name, float** ptr_dev, int* rows, int* cols) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(h)
   RLREP_CHECK(h && i >= 0 && i < (int)h->tensors.size(), "tensor index out of range");
   const TensorRef& t = h->tensors[i];
   if (name) *name = t.name.c_str();
@@ -671,7 +761,7 @@ int rlrep_ldiff_tensor_info(rlrep_ldiff* h, int i, const char** name, float** pt
   RLREP_API_END
 }
 int rlrep_ldiff_tensor_read(rlrep_ldiff* h, int i, float* out_host) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(h)
   RLREP_CHECK(h && out_host && i >= 0 && i < (int)h->tensors.size(), "tensor index out of range");
   const TensorRef& t = h->tensors[i];
   cudaStream_t st = h->impl->stream();
@@ -681,7 +771,7 @@ int rlrep_ldiff_tensor_read(rlrep_ldiff* h, int i, float* out_host) {
   RLREP_API_END
 }
 int rlrep_ldiff_tensor_write(rlrep_ldiff* h, int i, const float* in_host) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(h)
   RLREP_CHECK(h && in_host && i >= 0 && i < (int)h->tensors.size(), "tensor index out of range");
   const TensorRef& t = h->tensors[i];
   cudaStream_t st = h->impl->stream();
@@ -691,13 +781,13 @@ int rlrep_ldiff_tensor_write(rlrep_ldiff* h, int i, const float* in_host) {
   RLREP_API_END
 }
 int rlrep_ldiff_sync_targets(rlrep_ldiff* h) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(h)
   RLREP_CHECK(h, "null argument");
   h->impl->sync_targets_from_params();
   RLREP_API_END
 }
 int rlrep_ldiff_update(rlrep_ldiff* h, const rlrep_ldiff_inputs* in, float* metrics_host) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(h)
   RLREP_CHECK(h && in && metrics_host, "null argument");
   LatentDiffSR::Inputs x;
   x.frames = in->frames; x.next_frames = in->next_frames; x.shifts = in->shifts; x.next_shifts = in->next_shifts;
@@ -710,7 +800,7 @@ int rlrep_ldiff_update(rlrep_ldiff* h, const rlrep_ldiff_inputs* in, float* metr
   RLREP_API_END
 }
 int rlrep_ldiff_last_launches(rlrep_ldiff* h, int* launches) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(h)
   RLREP_CHECK(h && launches, "null argument");
   *launches = h->impl->last_launches;
   RLREP_API_END
@@ -732,12 +822,12 @@ int rlrep_comm_create(const unsigned char* id128, int rank, int world, rlrep_com
   RLREP_API_END
 }
 int rlrep_comm_destroy(rlrep_comm* comm) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(comm)
   delete comm;
   RLREP_API_END
 }
 int rlrep_comm_info(rlrep_comm* comm, int* rank, int* world, int* nccl_version, long long* collectives) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(comm)
   RLREP_CHECK(comm != nullptr, "null argument");
   if (rank) *rank = comm->impl->rank;
   if (world) *world = comm->impl->world;
@@ -805,7 +895,7 @@ static int create_agent(const rlrep_agent_config* c, rlrep_comm* comm, void* str
   RLREP_API_END
 }
 int rlrep_agent_destroy(rlrep_agent* agent) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(agent)
   if (agent && agent->impl) cudaStreamSynchronize(agent->impl->stream);
   if (agent) {
     agent->impl.reset();
@@ -815,12 +905,12 @@ int rlrep_agent_destroy(rlrep_agent* agent) {
   RLREP_API_END
 }
 int rlrep_agent_num_tensors(rlrep_agent* agent, int* n) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(agent)
   *n = (int)agent->tensors.size();
   RLREP_API_END
 }
 int rlrep_agent_tensor_info(rlrep_agent* agent, int i, const char** name, float** ptr_dev, int* rows, int* cols) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(agent)
   RLREP_CHECK(i >= 0 && i < (int)agent->tensors.size(), "tensor index out of range");
   const TensorRef& t = agent->tensors[i];
   if (name) *name = t.name.c_str();
@@ -830,7 +920,7 @@ int rlrep_agent_tensor_info(rlrep_agent* agent, int i, const char** name, float*
   RLREP_API_END
 }
 int rlrep_agent_tensor_read(rlrep_agent* agent, int i, float* out_host) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(agent)
   RLREP_CHECK(i >= 0 && i < (int)agent->tensors.size(), "tensor index out of range");
   const TensorRef& t = agent->tensors[i];
   cudaStream_t st = agent->impl->stream;
@@ -840,7 +930,7 @@ int rlrep_agent_tensor_read(rlrep_agent* agent, int i, float* out_host) {
   RLREP_API_END
 }
 int rlrep_agent_tensor_write(rlrep_agent* agent, int i, const float* in_host) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(agent)
   RLREP_CHECK(i >= 0 && i < (int)agent->tensors.size(), "tensor index out of range");
   const TensorRef& t = agent->tensors[i];
   cudaStream_t st = agent->impl->stream;
@@ -850,7 +940,7 @@ int rlrep_agent_tensor_write(rlrep_agent* agent, int i, const float* in_host) {
   RLREP_API_END
 }
 int rlrep_agent_get_log_alpha(rlrep_agent* agent, double* log_alpha) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(agent)
   Control h;
   RLREP_CUDA(cudaMemcpyAsync(&h, agent->impl->ctl, sizeof(h), cudaMemcpyDeviceToHost, agent->impl->stream));
   RLREP_CUDA(cudaStreamSynchronize(agent->impl->stream));
@@ -858,7 +948,7 @@ int rlrep_agent_get_log_alpha(rlrep_agent* agent, double* log_alpha) {
   RLREP_API_END
 }
 int rlrep_agent_set_log_alpha(rlrep_agent* agent, double log_alpha) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(agent)
   Control h;
   cudaStream_t st = agent->impl->stream;
   RLREP_CUDA(cudaMemcpyAsync(&h, agent->impl->ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
@@ -869,8 +959,34 @@ int rlrep_agent_set_log_alpha(rlrep_agent* agent, double log_alpha) {
   RLREP_CUDA(cudaStreamSynchronize(st));
   RLREP_API_END
 }
+int rlrep_agent_get_optim_state(rlrep_agent* agent, rlrep_optim_state* out) {
+  RLREP_API_BEGIN_ON(agent)
+  RLREP_CHECK(agent && out, "null argument");
+  Control h;
+  RLREP_CUDA(cudaMemcpyAsync(&h, agent->impl->ctl, sizeof(h), cudaMemcpyDeviceToHost, agent->impl->stream));
+  RLREP_CUDA(cudaStreamSynchronize(agent->impl->stream));
+  out->steps = h.steps;
+  out->t_feature = h.t_feat; out->t_critic = h.t_critic; out->t_actor = h.t_actor; out->t_alpha = h.t_alpha;
+  out->log_alpha = h.log_alpha; out->log_alpha_m = h.la_m; out->log_alpha_v = h.la_v;
+  RLREP_API_END
+}
+int rlrep_agent_set_optim_state(rlrep_agent* agent, const rlrep_optim_state* in) {
+  RLREP_API_BEGIN_ON(agent)
+  RLREP_CHECK(agent && in, "null argument");
+  Control h;
+  cudaStream_t st = agent->impl->stream;
+  RLREP_CUDA(cudaMemcpyAsync(&h, agent->impl->ctl, sizeof(h), cudaMemcpyDeviceToHost, st));
+  RLREP_CUDA(cudaStreamSynchronize(st));
+  h.steps = in->steps;
+  h.t_feat = in->t_feature; h.t_critic = in->t_critic; h.t_actor = in->t_actor; h.t_alpha = in->t_alpha;
+  h.log_alpha = in->log_alpha; h.la_m = in->log_alpha_m; h.la_v = in->log_alpha_v;
+  h.alpha = (float)std::exp(in->log_alpha);
+  RLREP_CUDA(cudaMemcpyAsync(agent->impl->ctl, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+  RLREP_CUDA(cudaStreamSynchronize(st));
+  RLREP_API_END
+}
 int rlrep_agent_get_steps(rlrep_agent* agent, int* steps) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(agent)
   Control h;
   RLREP_CUDA(cudaMemcpyAsync(&h, agent->impl->ctl, sizeof(h), cudaMemcpyDeviceToHost, agent->impl->stream));
   RLREP_CUDA(cudaStreamSynchronize(agent->impl->stream));
@@ -878,7 +994,7 @@ int rlrep_agent_get_steps(rlrep_agent* agent, int* steps) {
   RLREP_API_END
 }
 int rlrep_agent_train_counts(rlrep_agent* agent, int* n_idx, int* n_eps, int* n_metrics) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(agent)
   *n_idx = agent->impl->idx_per_train();
   *n_eps = agent->impl->eps_per_train();
   *n_metrics = (int)agent->impl->metric_names().size();
@@ -891,25 +1007,32 @@ const char* rlrep_agent_metric_name(rlrep_agent* agent, int i) {
 }
 int rlrep_agent_train(rlrep_agent* agent, rlrep_ring* ring, const int64_t* idx_host, int n_idx, const float* eps_host,
                       int n_eps, float* metrics_host, int n_metrics) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(agent)
   RLREP_CHECK(agent && ring && idx_host && eps_host && metrics_host, "null argument");
   agent->impl->train(*ring->impl, reinterpret_cast<const long long*>(idx_host), n_idx, eps_host, n_eps, metrics_host,
                      n_metrics);
   RLREP_API_END
 }
 int rlrep_agent_act(rlrep_agent* agent, const float* state_host, const float* eps_host, float* action_host) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(agent)
   agent->impl->act(state_host, eps_host, action_host);
   RLREP_API_END
 }
+int rlrep_agent_act_batch(rlrep_agent* agent, const float* states_host, const float* eps_host, int rows,
+                          float* actions_host) {
+  RLREP_API_BEGIN_ON(agent)
+  RLREP_CHECK(agent && states_host && actions_host && rows >= 0, "bad arguments");
+  agent->impl->act_batch(states_host, eps_host, rows, actions_host);
+  RLREP_API_END
+}
 int rlrep_agent_last_launches(rlrep_agent* agent, int* launches) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(agent)
   *launches = agent->impl->last_launches;
   RLREP_API_END
 }
 int rlrep_agent_train_resident(rlrep_agent* agent, rlrep_ring* ring, const int64_t* idx_host, const float* eps_host,
                                int n_steps, float* total_ms) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(agent)
   RLREP_CHECK(agent && ring && idx_host && eps_host && total_ms, "null argument");
   *total_ms = agent->impl->train_resident(*ring->impl, reinterpret_cast<const long long*>(idx_host), eps_host, n_steps);
   RLREP_API_END
@@ -917,7 +1040,7 @@ int rlrep_agent_train_resident(rlrep_agent* agent, rlrep_ring* ring, const int64
 int rlrep_agent_profile_train(rlrep_agent* agent, rlrep_ring* ring, const int64_t* idx_host, const float* eps_host,
                               int max_entries, const char** names, float* ms, double* bytes, double* flops,
                               int* n_entries) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(agent)
   RLREP_CHECK(agent && ring && idx_host && eps_host && n_entries && (max_entries == 0 || (names && ms)), "null argument");
   std::vector<ProfileEntry> prof =
       agent->impl->profile_train(*ring->impl, reinterpret_cast<const long long*>(idx_host), eps_host);
@@ -932,7 +1055,7 @@ int rlrep_agent_profile_train(rlrep_agent* agent, rlrep_ring* ring, const int64_
   RLREP_API_END
 }
 int rlrep_agent_sync_targets(rlrep_agent* agent) {
-  RLREP_API_BEGIN
+  RLREP_API_BEGIN_ON(agent)
   agent->impl->sync_targets_from_params();
   RLREP_API_END
 }

@@ -64,6 +64,11 @@ void read_gemm_trace(unsigned long long* out16);
 // Debug aid: device buffer of 80 uint64 the persistent kernel's CTA 0 stamps its first 16 tiles into (nullptr = off).
 void set_gemm_debug_buffer(unsigned long long* dev80);
 
+// TMA descriptor of one GEMM operand over fp32 memory, typed TFLOAT32 (the TMA unit rounds on the way into shared
+// memory): K-major = matrix [mn, K] with row pitch ld, box box_mn x 32, SWIZZLE_128B; MN-major = matrix [K, mn] viewed as
+// (mn % 32, k, mn / 32), box {32, 32, box_mn / 32}, SWIZZLE_128B_ATOM_32B (see gemm_tc_kernel.cuh).
+CUtensorMap make_operand_map(const float* base, bool mn_major, int mn, int K, int ld, int box_mn);
+
 // ---- CUDA-core path (exact FP32 FFMA; small-K / small-N layers and the strict-fp32 mode) ----
 void launch_simt(const GemmArgs& a, cudaStream_t stream);
 

@@ -146,6 +146,10 @@ double plan_cost(const GemmArgs& a, int nkb, int bn, int s, double sm_share, int
 
 void set_gemm_debug_buffer(unsigned long long* dev80) { tc::g_persist_dbg = dev80; }
 
+CUtensorMap make_operand_map(const float* base, bool mn_major, int mn, int K, int ld, int box_mn) {
+  return mn_major ? make_map_mnmajor(base, K, mn, ld, box_mn) : make_map_kmajor(base, mn, K, ld, box_mn);
+}
+
 void read_gemm_trace(unsigned long long* out16) {
   RLREP_CHECK(tc::g_trace_reader != nullptr, "no tcgen05 GEMM has been launched yet");
   tc::g_trace_reader(out16);

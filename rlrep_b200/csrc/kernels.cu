@@ -297,6 +297,52 @@ __global__ void actor_sample_kernel(const float* __restrict__ head, int ld_head,
   }
 }
 
+// select_action (sac_agent.py:89-96) as ONE launch: CTA r evaluates the whole tanh-Gaussian policy for row r of `in`
+// ([state (S) | eps (A)] per row, row pitch S + A) -- trunk 0 / 2 / 4 with ELU in shared memory, one warp per output unit
+// with the lanes striding over the inputs -- and writes tanh(mu) (explore = 0) or tanh(mu + std * eps).  `in` and `out` may
+// be mapped pinned host memory: the kernel then reads the observation and writes the action over PCIe itself and the host
+// only synchronises, no copy calls (the path main.py takes once per environment step).
+__global__ void __launch_bounds__(256) actor_act_kernel(const float* __restrict__ in, int S, int A, int H,
+                                                        const float* __restrict__ W0, int ld0, const float* __restrict__ b0,
+                                                        const float* __restrict__ W1, int ld1, const float* __restrict__ b1,
+                                                        const float* __restrict__ W2, int ld2, const float* __restrict__ b2,
+                                                        int explore, float* __restrict__ out) {
+  extern __shared__ float sm[];
+  float* x = sm;                 // [S]
+  float* h1 = x + ((S + 3) & ~3);  // [H]
+  float* h2 = h1 + H;            // [H]
+  float* hd = h2 + H;            // [2A]
+  const int row = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  const float* r = in + (size_t)row * (S + A);
+  for (int j = threadIdx.x; j < S; j += blockDim.x) x[j] = r[j];
+  __syncthreads();
+  auto layer = [&](const float* __restrict__ W, int ld, const float* __restrict__ b, const float* src, int n_in, float* dst,
+                   int n_out, bool elu) {
+    for (int o = warp; o < n_out; o += nw) {
+      const float* w = W + (size_t)o * ld;
+      float acc = 0.f;
+      for (int j = lane; j < n_in; j += 32) acc = fmaf(__ldg(w + j), src[j], acc);
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        const float v = acc + __ldg(b + o);
+        dst[o] = elu ? (v > 0.f ? v : expm1f(v)) : v;
+      }
+    }
+    __syncthreads();
+  };
+  layer(W0, ld0, b0, x, S, h1, H, true);
+  layer(W1, ld1, b1, h1, H, h2, H, true);
+  layer(W2, ld2, b2, h2, H, hd, 2 * A, false);
+  for (int j = threadIdx.x; j < A; j += blockDim.x) {
+    float u = hd[j];
+    if (explore) {
+      const float ls = kLogStdMin + 0.5f * (kLogStdMax - kLogStdMin) * (tanhf(hd[A + j]) + 1.f);
+      u += r[S + j] * expf(ls);
+    }
+    out[(size_t)row * A + j] = tanhf(u);
+  }
+}
+
 __global__ void actor_sample_bwd_kernel(const float* __restrict__ head, int ld_head, int B, int A,
                                         const float* __restrict__ eps, const float* __restrict__ d_action, int ldd,
                                         const float* __restrict__ dlogp_scalar, float* __restrict__ dhead, int ld_dh) {
@@ -773,6 +819,15 @@ void launch_actor_sample(const float* head, int ld_head, int B, int A, const flo
                          float* logp, cudaStream_t s, const float* obs, int ld_obs, int S) {
   actor_sample_kernel<<<ceil_div(B * 32, 128), 128, 0, s>>>(head, ld_head, B, A, eps, action, lda, logp, obs, ld_obs, S);
   RLREP_LAUNCHED("actor_sample", s);
+}
+
+void launch_actor_act(const float* in, int rows, int S, int A, int H, const float* W0, int ld0, const float* b0,
+                      const float* W1, int ld1, const float* b1, const float* W2, int ld2, const float* b2, int explore,
+                      float* out, cudaStream_t s) {
+  const size_t smem = (size_t)(((S + 3) & ~3) + 2 * H + 2 * A) * sizeof(float);
+  RLREP_CHECK(smem <= 48 * 1024, "actor too wide for the one-launch select_action kernel");
+  actor_act_kernel<<<rows, 256, smem, s>>>(in, S, A, H, W0, ld0, b0, W1, ld1, b1, W2, ld2, b2, explore, out);
+  RLREP_LAUNCHED("actor_act", s);
 }
 
 void launch_actor_sample_bwd(const float* head, int ld_head, int B, int A, const float* eps, const float* d_action,

@@ -91,6 +91,11 @@ void launch_feature_loss_finalize(const float* loss_rows, int rows, const float*
 void launch_actor_sample(const float* head, int ld_head, int B, int A, const float* eps, float* action, int lda,
                          float* logp, cudaStream_t s, const float* obs = nullptr, int ld_obs = 0, int S = 0);
 // Backward of the above: dhead [B, ld_dhead >= 2A] from d_action [B, ldd] and the per-row d_logp scalar.
+// select_action / batched policy evaluation in one launch: out[r, :] = tanh(mu(in[r, :S]) (+ std * in[r, S:S+A] if explore));
+// `in` / `out` may be mapped pinned host memory (see actor_act_kernel).
+void launch_actor_act(const float* in, int rows, int S, int A, int H, const float* W0, int ld0, const float* b0,
+                      const float* W1, int ld1, const float* b1, const float* W2, int ld2, const float* b2, int explore,
+                      float* out, cudaStream_t s);
 void launch_actor_sample_bwd(const float* head, int ld_head, int B, int A, const float* eps, const float* d_action,
                              int ldd, const float* dlogp_scalar, float* dhead, int ld_dhead, cudaStream_t s);
 

@@ -1,6 +1,7 @@
 // Host runtime: replay ring, GEMM dispatch with cached TMA plans, linear-layer pass helpers, graph replay.
 #include <algorithm>
 #include <atomic>
+#include <cstdlib>
 
 #include "agent.cuh"
 
@@ -156,6 +157,7 @@ void Ring::gather_from_host_idx(const long long* idx_host, int B, float* out_dev
 // ================================================================================================ GemmRunner
 void GemmRunner::init(Precision prec, size_t ws_floats) {
   prec_ = prec;
+  if (const char* e = std::getenv("RLREP_CHAIN")) chains_on_ = std::atoi(e) != 0;
   ws_floats_ = ws_floats;
   if (ws_floats_) RLREP_CUDA(cudaMalloc(&ws_, ws_floats_ * sizeof(float)));
 }
@@ -163,7 +165,52 @@ GemmRunner::~GemmRunner() {
   if (ws_) cudaFree(ws_);
 }
 
+void GemmRunner::begin_chain(cudaStream_t s) {
+  RLREP_CHECK(!recording_, "begin_chain inside a chain");
+  if (!chains_enabled()) return;
+  recording_ = true;
+  chain_stream_ = s;
+  pending_.clear();
+}
+
+void GemmRunner::flush_chain() {
+  if (pending_.empty()) return;
+  if (pending_.size() == 1) {  // nothing to chain: the one-GEMM kernels do this better
+    const GemmArgs a = pending_[0];
+    pending_.clear();
+    const bool rec = recording_;
+    recording_ = false;
+    run(a, chain_stream_);
+    recording_ = rec;
+    return;
+  }
+  GemmChain* chain = nullptr;
+  for (auto& c : chains_)
+    if (c->matches(pending_)) chain = c.get();
+  if (chain == nullptr) {
+    chains_.emplace_back(new GemmChain());
+    chain = chains_.back().get();
+    chain->build(pending_);
+  }
+  chain->launch(chain_stream_);
+  pending_.clear();
+}
+
+void GemmRunner::end_chain() {
+  if (!recording_) return;
+  flush_chain();
+  recording_ = false;
+}
+
 void GemmRunner::run(const GemmArgs& a, cudaStream_t s) {
+  if (recording_) {
+    if (chain_eligible(a)) {
+      pending_.push_back(a);
+      return;
+    }
+    flush_chain();  // program order on the chain's stream
+    s = chain_stream_;
+  }
   // Short-K layers (K = 17 / 23 inputs) also go to the tensor cores: the tensor maps carry the LOGICAL K, so TMA
   // zero-fills the rest of the 32-wide k-block whatever sits behind the operands in memory.
   const bool tc = prec_ == PREC_TF32 && tc_eligible(a) && a.M >= 32 && a.N >= 32 && a.K >= 8;

@@ -81,8 +81,8 @@ def worst_param_error(agent, oracle):
 def worst_param_error_conditioned(agent, oracle, before, g_floor=1e-3):
     """Per-tensor relative L2 distance after ONE train() call, leaving out the elements whose Adam step is ill-conditioned:
     on the first step m / (sqrt(v) + eps) = g / (|g| + eps') is +-1 whatever |g| is, so where the oracle's gradient is below
-    `g_floor` of the tensor's RMS gradient the SIGN of a +-lr move is decided by rounding.  The gradient is read off the
-    oracle's own update (p_after - p_before; zero for tensors no optimiser touches)  -> (worst, name, fraction left out)."""
+    `g_floor` of the tensor's RMS gradient the SIGN of a +-lr move is decided by rounding.  The gradients are the ones the
+    oracle recorded at each tensor's most recent optimiser step (`last_step_grads`)  -> (worst, name, fraction left out)."""
     csd, osd = agent.state_dict(), oracle.state_dict()
     worst, where, skipped, total = 0.0, None, 0, 0
     for k, v in osd.items():
@@ -90,8 +90,8 @@ def worst_param_error_conditioned(agent, oracle, before, g_floor=1e-3):
             assert abs(float(csd[k]) - float(v)) < 1e-5 * max(1.0, abs(float(v))), (float(csd[k]), float(v))
             continue
         c, v, b = csd[k].double().reshape(-1), v.double().reshape(-1), before[k].double().reshape(-1)
-        g = getattr(oracle, "p", {}).get(k)
-        g = g.grad.double().reshape(-1) if g is not None and g.grad is not None and g.grad.numel() == v.numel() else None
+        g = getattr(oracle, "last_step_grads", {}).get(k)  # gradient at the tensor's most recent optimiser step
+        g = g.double().reshape(-1) if g is not None and g.numel() == v.numel() else None
         keep = torch.ones_like(v, dtype=torch.bool)
         if g is not None and (v - b).abs().max() > 0:
             rms = g.pow(2).mean().sqrt()
