@@ -132,6 +132,31 @@ RLREP_EXPORT int rlrep_ring_load(rlrep_ring* ring, const void* state_host, const
 RLREP_EXPORT int rlrep_ring_gather(rlrep_ring* ring, const int64_t* idx_host, int B, float* out_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Pixel replay ring -- replaces agent/diffsrdrq/helper_functions/efficient_buffer.py:35-136 (EfficientReplayBuffer:
+ * storage + `gather_nstep_indices`; the mulvdrq loader's sample tuple, agent/mulvdrq/replay_buffer.py:149-168, has the
+ * same six fields).  One uint8 frame per environment step lives in HBM; a batch is assembled by one kernel of 128-bit
+ * copies into device tensors that rlrep_drq_update / rlrep_mulv_update / rlrep_ldiff_update accept in place of host
+ * arrays.  Which slots may be sampled is host bookkeeping and stays with the caller (rlrep_b200.PixelReplayBuffer keeps it
+ * exactly as the reference does).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct rlrep_pixring rlrep_pixring;
+RLREP_EXPORT int rlrep_pixring_create(long long capacity, int frame_bytes, int action_dim, int frame_stack, int nstep,
+                                      rlrep_pixring** out);
+RLREP_EXPORT int rlrep_pixring_destroy(rlrep_pixring* ring);
+/* efficient_buffer.py:66-105 `add_data_point`, storage part: frame_host [frame_bytes] goes to slots [slot, slot + copies)
+ * mod capacity (copies = frame_stack for the first observation of a trajectory, else 1); when has_step,
+ * (action_host [action_dim], reward, discount) go to `slot`.  Writes are staged and shipped 64 at a time. */
+RLREP_EXPORT int rlrep_pixring_write(rlrep_pixring* ring, long long slot, int copies, const unsigned char* frame_host,
+                                     const float* action_host, float reward, float discount, int has_step);
+RLREP_EXPORT int rlrep_pixring_flush(rlrep_pixring* ring);
+/* efficient_buffer.py:108-136 `gather_nstep_indices` for n sampled slots idx_host: obs / nobs / sobs_dev
+ * [n, frame_stack * frame_bytes] uint8 (sobs_dev may be NULL), act_dev [n, action_dim], rew_dev / dis_dev [n];
+ * discount_vec_host [nstep] = discount^k as float32, next_dis = discount^nstep.  Outputs are complete on return. */
+RLREP_EXPORT int rlrep_pixring_gather(rlrep_pixring* ring, const int64_t* idx_host, int n, const float* discount_vec_host,
+                                      float next_dis, unsigned char* obs_dev, float* act_dev, float* rew_dev, float* dis_dev,
+                                      unsigned char* nobs_dev, unsigned char* sobs_dev);
+
+/* ------------------------------------------------------------------------------------------------
  * Agent handles -- replace `Agent(**kwargs)`, `agent.train(buffer, batch_size)`, `agent.select_action(state)`
  * (sac_agent.py:19-31,89-96,169-188; ctrlsac_agent.py:127-143,327-362; main.py:71-104,130,144).
  * ---------------------------------------------------------------------------------------------- */

@@ -18,6 +18,9 @@ def __getattr__(name):  # lazy: importing the package must not require torch.cud
     if name in ("ConvEncoder", "DrQv2", "MuLVDrQv2", "LatentDiffSRDrQv2"):
         from . import pixel
         return getattr(pixel, name)
+    if name == "PixelReplayBuffer":
+        from . import pixel_replay
+        return pixel_replay.PixelReplayBuffer
     if name == "Population":
         from . import population
         return population.Population

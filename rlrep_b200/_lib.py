@@ -155,6 +155,11 @@ def _declare(lib: C.CDLL) -> None:
         "rlrep_agent_train_counts": [vp, C.POINTER(i), C.POINTER(i), C.POINTER(i)],
         "rlrep_agent_train": [vp, vp, vp, i, vp, i, vp, i],
         "rlrep_agent_act": [vp, vp, vp, vp],
+        "rlrep_pixring_create": [C.c_longlong, i, i, i, i, C.POINTER(vp)],
+        "rlrep_pixring_destroy": [vp],
+        "rlrep_pixring_write": [vp, C.c_longlong, i, vp, vp, C.c_float, C.c_float, i],
+        "rlrep_pixring_flush": [vp],
+        "rlrep_pixring_gather": [vp, vp, i, vp, C.c_float, vp, vp, vp, vp, vp, vp],
         "rlrep_agent_act_batch": [vp, vp, vp, i, vp],
         "rlrep_agent_last_launches": [vp, C.POINTER(i)],
         "rlrep_agent_train_resident": [vp, vp, vp, vp, i, C.POINTER(C.c_float)],

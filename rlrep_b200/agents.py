@@ -288,12 +288,15 @@ class SACAgent:
 
     def select_actions(self, states, explore=False):
         """Batched `select_action`: states [N, state_dim] -> actions [N, action_dim] in one kernel launch per 1024 rows
-        (`rlrep_agent_act_batch`).  With explore=True the noise is ONE torch.randn([N, action_dim]) draw from the CPU
-        generator (row i is what the i-th of N consecutive select_action(explore=True) calls would draw)."""
+        (`rlrep_agent_act_batch`).  With explore=True the noise is drawn row by row, torch.randn(1, action_dim) per
+        observation from the CPU generator -- exactly what N consecutive select_action(explore=True) calls draw (one
+        torch.randn(N, action_dim) call would consume the generator differently)."""
         h = self._ensure()
         s = np.ascontiguousarray(np.asarray(states, dtype=np.float32).reshape(-1, self.state_dim))
         out = np.empty((s.shape[0], self.action_dim), dtype=np.float32)
-        eps = np.ascontiguousarray(torch.randn(s.shape[0], self.action_dim).numpy()) if explore else None
+        eps = None
+        if explore:
+            eps = np.ascontiguousarray(torch.cat([torch.randn(1, self.action_dim) for _ in range(s.shape[0])]).numpy())
         _lib.check(h.lib.rlrep_agent_act_batch(h.h, s.ctypes.data, eps.ctypes.data if eps is not None else None,
                                                s.shape[0], out.ctypes.data))
         return np.clip(out, self.action_range[0], self.action_range[1])

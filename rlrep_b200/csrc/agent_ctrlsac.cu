@@ -88,6 +88,7 @@ class CtrlSacAgent final : public SacBase {
     arena_.want(&dq1_, B_);
     arena_.want(&dq2_, B_);
     arena_.want(&logp2_, B_);
+    arena_.want(&head_ctr_, 4);
     finish_setup((size_t)8 << 20);
 
     names_ = {"total_loss", "model_loss", "r_loss", "q1_loss", "q2_loss", "q1", "q2", "actor_loss", "alpha_loss",
@@ -256,9 +257,9 @@ class CtrlSacAgent final : public SacBase {
       gemm_.run(a, s0);
     }
     gemm_.end_chain();
-    launch_ce_rows(logits_, B_, B_, B_, 0, inv_b, loss_rows_, s0);  // logits_ now holds dL/dlogits
-    launch_rowdot(zphi_, D_, B_, D_, th.W, th.b, rpred_, s0);
-    launch_feature_loss_finalize(loss_rows_, B_, rpred_, reward(), R_, inv_b, drp_, metrics_dev_ + 0, s0);
+    // row log-sum-exp / CE gradient (logits_ now holds dL/dlogits), reward head and the loss metrics in one launch
+    launch_contrastive_head(logits_, B_, B_, B_, 0, inv_b, zphi_, D_, D_, th.W, th.b, reward(), R_, loss_rows_, rpred_, drp_,
+                            metrics_dev_ + 0, head_ctr_, s0);
     gemm_.begin_chain(s0);
     {  // d z_phi = G mu + drp (x) theta.w
       GemmArgs a;
@@ -442,6 +443,7 @@ class CtrlSacAgent final : public SacBase {
         *dhid_ = nullptr;
   float *q1_ = nullptr, *q2_ = nullptr, *nq1_ = nullptr, *nq2_ = nullptr, *dq1_ = nullptr, *dq2_ = nullptr;
   float *logp2_ = nullptr;
+  unsigned* head_ctr_ = nullptr;
   std::vector<std::string> names_;
 };
 

@@ -12,6 +12,7 @@
 #include "conv.cuh"
 #include "drq.cuh"
 #include "mulv.cuh"
+#include "pixel_replay.cuh"
 #include "ldiffsr.cuh"
 #include "gemm.cuh"
 #include "rlrep_b200.h"
@@ -807,6 +808,55 @@ int rlrep_ldiff_last_launches(rlrep_ldiff* h, int* launches) {
 }
 
 // ------------------------------------------------------------------------------------------------ communicator
+// ------------------------------------------------------------------------------------------------ pixel replay ring
+struct rlrep_pixring {
+  int device = current_device();
+  std::unique_ptr<PixelRing> impl;
+  cudaStream_t stream = nullptr;
+};
+
+int rlrep_pixring_create(long long capacity, int frame_bytes, int action_dim, int frame_stack, int nstep, rlrep_pixring** out) {
+  RLREP_API_BEGIN
+  RLREP_CHECK(out != nullptr, "null argument");
+  std::unique_ptr<rlrep_pixring> h(new rlrep_pixring);
+  RLREP_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  h->impl.reset(new PixelRing(capacity, frame_bytes, action_dim, frame_stack, nstep));
+  *out = h.release();
+  RLREP_API_END
+}
+int rlrep_pixring_destroy(rlrep_pixring* ring) {
+  RLREP_API_BEGIN_ON(ring)
+  if (ring) {
+    ring->impl.reset();
+    if (ring->stream) cudaStreamDestroy(ring->stream);
+    delete ring;
+  }
+  RLREP_API_END
+}
+int rlrep_pixring_write(rlrep_pixring* ring, long long slot, int copies, const unsigned char* frame_host,
+                        const float* action_host, float reward, float discount, int has_step) {
+  RLREP_API_BEGIN_ON(ring)
+  RLREP_CHECK(ring, "null argument");
+  ring->impl->write(slot, copies, frame_host, action_host, reward, discount, has_step != 0, ring->stream);
+  RLREP_API_END
+}
+int rlrep_pixring_flush(rlrep_pixring* ring) {
+  RLREP_API_BEGIN_ON(ring)
+  RLREP_CHECK(ring, "null argument");
+  ring->impl->flush(ring->stream);
+  RLREP_API_END
+}
+int rlrep_pixring_gather(rlrep_pixring* ring, const int64_t* idx_host, int n, const float* discount_vec_host, float next_dis,
+                         unsigned char* obs_dev, float* act_dev, float* rew_dev, float* dis_dev, unsigned char* nobs_dev,
+                         unsigned char* sobs_dev) {
+  RLREP_API_BEGIN_ON(ring)
+  RLREP_CHECK(ring, "null argument");
+  ring->impl->gather(reinterpret_cast<const long long*>(idx_host), n, discount_vec_host, next_dis, obs_dev, act_dev, rew_dev,
+                     dis_dev, nobs_dev, sobs_dev, ring->stream);
+  RLREP_CUDA(cudaStreamSynchronize(ring->stream));  // the batch is complete when the call returns, whatever stream reads it
+  RLREP_API_END
+}
+
 int rlrep_comm_unique_id(unsigned char* out128) {
   RLREP_API_BEGIN
   RLREP_CHECK(out128 != nullptr, "null argument");

@@ -19,6 +19,9 @@ constexpr int kBM = 128, kBK = 32;
 constexpr int kABytes = kBM * kBK * 4;  // 16 KB
 constexpr int kStageBytes = kABytes + kMaxBn * kBK * 4;  // 32 KB: A tile + the widest B tile
 constexpr int kTbufFloats = 4 * 32 * 36;
+// Completion counters: kSub sub-counters per GEMM, each alone in its 128-byte line (same-line atomics serialise in the L2
+// slice at ~27 clk each, and every waiting producer polls these lines); tile t publishes on sub-counter t % kSub.
+constexpr int kSub = 4, kCtrStride = 32;
 constexpr int kDbgItems = 16, kDbgEvents = 10;  // debug timeline: items per CTA x events per item
 // events: 0 producer picks the item up, 1 dependencies satisfied, 2 last TMA of the item issued, 3 MMA sees the first
 // operands, 4 accumulator committed, 5 epilogue sees the accumulator, 6 split-K arrival counted, 7 tile published
@@ -27,11 +30,6 @@ constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256 + kTbufFloats * 4;
 static_assert(kSmemBytes <= 227 * 1024, "chain kernel shared memory");
 
 // ------------------------------------------------------------------------------------------------ device helpers
-__device__ __forceinline__ unsigned ld_acquire(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ void red_release_add(unsigned* p, unsigned v) {
   asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -44,18 +42,35 @@ __device__ __forceinline__ void fence_proxy_async_global() { asm volatile("fence
 __device__ __forceinline__ void fence_tensormap_acquire(const CUtensorMap* m) {
   asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
-// Bounded spin: a scheduling bug must surface as a trap (launch error), never as a hung GPU.
-__device__ __forceinline__ void wait_counter(const unsigned* p, unsigned target) {
-  if (ld_acquire(p) >= target) return;
-  const long long t0 = clock64();
-  while (ld_acquire(p) < target) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("rlrep: chain dependency wait timed out (block %d, counter %p, target %u, value %u)\n", blockIdx.x, p, target,
-             ld_acquire(p));
-      __trap();
+__device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Bounded spin on the kSub sub-counters of GEMM `dep`: a scheduling bug must surface as a trap (launch error), never as a
+// hung GPU.  The polls are relaxed loads with a short back-off -- an acquire load would invalidate this SM's L1 on every
+// iteration under the feet of the epilogue warps, and 148 producers hammering one L2 line delay the very atomics they are
+// waiting for -- and ONE acquire fence follows once all counts are reached.
+__device__ __forceinline__ void wait_counter(const unsigned* done, int dep, int dep_tiles) {
+  const unsigned* p = done + (size_t)dep * kSub * kCtrStride;
+  long long t0 = 0;
+  for (int sub = 0; sub < kSub; ++sub) {
+    const unsigned target = (unsigned)((dep_tiles - sub + kSub - 1) / kSub);
+    while (ld_relaxed(p + sub * kCtrStride) < target) {
+      __nanosleep(32);
+      if (t0 == 0) t0 = clock64();
+      if (clock64() - t0 > 4000000000LL) {
+        printf("rlrep: chain dependency wait timed out (block %d, gemm %d sub %d, target %u, value %u)\n", blockIdx.x, dep,
+               sub, target, ld_relaxed(p + sub * kCtrStride));
+        __trap();
+      }
     }
   }
 }
+__device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+
+// Named barrier of the four epilogue warps (128 threads); barrier 0 stays with __syncthreads.
+__device__ __forceinline__ void epilogue_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
 
 __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -72,19 +87,43 @@ __device__ __forceinline__ float chain_epilogue_scalar(const Epilogue& e, float 
   return v;
 }
 
-// 32 x 32 chunk out of the warp's transpose buffer: lanes cover four rows x eight 16-byte pieces per store instruction, so
-// every store writes four complete 128-byte row segments.  ACT / DACT are compile-time (only the transcendental code of
-// the layer at hand is in the loop); the rare extras (scale, rank-1 term, pre-activation copy, accumulate) are
-// warp-uniform run-time branches.
-template <int ACT, int DACT>
-__device__ __forceinline__ void chain_store_rows(const Epilogue& epi, const float* tw, float* __restrict__ C, int ldc, int M,
-                                                 int m_base, int gn0, int lane) {
+// Global operands of one 32 x 32 epilogue chunk, fetched BEFORE the accumulator is touched: inside the store loop every
+// load would sit behind the previous row's store (the compiler must assume C aliases aux / bias), i.e. one L2 round trip
+// per row -- measured 2-4 us per chunk.  Issued together they cost one round trip, hidden behind tcgen05.ld, the split-K
+// sum and the transpose.  Lane mapping as in chain_store_rows: piece = lane & 7 (16-byte column piece), rsub = lane >> 3.
+struct ChunkOperands {
+  float4 bias, r1v;
+  float4 aux[8];
+  float r1u[8];
+};
+__device__ __forceinline__ void chunk_prefetch(ChunkOperands& o, const Epilogue& epi, int M, int m_base, int gn0, int lane) {
   const int piece = lane & 7, rsub = lane >> 3;
   const int on = gn0 + 4 * piece;
-  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (epi.bias) b4 = __ldg(reinterpret_cast<const float4*>(epi.bias + on));
-  float4 w4 = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (epi.r1_u) w4 = __ldcg(reinterpret_cast<const float4*>(epi.r1_v + on));
+  o.bias = make_float4(0.f, 0.f, 0.f, 0.f);
+  o.r1v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (epi.bias) o.bias = __ldg(reinterpret_cast<const float4*>(epi.bias + on));
+  if (epi.r1_u) o.r1v = __ldcg(reinterpret_cast<const float4*>(epi.r1_v + on));
+#pragma unroll
+  for (int r4 = 0; r4 < 8; ++r4) {
+    const int om = m_base + r4 * 4 + rsub;
+    o.aux[r4] = make_float4(0.f, 0.f, 0.f, 0.f);
+    o.r1u[r4] = 0.f;
+    if (om < M) {
+      if (epi.dact != DACT_NONE) o.aux[r4] = __ldcg(reinterpret_cast<const float4*>(epi.aux + (size_t)om * epi.ld_aux + on));
+      if (epi.r1_u) o.r1u[r4] = __ldcg(epi.r1_u + om);
+    }
+  }
+}
+
+// 32 x 32 chunk out of the warp's transpose buffer: lanes cover four rows x eight 16-byte pieces per store instruction, so
+// every store writes four complete 128-byte row segments.  ACT / DACT are compile-time (only the transcendental code of
+// the layer at hand is in the loop); the rare extras (scale, pre-activation copy, accumulate) are warp-uniform run-time
+// branches.
+template <int ACT, int DACT>
+__device__ __forceinline__ void chain_store_rows(const Epilogue& epi, const ChunkOperands& o, const float* tw,
+                                                 float* __restrict__ C, int ldc, int M, int m_base, int gn0, int lane) {
+  const int piece = lane & 7, rsub = lane >> 3;
+  const int on = gn0 + 4 * piece;
 #pragma unroll
   for (int r4 = 0; r4 < 8; ++r4) {
     const int r = r4 * 4 + rsub;
@@ -93,10 +132,10 @@ __device__ __forceinline__ void chain_store_rows(const Epilogue& epi, const floa
       const float4 a4 = *reinterpret_cast<const float4*>(tw + r * 36 + 4 * piece);
       float v[4] = {a4.x * epi.scale, a4.y * epi.scale, a4.z * epi.scale, a4.w * epi.scale};
       if (epi.r1_u) {
-        const float u = __ldcg(epi.r1_u + om);
-        v[0] = fmaf(u, w4.x, v[0]); v[1] = fmaf(u, w4.y, v[1]); v[2] = fmaf(u, w4.z, v[2]); v[3] = fmaf(u, w4.w, v[3]);
+        const float u = o.r1u[r4];
+        v[0] = fmaf(u, o.r1v.x, v[0]); v[1] = fmaf(u, o.r1v.y, v[1]); v[2] = fmaf(u, o.r1v.z, v[2]); v[3] = fmaf(u, o.r1v.w, v[3]);
       }
-      v[0] += b4.x; v[1] += b4.y; v[2] += b4.z; v[3] += b4.w;
+      v[0] += o.bias.x; v[1] += o.bias.y; v[2] += o.bias.z; v[3] += o.bias.w;
       if (epi.pre_out)
         *reinterpret_cast<float4*>(epi.pre_out + (size_t)om * epi.ld_pre + on) = make_float4(v[0], v[1], v[2], v[3]);
       if constexpr (ACT != ACT_NONE) {
@@ -106,14 +145,14 @@ __device__ __forceinline__ void chain_store_rows(const Epilogue& epi, const floa
       if constexpr (DACT != DACT_NONE) {
         const int dact = DACT < 0 ? epi.dact : DACT;
         if (dact != DACT_NONE) {
-          const float4 x = __ldcg(reinterpret_cast<const float4*>(epi.aux + (size_t)om * epi.ld_aux + on));
+          const float4 x = o.aux[r4];
           v[0] *= apply_dact(x.x, dact); v[1] *= apply_dact(x.y, dact); v[2] *= apply_dact(x.z, dact); v[3] *= apply_dact(x.w, dact);
         }
       }
       float4* cp = reinterpret_cast<float4*>(C + (size_t)om * ldc + on);
       if (epi.accumulate) {
-        const float4 o = __ldcg(cp);
-        v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
+        const float4 c0 = __ldcg(cp);
+        v[0] += c0.x; v[1] += c0.y; v[2] += c0.z; v[3] += c0.w;
       }
       *cp = make_float4(v[0], v[1], v[2], v[3]);
     }
@@ -140,6 +179,7 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
   uint64_t* acc_full = empty_bar + 8;   // [2] accumulator complete (MMA -> epilogue)
   uint64_t* acc_empty = acc_full + 2;   // [2] accumulator drained (epilogue -> MMA), one arrival per epilogue warp
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  volatile unsigned* arrival = reinterpret_cast<volatile unsigned*>(tmem_slot + 1);  // split-K arrival order, CTA-wide
   float* tbuf = reinterpret_cast<float*>(smem + kStages * kStageBytes + 256);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -177,9 +217,12 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
         if (dbg != nullptr && t - t_begin < kDbgItems)  // slot 8: which item this is
           dbg[((size_t)blockIdx.x * kDbgItems + (t - t_begin)) * kDbgEvents + 8] =
               (unsigned long long)tk.gemm | ((unsigned long long)tk.tile << 16) | ((unsigned long long)tk.split << 40);
-        for (int d = 0; d < n_deps; ++d) wait_counter(done + g->dep[d], g->dep_target[d]);
-        // the tiles were written through the generic proxy by other SMs; TMA reads through the async proxy
-        if (n_deps > 0 && !(flags & kFlagNoProxyFence)) fence_proxy_async_global();
+        for (int d = 0; d < n_deps; ++d) wait_counter(done, g->dep[d], (int)g->dep_target[d]);
+        if (n_deps > 0) {
+          fence_acquire_gpu();
+          // the tiles were written through the generic proxy by other SMs; TMA reads through the async proxy
+          if (!(flags & kFlagNoProxyFence)) fence_proxy_async_global();
+        }
         stamp(t - t_begin, 1);
         if (tk.gemm != last_gemm) {
           if (!(flags & kFlagNoTensormapFence)) {
@@ -250,8 +293,13 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
     for (int t = t_begin; t < t_end; ++t, ++tc) {
       const ChainTask tk = tasks[t];
       const ChainGemmDesc* g = gemms + tk.gemm;
+      // everything this item needs from its descriptor, read ONCE into registers: a reference into global memory would be
+      // re-read behind every store (the compiler must assume the stores alias it)
+      const Epilogue epi = g->epi;
       const int bn = g->bn, M = g->M, N = g->N, ldc = g->ldc, split_k = g->split_k;
       float* __restrict__ C = g->C;
+      float* __restrict__ ws = g->ws;
+      unsigned* __restrict__ tile_ctr = g->tile_ctr;
       const int m0 = (tk.tile % g->tiles_m) * kBM, n0 = (tk.tile / g->tiles_m) * bn;
       const int chunks = bn >> 5;
       const int acc = tc & 1;
@@ -263,7 +311,7 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
 
       bool final = true;
       const size_t part_floats = (size_t)kBM * bn;
-      float* ws_tile = split_k > 1 ? g->ws + (size_t)tk.tile * split_k * part_floats : nullptr;
+      float* ws_tile = split_k > 1 ? ws + (size_t)tk.tile * split_k * part_floats : nullptr;
       if (split_k > 1) {
         // pass 1: this CTA's partial quarter goes to the workspace, element (row, c*32 + 4*j + e) at
         // ((c*8 + j) * 128 + row) * 4 + e -- 512 contiguous bytes per store instruction
@@ -279,72 +327,117 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
                    make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                                __uint_as_float(v[4 * j + 3])));
         }
-        __syncwarp();
-        unsigned old = 0;
-        unsigned* ctr = g->tile_ctr + tk.tile * 4 + q;
-        if (lane == 0) old = atom_add_acq_rel(ctr, 1u);  // releases the warp's partial, acquires the other splits'
-        old = __shfl_sync(0xffffffffu, old, 0);
-        final = old == (unsigned)(split_k - 1);
-        if (final && lane == 0) *ctr = 0;  // every split has arrived: ready for the next launch
-        if (threadIdx.x == 64) stamp(t - t_begin, 6);
+        // ONE arrival per item: the four warps meet, a single thread releases the CTA's partial tile and acquires the others'
+        epilogue_bar();
+        if (threadIdx.x == 64) {
+          unsigned* ctr = tile_ctr + tk.tile;
+          const unsigned old = atom_add_acq_rel(ctr, 1u);
+          if (old == (unsigned)(split_k - 1)) *ctr = 0;  // every split has arrived: re-armed for the next launch
+          *arrival = old;
+          stamp(t - t_begin, 6);
+        }
+        epilogue_bar();
+        final = *arrival == (unsigned)(split_k - 1);
       }
       if (final) {
-        const Epilogue& epi = g->epi;
         const bool use_aux = epi.dact != DACT_NONE;
         const bool vec_ok = (ldc & 3) == 0 && aligned16(C) && (N & 3) == 0 &&
                             (!use_aux || ((epi.ld_aux & 3) == 0 && aligned16(epi.aux))) &&
                             (!epi.pre_out || ((epi.ld_pre & 3) == 0 && aligned16(epi.pre_out))) &&
                             (!epi.bias || aligned16(epi.bias)) && (!epi.r1_v || aligned16(epi.r1_v));
-        const int gm = m0 + row;
 #pragma unroll 1
         for (int c = 0; c < chunks; ++c) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(t_acc + c * 32, v);
-          ptx::tmem_ld_wait();
+          const int gn0 = n0 + c * 32;
+          const bool fast = vec_ok && gn0 + 32 <= N;
+          ChunkOperands ops;
+          if (fast) chunk_prefetch(ops, epi, M, m0 + 32 * q, gn0, lane);  // in flight while the accumulator is drained
           float a[32];
-          if (split_k > 1) {
-            // fixed summation order over the splits (this CTA's own partial comes from TMEM, bit-identical to what it wrote)
-#pragma unroll 1
-            for (int s = 0; s < split_k; ++s) {
-              if (s == tk.split) {
-#pragma unroll
-                for (int e = 0; e < 32; ++e) a[e] = s == 0 ? __uint_as_float(v[e]) : a[e] + __uint_as_float(v[e]);
-              } else {
-                const float* part = ws_tile + (size_t)s * part_floats;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  const float4 p4 = __ldcg(reinterpret_cast<const float4*>(part + ((size_t)(c * 8 + j) * kBM + row) * 4));
-                  if (s == 0) { a[4 * j] = p4.x; a[4 * j + 1] = p4.y; a[4 * j + 2] = p4.z; a[4 * j + 3] = p4.w; }
-                  else { a[4 * j] += p4.x; a[4 * j + 1] += p4.y; a[4 * j + 2] += p4.z; a[4 * j + 3] += p4.w; }
-                }
-              }
-            }
-          } else {
+          {
+            uint32_t v[32];
+            ptx::tmem_ld_32x32b_x32(t_acc + c * 32, v);
+            ptx::tmem_ld_wait();
 #pragma unroll
             for (int e = 0; e < 32; ++e) a[e] = __uint_as_float(v[e]);
           }
-          const int gn0 = n0 + c * 32;
-          if (vec_ok && gn0 + 32 <= N) {
+          if (split_k > 1) {
+            // Fixed summation order p_0 + p_1 + ... over the splits whoever arrives last (this CTA's own partial comes from
+            // TMEM, bit-identical to what it wrote): acc starts from the lowest split and the own values are folded in at
+            // their position.  The loads of split s+1 are in flight while split s is being added.
+            float own[32];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              *reinterpret_cast<float4*>(tw + lane * 36 + 4 * j) = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
-            __syncwarp();
-#define RLREP_CSTORE(A, D) chain_store_rows<A, D>(epi, tw, C, ldc, M, m0 + 32 * q, gn0, lane)
+            for (int e = 0; e < 32; ++e) own[e] = a[e];
+            const float* base = ws_tile + ((size_t)(c * 8) * kBM + row) * 4;
+            float4 nxt[8];
+            int s_next = tk.split == 0 ? 1 : 0;  // first remote split
+            if (s_next < split_k) {
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                nxt[j] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)s_next * part_floats + (size_t)j * kBM * 4));
+            }
+#pragma unroll 1
+            for (int s = 0; s < split_k; ++s) {
+              if (s == tk.split) {
+                if (s > 0) {
+#pragma unroll
+                  for (int e = 0; e < 32; ++e) a[e] += own[e];
+                }
+                continue;
+              }
+              float4 cur[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+              int s2 = s + 1;
+              if (s2 == tk.split) ++s2;
+              if (s2 < split_k) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j)
+                  nxt[j] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)s2 * part_floats + (size_t)j * kBM * 4));
+              }
+              if (s == 0) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { a[4 * j] = cur[j].x; a[4 * j + 1] = cur[j].y; a[4 * j + 2] = cur[j].z; a[4 * j + 3] = cur[j].w; }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { a[4 * j] += cur[j].x; a[4 * j + 1] += cur[j].y; a[4 * j + 2] += cur[j].z; a[4 * j + 3] += cur[j].w; }
+              }
+            }
+          }
+          // transpose through the warp's shared-memory buffer: thread = row on the way in, (row group, 16-byte piece) on the
+          // way out; ragged / unaligned tiles read the same buffer element-wise
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<float4*>(tw + lane * 36 + 4 * j) = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+          __syncwarp();
+          if (fast) {
+#define RLREP_CSTORE(A, D) chain_store_rows<A, D>(epi, ops, tw, C, ldc, M, m0 + 32 * q, gn0, lane)
             RLREP_EPILOGUE_SWITCH(epi, RLREP_CSTORE);
 #undef RLREP_CSTORE
-            __syncwarp();
-          } else if (gm < M && gn0 < N) {
-            float* crow = C + (size_t)gm * ldc + gn0;
-            for (int e = 0; e < 32 && gn0 + e < N; ++e) crow[e] = chain_epilogue_scalar(epi, a[e], gm, gn0 + e, crow + e);
+          } else if (gn0 < N) {
+            const int piece = lane & 7, rsub = lane >> 3;
+#pragma unroll 1
+            for (int r4 = 0; r4 < 8; ++r4) {
+              const int r = r4 * 4 + rsub, om = m0 + 32 * q + r;
+              if (om >= M) continue;
+#pragma unroll 1
+              for (int e = 0; e < 4; ++e) {
+                const int on = gn0 + 4 * piece + e;
+                if (on < N) {
+                  float* cp = C + (size_t)om * ldc + on;
+                  *cp = chain_epilogue_scalar(epi, tw[r * 36 + 4 * piece + e], om, on, cp);
+                }
+              }
+            }
           }
+          __syncwarp();
         }
-        // this quarter of the tile is final: publish it
-        __syncwarp();
-        if (lane == 0) {
+        // the tile is final: ONE release per item publishes it
+        if (threadIdx.x == 64) stamp(t - t_begin, 9);
+        epilogue_bar();
+        if (threadIdx.x == 64) {
           if (!(flags & kFlagNoProxyFence)) fence_proxy_async_global();
-          red_release_add(done + tk.gemm, 1u);
+          red_release_add(done + ((size_t)tk.gemm * kSub + (tk.tile % kSub)) * kCtrStride, 1u);
+          stamp(t - t_begin, 7);
         }
-        if (threadIdx.x == 64) stamp(t - t_begin, 7);
       }
       ptx::tc_fence_before_sync();
       __syncwarp();
@@ -358,7 +451,7 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
   if (threadIdx.x == 0) {
     const unsigned old = atom_add_acq_rel(exit_ctr, 1u);
     if (old == gridDim.x - 1) {
-      for (int i = 0; i < n_gemms; ++i) done[i] = 0;
+      for (int i = 0; i < n_gemms * kSub; ++i) done[(size_t)i * kCtrStride] = 0;
       *exit_ctr = 0;
       __threadfence();
     }
@@ -413,15 +506,20 @@ int env_int(const char* name, int dflt) {
   return e ? std::atoi(e) : dflt;
 }
 
-// Estimated microseconds for one GEMM laid out as `items` work items over `share` SMs: operands stream from L2 at
-// ~80 KB/us per SM (the 6300 B/clk LTS cap spread over 148 SMs), a fixed pipeline fill / drain per item, and for split-K
-// the partial round trip through L2 plus the last arriver's reads.
-double plan_cost(int tiles, int nkb, int bn, int split, int share) {
+// Estimated microseconds for one GEMM laid out as tiles x split items over `share` SMs.  Calibrated on the in-kernel
+// timeline (tests/gpu_chain_probe.py): operands stream at ~150 KB/us into one SM until the CHIP-wide L2 -> SM rate
+// (~12 TB/s, shared by everything running at this level) binds; every item pays ~1.5 us of dependency propagation, TMA
+// latency and publish; an epilogue chunk (32 columns) ~0.6 us; split-K adds the partial's round trip through L2 and one
+// L2 latency per (remote split, chunk) for the last arriver.
+double plan_cost(int tiles, int nkb, int bn, int split, int share, int n_sm) {
   const int kb_per = ceil_div(nkb, split);
-  const double per_kb = (kABytes + bn * kBK * 4) / 80e3;
-  double item = 1.0 + kb_per * per_kb + 0.25 * (bn / 32);
-  if (split > 1) item += 1.0 + 0.05 * split * (bn / 32);
-  return std::ceil((double)tiles * split / share) * item;
+  const double kb_bytes = kABytes + bn * kBK * 4;
+  const double waves = std::ceil((double)tiles * split / share);
+  const double stream = waves * kb_per * kb_bytes / 150e3;
+  const double chip = (double)tiles * split * kb_per * kb_bytes / (12e6 * share / n_sm);
+  double t = 1.5 + std::max(stream, chip) + waves * 0.6 * (bn / 32);
+  if (split > 1) t += 1.5 + 0.4 * (split - 1) * (bn / 32);
+  return t;
 }
 
 }  // namespace
@@ -528,7 +626,7 @@ void GemmChain::build(const std::vector<GemmArgs>& seq, int force_bn, int force_
         for (int s : {1, 2, 4, 8, 16}) {
           if (force_split && s != force_split) continue;
           if (s > 1 && (s - 1) * ceil_div(nkb, s) >= nkb) continue;  // would leave an empty split
-          const double c = plan_cost(tiles, nkb, cbn, s, sh);
+          const double c = plan_cost(tiles, nkb, cbn, s, sh, n_cta);
           if (c < best - 1e-9) {
             best = c;
             bn[i] = cbn;
@@ -574,10 +672,10 @@ void GemmChain::build(const std::vector<GemmArgs>& seq, int force_bn, int force_
     for (int k = 0; k < d.n_deps; ++k) {
       const int j = deps[i][k];
       d.dep[k] = j;
-      d.dep_target[k] = (unsigned)(ceil_div(seq[j].M, kBM) * ceil_div(seq[j].N, bn[j]) * 4);
+      d.dep_target[k] = (unsigned)(ceil_div(seq[j].M, kBM) * ceil_div(seq[j].N, bn[j]));  // tiles of the dependency
     }
     ctr_off[i] = ctr_count;
-    ctr_count += (size_t)tiles * 4;
+    ctr_count += (size_t)tiles;
     if (split[i] > 1) {
       ws_off[i] = ws_floats;
       ws_floats += (size_t)tiles * split[i] * kBM * bn[i];
@@ -599,7 +697,7 @@ void GemmChain::build(const std::vector<GemmArgs>& seq, int force_bn, int force_
   const size_t o_tasks = up(o_desc + sizeof(ChainGemmDesc) * n);
   const size_t o_begin = up(o_tasks + sizeof(ChainTask) * tasks.size());
   const size_t o_done = up(o_begin + sizeof(int) * begin.size());
-  const size_t o_exit = up(o_done + sizeof(unsigned) * n);
+  const size_t o_exit = up(o_done + sizeof(unsigned) * n * kSub * kCtrStride);
   const size_t o_ctr = up(o_exit + sizeof(unsigned));
   const size_t o_ws = up(o_ctr + sizeof(unsigned) * ctr_count);
   const size_t total_bytes = o_ws + sizeof(float) * ws_floats + 256;

@@ -32,13 +32,13 @@ struct alignas(128) ChainGemmDesc {
   Epilogue epi;
   float* C;
   float* ws;           // split-K partial tiles [tile][split][bn / 4][128 rows][4]; nullptr when split_k == 1
-  unsigned* tile_ctr;  // [tiles * 4] arrivals per (tile, row quarter); self-resetting
+  unsigned* tile_ctr;  // [tiles] split-K arrivals per tile; self-resetting
   int ldc, M, N, K;
   int bn, a_mn, b_mn, nkb;
   int split_k, kb_per_split, tiles_m, tiles_n;
   int n_deps;
   int dep[kChainMaxDeps];              // GEMMs of this chain whose output (or operands) this one must wait for
-  unsigned dep_target[kChainMaxDeps];  // their completion counts: tiles * 4
+  unsigned dep_target[kChainMaxDeps];  // their tile counts (completion = every tile published)
 };
 
 struct ChainTask {

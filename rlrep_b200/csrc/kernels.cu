@@ -259,6 +259,81 @@ __global__ void __launch_bounds__(256) feature_loss_finalize_kernel(const float*
   }
 }
 
+// ce_rows + rowdot(theta) + feature_loss_finalize in ONE launch (the chained CTRL feature step): CTA i does row i's
+// log-sum-exp / gradient rewrite and its reward-head prediction; the last CTA to finish (an arrival counter) adds up the
+// per-row terms in the fixed order of feature_loss_finalize_kernel and writes the three metrics.
+__global__ void __launch_bounds__(256) contrastive_head_kernel(float* __restrict__ logits, int ld, int cols, int diag_off,
+                                                               float inv_batch, const float* __restrict__ z, int ldz, int D,
+                                                               const float* __restrict__ theta_w,
+                                                               const float* __restrict__ theta_b,
+                                                               const float* __restrict__ reward, int ld_r,
+                                                               float* __restrict__ loss_rows, float* __restrict__ pred,
+                                                               float* __restrict__ dpred, float* __restrict__ metrics,
+                                                               unsigned* __restrict__ counter, int rows) {
+  __shared__ float scratch[33];
+  __shared__ bool last;
+  const int row = blockIdx.x;
+  float* l = logits + (size_t)row * ld;
+  float mx = -INFINITY;
+  for (int j = threadIdx.x; j < cols; j += 256) mx = fmaxf(mx, l[j]);
+  mx = block_max<256>(mx, scratch);
+  float sum = 0.f;
+  for (int j = threadIdx.x; j < cols; j += 256) sum += expf(l[j] - mx);
+  sum = block_sum<256>(sum, scratch);
+  const float lse = mx + logf(sum);
+  const int dj = diag_off + row;
+  const float loss = lse - l[dj];
+  __syncthreads();
+  for (int j = threadIdx.x; j < cols; j += 256) {
+    const float pr = expf(l[j] - lse);
+    l[j] = (pr - (j == dj ? 1.f : 0.f)) * inv_batch;
+  }
+  // reward head: pred = <z_row, theta.w> + theta.b
+  const float* x = z + (size_t)row * ldz;
+  float acc = 0.f;
+  if (((ldz | D) & 3) == 0 && ((reinterpret_cast<uintptr_t>(z) | reinterpret_cast<uintptr_t>(theta_w)) & 15) == 0) {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* w4 = reinterpret_cast<const float4*>(theta_w);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int j = threadIdx.x; j < D / 4; j += 256) {
+      const float4 xv = x4[j];
+      const float4 wv = __ldg(w4 + j);
+      a0 = fmaf(xv.x, wv.x, a0); a1 = fmaf(xv.y, wv.y, a1); a2 = fmaf(xv.z, wv.z, a2); a3 = fmaf(xv.w, wv.w, a3);
+    }
+    acc = (a0 + a1) + (a2 + a3);
+  } else {
+    for (int j = threadIdx.x; j < D; j += 256) acc = fmaf(x[j], __ldg(theta_w + j), acc);
+  }
+  acc = block_sum<256>(acc, scratch);
+  if (threadIdx.x == 0) {
+    const float p = acc + __ldg(theta_b);
+    loss_rows[row] = loss;
+    pred[row] = p;
+    dpred[row] = (p - reward[(size_t)row * ld_r]) * inv_batch;
+    __threadfence();
+    last = atomicAdd(counter, 1u) == (unsigned)(rows - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float ce = 0.f, se = 0.f;
+  for (int i = threadIdx.x; i < rows; i += 256) {
+    ce += __ldcg(loss_rows + i);
+    const float d = __ldcg(pred + i) - reward[(size_t)i * ld_r];
+    se = fmaf(d, d, se);
+  }
+  ce = block_sum<256>(ce, scratch);
+  se = block_sum<256>(se, scratch);
+  if (threadIdx.x == 0) {
+    const float model = ce * inv_batch;
+    const float r = 0.5f * (se * inv_batch);
+    metrics[0] = model + r;
+    metrics[1] = model;
+    metrics[2] = r;
+    *counter = 0;  // re-armed for the next launch
+  }
+}
+
 // ------------------------------------------------------------------------------------------- actor
 constexpr float kLogStdMin = -5.f, kLogStdMax = 2.f;  // sac_agent.py:64
 
@@ -813,6 +888,15 @@ void launch_feature_loss_finalize(const float* loss_rows, int rows, const float*
                                   float inv_batch, float* dpred, float* metrics, cudaStream_t s) {
   feature_loss_finalize_kernel<<<1, 256, 0, s>>>(loss_rows, rows, pred, reward, ld_r, inv_batch, dpred, metrics);
   RLREP_LAUNCHED("feature_loss_finalize", s);
+}
+
+void launch_contrastive_head(float* logits, int ld, int rows, int cols, int diag_off, float inv_batch, const float* z, int ldz,
+                             int D, const float* theta_w, const float* theta_b, const float* reward, int ld_r,
+                             float* loss_rows, float* pred, float* dpred, float* metrics, unsigned* counter,
+                             cudaStream_t s) {
+  contrastive_head_kernel<<<rows, 256, 0, s>>>(logits, ld, cols, diag_off, inv_batch, z, ldz, D, theta_w, theta_b, reward, ld_r,
+                                               loss_rows, pred, dpred, metrics, counter, rows);
+  RLREP_LAUNCHED_W("contrastive_head", s, 3.0 * 4.0 * (double)rows * cols + 4.0 * (double)rows * D, 0.0);
 }
 
 void launch_actor_sample(const float* head, int ld_head, int B, int A, const float* eps, float* action, int lda,

@@ -91,6 +91,12 @@ void launch_feature_loss_finalize(const float* loss_rows, int rows, const float*
 void launch_actor_sample(const float* head, int ld_head, int B, int A, const float* eps, float* action, int lda,
                          float* logp, cudaStream_t s, const float* obs = nullptr, int ld_obs = 0, int S = 0);
 // Backward of the above: dhead [B, ld_dhead >= 2A] from d_action [B, ldd] and the per-row d_logp scalar.
+// launch_ce_rows + launch_rowdot (reward head theta) + launch_feature_loss_finalize as one launch; `counter` is a
+// zero-initialised device word owned by the caller (arrival counter of the row CTAs, re-armed by the kernel).
+void launch_contrastive_head(float* logits, int ld, int rows, int cols, int diag_off, float inv_batch, const float* z, int ldz,
+                             int D, const float* theta_w, const float* theta_b, const float* reward, int ld_r,
+                             float* loss_rows, float* pred, float* dpred, float* metrics, unsigned* counter,
+                             cudaStream_t s);
 // select_action / batched policy evaluation in one launch: out[r, :] = tanh(mu(in[r, :S]) (+ std * in[r, S:S+A] if explore));
 // `in` / `out` may be mapped pinned host memory (see actor_act_kernel).
 void launch_actor_act(const float* in, int rows, int S, int A, int H, const float* W0, int ld0, const float* b0,

@@ -14,8 +14,23 @@
 
 namespace rlrep {
 
+// `src` may also be DEVICE memory (a batch assembled by the device-resident pixel replay ring, pixel_replay.cuh): then the
+// input is already in HBM and goes to its buffer with one device-to-device copy, no staging and no PCIe traffic.
+inline bool is_device_pointer(const void* p) {
+  cudaPointerAttributes at;
+  if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return at.type == cudaMemoryTypeDevice;
+}
+
 inline void stage_h2d(unsigned char*& cursor, void* dev, const void* src, size_t bytes, cudaStream_t s) {
   constexpr size_t kSlice = size_t(2) << 20;
+  if (bytes >= 4096 && is_device_pointer(src)) {
+    RLREP_CUDA(cudaMemcpyAsync(dev, src, bytes, cudaMemcpyDeviceToDevice, s));
+    return;
+  }
   if (bytes < 2 * kSlice) {
     std::memcpy(cursor, src, bytes);
     RLREP_CUDA(cudaMemcpyAsync(dev, cursor, bytes, cudaMemcpyHostToDevice, s));

@@ -15,6 +15,28 @@ import torch
 from . import _lib
 
 
+def _frames_arg(t):
+    """A uint8 frame stack as (keep-alive object, pointer).  CUDA tensors -- batches assembled by the device-resident
+    replay ring (rlrep_b200.PixelReplayBuffer) -- are handed over by device pointer: the C update recognises device memory
+    and copies it device-to-device instead of staging it over PCIe.  Anything else becomes a contiguous host array."""
+    if isinstance(t, torch.Tensor) and t.is_cuda:
+        t = t.contiguous()
+        assert t.dtype == torch.uint8, "frame stacks must be uint8 like the reference's buffers"
+        return t, t.data_ptr()
+    a = np.ascontiguousarray(torch.as_tensor(t).cpu().numpy())
+    assert a.dtype == np.uint8, "frame stacks must be uint8 like the reference's buffers"
+    return a, a.ctypes.data
+
+
+def _host_f32(t):
+    return np.ascontiguousarray(torch.as_tensor(t).detach().cpu().numpy(), dtype=np.float32).reshape(-1)
+
+
+def _sync_if_cuda(*ts):
+    if any(isinstance(t, torch.Tensor) and t.is_cuda for t in ts):
+        torch.cuda.current_stream().synchronize()  # the C library reads the tensors on its own stream
+
+
 class ConvEncoder:
     LAYERS = ("convnet.0", "convnet.2", "convnet.4", "convnet.6")
 
@@ -273,18 +295,17 @@ class DrQv2:
         if self._step % self.update_every != 0:
             return {}
         batch = next(replay_iter)
-        img, action, reward, discount, next_img = (np.ascontiguousarray(torch.as_tensor(t).cpu().numpy()) for t in batch[:5])
-        n = img.shape[0]
+        n = batch[0].shape[0]
+        (img, p_img), (next_img, p_next) = _frames_arg(batch[0]), _frames_arg(batch[4])
+        action, reward, discount = _host_f32(batch[1]), _host_f32(batch[2]), _host_f32(batch[3])
         self._ensure(n)
         shifts, eps = self._draw(n)
         stddev = float(self.stddev_schedule(step))
         m = np.zeros(8, dtype=np.float32)
-        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32).reshape(-1)
-        action, reward, discount = f32(action), f32(reward), f32(discount)
         shifts, eps = np.ascontiguousarray(shifts), np.ascontiguousarray(eps)
-        assert img.dtype == np.uint8 and next_img.dtype == np.uint8, "frame stacks must be uint8 like the reference's buffers"
-        _lib.check(self.lib.rlrep_drq_update(self._h, img.ctypes.data, action.ctypes.data, reward.ctypes.data,
-                                             discount.ctypes.data, next_img.ctypes.data, shifts.ctypes.data,
+        _sync_if_cuda(img, next_img)
+        _lib.check(self.lib.rlrep_drq_update(self._h, p_img, action.ctypes.data, reward.ctypes.data,
+                                             discount.ctypes.data, p_next, shifts.ctypes.data,
                                              eps.ctypes.data, stddev, m.ctypes.data))
         return {"loss/actor_loss": float(m[4]), "info/policy_std": stddev, "loss/critic_loss": float(m[0]),
                 "info/q_pred": float(m[1]), "info/q_target": float(m[2]), "info/reward": float(m[3])}
@@ -485,20 +506,17 @@ class MuLVDrQv2:
         if step % self.up_every != 0:
             return {}
         batch = next(replay_iter)
-        img, action, reward, discount, next_img, img_step1 = (np.ascontiguousarray(torch.as_tensor(t).cpu().numpy())
-                                                              for t in batch[:6])
-        n = img.shape[0]
+        n = batch[0].shape[0]
         self._ensure(n)
-        assert img.dtype == np.uint8 and next_img.dtype == np.uint8 and img_step1.dtype == np.uint8, \
-            "frames must be uint8 like the reference's buffers"
-        step1 = np.ascontiguousarray(img_step1[:, -3:, :, :])  # drqv2.py:330: only the newest frame is predicted
+        (img, p_img), (next_img, p_next) = _frames_arg(batch[0]), _frames_arg(batch[4])
+        step1, p_step1 = _frames_arg(batch[5][:, -3:, :, :])  # drqv2.py:330: only the newest frame is predicted
+        action, reward, discount = _host_f32(batch[1]), _host_f32(batch[2]), _host_f32(batch[3])
         shifts, eps_z, eps_act, noise = (np.ascontiguousarray(a) for a in self._draw(n))
         stddev = float(self.stddev_schedule(step))
-        f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32).reshape(-1)
-        action, reward, discount = f32(action), f32(reward), f32(discount)
         m = np.zeros(8, dtype=np.float32)
-        _lib.check(self.lib.rlrep_mulv_update(self._h, img.ctypes.data, action.ctypes.data, reward.ctypes.data,
-                                              discount.ctypes.data, next_img.ctypes.data, step1.ctypes.data,
+        _sync_if_cuda(img, next_img, step1)
+        _lib.check(self.lib.rlrep_mulv_update(self._h, p_img, action.ctypes.data, reward.ctypes.data,
+                                              discount.ctypes.data, p_next, p_step1,
                                               shifts.ctypes.data, eps_z.ctypes.data, eps_act.ctypes.data,
                                               noise.ctypes.data, stddev, m.ctypes.data))
         return {k: float(v) for k, v in zip(self.METRICS, m)}

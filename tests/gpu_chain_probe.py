@@ -63,13 +63,13 @@ valid = d[:, :, 0] > 0
 t0 = d[:, :, 0][valid].min()
 print(f"{which} chain: {len(specs)} GEMMs, {levels} levels, {ms * 1e3:.1f} us per launch (bn={bn}, split={split}); "
       f"{int(valid.sum())} items stamped, last publish at {(d[:, :, [5, 7]].max() - t0) / 1e3:.1f} us")
-names = ["pick", "deps", "tma", "opnd", "acc", "epi", "arrive", "publish"]
+names = ["pick", "deps", "tma", "opnd", "acc", "epi", "arrive", "publish", None, "stored"]
 for g in range(len(specs)):
     sel = valid & ((d[:, :, 8] & 0xFFFF) == g)
     if not sel.any():
         continue
     rows = []
-    for e in range(8):
+    for e in (0, 1, 2, 3, 4, 5, 6, 9, 7):
         v = d[:, :, e][sel]
         v = v[v > 0]
         rows.append(f"{names[e]} {((v.min() - t0) / 1e3):6.1f}..{((v.max() - t0) / 1e3):6.1f}" if len(v) else f"{names[e]}   -")
@@ -80,4 +80,4 @@ def med(a, b):
     x = (d[:, :, b] - d[:, :, a])[valid & (d[:, :, a] > 0) & (d[:, :, b] > 0)]
     return float(np.median(x)) / 1e3 if len(x) else float("nan")
 print(f"  medians: deps wait {med(0, 1):.2f} | deps->tma {med(1, 2):.2f} | deps->operands {med(1, 3):.2f} | operands->acc {med(3, 4):.2f} "
-      f"| acc->epi {med(4, 5):.2f} | epi->arrive {med(5, 6):.2f} | epi->publish {med(5, 7):.2f}")
+      f"| acc->epi {med(4, 5):.2f} | epi->arrive {med(5, 6):.2f} | epi->stored {med(5, 9):.2f} | stored->publish {med(9, 7):.2f}")

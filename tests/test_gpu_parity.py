@@ -416,7 +416,7 @@ def test_population_of_independent_agents():
     alone = []
     for i in range(n):
         agent, buf, _, _ = make_pair(alg, shp["S"], shp["A"], kw, rows=2000, seed=i)
-        idx, eps = [], []
+        agent._ensure(B)
         np.random.seed(10 + i)
         torch.manual_seed(10 + i)
         draws = [agent._draw(buf, B) for _ in range(3)]

@@ -10,7 +10,7 @@ import torch
 from oracle import rl_oracle as O
 
 GOLDEN = Path(__file__).resolve().parent / "golden"
-CASES = sorted(p.stem for p in GOLDEN.glob("*.npz") if not p.stem.startswith(("drqv2", "mulvdrq", "ldiffsr")))
+CASES = sorted(p.stem for p in GOLDEN.glob("*.npz") if not p.stem.startswith(("drqv2", "mulvdrq", "ldiffsr", "pixreplay")))
 DRQ_CASES = sorted(p.stem for p in GOLDEN.glob("drqv2*.npz"))
 MULV_CASES = sorted(p.stem for p in GOLDEN.glob("mulvdrq*.npz"))
 LDIFFSR_CASES = sorted(p.stem for p in GOLDEN.glob("ldiffsr*.npz"))
@@ -151,3 +151,20 @@ def test_ldiffsr_oracle_reproduces_reference(name):
         stride = max(1, t.numel() // 256)
         assert abs(t.norm().item() - stats[1]) <= 1e-5 * max(stats[1], 1e-6), k
         assert np.linalg.norm(t[::stride][:256].numpy() - sample) <= 2e-5 * max(np.linalg.norm(sample), 1e-6) + 1e-7, k
+
+
+def test_pixel_replay_oracle_matches_reference_fixture():
+    """oracle/pixel_replay_oracle.py vs outputs of the real EfficientReplayBuffer (efficient_buffer.py:35-149) recorded by
+    oracle/make_golden_pixreplay.py: valid mask, length and all six gathered arrays, bit for bit, across two ring wraps."""
+    import numpy as np
+    from pathlib import Path
+    from oracle.pixel_replay_oracle import OraclePixelReplay, synthetic_stream
+    g = np.load(Path(__file__).parent / "golden" / "pixreplay.npz")
+    ora = OraclePixelReplay(61, 24, 3, 0.99, 3)
+    for t, ts in enumerate(synthetic_stream(150, frame_stack=3, seed=5)):
+        ora.add(ts)
+        if f"idx_{t}" in g:
+            assert np.array_equal(ora.valid, g[f"valid_{t}"]) and len(ora) == int(g[f"len_{t}"])
+            got = ora.gather(g[f"idx_{t}"])
+            for name, a in zip(("obs", "act", "rew", "dis", "nobs", "sobs"), got):
+                assert a.dtype == g[f"{name}_{t}"].dtype and np.array_equal(a, g[f"{name}_{t}"]), (t, name)
