@@ -238,18 +238,19 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
       for (int t = t_begin; t < t_end; ++t) {
         const ChainTask tk = tasks[t];
         const ChainGemmDesc* g = gemms + tk.gemm;
+        // Everything that does not depend on the dependencies' DATA happens before the wait: the item's descriptor fields
+        // go to registers and the tensor maps are made visible to the TMA unit, so that once the counters are reached only
+        // the fences stand between this thread and the first operand load.
         const int n_deps = g->n_deps;
-        stamp(t - t_begin, 0);
-        if (dbg != nullptr && t - t_begin < kDbgItems)  // slot 8: which item this is
-          dbg[((size_t)blockIdx.x * kDbgItems + (t - t_begin)) * kDbgEvents + 8] =
-              (unsigned long long)tk.gemm | ((unsigned long long)tk.tile << 16) | ((unsigned long long)tk.split << 40);
-        for (int d = 0; d < n_deps; ++d) wait_counter(done, g->dep[d], (int)g->dep_target[d]);
-        if (n_deps > 0) {
-          fence_acquire_gpu();
-          // the tiles were written through the generic proxy by other SMs; TMA reads through the async proxy
-          if (!(flags & kFlagNoProxyFence)) fence_proxy_async_global();
+        const int bn = g->bn, a_mn = g->a_mn, b_mn = g->b_mn;
+        const int m0 = (tk.tile % g->tiles_m) * kBM, n0 = (tk.tile / g->tiles_m) * bn;
+        const int kb0 = tk.split * g->kb_per_split, kb1 = min(g->nkb, kb0 + g->kb_per_split);
+        int dep_id[kChainMaxDeps], dep_tiles[kChainMaxDeps];
+#pragma unroll
+        for (int d = 0; d < kChainMaxDeps; ++d) {
+          dep_id[d] = d < n_deps ? g->dep[d] : 0;
+          dep_tiles[d] = d < n_deps ? (int)g->dep_target[d] : 0;
         }
-        stamp(t - t_begin, 1);
         if (tk.gemm != last_gemm) {
           if (!(flags & kFlagNoTensormapFence)) {
             fence_tensormap_acquire(&g->tmA);
@@ -257,9 +258,19 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
           }
           last_gemm = tk.gemm;
         }
-        const int bn = g->bn, a_mn = g->a_mn, b_mn = g->b_mn;
-        const int m0 = (tk.tile % g->tiles_m) * kBM, n0 = (tk.tile / g->tiles_m) * bn;
-        const int kb0 = tk.split * g->kb_per_split, kb1 = min(g->nkb, kb0 + g->kb_per_split);
+        stamp(t - t_begin, 0);
+        if (dbg != nullptr && t - t_begin < kDbgItems)  // slot 8: which item this is
+          dbg[((size_t)blockIdx.x * kDbgItems + (t - t_begin)) * kDbgEvents + 8] =
+              (unsigned long long)tk.gemm | ((unsigned long long)tk.tile << 16) | ((unsigned long long)tk.split << 40);
+#pragma unroll
+        for (int d = 0; d < kChainMaxDeps; ++d)
+          if (d < n_deps) wait_counter(done, dep_id[d], dep_tiles[d]);
+        if (n_deps > 0) {
+          fence_acquire_gpu();
+          // the tiles were written through the generic proxy by other SMs; TMA reads through the async proxy
+          if (!(flags & kFlagNoProxyFence)) fence_proxy_async_global();
+        }
+        stamp(t - t_begin, 1);
         const uint32_t tx = kABytes + bn * kBK * 4;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % kStages;

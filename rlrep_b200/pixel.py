@@ -576,6 +576,12 @@ class LatentDiffSRDrQv2:
         self._batch = None
         self._pending = {}
 
+    @property
+    def gpu_launches_last_update(self):
+        v = C.c_int()
+        _lib.check(self.lib.rlrep_ldiff_last_launches(self._h, C.byref(v)))
+        return v.value
+
     def _draw(self, n):
         """RNG consumption of one updating train_step in the reference's order (oracle/ldiffsr_oracle.py header)."""
         L, A, keep = self.L, self.action_dim, 0.9
@@ -684,23 +690,33 @@ class LatentDiffSRDrQv2:
         if self._step % self.update_every != 0:
             return {}
         batch = next(replay_iter)
-        img, action, reward, discount, next_img, next_step = (np.ascontiguousarray(torch.as_tensor(t).cpu().numpy())
-                                                              for t in batch[:6])
-        n = img.shape[0]
+        n = batch[0].shape[0]
         self._ensure(n)
         d = self._draw(n)
-        frames = np.ascontiguousarray(np.concatenate([img.reshape(3 * n, 3, 84, 84), next_step[:, -3:]], axis=0))
-        next_frames = np.ascontiguousarray(next_img.reshape(3 * n, 3, 84, 84))
+        if all(isinstance(t, torch.Tensor) and t.is_cuda for t in (batch[0], batch[4], batch[5])):
+            # a batch assembled on the device (PixelReplayBuffer): the per-frame views are built there as well
+            frames = torch.cat([batch[0].reshape(3 * n, 3, 84, 84), batch[5][:, -3:]], dim=0).contiguous()
+            next_frames = batch[4].reshape(3 * n, 3, 84, 84).contiguous()
+            assert frames.dtype == torch.uint8 and next_frames.dtype == torch.uint8
+            p_frames, p_next = frames.data_ptr(), next_frames.data_ptr()
+            torch.cuda.current_stream().synchronize()
+        else:
+            img, next_img, next_step = (np.ascontiguousarray(torch.as_tensor(t).cpu().numpy()) for t in (batch[0], batch[4], batch[5]))
+            frames = np.ascontiguousarray(np.concatenate([img.reshape(3 * n, 3, 84, 84), next_step[:, -3:]], axis=0))
+            next_frames = np.ascontiguousarray(next_img.reshape(3 * n, 3, 84, 84))
+            assert frames.dtype == np.uint8 and next_frames.dtype == np.uint8
+            p_frames, p_next = frames.ctypes.data, next_frames.ctypes.data
+        action, reward, discount = (torch.as_tensor(t).detach().cpu().numpy() for t in batch[1:4])
         ident = np.full((n, 2), 4, dtype=np.int32)
         shifts = np.ascontiguousarray(np.concatenate([np.repeat(d["shifts"][0], 3, axis=0), ident], axis=0), dtype=np.int32)
         next_shifts = np.ascontiguousarray(np.repeat(d["shifts"][1], 3, axis=0), dtype=np.int32)
         f32 = lambda a: np.ascontiguousarray(a, dtype=np.float32)
-        keep = dict(frames=frames, next_frames=next_frames, shifts=shifts, next_shifts=next_shifts, action=f32(action),
+        keep = dict(shifts=shifts, next_shifts=next_shifts, action=f32(action),
                     reward=f32(reward).reshape(-1), discount=f32(discount).reshape(-1), eps_post=f32(d["eps_post"]),
                     alphabar=f32(d["alphabar"]), temb=f32(d["temb"]), noise=f32(d["noise"]), psi_masks=f32(d["psi_masks"]),
                     zeta_masks=f32(d["zeta_masks"]), eps_act=f32(d["eps_act"]))
         stddev = float(self.stddev_schedule(step))
-        inp = LdiffInputs(stddev=stddev, **{k: v.ctypes.data for k, v in keep.items()})
+        inp = LdiffInputs(stddev=stddev, frames=p_frames, next_frames=p_next, **{k: v.ctypes.data for k, v in keep.items()})
         m = np.zeros(8, dtype=np.float32)
         _lib.check(self.lib.rlrep_ldiff_update(self._h, C.byref(inp), m.ctypes.data))
         return {"loss/recon_loss": float(m[0]), "loss/kl_loss": float(m[1]), "loss/score_loss": float(m[2]), "loss/reg_loss": 0.0,

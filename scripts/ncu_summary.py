@@ -34,6 +34,9 @@ def main():
         rows = list(csv.reader(io.StringIO(raw)))
         hdr, units, data = rows[0], rows[1], rows[2:]
         cols = [hdr.index(k) for k in KEEP if k in hdr]
+        extra = re.compile(r"stalled_no_instruction|stalled_long_scoreboard|stalled_barrier|issue_active.*pct|lts__t_bytes.sum$|"
+                           r"lts__throughput.avg.pct|l1tex__m_xbar2l1tex_read_bytes.sum.per_second")
+        cols += [i for i, h in enumerate(hdr) if extra.search(h) and i not in cols][:12]
         out = ROOT / "profiles" / (Path(rep).stem + "_summary.csv")
         with open(out, "w", newline="") as f:
             w = csv.writer(f)
@@ -47,7 +50,7 @@ def main():
             b = float(r[ir]) * UNIT.get(units[ir], 1.0) + float(r[iw]) * UNIT.get(units[iw], 1.0)
             per.setdefault(short(r[ik]), []).append(b)
         for k, v in per.items():
-            key = {"adam_polyak_kernel": "adam_polyak", "gemm_tf32_kernel": "gemm_tf32", "ce_rows_kernel": "ce_rows"}.get(k, k)
+            key = k[:-7] if k.endswith("_kernel") else k  # the launch label bench.py uses
             traffic.setdefault(workload, {})[key] = sum(v) / len(v)
         print(out, {k: round(sum(v) / len(v) / 1e6, 2) for k, v in per.items()}, "MB/launch")
     tpath.write_text(json.dumps(traffic, indent=1) + "\n")

@@ -28,5 +28,6 @@ demangle = subprocess.run(["c++filt"], input="\n".join(counts), capture_output=T
 for (k, c), name in zip(counts.items(), demangle):
     if not any(c[x] for x in ("UTCHMMA", "UTMALDG", "LDTM")):
         continue
-    short = re.sub(r"\(.*", "", name).replace("rlrep::", "").replace("(anonymous namespace)::", "").replace("tc::", "")
+    short = name.replace("(anonymous namespace)::", "").replace("rlrep::", "").replace("tc::", "").replace("void ", "")
+    short = re.sub(r"\(.*", "", short)
     print(f"{short[:70]:70s} sass={total[k]:6d}  " + "  ".join(f"{x}={c[x]}" for x in ("UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "UTCBAR", "UTMACCTL", "UTCATOMSWS", "SYNCS", "RED", "ATOMG") if c[x]))
