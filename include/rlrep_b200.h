@@ -33,7 +33,7 @@ extern "C" {
 #define RLREP_EXPORT
 #endif
 
-#define RLREP_ABI_VERSION 2
+#define RLREP_ABI_VERSION 3
 
 RLREP_EXPORT int rlrep_abi_version(void);
 RLREP_EXPORT const char* rlrep_last_error(void);

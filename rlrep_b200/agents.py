@@ -70,18 +70,35 @@ class _Handle:
         except Exception:
             pass
 
+    # `logical` maps a tensor name to the (rows, cols) the caller sees when the handle was built with hidden widths rounded
+    # up to a multiple of 32 (see SACAgent._pad): reads crop to it, writes zero-pad from it.
+    logical: dict = {}
+
+    def _logical_shape(self, name, rows, cols):
+        base = name.split("/", 1)[1] if name.startswith("optim.") else name
+        return self.logical.get(base, (rows, cols))
+
     def read(self, name) -> torch.Tensor:
         i, _, rows, cols = self.index[name]
         out = np.empty(rows * cols, dtype=np.float32)
         _lib.check(self.lib.rlrep_agent_tensor_read(self.h, i, out.ctypes.data))
-        t = torch.from_numpy(out)
-        return t.reshape(rows, cols) if not name.endswith(".bias") else t.reshape(rows)
+        t = torch.from_numpy(out).reshape(rows, cols)
+        lr, lc = self._logical_shape(name, rows, cols)
+        if (lr, lc) != (rows, cols):
+            t = t[:lr, :lc].contiguous()
+        return t if not name.endswith(".bias") else t.reshape(lr)
 
     def write(self, name, value):
         i, _, rows, cols = self.index[name]
-        arr = np.ascontiguousarray(torch.as_tensor(value).detach().cpu().float().numpy().reshape(-1))
-        if arr.size != rows * cols:
-            raise ValueError(f"{name}: expected {rows * cols} values, got {arr.size}")
+        lr, lc = self._logical_shape(name, rows, cols)
+        arr = torch.as_tensor(value).detach().cpu().float().reshape(-1)
+        if arr.numel() != lr * lc:
+            raise ValueError(f"{name}: expected {lr * lc} values, got {arr.numel()}")
+        if (lr, lc) != (rows, cols):
+            full = torch.zeros(rows, cols)
+            full[:lr, :lc] = arr.reshape(lr, lc)
+            arr = full.reshape(-1)
+        arr = np.ascontiguousarray(arr.numpy())
         _lib.check(self.lib.rlrep_agent_tensor_write(self.h, i, arr.ctypes.data))
 
     def train(self, ring_handle, idx: np.ndarray, eps: np.ndarray) -> np.ndarray:
@@ -149,7 +166,7 @@ class SACAgent:
         c = _lib.AgentConfig()
         c.alg = _lib.ALG[self.alg]
         c.state_dim, c.action_dim, c.batch_size = self.state_dim, self.action_dim, int(batch_size)
-        c.hidden_dim, c.feature_dim, c.actor_hidden_dim = self._hidden, 0, self._hidden
+        c.hidden_dim, c.feature_dim, c.actor_hidden_dim = self._pad(self._hidden), 0, self._pad(self._hidden)
         c.feature_steps = 0
         c.lr_critic = c.lr_actor = c.lr_alpha = self._lr
         c.lr_feature = 0.0
@@ -202,8 +219,31 @@ class SACAgent:
             self.load_optimizer_state_dict(carried)
         return self._h
 
+    @staticmethod
+    def _pad(width):
+        """Hidden widths the tensor-core path wants as multiples of 32.  A hidden unit whose incoming and outgoing weights
+        and bias are zero outputs ELU(0) = ReLU(0) = tanh(0) = sin(0) = 0, receives a zero gradient and gives a zero
+        gradient to everything it touches, and Adam keeps zeros at zero: widening a hidden layer with such units is exact.
+        The handle is therefore built with the width rounded up, and weights are zero-padded / cropped at the boundary, so
+        any `hidden_dim` works like in the reference.  (Feature widths entering a mean -- LV-Rep's KL, Diff-SR's score
+        layout -- cannot be padded this way and must be multiples of 32.)"""
+        return (int(width) + 31) // 32 * 32
+
     def _make_handle(self, batch):
-        return _Handle(self._config(batch))
+        h = _Handle(self._config(batch))
+        self._attach_logical(h)
+        return h
+
+    def _attach_logical(self, h):
+        logical = {}
+        for name, out, inp, _ in self._layers():
+            logical[name + ".weight"], logical[name + ".bias"] = (out, inp), (out, 1)
+        targets = {}
+        for k, v in logical.items():  # Polyak copies carry the source module's shapes
+            mod = k.split(".", 1)[0]
+            targets[mod + "_target." + k.split(".", 1)[1]] = v
+        logical.update(targets)
+        h.logical = {k: v for k, v in logical.items() if k in h.index and tuple(h.index[k][2:]) != v}
 
     def state_dict(self):
         """All parameters and Polyak targets under the reference's state_dict names, plus float64 `log_alpha`."""
@@ -345,7 +385,9 @@ class CTRLSACAgent(SACAgent):
 
     def _config(self, batch_size):
         c = super()._config(batch_size)
-        c.feature_dim, c.actor_hidden_dim = self.feature_dim, 256  # actor hidden fixed at 256, ctrlsac_agent.py:188-194
+        # actor hidden fixed at 256, ctrlsac_agent.py:188-194; the feature width may be padded too (zero features are inert:
+        # no mean runs over the feature axis in CTRL)
+        c.feature_dim, c.actor_hidden_dim = self._pad(self.feature_dim), 256
         c.feature_steps = self.extra_feature_steps + 1
         c.lr_feature = c.lr_critic = self._lr
         c.lr_actor = c.lr_alpha = self._lr / 3  # :195-197
@@ -540,13 +582,13 @@ class SPEDERSACAgent(SACAgent):
 
     def _config(self, batch_size):
         c = super()._config(batch_size)  # critic / actor / alpha all at critic_and_actor_lr (:168-179)
-        c.feature_dim = self.feature_dim
+        c.feature_dim = self._pad(self.feature_dim)  # zero features are inert in SPEDER's losses as well
         c.feature_steps = self.extra_feature_steps + 1
         c.lr_feature = self._feat_lr
         c.feature_tau = self.feature_tau
         c.use_feature_target = int(self.use_feature_target)
-        c.phi_hidden_dim, c.phi_hidden_depth = self._phi
-        c.mu_hidden_dim, c.mu_hidden_depth = self._mu
+        c.phi_hidden_dim, c.phi_hidden_depth = self._pad(self._phi[0]) if self._phi[1] > 0 else self._phi[0], self._phi[1]
+        c.mu_hidden_dim, c.mu_hidden_depth = self._pad(self._mu[0]) if self._mu[1] > 0 else self._mu[0], self._mu[1]
         return c
 
     def _layers(self):
@@ -605,8 +647,9 @@ class DIFFSRSACAgent(SACAgent):
         c.feature_dim = self.feature_dim
         c.feature_steps = self.extra_feature_steps + 1
         c.lr_feature = self._feat_lr
-        c.phi_hidden_dim, c.phi_hidden_depth = self._phi
-        c.nabla_mu_hidden_dim, c.nabla_mu_hidden_depth = self._nabla
+        c.phi_hidden_dim, c.phi_hidden_depth = self._pad(self._phi[0]) if self._phi[1] > 0 else self._phi[0], self._phi[1]
+        c.nabla_mu_hidden_dim, c.nabla_mu_hidden_depth = (self._pad(self._nabla[0]) if self._nabla[1] > 0 else self._nabla[0],
+                                                          self._nabla[1])
         c.num_noises = self.num_noises
         c.sigma_scale_factor = self.sigma_scale_factor
         return c

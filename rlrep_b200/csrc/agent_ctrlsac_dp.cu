@@ -15,8 +15,18 @@
 //   critic / actor plain data parallelism: means are over the global batch (every partial is divided by Bg), gradients
 //                  and loss sums are all-reduced; the float64 temperature step runs on the all-reduced mean.
 // Kernels are the single-GPU ones; b = 2048 rows per rank makes every GEMM throughput-bound, so the step runs eagerly
-// (no graph).  The mu branch with its two collectives runs on a side stream so that the NVLink transfers overlap the
-// phi branch's GEMMs.
+// (no graph).
+//
+// Overlap (round 2).  One all-gather of mu_all (134 MB at 8 x 2048 rows) followed by one [b, Bg] logits GEMM leaves the
+// NVLink transfer exposed (nothing else can run: the logits need mu_all), and likewise the reduce-scatter behind the
+// d mu_all GEMM.  Both are pipelined in S ROW SLICES of the rank's batch: slice s of every rank's mu is gathered on a
+// communication stream while the logits columns of slice s-1 are being computed, and the d mu_all rows of slice s are
+// reduce-scattered while slice s+1 is computed.  The global column order of the logits becomes (slice, rank, row in
+// slice) instead of (rank, row) -- a permutation of the softmax axis, applied consistently to mu_all, G and d mu_all, so
+// every buffer stays contiguous, nothing is accumulated and the result is unchanged; only the column of a row's positive
+// moves (ce_rows: diag_blk / diag_stride).
+#include <algorithm>
+
 #include "agent_base.cuh"
 #include "comm.cuh"
 
@@ -34,6 +44,12 @@ class CtrlSacShardedAgent final : public SacBase {
     N_ = comm_->world;
     rank_ = comm_->rank;
     Bg_ = B_ * N_;
+    // row slices of the collectives' pipeline: slice rows must stay a multiple of 32 (MN-major GEMM operands)
+    int want_slices = 4;
+    if (const char* e = std::getenv("RLREP_DP_SLICES")) want_slices = std::max(1, std::atoi(e));
+    SL_ = 1;
+    for (int cand : {8, 4, 2})
+      if (cand <= want_slices && B_ % cand == 0 && (B_ / cand) % 32 == 0) { SL_ = cand; break; }
     cfg.use_graph = 0;
     dual_share_ = 1.0;  // throughput-bound GEMMs: plan each one for the whole GPU even when two branches overlap
     RLREP_CHECK(K_ >= 1 && K_ <= kMaxFeatureSteps, "extra_feature_steps out of range");
@@ -135,27 +151,52 @@ class CtrlSacShardedAgent final : public SacBase {
     const Linear th = th_.view(feat_g_);
     const float inv_bg = 1.f / (float)Bg_;
     cudaStream_t s = stream, s1 = side();
-    // mu and its all-gather on the side stream, phi on the main stream: the NVLink transfer hides behind phi's GEMMs.
-    // Every rank issues the collectives in the same host order, which is all NCCL asks for.
+    // mu on the side stream, phi on the main stream; the all-gather of mu runs slice by slice on the communication
+    // stream, and the logits columns of a slice are computed as soon as that slice has arrived.  Every rank issues the
+    // collectives in the same host order, which is all NCCL asks for.
+    cudaStream_t cs = aux(0);
+    const int bs = B_ / SL_;      // rows per slice on this rank
+    const int gs = Bg_ / SL_;     // columns (global rows) per slice
     fork();
     linear_fwd(gemm_, s1, B_, s2(), n1, ACT_ELU, g1_, H_);
     linear_fwd(gemm_, s1, B_, Mat{g1_, H_}, n2, ACT_ELU, g2_, H_);
     linear_fwd(gemm_, s1, B_, Mat{g2_, H_}, n3, ACT_TANH, zmu_, D_);
-    comm_->all_gather(zmu_, zmu_all_, (size_t)B_ * D_, s1);
+    wait_for(cs, mark(s1));
+    cudaEvent_t gathered[8];
+    for (int sl = 0; sl < SL_; ++sl) {  // slice sl of mu_all: rank r's rows [sl * bs, (sl + 1) * bs) at block offset r * bs
+      comm_->all_gather(zmu_ + (size_t)sl * bs * D_, zmu_all_ + (size_t)sl * gs * D_, (size_t)bs * D_, cs);
+      gathered[sl] = mark(cs);
+    }
     phi_forward(sa(), Mat(), 0, zphi_);
-    join();
-    {  // logits_local[i, j] = <phi_i, mu_all_j>
+    for (int sl = 0; sl < SL_; ++sl) {  // logits_local[i, sl * gs + j] = <phi_i, mu_all_slice_j>
+      wait_for(s, gathered[sl]);
       GemmArgs a;
-      a.M = B_; a.N = Bg_; a.K = D_;
+      a.M = B_; a.N = gs; a.K = D_;
       a.A = zphi_; a.lda = D_;
-      a.B = zmu_all_; a.ldb = D_;
-      a.C = logits_; a.ldc = Bg_;
+      a.B = zmu_all_ + (size_t)sl * gs * D_; a.ldb = D_;
+      a.C = logits_ + (size_t)sl * gs; a.ldc = Bg_;
       gemm_.run(a, s);
     }
-    launch_ce_rows(logits_, Bg_, B_, Bg_, rank_ * B_, inv_bg, loss_rows_, s);
+    join();
+    // positives: local row i = (slice, t) sits at column slice * gs + rank * bs + t
+    launch_ce_rows(logits_, Bg_, B_, Bg_, rank_ * bs, inv_bg, loss_rows_, s, bs, gs);
     launch_rowdot(zphi_, D_, B_, D_, th.W, th.b, rpred_, s);
     launch_feature_loss_finalize(loss_rows_, B_, rpred_, reward(), R_, inv_bg, drp_, metrics_dev_ + 0, s);
-    {  // d z_phi = G_local mu_all + drp (x) theta.w
+    // every rank's contribution to d mu of ALL rows, slice by slice: G_local[:, slice]^T phi_local -> reduce-scatter of the
+    // slice on the communication stream while the next slice (and then d z_phi and the phi backward) is computed
+    cudaEvent_t scattered = nullptr;
+    for (int sl = 0; sl < SL_; ++sl) {
+      GemmArgs a;
+      a.M = gs; a.N = D_; a.K = B_;
+      a.A = logits_ + (size_t)sl * gs; a.lda = Bg_; a.a_mn = true;
+      a.B = zphi_; a.ldb = D_; a.b_mn = true;
+      a.C = dmu_all_ + (size_t)sl * gs * D_; a.ldc = D_;
+      gemm_.run(a, s);
+      wait_for(cs, mark(s));
+      comm_->reduce_scatter(dmu_all_ + (size_t)sl * gs * D_, dzmu_ + (size_t)sl * bs * D_, (size_t)bs * D_, cs);
+      scattered = mark(cs);
+    }
+    {  // d z_phi = G_local mu_all + drp (x) theta.w   (the same column permutation on both operands)
       GemmArgs a;
       a.M = B_; a.N = D_; a.K = Bg_;
       a.A = logits_; a.lda = Bg_;
@@ -164,17 +205,9 @@ class CtrlSacShardedAgent final : public SacBase {
       a.epi.r1_u = drp_; a.epi.r1_v = th.W;
       gemm_.run(a, s);
     }
-    {  // every rank's contribution to d mu of ALL rows: G_local^T phi_local
-      GemmArgs a;
-      a.M = Bg_; a.N = D_; a.K = B_;
-      a.A = logits_; a.lda = Bg_; a.a_mn = true;
-      a.B = zphi_; a.ldb = D_; a.b_mn = true;
-      a.C = dmu_all_; a.ldc = D_;
-      gemm_.run(a, s);
-    }
-    // side stream: reduce-scatter of d mu and the mu backward; main stream: the phi backward
+    // side stream: the mu backward once its gradient has arrived; main stream: the phi backward
     fork();
-    comm_->reduce_scatter(dmu_all_, dzmu_, (size_t)B_ * D_, s1);
+    wait_for(s1, scattered);
     linear_wgrad(gemm_, s, B_, Mat{dzphi_, D_}, Mat{h2_, H_}, l3, Mat(), 0, false);
     linear_dgrad(gemm_, s, B_, Mat{dzphi_, D_}, l3, DACT_ELU_OUT, Mat{h2_, H_}, dh2_, H_);
     linear_wgrad(gemm_, s, B_, Mat{dh2_, H_}, Mat{h1_, H_}, l2, Mat(), 0, false);
@@ -197,6 +230,7 @@ class CtrlSacShardedAgent final : public SacBase {
                         bias_job(B_, Mat{dg1_, H_}, n1)};
       launch_colreduce_multi(jobs, 3, s1);
     }
+    join_aux(0, s);
     join();
     comm_->all_reduce(feat_g_.g, feat_g_.n, s);
     launch_adam_polyak(feat_g_.p, feat_g_.g, feat_g_.m, feat_g_.v, feat_g_.n, &ctl->feat[k],
@@ -260,7 +294,7 @@ class CtrlSacShardedAgent final : public SacBase {
   }
 
   Comm* comm_ = nullptr;
-  int H_ = 0, D_ = 0, K_ = 0, N_ = 1, rank_ = 0, Bg_ = 0, off_r_ = 0, off_d_ = 0, off_s2_ = 0;
+  int H_ = 0, D_ = 0, K_ = 0, N_ = 1, rank_ = 0, Bg_ = 0, SL_ = 1, off_r_ = 0, off_d_ = 0, off_s2_ = 0;
   ParamGroup feat_g_, crit_g_;
   LinearSlot p1_, p2_, p3_, m1_, m2_, m3_, th_, c14_, c2_, c5_;
   float *h1_ = nullptr, *h2_ = nullptr, *g1_ = nullptr, *g2_ = nullptr, *zphi_ = nullptr, *zmu_ = nullptr;

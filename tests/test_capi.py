@@ -25,7 +25,7 @@ def test_header_declares_the_expected_surface():
 def test_library_exports_every_declared_symbol(lib):
     missing = [n for n in declared_symbols() if not hasattr(lib, n)]
     assert not missing, missing
-    assert lib.rlrep_abi_version() == 2
+    assert lib.rlrep_abi_version() == 3
 
 
 def test_python_binding_declares_every_symbol_it_uses(lib):

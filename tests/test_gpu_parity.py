@@ -316,6 +316,10 @@ def test_loss_curves_track_the_oracle(case, keys):
 
 
 ODD = {
+    # widths that are not multiples of 32: the shim zero-pads hidden (and CTRL / SPEDER feature) widths, which is exact
+    "sac_unaligned": ("sac", dict(S=11, A=3), dict(hidden_dim=100), 64),
+    "ctrlsac_unaligned": ("ctrlsac", dict(S=11, A=3), dict(hidden_dim=72, feature_dim=100, extra_feature_steps=1), 64),
+    "vlsac_unaligned": ("vlsac", dict(S=11, A=3), dict(hidden_dim=50, feature_dim=64, extra_feature_steps=1), 40),
     # batch not a multiple of 32 / 128, odd state and action widths, tiny hidden sizes: exercises ragged tiles, TMA
     # zero-fill of short K, the CUDA-core fallbacks for M < 32 and the padded weight layouts
     "sac_odd": ("sac", dict(S=11, A=3), dict(hidden_dim=96), 100),
