@@ -45,7 +45,10 @@ class CtrlSacShardedAgent final : public SacBase {
     rank_ = comm_->rank;
     Bg_ = B_ * N_;
     // row slices of the collectives' pipeline: slice rows must stay a multiple of 32 (MN-major GEMM operands)
-    int want_slices = 4;
+    // measured on 8 x B200: 1 slice 7.45 ms / update, 2 slices 7.61, 4 slices 7.94 -- the smaller
+    // collectives lose more bandwidth, and take more SMs from the concurrent GEMMs, than the overlap wins; the pipeline
+    // stays available (RLREP_DP_SLICES) but is off by default
+    int want_slices = 1;
     if (const char* e = std::getenv("RLREP_DP_SLICES")) want_slices = std::max(1, std::atoi(e));
     SL_ = 1;
     for (int cand : {8, 4, 2})
