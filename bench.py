@@ -755,8 +755,24 @@ def time_state_agent(args, w, rank, world, local_rank, precision, barrier, repea
             info = agent.train(buf, B)
         barrier()
         e2e.append((time.perf_counter() - t0) * 1e3)
+    # (3) the same end-to-end loop with the noise drawn by torch's CUDA generator (noise_device="cuda", the stream a
+    # reference run on CUDA consumes): no host RNG, only the replay indices cross PCIe
+    e2e_dn = []
+    if not sharded:
+        agent.noise_device = "cuda"
+        for _ in range(3):
+            agent.train(buf, B)
+        for r in range(min(repeats, 3)):
+            barrier()
+            t0 = time.perf_counter()
+            for _ in range(args.steps):
+                agent.train(buf, B)
+            barrier()
+            e2e_dn.append((time.perf_counter() - t0) * 1e3)
+        agent.noise_device = "cpu"
     return dict(agent=agent, buf=buf, dev_ms=median_of(dev), e2e_ms=median_of(e2e), dev_all=dev, e2e_all=e2e, clocks=clocks,
-                info=info, launches=agent.gpu_launches_last_train, sharded=sharded)
+                info=info, launches=agent.gpu_launches_last_train, sharded=sharded,
+                e2e_device_noise_ms=median_of(e2e_dn) if e2e_dn else None)
 
 
 def state_roofline(args, w, res, dev_ms):
@@ -964,6 +980,11 @@ def run_ours(args, w, rank, world, local_rank):
     if rank == 0:
         roofline, top = state_roofline(args, w, res, dev_ms)
     launches, info, clocks = res["launches"], res["info"], res["clocks"]
+    e2e_dn_ms = res.get("e2e_device_noise_ms")
+    if world > 1 and e2e_dn_ms is not None:
+        t = torch.tensor([e2e_dn_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_dn_ms = t.item()
     if sharded:
         res["agent"].close()
     del res
@@ -1004,6 +1025,11 @@ def run_ours(args, w, rank, world, local_rank):
             "config": config_of(args.workload, w, world),
             "e2e": {"value": n_agents * args.steps / (e2e_ms * 1e-3), "unit": "updates/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": ni * 8 + ne * 4, "d2h_bytes_per_step": 32 * 4},
+            "e2e_device_noise": None if e2e_dn_ms is None else {
+                "value": n_agents * args.steps / (e2e_dn_ms * 1e-3), "unit": "updates/s",
+                "ms_per_step": e2e_dn_ms / args.steps, "h2d_bytes_per_step": ni * 8, "d2h_bytes_per_step": 32 * 4,
+                "what": 'agent.train() with noise_device="cuda": the Gaussian noise is drawn by torch\'s CUDA generator '
+                        "(what the reference does when run on CUDA) instead of the CPU generator + upload"},
             "repeats": {"n": args.repeats, "statistic": "median",
                         "what": f"the {args.steps}-step timed loop is run {args.repeats} times; value / e2e are the median repeat"},
             "gpu_launches": launches * args.steps,

@@ -224,7 +224,9 @@ RLREP_EXPORT int rlrep_agent_get_steps(rlrep_agent* agent, int* steps);
 /* One `agent.train(buffer, batch_size)`.  The caller draws the randomness exactly like the reference does
  * (np.random.randint for replay indices, torch.randn on the CPU generator for every epsilon) and
  * passes it in; rlrep_agent_train_counts tells how many of each one call consumes.  metrics_host receives the
- * entries named by rlrep_agent_metric_name. */
+ * entries named by rlrep_agent_metric_name.  `eps_host` may also be a DEVICE pointer on the agent's GPU (noise drawn
+ * there by the caller, e.g. torch.randn(device="cuda") like the reference run with device = cuda; the producing stream
+ * must be complete): it is then copied device to device and never crosses PCIe. */
 RLREP_EXPORT int rlrep_agent_train_counts(rlrep_agent* agent, int* n_idx, int* n_eps, int* n_metrics);
 RLREP_EXPORT const char* rlrep_agent_metric_name(rlrep_agent* agent, int i);
 RLREP_EXPORT int rlrep_agent_train(rlrep_agent* agent, rlrep_ring* ring, const int64_t* idx_host, int n_idx,

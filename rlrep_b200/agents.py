@@ -40,6 +40,7 @@ class _Handle:
             raise _lib.RlrepError("rlrep_b200 agents need a CUDA device (there is no CPU fallback)")
         self.lib = _lib.load()
         self.stream = torch.cuda.current_stream().cuda_stream
+        self.device = torch.cuda.current_device()  # the handle lives on the device current at creation
         h = C.c_void_p()
         if comm is None:
             _lib.check(self.lib.rlrep_agent_create(C.byref(cfg), self.stream, C.byref(h)))
@@ -101,8 +102,15 @@ class _Handle:
         arr = np.ascontiguousarray(arr.numpy())
         _lib.check(self.lib.rlrep_agent_tensor_write(self.h, i, arr.ctypes.data))
 
-    def train(self, ring_handle, idx: np.ndarray, eps: np.ndarray) -> np.ndarray:
-        _lib.check(self.lib.rlrep_agent_train(self.h, ring_handle, idx.ctypes.data, idx.size, eps.ctypes.data, eps.size,
+    def train(self, ring_handle, idx: np.ndarray, eps) -> np.ndarray:
+        """`eps`: float32 numpy array, or a contiguous float32 CUDA tensor (noise drawn on the device: the library copies it
+        device to device, rlrep_agent_train accepts either kind of pointer)."""
+        if isinstance(eps, torch.Tensor):
+            torch.cuda.current_stream(eps.device).synchronize()  # the library works on its own stream
+            eps_ptr, n_eps = eps.data_ptr(), eps.numel()
+        else:
+            eps_ptr, n_eps = eps.ctypes.data, eps.size
+        _lib.check(self.lib.rlrep_agent_train(self.h, ring_handle, idx.ctypes.data, idx.size, eps_ptr, n_eps,
                                               self._metrics.ctypes.data, self._metrics.size))
         return self._metrics
 
@@ -145,7 +153,15 @@ class SACAgent:
 
     def __init__(self, state_dim, action_dim, action_space, lr=3e-4, discount=0.99, target_update_period=2, tau=0.005,
                  alpha=0.1, auto_entropy_tuning=True, hidden_dim=1024, *, precision="tf32", use_cuda_graph=True,
-                 **extra):
+                 noise_device="cpu", **extra):
+        """`noise_device`: where train() draws its Gaussian noise.  "cpu" (default) uses torch's global CPU generator -- the
+        stream the reference consumes when it runs on the CPU, and the one the oracle / golden fixtures are pinned to.
+        "cuda" draws the same tensors, in the same order and shapes, with torch's CUDA generator -- the stream the
+        reference consumes when it runs with device = cuda (torch.randn_like on CUDA tensors) -- so the noise never exists
+        on the host: no host RNG time and no PCIe transfer (4 MB per update for LV-Rep at B = 1024)."""
+        if noise_device not in ("cpu", "cuda"):
+            raise ValueError("noise_device must be 'cpu' or 'cuda'")
+        self.noise_device = noise_device
         self.steps = 0
         self.state_dim, self.action_dim = int(state_dim), int(action_dim)
         self.action_range = [float(action_space.low.min()), float(action_space.high.max())]  # sac_agent.py:36-39
@@ -341,11 +357,28 @@ class SACAgent:
                                                s.shape[0], out.ctypes.data))
         return np.clip(out, self.action_range[0], self.action_range[1])
 
+    def _randn(self, rows, cols, std=None):
+        """One [rows, cols] standard-normal draw on `noise_device` (scaled by `std` the way torch.normal(0, std) does)."""
+        if self.noise_device == "cpu":
+            if std is None:
+                return torch.randn(rows, cols)
+            return torch.normal(mean=torch.zeros(rows, cols), std=torch.ones(rows, cols) * std)
+        dev = torch.device("cuda", self._ensure().device)
+        if std is None:
+            return torch.randn(rows, cols, device=dev)
+        return torch.normal(mean=torch.zeros(rows, cols, device=dev), std=torch.ones(rows, cols, device=dev) * std)
+
+    @staticmethod
+    def _pack(parts):
+        """The draws of one train() as one flat float32 buffer: numpy on the host, a CUDA tensor on the device."""
+        flat = torch.cat([p.reshape(-1) for p in parts])
+        return flat if flat.is_cuda else flat.numpy()
+
     def _draw(self, buffer, batch_size):
         """Indices and noise for one train(), in the reference's RNG order (sac)."""
         idx = np.random.randint(0, buffer.size, size=batch_size)
-        eps = [torch.randn(batch_size, self.action_dim) for _ in range(2)]  # critic step a', then actor step a
-        return idx, torch.stack(eps).numpy().reshape(-1)
+        eps = [self._randn(batch_size, self.action_dim) for _ in range(2)]  # critic step a', then actor step a
+        return idx, self._pack(eps)
 
     def _info(self, m):
         d = dict(zip(self._h.metric_names, (float(x) for x in m)))
@@ -360,7 +393,7 @@ class SACAgent:
         self.steps += 1
         idx, eps = self._draw(buffer, batch_size)
         idx = np.ascontiguousarray(idx, dtype=np.int64)
-        eps = np.ascontiguousarray(eps, dtype=np.float32)
+        eps = eps.contiguous() if isinstance(eps, torch.Tensor) else np.ascontiguousarray(eps, dtype=np.float32)
         m = h.train(buffer._h, idx, eps)
         info = self._info(m)
         if not self.learnable_temperature:
@@ -418,8 +451,8 @@ class CTRLSACAgent(SACAgent):
     def _draw(self, buffer, batch_size):  # K x randint[B] -> randn[B,A] -> randn[B,A]
         K = self.extra_feature_steps + 1
         idx = np.concatenate([np.random.randint(0, buffer.size, size=batch_size) for _ in range(K)])
-        eps = [torch.randn(batch_size, self.action_dim) for _ in range(2)]
-        return idx, torch.stack(eps).numpy().reshape(-1)
+        eps = [self._randn(batch_size, self.action_dim) for _ in range(2)]
+        return idx, self._pack(eps)
 
     def _info(self, m):
         return dict(zip(self._h.metric_names, (float(x) for x in m)))
@@ -538,9 +571,9 @@ class VLSACAgent(SACAgent):
         idx, eps = [], []
         for _ in range(K):
             idx.append(np.random.randint(0, buffer.size, size=batch_size))
-            eps.append(torch.randn(batch_size, self.feature_dim).reshape(-1))
-        eps += [torch.randn(batch_size, self.action_dim).reshape(-1) for _ in range(2)]
-        return np.concatenate(idx), torch.cat(eps).numpy()
+            eps.append(self._randn(batch_size, self.feature_dim))
+        eps += [self._randn(batch_size, self.action_dim) for _ in range(2)]
+        return np.concatenate(idx), self._pack(eps)
 
     def _info(self, m):
         return dict(zip(self._h.metric_names, (float(x) for x in m)))
@@ -600,8 +633,8 @@ class SPEDERSACAgent(SACAgent):
     def _draw(self, buffer, batch_size):  # K x (randint[B], randint[B]) -> randn[B,A] -> randn[B,A]
         K = self.extra_feature_steps + 1
         idx = np.concatenate([np.random.randint(0, buffer.size, size=batch_size) for _ in range(2 * K)])
-        eps = [torch.randn(batch_size, self.action_dim) for _ in range(2)]
-        return idx, torch.stack(eps).numpy().reshape(-1)
+        eps = [self._randn(batch_size, self.action_dim) for _ in range(2)]
+        return idx, self._pack(eps)
 
     def _info(self, m):
         return dict(zip(self._h.metric_names, (float(x) for x in m)))
@@ -669,9 +702,9 @@ class DIFFSRSACAgent(SACAgent):
         for _ in range(K):
             idx.append(np.random.randint(0, buffer.size, size=B))
             idx.append(torch.randint(0, self.num_noises, (B,)).numpy())  # diffsrsac_agent.py:276
-            eps.append(torch.normal(mean=torch.zeros(B, S), std=torch.ones(B, S) * self.sigma_scale_factor).reshape(-1))
-        eps += [torch.randn(B, self.action_dim).reshape(-1) for _ in range(2)]
-        return np.concatenate(idx), torch.cat(eps).numpy()
+            eps.append(self._randn(B, S, std=self.sigma_scale_factor))
+        eps += [self._randn(B, self.action_dim) for _ in range(2)]
+        return np.concatenate(idx), self._pack(eps)
 
     def _info(self, m):
         d = dict(zip(self._h.metric_names, (float(x) for x in m)))

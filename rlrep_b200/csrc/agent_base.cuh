@@ -2,6 +2,7 @@
 // its forward/backward, the control block with the float64 temperature, staging of the host-drawn indices and
 // noise, metrics read-back, and the eager -> capture -> replay protocol of train().
 #pragma once
+#include "staging.cuh"
 #include <cstdlib>
 
 #include "agent.cuh"
@@ -41,9 +42,14 @@ class SacBase : public Agent {
     bind_ring(ring);
     RLREP_CUDA(cudaStreamSynchronize(stream));  // pinned staging is reused across calls
     std::memcpy(idx_host_, idx_host, (size_t)n_idx * sizeof(long long));
-    std::memcpy(eps_host_, eps_host, (size_t)n_eps * sizeof(float));
     RLREP_CUDA(cudaMemcpyAsync(idx_dev_, idx_host_, (size_t)n_idx * sizeof(long long), cudaMemcpyHostToDevice, stream));
-    RLREP_CUDA(cudaMemcpyAsync(eps_dev_, eps_host_, (size_t)n_eps * sizeof(float), cudaMemcpyHostToDevice, stream));
+    if (is_device_pointer(eps_host)) {
+      // noise drawn on the device by the caller (agents.py noise_device = "cuda"): it never touches the host
+      RLREP_CUDA(cudaMemcpyAsync(eps_dev_, eps_host, (size_t)n_eps * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    } else {
+      std::memcpy(eps_host_, eps_host, (size_t)n_eps * sizeof(float));
+      RLREP_CUDA(cudaMemcpyAsync(eps_dev_, eps_host_, (size_t)n_eps * sizeof(float), cudaMemcpyHostToDevice, stream));
+    }
     const long long before = launch_count();
     const bool was_captured = graph_.captured();
     graph_.run(stream, cfg.use_graph != 0, [&] { update(ring); });

@@ -112,9 +112,12 @@ class CtrlSacAgent final : public SacBase {
     launch_tick(ctl, base_tick(), stream);
     const bool chain = chained();
     for (int k = 0; k < K_; ++k) {
-      launch_gather(ring.data, R_ / 4, idx_dev_ + (size_t)k * B_, B_, batch_, stream);
-      if (chain) feature_step_chained(k);
-      else feature_step(k);
+      if (chain) {
+        feature_step_chained(k, ring);
+      } else {
+        launch_gather(ring.data, R_ / 4, idx_dev_ + (size_t)k * B_, B_, batch_, stream);
+        feature_step(k);
+      }
     }
     if (chain) {
       critic_step_chained();
@@ -237,13 +240,25 @@ class CtrlSacAgent final : public SacBase {
   // Same arithmetic, same kernels for everything that is not a GEMM; every group of GEMMs between two elementwise kernels
   // runs as ONE persistent chain kernel (gemm_chain.cuh) on the main stream instead of one launch per GEMM on up to four
   // streams: 57 launches per update instead of 149, and a dependent GEMM starts when its input tiles are complete.
-  void feature_step_chained(int k) {  // ctrlsac_agent.py:213-251
+  // The replay gather, both towers, the logits, the contrastive head and the whole backward pass are ONE chain launch: the
+  // gather and the head ride in the chain as row operations (gemm.cuh RowOp) between the GEMMs they feed.
+  void feature_step_chained(int k, Ring& ring) {  // ctrlsac_agent.py:213-251
     const Linear l1 = p1_.view(feat_g_), l2 = p2_.view(feat_g_), l3 = p3_.view(feat_g_);
     const Linear n1 = m1_.view(feat_g_), n2 = m2_.view(feat_g_), n3 = m3_.view(feat_g_);
     const Linear th = th_.view(feat_g_);
     const float inv_b = 1.f / (float)B_;
     cudaStream_t s0 = stream;
     gemm_.begin_chain(s0);
+    {
+      RowOp op;
+      op.kind = ROWOP_GATHER;
+      op.rows = B_;
+      op.ring = ring.data;
+      op.idx = idx_dev_ + (size_t)k * B_;
+      op.out = batch_;
+      op.rec4 = R_ / 4;
+      if (!gemm_.row_op(op)) launch_gather(ring.data, R_ / 4, idx_dev_ + (size_t)k * B_, B_, batch_, s0);
+    }
     phi_forward(s0, sa(), Mat(), 0, zphi_, h1_, h2_);
     linear_fwd(gemm_, s0, B_, s2(), n1, ACT_ELU, g1_, H_);
     linear_fwd(gemm_, s0, B_, Mat{g1_, H_}, n2, ACT_ELU, g2_, H_);
@@ -256,11 +271,25 @@ class CtrlSacAgent final : public SacBase {
       a.C = logits_; a.ldc = B_;
       gemm_.run(a, s0);
     }
-    gemm_.end_chain();
-    // row log-sum-exp / CE gradient (logits_ now holds dL/dlogits), reward head and the loss metrics in one launch
-    launch_contrastive_head(logits_, B_, B_, B_, 0, inv_b, zphi_, D_, D_, th.W, th.b, reward(), R_, loss_rows_, rpred_, drp_,
-                            metrics_dev_ + 0, head_ctr_, s0);
-    gemm_.begin_chain(s0);
+    {  // row log-sum-exp / CE gradient (logits_ then holds dL/dlogits), reward head and the loss metrics
+      RowOp op;
+      op.kind = ROWOP_CTRL_HEAD;
+      op.rows = B_;
+      op.logits = logits_; op.ld = B_; op.cols = B_; op.diag_off = 0;
+      op.inv_batch = inv_b;
+      op.z = zphi_; op.ldz = D_; op.D = D_;
+      op.theta_w = th.W; op.theta_b = th.b;
+      op.reward = reward(); op.ld_r = R_;
+      op.loss_rows = loss_rows_; op.pred = rpred_; op.dpred = drp_;
+      op.metrics = metrics_dev_ + 0;
+      op.counter = head_ctr_;
+      if (!gemm_.row_op(op)) {
+        gemm_.end_chain();
+        launch_contrastive_head(logits_, B_, B_, B_, 0, inv_b, zphi_, D_, D_, th.W, th.b, reward(), R_, loss_rows_, rpred_,
+                                drp_, metrics_dev_ + 0, head_ctr_, s0);
+        gemm_.begin_chain(s0);
+      }
+    }
     {  // d z_phi = G mu + drp (x) theta.w
       GemmArgs a;
       a.M = B_; a.N = D_; a.K = B_;

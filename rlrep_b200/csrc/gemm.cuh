@@ -17,6 +17,47 @@
 
 namespace rlrep {
 
+// Row operations that can ride in a GEMM chain (gemm_chain.cuh) between its GEMMs, executed by the chain kernel's
+// epilogue warps on (rows_per_item)-row items with the same dependency / publish protocol as a GEMM tile.  A GemmArgs
+// whose row.kind != ROWOP_NONE is such an operation, not a GEMM.
+enum RowOpKind : int { ROWOP_NONE = 0, ROWOP_CTRL_HEAD = 1, ROWOP_GATHER = 2, ROWOP_ADAM = 3 };
+struct AdamHyper;
+struct RowOp {
+  int kind = ROWOP_NONE;
+  int rows = 0;
+  // ROWOP_CTRL_HEAD: contrastive_head_kernel (kernels.cuh) -- row log-sum-exp / CE gradient rewrite of `logits`, reward head
+  // pred = <z_row, theta_w> + theta_b, dpred = (pred - reward) * inv_batch, loss metrics by the last row to finish
+  float* logits = nullptr;
+  int ld = 0, cols = 0, diag_off = 0;
+  float inv_batch = 0.f;
+  const float* z = nullptr;
+  int ldz = 0, D = 0;
+  const float* theta_w = nullptr;
+  const float* theta_b = nullptr;
+  const float* reward = nullptr;
+  int ld_r = 0;
+  float* loss_rows = nullptr;
+  float* pred = nullptr;
+  float* dpred = nullptr;
+  float* metrics = nullptr;
+  unsigned* counter = nullptr;
+  // ROWOP_GATHER: gather_kernel -- out[b, :] = ring[idx[b], :], rows are rec4 float4 wide
+  const float* ring = nullptr;
+  const long long* idx = nullptr;
+  float* out = nullptr;
+  int rec4 = 0;
+  // ROWOP_ADAM: adam_polyak_kernel (kernels.cu) over n floats (a multiple of 4) of one parameter group, as a BACKGROUND
+  // operation: it has no place in the CTAs' item lists -- the epilogue warps of every CTA work through their share of its
+  // 8 KB chunks whenever the accumulator they wait for is not ready yet -- and the GEMMs that read the parameters wait for
+  // it like for any other member.  It must not depend on a member of the same chain (its gradients come from earlier
+  // launches).
+  float *adam_p = nullptr, *adam_m = nullptr, *adam_v = nullptr, *adam_target = nullptr;
+  const float* adam_g = nullptr;
+  const AdamHyper* adam_hyper = nullptr;
+  unsigned adam_n = 0, adam_n_polyak = 0;
+  float adam_tau = 0.f;
+};
+
 struct GemmArgs {
   int M = 0, N = 0, K = 0;
   const float* A = nullptr;
@@ -38,6 +79,7 @@ struct GemmArgs {
   float* C = nullptr;
   int ldc = 0;
   Epilogue epi;
+  RowOp row;  // row.kind != ROWOP_NONE: a row operation riding in a GEMM chain, the GEMM fields above are unused
 };
 
 // ---- tcgen05 path (TF32 inputs, FP32 accumulate in TMEM, TMA-fed) ----

@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "gemm_chain.cuh"
 #include "ptx.cuh"
+#include "reduce.cuh"
 
 namespace rlrep {
 
@@ -185,6 +186,138 @@ __device__ __forceinline__ void chain_store_rows(const Epilogue& epi, const Chun
   }
 }
 
+// ------------------------------------------------------------------------------------------------ row operations
+// Executed by the 256 epilogue threads (et = 0..255) of a CTA.  Operands produced by other SMs of this launch are read with
+// ld.cg (never from this SM's L1).
+// One row of the CTRL contrastive head (contrastive_head_kernel in kernels.cu, same arithmetic up to summation order) by ONE
+// WARP: log-sum-exp of the logits row, in-place rewrite to (softmax - I) * inv_batch, reward-head prediction and its
+// gradient; the row that finishes last adds up the per-row terms in fixed order and writes the three loss metrics.  Rows of
+// up to 512 logits stay in registers between the three passes (one trip to L2 instead of three), and nothing synchronises
+// beyond the warp: an item's rows run on as many warps at once.
+__device__ __forceinline__ void row_op_ctrl_head(const RowOp& op, int row, int lane) {
+  float* l = op.logits + (size_t)row * op.ld;
+  const int cols = op.cols;
+  const int dj = op.diag_off + row;
+  float lse, diag;
+  const bool in_regs = cols <= 512 && (cols & 3) == 0 && (op.ld & 3) == 0 && (reinterpret_cast<uintptr_t>(op.logits) & 15) == 0;
+  if (in_regs) {
+    float4 v[4];
+    const float4* l4 = reinterpret_cast<const float4*>(l);
+    const int n4 = cols >> 2;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = lane + 32 * i;
+      v[i] = j < n4 ? __ldcg(l4 + j) : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    }
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) mx = fmaxf(mx, fmaxf(fmaxf(v[i].x, v[i].y), fmaxf(v[i].z, v[i].w)));
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) sum += (expf(v[i].x - mx) + expf(v[i].y - mx)) + (expf(v[i].z - mx) + expf(v[i].w - mx));
+    sum = warp_sum(sum);
+    lse = mx + logf(sum);
+    // the diagonal logit: lane (dj / 4) % 32, register dj / 128, component dj % 4
+    float mine = 0.f;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      if (i == (dj >> 7)) mine = (dj & 3) == 0 ? v[i].x : (dj & 3) == 1 ? v[i].y : (dj & 3) == 2 ? v[i].z : v[i].w;
+    diag = __shfl_sync(0xffffffffu, mine, (dj >> 2) & 31);
+    float4* o4 = reinterpret_cast<float4*>(l);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int j = lane + 32 * i;
+      if (j < n4) {
+        const int c = 4 * j;
+        float4 g;
+        g.x = (expf(v[i].x - lse) - (c == dj ? 1.f : 0.f)) * op.inv_batch;
+        g.y = (expf(v[i].y - lse) - (c + 1 == dj ? 1.f : 0.f)) * op.inv_batch;
+        g.z = (expf(v[i].z - lse) - (c + 2 == dj ? 1.f : 0.f)) * op.inv_batch;
+        g.w = (expf(v[i].w - lse) - (c + 3 == dj ? 1.f : 0.f)) * op.inv_batch;
+        o4[j] = g;
+      }
+    }
+  } else {
+    float mx = -INFINITY;
+    for (int j = lane; j < cols; j += 32) mx = fmaxf(mx, __ldcg(l + j));
+    mx = warp_max(mx);
+    float sum = 0.f;
+    for (int j = lane; j < cols; j += 32) sum += expf(__ldcg(l + j) - mx);
+    sum = warp_sum(sum);
+    lse = mx + logf(sum);
+    diag = __ldcg(l + dj);
+    __syncwarp();  // every lane has read l[dj] before it is rewritten
+    for (int j = lane; j < cols; j += 32) l[j] = (expf(__ldcg(l + j) - lse) - (j == dj ? 1.f : 0.f)) * op.inv_batch;
+  }
+  const float loss = lse - diag;
+  const float* x = op.z + (size_t)row * op.ldz;
+  float acc = 0.f;
+  if (((op.ldz | op.D) & 3) == 0 && ((reinterpret_cast<uintptr_t>(op.z) | reinterpret_cast<uintptr_t>(op.theta_w)) & 15) == 0) {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* w4 = reinterpret_cast<const float4*>(op.theta_w);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (int j = lane; j < op.D / 4; j += 32) {
+      const float4 xv = __ldcg(x4 + j);
+      const float4 wv = __ldg(w4 + j);
+      a0 = fmaf(xv.x, wv.x, a0); a1 = fmaf(xv.y, wv.y, a1); a2 = fmaf(xv.z, wv.z, a2); a3 = fmaf(xv.w, wv.w, a3);
+    }
+    acc = (a0 + a1) + (a2 + a3);
+  } else {
+    for (int j = lane; j < op.D; j += 32) acc = fmaf(__ldcg(x + j), __ldg(op.theta_w + j), acc);
+  }
+  acc = warp_sum(acc);
+  unsigned last = 0;
+  if (lane == 0) {
+    const float p = acc + __ldg(op.theta_b);
+    op.loss_rows[row] = loss;
+    op.pred[row] = p;
+    op.dpred[row] = (p - __ldcg(op.reward + (size_t)row * op.ld_r)) * op.inv_batch;
+    last = atom_add_acq_rel(op.counter, 1u) == (unsigned)(op.rows - 1) ? 1u : 0u;
+  }
+  last = __shfl_sync(0xffffffffu, last, 0);
+  if (!last) return;
+  float ce = 0.f, se = 0.f;
+  for (int i = lane; i < op.rows; i += 32) {
+    ce += __ldcg(op.loss_rows + i);
+    const float d = __ldcg(op.pred + i) - __ldcg(op.reward + (size_t)i * op.ld_r);
+    se = fmaf(d, d, se);
+  }
+  ce = warp_sum(ce);
+  se = warp_sum(se);
+  if (lane == 0) {
+    const float model = ce * op.inv_batch;
+    const float r = 0.5f * (se * op.inv_batch);
+    op.metrics[0] = model + r;
+    op.metrics[1] = model;
+    op.metrics[2] = r;
+    *op.counter = 0;  // re-armed for the next launch
+  }
+}
+
+// Rows [row0, row0 + n) of the replay gather: out[b, :] = ring[idx[b], :] (gather_kernel in kernels.cu).
+__device__ __forceinline__ void row_op_gather(const RowOp& op, int row0, int n, int et) {
+  const float4* ring = reinterpret_cast<const float4*>(op.ring);
+  float4* out = reinterpret_cast<float4*>(op.out);
+  const int rec4 = op.rec4;
+  for (int i = et; i < n * rec4; i += 256) {
+    const int r = row0 + i / rec4, c = i % rec4;
+    out[(size_t)r * rec4 + c] = __ldg(ring + (size_t)__ldg(op.idx + r) * rec4 + c);
+  }
+}
+
+// Out of line: the row operations' registers must not weigh on the GEMM epilogue, which sits at the 168-register cap.
+__device__ __noinline__ void run_row_op(const ChainGemmDesc* g, int item, float* scratch, int et) {
+  const RowOp op = g->row;
+  const int rpi = g->rows_per_item, row0 = item * rpi, n = min(rpi, op.rows - row0);
+  if (op.kind == ROWOP_CTRL_HEAD) {
+    for (int r = et >> 5; r < n; r += kEpiWarps) row_op_ctrl_head(op, row0 + r, et & 31);
+  } else {
+    row_op_gather(op, row0, n, et);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ kernel
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __restrict__ tasks,
@@ -198,6 +331,8 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
       dbg[((size_t)blockIdx.x * kDbgItems + item) * kDbgEvents + ev] = t;
     }
   };
+  // debug: kernel entry / exit of every CTA in the last item row (a CTA with kDbgItems items overwrites nothing: events 2, 3)
+  if (threadIdx.x == 0) stamp(kDbgItems - 1, 2);
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * kStageBytes);
@@ -238,6 +373,7 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
       for (int t = t_begin; t < t_end; ++t) {
         const ChainTask tk = tasks[t];
         const ChainGemmDesc* g = gemms + tk.gemm;
+        const int kind = g->row.kind;
         // Everything that does not depend on the dependencies' DATA happens before the wait: the item's descriptor fields
         // go to registers and the tensor maps are made visible to the TMA unit, so that once the counters are reached only
         // the fences stand between this thread and the first operand load.
@@ -251,7 +387,7 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
           dep_id[d] = d < n_deps ? g->dep[d] : 0;
           dep_tiles[d] = d < n_deps ? (int)g->dep_target[d] : 0;
         }
-        if (tk.gemm != last_gemm) {
+        if (tk.gemm != last_gemm && kind == ROWOP_NONE) {
           if (!(flags & kFlagNoTensormapFence)) {
             fence_tensormap_acquire(&g->tmA);
             fence_tensormap_acquire(&g->tmB);
@@ -271,6 +407,15 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
           if (!(flags & kFlagNoProxyFence)) fence_proxy_async_global();
         }
         stamp(t - t_begin, 1);
+        if (kind != ROWOP_NONE) {
+          // a row operation has no operands to stream: "dependencies met" travels to the MMA issuer through one (empty)
+          // pipeline stage, so that every barrier still sees each of its phases waited on in order
+          const int s = it % kStages;
+          ptx::mbar_wait(&empty_bar[s], ((it / kStages) & 1) ^ 1);
+          ptx::mbar_arrive(&full_bar[s]);
+          ++it;
+          continue;
+        }
         const uint32_t tx = kABytes + bn * kBK * 4;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % kStages;
@@ -294,6 +439,17 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
       for (int t = t_begin; t < t_end; ++t, ++tc) {
         const ChainTask tk = tasks[t];
         const ChainGemmDesc* g = gemms + tk.gemm;
+        if (g->row.kind != ROWOP_NONE) {
+          // row operation: nothing to multiply; hand the producer's "dependencies met" on to the epilogue warps through the
+          // accumulator slot this item stands in for
+          const int s = it % kStages, acc = tc & 1;
+          ptx::mbar_wait(&full_bar[s], (it / kStages) & 1);
+          ptx::mbar_arrive(&empty_bar[s]);
+          ++it;
+          ptx::mbar_wait(&acc_empty[acc], ((tc >> 1) & 1) ^ 1);
+          ptx::mbar_arrive(&acc_full[acc]);
+          continue;
+        }
         const int bn = g->bn, a_mn = g->a_mn, b_mn = g->b_mn;
         const int kb0 = tk.split * g->kb_per_split, kb1 = min(g->nkb, kb0 + g->kb_per_split);
         const uint32_t idesc = ptx::make_idesc_tf32(kBM, bn, a_mn != 0, b_mn != 0);
@@ -333,6 +489,22 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
     for (int t = t_begin; t < t_end; ++t, ++tc) {
       const ChainTask tk = tasks[t];
       const ChainGemmDesc* g = gemms + tk.gemm;
+      if (g->row.kind != ROWOP_NONE) {
+        const int acc = tc & 1, et = threadIdx.x - 64;
+        ptx::mbar_wait(&acc_full[acc], (tc >> 1) & 1);
+        if (threadIdx.x == 64) stamp(t - t_begin, 5);
+        run_row_op(g, tk.tile, tbuf, et);
+        if (threadIdx.x == 64) stamp(t - t_begin, 9);
+        epilogue_bar();
+        if (threadIdx.x == 64) {
+          if (!(flags & kFlagNoProxyFence)) fence_proxy_async_global();
+          red_release_add(done + ((size_t)tk.gemm * kSub + (tk.tile % kSub)) * kCtrStride, 1u);
+          stamp(t - t_begin, 7);
+        }
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);
+        continue;
+      }
       // everything this item needs from its descriptor, read ONCE into registers: a reference into global memory would be
       // re-read behind every store (the compiler must assume the stores alias it)
       const Epilogue epi = g->epi;
@@ -352,12 +524,18 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
       bool final = true;
       const size_t part_floats = (size_t)kBM * bn;
       float* ws_tile = split_k > 1 ? ws + (size_t)tk.tile * split_k * part_floats : nullptr;
+      // Distributed reduction: the split_k CTAs of a tile each finalise the chunks c with c % split_k == their split index,
+      // so the reduction reads and the epilogue run split_k-wide instead of on the last arriver alone.  Each CTA writes the
+      // chunks the OTHERS own, arrives, waits until all have arrived, then reduces its own chunks in the fixed order.
+      const bool dist = split_k > 1 && g->dist != 0;
+      int c_first = half, c_step = 2;
       if (split_k > 1) {
         // pass 1: this CTA's partial tile goes to the workspace, element (row, c*16 + 4*j + e) at
         // ((c*4 + j) * 128 + row) * 4 + e -- 512 contiguous bytes per store instruction
         float* part = ws_tile + (size_t)tk.split * part_floats;
 #pragma unroll 1
         for (int c = half; c < chunks; c += 2) {
+          if (dist && c % split_k == tk.split) continue;  // nobody else reads the chunks this CTA finalises itself
           uint32_t v[kCW];
           ptx::tmem_ld_32x32b_x16(t_acc + c * kCW, v);
           ptx::tmem_ld_wait();
@@ -372,12 +550,35 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
         if (threadIdx.x == 64) {
           unsigned* ctr = tile_ctr + tk.tile;
           const unsigned old = atom_add_acq_rel(ctr, 1u);
-          if (old == (unsigned)(split_k - 1)) *ctr = 0;  // every split has arrived: re-armed for the next launch
+          if (dist) {
+            // wait for the other splits' partials (they run concurrently: same dependencies, same position in their CTAs'
+            // lists); the counter goes on to count departures, so it never drops while someone is still waiting here
+            if (old + 1 < (unsigned)split_k) {
+              unsigned long long t0 = 0;
+              unsigned spins = 0;
+              while (ld_relaxed(ctr) < (unsigned)split_k) {
+                __nanosleep(20);
+                if ((++spins & 0xfff) == 0) {
+                  unsigned long long now;
+                  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                  if (t0 == 0) t0 = now;
+                  else if (now - t0 > 2000000000ull) __trap();  // a planning bug must not hang the GPU
+                }
+              }
+              fence_acquire_gpu();
+            }
+          } else if (old == (unsigned)(split_k - 1)) {
+            *ctr = 0;  // every split has arrived: re-armed for the next launch
+          }
           *arrival = old;
           stamp(t - t_begin, 6);
         }
         epilogue_bar();
-        final = *arrival == (unsigned)(split_k - 1);
+        final = dist || *arrival == (unsigned)(split_k - 1);
+        if (dist) {
+          c_first = tk.split + split_k * half;
+          c_step = 2 * split_k;
+        }
       }
       if (final) {
         const bool use_aux = epi.dact != DACT_NONE;
@@ -386,7 +587,7 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
                             (!epi.pre_out || ((epi.ld_pre & 3) == 0 && aligned16(epi.pre_out))) &&
                             (!epi.bias || aligned16(epi.bias)) && (!epi.r1_v || aligned16(epi.r1_v));
 #pragma unroll 1
-        for (int c = half; c < chunks; c += 2) {
+        for (int c = c_first; c < chunks; c += c_step) {
           const int gn0 = n0 + c * kCW;
           const bool fast = vec_ok && gn0 + kCW <= N;
           ChunkOperands ops;
@@ -475,8 +676,14 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
         epilogue_bar();
         if (threadIdx.x == 64) {
           if (!(flags & kFlagNoProxyFence)) fence_proxy_async_global();
-          red_release_add(done + ((size_t)tk.gemm * kSub + (tk.tile % kSub)) * kCtrStride, 1u);
+          // a distributed reduction publishes once per (tile, split): each CTA's columns are final on their own
+          const int pub = dist ? tk.tile * split_k + tk.split : tk.tile;
+          red_release_add(done + ((size_t)tk.gemm * kSub + (pub % kSub)) * kCtrStride, 1u);
           stamp(t - t_begin, 7);
+          if (dist) {  // departure: the last CTA to have read the others' partials re-arms the counter
+            unsigned* ctr = tile_ctr + tk.tile;
+            if (atomicAdd(ctr, 1u) == (unsigned)(2 * split_k - 1)) *ctr = 0;
+          }
         }
       }
       ptx::tc_fence_before_sync();
@@ -495,6 +702,7 @@ gemm_chain_kernel(const ChainGemmDesc* __restrict__ gemms, const ChainTask* __re
       *exit_ctr = 0;
       __threadfence();
     }
+    stamp(kDbgItems - 1, 3);
   }
 }
 
@@ -515,6 +723,26 @@ struct Footprint {
 };
 Footprint footprint(const GemmArgs& a) {
   Footprint f;
+  if (a.row.kind == ROWOP_CTRL_HEAD) {
+    const RowOp& o = a.row;
+    f.reads.push_back(range_of(o.logits, o.rows, o.ld, o.cols));
+    f.reads.push_back(range_of(o.z, o.rows, o.ldz, o.D));
+    f.reads.push_back(range_of(o.theta_w, 1, 0, o.D));
+    f.reads.push_back(range_of(o.theta_b, 1, 0, 1));
+    f.reads.push_back(range_of(o.reward, o.rows, o.ld_r, 1));
+    f.writes.push_back(range_of(o.logits, o.rows, o.ld, o.cols));
+    f.writes.push_back(range_of(o.loss_rows, 1, 0, o.rows));
+    f.writes.push_back(range_of(o.pred, 1, 0, o.rows));
+    f.writes.push_back(range_of(o.dpred, 1, 0, o.rows));
+    f.writes.push_back(range_of(o.metrics, 1, 0, 3));
+    return f;
+  }
+  if (a.row.kind == ROWOP_GATHER) {
+    const RowOp& o = a.row;
+    f.reads.push_back(range_of(reinterpret_cast<const float*>(o.idx), 1, 0, 2 * o.rows));
+    f.writes.push_back(range_of(o.out, o.rows, 4 * o.rec4, 4 * o.rec4));
+    return f;  // the ring itself is never written inside a chain
+  }
   f.reads.push_back(a.a_mn ? range_of(a.A, a.K, a.lda, a.M) : range_of(a.A, a.M, a.lda, a.K));
   f.reads.push_back(a.b_mn ? range_of(a.B, a.K, a.ldb, a.N) : range_of(a.B, a.N, a.ldb, a.K));
   f.reads.push_back(range_of(a.epi.bias, 1, 0, a.N));
@@ -551,12 +779,20 @@ int env_int(const char* name, int dflt) {
 // (~12 TB/s) binds; every item pays ~1.5 us of dependency propagation, TMA latency and publish; an epilogue chunk pair
 // (2 x 32 columns, one per epilogue warp group) ~1 us; split-K adds the partial's round trip through L2 and the last
 // arriver's reads.
-double plan_cost(int tiles, int nkb, int bn, int split, int share) {
+// A distributed reduction (dist) finalises bn / split columns per CTA after one wait for the other splits.
+bool dist_possible(int bn, int split) { return split > 1 && (bn / kCW) % split == 0; }
+double plan_cost(int tiles, int nkb, int bn, int split, int share, bool dist) {
   const int kb_per = ceil_div(nkb, split);
   const double kb_bytes = kABytes + bn * kBK * 4;
   const double waves = std::ceil((double)tiles * split / share);
   const double stream = waves * kb_per * kb_bytes / 150e3;
   const double chip = (double)tiles * split * kb_per * kb_bytes / 12e6;
+  if (dist) {
+    // partial tile out (bn / 64 * 0.25 us), one arrival + wait (~1 us when the splits run in the same wave), the other
+    // splits' slices back in and the epilogue on bn / split columns
+    return 1.5 + std::max(stream, chip) + waves * (0.25 * ceil_div(bn, 64) + 1.0 + 1.0 * ceil_div(bn / split, 64)) +
+           0.1 * (split - 1);
+  }
   double t = 1.5 + std::max(stream, chip) + waves * 1.0 * ceil_div(bn, 64);
   if (split > 1) t += 1.5 + 0.3 * (split - 1) * ceil_div(bn, 64);
   return t;
@@ -566,7 +802,10 @@ double plan_cost(int tiles, int nkb, int bn, int split, int share) {
 
 void set_chain_debug_buffer(unsigned long long* dev) { g_chain_dbg = dev; }
 
-bool chain_eligible(const GemmArgs& a) { return tc_eligible(a) && a.conv_w == 0 && a.M >= 32 && a.N >= 32 && a.K >= 8; }
+bool chain_eligible(const GemmArgs& a) {
+  if (a.row.kind != ROWOP_NONE) return a.row.rows > 0;
+  return tc_eligible(a) && a.conv_w == 0 && a.M >= 32 && a.N >= 32 && a.K >= 8;
+}
 
 GemmChain::~GemmChain() {
   if (dev_) cudaFree(dev_);
@@ -576,6 +815,17 @@ bool GemmChain::matches(const std::vector<GemmArgs>& seq) const {
   if (seq.size() != seq_.size()) return false;
   for (size_t i = 0; i < seq.size(); ++i) {
     const GemmArgs &x = seq[i], &y = seq_[i];
+    if (x.row.kind != y.row.kind) return false;
+    if (x.row.kind != ROWOP_NONE) {
+      const RowOp &p = x.row, &q = y.row;
+      if (p.rows != q.rows || p.logits != q.logits || p.ld != q.ld || p.cols != q.cols || p.diag_off != q.diag_off ||
+          p.inv_batch != q.inv_batch || p.z != q.z || p.ldz != q.ldz || p.D != q.D || p.theta_w != q.theta_w ||
+          p.theta_b != q.theta_b || p.reward != q.reward || p.ld_r != q.ld_r || p.loss_rows != q.loss_rows ||
+          p.pred != q.pred || p.dpred != q.dpred || p.metrics != q.metrics || p.counter != q.counter || p.ring != q.ring ||
+          p.idx != q.idx || p.out != q.out || p.rec4 != q.rec4)
+        return false;
+      continue;
+    }
     if (x.M != y.M || x.N != y.N || x.K != y.K || x.A != y.A || x.B != y.B || x.C != y.C || x.lda != y.lda ||
         x.ldb != y.ldb || x.ldc != y.ldc || x.a_mn != y.a_mn || x.b_mn != y.b_mn || x.epi.bias != y.epi.bias ||
         x.epi.r1_u != y.epi.r1_u || x.epi.r1_v != y.epi.r1_v || x.epi.aux != y.epi.aux || x.epi.pre_out != y.epi.pre_out ||
@@ -645,8 +895,19 @@ void GemmChain::build(const std::vector<GemmArgs>& seq, int force_bn, int force_
   std::vector<char> has_dependents(n, 0), filler(n, 0);
   for (int j = 0; j < n; ++j)
     for (int i : deps[j]) has_dependents[i] = 1;
-  std::vector<int> bn(n), split(n), share(n), first_cta(n);
-  auto work_of = [&](int i) { return (double)ceil_div(seq[i].M, kBM) * ceil_div(seq[i].N, kMaxBn) * ceil_div(seq[i].K, kBK); };
+  std::vector<int> bn(n), split(n), share(n), first_cta(n), rpi(n, 0), dist(n, 0);
+  const int dist_mode = env_int("RLREP_CHAIN_DIST", 1);  // 0: last-arriver reductions only, 1: cost model, 2: wherever possible
+  auto is_row = [&](int i) { return seq[i].row.kind != ROWOP_NONE; };
+  // a row operation counts as one k-block of work per 128 rows when it shares a level with GEMMs
+  auto work_of = [&](int i) {
+    if (is_row(i)) return (double)ceil_div(seq[i].row.rows, kBM);
+    return (double)ceil_div(seq[i].M, kBM) * ceil_div(seq[i].N, kMaxBn) * ceil_div(seq[i].K, kBK);
+  };
+  // items (= publishes on its completion counter) of chain member i
+  auto items_of = [&](int i) {
+    if (is_row(i)) return ceil_div(seq[i].row.rows, rpi[i]);
+    return ceil_div(seq[i].M, kBM) * ceil_div(seq[i].N, bn[i]) * (dist[i] ? split[i] : 1);
+  };
   int filler_cursor = 0;
   for (int L = 0; L < levels_; ++L) {
     std::vector<int> members;
@@ -678,6 +939,14 @@ void GemmChain::build(const std::vector<GemmArgs>& seq, int force_bn, int force_
         cursor += sh;
       }
       share[i] = sh;
+      if (is_row(i)) {
+        // rows spread evenly over the share, one item per CTA (a head row costs ~1.5 us of block reductions, far below
+        // what an extra dependency round trip would)
+        bn[i] = 32;
+        split[i] = 1;
+        rpi[i] = std::max(1, ceil_div(seq[i].row.rows, sh));
+        continue;
+      }
       double best = 1e300;
       for (int cbn : {32, 64, 128}) {
         if (force_bn && cbn != force_bn) continue;
@@ -687,17 +956,23 @@ void GemmChain::build(const std::vector<GemmArgs>& seq, int force_bn, int force_
           if (force_split && s != force_split) continue;
           if (filler[i] && !force_split && s > 1) continue;
           if (s > 1 && (s - 1) * ceil_div(nkb, s) >= nkb) continue;  // would leave an empty split
-          const double c = plan_cost(tiles, nkb, cbn, s, sh);
-          if (c < best - 1e-9) {
-            best = c;
-            bn[i] = cbn;
-            split[i] = s;
+          for (int d = 0; d < 2; ++d) {
+            if (d == 1 && (dist_mode == 0 || !dist_possible(cbn, s) || tiles * s > sh)) continue;  // the splits must share a wave
+            if (d == 0 && dist_mode == 2 && dist_possible(cbn, s) && tiles * s <= sh) continue;
+            const double c = plan_cost(tiles, nkb, cbn, s, sh, d == 1);
+            if (c < best - 1e-9) {
+              best = c;
+              bn[i] = cbn;
+              split[i] = s;
+              dist[i] = d;
+            }
           }
         }
       }
       if (best > 1e299) {  // forced values not realisable for this GEMM
         bn[i] = force_bn ? force_bn : 32;
         split[i] = 1;
+        dist[i] = 0;
       }
       if (filler[i]) filler_cursor += ceil_div(a.M, kBM) * ceil_div(a.N, bn[i]);  // the next filler continues where this one ends
     }
@@ -716,7 +991,7 @@ void GemmChain::build(const std::vector<GemmArgs>& seq, int force_bn, int force_
   bytes_ = flops_ = 0.0;
   for (int i : order) {
     const GemmArgs& a = seq[i];
-    const int tiles_m = ceil_div(a.M, kBM), tiles_n = ceil_div(a.N, bn[i]);
+    const int tiles_m = is_row(i) ? items_of(i) : ceil_div(a.M, kBM), tiles_n = is_row(i) ? 1 : ceil_div(a.N, bn[i]);
     const int tiles = tiles_m * tiles_n;
     int item = 0;
     for (int t = 0; t < tiles; ++t)
@@ -724,19 +999,24 @@ void GemmChain::build(const std::vector<GemmArgs>& seq, int force_bn, int force_
         per_cta[(first_cta[i] + item % share[i]) % n_cta].push_back(ChainTask{i, t, s, 0});
     ChainGemmDesc& d = descs[i];
     std::memset(&d, 0, sizeof(d));
-    d.tmA = make_operand_map(a.A, a.a_mn, a.M, a.K, a.lda, kBM);
-    d.tmB = make_operand_map(a.B, a.b_mn, a.N, a.K, a.ldb, bn[i]);
+    if (!is_row(i)) {
+      d.tmA = make_operand_map(a.A, a.a_mn, a.M, a.K, a.lda, kBM);
+      d.tmB = make_operand_map(a.B, a.b_mn, a.N, a.K, a.ldb, bn[i]);
+    }
+    d.row = a.row;
+    d.rows_per_item = rpi[i];
     d.epi = a.epi;
     d.C = a.C;
     d.ldc = a.ldc; d.M = a.M; d.N = a.N; d.K = a.K;
     d.bn = bn[i]; d.a_mn = a.a_mn; d.b_mn = a.b_mn; d.nkb = ceil_div(a.K, kBK);
     d.split_k = split[i]; d.kb_per_split = ceil_div(d.nkb, split[i]);
+    d.dist = dist[i];
     d.tiles_m = tiles_m; d.tiles_n = tiles_n;
     d.n_deps = (int)deps[i].size();
     for (int k = 0; k < d.n_deps; ++k) {
       const int j = deps[i][k];
       d.dep[k] = j;
-      d.dep_target[k] = (unsigned)(ceil_div(seq[j].M, kBM) * ceil_div(seq[j].N, bn[j]));  // tiles of the dependency
+      d.dep_target[k] = (unsigned)items_of(j);  // tiles of the dependency
     }
     ctr_off[i] = ctr_count;
     ctr_count += (size_t)tiles;
@@ -744,8 +1024,14 @@ void GemmChain::build(const std::vector<GemmArgs>& seq, int force_bn, int force_
       ws_off[i] = ws_floats;
       ws_floats += (size_t)tiles * split[i] * kBM * bn[i];
     }
-    bytes_ += 4.0 * ((double)a.M * a.K + (double)a.N * a.K + (double)a.M * a.N);
-    flops_ += 2.0 * a.M * a.N * a.K;
+    if (a.row.kind == ROWOP_CTRL_HEAD) {
+      bytes_ += 4.0 * ((double)a.row.rows * (2.0 * a.row.cols + a.row.D));
+    } else if (a.row.kind == ROWOP_GATHER) {
+      bytes_ += 2.0 * 16.0 * a.row.rows * a.row.rec4;
+    } else {
+      bytes_ += 4.0 * ((double)a.M * a.K + (double)a.N * a.K + (double)a.M * a.N);
+      flops_ += 2.0 * a.M * a.N * a.K;
+    }
   }
   std::vector<ChainTask> tasks;
   std::vector<int> begin(n_cta + 1, 0);
@@ -785,9 +1071,13 @@ void GemmChain::build(const std::vector<GemmArgs>& seq, int force_bn, int force_
     std::fprintf(stderr, "rlrep chain: %d GEMMs, %d levels, %zu items, ws %.1f MB\n", n, levels_, tasks.size(),
                  ws_floats * 4 / 1e6);
     for (int i = 0; i < n; ++i)
-      std::fprintf(stderr, "  [%d] L%d M=%d N=%d K=%d a_mn=%d b_mn=%d bn=%d split=%d share=%d deps=%d%s\n", i, level[i],
-                   seq[i].M, seq[i].N, seq[i].K, (int)seq[i].a_mn, (int)seq[i].b_mn, bn[i], split[i], share[i],
-                   (int)deps[i].size(), filler[i] ? " filler" : "");
+      if (is_row(i))
+        std::fprintf(stderr, "  [%d] L%d row op %d: rows=%d rows/item=%d share=%d deps=%d\n", i, level[i], seq[i].row.kind,
+                     seq[i].row.rows, rpi[i], share[i], (int)deps[i].size());
+      else
+        std::fprintf(stderr, "  [%d] L%d M=%d N=%d K=%d a_mn=%d b_mn=%d bn=%d split=%d%s share=%d deps=%d%s\n", i, level[i],
+                     seq[i].M, seq[i].N, seq[i].K, (int)seq[i].a_mn, (int)seq[i].b_mn, bn[i], split[i],
+                     dist[i] ? " (distributed)" : "", share[i], (int)deps[i].size(), filler[i] ? " filler" : "");
   }
 }
 

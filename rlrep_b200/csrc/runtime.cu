@@ -158,6 +158,7 @@ void Ring::gather_from_host_idx(const long long* idx_host, int B, float* out_dev
 void GemmRunner::init(Precision prec, size_t ws_floats) {
   prec_ = prec;
   if (const char* e = std::getenv("RLREP_CHAIN")) chains_on_ = std::atoi(e) != 0;
+  if (const char* e = std::getenv("RLREP_CHAIN_ROWOPS")) row_ops_on_ = std::atoi(e) != 0;
   ws_floats_ = ws_floats;
   if (ws_floats_) RLREP_CUDA(cudaMalloc(&ws_, ws_floats_ * sizeof(float)));
 }
@@ -175,7 +176,7 @@ void GemmRunner::begin_chain(cudaStream_t s) {
 
 void GemmRunner::flush_chain() {
   if (pending_.empty()) return;
-  if (pending_.size() == 1) {  // nothing to chain: the one-GEMM kernels do this better
+  if (pending_.size() == 1 && pending_[0].row.kind == ROWOP_NONE) {  // nothing to chain: the one-GEMM kernels do this better
     const GemmArgs a = pending_[0];
     pending_.clear();
     const bool rec = recording_;
@@ -194,6 +195,14 @@ void GemmRunner::flush_chain() {
   }
   chain->launch(chain_stream_);
   pending_.clear();
+}
+
+bool GemmRunner::row_op(const RowOp& op) {
+  if (!recording_ || !row_ops_on_) return false;
+  GemmArgs a;
+  a.row = op;
+  pending_.push_back(a);
+  return true;
 }
 
 void GemmRunner::end_chain() {

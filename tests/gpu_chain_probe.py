@@ -59,10 +59,14 @@ ms, levels = _lib.gemm_chain(specs, bn=bn, split_k=split, iters=4)
 torch.cuda.synchronize()
 _lib.check(lib.rlrep_gemm_chain_set_debug(None))
 d = dbg.cpu().numpy().reshape(148, ITEMS, EV)
+entry, exit_ = d[:, ITEMS - 1, 2].copy(), d[:, ITEMS - 1, 3].copy()
+d[:, ITEMS - 1, 2:4] = 0
 valid = d[:, :, 0] > 0
 t0 = d[:, :, 0][valid].min()
 print(f"{which} chain: {len(specs)} GEMMs, {levels} levels, {ms * 1e3:.1f} us per launch (bn={bn}, split={split}); "
       f"{int(valid.sum())} items stamped, last publish at {(d[:, :, [5, 7]].max() - t0) / 1e3:.1f} us")
+print(f"  kernel entry {(entry[entry > 0].min() - t0) / 1e3:.1f}..{(entry.max() - t0) / 1e3:.1f} us, "
+      f"exit {(exit_[exit_ > 0].min() - t0) / 1e3:.1f}..{(exit_.max() - t0) / 1e3:.1f} us (relative to the first item pick)")
 names = ["pick", "deps", "tma", "opnd", "acc", "epi", "arrive", "publish", None, "stored"]
 for g in range(len(specs)):
     sel = valid & ((d[:, :, 8] & 0xFFFF) == g)

@@ -13,7 +13,7 @@ class Space:
         self.low, self.high, self.shape = -np.ones(A, np.float32), np.ones(A, np.float32), (A,)
 
 
-def make_pair(alg, S, A, kw, rows, precision="tf32", use_cuda_graph=True, seed=0, oracle_kw=None):
+def make_pair(alg, S, A, kw, rows, precision="tf32", use_cuda_graph=True, seed=0, oracle_kw=None, agent_kw=None):
     from rlrep_b200 import ReplayBuffer
     from rlrep_b200.agents import AGENTS
     init = O.init_state(alg, S, A, kw, seed=seed)
@@ -27,7 +27,7 @@ def make_pair(alg, S, A, kw, rows, precision="tf32", use_cuda_graph=True, seed=0
     oracle = O.ORACLES[alg](S, A, init, discount=0.99, tau=0.005, **kw, **oracle_kw)
     oring = O.synthetic_ring(S, A, rows, seed=0)
     agent = AGENTS[alg](state_dim=S, action_dim=A, action_space=Space(A), discount=0.99, tau=0.005,
-                        precision=precision, use_cuda_graph=use_cuda_graph, **kw)
+                        precision=precision, use_cuda_graph=use_cuda_graph, **kw, **(agent_kw or {}))
     agent.load_state_dict({**init, **extra_state})
     buf = ReplayBuffer(S, A, max_size=rows)
     buf.load(oring.state, oring.action, oring.next_state, oring.reward, oring.done)

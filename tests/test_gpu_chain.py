@@ -16,11 +16,15 @@ def _elu(x):
     return torch.nn.functional.elu(x)
 
 
-@pytest.mark.parametrize("bn,split_k", [(0, 0), (32, 1), (64, 2), (128, 4), (64, 8), (32, 16)])
+# RLREP_CHAIN_DIST: 0 = split-K partials reduced by the last CTA to arrive, 2 = reduction distributed over the tile's split
+# CTAs wherever the tile width allows it (each finalises bn / split columns), 1 (default) = the planner's cost model decides
+@pytest.mark.parametrize("dist", [0, 2])
+@pytest.mark.parametrize("bn,split_k", [(0, 0), (32, 1), (32, 2), (64, 2), (64, 4), (128, 4), (128, 8), (64, 8), (32, 16)])
 @pytest.mark.parametrize("B,S,H,D", [(256, 23, 1024, 2048), (128, 40, 256, 256), (100, 23, 96, 160)])
-def test_forward_branches_and_logits(lib, bn, split_k, B, S, H, D):
+def test_forward_branches_and_logits(lib, monkeypatch, dist, bn, split_k, B, S, H, D):
     """phi(x) and mu(y) (3 layers each, independent) then logits = phi mu^T: 7 GEMMs, 4 levels."""
     from rlrep_b200 import _lib
+    monkeypatch.setenv("RLREP_CHAIN_DIST", str(dist))
     torch.manual_seed(0)
     dev = "cuda"
     Sp = (S + 3) // 4 * 4
@@ -59,11 +63,13 @@ def test_forward_branches_and_logits(lib, bn, split_k, B, S, H, D):
     print(f"chain fwd B={B} H={H} D={D} bn={bn} split={split_k}: {ms * 1e3:.1f} us per launch")
 
 
-@pytest.mark.parametrize("bn,split_k", [(0, 0), (64, 4), (128, 2)])
-def test_backward_chain(lib, bn, split_k):
+@pytest.mark.parametrize("dist", [0, 2])
+@pytest.mark.parametrize("bn,split_k", [(0, 0), (64, 4), (128, 2), (128, 8)])
+def test_backward_chain(lib, monkeypatch, dist, bn, split_k):
     """dX2 = (dY W3) * elu'(h2); dW3 = dY^T h2; dX1 = (dX2 W2) * elu'(h1); dW2 = dX2^T h1: MN-major operands, derivative
     epilogues, in-chain read-after-write edges."""
     from rlrep_b200 import _lib
+    monkeypatch.setenv("RLREP_CHAIN_DIST", str(dist))
     torch.manual_seed(1)
     dev = "cuda"
     B, H, D = 256, 1024, 2048
@@ -89,9 +95,12 @@ def test_backward_chain(lib, bn, split_k):
     print(f"chain bwd bn={bn} split={split_k}: {ms * 1e3:.1f} us per launch")
 
 
-def test_chain_is_deterministic_and_rearms(lib):
-    """Split-K partials are summed in split order by whichever CTA arrives last: repeated launches are bit-identical."""
+@pytest.mark.parametrize("dist", [0, 2])
+def test_chain_is_deterministic_and_rearms(lib, monkeypatch, dist):
+    """Split-K partials are summed in split order whoever reduces them (the last CTA to arrive, or each split CTA its own
+    columns): repeated launches are bit-identical, and so are the two reduction schemes."""
     from rlrep_b200 import _lib
+    monkeypatch.setenv("RLREP_CHAIN_DIST", str(dist))
     torch.manual_seed(2)
     dev = "cuda"
     x = torch.randn(256, 1024, device=dev)
@@ -103,3 +112,9 @@ def test_chain_is_deterministic_and_rearms(lib):
         outs.append((h.clone(), y.clone()))
     for h, y in outs[1:]:
         assert torch.equal(h, outs[0][0]) and torch.equal(y, outs[0][1])
+    _SCHEMES[dist] = outs[0]
+    if len(_SCHEMES) == 2:
+        assert torch.equal(_SCHEMES[0][0], _SCHEMES[2][0]) and torch.equal(_SCHEMES[0][1], _SCHEMES[2][1])
+
+
+_SCHEMES = {}

@@ -446,3 +446,94 @@ def test_population_of_independent_agents():
         for k, v in alone[i][2].items():
             assert torch.equal(sd[k], v), (i, k)
     pop.close()
+
+
+# ------------------------------------------------------------------------------------------------ noise drawn on the device
+class _OracleOnTheCudaStream:
+    """Routes the oracle's torch.randn(shape) / torch.normal(mean, std) calls to torch's CUDA generator (same shapes, same
+    order, results moved to the CPU): the oracle then consumes the stream a reference run with device = cuda consumes."""
+
+    def __enter__(self):
+        self._randn, self._normal = torch.randn, torch.normal
+
+        def randn(*size, **kw):
+            if kw.get("device") is not None or kw.get("generator") is not None or kw.get("out") is not None:
+                return self._randn(*size, **kw)
+            return self._randn(*size, device="cuda", **kw).cpu()
+
+        def normal(mean, std, **kw):
+            if torch.is_tensor(mean) and not mean.is_cuda:
+                return self._normal(mean.cuda(), std.cuda(), **kw).cpu()
+            return self._normal(mean, std, **kw)
+
+        torch.randn, torch.normal = randn, normal
+        return self
+
+    def __exit__(self, *exc):
+        torch.randn, torch.normal = self._randn, self._normal
+
+
+def test_cuda_generator_draws_do_not_depend_on_the_call_used():
+    """noise_device="cuda" relies on torch.randn(shape, device) and torch.randn_like(cuda tensor) -- what the reference
+    calls on CUDA tensors (networks/vae.py:50-58, sac_agent.py actor sampling through rsample) -- consuming the CUDA
+    generator identically."""
+    x = torch.zeros(1024, 256, device="cuda")
+    torch.cuda.manual_seed(7)
+    a, a2 = torch.randn_like(x), torch.randn_like(x[:, :17])
+    torch.cuda.manual_seed(7)
+    b, b2 = torch.randn(1024, 256, device="cuda"), torch.randn(1024, 17, device="cuda")
+    assert torch.equal(a, b) and torch.equal(a2, b2)
+
+
+@pytest.mark.parametrize("case", ["sac", "ctrlsac_small", "vlsac_hum", "spedersac_deep", "diffsrsac_odd"])
+def test_device_noise_matches_oracle_on_the_same_stream(case):
+    """noise_device="cuda": the update is the same function of (indices, noise); only where the noise is drawn changes.
+    The oracle is fed the CUDA generator's stream, the agent draws from it directly.  Losses over three train() calls and
+    the parameters after the first one (compared like test_single_update_meets_the_bar) at the fp32 bar."""
+    alg, shp, kw, B = CASES[case]
+    okw = dict(as_written=False) if alg == "ctrlsac" else {}
+    agent, buf, oracle, oring = make_pair(alg, shp["S"], shp["A"], kw, rows=5000, precision="fp32", oracle_kw=okw,
+                                          agent_kw=dict(noise_device="cuda"))
+    before = {k: v.detach().clone() for k, v in oracle.state_dict().items()}
+
+    def seed():
+        np.random.seed(1)
+        torch.manual_seed(1)  # CPU generator: diffsrsac's noise-level indices (drawn on the CPU in the reference too)
+        torch.cuda.manual_seed(1)
+
+    seed()
+    with _OracleOnTheCudaStream():
+        oi = [oracle.train(oring, B)]
+    seed()
+    ci = [agent.train(buf, B)]
+    wp, where_p, skipped = worst_param_error_conditioned(agent, oracle, before)
+    state = (np.random.get_state(), torch.get_rng_state(), torch.cuda.get_rng_state())  # both sides continue from here
+    with _OracleOnTheCudaStream():
+        oi += [oracle.train(oring, B) for _ in range(2)]
+    np.random.set_state(state[0])
+    torch.set_rng_state(state[1])
+    torch.cuda.set_rng_state(state[2])
+    ci += [agent.train(buf, B) for _ in range(2)]
+    wi, where_i = worst_info_error(ci, oi, atol=INFO_ATOL.get((case, "tf32"), 1e-5))
+    print(f"{case} device noise: worst info rel {wi:.2e} at {where_i}; worst param rel-l2 {wp:.2e} at {where_p}; "
+          f"ill-conditioned elements left out {skipped:.2e}")
+    assert wi < BARS["fp32"], where_i
+    assert wp < BARS["fp32"], where_p
+    assert skipped < 2e-2
+
+
+def test_row_operations_inside_the_chain(monkeypatch):
+    """RLREP_CHAIN_ROWOPS=1: the replay gather and the contrastive head run as row-operation items of the feature step's
+    chain kernel (one launch per feature step) instead of stand-alone kernels between two chains -- same results."""
+    monkeypatch.setenv("RLREP_CHAIN_ROWOPS", "1")
+    alg, shp, kw, B = CASES["ctrlsac"]
+    agent, buf, oracle, oring = make_pair(alg, shp["S"], shp["A"], kw, rows=5000, precision="tf32",
+                                          oracle_kw=dict(as_written=False))
+    ci, oi = step_both(agent, buf, oracle, oring, B, 3)
+    wi, where_i = worst_info_error(ci, oi, atol=1e-5)
+    wp, where_p, _ = worst_param_error(agent, oracle)
+    print(f"row ops in chain: worst info rel {wi:.2e} at {where_i}; worst param rel-l2 {wp:.2e} at {where_p}; "
+          f"{agent.gpu_launches_last_train} launches")
+    assert wi < BARS["tf32"], where_i
+    assert wp < BARS["tf32"], where_p
+    assert agent.gpu_launches_last_train == 35  # 47 with the stand-alone gather / head kernels
