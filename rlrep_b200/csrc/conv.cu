@@ -127,6 +127,29 @@ __global__ void diag_block_sum_kernel(const float* __restrict__ C, int ldc, int 
   dW[(size_t)o * ld_dw + k] = acc;
 }
 
+// Implicit weight gradient, step 1: the output gradient [B, Ho, Ho, 32] onto the INPUT's grid (Hi = Ho + 2 wide), zero where
+// the 3x3 window would leave the image, so that input row m + ky * Hi + kx pairs with gradient row m for every tap.
+__global__ void scatter_to_input_grid_kernel(const float4* __restrict__ dy, int B, int Ho, int Hi, float4* __restrict__ grid) {
+  const long long total = (long long)B * Hi * Hi * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i & 7);
+    const long long pix = i >> 3;
+    const int x = (int)(pix % Hi), y = (int)((pix / Hi) % Hi), b = (int)(pix / ((long long)Hi * Hi));
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (x < Ho && y < Ho) v = dy[(((long long)b * Ho + y) * Ho + x) * 8 + c4];
+    grid[i] = v;
+  }
+}
+// Step 3: dW[n, (ky, kx), c] = sum_f C[(f, n), (ky, kx + f, c)] over the four folded rows, C [128, 576] (fixed order)
+__global__ void diag_tap_sum_kernel(const float* __restrict__ C, float* __restrict__ dW, int ld_dw) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 32 * 288) return;
+  const int n = i / 288, r = i - n * 288, t = r >> 5, c = r & 31, ky = t / 3, kx = t - 3 * ky;
+  float acc = 0.f;
+  for (int f = 0; f < 4; ++f) acc += C[(size_t)(f * 32 + n) * 576 + ky * 192 + (kx + f) * 32 + c];
+  dW[(size_t)n * ld_dw + r] = acc;
+}
+
 int grid_for(long long work, int threads) {
   const long long want = (work + threads - 1) / threads;
   return (int)std::min<long long>(want, (long long)kNumSMs * 16);
@@ -147,14 +170,18 @@ ConvEncoder::ConvEncoder(int batch, int in_channels, int height, Precision prec,
   for (int l = 1; l < 4; ++l) conv_[l] = add_linear(g_, "convnet." + std::to_string(2 * l), 32, 288);
   if (with_target) g_.n_target = g_.n;
   g_.want(arena_);
-  arena_.want(&col_[0], rows(0) * ldk1_);
-  for (int l = 1; l < 4; ++l) arena_.want(&col_[l], rows(l) * 288);
-  for (int l = 0; l < 4; ++l) {
-    arena_.want(&act_[l], rows(l) * 32);
-    arena_.want(&dact_[l], rows(l) * 32);
-  }
   // RLREP_CONV_V1=1 keeps the explicit  dcol = dY W  +  col2im  data gradient (A/B runs); default: implicit
   implicit_dgrad_ = !(std::getenv("RLREP_CONV_V1") && std::atoi(std::getenv("RLREP_CONV_V1")) != 0);
+  implicit_wgrad_ = implicit_dgrad_ && prec == PREC_TF32 && B_ % 4 == 0 &&
+                    !(std::getenv("RLREP_CONV_WGRAD_V1") && std::atoi(std::getenv("RLREP_CONV_WGRAD_V1")) != 0);
+  arena_.want(&col_[0], rows(0) * ldk1_);
+  if (!implicit_wgrad_)  // 1.2 GB at B = 256 that the implicit path never allocates
+    for (int l = 1; l < 4; ++l) arena_.want(&col_[l], rows(l) * 288);
+  for (int l = 0; l < 4; ++l) {
+    // + slack rows (zero from the arena, never written): the implicit weight gradient reads up to 2 Hi + 5 rows past a map
+    arena_.want(&act_[l], (rows(l) + 2 * hw_[l] + 8) * 32);
+    arena_.want(&dact_[l], rows(l) * 32);
+  }
   if (implicit_dgrad_) corr_.want(arena_, B_, hw_[1]);
   else arena_.want(&dcol_, rows(1) * 288);
   arena_.want(&bias_partial_, kBiasChunks * 32);
@@ -172,7 +199,7 @@ void ConvEncoder::forward(const unsigned char* obs_dev, const int* shifts_dev, f
   RLREP_LAUNCHED_W("im2col_u8_aug", s, (double)B_ * C_ * H_ * H_ + 4.0 * rows(0) * ldk1_, 0.0);
   linear_fwd(gemm_, s, (int)rows(0), Mat{col_[0], ldk1_}, conv_[0].view(g_, target), ACT_RELU, act_[0], 32);
   for (int l = 1; l < 4; ++l) {
-    if ((target || no_grad) && implicit_dgrad_) {
+    if ((target || no_grad || implicit_wgrad_) && implicit_dgrad_) {
       // no backward pass follows (target / no-grad evaluation), so no column matrix is needed: implicit convolution
       const Linear w = conv_[l].view(g_, target);
       valid_conv_3x3(gemm_, s, B_, hw_[l - 1], act_[l - 1], w.W, w.ld, w.b, ACT_RELU, act_[l], corr_);
@@ -203,7 +230,23 @@ void ConvEncoder::backward(const float* dfeat_dev, int ld_dfeat) {
     // split-K CTAs per N-tile would leave the GPU idle.  Fold kFold consecutive rows into one: dY as [rows / F, 32 F],
     // col as [rows / F, ldk F]; their product is an [32 F, ldk F] matrix whose F diagonal blocks sum to dW.  Same
     // tensor-core work as before (the tile is now full), K shrinks F-fold and the N-tiles multiply F-fold.
-    if (rows(l) % kFold == 0) {
+    if (l > 0 && implicit_wgrad_) {
+      // no column matrix: dY goes onto the input's grid (55 MB at B = 256 instead of the 450 MB col), and the GEMM's TMA
+      // producer reads the input map through the shifted (ky, q, c) view (gemm.cuh conv_wgrad_hi)
+      const int Hi = hw_[l - 1], Ho = hw_[l];
+      scatter_to_input_grid_kernel<<<grid_for(rows(l - 1) * 8, 256), 256, 0, s>>>(
+          reinterpret_cast<const float4*>(dact_[l]), B_, Ho, Hi, reinterpret_cast<float4*>(corr_.padded));
+      RLREP_LAUNCHED_W("scatter_to_input_grid", s, 4.0 * 32 * (rows(l) + rows(l - 1)), 0.0);
+      GemmArgs a;
+      a.M = 128; a.N = 576; a.K = (int)(rows(l - 1) / 4);
+      a.A = corr_.padded; a.lda = 128; a.a_mn = true;
+      a.B = act_[l - 1]; a.ldb = 128; a.b_mn = true;
+      a.conv_wgrad_hi = Hi;
+      a.C = wfold_; a.ldc = 576;
+      gemm_.run(a, s);
+      diag_tap_sum_kernel<<<ceil_div(32 * 288, 256), 256, 0, s>>>(wfold_, w.dW, w.ld);
+      RLREP_LAUNCHED("diag_tap_sum", s);
+    } else if (rows(l) % kFold == 0) {
       GemmArgs a;
       a.M = 32 * kFold; a.N = col.ld * kFold; a.K = (int)(rows(l) / kFold);
       a.A = dy.p; a.lda = 32 * kFold; a.a_mn = true;

@@ -39,6 +39,9 @@ class ConvEncoder {
   float* dact_[4] = {nullptr, nullptr, nullptr, nullptr};
   float* dcol_ = nullptr;
   bool implicit_dgrad_ = true;
+  // layers 2-4 without column matrices at all (TF32 path): implicit forward convolution, implicit data gradient and the
+  // implicit weight gradient of GemmArgs::conv_wgrad_hi; RLREP_CONV_WGRAD_V1=1 keeps the explicit im2col + folded GEMM
+  bool implicit_wgrad_ = false;
   FullCorrScratch corr_;
   static constexpr int kBiasChunks = 296;  // 2 x 148 SMs
   float* bias_partial_ = nullptr;

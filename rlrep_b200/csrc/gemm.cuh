@@ -73,6 +73,14 @@ struct GemmArgs {
   //   C[m, n] = sum_{ky, kx, c} A[m + ky * conv_w + kx, c] * B(n, (ky * 3 + kx) * 32 + c)
   // with rows past M read as zero.  No column matrix is materialised: the TMA producer shifts its row coordinate.
   int conv_w = 0;
+  // Implicit weight gradient of that convolution (tensor-core path, both operands MN-major): conv_wgrad_hi = Hi > 0 makes B
+  // the convolution's INPUT, a dense [rows, 32] NHWC map on a grid Hi wide, read through the view
+  //   B(k, n = ky * 192 + q * 32 + c) = X[4 k + q + ky * Hi, c],   q = 0..5, ky = 0..2   (N = 576),
+  // i.e. with A = the output gradient on the same grid folded four rows to one ([rows / 4, 128], zero where the window
+  // leaves the image) the product C[(f, n), (ky, q, c)] holds dW[n, (ky, kx), c] = sum_f C[(f, n), (ky, kx + f, c)].
+  // No column matrix exists; K = rows / 4, and 2 Hi + 5 rows of finite values must be readable behind the map (they meet
+  // zeros of A).
+  int conv_wgrad_hi = 0;
   const float* B = nullptr;
   int ldb = 0;
   bool b_mn = false;

@@ -215,6 +215,7 @@ void launch_simt(const GemmArgs& a, cudaStream_t stream) {
   RLREP_CHECK(a.A2 == nullptr || !a.a_mn, "two-segment A requires a K-major A");
   SimtParams p;
   RLREP_CHECK(a.conv_w == 0 || (!a.a_mn && a.A2 == nullptr && a.K == 9 * 32), "implicit convolution needs a K-major [M, 32] A");
+  RLREP_CHECK(a.conv_wgrad_hi == 0, "the implicit conv weight gradient exists on the tensor-core path only");
   p.M = a.M; p.N = a.N; p.K = a.K; p.K1 = a.A2 ? a.K1 : a.K;
   p.conv_w = a.conv_w;
   p.A = a.A;

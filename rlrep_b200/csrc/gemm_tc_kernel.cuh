@@ -354,7 +354,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else {
       ptx::tma_load_3d(a_dst, &tmA, &full_bar[s], 0, k0, m0 / 32);
     }
+    // implicit weight gradient (conv_w < 0): n-chunk j of the (ky, q, c) view is (q, ky) = (j % 6, j / 6)
     if (!B_MN) ptx::tma_load_2d(b_dst, &tmB, &full_bar[s], k0, n0);
+    else if (conv_w < 0) ptx::tma_load_4d(b_dst, &tmB, &full_bar[s], 0, k0, (n0 / 32) % 6, (n0 / 32) / 6);
     else ptx::tma_load_3d(b_dst, &tmB, &full_bar[s], 0, k0, n0 / 32);
   };
   // one stage before the setup barrier (TMA issue itself is not free) -- except under PDL, where no global read may
@@ -745,11 +747,13 @@ void launch_variant(const TcGemmPlan& p, cudaStream_t stream) {
   fill_launch_config<BN, A_MN, B_MN>(cfg, attr, dim3(ceil_div(a.N, BN), ceil_div(a.M, BM), p.split_k), p.split_k,
                                      p.stages, p.push, stream);
   RLREP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, A_MN, B_MN>, p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, a.K,
-                                p.kb_per_split, p.stages, (p.push ? 1 : 0) | (pdl_enabled() ? 2 : 0), a.conv_w, a.epi));
+                                p.kb_per_split, p.stages, (p.push ? 1 : 0) | (pdl_enabled() ? 2 : 0),
+                                a.conv_wgrad_hi > 0 ? -1 : a.conv_w, a.epi));
   g_trace_reader = &read_trace_here;
   // implicit convolution: A is the [M, 32] pixel matrix, read once from HBM (the nine shifted re-reads hit L2)
   RLREP_LAUNCHED_W("gemm_tf32", stream,
-                   4.0 * ((double)a.M * (a.conv_w > 0 ? 32 : a.K) + (double)a.N * a.K + (double)a.M * a.N),
+                   4.0 * ((double)a.M * (a.conv_w > 0 ? 32 : a.K) + (double)(a.conv_wgrad_hi > 0 ? 128 : a.N) * a.K +
+                          (double)a.M * a.N),
                    2.0 * a.M * a.N * a.K);
 }
 
