@@ -529,7 +529,7 @@ def run_pixels(args, w, rank, world, local_rank):
                 "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
                 "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu, "last_info": info,
                 ("tf32" if precision == "fp32" else "fp32"): other,
-                "top_kernels_us_per_step": [[k, round(v, 1), c] for k, v, c in top[:8]]}
+                "top_kernels_us_per_step": [[k, round(v, 1), c] for k, v, c in top[:16]]}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -24,19 +24,24 @@ constexpr int kPad = 4;  // RandomShiftsAug(pad=4)
 __global__ void im2col_u8_aug_kernel(const unsigned char* __restrict__ obs, const int* __restrict__ shifts, int B, int C,
                                      int H, int Ho, float4* __restrict__ col, int ldk) {
   // one thread per (output pixel, four consecutive k), k = c * 9 + ky * 3 + kx -- the reference's weight layout
-  // [32, C, 3, 3] flattened; 16-byte stores, consecutive threads on consecutive pieces of a row; byte loads served by L1
-  const int K = C * 9, q4 = ldk >> 2;
-  const long long total = (long long)B * Ho * Ho * q4;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int q = (int)(i % q4);
-    const long long row = i / q4;
-    const int ox = (int)(row % Ho), oy = (int)((row / Ho) % Ho), b = (int)(row / ((long long)Ho * Ho));
+  // [32, C, 3, 3] flattened; 16-byte stores, consecutive threads on consecutive pieces of a row; byte loads served by L1.
+  // obs / 255.0 - 0.5 (op by op like torch) comes from a 256-entry table built with exactly those two operations, and all
+  // index arithmetic is 32-bit (checked by the constructor): the IEEE divisions and 64-bit div / mod by run-time values
+  // were most of this kernel's instructions (100 us for a 165 MB write).
+  __shared__ float lut[256];
+  for (int p = threadIdx.x; p < 256; p += blockDim.x) lut[p] = __fsub_rn(__fdiv_rn((float)p, 255.0f), 0.5f);
+  __syncthreads();
+  const int K = C * 9, q4 = ldk >> 2, HoHo = Ho * Ho;
+  const int total = B * HoHo * q4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int row = i / q4, q = i - row * q4;
+    const int b = row / HoHo, rem = row - b * HoHo, oy = rem / Ho, ox = rem - oy * Ho;
     int sx = 0, sy = 0;
     if (shifts != nullptr) {  // padded[i + sy, j + sx] with replicate padding == clamp(i + sy - pad)
       sx = shifts[2 * b] - kPad;
       sy = shifts[2 * b + 1] - kPad;
     }
-    const unsigned char* img = obs + (long long)b * C * H * H;
+    const unsigned char* img = obs + (size_t)b * C * H * H;
     float v[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
@@ -45,8 +50,7 @@ __global__ void im2col_u8_aug_kernel(const unsigned char* __restrict__ obs, cons
       if (k < K) {
         const int c = k / 9, r9 = k - 9 * c, ky = r9 / 3, kx = r9 - 3 * ky;
         const int iy = min(max(2 * oy + ky + sy, 0), H - 1), ix = min(max(2 * ox + kx + sx, 0), H - 1);
-        const float p = (float)img[((long long)c * H + iy) * H + ix];
-        v[e] = __fsub_rn(__fdiv_rn(p, 255.0f), 0.5f);  // obs / 255.0 - 0.5, op by op like torch
+        v[e] = lut[img[(c * H + iy) * H + ix]];
       }
     }
     col[i] = make_float4(v[0], v[1], v[2], v[3]);
@@ -127,29 +131,6 @@ __global__ void diag_block_sum_kernel(const float* __restrict__ C, int ldc, int 
   dW[(size_t)o * ld_dw + k] = acc;
 }
 
-// Implicit weight gradient, step 1: the output gradient [B, Ho, Ho, 32] onto the INPUT's grid (Hi = Ho + 2 wide), zero where
-// the 3x3 window would leave the image, so that input row m + ky * Hi + kx pairs with gradient row m for every tap.
-__global__ void scatter_to_input_grid_kernel(const float4* __restrict__ dy, int B, int Ho, int Hi, float4* __restrict__ grid) {
-  const long long total = (long long)B * Hi * Hi * 8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i & 7);
-    const long long pix = i >> 3;
-    const int x = (int)(pix % Hi), y = (int)((pix / Hi) % Hi), b = (int)(pix / ((long long)Hi * Hi));
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (x < Ho && y < Ho) v = dy[(((long long)b * Ho + y) * Ho + x) * 8 + c4];
-    grid[i] = v;
-  }
-}
-// Step 3: dW[n, (ky, kx), c] = sum_f C[(f, n), (ky, kx + f, c)] over the four folded rows, C [128, 576] (fixed order)
-__global__ void diag_tap_sum_kernel(const float* __restrict__ C, float* __restrict__ dW, int ld_dw) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= 32 * 288) return;
-  const int n = i / 288, r = i - n * 288, t = r >> 5, c = r & 31, ky = t / 3, kx = t - 3 * ky;
-  float acc = 0.f;
-  for (int f = 0; f < 4; ++f) acc += C[(size_t)(f * 32 + n) * 576 + ky * 192 + (kx + f) * 32 + c];
-  dW[(size_t)n * ld_dw + r] = acc;
-}
-
 int grid_for(long long work, int threads) {
   const long long want = (work + threads - 1) / threads;
   return (int)std::min<long long>(want, (long long)kNumSMs * 16);
@@ -160,6 +141,7 @@ int grid_for(long long work, int threads) {
 ConvEncoder::ConvEncoder(int batch, int in_channels, int height, Precision prec, cudaStream_t s, bool with_target)
     : B_(batch), C_(in_channels), H_(height), stream_(s) {
   RLREP_CHECK(B_ > 0 && C_ > 0 && H_ >= 16, "bad encoder dimensions");
+  RLREP_CHECK((long long)B_ * H_ * H_ * (C_ * 9 + 32) / 4 < (1LL << 31), "encoder batch too large for 32-bit column indexing");
   hw_[0] = (H_ - 3) / 2 + 1;  // 84 -> 41
   for (int l = 1; l < 4; ++l) hw_[l] = hw_[l - 1] - 2;  // 39, 37, 35
   K1_ = C_ * 9;
@@ -233,19 +215,7 @@ void ConvEncoder::backward(const float* dfeat_dev, int ld_dfeat) {
     if (l > 0 && implicit_wgrad_) {
       // no column matrix: dY goes onto the input's grid (55 MB at B = 256 instead of the 450 MB col), and the GEMM's TMA
       // producer reads the input map through the shifted (ky, q, c) view (gemm.cuh conv_wgrad_hi)
-      const int Hi = hw_[l - 1], Ho = hw_[l];
-      scatter_to_input_grid_kernel<<<grid_for(rows(l - 1) * 8, 256), 256, 0, s>>>(
-          reinterpret_cast<const float4*>(dact_[l]), B_, Ho, Hi, reinterpret_cast<float4*>(corr_.padded));
-      RLREP_LAUNCHED_W("scatter_to_input_grid", s, 4.0 * 32 * (rows(l) + rows(l - 1)), 0.0);
-      GemmArgs a;
-      a.M = 128; a.N = 576; a.K = (int)(rows(l - 1) / 4);
-      a.A = corr_.padded; a.lda = 128; a.a_mn = true;
-      a.B = act_[l - 1]; a.ldb = 128; a.b_mn = true;
-      a.conv_wgrad_hi = Hi;
-      a.C = wfold_; a.ldc = 576;
-      gemm_.run(a, s);
-      diag_tap_sum_kernel<<<ceil_div(32 * 288, 256), 256, 0, s>>>(wfold_, w.dW, w.ld);
-      RLREP_LAUNCHED("diag_tap_sum", s);
+      conv3x3_wgrad_implicit(gemm_, s, B_, hw_[l - 1], dact_[l], act_[l - 1], w.dW, w.ld, /*transposed=*/false, corr_);
     } else if (rows(l) % kFold == 0) {
       GemmArgs a;
       a.M = 32 * kFold; a.N = col.ld * kFold; a.K = (int)(rows(l) / kFold);

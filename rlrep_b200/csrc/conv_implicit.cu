@@ -61,7 +61,63 @@ __global__ void compact_grid_kernel(const float4* __restrict__ grid, int B, int 
   }
 }
 
+// in [B, Hs, Hs, 32] onto a grid Hg wide (zero outside)
+__global__ void scatter_to_grid_kernel(const float4* __restrict__ in, int B, int Hs, int Hg, float4* __restrict__ grid) {
+  const long long total = (long long)B * Hg * Hg * 8;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c4 = (int)(i & 7);
+    const int pix = (int)(i >> 3);
+    const int b = pix / (Hg * Hg), rem = pix - b * Hg * Hg, y = rem / Hg, x = rem - y * Hg;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (x < Hs && y < Hs) v = in[(((long long)b * Hs + y) * Hs + x) * 8 + c4];
+    grid[i] = v;
+  }
+}
+// G[n, (ky, kx), c] = sum_f C[(f, n), (ky, kx + f, c)] over the four folded rows, C [128, 576] (fixed order)
+__global__ void diag_tap_sum_kernel(const float* __restrict__ C, float* __restrict__ dW, int ld_dw, int transposed) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 32 * 288) return;
+  const int n = i / 288, r = i - n * 288, t = r >> 5, c = r & 31, ky = t / 3, kx = t - 3 * ky;
+  float acc = 0.f;
+  for (int f = 0; f < 4; ++f) acc += C[(size_t)(f * 32 + n) * 576 + ky * 192 + (kx + f) * 32 + c];
+  if (transposed) dW[(size_t)r * ld_dw + n] = acc;
+  else dW[(size_t)n * ld_dw + r] = acc;
+}
+
 }  // namespace
+
+void conv3x3_wgrad_implicit(GemmRunner& g, cudaStream_t s, int B, int Hg, const float* small, const float* map, float* dW,
+                            int ld_dw, bool transposed, FullCorrScratch& sc) {
+  const long long rows = (long long)B * Hg * Hg;
+  RLREP_CHECK(rows % 4 == 0 && rows * 8 < (1LL << 31), "implicit weight gradient: batch must be a multiple of 4 (and < 2^28 pixels)");
+  scatter_to_grid_kernel<<<grid_for(rows * 8, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(small), B, Hg - 2, Hg,
+                                                               reinterpret_cast<float4*>(sc.padded));
+  RLREP_LAUNCHED_W("scatter_to_grid", s, 4.0 * 32 * ((double)B * (Hg - 2) * (Hg - 2) + rows), 0.0);
+  GemmArgs a;
+  a.M = 128; a.N = 576; a.K = (int)(rows / 4);
+  a.A = sc.padded; a.lda = 128; a.a_mn = true;
+  a.B = map; a.ldb = 128; a.b_mn = true;
+  a.conv_wgrad_hi = Hg;
+  a.C = sc.wfold; a.ldc = 576;
+  g.run(a, s);
+  diag_tap_sum_kernel<<<ceil_div(32 * 288, 256), 256, 0, s>>>(sc.wfold, dW, ld_dw, transposed ? 1 : 0);
+  RLREP_LAUNCHED("diag_tap_sum", s);
+}
+
+void valid_conv_3x3_wt(GemmRunner& g, cudaStream_t s, int B, int Hi, const float* in, const float* W, const float* mask,
+                       float* out, FullCorrScratch& sc) {
+  const int Ho = Hi - 2;
+  GemmArgs a;
+  a.M = B * Hi * Hi; a.N = 32; a.K = 288;
+  a.A = in; a.lda = 32; a.conv_w = Hi;
+  a.B = W; a.ldb = 32; a.b_mn = true;
+  a.C = sc.out_grid; a.ldc = 32;
+  g.run(a, s);
+  compact_grid_kernel<<<grid_for((long long)B * Ho * Ho * 8, 256), 256, 0, s>>>(
+      reinterpret_cast<const float4*>(sc.out_grid), B, Hi, Ho, reinterpret_cast<const float4*>(mask),
+      reinterpret_cast<float4*>(out));
+  RLREP_LAUNCHED_W("compact_grid", s, 4.0 * 32 * ((double)B * Ho * Ho * (mask ? 3 : 2)), 0.0);
+}
 
 void full_correlation_3x3(GemmRunner& g, cudaStream_t s, int B, int Hi, const float* in, const float* W, int weights,
                           const float* bias, int act, const float* mask, float* out, FullCorrScratch& sc) {

@@ -8,12 +8,13 @@ namespace rlrep {
 
 // Scratch for one full correlation at a time: the zero-padded input grid, the output grid and the repacked weights.
 struct FullCorrScratch {
-  float *padded = nullptr, *out_grid = nullptr, *w_flip = nullptr;
+  float *padded = nullptr, *out_grid = nullptr, *w_flip = nullptr, *wfold = nullptr;
   void want(DeviceArena& a, int batch, int max_hi) {
     const size_t rows = (size_t)batch * (max_hi + 4) * (max_hi + 4);
     a.want(&padded, rows * 32);
     a.want(&out_grid, rows * 32);
     a.want(&w_flip, 32 * 288);
+    a.want(&wfold, 128 * 576);
   }
 };
 
@@ -26,6 +27,21 @@ enum FullCorrWeights : int {
 // in [B, Hi, Hi, 32] (zero outside), out / mask [B, Hi + 2, Hi + 2, 32]; bias and mask may be null.
 void full_correlation_3x3(GemmRunner& g, cudaStream_t s, int B, int Hi, const float* in, const float* W, int weights,
                           const float* bias, int act, const float* mask, float* out, FullCorrScratch& scratch);
+
+// Weight gradient of a 3x3 valid convolution / stride-1 transposed convolution without a column matrix:
+//   G[n, (ky, kx), c] = sum_{b, y, x} small[b, y, x, n] * map[b, y + ky, x + kx, c]
+// small [B, Hg - 2, Hg - 2, 32] (the convolution's output gradient, or the transposed convolution's input), map
+// [B, Hg, Hg, 32] (the convolution's input, or the transposed convolution's output gradient) FOLLOWED BY 2 Hg + 5 readable
+// rows of finite values.  `small` is copied onto the map's grid (zero outside) and folded four rows to one; the GEMM's TMA
+// producer reads `map` through the shifted view of GemmArgs::conv_wgrad_hi.  Tensor-core path only; B % 4 == 0.
+// transposed = false writes dW[n * ld + (ky * 3 + kx) * 32 + c], true writes dW[((ky * 3 + kx) * 32 + c) * ld + n].
+void conv3x3_wgrad_implicit(GemmRunner& g, cudaStream_t s, int B, int Hg, const float* small, const float* map, float* dW,
+                            int ld_dw, bool transposed, FullCorrScratch& scratch);
+
+// Valid 3x3 convolution of dY-like maps with MN-major weights, for the data gradient of a stride-1 transposed convolution:
+// out[b, y, x, n] = (mask > 0) * sum_{ky, kx, c} in[b, y + ky, x + kx, c] * W[(ky * 3 + kx) * 32 + c, n], W [288, 32].
+void valid_conv_3x3_wt(GemmRunner& g, cudaStream_t s, int B, int Hi, const float* in, const float* W, const float* mask,
+                       float* out, FullCorrScratch& scratch);
 
 // Valid 3x3 convolution of a dense NHWC map without a column matrix: out[b, oy, ox, n] = act(bias[n] + sum_{ky, kx, c}
 // in[b, oy + ky, ox + kx, c] * W[n, (ky, kx), c]), in [B, Hi, Hi, 32], out [B, Hi - 2, Hi - 2, 32].  The GEMM runs on the

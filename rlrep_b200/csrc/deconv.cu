@@ -105,23 +105,28 @@ __global__ void __launch_bounds__(256) out_conv_fwd_kernel(const float4* __restr
   }
   __syncthreads();
   const float b0 = bias[0], b1 = bias[1], b2 = bias[2];
-  const long long total = (long long)B * Ho * Ho;  // pixels; the grid-stride loop keeps whole warps together
-  const int c4 = threadIdx.x & 7;
-  for (long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < ((total + 3) & ~3LL);
-       i += ((long long)gridDim.x * blockDim.x) >> 3) {
+  // 32-bit index arithmetic throughout (the launcher checks that every index fits): 64-bit div / mod by run-time values cost
+  // more instructions than the taps' FMAs.  All taps' loads are issued before the first FMA.
+  const int total = B * Ho * Ho;  // pixels; the grid-stride loop keeps whole warps together
+  const int c4 = threadIdx.x & 7, HoHo = Ho * Ho;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < ((total + 3) & ~3); i += (gridDim.x * blockDim.x) >> 3) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     if (i < total) {
-      const int ox = (int)(i % Ho), oy = (int)((i / Ho) % Ho), b = (int)(i / ((long long)Ho * Ho));
+      const int b = i / HoHo, rem = i - b * HoHo, oy = rem / Ho, ox = rem - oy * Ho;
+      float4 v[T];
 #pragma unroll
       for (int tap = 0; tap < T; ++tap) {
         const int iy = oy + (tap / KS) - 1, ix = ox + (tap % KS) - 1;
-        if (iy < 0 || iy >= Hi || ix < 0 || ix >= Hi) continue;
-        const float4 v = x[(((long long)b * Hi + iy) * Hi + ix) * 8 + c4];
+        const bool ok = iy >= 0 && iy < Hi && ix >= 0 && ix < Hi;
+        v[tap] = ok ? x[((b * Hi + iy) * Hi + ix) * 8 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+#pragma unroll
+      for (int tap = 0; tap < T; ++tap) {
         const float* wc = w_s + tap * 96 + c4 * 12;
-        a0 = fmaf(v.x, wc[0], a0); a1 = fmaf(v.x, wc[1], a1); a2 = fmaf(v.x, wc[2], a2);
-        a0 = fmaf(v.y, wc[3], a0); a1 = fmaf(v.y, wc[4], a1); a2 = fmaf(v.y, wc[5], a2);
-        a0 = fmaf(v.z, wc[6], a0); a1 = fmaf(v.z, wc[7], a1); a2 = fmaf(v.z, wc[8], a2);
-        a0 = fmaf(v.w, wc[9], a0); a1 = fmaf(v.w, wc[10], a1); a2 = fmaf(v.w, wc[11], a2);
+        a0 = fmaf(v[tap].x, wc[0], a0); a1 = fmaf(v[tap].x, wc[1], a1); a2 = fmaf(v[tap].x, wc[2], a2);
+        a0 = fmaf(v[tap].y, wc[3], a0); a1 = fmaf(v[tap].y, wc[4], a1); a2 = fmaf(v[tap].y, wc[5], a2);
+        a0 = fmaf(v[tap].z, wc[6], a0); a1 = fmaf(v[tap].z, wc[7], a1); a2 = fmaf(v[tap].z, wc[8], a2);
+        a0 = fmaf(v[tap].w, wc[9], a0); a1 = fmaf(v[tap].w, wc[10], a1); a2 = fmaf(v[tap].w, wc[11], a2);
       }
     }
 #pragma unroll
@@ -209,22 +214,26 @@ __global__ void __launch_bounds__(256) out_conv_dgrad_kernel(const float4* __res
     w_s[i] = W[(o * 32 + c) * T + tap];
   }
   __syncthreads();
-  const long long total = (long long)B * Hi * Hi * 8;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c4 = (int)(i & 7);
-    const long long pix = i >> 3;
-    const int ix = (int)(pix % Hi), iy = (int)((pix / Hi) % Hi), b = (int)(pix / ((long long)Hi * Hi));
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const int total = B * Hi * Hi * 8, HiHi = Hi * Hi;  // 32-bit index arithmetic (checked by the launcher), loads before FMAs
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c4 = i & 7, pix = i >> 3;
+    const int b = pix / HiHi, rem = pix - b * HiHi, iy = rem / Hi, ix = rem - iy * Hi;
+    float4 g[T];
 #pragma unroll
     for (int tap = 0; tap < T; ++tap) {
       const int oy = iy - (tap / KS) + 1, ox = ix - (tap % KS) + 1;
-      if (oy < 0 || oy >= Ho || ox < 0 || ox >= Ho) continue;
-      const float4 g = dpred[((long long)b * Ho + oy) * Ho + ox];
-      const float* w = w_s + tap * 96 + c4 * 12;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[j] = fmaf(g.x, w[3 * j], fmaf(g.y, w[3 * j + 1], fmaf(g.z, w[3 * j + 2], acc[j])));
+      const bool ok = oy >= 0 && oy < Ho && ox >= 0 && ox < Ho;
+      g[tap] = ok ? dpred[(b * Ho + oy) * Ho + ox] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
     const float4 xv = x[i];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int tap = 0; tap < T; ++tap) {
+      const float* w = w_s + tap * 96 + c4 * 12;
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        acc[j] = fmaf(g[tap].x, w[3 * j], fmaf(g[tap].y, w[3 * j + 1], fmaf(g[tap].z, w[3 * j + 2], acc[j])));
+    }
     dx[i] = make_float4(xv.x > 0.f ? acc[0] : 0.f, xv.y > 0.f ? acc[1] : 0.f, xv.z > 0.f ? acc[2] : 0.f,
                         xv.w > 0.f ? acc[3] : 0.f);
   }
@@ -239,34 +248,46 @@ __global__ void __launch_bounds__(256) out_conv_wgrad_kernel(const float4* __res
   constexpr int T = KS * KS, NA = 3 * T, PS = NA * 32 + 4;  // accumulators per lane, partial stride
   __shared__ float red[8][PS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const long long total = (long long)B * Ho * Ho;
-  const long long nw = (long long)gridDim.x * 8, gw = (long long)blockIdx.x * 8 + warp;
-  const long long span = (total + nw - 1) / nw;
-  const long long p0 = gw * span, p1 = p0 + span < total ? p0 + span : total;
+  // 32-bit index arithmetic (checked by the launcher).  U output pixels per trip: their U x T input loads are all in flight
+  // before the first FMA (one pixel at a time left the warp waiting on L2 every iteration); each accumulator still
+  // receives its pixels in ascending order.
+  constexpr int U = 4;
+  const int total = B * Ho * Ho;
+  const int nw = gridDim.x * 8, gw = blockIdx.x * 8 + warp;
+  const int span = (total + nw - 1) / nw;
+  const int p0 = min(gw * span, total), p1 = min(p0 + span, total);
   float acc[NA];
 #pragma unroll
   for (int j = 0; j < NA; ++j) acc[j] = 0.f;
   float bsum = 0.f;
-  int ox = (int)(p0 % Ho), oy = (int)((p0 / Ho) % Ho), b = (int)(p0 / ((long long)Ho * Ho));
-  for (long long i = p0; i < p1; ++i) {
-    const float4 g = dpred[i];
-    float v[T];
+  int b = p0 / (Ho * Ho), oy = (p0 - b * Ho * Ho) / Ho, ox = p0 - b * Ho * Ho - oy * Ho;
+  for (int i = p0; i < p1; i += U) {
+    float4 g[U];
+    float v[U][T];
 #pragma unroll
-    for (int tap = 0; tap < T; ++tap) {  // the loads are independent: issued back to back
-      const int iy = oy + (tap / KS) - 1, ix = ox + (tap % KS) - 1;
-      const bool ok = iy >= 0 && iy < Hi && ix >= 0 && ix < Hi;
-      v[tap] = ok ? x[(((long long)b * Hi + iy) * Hi + ix) * 32 + lane] : 0.f;
-    }
-    if (lane < 3) bsum += lane == 0 ? g.x : (lane == 1 ? g.y : g.z);
+    for (int u = 0; u < U; ++u) {
+      const bool live = i + u < p1;
+      g[u] = live ? dpred[i + u] : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-    for (int tap = 0; tap < T; ++tap) {
-      acc[tap * 3 + 0] = fmaf(g.x, v[tap], acc[tap * 3 + 0]);
-      acc[tap * 3 + 1] = fmaf(g.y, v[tap], acc[tap * 3 + 1]);
-      acc[tap * 3 + 2] = fmaf(g.z, v[tap], acc[tap * 3 + 2]);
+      for (int tap = 0; tap < T; ++tap) {
+        const int iy = oy + (tap / KS) - 1, ix = ox + (tap % KS) - 1;
+        const bool ok = live && iy >= 0 && iy < Hi && ix >= 0 && ix < Hi;
+        v[u][tap] = ok ? x[((b * Hi + iy) * Hi + ix) * 32 + lane] : 0.f;
+      }
+      if (++ox == Ho) {
+        ox = 0;
+        if (++oy == Ho) { oy = 0; ++b; }
+      }
     }
-    if (++ox == Ho) {
-      ox = 0;
-      if (++oy == Ho) { oy = 0; ++b; }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      if (lane < 3) bsum += lane == 0 ? g[u].x : (lane == 1 ? g[u].y : g[u].z);
+#pragma unroll
+      for (int tap = 0; tap < T; ++tap) {
+        acc[tap * 3 + 0] = fmaf(g[u].x, v[u][tap], acc[tap * 3 + 0]);
+        acc[tap * 3 + 1] = fmaf(g[u].y, v[u][tap], acc[tap * 3 + 1]);
+        acc[tap * 3 + 2] = fmaf(g[u].z, v[u][tap], acc[tap * 3 + 2]);
+      }
     }
   }
 #pragma unroll
@@ -324,6 +345,7 @@ __global__ void pred_to_nchw_kernel(const float4* __restrict__ pred, int B, long
 ConvDecoder::ConvDecoder(int batch, Precision prec, cudaStream_t s, int out_kernel, bool with_target)
     : B_(batch), ks_(out_kernel), stream_(s) {
   RLREP_CHECK(B_ > 0 && (ks_ == 2 || ks_ == 3), "bad decoder batch / output kernel size");
+  RLREP_CHECK((long long)B_ * 84 * 84 * 32 < (1LL << 31), "decoder batch too large for the output layer's 32-bit indexing");
   // out_kernel 2: muLV-Rep (stride-2 layer 41 -> 83, Conv2d k2 p1 -> 84); out_kernel 3: the latent Diff-SR VAE
   // (stride-2 layer with output_padding 1: 41 -> 84, Conv2d k3 p1 -> 84)
   if (ks_ == 3) hw_[4] = 84;
@@ -338,7 +360,8 @@ ConvDecoder::ConvDecoder(int batch, Precision prec, cudaStream_t s, int out_kern
   g_.want(arena_);
   for (int i = 0; i < 5; ++i) {
     arena_.want(&act_[i], rows(i) * 32);
-    arena_.want(&dact_[i], rows(i) * 32);
+    // + slack rows (zero from the arena, never written): the implicit weight gradient reads up to 2 H + 5 rows past the map
+    arena_.want(&dact_[i], (rows(i) + 2 * hw_[i] + 8) * 32);
   }
   arena_.want(&col_, rows(3) * 288);  // the largest GEMM side: 41 x 41 pixels per image
   arena_.want(&pred_, rows(5) * 4);
@@ -349,6 +372,9 @@ ConvDecoder::ConvDecoder(int batch, Precision prec, cudaStream_t s, int out_kern
   arena_.want(&wfold_, (size_t)288 * kFold * 32 * kFold);
   implicit_fwd_ = !(std::getenv("RLREP_CONV_V1") && std::atoi(std::getenv("RLREP_CONV_V1")) != 0);
   if (implicit_fwd_) corr_.want(arena_, B_, hw_[2]);
+  // the stride-1 layers' backward pass without column matrices (TF32 path); RLREP_CONV_WGRAD_V1=1 keeps im2col + folded GEMM
+  implicit_bwd_ = implicit_fwd_ && prec == PREC_TF32 && B_ % 4 == 0 &&
+                  !(std::getenv("RLREP_CONV_WGRAD_V1") && std::atoi(std::getenv("RLREP_CONV_WGRAD_V1")) != 0);
   arena_.commit();
   gemm_.init(prec, 0);
 }
@@ -441,6 +467,13 @@ void ConvDecoder::backward(float* dx_dev, int ld_dx) {
     const int Hi = hw_[l], Ho = hw_[l + 1];
     const Linear w = layer(l);
     launch_colsum_tall(dact_[l + 1], 32, rows(l + 1), 32, bias_partial_, kBiasChunks, g_.g + b_off_[l], s);
+    if (implicit_bwd_ && l < 3) {
+      // stride 1: dWd[(tap, co), ci] = sum X[b, y, x, ci] dY[b, y + ky, x + kx, co] and dX = valid convolution of dY with
+      // Wd (x ReLU mask; the decoder input, l == 0, is a plain linear output) -- neither builds the [rows, 288] matrix
+      conv3x3_wgrad_implicit(gemm_, s, B_, Ho, act_[l], dact_[l + 1], w.dW, 32, /*transposed=*/true, corr_);
+      valid_conv_3x3_wt(gemm_, s, B_, Ho, dact_[l + 1], w.W, l > 0 ? act_[l] : nullptr, dact_[l], corr_);
+      continue;
+    }
     const float4* dy = reinterpret_cast<const float4*>(dact_[l + 1]);
     float4* col = reinterpret_cast<float4*>(col_);
     if (l < 3) im2col_strided_kernel<1><<<grid_for(rows(l) * 72, 256), 256, 0, s>>>(dy, B_, Hi, Ho, col);

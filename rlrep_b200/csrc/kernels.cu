@@ -168,6 +168,40 @@ __global__ void __launch_bounds__(256) colsum_tall_stage1_kernel(const float* __
     partial[(long long)blockIdx.y * cols + j] = t;
   }
 }
+// The conv-shaped case (32 dense columns: the bias gradients of the pixel agents' layers, ~430k rows): float4 loads, 32 rows
+// per trip and four trips in flight per thread -- the one-load-per-thread loop above leaves HBM waiting on latency (31 us for
+// 55 MB).  Fixed summation order per thread, then over the 32 row groups.
+__global__ void __launch_bounds__(256) colsum_tall32_stage1_kernel(const float4* __restrict__ X, long long rows,
+                                                                   int rows_per_cta, float* __restrict__ partial) {
+  __shared__ float4 part[32][9];
+  const int c4 = threadIdx.x & 7, rg = threadIdx.x >> 3;
+  const long long r0 = (long long)blockIdx.y * rows_per_cta;
+  const long long r1 = r0 + rows_per_cta < rows ? r0 + rows_per_cta : rows;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  long long i = r0 + rg;
+  for (; i + 96 < r1; i += 128) {
+    const float4 a = X[i * 8 + c4], b = X[(i + 32) * 8 + c4], c = X[(i + 64) * 8 + c4], d = X[(i + 96) * 8 + c4];
+    acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    acc.x += b.x; acc.y += b.y; acc.z += b.z; acc.w += b.w;
+    acc.x += c.x; acc.y += c.y; acc.z += c.z; acc.w += c.w;
+    acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
+  }
+  for (; i < r1; i += 32) {
+    const float4 a = X[i * 8 + c4];
+    acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+  }
+  part[rg][c4] = acc;
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int q = 0; q < 32; ++q) {
+      const float4 a = part[q][threadIdx.x];
+      t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+    }
+    reinterpret_cast<float4*>(partial + (long long)blockIdx.y * 32)[threadIdx.x] = t;
+  }
+}
 // 32 columns x 8 chunk-slices per CTA: eight independent partial sums per column, combined in a fixed order
 __global__ void __launch_bounds__(256) colsum_tall_stage2_kernel(const float* __restrict__ partial, int chunks, int cols,
                                                                  float* __restrict__ out) {
@@ -868,7 +902,10 @@ void launch_colreduce(const float* X, int ld, int rows, int cols, const float* u
 void launch_colsum_tall(const float* X, int ld, long long rows, int cols, float* partial, int chunks, float* out,
                         cudaStream_t s) {
   const int rows_per = (int)((rows + chunks - 1) / chunks);
-  colsum_tall_stage1_kernel<<<dim3(ceil_div(cols, 32), chunks), 256, 0, s>>>(X, ld, rows, cols, rows_per, partial);
+  if (cols == 32 && ld == 32 && (reinterpret_cast<uintptr_t>(X) & 15) == 0 && (reinterpret_cast<uintptr_t>(partial) & 15) == 0)
+    colsum_tall32_stage1_kernel<<<dim3(1, chunks), 256, 0, s>>>(reinterpret_cast<const float4*>(X), rows, rows_per, partial);
+  else
+    colsum_tall_stage1_kernel<<<dim3(ceil_div(cols, 32), chunks), 256, 0, s>>>(X, ld, rows, cols, rows_per, partial);
   RLREP_LAUNCHED_W("colsum_tall", s, 4.0 * (double)rows * cols, 0.0);
   colsum_tall_stage2_kernel<<<ceil_div(cols, 32), 256, 0, s>>>(partial, chunks, cols, out);
   RLREP_LAUNCHED("colsum_tall_final", s);
