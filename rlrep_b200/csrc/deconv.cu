@@ -98,17 +98,20 @@ __global__ void __launch_bounds__(256) out_conv_fwd_kernel(const float4* __restr
                                                            const float* __restrict__ bias, int B, int Hi, int Ho,
                                                            float4* __restrict__ pred) {
   constexpr int T = KS * KS;
-  __shared__ float w_s[T * 32 * 3];
+  // w_s[(tap * 32 + c) * 3 + o] = W[o, c, tap]: a thread's 12 weights of a tap are three aligned float4 (conflict-free
+  // LDS.128; as 12 scalar loads per 12 FMAs the kernel was LDS-bound, in registers it lost two thirds of its occupancy)
+  __shared__ __align__(16) float w_s[T * 32 * 3];
   for (int i = threadIdx.x; i < T * 96; i += 256) {
     const int o = i % 3, c = (i / 3) % 32, tap = i / 96;
     w_s[i] = W[(o * 32 + c) * T + tap];
   }
   __syncthreads();
+  const int c4 = threadIdx.x & 7;
   const float b0 = bias[0], b1 = bias[1], b2 = bias[2];
   // 32-bit index arithmetic throughout (the launcher checks that every index fits): 64-bit div / mod by run-time values cost
   // more instructions than the taps' FMAs.  All taps' loads are issued before the first FMA.
   const int total = B * Ho * Ho;  // pixels; the grid-stride loop keeps whole warps together
-  const int c4 = threadIdx.x & 7, HoHo = Ho * Ho;
+  const int HoHo = Ho * Ho;
   for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < ((total + 3) & ~3); i += (gridDim.x * blockDim.x) >> 3) {
     float a0 = 0.f, a1 = 0.f, a2 = 0.f;
     if (i < total) {
@@ -122,7 +125,9 @@ __global__ void __launch_bounds__(256) out_conv_fwd_kernel(const float4* __restr
       }
 #pragma unroll
       for (int tap = 0; tap < T; ++tap) {
-        const float* wc = w_s + tap * 96 + c4 * 12;
+        const float4* wq = reinterpret_cast<const float4*>(w_s + tap * 96 + c4 * 12);
+        const float4 q0 = wq[0], q1 = wq[1], q2 = wq[2];
+        const float wc[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
         a0 = fmaf(v[tap].x, wc[0], a0); a1 = fmaf(v[tap].x, wc[1], a1); a2 = fmaf(v[tap].x, wc[2], a2);
         a0 = fmaf(v[tap].y, wc[3], a0); a1 = fmaf(v[tap].y, wc[4], a1); a2 = fmaf(v[tap].y, wc[5], a2);
         a0 = fmaf(v[tap].z, wc[6], a0); a1 = fmaf(v[tap].z, wc[7], a1); a2 = fmaf(v[tap].z, wc[8], a2);
@@ -240,53 +245,68 @@ __global__ void __launch_bounds__(256) out_conv_dgrad_kernel(const float4* __res
 }
 
 // Pass 1 of dW[o, c, tap] = sum_pixels dpred[pix, o] * X[pix + tap - 1, c] and db[o] = sum dpred[pix, o]:
-// lane = input channel; each warp walks a CONTIGUOUS span of output pixels (the rows it touches stay in L1 from one
-// output row to the next); partial[block] = [12 * 32 weight sums | 3 bias sums | pad] (388 floats).
+// lane = input channel; each warp walks whole output ROWS with a sliding KS x KS window of the input in registers, so a
+// pixel costs KS new loads (the window's next column) instead of KS * KS, and the next four columns are in flight while
+// the current four pixels are accumulated; partial[block] = [3 T * 32 weight sums | 3 bias sums | pad].
 template <int KS>
-__global__ void __launch_bounds__(256) out_conv_wgrad_kernel(const float4* __restrict__ dpred, const float* __restrict__ x,
+__global__ void __launch_bounds__(256, 3) out_conv_wgrad_kernel(const float4* __restrict__ dpred, const float* __restrict__ x,
                                                              int B, int Hi, int Ho, float* __restrict__ partial) {
   constexpr int T = KS * KS, NA = 3 * T, PS = NA * 32 + 4;  // accumulators per lane, partial stride
+  constexpr int U = 4;
   __shared__ float red[8][PS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  // 32-bit index arithmetic (checked by the launcher).  U output pixels per trip: their U x T input loads are all in flight
-  // before the first FMA (one pixel at a time left the warp waiting on L2 every iteration); each accumulator still
-  // receives its pixels in ascending order.
-  constexpr int U = 4;
-  const int total = B * Ho * Ho;
+  const int n_rows = B * Ho;  // (b, oy) pairs; 32-bit index arithmetic (checked by the launcher)
   const int nw = gridDim.x * 8, gw = blockIdx.x * 8 + warp;
-  const int span = (total + nw - 1) / nw;
-  const int p0 = min(gw * span, total), p1 = min(p0 + span, total);
+  const int per = (n_rows + nw - 1) / nw;
+  const int r0 = min(gw * per, n_rows), r1 = min(r0 + per, n_rows);
   float acc[NA];
 #pragma unroll
   for (int j = 0; j < NA; ++j) acc[j] = 0.f;
   float bsum = 0.f;
-  int b = p0 / (Ho * Ho), oy = (p0 - b * Ho * Ho) / Ho, ox = p0 - b * Ho * Ho - oy * Ho;
-  for (int i = p0; i < p1; i += U) {
-    float4 g[U];
-    float v[U][T];
+  for (int r = r0; r < r1; ++r) {
+    const int b = r / Ho, oy = r - b * Ho;
+    const float* xrow[KS];  // input row of tap row ky (nullptr outside the image)
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      const bool live = i + u < p1;
-      g[u] = live ? dpred[i + u] : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-      for (int tap = 0; tap < T; ++tap) {
-        const int iy = oy + (tap / KS) - 1, ix = ox + (tap % KS) - 1;
-        const bool ok = live && iy >= 0 && iy < Hi && ix >= 0 && ix < Hi;
-        v[u][tap] = ok ? x[((b * Hi + iy) * Hi + ix) * 32 + lane] : 0.f;
-      }
-      if (++ox == Ho) {
-        ox = 0;
-        if (++oy == Ho) { oy = 0; ++b; }
-      }
+    for (int ky = 0; ky < KS; ++ky) {
+      const int iy = oy + ky - 1;
+      xrow[ky] = (iy >= 0 && iy < Hi) ? x + (size_t)((b * Hi + iy) * Hi) * 32 + lane : nullptr;
     }
+    auto ld = [&](int ky, int ix) { return (xrow[ky] != nullptr && ix >= 0 && ix < Hi) ? xrow[ky][ix * 32] : 0.f; };
+    float win[KS][KS];  // win[ky][kx] = X[iy, ox + kx - 1] for the current output pixel
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      if (lane < 3) bsum += lane == 0 ? g[u].x : (lane == 1 ? g[u].y : g[u].z);
+    for (int ky = 0; ky < KS; ++ky) {
+      win[ky][0] = 0.f;
 #pragma unroll
-      for (int tap = 0; tap < T; ++tap) {
-        acc[tap * 3 + 0] = fmaf(g[u].x, v[u][tap], acc[tap * 3 + 0]);
-        acc[tap * 3 + 1] = fmaf(g[u].y, v[u][tap], acc[tap * 3 + 1]);
-        acc[tap * 3 + 2] = fmaf(g[u].z, v[u][tap], acc[tap * 3 + 2]);
+      for (int kx = 1; kx < KS; ++kx) win[ky][kx] = ld(ky, kx - 1);
+    }
+    const float4* grow = dpred + (size_t)r * Ho;
+    for (int ox = 0; ox < Ho; ox += U) {
+      float4 g[U];
+      float nxt[U][KS];  // the window's next column for pixel ox + u + 1: ix = ox + u + KS - 1
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        g[u] = ox + u < Ho ? grow[ox + u] : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky) nxt[u][ky] = ld(ky, ox + u + KS - 1);
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        if (lane < 3) bsum += lane == 0 ? g[u].x : (lane == 1 ? g[u].y : g[u].z);
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+          for (int kx = 0; kx < KS; ++kx) {
+            const int tap = ky * KS + kx;
+            acc[tap * 3 + 0] = fmaf(g[u].x, win[ky][kx], acc[tap * 3 + 0]);
+            acc[tap * 3 + 1] = fmaf(g[u].y, win[ky][kx], acc[tap * 3 + 1]);
+            acc[tap * 3 + 2] = fmaf(g[u].z, win[ky][kx], acc[tap * 3 + 2]);
+          }
+#pragma unroll
+        for (int ky = 0; ky < KS; ++ky) {
+#pragma unroll
+          for (int kx = 0; kx + 1 < KS; ++kx) win[ky][kx] = win[ky][kx + 1];
+          win[ky][KS - 1] = nxt[u][ky];
+        }
       }
     }
   }
@@ -444,13 +464,13 @@ void ConvDecoder::backward(float* dx_dev, int ld_dx) {
   cudaStream_t s = stream_;
   // ---- output layer
   if (ks_ == 2)
-    out_conv_wgrad_kernel<2><<<kWgBlocks, 256, 0, s>>>(reinterpret_cast<const float4*>(dpred_), act_[4], B_, hw_[4], hw_[5],
+    out_conv_wgrad_kernel<2><<<kWgBlocks2, 256, 0, s>>>(reinterpret_cast<const float4*>(dpred_), act_[4], B_, hw_[4], hw_[5],
                                                       wg_partial_);
   else
     out_conv_wgrad_kernel<3><<<kWgBlocks, 256, 0, s>>>(reinterpret_cast<const float4*>(dpred_), act_[4], B_, hw_[4], hw_[5],
                                                       wg_partial_);
   RLREP_LAUNCHED_W("out_conv_wgrad", s, 4.0 * (rows(4) * 32 + rows(5) * 4), 2.0 * rows(5) * 384);
-  if (ks_ == 2) out_conv_wgrad_finish_kernel<2><<<2, 256, 0, s>>>(wg_partial_, kWgBlocks, g_.g + w_off_[4], g_.g + b_off_[4]);
+  if (ks_ == 2) out_conv_wgrad_finish_kernel<2><<<2, 256, 0, s>>>(wg_partial_, kWgBlocks2, g_.g + w_off_[4], g_.g + b_off_[4]);
   else out_conv_wgrad_finish_kernel<3><<<4, 256, 0, s>>>(wg_partial_, kWgBlocks, g_.g + w_off_[4], g_.g + b_off_[4]);
   RLREP_LAUNCHED("out_conv_wgrad_finish", s);
   if (ks_ == 2)

@@ -44,7 +44,9 @@ class ConvDecoder {
   float *col_ = nullptr, *pred_ = nullptr, *dpred_ = nullptr, *loss_partial_ = nullptr, *wg_partial_ = nullptr;
   float* bias_partial_ = nullptr;
   static constexpr int kBiasChunks = 296;
-  static constexpr int kWgBlocks = 592;
+  // CTAs of the output layer's weight-gradient pass: 6 per SM for the 3x3 kernel (two waves of the 3 CTAs an SM holds,
+  // measured 1253 -> 762 us at 1024 frames), 4 per SM for the 2x2 kernel (fewer rows per warp there: 134 vs 184 us)
+  static constexpr int kWgBlocks = 888, kWgBlocks2 = 592;
   static constexpr int kFold = 4;  // rows folded per GEMM row in the weight-gradient GEMMs (deconv.cu backward())
   float* wfold_ = nullptr;
   bool implicit_fwd_ = true;

@@ -1,0 +1,15 @@
+mkdir -p gpurun_out/r02
+timeout 1500 python -m pytest tests/test_gpu_mulv.py tests/test_gpu_ldiffsr.py -m gpu -q -x > gpurun_out/r02/pytest_pix3.log 2>&1; tail -5 gpurun_out/r02/pytest_pix3.log
+for w in mulvdrq_pixels_b256 ldiffsr_pixels_b256; do
+  timeout 600 python bench.py --workload $w --steps 10 --warmup 3 --repeats 3 --no-cpu-baseline --no-alt-precision > gpurun_out/r02/bench_${w}_v4.json 2> gpurun_out/r02/bench_${w}_v4.err
+done
+python - <<'PY'
+import json
+for f in ('bench_mulvdrq_pixels_b256_v4','bench_ldiffsr_pixels_b256_v4'):
+    try:
+        d=json.loads(open(f'gpurun_out/r02/{f}.json').read().strip().splitlines()[-1])
+        print(f, round(d['value'],1), round(d['ms_per_step'],4), round(d['e2e']['value'],1), d.get('gpu_launches_per_step'))
+        print('   ', d['top_kernels_us_per_step'])
+    except Exception as e:
+        print(f, 'ERR', e)
+PY
