@@ -100,6 +100,7 @@ struct TcGemmPlan {
   int stages = 0;       // TMA ring depth (shallow for short K-slices so two CTAs share an SM)
   bool push = false;    // split-K partials pushed into the owner CTA's shared memory (see gemm_tc_kernel.cuh)
   bool persistent = false;  // one CTA per SM walks the tiles with a double-buffered TMEM accumulator (no split-K)
+  int halo_rows = 0;        // > 0: implicit convolution with the tile's halo in shared memory (gemm_conv_halo_kernel)
   float* ws = nullptr;  // unused (split-K reduces over DSMEM); kept for ABI stability of rlrep_gemm
 };
 

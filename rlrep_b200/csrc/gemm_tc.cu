@@ -237,8 +237,17 @@ TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* /*ws*/, s
   }
   // K-major operand: matrix [rows = M|N, cols = K]; MN-major: matrix [rows = K, cols = M|N].
   // implicit convolution: A is the [M, 32] pixel matrix itself (rows past M zero-fill), not an [M, 288] column matrix
+  {
+    // implicit convolution, many tiles, 32 output channels: the halo kernel (one A load per tile instead of nine)
+    static const int halo_on = [] {
+      const char* e = std::getenv("RLREP_CONV_HALO");
+      return e ? std::atoi(e) : 1;
+    }();
+    const int rows = (128 + 2 * a.conv_w + 2 + 7) & ~7;
+    if (halo_on && a.conv_w > 0 && p.persistent && p.bn == 32 && a.N <= 32 && rows <= 256) p.halo_rows = rows;
+  }
   p.tmA = a.a_mn ? make_map_mnmajor(a.A, a.K, a.M, a.lda, BM)
-                 : make_map_kmajor(a.A, a.M, a.conv_w > 0 ? 32 : a.K, a.lda, BM);
+                 : make_map_kmajor(a.A, a.M, a.conv_w > 0 ? 32 : a.K, a.lda, p.halo_rows > 0 ? p.halo_rows : BM);
   if (a.conv_wgrad_hi > 0) {
     RLREP_CHECK(p.bn <= 64 && !p.persistent, "implicit weight gradient: tile width 32 or 64, one tile per CTA");
     p.tmB = make_map_conv_wgrad(a.B, 4LL * a.K, a.conv_wgrad_hi, p.bn);

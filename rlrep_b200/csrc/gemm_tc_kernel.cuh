@@ -685,6 +685,183 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
   if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
+// ------------------------------------------------------------------------------------------------ implicit 3x3 conv, halo in smem
+// The persistent kernel above runs an implicit convolution (GemmArgs::conv_w) as nine k-blocks whose A tile is the same 128
+// grid rows shifted by the tap: nine TMA loads of 16 KB per tile, i.e. the input map crosses L2 -> SM nine times (measured:
+// 65 us for a 55 MB map, the ~12 TB/s L2 ceiling).  Here a tile's A operand is loaded ONCE, with its halo -- grid rows
+// [m0, m0 + 128 + 2 conv_w + 2) as one 128B-swizzled box -- and the nine taps are nine sets of MMAs whose A descriptors
+// start `shift` rows into that buffer.  Measured on B200: the 128-byte swizzle is a function of the ABSOLUTE shared-memory
+// address (bits 4-6 XOR bits 7-9), so a start address that is not 1024-byte aligned needs nothing else -- the descriptor's
+// base-offset field stays 0 (setting it to shift % 8 gives wrong products; RLREP_HALO_FLAGS=1 keeps that variant for the
+// record).  The 36 KB of weights are loaded once per CTA and stay resident.
+// N <= 32 (every convolution of the pixel agents has 32 output channels), A K-major.
+constexpr int kHaloStages = 4;
+constexpr int kHaloMaxRows = 256;                  // TMA box limit; 128 + 2 conv_w + 2 <= 256  ->  conv_w <= 63
+constexpr int kHaloBytes = kHaloMaxRows * 128;     // per stage
+constexpr int kHaloSmem = kHaloStages * kHaloBytes + 9 * 32 * BK * 4 + 1024 + 256 + 4 * 32 * 36 * 4;
+static_assert(kHaloSmem <= kMaxSmem, "halo kernel shared memory");
+
+__device__ __forceinline__ uint64_t smem_desc_sw128_rows(uint32_t addr, uint32_t base_offset) {
+  return ptx::make_smem_desc(addr, 16, 1024, 2) | (static_cast<uint64_t>(base_offset & 7u) << 49);
+}
+
+template <bool B_MN>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+gemm_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      float* __restrict__ C, int ldc, int M, int N, int conv_w, int halo_rows, int flags, const Epilogue epi) {
+  constexpr int BN = 32;
+  constexpr int B_BYTES = BN * BK * 4;
+  constexpr uint32_t TMEM_COLS = 2 * BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                                  // [kHaloStages][kHaloBytes]
+  uint8_t* sB = smem + kHaloStages * kHaloBytes;       // [9][B_BYTES], resident
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(sB + 9 * B_BYTES);
+  uint64_t* empty_bar = full_bar + 8;
+  uint64_t* acc_full = empty_bar + 8;
+  uint64_t* acc_empty = acc_full + 2;
+  uint64_t* w_bar = acc_empty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(w_bar + 1);
+  float* tbuf = reinterpret_cast<float*>(sB + 9 * B_BYTES + 256);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total = (M + BM - 1) / BM;  // one n-tile
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kHaloStages; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&acc_full[a], 1);
+      ptx::mbar_init(&acc_empty[a], 4);
+    }
+    ptx::mbar_init(w_bar, 1);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  ptx::tc_fence_after_sync();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // the weights, once: nine k-blocks of [32, 32]
+      ptx::mbar_arrive_expect_tx(w_bar, 9 * B_BYTES);
+      for (int kb = 0; kb < 9; ++kb) {
+        if (!B_MN) ptx::tma_load_2d(sB + kb * B_BYTES, &tmB, w_bar, kb * BK, 0);
+        else ptx::tma_load_3d(sB + kb * B_BYTES, &tmB, w_bar, 0, kb * BK, 0);
+      }
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int s = it % kHaloStages;
+        ptx::mbar_wait(&empty_bar[s], ((it / kHaloStages) & 1) ^ 1);
+        ptx::mbar_arrive_expect_tx(&full_bar[s], halo_rows * 128);
+        ptx::tma_load_2d(sA + s * kHaloBytes, &tmA, &full_bar[s], 0, t * BM);  // rows past M read as zero
+      }
+    }
+  } else if (warp == 1) {
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_tf32(BM, BN, false, B_MN);
+      ptx::mbar_wait(w_bar, 0);
+      int it = 0;
+      for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
+        const int acc = it & 1, s = it % kHaloStages;
+        ptx::mbar_wait(&acc_empty[acc], ((it >> 1) & 1) ^ 1);
+        ptx::mbar_wait(&full_bar[s], (it / kHaloStages) & 1);
+        ptx::tc_fence_after_sync();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        const uint32_t a_base = ptx::smem_u32(sA + s * kHaloBytes), b_base = ptx::smem_u32(sB);
+#pragma unroll 1
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t shift = (tap / 3) * conv_w + (tap % 3);
+          const uint32_t a_addr = a_base + shift * 128, b_addr = b_base + tap * B_BYTES;
+          const uint32_t bo = (flags & 1) ? (shift & 7u) : 0u;
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k) {
+            const uint64_t adesc = smem_desc_sw128_rows(a_addr + k * UMMA_K * 4, bo);
+            const uint64_t bdesc = B_MN ? ptx::make_smem_desc(b_addr + k * 1024, 4096, 512, 1)
+                                        : ptx::make_smem_desc(b_addr + k * UMMA_K * 4, 16, 1024, 2);
+            ptx::mma_tf32_ss(d_tmem, adesc, bdesc, idesc, (tap > 0 || k > 0) ? 1u : 0u);
+          }
+        }
+        ptx::mma_commit(&empty_bar[s]);
+        ptx::mma_commit(&acc_full[acc]);
+      }
+    }
+  } else {
+    // epilogue warps 2..5: one output row per thread (same as the persistent kernel)
+    const int q = warp & 3;
+    const bool vec_ok = (ldc & 3) == 0 && aligned16(C);
+    float* tw = tbuf + q * (32 * 36);
+    int tc = 0;
+    for (int t = blockIdx.x; t < total; t += gridDim.x, ++tc) {
+      const int acc = tc & 1;
+      const int m0 = t * BM;
+      ptx::mbar_wait(&acc_full[acc], (tc >> 1) & 1);
+      ptx::tc_fence_after_sync();
+      const int gm = m0 + 32 * q + lane;
+      uint32_t v[32];
+      ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + acc * BN, v);
+      ptx::tmem_ld_wait();
+      if (vec_ok && N == 32) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          *reinterpret_cast<float4*>(tw + lane * 36 + 4 * j) =
+              make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
+                          __uint_as_float(v[4 * j + 3]));
+        __syncwarp();
+#define RLREP_HSTORE(A, D) persist_store_rows<A, D>(epi, tw, C, ldc, M, m0 + 32 * q, 0, lane)
+        RLREP_EPILOGUE_SWITCH(epi, RLREP_HSTORE);
+#undef RLREP_HSTORE
+        __syncwarp();
+      } else if (gm < M) {
+        float* crow = C + (size_t)gm * ldc;
+        for (int e = 0; e < 32 && e < N; ++e) crow[e] = epilogue_apply<-1, -1>(epi, __uint_as_float(v[e]), gm, e, crow + e);
+      }
+      ptx::tc_fence_before_sync();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&acc_empty[acc]);
+    }
+  }
+  ptx::tc_fence_before_sync();
+  __syncthreads();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+template <bool B_MN>
+void launch_conv_halo(const TcGemmPlan& p, cudaStream_t stream) {
+  auto kern = gemm_conv_halo_kernel<B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    RLREP_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, kHaloSmem));
+    attr_set = true;
+  }
+  static const int flags = [] {
+    const char* e = std::getenv("RLREP_HALO_FLAGS");
+    return e ? std::atoi(e) : 0;
+  }();
+  const GemmArgs& a = p.args;
+  const int tiles = ceil_div(a.M, BM);
+  kern<<<std::min(tiles, kNumSMs), kPersistThreads, kHaloSmem, stream>>>(p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, a.conv_w,
+                                                                       p.halo_rows, flags, a.epi);
+  RLREP_LAUNCHED_W("gemm_conv_halo", stream, 4.0 * ((double)a.M * 32 + (double)a.N * a.K + (double)a.M * a.N),
+                   2.0 * a.M * a.N * a.K);
+}
+template <int BN, int AMN>
+void launch_conv_halo_if(const TcGemmPlan& p, cudaStream_t stream) {
+  if constexpr (BN == 32 && AMN == 0) {
+    if (p.args.b_mn) launch_conv_halo<true>(p, stream);
+    else launch_conv_halo<false>(p, stream);
+  } else {
+    throw Error("the halo convolution kernel exists for BN = 32, K-major A only");
+  }
+}
+
 template <int BN, bool A_MN, bool B_MN>
 void launch_variant_persistent(const TcGemmPlan& p, cudaStream_t stream) {
   auto kern = gemm_tf32_persistent_kernel<BN, A_MN, B_MN>;
@@ -776,6 +953,10 @@ int max_clusters_variant(int split_k, int stages, bool push) {
 
 #define RLREP_TC_DEFINE(BN, AMN)                                              \
   void launch_tc_##BN##_##AMN(const TcGemmPlan& p, cudaStream_t stream) {     \
+    if (p.halo_rows > 0) {                                                    \
+      launch_conv_halo_if<BN, AMN>(p, stream);                                \
+      return;                                                                 \
+    }                                                                         \
     if (p.persistent) {                                                       \
       if (p.args.b_mn) launch_variant_persistent<BN, (AMN) != 0, true>(p, stream);   \
       else launch_variant_persistent<BN, (AMN) != 0, false>(p, stream);       \
