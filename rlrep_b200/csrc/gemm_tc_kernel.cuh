@@ -695,10 +695,32 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 // base-offset field stays 0 (setting it to shift % 8 gives wrong products; RLREP_HALO_FLAGS=1 keeps that variant for the
 // record).  The 36 KB of weights are loaded once per CTA and stay resident.
 // N <= 32 (every convolution of the pixel agents has 32 output channels), A K-major.
+// Rows of a 32 x 16 accumulator chunk staged in tw[32][20]: lane = (row group of 8, 16-byte piece), four passes
+template <int ACT, int DACT>
+__device__ __forceinline__ void halo_store_rows16(const Epilogue& epi, const float* tw, float* __restrict__ C, int ldc,
+                                                  int M, int m_base, int gn0, int lane) {
+  const int piece = lane & 3, rsub = lane >> 2;
+#pragma unroll
+  for (int r4 = 0; r4 < 4; ++r4) {
+    const int r = r4 * 8 + rsub;
+    const int om = m_base + r, on = gn0 + 4 * piece;
+    if (om < M) {
+      const float4 a4 = *reinterpret_cast<const float4*>(tw + r * 20 + 4 * piece);
+      float* cp = C + (size_t)om * ldc + on;
+      const float in[4] = {a4.x, a4.y, a4.z, a4.w};
+      float o[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = epilogue_apply<ACT, DACT>(epi, in[e], om, on + e, cp + e);
+      *reinterpret_cast<float4*>(cp) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+}
+
+constexpr int kHaloThreads = 320;  // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue: two per TMEM lane quarter, 16 columns each
 constexpr int kHaloStages = 4;
 constexpr int kHaloMaxRows = 256;                  // TMA box limit; 128 + 2 conv_w + 2 <= 256  ->  conv_w <= 63
 constexpr int kHaloBytes = kHaloMaxRows * 128;     // per stage
-constexpr int kHaloSmem = kHaloStages * kHaloBytes + 9 * 32 * BK * 4 + 1024 + 256 + 4 * 32 * 36 * 4;
+constexpr int kHaloSmem = kHaloStages * kHaloBytes + 9 * 32 * BK * 4 + 1024 + 256 + 8 * 32 * 20 * 4;
 static_assert(kHaloSmem <= kMaxSmem, "halo kernel shared memory");
 
 __device__ __forceinline__ uint64_t smem_desc_sw128_rows(uint32_t addr, uint32_t base_offset) {
@@ -706,7 +728,7 @@ __device__ __forceinline__ uint64_t smem_desc_sw128_rows(uint32_t addr, uint32_t
 }
 
 template <bool B_MN>
-__global__ void __launch_bounds__(kPersistThreads, 1)
+__global__ void __launch_bounds__(kHaloThreads, 1)
 gemm_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                       float* __restrict__ C, int ldc, int M, int N, int conv_w, int halo_rows, int flags, const Epilogue epi) {
   constexpr int BN = 32;
@@ -734,7 +756,7 @@ gemm_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     }
     for (int a = 0; a < 2; ++a) {
       ptx::mbar_init(&acc_full[a], 1);
-      ptx::mbar_init(&acc_empty[a], 4);
+      ptx::mbar_init(&acc_empty[a], 8);
     }
     ptx::mbar_init(w_bar, 1);
     ptx::fence_mbar_init();
@@ -794,34 +816,36 @@ gemm_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
     }
   } else {
-    // epilogue warps 2..5: one output row per thread (same as the persistent kernel)
-    const int q = warp & 3;
+    // epilogue warps 2..9: TMEM lane quarter warp % 4, columns [16 half, 16 half + 16) -- with one warp per quarter the
+    // epilogue (1.3 us per tile) was the longest stage of the pipeline
+    const int q = warp & 3, half = (warp - 2) >> 2;
     const bool vec_ok = (ldc & 3) == 0 && aligned16(C);
-    float* tw = tbuf + q * (32 * 36);
+    float* tw = tbuf + (warp - 2) * (32 * 20);
     int tc = 0;
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++tc) {
       const int acc = tc & 1;
       const int m0 = t * BM;
       ptx::mbar_wait(&acc_full[acc], (tc >> 1) & 1);
       ptx::tc_fence_after_sync();
-      const int gm = m0 + 32 * q + lane;
-      uint32_t v[32];
-      ptx::tmem_ld_32x32b_x32(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + acc * BN, v);
+      const int gm = m0 + 32 * q + lane, gn0 = 16 * half;
+      uint32_t v[16];
+      ptx::tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + acc * BN + gn0, v);
       ptx::tmem_ld_wait();
       if (vec_ok && N == 32) {
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          *reinterpret_cast<float4*>(tw + lane * 36 + 4 * j) =
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(tw + lane * 20 + 4 * j) =
               make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                           __uint_as_float(v[4 * j + 3]));
         __syncwarp();
-#define RLREP_HSTORE(A, D) persist_store_rows<A, D>(epi, tw, C, ldc, M, m0 + 32 * q, 0, lane)
+#define RLREP_HSTORE(A, D) halo_store_rows16<A, D>(epi, tw, C, ldc, M, m0 + 32 * q, gn0, lane)
         RLREP_EPILOGUE_SWITCH(epi, RLREP_HSTORE);
 #undef RLREP_HSTORE
         __syncwarp();
       } else if (gm < M) {
         float* crow = C + (size_t)gm * ldc;
-        for (int e = 0; e < 32 && e < N; ++e) crow[e] = epilogue_apply<-1, -1>(epi, __uint_as_float(v[e]), gm, e, crow + e);
+        for (int e = 0; e < 16 && gn0 + e < N; ++e)
+          crow[gn0 + e] = epilogue_apply<-1, -1>(epi, __uint_as_float(v[e]), gm, gn0 + e, crow + gn0 + e);
       }
       ptx::tc_fence_before_sync();
       __syncwarp();
@@ -847,7 +871,7 @@ void launch_conv_halo(const TcGemmPlan& p, cudaStream_t stream) {
   }();
   const GemmArgs& a = p.args;
   const int tiles = ceil_div(a.M, BM);
-  kern<<<std::min(tiles, kNumSMs), kPersistThreads, kHaloSmem, stream>>>(p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, a.conv_w,
+  kern<<<std::min(tiles, kNumSMs), kHaloThreads, kHaloSmem, stream>>>(p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, a.conv_w,
                                                                        p.halo_rows, flags, a.epi);
   RLREP_LAUNCHED_W("gemm_conv_halo", stream, 4.0 * ((double)a.M * 32 + (double)a.N * a.K + (double)a.M * a.N),
                    2.0 * a.M * a.N * a.K);
