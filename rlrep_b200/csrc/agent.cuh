@@ -221,6 +221,10 @@ class GemmRunner {
   ~GemmRunner();
   // Chooses the tcgen05 path when the operands allow it and the shape is worth a 128-row tile, else CUDA cores.
   void run(const GemmArgs& a, cudaStream_t s);
+  // Implicit convolution (a.conv_w > 0) whose valid rows go straight to their compact positions (GemmArgs::compact_*):
+  // true when the GEMM ran that way (the halo kernel), false when this GEMM does not qualify -- nothing was launched and
+  // the caller runs it on the grid and compacts afterwards.
+  bool run_compact(GemmArgs a, int wp, int ho, cudaStream_t s);
   // Share of the GPU the next GEMMs should plan for: 0.5 inside fork()/join() sections where two independent kernel
   // chains run on two streams, 1.0 elsewhere.  Part of the plan-cache key.
   void set_sm_share(double share) { sm_share_ = share; }

@@ -111,7 +111,14 @@ void valid_conv_3x3_wt(GemmRunner& g, cudaStream_t s, int B, int Hi, const float
   a.M = B * Hi * Hi; a.N = 32; a.K = 288;
   a.A = in; a.lda = 32; a.conv_w = Hi;
   a.B = W; a.ldb = 32; a.b_mn = true;
-  a.C = sc.out_grid; a.ldc = 32;
+  a.ldc = 32;
+  {  // the halo kernel stores the valid rows at their compact positions (x mask) itself
+    GemmArgs c = a;
+    c.C = out;
+    if (mask != nullptr) { c.epi.dact = DACT_RELU_OUT; c.epi.aux = mask; c.epi.ld_aux = 32; }
+    if (g.run_compact(c, Hi, Ho, s)) return;
+  }
+  a.C = sc.out_grid;
   g.run(a, s);
   compact_grid_kernel<<<grid_for((long long)B * Ho * Ho * 8, 256), 256, 0, s>>>(
       reinterpret_cast<const float4*>(sc.out_grid), B, Hi, Ho, reinterpret_cast<const float4*>(mask),
@@ -132,9 +139,16 @@ void full_correlation_3x3(GemmRunner& g, cudaStream_t s, int B, int Hi, const fl
   a.M = (int)rows; a.N = 32; a.K = 288;
   a.A = sc.padded; a.lda = 32; a.conv_w = Wp;
   a.B = sc.w_flip; a.ldb = 288;
-  a.C = sc.out_grid; a.ldc = 32;
+  a.ldc = 32;
   a.epi.bias = bias;
   a.epi.act = act;
+  {
+    GemmArgs c = a;
+    c.C = out;
+    if (mask != nullptr) { c.epi.dact = DACT_RELU_OUT; c.epi.aux = mask; c.epi.ld_aux = 32; }
+    if (g.run_compact(c, Wp, Ho, s)) return;
+  }
+  a.C = sc.out_grid;
   g.run(a, s);
   compact_grid_kernel<<<grid_for((long long)B * Ho * Ho * 8, 256), 256, 0, s>>>(
       reinterpret_cast<const float4*>(sc.out_grid), B, Wp, Ho, reinterpret_cast<const float4*>(mask),
@@ -149,9 +163,15 @@ void valid_conv_3x3(GemmRunner& g, cudaStream_t s, int B, int Hi, const float* i
   a.M = B * Hi * Hi; a.N = 32; a.K = 288;
   a.A = in; a.lda = 32; a.conv_w = Hi;
   a.B = W; a.ldb = ldw;
-  a.C = sc.out_grid; a.ldc = 32;
+  a.ldc = 32;
   a.epi.bias = bias;
   a.epi.act = act;
+  {
+    GemmArgs c = a;
+    c.C = out;
+    if (g.run_compact(c, Hi, Ho, s)) return;
+  }
+  a.C = sc.out_grid;
   g.run(a, s);
   compact_grid_kernel<<<grid_for((long long)B * Ho * Ho * 8, 256), 256, 0, s>>>(
       reinterpret_cast<const float4*>(sc.out_grid), B, Hi, Ho, nullptr, reinterpret_cast<float4*>(out));

@@ -81,6 +81,10 @@ struct GemmArgs {
   // No column matrix exists; K = rows / 4, and 2 Hi + 5 rows of finite values must be readable behind the map (they meet
   // zeros of A).
   int conv_wgrad_hi = 0;
+  // Compacting store of an implicit convolution (halo kernel only, GemmRunner::run_compact): the GEMM's rows live on a grid
+  // compact_wp wide; only rows with x < compact_ho and y < compact_ho are stored, at row (b * ho + y) * ho + x of C -- and
+  // of epi.aux / epi.pre_out, which are indexed by the compact row too.
+  int compact_wp = 0, compact_ho = 0;
   const float* B = nullptr;
   int ldb = 0;
   bool b_mn = false;

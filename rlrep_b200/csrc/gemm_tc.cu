@@ -244,8 +244,13 @@ TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* /*ws*/, s
       return e ? std::atoi(e) : 1;
     }();
     const int rows = (128 + 2 * a.conv_w + 2 + 7) & ~7;
-    if (halo_on && a.conv_w > 0 && p.persistent && p.bn == 32 && a.N <= 32 && rows <= 256) p.halo_rows = rows;
+    // its epilogue is bias + activation + derivative mask (16-byte aligned, dense 32-column operands)
+    const bool plain = a.epi.r1_u == nullptr && a.epi.pre_out == nullptr && !a.epi.accumulate &&
+                       (a.epi.bias == nullptr || (reinterpret_cast<uintptr_t>(a.epi.bias) & 15) == 0) &&
+                       (a.epi.dact == DACT_NONE || ((reinterpret_cast<uintptr_t>(a.epi.aux) & 15) == 0 && (a.epi.ld_aux & 3) == 0));
+    if (halo_on && plain && a.conv_w > 0 && p.persistent && p.bn == 32 && a.N <= 32 && rows <= 256) p.halo_rows = rows;
   }
+  // (a compacting GEMM whose plan has no halo is refused by GemmRunner::run_compact before anything is launched)
   p.tmA = a.a_mn ? make_map_mnmajor(a.A, a.K, a.M, a.lda, BM)
                  : make_map_kmajor(a.A, a.M, a.conv_w > 0 ? 32 : a.K, a.lda, p.halo_rows > 0 ? p.halo_rows : BM);
   if (a.conv_wgrad_hi > 0) {

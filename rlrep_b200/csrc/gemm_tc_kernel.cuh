@@ -696,23 +696,64 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 // record).  The 36 KB of weights are loaded once per CTA and stay resident.
 // N <= 32 (every convolution of the pixel agents has 32 output channels), A K-major.
 // Rows of a 32 x 16 accumulator chunk staged in tw[32][20]: lane = (row group of 8, 16-byte piece), four passes
+// wp > 0: compacting store -- grid row m = (b, y, x) on a grid wp wide goes to row (b * ho + y) * ho + x when x, y < ho and
+// nowhere otherwise (the thread's first row is decomposed once per tile, the other three follow by carrying 8 columns).
+// The epilogue of this kernel is bias + activation + derivative mask only (checked by the launcher); the four rows' mask
+// values are fetched as float4 BEFORE the first store -- behind a store the compiler cannot hoist them (aliasing), and four
+// serialised global-load latencies per tile made this epilogue the slowest stage of the pipeline.
 template <int ACT, int DACT>
 __device__ __forceinline__ void halo_store_rows16(const Epilogue& epi, const float* tw, float* __restrict__ C, int ldc,
-                                                  int M, int m_base, int gn0, int lane) {
+                                                  int M, int m_base, int gn0, int lane, int wp, int ho) {
   const int piece = lane & 3, rsub = lane >> 2;
+  const int on = gn0 + 4 * piece;
+  int gb = 0, gy = 0, gx = 0;
+  if (wp > 0) {
+    // m < 2^24 (checked by the launcher): quotient from a float reciprocal, corrected by one
+    const int m = m_base + rsub, wp2 = wp * wp;
+    gb = __float2int_rz(__int2float_rn(m) * __frcp_rn(__int2float_rn(wp2)));
+    int rem = m - gb * wp2;
+    if (rem < 0) { --gb; rem += wp2; } else if (rem >= wp2) { ++gb; rem -= wp2; }
+    gy = __float2int_rz(__int2float_rn(rem) * __frcp_rn(__int2float_rn(wp)));
+    gx = rem - gy * wp;
+    if (gx < 0) { --gy; gx += wp; } else if (gx >= wp) { ++gy; gx -= wp; }
+  }
+  int row_of[4];
+  bool live[4];
 #pragma unroll
   for (int r4 = 0; r4 < 4; ++r4) {
-    const int r = r4 * 8 + rsub;
-    const int om = m_base + r, on = gn0 + 4 * piece;
-    if (om < M) {
-      const float4 a4 = *reinterpret_cast<const float4*>(tw + r * 20 + 4 * piece);
-      float* cp = C + (size_t)om * ldc + on;
-      const float in[4] = {a4.x, a4.y, a4.z, a4.w};
-      float o[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) o[e] = epilogue_apply<ACT, DACT>(epi, in[e], om, on + e, cp + e);
-      *reinterpret_cast<float4*>(cp) = make_float4(o[0], o[1], o[2], o[3]);
+    const int om = m_base + r4 * 8 + rsub;
+    live[r4] = om < M;
+    row_of[r4] = om;
+    if (wp > 0) {
+      live[r4] = live[r4] && gx < ho && gy < ho;
+      row_of[r4] = (gb * ho + gy) * ho + gx;
+      gx += 8;  // wp > 8: at most one wrap
+      if (gx >= wp) { gx -= wp; ++gy; }
+      if (gy >= wp) { gy -= wp; ++gb; }
     }
+  }
+  constexpr bool kRuntime = ACT < 0 || DACT < 0;
+  const bool use_aux = kRuntime ? epi.dact != DACT_NONE : DACT != DACT_NONE;
+  float4 ax[4];
+#pragma unroll
+  for (int r4 = 0; r4 < 4; ++r4)
+    ax[r4] = (use_aux && live[r4]) ? __ldg(reinterpret_cast<const float4*>(epi.aux + (size_t)row_of[r4] * epi.ld_aux + on))
+                                   : make_float4(1.f, 1.f, 1.f, 1.f);
+  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (epi.bias) bv = __ldg(reinterpret_cast<const float4*>(epi.bias + on));
+  const int act = kRuntime ? epi.act : ACT, dact = kRuntime ? epi.dact : DACT;
+#pragma unroll
+  for (int r4 = 0; r4 < 4; ++r4) {
+    if (!live[r4]) continue;
+    const float4 a4 = *reinterpret_cast<const float4*>(tw + (r4 * 8 + rsub) * 20 + 4 * piece);
+    float o[4] = {fmaf(a4.x, epi.scale, bv.x), fmaf(a4.y, epi.scale, bv.y), fmaf(a4.z, epi.scale, bv.z), fmaf(a4.w, epi.scale, bv.w)};
+    const float h[4] = {ax[r4].x, ax[r4].y, ax[r4].z, ax[r4].w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      o[e] = apply_act(o[e], act);
+      if (use_aux) o[e] *= apply_dact(h[e], dact);
+    }
+    *reinterpret_cast<float4*>(C + (size_t)row_of[r4] * ldc + on) = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -730,7 +771,8 @@ __device__ __forceinline__ uint64_t smem_desc_sw128_rows(uint32_t addr, uint32_t
 template <bool B_MN>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 gemm_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      float* __restrict__ C, int ldc, int M, int N, int conv_w, int halo_rows, int flags, const Epilogue epi) {
+                      float* __restrict__ C, int ldc, int M, int N, int conv_w, int halo_rows, int flags, int compact_wp,
+                      int compact_ho, const Epilogue epi) {
   constexpr int BN = 32;
   constexpr int B_BYTES = BN * BK * 4;
   constexpr uint32_t TMEM_COLS = 2 * BN;
@@ -838,14 +880,24 @@ gemm_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
               make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                           __uint_as_float(v[4 * j + 3]));
         __syncwarp();
-#define RLREP_HSTORE(A, D) halo_store_rows16<A, D>(epi, tw, C, ldc, M, m0 + 32 * q, gn0, lane)
+#define RLREP_HSTORE(A, D) halo_store_rows16<A, D>(epi, tw, C, ldc, M, m0 + 32 * q, gn0, lane, compact_wp, compact_ho)
         RLREP_EPILOGUE_SWITCH(epi, RLREP_HSTORE);
 #undef RLREP_HSTORE
         __syncwarp();
       } else if (gm < M) {
-        float* crow = C + (size_t)gm * ldc;
-        for (int e = 0; e < 16 && gn0 + e < N; ++e)
-          crow[gn0 + e] = epilogue_apply<-1, -1>(epi, __uint_as_float(v[e]), gm, gn0 + e, crow + gn0 + e);
+        int om = gm;
+        bool live = true;
+        if (compact_wp > 0) {
+          const int gb = gm / (compact_wp * compact_wp), rem = gm - gb * compact_wp * compact_wp;
+          const int gy = rem / compact_wp, gx = rem - gy * compact_wp;
+          live = gx < compact_ho && gy < compact_ho;
+          om = (gb * compact_ho + gy) * compact_ho + gx;
+        }
+        if (live) {
+          float* crow = C + (size_t)om * ldc;
+          for (int e = 0; e < 16 && gn0 + e < N; ++e)
+            crow[gn0 + e] = epilogue_apply<-1, -1>(epi, __uint_as_float(v[e]), om, gn0 + e, crow + gn0 + e);
+        }
       }
       ptx::tc_fence_before_sync();
       __syncwarp();
@@ -872,7 +924,7 @@ void launch_conv_halo(const TcGemmPlan& p, cudaStream_t stream) {
   const GemmArgs& a = p.args;
   const int tiles = ceil_div(a.M, BM);
   kern<<<std::min(tiles, kNumSMs), kHaloThreads, kHaloSmem, stream>>>(p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, a.conv_w,
-                                                                       p.halo_rows, flags, a.epi);
+                                                                       p.halo_rows, flags, a.compact_wp, a.compact_ho, a.epi);
   RLREP_LAUNCHED_W("gemm_conv_halo", stream, 4.0 * ((double)a.M * 32 + (double)a.N * a.K + (double)a.M * a.N),
                    2.0 * a.M * a.N * a.K);
 }
@@ -895,6 +947,7 @@ void launch_variant_persistent(const TcGemmPlan& p, cudaStream_t stream) {
     attr_set = true;
   }
   const GemmArgs& a = p.args;
+  RLREP_CHECK(a.compact_wp == 0, "compacting stores exist on the halo convolution kernel only");
   const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN);
   kern<<<std::min(tiles, kNumSMs), kPersistThreads, smem_bytes(BN) + 4 * 32 * 36 * 4, stream>>>(p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, a.K, a.conv_w, a.epi, g_persist_dbg);
   RLREP_LAUNCHED_W("gemm_tf32_persistent", stream,
@@ -941,6 +994,7 @@ void fill_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, dim3
 template <int BN, bool A_MN, bool B_MN>
 void launch_variant(const TcGemmPlan& p, cudaStream_t stream) {
   const GemmArgs& a = p.args;
+  RLREP_CHECK(a.compact_wp == 0, "compacting stores exist on the halo convolution kernel only");
   RLREP_CHECK(p.stages >= (p.push ? 2 : min_stages(BN)) && p.stages <= num_stages(BN), "bad pipeline depth");
   RLREP_CHECK(!p.push || (p.split_k > 1 && smem_bytes(BN, p.stages, true) <= kMaxSmem), "bad push-mode plan");
   cudaLaunchConfig_t cfg;

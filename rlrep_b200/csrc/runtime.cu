@@ -211,6 +211,18 @@ void GemmRunner::end_chain() {
   recording_ = false;
 }
 
+bool GemmRunner::run_compact(GemmArgs a, int wp, int ho, cudaStream_t s) {
+  if (recording_ || prec_ != PREC_TF32 || !tc_eligible(a) || a.conv_w <= 0 || a.M < 32 || a.N != 32 || wp <= 8 ||
+      a.M >= (1 << 24))
+    return false;
+  a.compact_wp = wp;
+  a.compact_ho = ho;
+  const TcGemmPlan probe = make_tc_plan(a, 0, 0, ws_, ws_floats_, sm_share_);  // cheap: cost model + two tensor maps
+  if (probe.halo_rows <= 0) return false;
+  run(a, s);
+  return true;
+}
+
 void GemmRunner::run(const GemmArgs& a, cudaStream_t s) {
   if (recording_) {
     if (chain_eligible(a)) {
@@ -223,6 +235,7 @@ void GemmRunner::run(const GemmArgs& a, cudaStream_t s) {
   // Short-K layers (K = 17 / 23 inputs) also go to the tensor cores: the tensor maps carry the LOGICAL K, so TMA
   // zero-fills the rest of the 32-wide k-block whatever sits behind the operands in memory.
   const bool tc = prec_ == PREC_TF32 && tc_eligible(a) && a.M >= 32 && a.N >= 32 && a.K >= 8;
+  RLREP_CHECK(a.compact_wp == 0 || tc, "compacting stores exist on the tensor-core halo kernel only");
   if (!tc) {
     launch_simt(a, s);
     return;
@@ -235,6 +248,7 @@ void GemmRunner::run(const GemmArgs& a, cudaStream_t s) {
     k->A = a.A; k->lda = a.lda; k->a_mn = a.a_mn;
     k->B = a.B; k->ldb = a.ldb; k->b_mn = a.b_mn;
     k->C = a.C; k->ldc = a.ldc; k->conv_w = a.conv_w; k->conv_wgrad_hi = a.conv_wgrad_hi;
+    k->compact_wp = a.compact_wp; k->compact_ho = a.compact_ho;
     k->epi.bias = a.epi.bias; k->epi.r1_u = a.epi.r1_u; k->epi.r1_v = a.epi.r1_v; k->epi.aux = a.epi.aux;
     k->epi.pre_out = a.epi.pre_out; k->epi.ld_aux = a.epi.ld_aux; k->epi.ld_pre = a.epi.ld_pre;
     k->epi.act = a.epi.act; k->epi.dact = a.epi.dact; k->epi.accumulate = a.epi.accumulate;
