@@ -2,13 +2,15 @@
 // agent/mulvdrq/drqv2.py:52-96): RandomShiftsAug (replicate-pad 4 + integer shift) -> x / 255 - 0.5 ->
 // Conv 3x3 s2 (C -> 32) + ReLU -> 3 x [Conv 3x3 s1 (32 -> 32) + ReLU] -> flatten, forward and backward.
 //
-// First building block of the pixel agents (kernel K15).  Version 1 is a lowering onto
-// the library's tcgen05 GEMM: activations are kept NHWC ([B, H, W, 32] == a row-major [B*H*W, 32] matrix, so a GEMM
-// output IS the next layer's activation), each layer is   im2col (explicit, fp32)  ->  GEMM [B*Ho*Wo, 9*Cin] x [32, 9*Cin]^T
-// with the bias + ReLU epilogue; the backward pass is  wgrad = dY^T col,  dcol = dY W,  col2im (gather form, fused with
-// the ReLU mask of the layer below).  The augmentation, the uint8 -> float conversion and the normalisation are fused
-// into the first im2col, so the frames are read once as bytes.  The explicit column matrices cost ~10x the algorithmic
-// HBM traffic of the convolutions; replacing them with TMA im2col loads inside the GEMM's producer is the planned v2.
+// First building block of the pixel agents (kernel K15).  Activations are kept NHWC
+// ([B, H, W, 32] == a row-major [B*H*W, 32] matrix, so a GEMM output IS the next layer's activation).
+//   * layer 1 (stride 2, C input channels): explicit im2col -- augmentation, uint8 -> float and the normalisation fused into
+//     it, so the frames are read once as bytes -- then a GEMM with the bias + ReLU epilogue; backward: dW = dY^T col.
+//   * layers 2-4 (3x3, stride 1, 32 -> 32), TF32 path: NO column matrices.  Forward = implicit convolution on the input's
+//     own grid (the halo kernel, gemm_tc_kernel.cuh: one TMA box per tile, nine taps as shifted UMMA descriptors, valid
+//     rows stored compactly); data gradient = implicit full correlation on a zero-padded grid (conv_implicit.cu); weight
+//     gradient = a GEMM whose B operand reads the input map through a shifted 4-D TMA view (GemmArgs::conv_wgrad_hi).
+//   * strict-fp32 mode and RLREP_CONV_V1 / RLREP_CONV_WGRAD_V1: round 1's explicit im2col / folded-GEMM / col2im lowering.
 #include "conv.cuh"
 
 #include <cstdlib>

@@ -74,12 +74,15 @@ __global__ void scatter_to_grid_kernel(const float4* __restrict__ in, int B, int
   }
 }
 // G[n, (ky, kx), c] = sum_f C[(f, n), (ky, kx + f, c)] over the four folded rows, C [128, 576] (fixed order)
-__global__ void diag_tap_sum_kernel(const float* __restrict__ C, float* __restrict__ dW, int ld_dw, int transposed) {
+__global__ void diag_tap_sum_kernel(const float* __restrict__ C, int groups, float* __restrict__ dW, int ld_dw,
+                                    int transposed) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 32 * 288) return;
   const int n = i / 288, r = i - n * 288, t = r >> 5, c = r & 31, ky = t / 3, kx = t - 3 * ky;
   float acc = 0.f;
-  for (int f = 0; f < 4; ++f) acc += C[(size_t)(f * 32 + n) * 576 + ky * 192 + (kx + f) * 32 + c];
+  for (int g = 0; g < groups; ++g)  // the GEMM's K groups, then the four folded rows: fixed order
+    for (int f = 0; f < 4; ++f)
+      acc += C[(size_t)g * 128 * 576 + (size_t)(f * 32 + n) * 576 + ky * 192 + (kx + f) * 32 + c];
   if (transposed) dW[(size_t)r * ld_dw + n] = acc;
   else dW[(size_t)n * ld_dw + r] = acc;
 }
@@ -99,8 +102,16 @@ void conv3x3_wgrad_implicit(GemmRunner& g, cudaStream_t s, int B, int Hg, const 
   a.B = map; a.ldb = 128; a.b_mn = true;
   a.conv_wgrad_hi = Hg;
   a.C = sc.wfold; a.ldc = 576;
+  // nine or eighteen tiles x a split-K cluster of 8 leave half the GPU idle and every CTA with ~10 MB to stream: cut K
+  // into groups with their own output matrices (summed by diag_tap_sum)
+  static const int want_groups = [] {
+    const char* e = std::getenv("RLREP_WGRAD_GROUPS");
+    return e ? std::max(1, std::min(kWgradGroupsMax, std::atoi(e))) : 4;  // measured at B = 256: 1 and 2 groups 131 us, 4 groups 117 us
+  }();
+  a.k_groups = want_groups;
+  const int groups = (a.k_groups > 1 && ceil_div(a.K, 32) >= 64 * a.k_groups) ? a.k_groups : 1;  // make_tc_plan's rule
   g.run(a, s);
-  diag_tap_sum_kernel<<<ceil_div(32 * 288, 256), 256, 0, s>>>(sc.wfold, dW, ld_dw, transposed ? 1 : 0);
+  diag_tap_sum_kernel<<<ceil_div(32 * 288, 256), 256, 0, s>>>(sc.wfold, groups, dW, ld_dw, transposed ? 1 : 0);
   RLREP_LAUNCHED("diag_tap_sum", s);
 }
 

@@ -20,8 +20,7 @@ namespace rlrep {
 // Row operations that can ride in a GEMM chain (gemm_chain.cuh) between its GEMMs, executed by the chain kernel's
 // epilogue warps on (rows_per_item)-row items with the same dependency / publish protocol as a GEMM tile.  A GemmArgs
 // whose row.kind != ROWOP_NONE is such an operation, not a GEMM.
-enum RowOpKind : int { ROWOP_NONE = 0, ROWOP_CTRL_HEAD = 1, ROWOP_GATHER = 2, ROWOP_ADAM = 3 };
-struct AdamHyper;
+enum RowOpKind : int { ROWOP_NONE = 0, ROWOP_CTRL_HEAD = 1, ROWOP_GATHER = 2 };
 struct RowOp {
   int kind = ROWOP_NONE;
   int rows = 0;
@@ -46,16 +45,6 @@ struct RowOp {
   const long long* idx = nullptr;
   float* out = nullptr;
   int rec4 = 0;
-  // ROWOP_ADAM: adam_polyak_kernel (kernels.cu) over n floats (a multiple of 4) of one parameter group, as a BACKGROUND
-  // operation: it has no place in the CTAs' item lists -- the epilogue warps of every CTA work through their share of its
-  // 8 KB chunks whenever the accumulator they wait for is not ready yet -- and the GEMMs that read the parameters wait for
-  // it like for any other member.  It must not depend on a member of the same chain (its gradients come from earlier
-  // launches).
-  float *adam_p = nullptr, *adam_m = nullptr, *adam_v = nullptr, *adam_target = nullptr;
-  const float* adam_g = nullptr;
-  const AdamHyper* adam_hyper = nullptr;
-  unsigned adam_n = 0, adam_n_polyak = 0;
-  float adam_tau = 0.f;
 };
 
 struct GemmArgs {
@@ -85,6 +74,10 @@ struct GemmArgs {
   // compact_wp wide; only rows with x < compact_ho and y < compact_ho are stored, at row (b * ho + y) * ho + x of C -- and
   // of epi.aux / epi.pre_out, which are indexed by the compact row too.
   int compact_wp = 0, compact_ho = 0;
+  // K groups (tensor-core path, one tile per CTA): the K range is cut into k_groups parts, each reduced by its own split-K
+  // cluster into its own output matrix -- k_groups matrices of ceil(M / 128) * 128 rows (pitch ldc) behind each other at C,
+  // which the caller sums.  For GEMMs with K ~ 1e5 and a handful of tiles, where a cluster's 8 CTAs are not enough.
+  int k_groups = 1;
   const float* B = nullptr;
   int ldb = 0;
   bool b_mn = false;
@@ -104,6 +97,7 @@ struct TcGemmPlan {
   int stages = 0;       // TMA ring depth (shallow for short K-slices so two CTAs share an SM)
   bool push = false;    // split-K partials pushed into the owner CTA's shared memory (see gemm_tc_kernel.cuh)
   bool persistent = false;  // one CTA per SM walks the tiles with a double-buffered TMEM accumulator (no split-K)
+  int k_groups = 1;         // GemmArgs::k_groups as planned (1 when the K range is too short to cut)
   int halo_rows = 0;        // > 0: implicit convolution with the tile's halo in shared memory (gemm_conv_halo_kernel)
   float* ws = nullptr;  // unused (split-K reduces over DSMEM); kept for ABI stability of rlrep_gemm
 };

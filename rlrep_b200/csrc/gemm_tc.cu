@@ -133,13 +133,14 @@ int pick_stages(int bn, int kb_per, bool push) {
 // grows with the cluster size, times the number of waves.  The wave count uses the occupancy API's answer for how
 // many clusters of this shape the GPU holds at once (8-CTA clusters must fit in a GPC: far fewer than 148 / 8), scaled
 // by the share of the GPU the caller expects to have.
-double plan_cost(const GemmArgs& a, int nkb, int bn, int s, double sm_share, int* kb_per_out, int* stages_out) {
+double plan_cost(const GemmArgs& a, int nkb, int bn, int s, double sm_share, int* kb_per_out, int* stages_out,
+                 int groups = 1) {
   const int kb_per = ceil_div(nkb, s);
   const bool push = use_push(bn, s);
   const int stages = pick_stages(bn, kb_per, push);
   *kb_per_out = kb_per;
   *stages_out = stages;
-  const int clusters = ceil_div(a.M, BM) * ceil_div(a.N, bn);
+  const int clusters = ceil_div(a.M, BM) * ceil_div(a.N, bn) * groups;
   const double cap = std::max(1.0, max_clusters(bn, a.a_mn, a.b_mn, s, stages, push) * sm_share);
   const double waves = std::ceil(clusters / cap);
   // When the GEMM shares the GPU with other branches the aggregate L2 -> SM operand traffic (not the per-CTA stream) is
@@ -190,7 +191,12 @@ TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* /*ws*/, s
               "split_k is the cluster size along K: 1, 2, 4 or 8");
   TcGemmPlan p;
   p.args = a;
-  const int nkb = ceil_div(a.K, BK);
+  const int nkb_all = ceil_div(a.K, BK);
+  // K groups (GemmArgs::k_groups): each group is planned like a GEMM over its share of K
+  const int groups = (a.k_groups > 1 && nkb_all >= 64 * a.k_groups) ? a.k_groups : 1;
+  RLREP_CHECK(a.k_groups == 1 || (a.conv_w == 0 && !a.epi.accumulate), "K groups: plain GEMMs only");
+  p.k_groups = groups;
+  const int nkb = ceil_div(nkb_all, groups);
   double best = 1e300;
   for (int cand_bn : {32, 64, 128, 256}) {
     if (bn != 0 && cand_bn != bn) continue;
@@ -200,7 +206,8 @@ TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* /*ws*/, s
       if (split_k != 0 && s != split_k) continue;
       int kb_per = 0, stages = 0;
       if (s > 1 && (s - 1) * ceil_div(nkb, s) >= nkb) continue;  // would leave an empty split
-      const double c = plan_cost(a, nkb, cand_bn, s, sm_share, &kb_per, &stages);
+      if (groups > 1 && (s * groups - 1) * ceil_div(nkb, s) >= nkb_all) continue;
+      const double c = plan_cost(a, nkb, cand_bn, s, sm_share, &kb_per, &stages, groups);
       if (c < best) {
         best = c;
         p.bn = cand_bn;
@@ -214,7 +221,8 @@ TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* /*ws*/, s
   if (p.bn == 0) {  // requested split not realisable (K too short): fall back to no split
     p.bn = bn ? bn : 32;
     p.split_k = 1;
-    p.kb_per_split = nkb;
+    p.k_groups = 1;
+    p.kb_per_split = nkb_all;
     p.stages = pick_stages(p.bn, nkb, false);
     p.push = false;
   }

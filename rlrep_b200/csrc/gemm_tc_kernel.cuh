@@ -306,6 +306,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   // prologue (barrier init, TMEM allocation), lets ITS dependents start theirs (launch_dependents), and only then waits
   // for the previous grid's memory (griddepcontrol.wait) before the first operand load.
   const bool pdl = (push & 2) != 0;
+  // bits 8..15: K groups - 1.  gridDim.z = groups x splits: every group of `splits` CTAs (one cluster) reduces its own K
+  // range into its own output matrix, `group` matrices of ceil(M / 128) * 128 rows behind each other -- K-parallelism
+  // beyond the 8 CTAs a cluster can hold, for the caller to sum (the implicit conv weight gradient: K ~ 1e5)
+  const int groups = ((push >> 8) & 0xff) + 1;
   push &= 1;
   constexpr int A_BYTES = BM * BK * 4;
   constexpr int B_BYTES = BN * BK * 4;
@@ -332,7 +336,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (threadIdx.x == 0) trace(0);
   const int n0 = blockIdx.x * BN;
   const int m0 = blockIdx.y * BM;
-  const int splits = gridDim.z;
+  const int splits = gridDim.z / groups;
+  if (groups > 1) C += (size_t)(blockIdx.z / splits) * (size_t)(((M + BM - 1) / BM) * BM) * ldc;
   const int nkb_total = (K + BK - 1) / BK;
   const int kb_begin = blockIdx.z * kb_per_split;
   const int kb_end = min(nkb_total, kb_begin + kb_per_split);
@@ -999,10 +1004,11 @@ void launch_variant(const TcGemmPlan& p, cudaStream_t stream) {
   RLREP_CHECK(!p.push || (p.split_k > 1 && smem_bytes(BN, p.stages, true) <= kMaxSmem), "bad push-mode plan");
   cudaLaunchConfig_t cfg;
   cudaLaunchAttribute attr[2];
-  fill_launch_config<BN, A_MN, B_MN>(cfg, attr, dim3(ceil_div(a.N, BN), ceil_div(a.M, BM), p.split_k), p.split_k,
-                                     p.stages, p.push, stream);
+  fill_launch_config<BN, A_MN, B_MN>(cfg, attr, dim3(ceil_div(a.N, BN), ceil_div(a.M, BM), p.split_k * p.k_groups),
+                                     p.split_k, p.stages, p.push, stream);
   RLREP_CUDA(cudaLaunchKernelEx(&cfg, gemm_tf32_kernel<BN, A_MN, B_MN>, p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, a.K,
-                                p.kb_per_split, p.stages, (p.push ? 1 : 0) | (pdl_enabled() ? 2 : 0),
+                                p.kb_per_split, p.stages,
+                                (p.push ? 1 : 0) | (pdl_enabled() ? 2 : 0) | ((p.k_groups - 1) << 8),
                                 a.conv_wgrad_hi > 0 ? -1 : a.conv_w, a.epi));
   g_trace_reader = &read_trace_here;
   // implicit convolution: A is the [M, 32] pixel matrix, read once from HBM (the nine shifted re-reads hit L2)

@@ -248,7 +248,7 @@ void GemmRunner::run(const GemmArgs& a, cudaStream_t s) {
     k->A = a.A; k->lda = a.lda; k->a_mn = a.a_mn;
     k->B = a.B; k->ldb = a.ldb; k->b_mn = a.b_mn;
     k->C = a.C; k->ldc = a.ldc; k->conv_w = a.conv_w; k->conv_wgrad_hi = a.conv_wgrad_hi;
-    k->compact_wp = a.compact_wp; k->compact_ho = a.compact_ho;
+    k->compact_wp = a.compact_wp; k->compact_ho = a.compact_ho; k->k_groups = a.k_groups;
     k->epi.bias = a.epi.bias; k->epi.r1_u = a.epi.r1_u; k->epi.r1_v = a.epi.r1_v; k->epi.aux = a.epi.aux;
     k->epi.pre_out = a.epi.pre_out; k->epi.ld_aux = a.epi.ld_aux; k->epi.ld_pre = a.epi.ld_pre;
     k->epi.act = a.epi.act; k->epi.dact = a.epi.dact; k->epi.accumulate = a.epi.accumulate;
