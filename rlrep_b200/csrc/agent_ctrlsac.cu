@@ -352,11 +352,19 @@ class CtrlSacAgent final : public SacBase {
     linear_fwd(gemm_, s0, B_, Mat{zphi_, D_}, l14, ACT_ELU, hid_, 2 * H_);
     phi_forward(s0, spi, Mat(), 0, zpi_, hc1_, hc2_);  // frozen_phi(s, a_pi), consumed by the actor step
     gemm_.end_chain();
-    launch_rowdot_pair(RowDotJob{hid_t_, l2t.W, l2t.b, nq1_, 2 * H_, H_}, RowDotJob{hid_t_ + H_, l5t.W, l5t.b, nq2_, 2 * H_, H_}, B_, s0);
-    launch_rowdot_pair(RowDotJob{hid_, l2.W, l2.b, q1_, 2 * H_, H_}, RowDotJob{hid_ + H_, l5.W, l5.b, q2_, 2 * H_, H_}, B_, s0);
-    launch_td_critic_loss(reward(), done(), R_, nq1_, nq2_, logp2_, q1_, q2_, B_, cfg.discount, ctl, dq1_, dq2_,
-                          metrics_dev_ + 3, s0);
-    critic_heads_backward_to_hidden();
+    {  // the four N = 1 heads, the TD loss and the way back to the hidden layer: one launch, a CTA per row
+      CriticHeadArgs a;
+      a.hid_t = hid_t_; a.hid = hid_; a.ldh = 2 * H_; a.H = H_; a.B = B_;
+      a.w2t = l2t.W; a.b2t = l2t.b; a.w5t = l5t.W; a.b5t = l5t.b;
+      a.w2 = l2.W; a.b2 = l2.b; a.w5 = l5.W; a.b5 = l5.b;
+      a.reward = reward(); a.done = done(); a.ld_rd = R_;
+      a.logp2 = logp2_; a.gamma = cfg.discount; a.c = ctl;
+      a.nq1 = nq1_; a.nq2 = nq2_; a.q1 = q1_; a.q2 = q2_; a.dq1 = dq1_; a.dq2 = dq2_;
+      a.dhid = dhid_; a.ld_dh = 2 * H_;
+      a.metrics = metrics_dev_ + 3;
+      a.counter = head_ctr_ + 1;
+      launch_critic_td_head(a, s0);
+    }
     {
       ColJob jobs[5] = {ColJob{hid_, dq1_, l2.dW, 2 * H_, B_, H_}, ColJob{dq1_, nullptr, l2.db, 1, B_, 1},
                         ColJob{hid_ + H_, dq2_, l5.dW, 2 * H_, B_, H_}, ColJob{dq2_, nullptr, l5.db, 1, B_, 1},
@@ -370,12 +378,22 @@ class CtrlSacAgent final : public SacBase {
 
   void actor_step_chained() {  // ctrlsac_agent.py:295-325
     const float* eps = eps_dev_ + (size_t)B_ * A_;
-    critic_forward(stream, zpi_, false, hid_, q1_, q2_);  // the UPDATED critic on frozen_phi(s, a_pi)
-    launch_actor_alpha_loss(q1_, q2_, logp_, B_, (float)(-A_), cfg.learn_alpha, ctl, dq1_, dq2_, dlogp_,
-                            metrics_dev_ + 7, stream);
     const Linear l14 = c14_.view(crit_g_);
     const Linear l1 = p1_.view(feat_g_), l2 = p2_.view(feat_g_), l3 = p3_.view(feat_g_);
-    critic_heads_backward_to_hidden();
+    {  // the UPDATED critic on frozen_phi(s, a_pi): hidden layer, then heads + actor / temperature loss + backward in one launch
+      const Linear c2 = c2_.view(crit_g_), c5 = c5_.view(crit_g_);
+      linear_fwd(gemm_, stream, B_, Mat{zpi_, D_}, l14, ACT_ELU, hid_, 2 * H_);
+      ActorHeadArgs a;
+      a.hid = hid_; a.ldh = 2 * H_; a.H = H_; a.B = B_;
+      a.w2 = c2.W; a.b2 = c2.b; a.w5 = c5.W; a.b5 = c5.b;
+      a.logp = logp_; a.target_entropy = (float)(-A_); a.learn_alpha = cfg.learn_alpha; a.c = ctl;
+      a.q1 = q1_; a.q2 = q2_; a.dq1 = dq1_; a.dq2 = dq2_;
+      a.dhid = dhid_; a.ld_dh = 2 * H_;
+      a.dlogp_scalar = dlogp_;
+      a.metrics = metrics_dev_ + 7;
+      a.counter = head_ctr_ + 2;
+      launch_actor_head(a, stream);
+    }
     gemm_.begin_chain(stream);
     linear_dgrad(gemm_, stream, B_, Mat{dhid_, 2 * H_}, l14, DACT_NONE, Mat(), dzphi_, D_);
     linear_dgrad(gemm_, stream, B_, Mat{dzphi_, D_}, l3, DACT_ELU_OUT, Mat{hc2_, H_}, dh2_, H_);

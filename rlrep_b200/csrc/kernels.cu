@@ -560,6 +560,154 @@ __global__ void __launch_bounds__(256) actor_alpha_loss_kernel(const float* __re
   }
 }
 
+// ------------------------------------------------------------------------------------------- fused SAC heads (chained path)
+// The N = 1 heads of the twin critic, the loss on them and the way back to the hidden layer are row-local except for the
+// loss means: ONE launch with a CTA per batch row replaces rowdot x2 + td_critic_loss + outer_dact x2 (critic step) and
+// rowdot + actor_alpha_loss + outer_dact x2 (actor step); the last CTA to finish (arrival counter) runs the reductions of
+// td_critic_loss_kernel / actor_alpha_loss_kernel unchanged, so metrics and the temperature step are bit-identical.
+__device__ __forceinline__ float head_dot(const float* __restrict__ x, const float* __restrict__ w, int D, int tid) {
+  float acc = 0.f;
+  if ((D & 3) == 0 && ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(w)) & 15) == 0) {
+    const float4* x4 = reinterpret_cast<const float4*>(x);
+    const float4* w4 = reinterpret_cast<const float4*>(w);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    for (int j = tid; j < D / 4; j += 256) {
+      const float4 xv = x4[j];
+      const float4 wv = __ldg(w4 + j);
+      a0 = fmaf(xv.x, wv.x, a0); a1 = fmaf(xv.y, wv.y, a1); a2 = fmaf(xv.z, wv.z, a2); a3 = fmaf(xv.w, wv.w, a3);
+    }
+    acc = (a0 + a1) + (a2 + a3);
+  } else {
+    for (int j = tid; j < D; j += 256) acc = fmaf(x[j], __ldg(w + j), acc);
+  }
+  return acc;
+}
+// dhid[row, 0:H] = dq1 * w2 * elu'(hid[row, 0:H]), dhid[row, H:2H] = dq2 * w5 * elu'(hid[row, H:2H])  (outer_dact, ELU_OUT)
+__device__ __forceinline__ void head_backward_row(const float* __restrict__ hid, const float* __restrict__ w2,
+                                                  const float* __restrict__ w5, float dq1, float dq2, int H,
+                                                  float* __restrict__ dhid, int tid) {
+  for (int j = tid; j < 2 * H; j += 256) {
+    const bool second = j >= H;
+    float v = (second ? dq2 : dq1) * __ldg((second ? w5 : w2) + (second ? j - H : j));
+    v *= apply_dact(hid[j], DACT_ELU_OUT);
+    dhid[j] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) critic_td_head_kernel(const CriticHeadArgs a) {
+  __shared__ float scratch[33];
+  __shared__ float bc[2];
+  __shared__ bool last;
+  const int row = blockIdx.x, tid = threadIdx.x, H = a.H;
+  const float* ht = a.hid_t + (size_t)row * a.ldh;
+  const float* h = a.hid + (size_t)row * a.ldh;
+  float nq1 = block_sum<256>(head_dot(ht, a.w2t, H, tid), scratch);
+  float nq2 = block_sum<256>(head_dot(ht + H, a.w5t, H, tid), scratch);
+  float q1 = block_sum<256>(head_dot(h, a.w2, H, tid), scratch);
+  float q2 = block_sum<256>(head_dot(h + H, a.w5, H, tid), scratch);
+  if (tid == 0) {
+    nq1 += __ldg(a.b2t); nq2 += __ldg(a.b5t); q1 += __ldg(a.b2); q2 += __ldg(a.b5);
+    const float alpha = a.c->alpha, inv_b = 1.f / (float)a.B;
+    const float nq = fminf(nq1, nq2) - alpha * a.logp2[row];
+    const float y = a.reward[(size_t)row * a.ld_rd] + (1.f - a.done[(size_t)row * a.ld_rd]) * a.gamma * nq;
+    const float e1 = q1 - y, e2 = q2 - y;
+    a.nq1[row] = nq1; a.nq2[row] = nq2; a.q1[row] = q1; a.q2[row] = q2;
+    bc[0] = 2.f * e1 * inv_b;
+    bc[1] = 2.f * e2 * inv_b;
+    a.dq1[row] = bc[0];
+    a.dq2[row] = bc[1];
+  }
+  __syncthreads();
+  head_backward_row(h, a.w2, a.w5, bc[0], bc[1], H, a.dhid + (size_t)row * a.ld_dh, tid);
+  if (tid == 0) {
+    __threadfence();
+    last = atomicAdd(a.counter, 1u) == (unsigned)(a.B - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // td_critic_loss_kernel's reductions, same order
+  const float alpha = a.c->alpha, inv_b = 1.f / (float)a.B;
+  float l1 = 0.f, l2 = 0.f, s1 = 0.f, s2 = 0.f;
+  for (int i = tid; i < a.B; i += 256) {
+    const float nq = fminf(__ldcg(a.nq1 + i), __ldcg(a.nq2 + i)) - alpha * a.logp2[i];
+    const float y = a.reward[(size_t)i * a.ld_rd] + (1.f - a.done[(size_t)i * a.ld_rd]) * a.gamma * nq;
+    const float v1 = __ldcg(a.q1 + i), v2 = __ldcg(a.q2 + i);
+    const float e1 = v1 - y, e2 = v2 - y;
+    l1 = fmaf(e1, e1, l1);
+    l2 = fmaf(e2, e2, l2);
+    s1 += v1;
+    s2 += v2;
+  }
+  l1 = block_sum<256>(l1, scratch);
+  l2 = block_sum<256>(l2, scratch);
+  s1 = block_sum<256>(s1, scratch);
+  s2 = block_sum<256>(s2, scratch);
+  if (tid == 0) {
+    a.metrics[0] = l1 * inv_b;
+    a.metrics[1] = l2 * inv_b;
+    a.metrics[2] = s1 * inv_b;
+    a.metrics[3] = s2 * inv_b;
+    *a.counter = 0;  // re-armed for the next launch
+  }
+}
+
+__global__ void __launch_bounds__(256) actor_head_kernel(const ActorHeadArgs a) {
+  __shared__ float scratch[33];
+  __shared__ float bc[2];
+  __shared__ bool last;
+  const int row = blockIdx.x, tid = threadIdx.x, H = a.H;
+  const float* h = a.hid + (size_t)row * a.ldh;
+  float q1 = block_sum<256>(head_dot(h, a.w2, H, tid), scratch);
+  float q2 = block_sum<256>(head_dot(h + H, a.w5, H, tid), scratch);
+  if (tid == 0) {
+    q1 += __ldg(a.b2); q2 += __ldg(a.b5);
+    a.q1[row] = q1; a.q2[row] = q2;
+    // torch.min backward: the smaller input gets the gradient, a tie splits it
+    const float g = -1.f / (float)a.B;
+    bc[0] = q1 < q2 ? g : (q1 == q2 ? 0.5f * g : 0.f);
+    bc[1] = q2 < q1 ? g : (q1 == q2 ? 0.5f * g : 0.f);
+    a.dq1[row] = bc[0];
+    a.dq2[row] = bc[1];
+  }
+  __syncthreads();
+  head_backward_row(h, a.w2, a.w5, bc[0], bc[1], H, a.dhid + (size_t)row * a.ld_dh, tid);
+  if (tid == 0) {
+    __threadfence();
+    last = atomicAdd(a.counter, 1u) == (unsigned)(a.B - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  // actor_alpha_loss_kernel's reductions and temperature step, same order
+  Control* c = a.c;
+  const float alpha = c->alpha, inv_b = 1.f / (float)a.B;
+  float la = 0.f, ent = 0.f, raw = 0.f;
+  for (int i = tid; i < a.B; i += 256) {
+    const float v1 = __ldcg(a.q1 + i), v2 = __ldcg(a.q2 + i);
+    la += alpha * a.logp[i] - fminf(v1, v2);
+    ent += alpha * (-a.logp[i] - a.target_entropy);
+    raw += -a.logp[i] - a.target_entropy;
+  }
+  la = block_sum<256>(la, scratch);
+  ent = block_sum<256>(ent, scratch);
+  raw = block_sum<256>(raw, scratch);
+  if (tid == 0) {
+    *a.dlogp_scalar = alpha * inv_b;
+    a.metrics[0] = la * inv_b;
+    a.metrics[1] = ent * inv_b;
+    if (a.learn_alpha) {
+      const double g = (double)(raw * inv_b) * exp(c->log_alpha);
+      c->la_m = c->la_m + (1.0 - 0.9) * (g - c->la_m);
+      c->la_v = c->la_v * 0.999 + (1.0 - 0.999) * g * g;
+      const double denom = sqrt(c->la_v) / c->alpha_bc2_sqrt + 1e-8;
+      c->log_alpha = c->log_alpha - c->alpha_step_size * (c->la_m / denom);
+    }
+    a.metrics[2] = (float)exp(c->log_alpha);
+    *a.counter = 0;
+  }
+}
+
 // Batch-sharded variant of the kernel above (agent_ctrlsac_dp.cu): the rank's rows contribute partial means over the
 // GLOBAL batch; the temperature step runs after the partials have been all-reduced.
 __global__ void __launch_bounds__(256) actor_loss_partial_kernel(const float* __restrict__ q1,
@@ -943,6 +1091,15 @@ void launch_contrastive_head(float* logits, int ld, int rows, int cols, int diag
   contrastive_head_kernel<<<rows, 256, 0, s>>>(logits, ld, cols, diag_off, inv_batch, z, ldz, D, theta_w, theta_b, reward, ld_r,
                                                loss_rows, pred, dpred, metrics, counter, rows);
   RLREP_LAUNCHED_W("contrastive_head", s, 3.0 * 4.0 * (double)rows * cols + 4.0 * (double)rows * D, 0.0);
+}
+
+void launch_critic_td_head(const CriticHeadArgs& a, cudaStream_t s) {
+  critic_td_head_kernel<<<a.B, 256, 0, s>>>(a);
+  RLREP_LAUNCHED_W("critic_td_head", s, 4.0 * a.B * (4.0 * a.H + 2.0 * a.H), 0.0);
+}
+void launch_actor_head(const ActorHeadArgs& a, cudaStream_t s) {
+  actor_head_kernel<<<a.B, 256, 0, s>>>(a);
+  RLREP_LAUNCHED_W("actor_head", s, 4.0 * a.B * (4.0 * a.H), 0.0);
 }
 
 void launch_actor_sample(const float* head, int ld_head, int B, int A, const float* eps, float* action, int lda,

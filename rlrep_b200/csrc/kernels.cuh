@@ -112,6 +112,39 @@ void launch_td_critic_loss(const float* reward, const float* done, int ld_rd, co
                            const float* logp2, const float* q1, const float* q2, int B, float gamma, const Control* c,
                            float* dq1, float* dq2, float* metrics, cudaStream_t s, int norm_B = 0);
 
+// Fused heads of the chained CTRL critic / actor steps (kernels.cu "fused SAC heads"): hid_t / hid are [B, 2H] hidden
+// activations of the twin critic (target / live), w2 / w5 the two N = 1 heads; outputs as the kernels they replace.
+struct CriticHeadArgs {
+  const float *hid_t, *hid;
+  int ldh, H, B;
+  const float *w2t, *b2t, *w5t, *b5t, *w2, *b2, *w5, *b5;
+  const float *reward, *done;
+  int ld_rd;
+  const float* logp2;
+  float gamma;
+  const Control* c;
+  float *nq1, *nq2, *q1, *q2, *dq1, *dq2, *dhid;
+  int ld_dh;
+  float* metrics;     // q1_loss, q2_loss, mean(q1), mean(q2)
+  unsigned* counter;  // zero before the first launch; re-armed by the kernel
+};
+void launch_critic_td_head(const CriticHeadArgs& a, cudaStream_t s);
+struct ActorHeadArgs {
+  const float* hid;
+  int ldh, H, B;
+  const float *w2, *b2, *w5, *b5;
+  const float* logp;
+  float target_entropy;
+  int learn_alpha;
+  Control* c;
+  float *q1, *q2, *dq1, *dq2, *dhid;
+  int ld_dh;
+  float* dlogp_scalar;
+  float* metrics;  // actor_loss, alpha_loss, alpha
+  unsigned* counter;
+};
+void launch_actor_head(const ActorHeadArgs& a, cudaStream_t s);
+
 // Actor / temperature losses (ctrlsac_agent.py:308-320; sac_agent.py:146-161), single block:
 //   actor_loss = mean(alpha * logp - min(q1, q2));  dq1/dq2 = -[argmin] / B;  *dlogp_scalar = alpha / B
 //   alpha_loss = mean(alpha * (-logp - target_entropy)); fp64 Adam step on log_alpha inside the control block.
