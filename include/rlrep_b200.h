@@ -385,6 +385,12 @@ RLREP_EXPORT int rlrep_ldiff_tensor_write(rlrep_ldiff* h, int i, const float* in
 RLREP_EXPORT int rlrep_ldiff_sync_targets(rlrep_ldiff* h);
 /* metrics_host[8] = {recon_loss, kl_loss, score_loss, critic_loss, mean(q_pred), mean(q_target), mean(reward), actor_loss} */
 RLREP_EXPORT int rlrep_ldiff_update(rlrep_ldiff* h, const rlrep_ldiff_inputs* in, float* metrics_host);
+/* Measurement aids (bench.py), like rlrep_drq_update_resident / rlrep_drq_profile_update: n_steps updates on the inputs
+ * the last rlrep_ldiff_update left in device memory, timed with CUDA events; one eager update with an event behind every
+ * kernel launch. */
+RLREP_EXPORT int rlrep_ldiff_update_resident(rlrep_ldiff* h, int n_steps, float stddev, float* total_ms);
+RLREP_EXPORT int rlrep_ldiff_profile_update(rlrep_ldiff* h, float stddev, int max_entries, const char** names, float* ms,
+                                            double* bytes, double* flops, int* n_entries);
 RLREP_EXPORT int rlrep_ldiff_last_launches(rlrep_ldiff* h, int* launches);
 
 /* Kernels launched by the most recent train() (a graph replay counts the kernels it contains). */

@@ -123,6 +123,9 @@ def _declare(lib: C.CDLL) -> None:
         "rlrep_ldiff_tensor_write": [vp, i, vp],
         "rlrep_ldiff_sync_targets": [vp],
         "rlrep_ldiff_update": [vp, vp, vp],
+        "rlrep_ldiff_update_resident": [vp, i, C.c_float, C.POINTER(C.c_float)],
+        "rlrep_ldiff_profile_update": [vp, C.c_float, i, C.POINTER(C.c_char_p), C.POINTER(C.c_float),
+                                       C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i)],
         "rlrep_ldiff_last_launches": [vp, C.POINTER(i)],
         "rlrep_mulv_create": [vp, vp, C.POINTER(vp)],
         "rlrep_mulv_destroy": [vp],

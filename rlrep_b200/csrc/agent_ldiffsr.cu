@@ -382,6 +382,30 @@ void LatentDiffSR::update(const Inputs& in, float* metrics_out) {
   std::memcpy(metrics_out, metrics_host_, 8 * sizeof(float));
 }
 
+float LatentDiffSR::update_resident(int n_steps, float stddev) {
+  RLREP_CHECK(n_steps > 0, "bad step count");
+  cudaEvent_t e0, e1;
+  RLREP_CUDA(cudaEventCreate(&e0));
+  RLREP_CUDA(cudaEventCreate(&e1));
+  RLREP_CUDA(cudaStreamSynchronize(stream_));
+  RLREP_CUDA(cudaEventRecord(e0, stream_));
+  for (int i = 0; i < n_steps; ++i) launch_update(stddev);
+  RLREP_CUDA(cudaEventRecord(e1, stream_));
+  RLREP_CUDA(cudaEventSynchronize(e1));
+  float ms = 0.f;
+  RLREP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  return ms;
+}
+
+std::vector<ProfileEntry> LatentDiffSR::profile_update(float stddev) {
+  RLREP_CUDA(cudaStreamSynchronize(stream_));
+  profile_begin(stream_);
+  launch_update(stddev);
+  return profile_end(stream_);
+}
+
 void LatentDiffSR::launch_update(float stddev) {
   cudaStream_t s = stream_;
   const size_t B2 = 2 * (size_t)B_, BL3 = (size_t)B_ * 3 * L_;

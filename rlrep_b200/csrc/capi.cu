@@ -800,6 +800,27 @@ int rlrep_ldiff_update(rlrep_ldiff* h, const rlrep_ldiff_inputs* in, float* metr
   h->impl->update(x, metrics_host);
   RLREP_API_END
 }
+int rlrep_ldiff_update_resident(rlrep_ldiff* h, int n_steps, float stddev, float* total_ms) {
+  RLREP_API_BEGIN_ON(h)
+  RLREP_CHECK(h && total_ms, "null argument");
+  *total_ms = h->impl->update_resident(n_steps, stddev);
+  RLREP_API_END
+}
+int rlrep_ldiff_profile_update(rlrep_ldiff* h, float stddev, int max_entries, const char** names, float* ms, double* bytes,
+                               double* flops, int* n_entries) {
+  RLREP_API_BEGIN_ON(h)
+  RLREP_CHECK(h && n_entries && (max_entries == 0 || (names && ms)), "null argument");
+  std::vector<ProfileEntry> prof = h->impl->profile_update(stddev);
+  const int n = (int)std::min<size_t>(prof.size(), (size_t)max_entries);
+  for (int i = 0; i < n; ++i) {
+    names[i] = prof[i].name;
+    ms[i] = prof[i].ms;
+    if (bytes) bytes[i] = prof[i].bytes;
+    if (flops) flops[i] = prof[i].flops;
+  }
+  *n_entries = (int)prof.size();
+  RLREP_API_END
+}
 int rlrep_ldiff_last_launches(rlrep_ldiff* h, int* launches) {
   RLREP_API_BEGIN_ON(h)
   RLREP_CHECK(h && launches, "null argument");

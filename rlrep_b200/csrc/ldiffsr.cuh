@@ -63,6 +63,10 @@ class LatentDiffSR {
   };
   // metrics_out[8] = {recon_loss, kl_loss, score_loss, critic_loss, mean(q_pred), mean(q_target), mean(reward), actor_loss}
   void update(const Inputs& in, float* metrics_out);
+  // n_steps updates on the inputs the last update() left in HBM (bench.py's device-timed figure) -> total ms; one eager
+  // update with an event behind every launch (per-kernel profile)
+  float update_resident(int n_steps, float stddev);
+  std::vector<ProfileEntry> profile_update(float stddev);
   void sync_targets_from_params();
   std::vector<ParamGroup*> groups() {
     return {&enc_->group(), &vh_g_, &dec_->group(), &score_g_, &dead_g_, &actor_g_, &crit_g_};
