@@ -225,6 +225,7 @@ class GemmRunner {
   // true when the GEMM ran that way (the halo kernel), false when this GEMM does not qualify -- nothing was launched and
   // the caller runs it on the grid and compacts afterwards.
   bool run_compact(GemmArgs a, int wp, int ho, cudaStream_t s);
+  bool compact_supported(GemmArgs a, int wp, int ho);  // the same decision without launching anything
   // Share of the GPU the next GEMMs should plan for: 0.5 inside fork()/join() sections where two independent kernel
   // chains run on two streams, 1.0 elsewhere.  Part of the plan-cache key.
   void set_sm_share(double share) { sm_share_ = share; }

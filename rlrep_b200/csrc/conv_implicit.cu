@@ -44,6 +44,14 @@ __global__ void repack_flip_kernel(const float* __restrict__ W, int weights, flo
   w_flip[i] = weights == FC_CONV_DGRAD ? W[c * 288 + tap * 32 + n] : W[(tap * 32 + n) * 32 + c];
 }
 
+// w_rep[co, t * 32 + ci] = W[(t * 32 + co) * 32 + ci]: the transposed-conv weight [(ky, kx, co), ci] as nine K-major k-blocks
+__global__ void repack_deconv_kernel(const float* __restrict__ W, float* __restrict__ w_rep) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 32 * 288) return;
+  const int co = i / 288, r = i - co * 288, t = r >> 5, ci = r & 31;
+  w_rep[i] = W[(t * 32 + co) * 32 + ci];
+}
+
 // out[b, y, x] = grid[b, y, x] (y, x < Ho) * (mask > 0)
 __global__ void compact_grid_kernel(const float4* __restrict__ grid, int B, int Wp, int Ho, const float4* __restrict__ mask,
                                     float4* __restrict__ out) {
@@ -113,6 +121,48 @@ void conv3x3_wgrad_implicit(GemmRunner& g, cudaStream_t s, int B, int Hg, const 
   g.run(a, s);
   diag_tap_sum_kernel<<<ceil_div(32 * 288, 256), 256, 0, s>>>(sc.wfold, groups, dW, ld_dw, transposed ? 1 : 0);
   RLREP_LAUNCHED("diag_tap_sum", s);
+}
+
+bool deconv3x3_s2_forward(GemmRunner& g, cudaStream_t s, int B, int Hi, int Ho, const float* in, const float* W,
+                          const float* bias, float* out, FullCorrScratch& sc) {
+  const int Wp = Hi + 4;
+  const long long rows = (long long)B * Wp * Wp;
+  GemmArgs a;
+  a.M = (int)rows; a.N = 32; a.K = 288;
+  a.A = sc.padded; a.lda = 32; a.conv_w = Wp;
+  a.B = sc.w_flip; a.ldb = 288;
+  a.C = out; a.ldc = 32;
+  a.epi.bias = bias;
+  a.epi.act = ACT_RELU;
+  a.compact_stride = 2;
+  a.compact_out_w = Ho;
+  for (int par = 0; par < 4; ++par) {
+    const int py = par >> 1, px = par & 1;
+    GemmArgs c = a;
+    c.compact_oy = py; c.compact_ox = px;
+    const int hy = (Ho - py + 1) / 2, hx = (Ho - px + 1) / 2;  // outputs oy = 2 y + py < Ho
+    c.compact_hx = hx;
+    // taps: ky = py + 2 dy (dy = 0, 1 while ky <= 2) reads in[y - dy] = padded[y + 2 - dy]
+    int n = 0;
+    for (int dy = 0; py + 2 * dy <= 2; ++dy)
+      for (int dx = 0; px + 2 * dx <= 2; ++dx) {
+        c.conv_tap_shift[n] = (2 - dy) * Wp + (2 - dx);
+        c.conv_tap_kb[n] = (py + 2 * dy) * 3 + (px + 2 * dx);
+        ++n;
+      }
+    c.conv_ntaps = n;
+    if (par == 0) {
+      // probe first: nothing is launched (not even the padding pass) unless the halo kernel takes this GEMM
+      if (!g.compact_supported(c, Wp, hy)) return false;
+      pad_grid_kernel<<<grid_for(rows * 8, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(in), B, Hi,
+                                                             reinterpret_cast<float4*>(sc.padded));
+      RLREP_LAUNCHED_W("pad_grid", s, 4.0 * 32 * ((double)B * Hi * Hi + rows), 0.0);
+      repack_deconv_kernel<<<ceil_div(32 * 288, 256), 256, 0, s>>>(W, sc.w_flip);
+      RLREP_LAUNCHED("repack_deconv", s);
+    }
+    RLREP_CHECK(g.run_compact(c, Wp, hy, s), "stride-2 transposed convolution: the halo kernel refused a parity class");
+  }
+  return true;
 }
 
 void valid_conv_3x3_wt(GemmRunner& g, cudaStream_t s, int B, int Hi, const float* in, const float* W, const float* mask,

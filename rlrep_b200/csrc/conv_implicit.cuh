@@ -39,6 +39,15 @@ void full_correlation_3x3(GemmRunner& g, cudaStream_t s, int B, int Hi, const fl
 void conv3x3_wgrad_implicit(GemmRunner& g, cudaStream_t s, int B, int Hg, const float* small, const float* map, float* dW,
                             int ld_dw, bool transposed, FullCorrScratch& scratch);
 
+// Forward pass of a STRIDE-2 3x3 transposed convolution (+ bias + ReLU) without the [rows, 288] column matrix:
+//   out[b, oy, ox, co] = relu(bias[co] + sum over (ky, kx) with oy - ky = 2 iy, ox - kx = 2 ix of in[b, iy, ix, :] . W[(ky, kx, co), :])
+// in [B, Hi, Hi, 32], out [B, Ho, Ho, 32] (Ho = 2 Hi + 1 or 2 Hi + 2), W [288, 32] = [(ky, kx, co), ci].  The four output
+// parity classes (oy % 2, ox % 2) are four stride-1 problems with 4 / 2 / 2 / 1 taps on the zero-padded input grid: four
+// launches of the halo kernel with a tap list and a stride-2 compacting store.  Returns false (nothing launched) when the
+// halo kernel does not take this shape / precision: the caller falls back to GEMM + col2im.
+bool deconv3x3_s2_forward(GemmRunner& g, cudaStream_t s, int B, int Hi, int Ho, const float* in, const float* W,
+                          const float* bias, float* out, FullCorrScratch& scratch);
+
 // Valid 3x3 convolution of dY-like maps with MN-major weights, for the data gradient of a stride-1 transposed convolution:
 // out[b, y, x, n] = (mask > 0) * sum_{ky, kx, c} in[b, y + ky, x + kx, c] * W[(ky * 3 + kx) * 32 + c, n], W [288, 32].
 void valid_conv_3x3_wt(GemmRunner& g, cudaStream_t s, int B, int Hi, const float* in, const float* W, const float* mask,

@@ -391,7 +391,7 @@ ConvDecoder::ConvDecoder(int batch, Precision prec, cudaStream_t s, int out_kern
   arena_.want(&bias_partial_, kBiasChunks * 32);
   arena_.want(&wfold_, (size_t)288 * kFold * 32 * kFold);
   implicit_fwd_ = !(std::getenv("RLREP_CONV_V1") && std::atoi(std::getenv("RLREP_CONV_V1")) != 0);
-  if (implicit_fwd_) corr_.want(arena_, B_, hw_[2]);
+  if (implicit_fwd_) corr_.want(arena_, B_, hw_[3]);  // grids up to (hw_[3] + 4)^2: the stride-2 layer's padded input
   // the stride-1 layers' backward pass without column matrices (TF32 path); RLREP_CONV_WGRAD_V1=1 keeps im2col + folded GEMM
   implicit_bwd_ = implicit_fwd_ && prec == PREC_TF32 && B_ % 4 == 0 &&
                   !(std::getenv("RLREP_CONV_WGRAD_V1") && std::atoi(std::getenv("RLREP_CONV_WGRAD_V1")) != 0);
@@ -422,6 +422,9 @@ void ConvDecoder::forward(const float* x_dev, int ld_x) {
                            act_[l + 1], corr_);
       continue;
     }
+    if (implicit_fwd_ && l == 3 &&
+        deconv3x3_s2_forward(gemm_, s, B_, Hi, Ho, act_[l], g_.p + w_off_[l], g_.p + b_off_[l], act_[l + 1], corr_))
+      continue;  // stride 2: four parity classes on the halo kernel, no [rows, 288] matrix
     linear_fwd(gemm_, s, (int)rows(l), Mat{act_[l], 32}, layer(l), ACT_NONE, col_, 288);
     const float4* colT = reinterpret_cast<const float4*>(col_);
     const float4* bias = reinterpret_cast<const float4*>(g_.p + b_off_[l]);

@@ -74,6 +74,14 @@ struct GemmArgs {
   // compact_wp wide; only rows with x < compact_ho and y < compact_ho are stored, at row (b * ho + y) * ho + x of C -- and
   // of epi.aux / epi.pre_out, which are indexed by the compact row too.
   int compact_wp = 0, compact_ho = 0;
+  // Generalisations used by the stride-2 transposed convolution (one launch per output parity class): the valid extent in x
+  // (0: compact_ho), an output stride / offset -- grid (b, y, x) goes to output row (b * out_w + s*y + oy) * out_w + s*x + ox
+  // (out_w = 0: compact_ho) -- and a subset / reordering of the nine taps: tap i reads rows shifted by conv_tap_shift[i]
+  // and multiplies by weight k-block conv_tap_kb[i] (conv_ntaps = 0: the nine taps (ky, kx) -> shift ky * conv_w + kx).
+  int compact_hx = 0, compact_stride = 1, compact_oy = 0, compact_ox = 0, compact_out_w = 0;
+  int conv_ntaps = 0;
+  int conv_tap_shift[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int conv_tap_kb[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   // K groups (tensor-core path, one tile per CTA): the K range is cut into k_groups parts, each reduced by its own split-K
   // cluster into its own output matrix -- k_groups matrices of ceil(M / 128) * 128 rows (pitch ldc) behind each other at C,
   // which the caller sums.  For GEMMs with K ~ 1e5 and a handful of tiles, where a cluster's 8 CTAs are not enough.

@@ -701,14 +701,30 @@ gemm_tf32_persistent_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 // record).  The 36 KB of weights are loaded once per CTA and stay resident.
 // N <= 32 (every convolution of the pixel agents has 32 output channels), A K-major.
 // Rows of a 32 x 16 accumulator chunk staged in tw[32][20]: lane = (row group of 8, 16-byte piece), four passes
+// Output mapping and tap list of a halo-kernel launch (GemmArgs::compact_* / conv_tap_*), by value
+struct HaloGeom {
+  int wp, hy, hx, stride, oy, ox, out_w;  // wp = 0: no compaction (rows stored where they are)
+  int ntaps;
+  int shift[9], kb[9];
+};
+
 // wp > 0: compacting store -- grid row m = (b, y, x) on a grid wp wide goes to row (b * ho + y) * ho + x when x, y < ho and
 // nowhere otherwise (the thread's first row is decomposed once per tile, the other three follow by carrying 8 columns).
 // The epilogue of this kernel is bias + activation + derivative mask only (checked by the launcher); the four rows' mask
 // values are fetched as float4 BEFORE the first store -- behind a store the compiler cannot hoist them (aliasing), and four
 // serialised global-load latencies per tile made this epilogue the slowest stage of the pipeline.
-template <int ACT, int DACT>
-__device__ __forceinline__ void halo_store_rows16(const Epilogue& epi, const float* tw, float* __restrict__ C, int ldc,
-                                                  int M, int m_base, int gn0, int lane, int wp, int ho) {
+// Split in two so that the row mapping and the mask / bias loads are issued BEFORE the thread waits for the accumulator
+// (they depend on the tile index only): the loads' latency hides behind the MMAs of the tile.
+struct HaloRows {
+  int row_of[4];
+  bool live[4];
+  float4 ax[4];
+  float4 bv;
+  bool use_aux;
+};
+__device__ __forceinline__ void halo_rows_prepare(HaloRows& hr, const Epilogue& epi, int M, int m_base, int gn0, int lane,
+                                                  const HaloGeom& geo) {
+  const int wp = geo.wp;
   const int piece = lane & 3, rsub = lane >> 2;
   const int on = gn0 + 4 * piece;
   int gb = 0, gy = 0, gx = 0;
@@ -722,43 +738,47 @@ __device__ __forceinline__ void halo_store_rows16(const Epilogue& epi, const flo
     gx = rem - gy * wp;
     if (gx < 0) { --gy; gx += wp; } else if (gx >= wp) { ++gy; gx -= wp; }
   }
-  int row_of[4];
-  bool live[4];
 #pragma unroll
   for (int r4 = 0; r4 < 4; ++r4) {
     const int om = m_base + r4 * 8 + rsub;
-    live[r4] = om < M;
-    row_of[r4] = om;
+    hr.live[r4] = om < M;
+    hr.row_of[r4] = om;
     if (wp > 0) {
-      live[r4] = live[r4] && gx < ho && gy < ho;
-      row_of[r4] = (gb * ho + gy) * ho + gx;
+      hr.live[r4] = hr.live[r4] && gx < geo.hx && gy < geo.hy;
+      hr.row_of[r4] = (gb * geo.out_w + geo.stride * gy + geo.oy) * geo.out_w + geo.stride * gx + geo.ox;
       gx += 8;  // wp > 8: at most one wrap
       if (gx >= wp) { gx -= wp; ++gy; }
       if (gy >= wp) { gy -= wp; ++gb; }
     }
   }
-  constexpr bool kRuntime = ACT < 0 || DACT < 0;
-  const bool use_aux = kRuntime ? epi.dact != DACT_NONE : DACT != DACT_NONE;
-  float4 ax[4];
+  hr.use_aux = epi.dact != DACT_NONE;
 #pragma unroll
   for (int r4 = 0; r4 < 4; ++r4)
-    ax[r4] = (use_aux && live[r4]) ? __ldg(reinterpret_cast<const float4*>(epi.aux + (size_t)row_of[r4] * epi.ld_aux + on))
-                                   : make_float4(1.f, 1.f, 1.f, 1.f);
-  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (epi.bias) bv = __ldg(reinterpret_cast<const float4*>(epi.bias + on));
+    hr.ax[r4] = (hr.use_aux && hr.live[r4])
+                    ? __ldg(reinterpret_cast<const float4*>(epi.aux + (size_t)hr.row_of[r4] * epi.ld_aux + on))
+                    : make_float4(1.f, 1.f, 1.f, 1.f);
+  hr.bv = epi.bias ? __ldg(reinterpret_cast<const float4*>(epi.bias + on)) : make_float4(0.f, 0.f, 0.f, 0.f);
+}
+template <int ACT, int DACT>
+__device__ __forceinline__ void halo_rows_finish(const HaloRows& hr, const Epilogue& epi, const float* tw,
+                                                 float* __restrict__ C, int ldc, int gn0, int lane) {
+  const int piece = lane & 3, rsub = lane >> 2;
+  const int on = gn0 + 4 * piece;
+  constexpr bool kRuntime = ACT < 0 || DACT < 0;
   const int act = kRuntime ? epi.act : ACT, dact = kRuntime ? epi.dact : DACT;
 #pragma unroll
   for (int r4 = 0; r4 < 4; ++r4) {
-    if (!live[r4]) continue;
+    if (!hr.live[r4]) continue;
     const float4 a4 = *reinterpret_cast<const float4*>(tw + (r4 * 8 + rsub) * 20 + 4 * piece);
-    float o[4] = {fmaf(a4.x, epi.scale, bv.x), fmaf(a4.y, epi.scale, bv.y), fmaf(a4.z, epi.scale, bv.z), fmaf(a4.w, epi.scale, bv.w)};
-    const float h[4] = {ax[r4].x, ax[r4].y, ax[r4].z, ax[r4].w};
+    float o[4] = {fmaf(a4.x, epi.scale, hr.bv.x), fmaf(a4.y, epi.scale, hr.bv.y), fmaf(a4.z, epi.scale, hr.bv.z),
+                  fmaf(a4.w, epi.scale, hr.bv.w)};
+    const float h[4] = {hr.ax[r4].x, hr.ax[r4].y, hr.ax[r4].z, hr.ax[r4].w};
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       o[e] = apply_act(o[e], act);
-      if (use_aux) o[e] *= apply_dact(h[e], dact);
+      if (hr.use_aux) o[e] *= apply_dact(h[e], dact);
     }
-    *reinterpret_cast<float4*>(C + (size_t)row_of[r4] * ldc + on) = make_float4(o[0], o[1], o[2], o[3]);
+    *reinterpret_cast<float4*>(C + (size_t)hr.row_of[r4] * ldc + on) = make_float4(o[0], o[1], o[2], o[3]);
   }
 }
 
@@ -776,8 +796,8 @@ __device__ __forceinline__ uint64_t smem_desc_sw128_rows(uint32_t addr, uint32_t
 template <bool B_MN>
 __global__ void __launch_bounds__(kHaloThreads, 1)
 gemm_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                      float* __restrict__ C, int ldc, int M, int N, int conv_w, int halo_rows, int flags, int compact_wp,
-                      int compact_ho, const Epilogue epi) {
+                      float* __restrict__ C, int ldc, int M, int N, int halo_rows, int flags, const HaloGeom geo,
+                      const Epilogue epi) {
   constexpr int BN = 32;
   constexpr int B_BYTES = BN * BK * 4;
   constexpr uint32_t TMEM_COLS = 2 * BN;
@@ -837,6 +857,15 @@ gemm_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_tf32(BM, BN, false, B_MN);
       ptx::mbar_wait(w_bar, 0);
+      // the tap list in registers (static indexing of the parameter arrays): a run-time-indexed constant load per tap in
+      // front of every MMA group cost the issuing thread ~20 us per launch
+      uint32_t tap_a[9], tap_b[9];
+#pragma unroll
+      for (int tap = 0; tap < 9; ++tap) {
+        tap_a[tap] = (uint32_t)geo.shift[tap] * 128u;
+        tap_b[tap] = (uint32_t)geo.kb[tap] * (uint32_t)B_BYTES;
+      }
+      const int ntaps = geo.ntaps;
       int it = 0;
       for (int t = blockIdx.x; t < total; t += gridDim.x, ++it) {
         const int acc = it & 1, s = it % kHaloStages;
@@ -845,11 +874,11 @@ gemm_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         ptx::tc_fence_after_sync();
         const uint32_t d_tmem = tmem_base + acc * BN;
         const uint32_t a_base = ptx::smem_u32(sA + s * kHaloBytes), b_base = ptx::smem_u32(sB);
-#pragma unroll 1
+#pragma unroll
         for (int tap = 0; tap < 9; ++tap) {
-          const uint32_t shift = (tap / 3) * conv_w + (tap % 3);
-          const uint32_t a_addr = a_base + shift * 128, b_addr = b_base + tap * B_BYTES;
-          const uint32_t bo = (flags & 1) ? (shift & 7u) : 0u;
+          if (tap >= ntaps) break;
+          const uint32_t a_addr = a_base + tap_a[tap], b_addr = b_base + tap_b[tap];
+          const uint32_t bo = (flags & 1) ? ((tap_a[tap] >> 7) & 7u) : 0u;
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             const uint64_t adesc = smem_desc_sw128_rows(a_addr + k * UMMA_K * 4, bo);
@@ -872,31 +901,34 @@ gemm_conv_halo_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
     for (int t = blockIdx.x; t < total; t += gridDim.x, ++tc) {
       const int acc = tc & 1;
       const int m0 = t * BM;
+      const int gm = m0 + 32 * q + lane, gn0 = 16 * half;
+      const bool fast = vec_ok && N == 32;
+      HaloRows hr;
+      if (fast) halo_rows_prepare(hr, epi, M, m0 + 32 * q, gn0, lane, geo);  // mask / bias loads in flight during the MMAs
       ptx::mbar_wait(&acc_full[acc], (tc >> 1) & 1);
       ptx::tc_fence_after_sync();
-      const int gm = m0 + 32 * q + lane, gn0 = 16 * half;
       uint32_t v[16];
       ptx::tmem_ld_32x32b_x16(tmem_base + (static_cast<uint32_t>(32 * q) << 16) + acc * BN + gn0, v);
       ptx::tmem_ld_wait();
-      if (vec_ok && N == 32) {
+      if (fast) {
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           *reinterpret_cast<float4*>(tw + lane * 20 + 4 * j) =
               make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]),
                           __uint_as_float(v[4 * j + 3]));
         __syncwarp();
-#define RLREP_HSTORE(A, D) halo_store_rows16<A, D>(epi, tw, C, ldc, M, m0 + 32 * q, gn0, lane, compact_wp, compact_ho)
+#define RLREP_HSTORE(A, D) halo_rows_finish<A, D>(hr, epi, tw, C, ldc, gn0, lane)
         RLREP_EPILOGUE_SWITCH(epi, RLREP_HSTORE);
 #undef RLREP_HSTORE
         __syncwarp();
       } else if (gm < M) {
         int om = gm;
         bool live = true;
-        if (compact_wp > 0) {
-          const int gb = gm / (compact_wp * compact_wp), rem = gm - gb * compact_wp * compact_wp;
-          const int gy = rem / compact_wp, gx = rem - gy * compact_wp;
-          live = gx < compact_ho && gy < compact_ho;
-          om = (gb * compact_ho + gy) * compact_ho + gx;
+        if (geo.wp > 0) {
+          const int gb = gm / (geo.wp * geo.wp), rem = gm - gb * geo.wp * geo.wp;
+          const int gy = rem / geo.wp, gx = rem - gy * geo.wp;
+          live = gx < geo.hx && gy < geo.hy;
+          om = (gb * geo.out_w + geo.stride * gy + geo.oy) * geo.out_w + geo.stride * gx + geo.ox;
         }
         if (live) {
           float* crow = C + (size_t)om * ldc;
@@ -928,8 +960,21 @@ void launch_conv_halo(const TcGemmPlan& p, cudaStream_t stream) {
   }();
   const GemmArgs& a = p.args;
   const int tiles = ceil_div(a.M, BM);
-  kern<<<std::min(tiles, kNumSMs), kHaloThreads, kHaloSmem, stream>>>(p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, a.conv_w,
-                                                                       p.halo_rows, flags, a.compact_wp, a.compact_ho, a.epi);
+  HaloGeom geo;
+  geo.wp = a.compact_wp;
+  geo.hy = a.compact_ho;
+  geo.hx = a.compact_hx > 0 ? a.compact_hx : a.compact_ho;
+  geo.stride = a.compact_stride; geo.oy = a.compact_oy; geo.ox = a.compact_ox;
+  geo.out_w = a.compact_out_w > 0 ? a.compact_out_w : a.compact_ho;
+  geo.ntaps = a.conv_ntaps > 0 ? a.conv_ntaps : 9;
+  for (int t = 0; t < 9; ++t) {
+    geo.shift[t] = a.conv_ntaps > 0 ? a.conv_tap_shift[t] : (t / 3) * a.conv_w + (t % 3);
+    geo.kb[t] = a.conv_ntaps > 0 ? a.conv_tap_kb[t] : t;
+    RLREP_CHECK(t >= geo.ntaps || (geo.shift[t] >= 0 && geo.shift[t] + 128 <= p.halo_rows && geo.kb[t] >= 0 && geo.kb[t] < 9),
+                "halo convolution: tap outside the halo buffer");
+  }
+  kern<<<std::min(tiles, kNumSMs), kHaloThreads, kHaloSmem, stream>>>(p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, p.halo_rows, flags,
+                                                                       geo, a.epi);
   RLREP_LAUNCHED_W("gemm_conv_halo", stream, 4.0 * ((double)a.M * 32 + (double)a.N * a.K + (double)a.M * a.N),
                    2.0 * a.M * a.N * a.K);
 }
@@ -952,7 +997,7 @@ void launch_variant_persistent(const TcGemmPlan& p, cudaStream_t stream) {
     attr_set = true;
   }
   const GemmArgs& a = p.args;
-  RLREP_CHECK(a.compact_wp == 0, "compacting stores exist on the halo convolution kernel only");
+  RLREP_CHECK(a.compact_wp == 0 && a.conv_ntaps == 0, "compacting stores / tap lists exist on the halo convolution kernel only");
   const int tiles = ceil_div(a.M, BM) * ceil_div(a.N, BN);
   kern<<<std::min(tiles, kNumSMs), kPersistThreads, smem_bytes(BN) + 4 * 32 * 36 * 4, stream>>>(p.tmA, p.tmB, a.C, a.ldc, a.M, a.N, a.K, a.conv_w, a.epi, g_persist_dbg);
   RLREP_LAUNCHED_W("gemm_tf32_persistent", stream,
@@ -999,7 +1044,7 @@ void fill_launch_config(cudaLaunchConfig_t& cfg, cudaLaunchAttribute* attr, dim3
 template <int BN, bool A_MN, bool B_MN>
 void launch_variant(const TcGemmPlan& p, cudaStream_t stream) {
   const GemmArgs& a = p.args;
-  RLREP_CHECK(a.compact_wp == 0, "compacting stores exist on the halo convolution kernel only");
+  RLREP_CHECK(a.compact_wp == 0 && a.conv_ntaps == 0, "compacting stores / tap lists exist on the halo convolution kernel only");
   RLREP_CHECK(p.stages >= (p.push ? 2 : min_stages(BN)) && p.stages <= num_stages(BN), "bad pipeline depth");
   RLREP_CHECK(!p.push || (p.split_k > 1 && smem_bytes(BN, p.stages, true) <= kMaxSmem), "bad push-mode plan");
   cudaLaunchConfig_t cfg;

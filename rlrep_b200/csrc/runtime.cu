@@ -211,14 +211,19 @@ void GemmRunner::end_chain() {
   recording_ = false;
 }
 
-bool GemmRunner::run_compact(GemmArgs a, int wp, int ho, cudaStream_t s) {
+bool GemmRunner::compact_supported(GemmArgs a, int wp, int ho) {
   if (recording_ || prec_ != PREC_TF32 || !tc_eligible(a) || a.conv_w <= 0 || a.M < 32 || a.N != 32 || wp <= 8 ||
       a.M >= (1 << 24))
     return false;
   a.compact_wp = wp;
   a.compact_ho = ho;
   const TcGemmPlan probe = make_tc_plan(a, 0, 0, ws_, ws_floats_, sm_share_);  // cheap: cost model + two tensor maps
-  if (probe.halo_rows <= 0) return false;
+  return probe.halo_rows > 0;
+}
+bool GemmRunner::run_compact(GemmArgs a, int wp, int ho, cudaStream_t s) {
+  if (!compact_supported(a, wp, ho)) return false;
+  a.compact_wp = wp;
+  a.compact_ho = ho;
   run(a, s);
   return true;
 }
@@ -249,6 +254,9 @@ void GemmRunner::run(const GemmArgs& a, cudaStream_t s) {
     k->B = a.B; k->ldb = a.ldb; k->b_mn = a.b_mn;
     k->C = a.C; k->ldc = a.ldc; k->conv_w = a.conv_w; k->conv_wgrad_hi = a.conv_wgrad_hi;
     k->compact_wp = a.compact_wp; k->compact_ho = a.compact_ho; k->k_groups = a.k_groups;
+    k->compact_hx = a.compact_hx; k->compact_stride = a.compact_stride; k->compact_oy = a.compact_oy;
+    k->compact_ox = a.compact_ox; k->compact_out_w = a.compact_out_w; k->conv_ntaps = a.conv_ntaps;
+    for (int t = 0; t < 9; ++t) { k->conv_tap_shift[t] = a.conv_tap_shift[t]; k->conv_tap_kb[t] = a.conv_tap_kb[t]; }
     k->epi.bias = a.epi.bias; k->epi.r1_u = a.epi.r1_u; k->epi.r1_v = a.epi.r1_v; k->epi.aux = a.epi.aux;
     k->epi.pre_out = a.epi.pre_out; k->epi.ld_aux = a.epi.ld_aux; k->epi.ld_pre = a.epi.ld_pre;
     k->epi.act = a.epi.act; k->epi.dact = a.epi.dact; k->epi.accumulate = a.epi.accumulate;
