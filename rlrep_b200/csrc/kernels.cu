@@ -917,10 +917,16 @@ __global__ void __launch_bounds__(256) vae_kl_bwd_kernel(const float* __restrict
 __global__ void vae_finalize_kernel(const float* __restrict__ recon_partial, int n_recon,
                                     const float* __restrict__ kl_partial, int n_kl, int B, int S, int D,
                                     float* __restrict__ metrics) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  // one warp: lane l adds partials l, l + 32, ... in order, then a fixed shuffle tree (a single thread walking 3 x 296
+  // partials was 5+ us at the tail of every feature step)
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
   float se_s = 0.f, se_r = 0.f, kl = 0.f;
-  for (int i = 0; i < n_recon; ++i) { se_s += recon_partial[2 * i]; se_r += recon_partial[2 * i + 1]; }
-  for (int i = 0; i < n_kl; ++i) kl += kl_partial[i];
+  for (int i = threadIdx.x; i < n_recon; i += 32) { se_s += recon_partial[2 * i]; se_r += recon_partial[2 * i + 1]; }
+  for (int i = threadIdx.x; i < n_kl; i += 32) kl += kl_partial[i];
+  se_s = warp_sum(se_s);
+  se_r = warp_sum(se_r);
+  kl = warp_sum(kl);
+  if (threadIdx.x != 0) return;
   const float s_loss = 0.5f * (se_s / ((float)B * (float)S));
   const float r_loss = 0.5f * (se_r / (float)B);
   const float ml = r_loss + s_loss;
@@ -932,6 +938,25 @@ __global__ void vae_finalize_kernel(const float* __restrict__ recon_partial, int
   metrics[4] = r_loss;
 }
 
+// x[(b, j), d] = mean[b, d] + exp(clamp(log_std[b, d])) * noise[j, d].  One thread per (b, four columns): the head is read and
+// exponentiated once and the NN rows are written as float4 (per element with 64-bit div / mod and NN x the expf this
+// took 21 us for a 21 MB write); the scalar kernel keeps unaligned shapes.
+__global__ void noise_expand4_kernel(const float* __restrict__ head, int ld_head, int B, int D,
+                                     const float* __restrict__ noise, int NN, float* __restrict__ x) {
+  const int D4 = D >> 2, total = B * D4;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int b = i / D4, d = (i - b * D4) << 2;
+    const float* h = head + (size_t)b * ld_head;
+    const float4 m = *reinterpret_cast<const float4*>(h + d);
+    const float4 r = *reinterpret_cast<const float4*>(h + D + d);
+    const float4 sd = make_float4(expf(clamp_ls(r.x)), expf(clamp_ls(r.y)), expf(clamp_ls(r.z)), expf(clamp_ls(r.w)));
+    float4* out = reinterpret_cast<float4*>(x + ((size_t)b * NN) * D + d);
+    for (int j = 0; j < NN; ++j) {
+      const float4 n = __ldg(reinterpret_cast<const float4*>(noise + (size_t)j * D + d));
+      out[(size_t)j * D4] = make_float4(m.x + sd.x * n.x, m.y + sd.y * n.y, m.z + sd.z * n.z, m.w + sd.w * n.w);
+    }
+  }
+}
 __global__ void noise_expand_kernel(const float* __restrict__ head, int ld_head, int B, int D,
                                     const float* __restrict__ noise, int NN, float* __restrict__ x) {
   const size_t total = (size_t)B * NN * D;
@@ -1189,7 +1214,10 @@ void launch_vae_finalize(const float* recon_partial, int n_recon, const float* k
 }
 void launch_noise_expand(const float* head, int ld_head, int B, int D, const float* noise, int NN, float* x,
                          cudaStream_t s) {
-  noise_expand_kernel<<<grid_for((size_t)B * NN * D, 256, 16), 256, 0, s>>>(head, ld_head, B, D, noise, NN, x);
+  const bool vec = (D & 3) == 0 && (ld_head & 3) == 0 && (long long)B * NN * D < (1LL << 31) &&
+                   ((reinterpret_cast<uintptr_t>(head) | reinterpret_cast<uintptr_t>(noise) | reinterpret_cast<uintptr_t>(x)) & 15) == 0;
+  if (vec) noise_expand4_kernel<<<grid_for((size_t)B * (D / 4), 256, 16), 256, 0, s>>>(head, ld_head, B, D, noise, NN, x);
+  else noise_expand_kernel<<<grid_for((size_t)B * NN * D, 256, 16), 256, 0, s>>>(head, ld_head, B, D, noise, NN, x);
   RLREP_LAUNCHED("noise_expand", s);
 }
 void launch_noise_expand_bwd(const float* dx, const float* head, int ld_head, int B, int D, const float* noise, int NN,
