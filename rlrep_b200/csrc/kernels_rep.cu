@@ -13,26 +13,43 @@ namespace {
 
 // ------------------------------------------------------------------------------------------- SPEDER
 // One warp per row i < B: diag_i = <phi_i, mu_i>, rpred_i = <phi_i, theta> + b, c_i = <mu~_i, u>.
-__global__ void speder_rows_kernel(const float* __restrict__ zphi, const float* __restrict__ zmu, int D, int B,
-                                   const float* __restrict__ theta_w, const float* __restrict__ theta_b,
-                                   const float* __restrict__ u, float* __restrict__ diag, float* __restrict__ rpred,
-                                   float* __restrict__ c) {
-  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (row >= B) return;
+// One CTA per row (a warp per row left 32 SMs with 64 dependent scalar iterations each: 21 us at B = 256, D = 2048): float4
+// loads, three block sums in a fixed order.
+__global__ void __launch_bounds__(256) speder_rows_kernel(const float* __restrict__ zphi, const float* __restrict__ zmu,
+                                                          int D, int B, const float* __restrict__ theta_w,
+                                                          const float* __restrict__ theta_b, const float* __restrict__ u,
+                                                          float* __restrict__ diag, float* __restrict__ rpred,
+                                                          float* __restrict__ c) {
+  __shared__ float scratch[33];
+  const int row = blockIdx.x, tid = threadIdx.x;
   const float* p = zphi + (size_t)row * D;
   const float* m = zmu + (size_t)row * D;
   const float* mr = zmu + (size_t)(B + row) * D;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-  for (int j = lane; j < D; j += 32) {
-    const float pj = p[j];
-    a0 = fmaf(pj, m[j], a0);
-    a1 = fmaf(pj, __ldg(theta_w + j), a1);
-    a2 = fmaf(mr[j], u[j], a2);
+  const bool vec = (D & 3) == 0 && ((reinterpret_cast<uintptr_t>(zphi) | reinterpret_cast<uintptr_t>(zmu) |
+                                     reinterpret_cast<uintptr_t>(theta_w) | reinterpret_cast<uintptr_t>(u)) & 15) == 0;
+  if (vec) {
+    const float4 *p4 = reinterpret_cast<const float4*>(p), *m4 = reinterpret_cast<const float4*>(m),
+                 *r4 = reinterpret_cast<const float4*>(mr), *t4 = reinterpret_cast<const float4*>(theta_w),
+                 *u4 = reinterpret_cast<const float4*>(u);
+    for (int j = tid; j < D / 4; j += 256) {
+      const float4 pv = p4[j], mv = m4[j], rv = r4[j], tv = __ldg(t4 + j), uv = u4[j];
+      a0 = fmaf(pv.x, mv.x, fmaf(pv.y, mv.y, fmaf(pv.z, mv.z, fmaf(pv.w, mv.w, a0))));
+      a1 = fmaf(pv.x, tv.x, fmaf(pv.y, tv.y, fmaf(pv.z, tv.z, fmaf(pv.w, tv.w, a1))));
+      a2 = fmaf(rv.x, uv.x, fmaf(rv.y, uv.y, fmaf(rv.z, uv.z, fmaf(rv.w, uv.w, a2))));
+    }
+  } else {
+    for (int j = tid; j < D; j += 256) {
+      const float pj = p[j];
+      a0 = fmaf(pj, m[j], a0);
+      a1 = fmaf(pj, __ldg(theta_w + j), a1);
+      a2 = fmaf(mr[j], u[j], a2);
+    }
   }
-  a0 = warp_sum(a0);
-  a1 = warp_sum(a1);
-  a2 = warp_sum(a2);
-  if (lane == 0) {
+  a0 = block_sum<256>(a0, scratch);
+  a1 = block_sum<256>(a1, scratch);
+  a2 = block_sum<256>(a2, scratch);
+  if (tid == 0) {
     diag[row] = a0;
     rpred[row] = a1 + __ldg(theta_b);
     c[row] = a2;
@@ -181,7 +198,7 @@ __global__ void __launch_bounds__(256) sum_scaled_kernel(const float* __restrict
 
 void launch_speder_rows(const float* zphi, const float* zmu, int D, int B, const float* theta_w, const float* theta_b,
                         const float* u, float* diag, float* rpred, float* c, cudaStream_t s) {
-  speder_rows_kernel<<<ceil_div(B * 32, 256), 256, 0, s>>>(zphi, zmu, D, B, theta_w, theta_b, u, diag, rpred, c);
+  speder_rows_kernel<<<B, 256, 0, s>>>(zphi, zmu, D, B, theta_w, theta_b, u, diag, rpred, c);
   RLREP_LAUNCHED("speder_rows", s);
 }
 void launch_speder_finalize(const float* diag, const float* c, const float* rpred, const float* reward, int ld_r, int B,
