@@ -12,6 +12,7 @@
 //     gradient = a GEMM whose B operand reads the input map through a shifted 4-D TMA view (GemmArgs::conv_wgrad_hi).
 //   * strict-fp32 mode and RLREP_CONV_V1 / RLREP_CONV_WGRAD_V1: round 1's explicit im2col / folded-GEMM / col2im lowering.
 #include "conv.cuh"
+#include "layout.cuh"
 
 #include <cstdlib>
 
@@ -99,29 +100,6 @@ __global__ void col2im_nhwc32_kernel(const float4* __restrict__ dcol, const floa
   }
 }
 
-// NHWC [B, P, 32] <-> the reference's flatten order [B, 32, P] (P = Ho*Ho); the backward direction also applies the
-// ReLU mask of the last layer.
-__global__ void nhwc_to_nchw_kernel(const float* __restrict__ in, int B, int P, float* __restrict__ out, long long ld) {
-  const long long total = (long long)B * P * 32;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int p = (int)(i % P);
-    const int c = (int)((i / P) % 32);
-    const long long b = i / ((long long)P * 32);
-    out[b * ld + (long long)c * P + p] = in[(b * P + p) * 32 + c];
-  }
-}
-__global__ void nchw_to_nhwc_relu_bwd_kernel(const float* __restrict__ dfeat, long long ld, const float* __restrict__ act,
-                                             int B, int P, float* __restrict__ dact) {
-  const long long total = (long long)B * P * 32;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i & 31);
-    const long long bp = i >> 5;
-    const int p = (int)(bp % P);
-    const long long b = bp / P;
-    dact[i] = act[i] > 0.f ? dfeat[b * ld + (long long)c * P + p] : 0.f;
-  }
-}
-
 // dW[o, k] = sum_p C[p*32 + o, p*ldk + k]: the diagonal blocks of the folded weight-gradient GEMM (see backward())
 __global__ void diag_block_sum_kernel(const float* __restrict__ C, int ldc, int P, int ldk, float* __restrict__ dW,
                                       int ld_dw) {
@@ -195,16 +173,14 @@ void ConvEncoder::forward(const unsigned char* obs_dev, const int* shifts_dev, f
     linear_fwd(gemm_, s, (int)rows(l), Mat{col_[l], 288}, conv_[l].view(g_, target), ACT_RELU, act_[l], 32);
   }
   const int P = hw_[3] * hw_[3];
-  nhwc_to_nchw_kernel<<<grid_for((long long)B_ * P * 32, 256), 256, 0, s>>>(act_[3], B_, P, feat_dev,
-                                                                              ld_feat > 0 ? ld_feat : (long long)P * 32);
+  launch_nhwc_to_cp(act_[3], B_, P, feat_dev, ld_feat > 0 ? ld_feat : (long long)P * 32, s);
   RLREP_LAUNCHED_W("nhwc_to_nchw", s, 8.0 * B_ * P * 32, 0.0);
 }
 
 void ConvEncoder::backward(const float* dfeat_dev, int ld_dfeat) {
   cudaStream_t s = stream_;
   const int P = hw_[3] * hw_[3];
-  nchw_to_nhwc_relu_bwd_kernel<<<grid_for((long long)B_ * P * 32, 256), 256, 0, s>>>(
-      dfeat_dev, ld_dfeat > 0 ? ld_dfeat : (long long)P * 32, act_[3], B_, P, dact_[3]);
+  launch_cp_to_nhwc(dfeat_dev, ld_dfeat > 0 ? ld_dfeat : (long long)P * 32, B_, P, /*mask=*/act_[3], dact_[3], s);
   RLREP_LAUNCHED_W("nchw_to_nhwc_relu_bwd", s, 12.0 * B_ * P * 32, 0.0);
   for (int l = 3; l >= 0; --l) {
     const Linear w = conv_[l].view(g_);

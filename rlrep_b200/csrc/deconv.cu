@@ -9,6 +9,7 @@
 // API).  The 3-channel output layer is a direct CUDA-core kernel (384 FMAs per pixel) fused with nothing; its weight
 // gradient is a two-pass deterministic reduction.
 #include "deconv.cuh"
+#include "layout.cuh"
 
 #include <cstdlib>
 
@@ -23,27 +24,6 @@ namespace {
 int grid_for(long long work, int threads) {
   const long long want = (work + threads - 1) / threads;
   return (int)std::max<long long>(1, std::min<long long>(want, (long long)kNumSMs * 16));
-}
-
-// [B, 32, P] (row pitch ld) -> NHWC [B, P, 32]
-__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, long long ld, int B, int P, float* __restrict__ out) {
-  const long long total = (long long)B * P * 32;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(i & 31);
-    const long long bp = i >> 5;
-    const int p = (int)(bp % P);
-    const long long b = bp / P;
-    out[i] = in[b * ld + (long long)c * P + p];
-  }
-}
-__global__ void nhwc_to_nchw_pitch_kernel(const float* __restrict__ in, int B, int P, float* __restrict__ out, long long ld) {
-  const long long total = (long long)B * P * 32;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int p = (int)(i % P);
-    const int c = (int)((i / P) % 32);
-    const long long b = i / ((long long)P * 32);
-    out[b * ld + (long long)c * P + p] = in[(b * P + p) * 32 + c];
-  }
 }
 
 // Y[b, y, x, co] = relu(bias[co] + sum over taps with (y - ky) = S*iy, (x - kx) = S*ix of colT[(b, iy, ix), tap, co])
@@ -412,8 +392,7 @@ Linear ConvDecoder::layer(int l) const {
 void ConvDecoder::forward(const float* x_dev, int ld_x) {
   cudaStream_t s = stream_;
   const int P0 = hw_[0] * hw_[0];
-  nchw_to_nhwc_kernel<<<grid_for((long long)B_ * P0 * 32, 256), 256, 0, s>>>(x_dev, ld_x > 0 ? ld_x : (long long)P0 * 32, B_,
-                                                                            P0, act_[0]);
+  launch_cp_to_nhwc(x_dev, ld_x > 0 ? ld_x : (long long)P0 * 32, B_, P0, nullptr, act_[0], s);
   RLREP_LAUNCHED_W("nchw_to_nhwc", s, 8.0 * B_ * P0 * 32, 0.0);
   for (int l = 0; l < 4; ++l) {
     const int Hi = hw_[l], Ho = hw_[l + 1];
@@ -522,8 +501,7 @@ void ConvDecoder::backward(float* dx_dev, int ld_dx) {
                  l > 0 ? Mat{act_[l], 32} : Mat(), dact_[l], 32);
   }
   const int P0 = hw_[0] * hw_[0];
-  nhwc_to_nchw_pitch_kernel<<<grid_for((long long)B_ * P0 * 32, 256), 256, 0, s>>>(dact_[0], B_, P0, dx_dev,
-                                                                                  ld_dx > 0 ? ld_dx : (long long)P0 * 32);
+  launch_nhwc_to_cp(dact_[0], B_, P0, dx_dev, ld_dx > 0 ? ld_dx : (long long)P0 * 32, s);
   RLREP_LAUNCHED_W("nhwc_to_nchw", s, 8.0 * B_ * P0 * 32, 0.0);
 }
 
