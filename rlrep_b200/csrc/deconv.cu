@@ -77,9 +77,10 @@ template <int KS>
 __global__ void __launch_bounds__(256) out_conv_fwd_kernel(const float4* __restrict__ x, const float* __restrict__ W,
                                                            const float* __restrict__ bias, int B, int Hi, int Ho,
                                                            float4* __restrict__ pred) {
-  constexpr int T = KS * KS;
-  // w_s[(tap * 32 + c) * 3 + o] = W[o, c, tap]: a thread's 12 weights of a tap are three aligned float4 (conflict-free
-  // LDS.128; as 12 scalar loads per 12 FMAs the kernel was LDS-bound, in registers it lost two thirds of its occupancy)
+  constexpr int T = KS * KS, Q = 4, COLS = Q + KS - 1;  // Q consecutive output pixels per thread, their input columns
+  // w_s[(tap * 32 + c) * 3 + o] = W[o, c, tap]: a thread's 12 weights of a tap are three aligned float4.  The kernel is
+  // bound by these shared-memory reads (ncu: 218 M wavefronts per launch at 1024 frames), so every weight fetched is used
+  // for FOUR pixels: a thread keeps the (KS + 3) x KS window of its channel group in registers.
   __shared__ __align__(16) float w_s[T * 32 * 3];
   for (int i = threadIdx.x; i < T * 96; i += 256) {
     const int o = i % 3, c = (i / 3) % 32, tap = i / 96;
@@ -88,39 +89,58 @@ __global__ void __launch_bounds__(256) out_conv_fwd_kernel(const float4* __restr
   __syncthreads();
   const int c4 = threadIdx.x & 7;
   const float b0 = bias[0], b1 = bias[1], b2 = bias[2];
-  // 32-bit index arithmetic throughout (the launcher checks that every index fits): 64-bit div / mod by run-time values cost
-  // more instructions than the taps' FMAs.  All taps' loads are issued before the first FMA.
-  const int total = B * Ho * Ho;  // pixels; the grid-stride loop keeps whole warps together
-  const int HoHo = Ho * Ho;
+  // 32-bit index arithmetic (the constructor checks that every index fits); eight lanes (channel groups) per pixel quad
+  const int quads_x = (Ho + Q - 1) / Q, total = B * Ho * quads_x;
   for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 3; i < ((total + 3) & ~3); i += (gridDim.x * blockDim.x) >> 3) {
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    float acc[Q][3];
+#pragma unroll
+    for (int q = 0; q < Q; ++q) acc[q][0] = acc[q][1] = acc[q][2] = 0.f;
+    int b = 0, oy = 0, ox0 = 0;
     if (i < total) {
-      const int b = i / HoHo, rem = i - b * HoHo, oy = rem / Ho, ox = rem - oy * Ho;
-      float4 v[T];
+      const int row = i / quads_x;
+      ox0 = (i - row * quads_x) * Q;
+      b = row / Ho;
+      oy = row - b * Ho;
+      float4 v[KS][COLS];
 #pragma unroll
-      for (int tap = 0; tap < T; ++tap) {
-        const int iy = oy + (tap / KS) - 1, ix = ox + (tap % KS) - 1;
-        const bool ok = iy >= 0 && iy < Hi && ix >= 0 && ix < Hi;
-        v[tap] = ok ? x[((b * Hi + iy) * Hi + ix) * 8 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+      for (int ky = 0; ky < KS; ++ky) {
+        const int iy = oy + ky - 1;
+#pragma unroll
+        for (int cx = 0; cx < COLS; ++cx) {
+          const int ix = ox0 + cx - 1;
+          const bool ok = iy >= 0 && iy < Hi && ix >= 0 && ix < Hi;
+          v[ky][cx] = ok ? x[((b * Hi + iy) * Hi + ix) * 8 + c4] : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
       }
 #pragma unroll
-      for (int tap = 0; tap < T; ++tap) {
-        const float4* wq = reinterpret_cast<const float4*>(w_s + tap * 96 + c4 * 12);
-        const float4 q0 = wq[0], q1 = wq[1], q2 = wq[2];
-        const float wc[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
-        a0 = fmaf(v[tap].x, wc[0], a0); a1 = fmaf(v[tap].x, wc[1], a1); a2 = fmaf(v[tap].x, wc[2], a2);
-        a0 = fmaf(v[tap].y, wc[3], a0); a1 = fmaf(v[tap].y, wc[4], a1); a2 = fmaf(v[tap].y, wc[5], a2);
-        a0 = fmaf(v[tap].z, wc[6], a0); a1 = fmaf(v[tap].z, wc[7], a1); a2 = fmaf(v[tap].z, wc[8], a2);
-        a0 = fmaf(v[tap].w, wc[9], a0); a1 = fmaf(v[tap].w, wc[10], a1); a2 = fmaf(v[tap].w, wc[11], a2);
-      }
+      for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+        for (int kx = 0; kx < KS; ++kx) {
+          const float4* wq = reinterpret_cast<const float4*>(w_s + (ky * KS + kx) * 96 + c4 * 12);
+          const float4 q0 = wq[0], q1 = wq[1], q2 = wq[2];
+          const float wc[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+          for (int q = 0; q < Q; ++q) {
+            const float4 t = v[ky][q + kx];
+#pragma unroll
+            for (int o = 0; o < 3; ++o)
+              acc[q][o] = fmaf(t.x, wc[o], fmaf(t.y, wc[3 + o], fmaf(t.z, wc[6 + o], fmaf(t.w, wc[9 + o], acc[q][o]))));
+          }
+        }
     }
 #pragma unroll
-    for (int o = 4; o > 0; o >>= 1) {  // fixed-order reduction over the eight channel groups of the pixel
-      a0 += __shfl_xor_sync(0xffffffffu, a0, o);
-      a1 += __shfl_xor_sync(0xffffffffu, a1, o);
-      a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    for (int sh = 4; sh > 0; sh >>= 1)  // fixed-order reduction over the eight channel groups
+#pragma unroll
+      for (int q = 0; q < Q; ++q)
+#pragma unroll
+        for (int o = 0; o < 3; ++o) acc[q][o] += __shfl_xor_sync(0xffffffffu, acc[q][o], sh);
+    if (i < total && c4 < Q && ox0 + c4 < Ho) {  // lane q of the group stores pixel q
+      float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < Q; ++q)
+        if (q == c4) { r0 = acc[q][0]; r1 = acc[q][1]; r2 = acc[q][2]; }
+      pred[(b * Ho + oy) * Ho + ox0 + c4] = make_float4(r0 + b0, r1 + b1, r2 + b2, 0.f);
     }
-    if (c4 == 0 && i < total) pred[i] = make_float4(a0 + b0, a1 + b1, a2 + b2, 0.f);
   }
 }
 
@@ -192,35 +212,62 @@ template <int KS>
 __global__ void __launch_bounds__(256) out_conv_dgrad_kernel(const float4* __restrict__ dpred, const float* __restrict__ W,
                                                              const float4* __restrict__ x, int B, int Hi, int Ho,
                                                              float4* __restrict__ dx) {
-  constexpr int T = KS * KS;
-  __shared__ float w_s[T * 32 * 3];
+  constexpr int T = KS * KS, Q = 4, COLS = Q + KS - 1;
+  // like the forward kernel: weights from shared memory once per FOUR input pixels of a thread's channel group; the
+  // (KS + 3) x KS window of output gradients (one float4 = three channels each) lives in registers
+  __shared__ __align__(16) float w_s[T * 32 * 3];  // [(tap * 32 + c) * 3 + o]
   for (int i = threadIdx.x; i < T * 96; i += 256) {
     const int o = i % 3, c = (i / 3) % 32, tap = i / 96;
     w_s[i] = W[(o * 32 + c) * T + tap];
   }
   __syncthreads();
-  const int total = B * Hi * Hi * 8, HiHi = Hi * Hi;  // 32-bit index arithmetic (checked by the launcher), loads before FMAs
+  const int c4 = threadIdx.x & 7;
+  const int quads_x = (Hi + Q - 1) / Q, total = B * Hi * quads_x * 8;  // 32-bit index arithmetic (checked by the constructor)
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int c4 = i & 7, pix = i >> 3;
-    const int b = pix / HiHi, rem = pix - b * HiHi, iy = rem / Hi, ix = rem - iy * Hi;
-    float4 g[T];
+    const int quad = i >> 3;  // (i & 7) == c4: the grid-stride step is a multiple of 8
+    const int row = quad / quads_x, ix0 = (quad - row * quads_x) * Q;
+    const int b = row / Hi, iy = row - b * Hi;
+    // dX[iy, ix] = sum_{ky, kx} dpred[iy - ky + 1, ix - kx + 1] . W[:, c, ky, kx]: window columns ox = ix0 - (KS - 2) + cx
+    float4 g[KS][COLS];
 #pragma unroll
-    for (int tap = 0; tap < T; ++tap) {
-      const int oy = iy - (tap / KS) + 1, ox = ix - (tap % KS) + 1;
-      const bool ok = oy >= 0 && oy < Ho && ox >= 0 && ox < Ho;
-      g[tap] = ok ? dpred[(b * Ho + oy) * Ho + ox] : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int ky = 0; ky < KS; ++ky) {
+      const int oy = iy - ky + 1;
+#pragma unroll
+      for (int cx = 0; cx < COLS; ++cx) {
+        const int ox = ix0 - (KS - 2) + cx;
+        const bool ok = oy >= 0 && oy < Ho && ox >= 0 && ox < Ho;
+        g[ky][cx] = ok ? dpred[(b * Ho + oy) * Ho + ox] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
     }
-    const float4 xv = x[i];
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    float acc[Q][4];
 #pragma unroll
-    for (int tap = 0; tap < T; ++tap) {
-      const float* w = w_s + tap * 96 + c4 * 12;
+    for (int q = 0; q < Q; ++q) acc[q][0] = acc[q][1] = acc[q][2] = acc[q][3] = 0.f;
 #pragma unroll
-      for (int j = 0; j < 4; ++j)
-        acc[j] = fmaf(g[tap].x, w[3 * j], fmaf(g[tap].y, w[3 * j + 1], fmaf(g[tap].z, w[3 * j + 2], acc[j])));
+    for (int ky = 0; ky < KS; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < KS; ++kx) {
+        const float4* wq = reinterpret_cast<const float4*>(w_s + (ky * KS + kx) * 96 + c4 * 12);
+        const float4 q0 = wq[0], q1 = wq[1], q2 = wq[2];
+        const float w[12] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w, q2.x, q2.y, q2.z, q2.w};
+#pragma unroll
+        for (int q = 0; q < Q; ++q) {
+          // input pixel ix0 + q, tap kx reads output column ox = ix0 + q - kx + 1 = window index q - kx + 1 + (KS - 2)
+          const float4 t = g[ky][q - kx + KS - 1];
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            acc[q][j] = fmaf(t.x, w[3 * j], fmaf(t.y, w[3 * j + 1], fmaf(t.z, w[3 * j + 2], acc[q][j])));
+        }
+      }
+#pragma unroll
+    for (int q = 0; q < Q; ++q) {
+      const int ix = ix0 + q;
+      if (ix < Hi) {
+        const int o = ((b * Hi + iy) * Hi + ix) * 8 + c4;
+        const float4 xv = x[o];
+        dx[o] = make_float4(xv.x > 0.f ? acc[q][0] : 0.f, xv.y > 0.f ? acc[q][1] : 0.f, xv.z > 0.f ? acc[q][2] : 0.f,
+                            xv.w > 0.f ? acc[q][3] : 0.f);
+      }
     }
-    dx[i] = make_float4(xv.x > 0.f ? acc[0] : 0.f, xv.y > 0.f ? acc[1] : 0.f, xv.z > 0.f ? acc[2] : 0.f,
-                        xv.w > 0.f ? acc[3] : 0.f);
   }
 }
 
@@ -413,11 +460,11 @@ void ConvDecoder::forward(const float* x_dev, int ld_x) {
     RLREP_LAUNCHED_W("col2im_bias_relu", s, 4.0 * (rows(l) * 288 + rows(l + 1) * 32), 0.0);
   }
   if (ks_ == 2)
-    out_conv_fwd_kernel<2><<<grid_for(rows(5) * 8, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(act_[4]),
+    out_conv_fwd_kernel<2><<<grid_for(rows(5) * 2, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(act_[4]),
                                                                     g_.p + w_off_[4], g_.p + b_off_[4], B_, hw_[4], hw_[5],
                                                                     reinterpret_cast<float4*>(pred_));
   else
-    out_conv_fwd_kernel<3><<<grid_for(rows(5) * 8, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(act_[4]),
+    out_conv_fwd_kernel<3><<<grid_for(rows(5) * 2, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(act_[4]),
                                                                     g_.p + w_off_[4], g_.p + b_off_[4], B_, hw_[4], hw_[5],
                                                                     reinterpret_cast<float4*>(pred_));
   RLREP_LAUNCHED_W("out_conv_fwd", s, 4.0 * (rows(4) * 32 + rows(5) * 4), 2.0 * rows(5) * 384);
@@ -456,11 +503,11 @@ void ConvDecoder::backward(float* dx_dev, int ld_dx) {
   else out_conv_wgrad_finish_kernel<3><<<4, 256, 0, s>>>(wg_partial_, kWgBlocks, g_.g + w_off_[4], g_.g + b_off_[4]);
   RLREP_LAUNCHED("out_conv_wgrad_finish", s);
   if (ks_ == 2)
-    out_conv_dgrad_kernel<2><<<grid_for(rows(4) * 8, 256), 256, 0, s>>>(
+    out_conv_dgrad_kernel<2><<<grid_for(rows(4) * 2 + 2048, 256), 256, 0, s>>>(
         reinterpret_cast<const float4*>(dpred_), g_.p + w_off_[4], reinterpret_cast<const float4*>(act_[4]), B_, hw_[4],
         hw_[5], reinterpret_cast<float4*>(dact_[4]));
   else
-    out_conv_dgrad_kernel<3><<<grid_for(rows(4) * 8, 256), 256, 0, s>>>(
+    out_conv_dgrad_kernel<3><<<grid_for(rows(4) * 2 + 2048, 256), 256, 0, s>>>(
         reinterpret_cast<const float4*>(dpred_), g_.p + w_off_[4], reinterpret_cast<const float4*>(act_[4]), B_, hw_[4],
         hw_[5], reinterpret_cast<float4*>(dact_[4]));
   RLREP_LAUNCHED_W("out_conv_dgrad", s, 4.0 * (rows(5) * 4 + 2.0 * rows(4) * 32), 2.0 * rows(4) * 384);
