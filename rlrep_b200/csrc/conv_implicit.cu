@@ -81,7 +81,7 @@ __global__ void scatter_to_grid_kernel(const float4* __restrict__ in, int B, int
     grid[i] = v;
   }
 }
-// G[n, (ky, kx), c] = sum_f C[(f, n), (ky, kx + f, c)] over the four folded rows, C [128, 576] (fixed order)
+// G[n, (ky, kx), c] = sum_f C[(f, n), (ky, kx + f, c)] over the four folded rows, C [128, 768] (fixed order)
 __global__ void diag_tap_sum_kernel(const float* __restrict__ C, int groups, float* __restrict__ dW, int ld_dw,
                                     int transposed) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -90,7 +90,7 @@ __global__ void diag_tap_sum_kernel(const float* __restrict__ C, int groups, flo
   float acc = 0.f;
   for (int g = 0; g < groups; ++g)  // the GEMM's K groups, then the four folded rows: fixed order
     for (int f = 0; f < 4; ++f)
-      acc += C[(size_t)g * 128 * 576 + (size_t)(f * 32 + n) * 576 + ky * 192 + (kx + f) * 32 + c];
+      acc += C[(size_t)g * 128 * 768 + (size_t)(f * 32 + n) * 768 + ky * 256 + (kx + f) * 32 + c];
   if (transposed) dW[(size_t)r * ld_dw + n] = acc;
   else dW[(size_t)n * ld_dw + r] = acc;
 }
@@ -105,11 +105,11 @@ void conv3x3_wgrad_implicit(GemmRunner& g, cudaStream_t s, int B, int Hg, const 
                                                                reinterpret_cast<float4*>(sc.padded));
   RLREP_LAUNCHED_W("scatter_to_grid", s, 4.0 * 32 * ((double)B * (Hg - 2) * (Hg - 2) + rows), 0.0);
   GemmArgs a;
-  a.M = 128; a.N = 576; a.K = (int)(rows / 4);
+  a.M = 128; a.N = 768; a.K = (int)(rows / 4);
   a.A = sc.padded; a.lda = 128; a.a_mn = true;
   a.B = map; a.ldb = 128; a.b_mn = true;
   a.conv_wgrad_hi = Hg;
-  a.C = sc.wfold; a.ldc = 576;
+  a.C = sc.wfold; a.ldc = 768;
   // nine or eighteen tiles x a split-K cluster of 8 leave half the GPU idle and every CTA with ~10 MB to stream: cut K
   // into groups with their own output matrices (summed by diag_tap_sum)
   static const int want_groups = [] {

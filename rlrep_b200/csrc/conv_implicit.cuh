@@ -15,7 +15,7 @@ struct FullCorrScratch {
     a.want(&padded, rows * 32);
     a.want(&out_grid, rows * 32);
     a.want(&w_flip, 32 * 288);
-    a.want(&wfold, kWgradGroupsMax * 128 * 576);
+    a.want(&wfold, kWgradGroupsMax * 128 * 768);
   }
 };
 

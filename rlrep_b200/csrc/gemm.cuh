@@ -64,11 +64,11 @@ struct GemmArgs {
   int conv_w = 0;
   // Implicit weight gradient of that convolution (tensor-core path, both operands MN-major): conv_wgrad_hi = Hi > 0 makes B
   // the convolution's INPUT, a dense [rows, 32] NHWC map on a grid Hi wide, read through the view
-  //   B(k, n = ky * 192 + q * 32 + c) = X[4 k + q + ky * Hi, c],   q = 0..5, ky = 0..2   (N = 576),
+  //   B(k, n = ky * 256 + q * 32 + c) = X[4 k + q + ky * Hi, c],   q = 0..7 (6, 7: padding), ky = 0..2   (N = 768),
   // i.e. with A = the output gradient on the same grid folded four rows to one ([rows / 4, 128], zero where the window
   // leaves the image) the product C[(f, n), (ky, q, c)] holds dW[n, (ky, kx), c] = sum_f C[(f, n), (ky, kx + f, c)].
-  // No column matrix exists; K = rows / 4, and 2 Hi + 5 rows of finite values must be readable behind the map (they meet
-  // zeros of A).
+  // No column matrix exists; K = rows / 4, and 2 Hi + 7 rows of finite values must be readable behind the map (they meet
+  // zeros of A, or land in the padding columns nobody reads).
   int conv_wgrad_hi = 0;
   // Compacting store of an implicit convolution (halo kernel only, GemmRunner::run_compact): the GEMM's rows live on a grid
   // compact_wp wide; only rows with x < compact_ho and y < compact_ho are stored, at row (b * ho + y) * ho + x of C -- and

@@ -72,12 +72,13 @@ CUtensorMap make_map_mnmajor(const float* base, int K, int mn, int ld, int tile_
 }
 
 // Implicit conv weight gradient (GemmArgs::conv_wgrad_hi): the convolution's input X [rows, 32] on a grid Hi wide as the
-// 4-D tensor (c, k, q, ky) -> X[4 k + q + ky * Hi, c]; box {32, 32, tile_n / 32, 1} lands exactly like the 3-D MN-major
-// box.  The largest shift (q = 5, ky = 2) reads 2 Hi + 5 rows past the map: the caller keeps that many readable rows of
+// 4-D tensor (c, k, q, ky) -> X[4 k + q + ky * Hi, c], q = 0..7 (6 and 7 are padding: a ky row of the view is 256 columns, so
+// that 128- and 256-wide tiles never straddle two ky rows); box {32, 32, tile_n / 32, 1} lands exactly like the 3-D
+// MN-major box.  The largest shift (q = 7, ky = 2) reads 2 Hi + 7 rows past the map: the caller keeps that many readable rows of
 // finite values behind it (they meet zeros of the folded gradient).
 CUtensorMap make_map_conv_wgrad(const float* base, long long rows, int hi, int tile_n) {
   CUtensorMap m;
-  cuuint64_t gdim[4] = {32u, (cuuint64_t)(rows / 4), 6u, 3u};
+  cuuint64_t gdim[4] = {32u, (cuuint64_t)(rows / 4), 8u, 3u};
   cuuint64_t gstride[3] = {512u, 128u, (cuuint64_t)hi * 128u};
   cuuint32_t box[4] = {32u, 32u, (cuuint32_t)(tile_n / 32), 1u};
   cuuint32_t estr[4] = {1u, 1u, 1u, 1u};
@@ -180,7 +181,7 @@ bool tc_eligible(const GemmArgs& a) {
   if (a.a_mn && (a.M & 31) != 0) return false;
   if (a.b_mn && (a.N & 31) != 0) return false;
   if (a.conv_w > 0 && (a.a_mn || a.K != 9 * 32)) return false;
-  if (a.conv_wgrad_hi > 0 && (!a.a_mn || !a.b_mn || a.N != 576 || a.conv_w > 0 || a.ldb != 128)) return false;
+  if (a.conv_wgrad_hi > 0 && (!a.a_mn || !a.b_mn || a.N != 768 || a.conv_w > 0 || a.ldb != 128)) return false;
   return a.A2 == nullptr && ok(a.A, a.lda) && ok(a.B, a.ldb) && a.M > 0 && a.N > 0 && a.K > 0;
 }
 
@@ -201,7 +202,6 @@ TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* /*ws*/, s
   for (int cand_bn : {32, 64, 128, 256}) {
     if (bn != 0 && cand_bn != bn) continue;
     if (bn == 0 && cand_bn > 32 && cand_bn / 2 >= a.N) continue;  // tile mostly out of bounds
-    if (a.conv_wgrad_hi > 0 && cand_bn > 64) continue;  // a tile's q-chunks must stay inside one ky row of the view (6 chunks)
     for (int s : {1, 2, 4, 8}) {
       if (split_k != 0 && s != split_k) continue;
       int kb_per = 0, stages = 0;
@@ -262,7 +262,7 @@ TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* /*ws*/, s
   p.tmA = a.a_mn ? make_map_mnmajor(a.A, a.K, a.M, a.lda, BM)
                  : make_map_kmajor(a.A, a.M, a.conv_w > 0 ? 32 : a.K, a.lda, p.halo_rows > 0 ? p.halo_rows : BM);
   if (a.conv_wgrad_hi > 0) {
-    RLREP_CHECK(p.bn <= 64 && !p.persistent, "implicit weight gradient: tile width 32 or 64, one tile per CTA");
+    RLREP_CHECK(!p.persistent, "implicit weight gradient: one tile per CTA");
     p.tmB = make_map_conv_wgrad(a.B, 4LL * a.K, a.conv_wgrad_hi, p.bn);
   } else {
     p.tmB = a.b_mn ? make_map_mnmajor(a.B, a.K, a.N, a.ldb, p.bn) : make_map_kmajor(a.B, a.N, a.K, a.ldb, p.bn);

@@ -359,9 +359,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     } else {
       ptx::tma_load_3d(a_dst, &tmA, &full_bar[s], 0, k0, m0 / 32);
     }
-    // implicit weight gradient (conv_w < 0): n-chunk j of the (ky, q, c) view is (q, ky) = (j % 6, j / 6)
+    // implicit weight gradient (conv_w < 0): n-chunk j of the (ky, q, c) view is (q, ky) = (j % 8, j / 8)
     if (!B_MN) ptx::tma_load_2d(b_dst, &tmB, &full_bar[s], k0, n0);
-    else if (conv_w < 0) ptx::tma_load_4d(b_dst, &tmB, &full_bar[s], 0, k0, (n0 / 32) % 6, (n0 / 32) / 6);
+    else if (conv_w < 0) ptx::tma_load_4d(b_dst, &tmB, &full_bar[s], 0, k0, (n0 / 32) % 8, (n0 / 32) / 8);
     else ptx::tma_load_3d(b_dst, &tmB, &full_bar[s], 0, k0, n0 / 32);
   };
   // one stage before the setup barrier (TMA issue itself is not free) -- except under PDL, where no global read may
