@@ -7,7 +7,7 @@
 namespace rlrep {
 
 // Scratch for one full correlation at a time: the zero-padded input grid, the output grid and the repacked weights.
-constexpr int kWgradGroupsMax = 4;  // K groups of the implicit weight-gradient GEMM (GemmArgs::k_groups)
+constexpr int kWgradGroupsMax = 8;  // K groups of the implicit weight-gradient GEMM (GemmArgs::k_groups)
 struct FullCorrScratch {
   float *padded = nullptr, *out_grid = nullptr, *w_flip = nullptr, *wfold = nullptr;
   void want(DeviceArena& a, int batch, int max_hi) {
