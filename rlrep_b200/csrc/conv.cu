@@ -193,7 +193,8 @@ void ConvEncoder::backward(const float* dfeat_dev, int ld_dfeat) {
     if (l > 0 && implicit_wgrad_) {
       // no column matrix: dY goes onto the input's grid (55 MB at B = 256 instead of the 450 MB col), and the GEMM's TMA
       // producer reads the input map through the shifted (ky, q, c) view (gemm.cuh conv_wgrad_hi)
-      conv3x3_wgrad_implicit(gemm_, s, B_, hw_[l - 1], dact_[l], act_[l - 1], w.dW, w.ld, /*transposed=*/false, corr_);
+      conv3x3_wgrad_implicit(gemm_, s, B_, hw_[l - 1], dact_[l], act_[l - 1], w.dW, w.ld, /*transposed=*/false, corr_,
+                             /*small_colsum=*/w.db);  // the bias gradient rides in the scatter pass
     } else if (rows(l) % kFold == 0) {
       GemmArgs a;
       a.M = 32 * kFold; a.N = col.ld * kFold; a.K = (int)(rows(l) / kFold);
@@ -206,7 +207,7 @@ void ConvEncoder::backward(const float* dfeat_dev, int ld_dfeat) {
     } else {
       linear_wgrad(gemm_, s, (int)rows(l), dy, col, w, Mat(), 0, /*bias_grad=*/false);
     }
-    launch_colsum_tall(dy.p, 32, rows(l), 32, bias_partial_, kBiasChunks, w.db, s);
+    if (!(l > 0 && implicit_wgrad_)) launch_colsum_tall(dy.p, 32, rows(l), 32, bias_partial_, kBiasChunks, w.db, s);
     if (l == 0) break;
     if (implicit_dgrad_) {
       // dX = full correlation of dY with W (x ReLU mask), the taps walked by the GEMM's TMA producer (conv_implicit.cu)

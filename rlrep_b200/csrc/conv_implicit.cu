@@ -9,6 +9,7 @@
 // output on the same grid, then one compaction pass that also applies the ReLU mask.  Taps are visited in flipped
 // order (t -> 8 - t) so all shifts are non-negative; the weights are repacked to match ([32, 9 * 32], 37 KB).
 #include "conv_implicit.cuh"
+#include "kernels.cuh"
 
 #include <algorithm>
 
@@ -69,9 +70,13 @@ __global__ void compact_grid_kernel(const float4* __restrict__ grid, int B, int 
   }
 }
 
-// in [B, Hs, Hs, 32] onto a grid Hg wide (zero outside)
-__global__ void scatter_to_grid_kernel(const float4* __restrict__ in, int B, int Hs, int Hg, float4* __restrict__ grid) {
+// in [B, Hs, Hs, 32] onto a grid Hg wide (zero outside); colsum_partial != nullptr: per-CTA column sums of `in` as well
+// ([gridDim.x][32], fixed order inside the CTA) -- every element of `in` is read exactly once by this pass
+__global__ void __launch_bounds__(256) scatter_to_grid_kernel(const float4* __restrict__ in, int B, int Hs, int Hg,
+                                                              float4* __restrict__ grid, float* __restrict__ colsum_partial) {
+  __shared__ float4 part[32][8];
   const long long total = (long long)B * Hg * Hg * 8;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c4 = (int)(i & 7);
     const int pix = (int)(i >> 3);
@@ -79,6 +84,18 @@ __global__ void scatter_to_grid_kernel(const float4* __restrict__ in, int B, int
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (x < Hs && y < Hs) v = in[(((long long)b * Hs + y) * Hs + x) * 8 + c4];
     grid[i] = v;
+    acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+  }
+  if (colsum_partial == nullptr) return;
+  part[threadIdx.x >> 3][threadIdx.x & 7] = acc;  // the grid-stride step is a multiple of 8: a thread keeps its columns
+  __syncthreads();
+  if (threadIdx.x < 8) {
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int q = 0; q < 32; ++q) {
+      const float4 a = part[q][threadIdx.x];
+      t.x += a.x; t.y += a.y; t.z += a.z; t.w += a.w;
+    }
+    reinterpret_cast<float4*>(colsum_partial + (size_t)blockIdx.x * 32)[threadIdx.x] = t;
   }
 }
 // G[n, (ky, kx), c] = sum_f C[(f, n), (ky, kx + f, c)] over the four folded rows, C [128, 768] (fixed order)
@@ -98,12 +115,16 @@ __global__ void diag_tap_sum_kernel(const float* __restrict__ C, int groups, flo
 }  // namespace
 
 void conv3x3_wgrad_implicit(GemmRunner& g, cudaStream_t s, int B, int Hg, const float* small, const float* map, float* dW,
-                            int ld_dw, bool transposed, FullCorrScratch& sc) {
+                            int ld_dw, bool transposed, FullCorrScratch& sc, float* small_colsum) {
   const long long rows = (long long)B * Hg * Hg;
   RLREP_CHECK(rows % 4 == 0 && rows * 8 < (1LL << 31), "implicit weight gradient: batch must be a multiple of 4 (and < 2^28 pixels)");
-  scatter_to_grid_kernel<<<grid_for(rows * 8, 256), 256, 0, s>>>(reinterpret_cast<const float4*>(small), B, Hg - 2, Hg,
-                                                               reinterpret_cast<float4*>(sc.padded));
+  const int blocks = grid_for(rows * 8, 256);
+  RLREP_CHECK(blocks <= kScatterMaxBlocks, "scatter grid larger than its partial buffer");
+  scatter_to_grid_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(small), B, Hg - 2, Hg,
+                                              reinterpret_cast<float4*>(sc.padded),
+                                              small_colsum != nullptr ? sc.colsum_partial : nullptr);
   RLREP_LAUNCHED_W("scatter_to_grid", s, 4.0 * 32 * ((double)B * (Hg - 2) * (Hg - 2) + rows), 0.0);
+  if (small_colsum != nullptr) launch_colsum_finish(sc.colsum_partial, blocks, 32, small_colsum, s);
   GemmArgs a;
   a.M = 128; a.N = 768; a.K = (int)(rows / 4);
   a.A = sc.padded; a.lda = 128; a.a_mn = true;

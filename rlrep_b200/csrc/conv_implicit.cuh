@@ -7,15 +7,17 @@
 namespace rlrep {
 
 // Scratch for one full correlation at a time: the zero-padded input grid, the output grid and the repacked weights.
-constexpr int kWgradGroupsMax = 8;  // K groups of the implicit weight-gradient GEMM (GemmArgs::k_groups)
+constexpr int kWgradGroupsMax = 8;
+constexpr int kScatterMaxBlocks = kNumSMs * 16;  // grid cap of the scatter pass (its per-CTA column partials)  // K groups of the implicit weight-gradient GEMM (GemmArgs::k_groups)
 struct FullCorrScratch {
-  float *padded = nullptr, *out_grid = nullptr, *w_flip = nullptr, *wfold = nullptr;
+  float *padded = nullptr, *out_grid = nullptr, *w_flip = nullptr, *wfold = nullptr, *colsum_partial = nullptr;
   void want(DeviceArena& a, int batch, int max_hi) {
     const size_t rows = (size_t)batch * (max_hi + 4) * (max_hi + 4);
     a.want(&padded, rows * 32);
     a.want(&out_grid, rows * 32);
     a.want(&w_flip, 32 * 288);
     a.want(&wfold, kWgradGroupsMax * 128 * 768);
+    a.want(&colsum_partial, (size_t)kScatterMaxBlocks * 32);
   }
 };
 
@@ -36,8 +38,10 @@ void full_correlation_3x3(GemmRunner& g, cudaStream_t s, int B, int Hi, const fl
 // rows of finite values.  `small` is copied onto the map's grid (zero outside) and folded four rows to one; the GEMM's TMA
 // producer reads `map` through the shifted view of GemmArgs::conv_wgrad_hi.  Tensor-core path only; B % 4 == 0.
 // transposed = false writes dW[n * ld + (ky * 3 + kx) * 32 + c], true writes dW[((ky * 3 + kx) * 32 + c) * ld + n].
+// small_colsum != nullptr: also small_colsum[n] = sum over pixels of small[., n] -- the convolution's bias gradient, a
+// by-product of the pass that copies `small` onto the grid (saves a separate read of the gradient map).
 void conv3x3_wgrad_implicit(GemmRunner& g, cudaStream_t s, int B, int Hg, const float* small, const float* map, float* dW,
-                            int ld_dw, bool transposed, FullCorrScratch& scratch);
+                            int ld_dw, bool transposed, FullCorrScratch& scratch, float* small_colsum = nullptr);
 
 // Forward pass of a STRIDE-2 3x3 transposed convolution (+ bias + ReLU) without the [rows, 288] column matrix:
 //   out[b, oy, ox, co] = relu(bias[co] + sum over (ky, kx) with oy - ky = 2 iy, ox - kx = 2 ix of in[b, iy, ix, :] . W[(ky, kx, co), :])

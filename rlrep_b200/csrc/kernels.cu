@@ -1084,6 +1084,11 @@ void launch_colsum_tall(const float* X, int ld, long long rows, int cols, float*
   RLREP_LAUNCHED("colsum_tall_final", s);
 }
 
+void launch_colsum_finish(const float* partial, int chunks, int cols, float* out, cudaStream_t s) {
+  colsum_tall_stage2_kernel<<<ceil_div(cols, 32), 256, 0, s>>>(partial, chunks, cols, out);
+  RLREP_LAUNCHED("colsum_tall_final", s);
+}
+
 void launch_colreduce_multi(const ColJob* jobs, int n_jobs, cudaStream_t s) {
   RLREP_CHECK(n_jobs >= 1 && n_jobs <= kMaxColJobs, "too many column-reduction jobs for one launch");
   ColJobs js;

@@ -65,6 +65,9 @@ void launch_rowdot_pair(const RowDotJob& a, const RowDotJob& b, int rows, cudaSt
 void launch_colreduce(const float* X, int ld, int rows, int cols, const float* u, float* out, int accumulate,
                       cudaStream_t s);
 // out[j] = sum_i X[i, j] for very tall X (rows ~ 1e5..1e6): `chunks` CTAs per 32 columns, partial is [chunks, cols].
+// Second stage alone: out[j] = sum_c partial[c * cols + j] in a fixed order (for kernels that produce per-CTA column
+// partials as a by-product of another pass).
+void launch_colsum_finish(const float* partial, int chunks, int cols, float* out, cudaStream_t s);
 void launch_colsum_tall(const float* X, int ld, long long rows, int cols, float* partial, int chunks, float* out,
                         cudaStream_t s);
 // Several column reductions in one launch (all the bias gradients of a network's backward pass).
