@@ -202,21 +202,31 @@ __global__ void __launch_bounds__(256) colsum_tall32_stage1_kernel(const float4*
     reinterpret_cast<float4*>(partial + (long long)blockIdx.y * 32)[threadIdx.x] = t;
   }
 }
-// 32 columns x 8 chunk-slices per CTA: eight independent partial sums per column, combined in a fixed order
-__global__ void __launch_bounds__(256) colsum_tall_stage2_kernel(const float* __restrict__ partial, int chunks, int cols,
-                                                                 float* __restrict__ out) {
-  __shared__ float part[8][33];
+// 32 columns x 32 chunk-slices per 1024-thread CTA: every slice adds its chunks with four independent accumulators (the loads
+// of a slice are all in flight together; with 8 slices and one accumulator 2,368 partials took 10 us), then a fixed-order
+// combination of the 32 slices.
+__global__ void __launch_bounds__(1024) colsum_tall_stage2_kernel(const float* __restrict__ partial, int chunks, int cols,
+                                                                  float* __restrict__ out) {
+  __shared__ float part[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   const int j = blockIdx.x * 32 + tx;
-  float t = 0.f;
-  if (j < cols)
-    for (int c = ty; c < chunks; c += 8) t += partial[(long long)c * cols + j];
-  part[ty][tx] = t;
+  float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+  if (j < cols) {
+    int c = ty;
+    for (; c + 96 < chunks; c += 128) {
+      t0 += partial[(long long)c * cols + j];
+      t1 += partial[(long long)(c + 32) * cols + j];
+      t2 += partial[(long long)(c + 64) * cols + j];
+      t3 += partial[(long long)(c + 96) * cols + j];
+    }
+    for (; c < chunks; c += 32) t0 += partial[(long long)c * cols + j];
+  }
+  part[ty][tx] = (t0 + t1) + (t2 + t3);
   __syncthreads();
   if (ty == 0 && j < cols) {
     float v = 0.f;
 #pragma unroll
-    for (int q = 0; q < 8; ++q) v += part[q][tx];
+    for (int q = 0; q < 32; ++q) v += part[q][tx];
     out[j] = v;
   }
 }
@@ -1080,12 +1090,12 @@ void launch_colsum_tall(const float* X, int ld, long long rows, int cols, float*
   else
     colsum_tall_stage1_kernel<<<dim3(ceil_div(cols, 32), chunks), 256, 0, s>>>(X, ld, rows, cols, rows_per, partial);
   RLREP_LAUNCHED_W("colsum_tall", s, 4.0 * (double)rows * cols, 0.0);
-  colsum_tall_stage2_kernel<<<ceil_div(cols, 32), 256, 0, s>>>(partial, chunks, cols, out);
+  colsum_tall_stage2_kernel<<<ceil_div(cols, 32), 1024, 0, s>>>(partial, chunks, cols, out);
   RLREP_LAUNCHED("colsum_tall_final", s);
 }
 
 void launch_colsum_finish(const float* partial, int chunks, int cols, float* out, cudaStream_t s) {
-  colsum_tall_stage2_kernel<<<ceil_div(cols, 32), 256, 0, s>>>(partial, chunks, cols, out);
+  colsum_tall_stage2_kernel<<<ceil_div(cols, 32), 1024, 0, s>>>(partial, chunks, cols, out);
   RLREP_LAUNCHED("colsum_tall_final", s);
 }
 
