@@ -118,7 +118,8 @@ void conv3x3_wgrad_implicit(GemmRunner& g, cudaStream_t s, int B, int Hg, const 
                             int ld_dw, bool transposed, FullCorrScratch& sc, float* small_colsum) {
   const long long rows = (long long)B * Hg * Hg;
   RLREP_CHECK(rows % 4 == 0 && rows * 8 < (1LL << 31), "implicit weight gradient: batch must be a multiple of 4 (and < 2^28 pixels)");
-  const int blocks = grid_for(rows * 8, 256);
+  // with column partials: 4 CTAs per SM -- the second stage is one CTA walking [blocks][32] partials (8 us for 2,368)
+  const int blocks = small_colsum != nullptr ? std::min(grid_for(rows * 8, 256), kNumSMs * 4) : grid_for(rows * 8, 256);
   RLREP_CHECK(blocks <= kScatterMaxBlocks, "scatter grid larger than its partial buffer");
   scatter_to_grid_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<const float4*>(small), B, Hg - 2, Hg,
                                               reinterpret_cast<float4*>(sc.padded),
