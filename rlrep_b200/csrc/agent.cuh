@@ -258,6 +258,11 @@ class GemmRunner {
   double sm_share_ = 1.0;
   float* ws_ = nullptr;
   size_t ws_floats_ = 0;
+  // K-group partial outputs of GEMMs with a huge K and a handful of tiles (run(): "deep and skinny"); grown on first use of a
+  // shape -- the first call of every update path runs eagerly, so never inside a graph capture
+  float* kg_ws_ = nullptr;
+  size_t kg_ws_floats_ = 0;
+  bool kg_on_ = true;  // RLREP_GEMM_KGROUPS=0 disables
   std::unordered_map<std::string, TcGemmPlan> plans_;
 };
 

@@ -1025,6 +1025,18 @@ __global__ void group_mean_bwd_kernel(const float* __restrict__ dmean, const flo
   }
 }
 
+__global__ void kgroup_finish_kernel(const float* __restrict__ ws, int groups, int M, int N, int ldw, size_t group_stride,
+                                     float* __restrict__ C, int ldc, const Epilogue epi) {
+  const size_t total = (size_t)M * N;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(i / N), n = (int)(i - (size_t)m * N);
+    float acc = 0.f;
+    for (int g = 0; g < groups; ++g) acc += ws[(size_t)g * group_stride + (size_t)m * ldw + n];
+    float* cp = C + (size_t)m * ldc + n;
+    *cp = epilogue_apply<-1, -1>(epi, acc, m, n, cp);
+  }
+}
+
 int grid_for(size_t work_items, int threads, int per_sm = 8) {
   size_t blocks = (work_items + threads - 1) / threads;
   const size_t cap = (size_t)kNumSMs * per_sm;
@@ -1092,6 +1104,13 @@ void launch_colsum_tall(const float* X, int ld, long long rows, int cols, float*
   RLREP_LAUNCHED_W("colsum_tall", s, 4.0 * (double)rows * cols, 0.0);
   colsum_tall_stage2_kernel<<<ceil_div(cols, 32), 1024, 0, s>>>(partial, chunks, cols, out);
   RLREP_LAUNCHED("colsum_tall_final", s);
+}
+
+void launch_kgroup_finish(const float* ws, int groups, int M, int N, int ldw, size_t group_stride, float* C, int ldc,
+                          const Epilogue& epi, cudaStream_t s) {
+  const size_t total = (size_t)M * N;
+  kgroup_finish_kernel<<<grid_for(total, 256, 16), 256, 0, s>>>(ws, groups, M, N, ldw, group_stride, C, ldc, epi);
+  RLREP_LAUNCHED_W("kgroup_finish", s, 4.0 * (double)total * (groups + 1), 0.0);
 }
 
 void launch_colsum_finish(const float* partial, int chunks, int cols, float* out, cudaStream_t s) {

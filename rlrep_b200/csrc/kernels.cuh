@@ -7,6 +7,8 @@
 
 #include <cstdint>
 
+#include "epilogue.cuh"
+
 namespace rlrep {
 
 constexpr int kMaxFeatureSteps = 16;
@@ -65,6 +67,10 @@ void launch_rowdot_pair(const RowDotJob& a, const RowDotJob& b, int rows, cudaSt
 void launch_colreduce(const float* X, int ld, int rows, int cols, const float* u, float* out, int accumulate,
                       cudaStream_t s);
 // out[j] = sum_i X[i, j] for very tall X (rows ~ 1e5..1e6): `chunks` CTAs per 32 columns, partial is [chunks, cols].
+// C[m, n] = epilogue(sum_g ws[g * group_stride + m * ldw + n]): the finish of a K-grouped GEMM (GemmArgs::k_groups), groups
+// added in order.
+void launch_kgroup_finish(const float* ws, int groups, int M, int N, int ldw, size_t group_stride, float* C, int ldc,
+                          const Epilogue& epi, cudaStream_t s);
 // Second stage alone: out[j] = sum_c partial[c * cols + j] in a fixed order (for kernels that produce per-CTA column
 // partials as a by-product of another pass).
 void launch_colsum_finish(const float* partial, int chunks, int cols, float* out, cudaStream_t s);

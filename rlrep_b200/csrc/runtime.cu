@@ -159,11 +159,13 @@ void GemmRunner::init(Precision prec, size_t ws_floats) {
   prec_ = prec;
   if (const char* e = std::getenv("RLREP_CHAIN")) chains_on_ = std::atoi(e) != 0;
   if (const char* e = std::getenv("RLREP_CHAIN_ROWOPS")) row_ops_on_ = std::atoi(e) != 0;
+  if (const char* e = std::getenv("RLREP_GEMM_KGROUPS")) kg_on_ = std::atoi(e) != 0;
   ws_floats_ = ws_floats;
   if (ws_floats_) RLREP_CUDA(cudaMalloc(&ws_, ws_floats_ * sizeof(float)));
 }
 GemmRunner::~GemmRunner() {
   if (ws_) cudaFree(ws_);
+  if (kg_ws_) cudaFree(kg_ws_);
 }
 
 void GemmRunner::begin_chain(cudaStream_t s) {
@@ -244,6 +246,34 @@ void GemmRunner::run(const GemmArgs& a, cudaStream_t s) {
   if (!tc) {
     launch_simt(a, s);
     return;
+  }
+  // Deep and skinny (the pixel agents' 39,200-wide linears at batch 256: K = 39,200 and 2 x 1..4 tiles): a split-K cluster
+  // holds 8 CTAs, so such a GEMM runs on 16-64 CTAs that stream ~5 MB each.  Cut K into groups (GemmArgs::k_groups: own
+  // cluster and raw partial output each), then one elementwise pass adds the groups and applies the epilogue.
+  if (kg_on_ && a.k_groups == 1 && a.conv_w == 0 && a.conv_wgrad_hi == 0 && !recording_) {
+    const int tiles = ceil_div(a.M, 128) * ceil_div(a.N, 128), nkb = ceil_div(a.K, 32);
+    int groups = 1;
+    while (groups < 8 && tiles * 8 * groups * 2 <= 148 && nkb >= 256 * groups * 2) groups *= 2;
+    if (groups > 1 && nkb >= 1024) {
+      const int ldw = (a.N + 3) & ~3, m_pad = ceil_div(a.M, 128) * 128;
+      const size_t need = (size_t)groups * m_pad * ldw;
+      if (need > kg_ws_floats_) {
+        cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+        RLREP_CUDA(cudaStreamIsCapturing(s, &cap));
+        RLREP_CHECK(cap == cudaStreamCaptureStatusNone, "K-group workspace must be sized before a graph capture");
+        if (kg_ws_) RLREP_CUDA(cudaFree(kg_ws_));
+        RLREP_CUDA(cudaMalloc(&kg_ws_, need * sizeof(float)));
+        kg_ws_floats_ = need;
+        plans_.clear();  // plans hold the old workspace address as their C
+      }
+      GemmArgs g = a;
+      g.C = kg_ws_; g.ldc = ldw;
+      g.epi = Epilogue();
+      g.k_groups = groups;
+      run(g, s);
+      launch_kgroup_finish(kg_ws_, groups, a.M, a.N, ldw, (size_t)m_pad * ldw, a.C, a.ldc, a.epi, s);
+      return;
+    }
   }
   std::string key(sizeof(GemmArgs), '\0');
   {
