@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdio>
 #include <cstdlib>
 #include <mutex>
 #include <unordered_map>
@@ -261,6 +262,16 @@ TcGemmPlan make_tc_plan(const GemmArgs& a, int bn, int split_k, float* /*ws*/, s
   // (a compacting GEMM whose plan has no halo is refused by GemmRunner::run_compact before anything is launched)
   p.tmA = a.a_mn ? make_map_mnmajor(a.A, a.K, a.M, a.lda, BM)
                  : make_map_kmajor(a.A, a.M, a.conv_w > 0 ? 32 : a.K, a.lda, p.halo_rows > 0 ? p.halo_rows : BM);
+  {
+    static const bool verbose = [] {
+      const char* e = std::getenv("RLREP_TC_VERBOSE");
+      return e != nullptr && std::atoi(e) != 0;
+    }();
+    if (verbose)
+      std::fprintf(stderr, "rlrep tc plan: M=%d N=%d K=%d a_mn=%d b_mn=%d conv_w=%d wgrad=%d -> bn=%d split=%d groups=%d stages=%d%s%s%s\n",
+                   a.M, a.N, a.K, (int)a.a_mn, (int)a.b_mn, a.conv_w, a.conv_wgrad_hi, p.bn, p.split_k, p.k_groups, p.stages,
+                   p.push ? " push" : "", p.persistent ? " persistent" : "", p.halo_rows > 0 ? " halo" : "");
+  }
   if (a.conv_wgrad_hi > 0) {
     RLREP_CHECK(!p.persistent, "implicit weight gradient: one tile per CTA");
     p.tmB = make_map_conv_wgrad(a.B, 4LL * a.K, a.conv_wgrad_hi, p.bn);

@@ -253,7 +253,11 @@ void GemmRunner::run(const GemmArgs& a, cudaStream_t s) {
   if (kg_on_ && a.k_groups == 1 && a.conv_w == 0 && a.conv_wgrad_hi == 0 && !recording_) {
     const int tiles = ceil_div(a.M, 128) * ceil_div(a.N, 128), nkb = ceil_div(a.K, 32);
     int groups = 1;
-    while (groups < 8 && tiles * 8 * groups * 2 <= 148 && nkb >= 256 * groups * 2) groups *= 2;
+    static const int cta_cap = [] {
+      const char* e = std::getenv("RLREP_GEMM_KGROUP_CTAS");
+      return e ? std::atoi(e) : 296;  // up to two waves of CTAs (measured on the muLV update: 148 -> 5.82 ms, 296 -> 5.77 ms)
+    }();
+    while (groups < 8 && tiles * 8 * groups * 2 <= cta_cap && nkb >= 256 * groups * 2) groups *= 2;
     if (groups > 1 && nkb >= 1024) {
       const int ldw = (a.N + 3) & ~3, m_pad = ceil_div(a.M, 128) * 128;
       const size_t need = (size_t)groups * m_pad * ldw;
