@@ -23,6 +23,7 @@ namespace rlrep {
 namespace {
 
 constexpr int kPad = 4;  // RandomShiftsAug(pad=4)
+constexpr int kMaxK1 = 512;  // padded first-layer column count the im2col kernel's tap table holds (C <= 56 channels)
 
 __global__ void im2col_u8_aug_kernel(const unsigned char* __restrict__ obs, const int* __restrict__ shifts, int B, int C,
                                      int H, int Ho, float4* __restrict__ col, int ldk) {
@@ -32,9 +33,14 @@ __global__ void im2col_u8_aug_kernel(const unsigned char* __restrict__ obs, cons
   // index arithmetic is 32-bit (checked by the constructor): the IEEE divisions and 64-bit div / mod by run-time values
   // were most of this kernel's instructions (100 us for a 165 MB write).
   __shared__ float lut[256];
+  __shared__ __align__(16) int tap_off[kMaxK1];  // per column k: (c * H * H) << 4 | ky << 2 | kx, or -1 for the padding columns
   for (int p = threadIdx.x; p < 256; p += blockDim.x) lut[p] = __fsub_rn(__fdiv_rn((float)p, 255.0f), 0.5f);
+  for (int k = threadIdx.x; k < ldk; k += blockDim.x) {
+    const int c = k / 9, r9 = k - 9 * c, ky = r9 / 3, kx = r9 - 3 * ky;
+    tap_off[k] = k < C * 9 ? ((c * H * H) << 4) | (ky << 2) | kx : -1;
+  }
   __syncthreads();
-  const int K = C * 9, q4 = ldk >> 2, HoHo = Ho * Ho;
+  const int q4 = ldk >> 2, HoHo = Ho * Ho;
   const int total = B * HoHo * q4;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int row = i / q4, q = i - row * q4;
@@ -47,13 +53,15 @@ __global__ void im2col_u8_aug_kernel(const unsigned char* __restrict__ obs, cons
     const unsigned char* img = obs + (size_t)b * C * H * H;
     float v[4];
 #pragma unroll
+    const int4 t4 = *reinterpret_cast<const int4*>(tap_off + 4 * q);  // the column decomposition comes from the table
+    const int tt[4] = {t4.x, t4.y, t4.z, t4.w};
+    const int by = 2 * oy + sy, bx = 2 * ox + sx;
+#pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int k = 4 * q + e;
       v[e] = 0.f;
-      if (k < K) {
-        const int c = k / 9, r9 = k - 9 * c, ky = r9 / 3, kx = r9 - 3 * ky;
-        const int iy = min(max(2 * oy + ky + sy, 0), H - 1), ix = min(max(2 * ox + kx + sx, 0), H - 1);
-        v[e] = lut[img[(c * H + iy) * H + ix]];
+      if (tt[e] >= 0) {
+        const int iy = min(max(by + ((tt[e] >> 2) & 3), 0), H - 1), ix = min(max(bx + (tt[e] & 3), 0), H - 1);
+        v[e] = lut[img[(tt[e] >> 4) + iy * H + ix]];
       }
     }
     col[i] = make_float4(v[0], v[1], v[2], v[3]);
@@ -122,6 +130,7 @@ ConvEncoder::ConvEncoder(int batch, int in_channels, int height, Precision prec,
     : B_(batch), C_(in_channels), H_(height), stream_(s) {
   RLREP_CHECK(B_ > 0 && C_ > 0 && H_ >= 16, "bad encoder dimensions");
   RLREP_CHECK((long long)B_ * H_ * H_ * (C_ * 9 + 32) / 4 < (1LL << 31), "encoder batch too large for 32-bit column indexing");
+  RLREP_CHECK(round_up32(C_ * 9) <= kMaxK1 && (long long)C_ * H_ * H_ < (1 << 27), "too many input channels for the im2col tap table");
   hw_[0] = (H_ - 3) / 2 + 1;  // 84 -> 41
   for (int l = 1; l < 4; ++l) hw_[l] = hw_[l - 1] - 2;  // 39, 37, 35
   K1_ = C_ * 9;
